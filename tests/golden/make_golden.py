@@ -1,0 +1,242 @@
+"""Generate the golden vectors in this directory by running the UNMODIFIED reference in-process.
+
+Runs only where /root/reference exists (the build container):
+    python tests/golden/make_golden.py
+Inputs are seeded numpy data from the package's own recipes (``synth``, ``weights``), so the tests can
+regenerate them anywhere; only the reference's OUTPUTS are stored (small .npz files).
+
+Files written:
+  tracker_seq_f32.npz / tracker_seq_f64.npz   EnhancedMultiTargetTracker over a 260-frame multi-target
+                                              sequence (float32 resp. python-float detections)
+  tracker_kat.npz                             the 3-frame known-answer case of SURVEY.md 8c
+  kf_ultra.npz                                KalmanFilterXYAH / XYWH initiate/predict/update/gating
+  nms_cases.npz                               non_max_suppression, both branches (TorchNMS.nms / torchvision)
+  net_n_p2_small.npz                          yolov8n-p2 head maps + decoded tensor on a 64x96 input
+  predict_n_p2.npz                            YOLO('yolov8n-p2.yaml').predict on 512x640 and 500x640 frames
+"""
+import contextlib
+import importlib.util
+import io
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp/ycfg")
+os.environ.setdefault("OMP_NUM_THREADS", "8")
+
+import numpy as np
+import torch
+
+import b200dt  # noqa: F401
+from b200dt import cfg, synth, weights
+
+sys.path.insert(0, os.path.dirname(HERE))
+from golden_common import pack_tracks, synth_pred  # noqa: E402
+
+def run_tracker(dets_per_frame, as_python_floats, params):
+    from kalman.enhanced_multi_target_tracker import EnhancedMultiTargetTracker
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        trk = EnhancedMultiTargetTracker(*params)
+        outs, states = [], []
+        for d in dets_per_frame:
+            dd = [[float(v) for v in row] for row in d] if as_python_floats else [row for row in d]
+            res = trk.update(dd)
+            # deep-copy what get_track_info returned (velocity is a view of x)
+            outs.append([{**t, "bbox": np.array(t["bbox"]), "velocity": np.array(t["velocity"])} for t in res])
+            states.append([(int(t.track_id[1:]), t.x.copy(), t.P.copy(), t.lost_frames, t.is_lost) for t in trk.trackers])
+    return trk, outs, states
+
+
+def gold_tracker():
+    params = (150, 1, 0.1)
+    seq = synth.DetectionSequence(seed=3, n_targets=8)
+    dets = [seq.step() for _ in range(260)]
+    for tag, pyf in (("f32", False), ("f64", True)):
+        trk, outs, states = run_tracker(dets, pyf, params)
+        rows, cols, tl, tr = pack_tracks(outs)
+        st_rows = []
+        for f, st in enumerate(states):
+            for tid, x, P, lf, il in st:
+                st_rows.append(np.r_[f, tid, x, P.reshape(-1), lf, float(il)])
+        stats = trk.get_statistics()
+        np.savez_compressed(os.path.join(HERE, f"tracker_seq_{tag}.npz"), rows=rows, cols=np.array(cols), traj_len=tl,
+                            traj=tr.astype(np.float32), states=np.asarray(st_rows),
+                            stats=np.array([stats[k] for k in ("total_tracks_created", "total_tracks_terminated",
+                                                               "current_active_tracks", "long_term_predictions",
+                                                               "successful_recoveries", "frame_count")]),
+                            params=np.array(params), seed=3, n_frames=260)
+        print("tracker", tag, rows.shape, "tracks created", stats["total_tracks_created"], "terminated", stats["total_tracks_terminated"],
+              "recoveries", stats["successful_recoveries"], "ltp", stats["long_term_predictions"])
+    # second parameterisation: (40, 3, 0.3): min_hits gating, deletions after 40 lost frames
+    seq = synth.DetectionSequence(seed=11, n_targets=12, p_detect=0.7, clutter=0.5, burst=(50, 110))
+    dets = [seq.step() for _ in range(200)]
+    trk, outs, states = run_tracker(dets, False, (40, 3, 0.3))
+    rows, cols, tl, tr = pack_tracks(outs)
+    np.savez_compressed(os.path.join(HERE, "tracker_seq_default.npz"), rows=rows, cols=np.array(cols), traj_len=tl,
+                        traj=tr.astype(np.float32), params=np.array((40, 3, 0.3)), seed=11, n_frames=200,
+                        stats=np.array([trk.stats[k] for k in ("total_tracks_created", "total_tracks_terminated",
+                                                               "current_active_tracks", "long_term_predictions",
+                                                               "successful_recoveries")] + [trk.frame_count]))
+    print("tracker default", rows.shape, trk.stats)
+    # known-answer
+    kat = [[[10, 10, 20, 20, .9], [100, 100, 110, 112, .5]], [[11, 11, 21, 21, .9]], [[12, 12, 22, 22, .9]]]
+    trk, outs, states = run_tracker(kat, True, (150, 1, 0.1))
+    rows, cols, tl, tr = pack_tracks(outs)
+    st = states[-1]
+    np.savez_compressed(os.path.join(HERE, "tracker_kat.npz"), rows=rows, cols=np.array(cols),
+                        x_T001=st[0][1], P_T001=st[0][2], x_T002=st[1][1], P_T002=st[1][2])
+    print("kat T001 x", st[0][1])
+
+
+def gold_kf():
+    spec = importlib.util.spec_from_file_location("ref_kf", os.path.join(REF, "ultralytics/trackers/utils/kalman_filter.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.random.default_rng(5)
+    out = {}
+    for kind, cls in (("xyah", mod.KalmanFilterXYAH), ("xywh", mod.KalmanFilterXYWH)):
+        kf = cls()
+        N, T = 16, 12
+        if kind == "xyah":
+            z0 = np.stack([g.uniform(50, 600, N), g.uniform(50, 400, N), g.uniform(0.3, 2.0, N), g.uniform(10, 120, N)], 1)
+        else:
+            z0 = np.stack([g.uniform(50, 600, N), g.uniform(50, 400, N), g.uniform(8, 90, N), g.uniform(10, 120, N)], 1)
+        meas = z0[None] + np.cumsum(g.normal(0, 1.0, (T, N, 4)) * np.array([2, 2, 0.01 if kind == "xyah" else 1, 1]), 0)
+        hit = g.random((T, N)) < 0.75
+        means, covs = zip(*[kf.initiate(z) for z in z0])
+        means, covs = np.array(means), np.array(covs)
+        out[f"{kind}_z0"], out[f"{kind}_meas"], out[f"{kind}_hit"] = z0, meas, hit
+        out[f"{kind}_init_mean"], out[f"{kind}_init_cov"] = means.copy(), covs.copy()
+        mh, ch, gh = [], [], []
+        for t in range(T):
+            pm, pc = kf.multi_predict(means, covs)
+            # per-track predict must agree with multi_predict (reference property)
+            for i in range(N):
+                a, b = kf.predict(means[i], covs[i])
+                assert np.allclose(a, pm[i]) and np.allclose(b, pc[i])
+            means, covs = pm.copy(), pc.copy()
+            gd = np.stack([kf.gating_distance(means[i], covs[i], meas[t]) for i in range(N)])
+            gd_pos = np.stack([kf.gating_distance(means[i], covs[i], meas[t], only_position=True) for i in range(N)])
+            for i in range(N):
+                if hit[t, i]:
+                    means[i], covs[i] = kf.update(means[i], covs[i], meas[t, i])
+            mh.append(means.copy()); ch.append(covs.copy()); gh.append(np.stack([gd, gd_pos]))
+        out[f"{kind}_means"], out[f"{kind}_covs"], out[f"{kind}_gating"] = np.array(mh), np.array(ch), np.array(gh)
+    # survey known answers
+    kf = mod.KalmanFilterXYWH()
+    m, c = kf.initiate(np.array([100., 50, 20, 40])); m, c = kf.predict(m, c); m2, c2 = kf.update(m, c, np.array([102., 51, 21, 41]))
+    out["kat_xywh_mean"], out["kat_xywh_diag"] = m2, np.diag(c2)
+    out["kat_xywh_gate"] = kf.gating_distance(m, c, np.array([[102., 51, 21, 41], [107., 56, 26, 46]]))
+    np.savez_compressed(os.path.join(HERE, "kf_ultra.npz"), **out)
+    print("kf", {k: v.shape for k, v in out.items() if "means" in k}, out["kat_xywh_gate"])
+
+
+def _nms_both(pred, conf, iou, **kw):
+    from ultralytics.utils.nms import non_max_suppression
+
+    res = {}
+    tv = sys.modules.pop("torchvision", None)
+    try:
+        assert "torchvision" not in sys.modules
+        res["legacy"] = non_max_suppression(pred.clone(), conf, iou, **kw)
+    finally:
+        if tv is not None:
+            sys.modules["torchvision"] = tv
+    import torchvision  # noqa: F401
+
+    res["exact"] = non_max_suppression(pred.clone(), conf, iou, **kw)
+    return res
+
+
+def gold_nms():
+    out = {}
+    cases = [dict(seed=0, B=2, nc=80, A=800, conf=0.15, iou=0.6, frac=0.05), dict(seed=1, B=1, nc=1, A=1200, conf=0.15, iou=0.6),
+             dict(seed=2, B=3, nc=4, A=600, conf=0.25, iou=0.45), dict(seed=3, B=1, nc=2, A=3000, conf=0.05, iou=0.7, max_det=50),
+             dict(seed=4, B=1, nc=80, A=500, conf=0.15, iou=0.6, agnostic=True),
+             dict(seed=5, B=1, nc=80, A=500, conf=0.15, iou=0.6, classes=[0, 3, 7])]
+    for ci, c in enumerate(cases):
+        pred = synth_pred(c["seed"], c["B"], c["nc"], c["A"], frac=c.get("frac", 0.15))
+        kw = {k: c[k] for k in ("max_det", "agnostic", "classes") if k in c}
+        res = _nms_both(torch.from_numpy(pred), c["conf"], c["iou"], **kw)
+        for mode, lst in res.items():
+            for b, det in enumerate(lst):
+                out[f"c{ci}_{mode}_{b}"] = det.numpy()
+        out[f"c{ci}_cfg"] = np.array([c["seed"], c["B"], c["nc"], c["A"], c["conf"], c["iou"], c.get("max_det", 300),
+                                      float(c.get("agnostic", False))])
+        if "classes" in c:
+            out[f"c{ci}_classes"] = np.array(c["classes"])
+        print("nms case", ci, {m: [len(d) for d in l] for m, l in res.items()})
+    # SURVEY 8c hand cases through TorchNMS.nms / torchvision.ops.nms directly
+    from ultralytics.utils.nms import TorchNMS
+    import torchvision
+    b = torch.tensor([[200., 200, 210, 210], [0, 0, 10, 10], [0, 0, 10, 10.5]]); s = torch.tensor([.9, .8, .7])
+    out["hand_div_legacy"] = TorchNMS.nms(b, s, 0.6).numpy(); out["hand_div_exact"] = torchvision.ops.nms(b, s, 0.6).numpy()
+    np.savez_compressed(os.path.join(HERE, "nms_cases.npz"), **out)
+    print("hand", out["hand_div_legacy"], out["hand_div_exact"])
+
+
+def _ref_model(name, seed=0):
+    from ultralytics.nn.tasks import DetectionModel
+
+    spec = cfg.resolve(name)
+    sd = weights.synthetic_state_dict(spec, seed=seed)
+    m = DetectionModel(name + ".yaml", ch=3, nc=spec["nc"], verbose=False).eval()
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    return spec, sd, m
+
+
+def gold_net():
+    spec, sd, m = _ref_model("yolov8n-p2")
+    x = np.random.default_rng(0).random((1, 3, 64, 96), dtype=np.float32)
+    m.fuse()   # the predict path always runs the BN-folded graph (AutoBackend(fuse=True))
+    feats = {}
+    hooks = [m.model[i].register_forward_hook(lambda mod, inp, out, i=i: feats.__setitem__(i, out.detach().numpy().copy()))
+             for i in (0, 2, 9, 18, 27)]
+    with torch.no_grad():
+        y, heads = m(torch.from_numpy(x))
+    for h in hooks:
+        h.remove()
+    np.savez_compressed(os.path.join(HERE, "net_n_p2_small.npz"), y=y.numpy(), **{f"head{i}": h.numpy() for i, h in enumerate(heads)},
+                        **{f"layer{i}": v for i, v in feats.items()})
+    print("net", y.shape, [h.shape for h in heads])
+
+
+def gold_predict():
+    from ultralytics import YOLO
+
+    spec = cfg.resolve("yolov8n-p2")
+    sd = weights.synthetic_state_dict(spec, seed=0)
+    out = {}
+    for tag, (h, w) in (("512x640", (512, 640)), ("500x640", (500, 640))):
+        frames = [synth.IRStream(seed=7, h=h, w=w).frame(), synth.IRStream(seed=8, h=h, w=w).frame()]
+        for mode in ("legacy", "exact"):
+            tv = sys.modules.pop("torchvision", None) if mode == "legacy" else None
+            try:
+                if mode == "exact":
+                    import torchvision  # noqa: F401
+                yolo = YOLO("yolov8n-p2.yaml", verbose=False)
+                yolo.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+                raw = {}
+                res = yolo.predict(frames, conf=0.15, iou=0.6, device="cpu", verbose=False)
+            finally:
+                if tv is not None:
+                    sys.modules["torchvision"] = tv
+            for b, r in enumerate(res):
+                out[f"{tag}_{mode}_{b}"] = r.boxes.data.numpy()
+                assert r.orig_shape == (h, w)
+            print("predict", tag, mode, [len(r.boxes) for r in res])
+    np.savez_compressed(os.path.join(HERE, "predict_n_p2.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["tracker", "kf", "nms", "net", "predict"]
+    for w in which:
+        globals()["gold_" + w]()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
