@@ -1,0 +1,183 @@
+/* b2dt -- C ABI of the B200-native detect+track hot path.
+ *
+ * Drop-in boundary.  The reference is pure Python and has no FFI; these are
+ * the entry points a ctypes binding for its detect+track path needs.  Each entry cites the reference
+ * interface it replaces (paths relative to the reference root).  Conventions:
+ *   - extern "C", plain pointers and sizes only; every function returns an int status
+ *     (B2_OK = 0, negative = error; text via b2_last_error()).
+ *   - all tensor memory is caller-owned DEVICE memory unless a parameter says "host";
+ *     `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - the library owns only its workspaces, activation arena and track banks (opaque handles);
+ *     handles are independent: no global mutable state.
+ *   - activations are NHWC bf16; "cstride"/"coff" address a channel slice [coff, coff+C) of a
+ *     buffer whose pixels are cstride channels apart (this is how torch.cat / chunk disappear).
+ */
+#ifndef B2DT_H
+#define B2DT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_ARG (-1)
+#define B2_ERR_CUDA (-2)
+#define B2_ERR_STATE (-3)
+#define B2_ERR_UNSUPPORTED (-4)
+
+#define B2_ACT_NONE 0
+#define B2_ACT_SILU 1
+
+const char* b2_last_error(void);
+int b2_version(void);
+/* number of kernels this library has launched since load (bench.py "gpu_launches") */
+long long b2_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Module-level ops (per-layer parity; the engine below is composed of exactly these launches)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Conv.forward_fuse = SiLU(conv2d(x, w', b')) with BN folded, optional fused residual add
+ * (ultralytics/nn/modules/conv.py:83-93; Bottleneck.forward block.py:493-495; plain nn.Conv2d 1x1 of
+ * Detect head.py:93-96 with act = B2_ACT_NONE).  Implicit GEMM on tcgen05/TMEM, TMA-staged bf16 tiles.
+ * in  : [B][H][W][in_cstride] bf16, channels [in_coff, in_coff+Cin)
+ * w   : [Cout][k][k][Cin] bf16 (GEMM-K = (kh*k+kw)*Cin + c), bias: [Cout] fp32
+ * out : [B][Ho][Wo][out_cstride] bf16, channels [out_coff, out_coff+Cout);  Ho = (H + 2(k/2) - k)/stride + 1
+ * residual (may be NULL): same spatial shape as out, added after the activation.
+ * Constraints: k in {1,3}; stride in {1,2}; Cin % 16 == 0; cstrides/coffs % 8 == 0. */
+int b2_conv2d_bf16(const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
+                   const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                   void* out, int out_cstride, int out_coff,
+                   const void* residual, int res_cstride, int res_coff, void* stream);
+
+/* Stem: letterbox-pad + BGR->RGB + /255 + Conv(3->C0, k3 s2) + SiLU in one pass over uint8 frames
+ * (data/augment.py:1692-1733 LetterBox pad value 114; engine/predictor.py:152-175 preprocess;
+ * model.0 of yolov8-p2.yaml).  frames: [B][src_h][src_w][3] uint8 BGR.  The letterboxed canvas is
+ * H x W with the frame at (pad_top, pad_left).  w: [C0][3][3][3] fp32 (o,kh,kw,c_rgb) BN-folded,
+ * NOT divided by 255 (the kernel scales).  out: [B][H/2][W/2][out_cstride] bf16. */
+int b2_stem_u8(const uint8_t* frames, int B, int src_h, int src_w, int H, int W, int pad_top, int pad_left,
+               const float* w, const float* bias, int C0, void* out, int out_cstride, int out_coff, void* stream);
+/* Same stem for float tensors BCHW RGB in [0,1] (data/loaders.py:566-638 LoadTensor). dtype: 0 fp32, 1 bf16 */
+int b2_stem_f32(const void* bchw, int dtype, int B, int H, int W, const float* w, const float* bias, int C0,
+                void* out, int out_cstride, int out_coff, void* stream);
+
+/* Stand-alone preprocess (engine/predictor.py:152-175 + LetterBox pad-only path): uint8 HWC BGR ->
+ * fp32 BCHW RGB in [0,1], canvas H x W, border 114/255.  For API parity (BasePredictor.preprocess). */
+int b2_preprocess_u8(const uint8_t* frames, int B, int src_h, int src_w, int H, int W, int pad_top, int pad_left,
+                     float* out_bchw, void* stream);
+/* cv2.resize(INTER_LINEAR) on uint8 HWC (data/augment.py:1718): fixed-point bilinear identical to OpenCV. */
+int b2_resize_bilinear_u8(const uint8_t* src, int B, int sh, int sw, uint8_t* dst, int dh, int dw, void* stream);
+
+/* SPPF pooling (block.py:237-241): y1 = maxpool5(x), y2 = maxpool5(y1), y3 = maxpool5(y2) (stride 1, pad 2).
+ * buf: [B][H][W][cstride] bf16; reads channels [coff, coff+C), writes [coff+C, coff+4C). */
+int b2_sppf_pool(void* buf, int B, int H, int W, int cstride, int coff, int C, void* stream);
+
+/* nn.Upsample(None, 2, 'nearest') / channel-slice copy written into a concat slice
+ * (yolov8-p2.yaml:33-54, conv.py:673-683 Concat).  scale in {1,2}. */
+int b2_upsample_slice(const void* in, int B, int H, int W, int in_cstride, int in_coff, int C, int scale,
+                      void* out, int out_cstride, int out_coff, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Detect post-processing
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Detect._inference + confidence filter (head.py:152-187, block.py:78-81 DFL, tal.py:367-391,
+ * nms.py:74 `amax > conf`, :111 best class): reads per-level NHWC bf16 logits
+ * [B][h_l*w_l][lstride] (64 DFL bins then nc class logits) and appends one candidate per anchor whose
+ * best class score > conf:  cand[b][i] = {x1,y1,x2,y2 (letterboxed-input pixels), score, cls} fp32,
+ * cand_idx[b][i] = anchor index, cand_count[b].  At most cand_cap candidates per image are stored
+ * (count keeps counting).  classes_mask: optional nc uint8 (nms.py:120-124 `classes=` filter).
+ * dense_out (may be NULL): the reference-shaped (B, 4+nc, A) fp32 tensor [cx,cy,w,h,sigmoid(cls)...]. */
+int b2_decode(const void* const* level_logits, const int* level_h, const int* level_w, const int* level_stride,
+              int n_levels, int B, int nc, int lstride, float conf, const uint8_t* classes_mask,
+              float* cand, int32_t* cand_idx, int32_t* cand_count, int cand_cap, float* dense_out, void* stream);
+
+/* non_max_suppression tail + scale_boxes/clip_boxes (utils/nms.py:129-160; torchvision.ops.nms or
+ * TorchNMS.nms :237-304; utils/ops.py:105-138,157-183).  Per image: sort candidates by (score desc,
+ * anchor asc), cap at max_nms, greedy NMS on class-offset fp32 boxes (cls*max_wh unless agnostic),
+ * suppress iou > iou_thres, keep <= max_det, then subtract (pad_x,pad_y), divide by gain, clip to
+ * (orig_w, orig_h).  mode: 0 = exact greedy (torchvision branch), 1 = legacy TorchNMS early exit.
+ * out: [B][max_det][6] {x1,y1,x2,y2,conf,cls}; out_count[B]; out_idx (may be NULL): kept anchor ids. */
+int b2_nms(const float* cand, const int32_t* cand_idx, const int32_t* cand_count, int cand_cap, int B,
+           float iou_thres, int max_det, int max_nms, int agnostic, float max_wh, int mode,
+           float gain, float pad_x, float pad_y, float orig_w, float orig_h, int do_scale,
+           float* out, int32_t* out_count, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+size_t b2_nms_workspace_bytes(int B, int cand_cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * Engine: the whole YOLOv8-P2 forward as one launch plan (nn/tasks.py:159-188 _predict_once over
+ * the fused graph; replaces AutoBackend.forward nn/autobackend.py:608-637 for the pt branch).
+ * `plan` is the int32 program emitted by the host (engine.py); `weights` a host blob it indexes.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b2_engine b2_engine_t;
+int b2_engine_create(const int32_t* plan, int plan_words, const void* weights_host, size_t weight_bytes,
+                     int B, int H, int W, b2_engine_t** out);
+int b2_engine_destroy(b2_engine_t* e);
+/* frames: [B][src_h][src_w][3] uint8 BGR device memory, placed at (pad_top,pad_left) of the HxW canvas */
+int b2_engine_forward_u8(b2_engine_t* e, const uint8_t* frames, int src_h, int src_w, int pad_top, int pad_left, void* stream);
+/* x: BCHW RGB [0,1], dtype 0 fp32 / 1 bf16 */
+int b2_engine_forward_f32(b2_engine_t* e, const void* bchw, int dtype, void* stream);
+/* Per-level head logits of the last forward: device pointers, [B][h*w][lstride] bf16 */
+int b2_engine_levels(b2_engine_t* e, int* n_levels, const void** logits, int* h, int* w, int* stride, int* lstride);
+/* Debug/parity: device pointer + geometry of activation buffer `buf` (NHWC bf16) */
+int b2_engine_buffer(b2_engine_t* e, int buf, const void** ptr, int* h, int* w, int* c);
+size_t b2_engine_arena_bytes(b2_engine_t* e);
+int b2_engine_num_launches(b2_engine_t* e);
+/* 1 = replay the layer launches from a captured CUDA graph (default), 0 = eager launches */
+int b2_engine_use_graph(b2_engine_t* e, int on);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tracker: structure-of-arrays Kalman bank, one independent tracker per stream
+ * (kalman/enhanced_multi_target_tracker.py:15-132 EnhancedMultiTargetTracker.update,
+ *  kalman/enhanced_aircraft_kalman_tracker.py:23-405 AircraftKalmanTracker).
+ * ---------------------------------------------------------------------------------------------- */
+#define B2_TRACK_COLS 20
+/* output row (fp32 unless noted; "i32" columns are int32 bit patterns):
+ *  0 id(i32) 1..4 bbox x1,y1,x2,y2 5 confidence 6 predicted(i32: 1 = 'predicted', 0 = 'detected')
+ *  7 age(i32) 8 hits(i32) 9 hit_streak(i32) 10 time_since_update(i32) 11 lost_frames(i32, = tsu)
+ *  12 is_lost(i32) 13 vx 14 vy 15 motion_confidence 16 is_stable_motion(i32) 17 speed 18 direction 19 slot(i32) */
+#define B2_TRAJ_LEN 30
+typedef struct b2_tracker b2_tracker_t;
+int b2_tracker_create(int n_streams, int capacity, int max_dets, int max_lost_frames, int min_hits,
+                      float iou_threshold, b2_tracker_t** out);
+int b2_tracker_destroy(b2_tracker_t* t);
+int b2_tracker_reset(b2_tracker_t* t, void* stream);
+/* One frame for every stream.  dets: [n_streams][max_dets][det_cols] fp32 rows starting with
+ * x1,y1,x2,y2 (det_cols >= 4, e.g. 6 for NMS output rows); det_counts: [n_streams] int32.
+ * out_rows: [n_streams][capacity][B2_TRACK_COLS]; out_counts: [n_streams] int32;
+ * out_traj (may be NULL): [n_streams][capacity][B2_TRAJ_LEN][2] fp32 last centres, oldest first,
+ * out_traj_len (may be NULL): [n_streams][capacity] int32. */
+int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_cols, const int32_t* det_counts,
+                      float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, void* stream);
+/* Host-side inspection (synchronises): dense state of one stream.  x: [cap][8], P: [cap][64] (dense 8x8
+ * rebuilt from the decoupled blocks), meta: [cap][8] int32 {id, age, hits, hit_streak, tsu, lost_frames, is_lost, n_vel},
+ * stats: [6] int64 {created, terminated, active, long_term_predictions, recoveries, frame_count}. */
+int b2_tracker_export(b2_tracker_t* t, int stream_idx, float* x_host, float* P_host, int32_t* meta_host,
+                      int32_t* n_tracks_host, long long* stats_host);
+/* bytes of bank state read+written per live track by one predict / one update (for roofline accounting) */
+int b2_tracker_bytes_per_track(int* predict_bytes, int* update_bytes);
+/* Bank-only kernels for roofline measurement at C3 scale: predict every live track;
+ * update tracks whose match[slot] >= 0 with dets[match]; no association/lifecycle. */
+int b2_tracker_bank_predict(b2_tracker_t* t, void* stream);
+int b2_tracker_seed(b2_tracker_t* t, const float* boxes, const int32_t* counts, int max_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ultralytics ByteTrack/BoT-SORT Kalman filters (ultralytics/trackers/utils/kalman_filter.py:
+ * KalmanFilterXYAH :39-286, KalmanFilterXYWH :289-493), batched over N tracks, dense 8x8 fp32.
+ * kind: 0 = XYAH, 1 = XYWH.  mean [N][8], cov [N][64] row-major, measurements [.][4].
+ * ---------------------------------------------------------------------------------------------- */
+int b2_kf_initiate(int kind, const float* meas, float* mean, float* cov, int N, void* stream);
+int b2_kf_predict(int kind, float* mean, float* cov, int N, void* stream);           /* multi_predict, in place */
+int b2_kf_project(int kind, const float* mean, const float* cov, float* pmean, float* pcov, int N, void* stream);
+int b2_kf_update(int kind, float* mean, float* cov, const float* meas, const uint8_t* mask, int N, void* stream);
+/* out[n][m] = gating distance of track n to measurement m; metric 0 = 'maha', 1 = 'gaussian' */
+int b2_kf_gating(int kind, const float* mean, const float* cov, int N, const float* meas, int M,
+                 int only_position, int metric, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2DT_H */

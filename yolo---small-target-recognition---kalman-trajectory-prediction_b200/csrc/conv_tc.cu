@@ -1,0 +1,385 @@
+// Implicit-GEMM convolution on tcgen05 / TMEM for NHWC bf16 activations (sm_100a).
+//
+// Replaces Conv.forward_fuse = SiLU(conv2d(x, w', b')) (ultralytics/nn/modules/conv.py:83-93) with BN
+// folded (utils/torch_utils.py:255-286), the Bottleneck residual add (block.py:493-495) and the bias-only
+// 1x1 convs of Detect (head.py:93-96).
+//
+// GEMM view:  D[M = B*Ho*Wo pixels, N = Cout] = sum over (tap, channel chunk) A[M, BK] * W[N, BK]^T
+//   * M tile = 128 output pixels arranged as an (NB x TH x TW) patch, so that the A operand of filter tap
+//     (kh,kw) is ONE tiled 4-D TMA box of the NHWC input shifted by (kw-pad, kh-pad); image borders are
+//     the TMA's out-of-bounds zero fill (= conv zero padding).  Stride-2 convs read one of four
+//     parity-decimated views of the input (even/odd rows x even/odd columns), each again a plain tiled map.
+//   * The box's innermost extent is BK channels = 128/64/32 bytes -> SWIZZLE_128B/64B/32B K-major
+//     canonical UMMA layout, consumed by tcgen05.mma (M=128, N=n_tile, K=16) straight from shared memory.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..5 =
+//     epilogue (TMEM -> registers -> +bias -> SiLU -> (+residual) -> bf16 -> global channel slice).
+//   * Persistent CTAs (grid = min(tiles, #SM)), multi-stage smem ring (mbarrier full/empty), two TMEM
+//     accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * Output goes to a channel slice [coff, coff+Cout) of a wider NHWC buffer: torch.cat / chunk of
+//     C2f / SPPF / Concat / Detect become offset writes and offset reads.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+
+struct alignas(64) ConvParams {
+    CUtensorMap tmA[4];
+    CUtensorMap tmB;
+    int B, Ho, Wo;
+    int TW, TH, NB;
+    int tiles_w, tiles_h, tiles_nb;
+    int n_tiles, n_tile, Cout;
+    int Cin, ksize, stride, pad;
+    int BK, kchunks, num_stages;
+    uint32_t a_bytes, b_bytes, b_stage_stride;
+    uint32_t tmem_cols;
+    uint32_t swizzle_code;   // UMMA layout type: 2 = 128B, 4 = 64B, 6 = 32B
+    uint32_t sbo;            // 8 rows * row bytes
+    __nv_bfloat16* out; int out_cstride, out_coff;
+    const __nv_bfloat16* res; int res_cstride, res_coff;
+    const float* bias;
+    int act;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo, uint32_t layout) {
+    // cute::UMMA::SmemDescriptor (sm100): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.num_stages * p.a_bytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA[0]);
+        if (p.stride == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
+        tma_prefetch_desc(&p.tmB);
+        for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_s, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_nb;
+    const int total_tiles = tiles_m * p.n_tiles;
+    const int ksteps = p.ksize * p.ksize * p.kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_idx = tile % p.n_tiles;
+                int m_idx = tile / p.n_tiles;
+                const int w0 = (m_idx % p.tiles_w) * p.TW; m_idx /= p.tiles_w;
+                const int h0 = (m_idx % p.tiles_h) * p.TH;
+                const int n0 = (m_idx / p.tiles_h) * p.NB;
+                for (int tap = 0; tap < p.ksize * p.ksize; ++tap) {
+                    const int kh = tap / p.ksize, kw = tap % p.ksize;
+                    int map = 0, cw, chh;
+                    if (p.stride == 1) {
+                        cw = w0 + kw - p.pad; chh = h0 + kh - p.pad;
+                    } else {
+                        const int ih0 = kh - p.pad, iw0 = kw - p.pad;       // input = 2*out + i?0
+                        const int ph = ih0 & 1, pw = iw0 & 1;
+                        map = ph * 2 + pw;
+                        chh = h0 + (ih0 - ph) / 2; cw = w0 + (iw0 - pw) / 2;
+                    }
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+                        tma_load_4d(smem_a + (size_t)stage * p.a_bytes, &p.tmA[map], &full_bar[stage], kc * p.BK, cw, chh, n0);
+                        tma_load_2d(smem_b + (size_t)stage * p.b_stage_stride, &p.tmB, &full_bar[stage],
+                                    tap * p.Cin + kc * p.BK, n_idx * p.n_tile);
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            // InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B, N>>3 at 17, M>>4 at 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const int mma_per_step = p.BK / 16;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.n_tile);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc(smem_u32(smem_a + (size_t)stage * p.a_bytes), p.sbo, p.swizzle_code);
+                    const uint64_t db = make_smem_desc(smem_u32(smem_b + (size_t)stage * p.b_stage_stride), p.sbo, p.swizzle_code);
+                    for (int j = 0; j < mma_per_step; ++j) {
+                        // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                        tc_mma_bf16(d_addr, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (ks | j) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;                   // row of the 128-row tile == TMEM lane
+        const int tw = row % p.TW, th = (row / p.TW) % p.TH, nb = row / (p.TW * p.TH);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_idx = tile % p.n_tiles;
+            int m_idx = tile / p.n_tiles;
+            const int w = (m_idx % p.tiles_w) * p.TW + tw; m_idx /= p.tiles_w;
+            const int h = (m_idx % p.tiles_h) * p.TH + th;
+            const int n = (m_idx / p.tiles_h) * p.NB + nb;
+            const bool valid = (w < p.Wo) && (h < p.Ho) && (n < p.B);
+            const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+            const int n_base = n_idx * p.n_tile;
+            __nv_bfloat16* optr = p.out + pix * p.out_cstride + p.out_coff + n_base;
+            const __nv_bfloat16* rptr = p.res ? p.res + pix * p.res_cstride + p.res_coff + n_base : nullptr;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n_tile);
+            const int ncols = min(p.n_tile, p.Cout - n_base);
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_addr + c0, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float f[16];
+                    const int nv = min(16, ncols - c0);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float x = __uint_as_float(v[i]) + ((i < nv) ? __ldg(p.bias + n_base + c0 + i) : 0.f);
+                        f[i] = p.act ? silu_f(x) : x;
+                    }
+                    if (nv == 16) {
+                        if (rptr) {
+                            const uint4 r0 = *reinterpret_cast<const uint4*>(rptr + c0);
+                            const uint4 r1 = *reinterpret_cast<const uint4*>(rptr + c0 + 8);
+                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { f[2 * i] += bf16_lo(rr[i]); f[2 * i + 1] += bf16_hi(rr[i]); }
+                        }
+                        uint4 o0, o1;
+                        o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+                        o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+                        o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+                        o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                        *reinterpret_cast<uint4*>(optr + c0) = o0;
+                        *reinterpret_cast<uint4*>(optr + c0 + 8) = o1;
+                    } else {
+                        for (int i = 0; i < nv; ++i) {
+                            float x = f[i];
+                            if (rptr) x += __bfloat162float(rptr[c0 + i]);
+                            optr[c0 + i] = __float2bfloat16_rn(x);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    });
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int bk) {
+    return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+}  // namespace
+
+// Choose the (TW, TH, NB) patch (product 128, powers of two) that wastes the fewest tile slots.
+void b2_pick_tile(int B, int Ho, int Wo, int* TW, int* TH, int* NB) {
+    double best = -1; int bw = 16, bh = 8, bn = 1;
+    for (int tw = 1; tw <= 128; tw *= 2)
+        for (int th = 1; tw * th <= 128; th *= 2) {
+            const int nb = 128 / (tw * th);
+            const double slots = (double)b2_ceil_div(Wo, tw) * tw * b2_ceil_div(Ho, th) * th * b2_ceil_div(B, nb) * nb;
+            double score = (double)B * Ho * Wo / slots;
+            score += 1e-6 * tw - 1e-5 * nb;   // tie-break: wide rows, few images per tile
+            if (tw > 256 || th > 256 || nb > 256) continue;
+            if (score > best) { best = score; bw = tw; bh = th; bn = nb; }
+        }
+    *TW = bw; *TH = bh; *NB = bn;
+}
+
+struct B2ConvLaunch {
+    ConvParams p;
+    int grid;
+    size_t smem;
+};
+
+size_t b2_conv_launch_size() { return sizeof(B2ConvLaunch); }
+
+// Build the launch descriptor (tensor maps + geometry).  `storage` must hold b2_conv_launch_size() bytes, 64B aligned.
+int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
+                    const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                    void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff) {
+    B2_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize %d unsupported (1 or 3)", ksize);
+    B2_REQUIRE(stride == 1 || stride == 2, "conv: stride %d unsupported (1 or 2)", stride);
+    B2_REQUIRE(Cin % 16 == 0 && Cin > 0, "conv: Cin=%d must be a positive multiple of 16", Cin);
+    B2_REQUIRE(in_cstride % 8 == 0 && in_coff % 8 == 0 && out_cstride % 8 == 0 && out_coff % 8 == 0,
+               "conv: channel strides/offsets must be multiples of 8 (16-byte TMA / vector alignment)");
+    B2_REQUIRE(!residual || (res_cstride % 8 == 0 && res_coff % 8 == 0), "conv: residual stride/offset must be multiples of 8");
+    B2_REQUIRE(Cout > 0 && B > 0 && H > 0 && W > 0, "conv: bad shape");
+    B2_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)w % 16 == 0), "conv: pointers must be 16-byte aligned");
+    {   // opt in to the large dynamic shared memory carve-out once (not a stream operation: safe before graph capture)
+        static std::once_flag once;
+        static cudaError_t attr_err = cudaSuccess;
+        std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048); });
+        B2_CUDA(attr_err);
+    }
+    EncodeTiledFn encode = get_encode();
+    if (!encode) { b2_set_error("cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_CUDA; }
+
+    B2ConvLaunch* L = reinterpret_cast<B2ConvLaunch*>(storage);
+    memset(L, 0, sizeof(*L));
+    ConvParams& p = L->p;
+    const int pad = ksize / 2;
+    p.B = B; p.Ho = (H + 2 * pad - ksize) / stride + 1; p.Wo = (W + 2 * pad - ksize) / stride + 1;
+    b2_pick_tile(B, p.Ho, p.Wo, &p.TW, &p.TH, &p.NB);
+    p.tiles_w = b2_ceil_div(p.Wo, p.TW); p.tiles_h = b2_ceil_div(p.Ho, p.TH); p.tiles_nb = b2_ceil_div(B, p.NB);
+    p.Cout = Cout; p.Cin = Cin; p.ksize = ksize; p.stride = stride; p.pad = pad;
+    p.BK = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
+    p.kchunks = Cin / p.BK;
+    const int cout16 = b2_ceil_div(Cout, 16) * 16;
+    if (cout16 <= 256) { p.n_tiles = 1; p.n_tile = cout16; }
+    else {
+        p.n_tiles = b2_ceil_div(cout16, 256);
+        p.n_tile = b2_ceil_div(b2_ceil_div(cout16, p.n_tiles), 16) * 16;
+        p.n_tiles = b2_ceil_div(cout16, p.n_tile);
+    }
+    p.a_bytes = 128u * p.BK * 2u;
+    p.b_bytes = (uint32_t)p.n_tile * p.BK * 2u;
+    p.b_stage_stride = (p.b_bytes + 1023u) & ~1023u;
+    p.swizzle_code = p.BK == 64 ? 2u : p.BK == 32 ? 4u : 6u;
+    p.sbo = 8u * p.BK * 2u;
+    uint32_t cols = 2u * p.n_tile, pw = 32;
+    while (pw < cols) pw <<= 1;
+    p.tmem_cols = pw;
+    const size_t per_stage = p.a_bytes + p.b_stage_stride;
+    int stages = (int)((200 * 1024) / per_stage);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    p.num_stages = stages;
+    L->smem = per_stage * stages + 1024;
+    p.out = (__nv_bfloat16*)out; p.out_cstride = out_cstride; p.out_coff = out_coff;
+    p.res = (const __nv_bfloat16*)residual; p.res_cstride = res_cstride; p.res_coff = res_coff;
+    p.bias = bias; p.act = act;
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_nb * p.n_tiles;
+    const int sms = b2_num_sms();
+    L->grid = total_tiles < sms ? total_tiles : sms;
+
+    // ---- A maps: (C, W', H', B) views of the NHWC input -------------------------------------------------
+    const CUtensorMapSwizzle sw = swizzle_for(p.BK);
+    const cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.NB};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const char* base = (const char*)in + (size_t)in_coff * 2;
+    const int nmaps = stride == 1 ? 1 : 4;
+    for (int m = 0; m < nmaps; ++m) {
+        const int ph = m >> 1, pw_ = m & 1;
+        cuuint64_t dims[4], strides[3];
+        const char* ptr = base;
+        if (stride == 1) {
+            dims[0] = Cin; dims[1] = W; dims[2] = H; dims[3] = B;
+            strides[0] = (cuuint64_t)in_cstride * 2; strides[1] = (cuuint64_t)W * in_cstride * 2; strides[2] = (cuuint64_t)H * W * in_cstride * 2;
+        } else {
+            dims[0] = Cin; dims[1] = (W - pw_ + 1) / 2; dims[2] = (H - ph + 1) / 2; dims[3] = B;
+            if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
+            strides[0] = (cuuint64_t)in_cstride * 4; strides[1] = (cuuint64_t)W * in_cstride * 4; strides[2] = (cuuint64_t)H * W * in_cstride * 2;
+            ptr = base + ((size_t)ph * W + pw_) * in_cstride * 2;
+        }
+        CUresult r = encode(&p.tmA[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(A, map %d) failed with %d", m, (int)r); return B2_ERR_CUDA; }
+    }
+    // ---- B map: weights [Cout][K] K-major ---------------------------------------------------------------
+    {
+        const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
+        const cuuint64_t dims[2] = {K, (cuuint64_t)Cout};
+        const cuuint64_t strides[1] = {K * 2};
+        const cuuint32_t boxb[2] = {(cuuint32_t)p.BK, (cuuint32_t)p.n_tile};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = encode(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, boxb, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(B) failed with %d", (int)r); return B2_ERR_CUDA; }
+    }
+    return B2_OK;
+}
+
+void b2_count_launch(int n);
+
+int b2_conv_launch(const void* storage, cudaStream_t stream) {
+    const B2ConvLaunch* L = reinterpret_cast<const B2ConvLaunch*>(storage);
+    conv_tc_kernel<<<L->grid, kThreads, L->smem, stream>>>(L->p);
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch(1);
+    return B2_OK;
+}
+
+extern "C" int b2_conv2d_bf16(const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
+                              const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                              void* out, int out_cstride, int out_coff,
+                              const void* residual, int res_cstride, int res_coff, void* stream) {
+    alignas(64) unsigned char storage[sizeof(B2ConvLaunch)];
+    int rc = b2_conv_prepare(storage, in, B, H, W, in_cstride, in_coff, Cin, w, bias, Cout, ksize, stride, act,
+                             out, out_cstride, out_coff, residual, res_cstride, res_coff);
+    if (rc != B2_OK) return rc;
+    return b2_conv_launch(storage, (cudaStream_t)stream);
+}

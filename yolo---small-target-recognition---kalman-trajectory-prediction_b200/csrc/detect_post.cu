@@ -1,0 +1,337 @@
+// Detect post-processing for sm_100a: DFL decode + confidence filter + compaction, and per-image NMS
+// (sort, greedy suppression, scale_boxes/clip) -- HBM-bandwidth kernels with coalesced 16-byte accesses.
+//
+//   decode_kernel  Detect._inference (ultralytics/nn/modules/head.py:152-187), DFL (block.py:78-81),
+//                  make_anchors / dist2bbox (utils/tal.py:367-391), then the candidate test of
+//                  non_max_suppression (utils/nms.py:74 amax > conf, :111 best class, :120-124 classes).
+//   nms_kernel     utils/nms.py:129-160 (+ torchvision.ops.nms / TorchNMS.nms :237-304) and
+//                  scale_boxes / clip_boxes (utils/ops.py:105-138, :157-183).
+#include "common.cuh"
+
+void b2_count_launch(int n);
+
+namespace {
+
+constexpr int kMaxLevels = 8;
+
+struct DecodeParams {
+    const __nv_bfloat16* lv[kMaxLevels];
+    int h[kMaxLevels], w[kMaxLevels], stride[kMaxLevels], a_off[kMaxLevels + 1];
+    int n_levels, B, nc, lstride, A;
+    float conf;
+    const uint8_t* cmask;
+    float* cand; int32_t* cand_idx; int32_t* cand_count; int cand_cap;
+    float* dense;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+// 8 lanes cooperate on one anchor: lane s loads 16-byte chunk s of the 64 DFL logits (side = s/2,
+// bins (s&1)*8..+7), then chunks s, s+8, ... of the class logits.  A warp covers 4 consecutive anchors
+// = 4 x (64+nc) x 2 contiguous bytes of the NHWC logits.
+__global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const int b = blockIdx.y;
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool active = a < p.A;
+    int lvl = 0;
+    if (active) { while (lvl + 1 < p.n_levels && a >= p.a_off[lvl + 1]) ++lvl; }
+    const int la = active ? a - p.a_off[lvl] : 0;
+    const int W = p.w[lvl], H = p.h[lvl];
+    const __nv_bfloat16* row = p.lv[lvl] + ((size_t)b * H * W + la) * p.lstride;
+
+    // ---- DFL: softmax expectation over 16 bins per side ----
+    float f[8];
+    if (active) unpack8(ldg_nc_v4(row + sub * 8), f);
+    else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = 0.f;
+    }
+    float m = f[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    float se = 0.f, sw = 0.f;
+    const float bin0 = (float)((sub & 1) * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float e = __expf(f[i] - m);
+        se += e; sw = fmaf(e, bin0 + (float)i, sw);
+    }
+    se += __shfl_xor_sync(0xffffffffu, se, 1);
+    sw += __shfl_xor_sync(0xffffffffu, sw, 1);
+    const float dist = sw / se;
+    const int gbase = lane & ~7;
+    const float dl = __shfl_sync(0xffffffffu, dist, gbase + 0), dt = __shfl_sync(0xffffffffu, dist, gbase + 2);
+    const float dr = __shfl_sync(0xffffffffu, dist, gbase + 4), db = __shfl_sync(0xffffffffu, dist, gbase + 6);
+
+    // ---- classes: max logit / argmax over nc ----
+    float best = -INFINITY; int bidx = 0x7fffffff;
+    const int nchunks = (p.nc + 7) >> 3;
+    const size_t dense_base = (size_t)b * (4 + p.nc) * p.A + a;
+    for (int ck = sub; ck < nchunks; ck += 8) {
+        float c[8];
+        if (active) unpack8(ldg_nc_v4(row + 64 + ck * 8), c);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int ci = ck * 8 + i;
+            if (ci < p.nc) {
+                if (p.dense && active) p.dense[dense_base + (size_t)(4 + ci) * p.A] = 1.f / (1.f + __expf(-c[i]));
+                const bool allowed = !p.cmask || p.cmask[ci];
+                if (allowed && (c[i] > best)) { best = c[i]; bidx = ci; }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+
+    // ---- box (tal.py:382-391 then * stride; xywh2xyxy ops.py:277-294), same fp32 operation order ----
+    const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f, st = (float)p.stride[lvl];
+    const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + db;
+    const float cx = (x1 + x2) / 2.f * st, cy = (y1 + y2) / 2.f * st, bw = (x2 - x1) * st, bh = (y2 - y1) * st;
+    if (p.dense && active && sub < 4) p.dense[dense_base + (size_t)sub * p.A] = sub == 0 ? cx : sub == 1 ? cy : sub == 2 ? bw : bh;
+
+    const float score = 1.f / (1.f + __expf(-best));
+    const bool is_cand = active && sub == 0 && bidx != 0x7fffffff && score > p.conf;
+    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+    if (ball) {
+        int base = 0;
+        const int leader = __ffs(ball) - 1;
+        if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (is_cand) {
+            const int pos = base + __popc(ball & ((1u << lane) - 1));
+            if (pos < p.cand_cap) {
+                float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
+                const float hw = bw / 2.f, hh = bh / 2.f;
+                o[0] = cx - hw; o[1] = cy - hh; o[2] = cx + hw; o[3] = cy + hh; o[4] = score; o[5] = (float)bidx;
+                p.cand_idx[(size_t)b * p.cand_cap + pos] = a;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS: one CTA per image
+// ------------------------------------------------------------------------------------------------
+constexpr int kNmsThreads = 1024;
+constexpr int kSmemSort = 2048;      // pairs sorted entirely in shared memory
+constexpr int kMaxCand = 65536;      // alive bitmask (shared memory) covers this many sorted candidates
+constexpr int kMaxKeep = 1024;
+
+struct NmsParams {
+    const float* cand; const int32_t* cand_idx; const int32_t* cand_count; int cand_cap, B;
+    float iou_thres; int max_det, max_nms, agnostic; float max_wh; int mode;
+    float gain, pad_x, pad_y, orig_w, orig_h; int do_scale;
+    float* out; int32_t* out_count; int32_t* out_idx;
+    unsigned long long* ws_keys; int32_t* ws_pay; float4* ws_box; int P_max;
+};
+
+__device__ __forceinline__ void bitonic_exchange(unsigned long long* keys, int32_t* pay, int i, int j, bool desc_block) {
+    const unsigned long long a = keys[i], b = keys[j];
+    // descending overall: within a "descending" block the larger key goes first
+    if ((a < b) == desc_block) {
+        keys[i] = b; keys[j] = a;
+        const int32_t t = pay[i]; pay[i] = pay[j]; pay[j] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) {
+    __shared__ unsigned long long s_keys[kSmemSort];
+    __shared__ int32_t s_pay[kSmemSort];
+    __shared__ int32_t s_keep[kMaxKeep];
+    __shared__ uint32_t alive[kMaxCand / 32];
+    __shared__ int s_cur, s_nkeep, s_any, s_done;
+
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int n = min(p.cand_count[b], p.cand_cap);
+    const float* cand = p.cand + (size_t)b * p.cand_cap * 6;
+    const int32_t* cidx = p.cand_idx + (size_t)b * p.cand_cap;
+    float* out = p.out + (size_t)b * p.max_det * 6;
+    if (n == 0) { if (tid == 0) p.out_count[b] = 0; return; }
+
+    int P = 32;
+    while (P < n) P <<= 1;
+    const bool in_smem = P <= kSmemSort;
+    unsigned long long* keys = in_smem ? s_keys : p.ws_keys + (size_t)b * p.P_max;
+    int32_t* pay = in_smem ? s_pay : p.ws_pay + (size_t)b * p.P_max;
+    for (int i = tid; i < P; i += kNmsThreads) {
+        if (i < n) {
+            // score > 0: its bit pattern orders like the float; ties -> lower anchor index first (stable sort of the reference)
+            keys[i] = ((unsigned long long)__float_as_uint(cand[i * 6 + 4]) << 32) | (unsigned)(0x7fffffff - cidx[i]);
+            pay[i] = i;
+        } else { keys[i] = 0ull; pay[i] = -1; }
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += kNmsThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                bitonic_exchange(keys, pay, i, i | j, (i & k) == 0);
+            }
+            __syncthreads();
+        }
+    }
+    n = min(n, p.max_nms);
+
+    // sorted, class-offset boxes (nms.py:144,150: boxes = x[:, :4] + cls * max_wh, fp32) + alive bitmask
+    float4* sbox = p.ws_box + (size_t)b * p.P_max;
+    for (int i = tid; i < n; i += kNmsThreads) {
+        const float* c = cand + (size_t)pay[i] * 6;
+        const float off = p.agnostic ? 0.f : __fmul_rn(c[5], p.max_wh);
+        sbox[i] = make_float4(__fadd_rn(c[0], off), __fadd_rn(c[1], off), __fadd_rn(c[2], off), __fadd_rn(c[3], off));
+    }
+    for (int i = tid; i < (n + 31) / 32; i += kNmsThreads) {
+        const int rem = n - i * 32;
+        alive[i] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    }
+    if (tid == 0) { s_cur = 0; s_nkeep = 0; s_done = 0; }
+    __syncthreads();
+
+    const int max_keep = min(p.max_det, kMaxKeep);
+    while (true) {
+        // -- next alive index >= s_cur (warp 0 scans the bitmask) --
+        if (tid < 32) {
+            int cur = s_cur, found = -1;
+            const int nwords = (n + 31) / 32;
+            for (int wbase = cur >> 5; wbase < nwords && found < 0; wbase += 32) {
+                const int wi = wbase + tid;
+                uint32_t word = wi < nwords ? alive[wi] : 0u;
+                if (wi == (cur >> 5)) word &= ~((1u << (cur & 31)) - 1u);
+                const unsigned has = __ballot_sync(0xffffffffu, word != 0u);
+                if (has) {
+                    const int src = __ffs(has) - 1;
+                    const uint32_t wsel = __shfl_sync(0xffffffffu, word, src);
+                    found = (wbase + src) * 32 + __ffs(wsel) - 1;
+                }
+            }
+            if (tid == 0) {
+                if (found < 0 || s_nkeep >= max_keep) s_done = 1;
+                else { s_keep[s_nkeep++] = found; s_cur = found + 1; s_any = 0; }
+            }
+        }
+        __syncthreads();
+        if (s_done) break;
+        const int i = s_cur - 1;
+        const float4 bi = sbox[i];
+        const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+        int any = 0;
+        for (int j = i + 1 + tid; j < n; j += kNmsThreads) {
+            if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;
+            const float4 bj = sbox[j];
+            const float iw = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
+            const float ih = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
+            const float inter = __fmul_rn(iw, ih);
+            if (inter != 0.f) any = 1;
+            const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
+            if (iou > p.iou_thres) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
+        }
+        if (p.mode == 1) {
+            if (any) s_any = 1;      // benign race: all writers store 1
+            __syncthreads();
+            if (!s_any) {
+                // TorchNMS.nms early exit (nms.py:290-296): nothing intersects -> keep every remaining box, stop.
+                // (the suppression pass above cleared nothing: iou == 0 for all of them)
+                if (tid == 0) {
+                    for (int j = i + 1; j < n && s_nkeep < max_keep; ++j)
+                        if ((alive[j >> 5] >> (j & 31)) & 1u) s_keep[s_nkeep++] = j;
+                    s_done = 1;
+                }
+                __syncthreads();
+                break;
+            }
+        }
+        __syncthreads();
+    }
+
+    const int nk = s_nkeep;
+    for (int k = tid; k < nk; k += kNmsThreads) {
+        const int src = pay[s_keep[k]];
+        const float* c = cand + (size_t)src * 6;
+        float x1 = c[0], y1 = c[1], x2 = c[2], y2 = c[3];
+        if (p.do_scale) {
+            x1 = __fdiv_rn(__fsub_rn(x1, p.pad_x), p.gain); y1 = __fdiv_rn(__fsub_rn(y1, p.pad_y), p.gain);
+            x2 = __fdiv_rn(__fsub_rn(x2, p.pad_x), p.gain); y2 = __fdiv_rn(__fsub_rn(y2, p.pad_y), p.gain);
+            x1 = fminf(fmaxf(x1, 0.f), p.orig_w); x2 = fminf(fmaxf(x2, 0.f), p.orig_w);
+            y1 = fminf(fmaxf(y1, 0.f), p.orig_h); y2 = fminf(fmaxf(y2, 0.f), p.orig_h);
+        }
+        float* o = out + (size_t)k * 6;
+        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = c[4]; o[5] = c[5];
+        if (p.out_idx) p.out_idx[(size_t)b * p.max_det + k] = cidx[src];
+    }
+    if (tid == 0) p.out_count[b] = nk;
+}
+
+inline int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+extern "C" int b2_decode(const void* const* level_logits, const int* level_h, const int* level_w, const int* level_stride,
+                         int n_levels, int B, int nc, int lstride, float conf, const uint8_t* classes_mask,
+                         float* cand, int32_t* cand_idx, int32_t* cand_count, int cand_cap, float* dense_out, void* stream) {
+    B2_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "decode: n_levels=%d out of range", n_levels);
+    B2_REQUIRE(nc >= 1 && lstride % 8 == 0 && lstride >= 64 + ((nc + 7) / 8) * 8, "decode: lstride=%d too small for nc=%d", lstride, nc);
+    B2_REQUIRE(cand && cand_idx && cand_count && cand_cap > 0, "decode: candidate buffers required");
+    DecodeParams p{};
+    p.a_off[0] = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        p.lv[l] = (const __nv_bfloat16*)level_logits[l];
+        B2_REQUIRE(p.lv[l] && ((uintptr_t)p.lv[l] % 16 == 0), "decode: level %d pointer null/unaligned", l);
+        p.h[l] = level_h[l]; p.w[l] = level_w[l]; p.stride[l] = level_stride[l];
+        p.a_off[l + 1] = p.a_off[l] + level_h[l] * level_w[l];
+    }
+    p.n_levels = n_levels; p.B = B; p.nc = nc; p.lstride = lstride; p.A = p.a_off[n_levels];
+    p.conf = conf; p.cmask = classes_mask; p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count;
+    p.cand_cap = cand_cap; p.dense = dense_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
+    dim3 grid(b2_ceil_div(p.A * 8, 256), B);
+    decode_kernel<<<grid, 256, 0, st>>>(p);
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch(1);
+    return B2_OK;
+}
+
+extern "C" size_t b2_nms_workspace_bytes(int B, int cand_cap) {
+    const size_t P = (size_t)next_pow2(cand_cap);
+    return (size_t)B * (P * (8 + 4 + 16)) + 256;
+}
+
+extern "C" int b2_nms(const float* cand, const int32_t* cand_idx, const int32_t* cand_count, int cand_cap, int B,
+                      float iou_thres, int max_det, int max_nms, int agnostic, float max_wh, int mode,
+                      float gain, float pad_x, float pad_y, float orig_w, float orig_h, int do_scale,
+                      float* out, int32_t* out_count, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+    B2_REQUIRE(cand && cand_idx && cand_count && out && out_count && workspace, "nms: null pointer");
+    B2_REQUIRE(max_det >= 1 && max_det <= kMaxKeep, "nms: max_det=%d out of range [1,%d]", max_det, kMaxKeep);
+    B2_REQUIRE(mode == 0 || mode == 1, "nms: mode must be 0 (exact) or 1 (legacy TorchNMS)");
+    B2_REQUIRE(cand_cap >= 1 && cand_cap <= kMaxCand, "nms: cand_cap=%d out of range [1,%d]", cand_cap, kMaxCand);
+    B2_REQUIRE(workspace_bytes >= b2_nms_workspace_bytes(B, cand_cap), "nms: workspace too small");
+    B2_REQUIRE(iou_thres >= 0.f && iou_thres <= 1.f, "Invalid IoU %f, valid values are between 0.0 and 1.0", iou_thres);
+    NmsParams p{};
+    p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count; p.cand_cap = cand_cap; p.B = B;
+    p.iou_thres = iou_thres; p.max_det = max_det; p.max_nms = max_nms; p.agnostic = agnostic; p.max_wh = max_wh; p.mode = mode;
+    p.gain = gain; p.pad_x = pad_x; p.pad_y = pad_y; p.orig_w = orig_w; p.orig_h = orig_h; p.do_scale = do_scale;
+    p.out = out; p.out_count = out_count; p.out_idx = out_idx;
+    const size_t P = (size_t)next_pow2(cand_cap);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    p.ws_box = (float4*)ws; ws += (size_t)B * P * 16;
+    p.ws_keys = (unsigned long long*)ws; ws += (size_t)B * P * 8;
+    p.ws_pay = (int32_t*)ws;
+    p.P_max = (int)P;
+    nms_kernel<<<B, kNmsThreads, 0, (cudaStream_t)stream>>>(p);
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch(1);
+    return B2_OK;
+}

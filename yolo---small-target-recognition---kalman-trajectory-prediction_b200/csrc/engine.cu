@@ -1,0 +1,242 @@
+// Launch-plan executor for the YOLOv8-P2 forward (sm_100a) + C-ABI plumbing shared by all entry points.
+//
+// Replaces the python layer loop BaseModel._predict_once (ultralytics/nn/tasks.py:159-188) over the fused
+// graph that AutoBackend(fuse=True) runs (nn/autobackend.py:196-219, :608-637).  The host (engine.py) lowers the
+// resolved YAML graph to a flat int32 program over NHWC bf16 buffers; concat/chunk are channel offsets, so
+// the program consists only of: stem, conv (tcgen05 implicit GEMM), SPPF pooling, nearest-upsample slice copy.
+// All tensor maps are built once at create time; the layer launches are replayed from a CUDA graph.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+#include <atomic>
+#include <new>
+#include <vector>
+
+// ---- from conv_tc.cu ----
+size_t b2_conv_launch_size();
+int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
+                    const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                    void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff);
+int b2_conv_launch(const void* storage, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// library-wide plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void b2_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void b2_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int b2_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+extern "C" const char* b2_last_error(void) { return g_err; }
+extern "C" int b2_version(void) { return 100; }
+extern "C" long long b2_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kMagic = 0xB2D7;
+constexpr int kOpWords = 14;
+enum Op { OP_STEM = 1, OP_CONV = 2, OP_POOL = 3, OP_UP = 4 };
+
+struct Buf { int h, w, c; size_t off; };
+struct Step {
+    int op;
+    int a[kOpWords - 1];
+    std::vector<unsigned char> conv;   // B2ConvLaunch storage (64B aligned inside)
+    void* conv_ptr() { return (void*)(((uintptr_t)conv.data() + 63) & ~(uintptr_t)63); }
+};
+}  // namespace
+
+struct b2_engine {
+    int B, H, W, nc, lstride, n_levels;
+    std::vector<Buf> bufs;
+    std::vector<Step> steps;
+    std::vector<int> level_buf, level_stride;
+    char* arena = nullptr;
+    size_t arena_bytes = 0, weights_off = 0;
+    cudaGraphExec_t graph = nullptr;
+    cudaStream_t graph_stream = nullptr;
+    bool use_graph = true;
+    int n_launch = 0;
+    char* buf_ptr(int i) { return arena + bufs[i].off; }
+};
+
+static int run_step(b2_engine* e, Step& s, cudaStream_t st) {
+    const int* a = s.a;
+    switch (s.op) {
+        case OP_CONV: return b2_conv_launch(s.conv_ptr(), st);
+        case OP_POOL: { const Buf& b = e->bufs[a[0]]; return b2_sppf_pool(e->buf_ptr(a[0]), e->B, b.h, b.w, b.c, a[1], a[2], st); }
+        case OP_UP: {
+            const Buf& bi = e->bufs[a[0]]; const Buf& bo = e->bufs[a[4]];
+            return b2_upsample_slice(e->buf_ptr(a[0]), e->B, bi.h, bi.w, bi.c, a[1], a[2], a[3], e->buf_ptr(a[4]), bo.c, a[5], st);
+        }
+        default: b2_set_error("engine: bad opcode %d", s.op); return B2_ERR_STATE;
+    }
+}
+
+extern "C" int b2_engine_create(const int32_t* plan, int plan_words, const void* weights_host, size_t weight_bytes,
+                                int B, int H, int W, b2_engine_t** out) {
+    B2_REQUIRE(plan && weights_host && out, "engine_create: null pointer");
+    B2_REQUIRE(plan_words >= 6 && plan[0] == kMagic, "engine_create: bad plan header");
+    B2_REQUIRE(B >= 1 && H % 32 == 0 && W % 32 == 0 && H > 0 && W > 0, "engine_create: H and W must be positive multiples of 32 (got %dx%d)", H, W);
+    const int n_bufs = plan[1], n_ops = plan[2], n_levels = plan[3];
+    B2_REQUIRE(plan_words == 6 + 3 * n_bufs + 2 * n_levels + kOpWords * n_ops, "engine_create: plan length mismatch");
+    b2_engine* e = new (std::nothrow) b2_engine();
+    if (!e) { b2_set_error("out of host memory"); return B2_ERR_STATE; }
+    e->B = B; e->H = H; e->W = W; e->n_levels = n_levels; e->nc = plan[4]; e->lstride = plan[5];
+    const int32_t* p = plan + 6;
+    size_t off = 0;
+    auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+    for (int i = 0; i < n_bufs; ++i, p += 3) {
+        Buf b{p[0], p[1], p[2], off};
+        off += up((size_t)B * b.h * b.w * b.c * 2);
+        e->bufs.push_back(b);
+    }
+    for (int l = 0; l < n_levels; ++l, p += 2) { e->level_buf.push_back(p[0]); e->level_stride.push_back(p[1]); }
+    e->weights_off = off;
+    off += up(weight_bytes);
+    e->arena_bytes = off;
+    cudaError_t ce = cudaMalloc((void**)&e->arena, off);
+    if (ce != cudaSuccess) { b2_set_error("engine_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(ce)); delete e; return B2_ERR_CUDA; }
+    int rc = B2_OK;
+    auto fail = [&](int code) { cudaFree(e->arena); delete e; return code; };
+    if (cudaMemset(e->arena, 0, off) != cudaSuccess ||
+        cudaMemcpy(e->arena + e->weights_off, weights_host, weight_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        b2_set_error("engine_create: arena initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(B2_ERR_CUDA);
+    }
+    char* wbase = e->arena + e->weights_off;
+    e->steps.resize(n_ops);
+    for (int i = 0; i < n_ops; ++i, p += kOpWords) {
+        Step& s = e->steps[i];
+        s.op = p[0];
+        for (int k = 0; k < kOpWords - 1; ++k) s.a[k] = p[1 + k];
+        const int* a = s.a;
+        auto buf_ok = [&](int id) { return id >= 0 && id < n_bufs; };
+        if (s.op == OP_STEM) {
+            if (i != 0 || !buf_ok(a[0])) { b2_set_error("engine_create: stem must be op 0 with a valid buffer"); return fail(B2_ERR_ARG); }
+        } else if (s.op == OP_CONV) {
+            if (!buf_ok(a[0]) || !buf_ok(a[3]) || (a[9] >= 0 && !buf_ok(a[9]))) { b2_set_error("engine_create: op %d: bad buffer id", i); return fail(B2_ERR_ARG); }
+            const Buf& bi = e->bufs[a[0]]; const Buf& bo = e->bufs[a[3]];
+            s.conv.resize(b2_conv_launch_size() + 64);
+            rc = b2_conv_prepare(s.conv_ptr(), e->buf_ptr(a[0]), B, bi.h, bi.w, bi.c, a[1], a[2],
+                                 wbase + (size_t)(uint32_t)a[11], (const float*)(wbase + (size_t)(uint32_t)a[12]), a[5], a[6], a[7], a[8],
+                                 e->buf_ptr(a[3]), bo.c, a[4], a[9] >= 0 ? e->buf_ptr(a[9]) : nullptr,
+                                 a[9] >= 0 ? e->bufs[a[9]].c : 0, a[10]);
+            if (rc != B2_OK) return fail(rc);
+            const int pad = a[6] / 2, ho = (bi.h + 2 * pad - a[6]) / a[7] + 1, wo = (bi.w + 2 * pad - a[6]) / a[7] + 1;
+            if (ho != bo.h || wo != bo.w || a[4] + a[5] > bo.c || a[1] + a[2] > bi.c) {
+                b2_set_error("engine_create: op %d: conv geometry does not match its buffers", i); return fail(B2_ERR_ARG);
+            }
+        } else if (s.op == OP_POOL) {
+            if (!buf_ok(a[0])) { b2_set_error("engine_create: op %d: bad buffer id", i); return fail(B2_ERR_ARG); }
+        } else if (s.op == OP_UP) {
+            if (!buf_ok(a[0]) || !buf_ok(a[4])) { b2_set_error("engine_create: op %d: bad buffer id", i); return fail(B2_ERR_ARG); }
+        } else { b2_set_error("engine_create: op %d: unknown opcode %d", i, s.op); return fail(B2_ERR_ARG); }
+    }
+    e->n_launch = n_ops;
+    *out = e;
+    return B2_OK;
+}
+
+extern "C" int b2_engine_destroy(b2_engine_t* e) {
+    if (!e) return B2_OK;
+    if (e->graph) cudaGraphExecDestroy(e->graph);
+    cudaFree(e->arena);
+    delete e;
+    return B2_OK;
+}
+
+static int run_tail(b2_engine* e, cudaStream_t st) {
+    if (e->use_graph) {
+        if (!e->graph) {
+            cudaGraph_t g = nullptr;
+            B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = B2_OK;
+            for (size_t i = 1; i < e->steps.size() && rc == B2_OK; ++i) rc = run_step(e, e->steps[i], st);
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc != B2_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            B2_CUDA(ce);
+            ce = cudaGraphInstantiate(&e->graph, g, 0);
+            cudaGraphDestroy(g);
+            B2_CUDA(ce);
+        } else {
+            b2_count_launch((int)e->steps.size() - 1);
+        }
+        B2_CUDA(cudaGraphLaunch(e->graph, st));
+        return B2_OK;
+    }
+    for (size_t i = 1; i < e->steps.size(); ++i) {
+        int rc = run_step(e, e->steps[i], st);
+        if (rc != B2_OK) return rc;
+    }
+    return B2_OK;
+}
+
+extern "C" int b2_engine_forward_u8(b2_engine_t* e, const uint8_t* frames, int src_h, int src_w, int pad_top, int pad_left, void* stream) {
+    B2_REQUIRE(e && frames, "engine_forward: null pointer");
+    const int* a = e->steps[0].a;
+    char* wbase = e->arena + e->weights_off;
+    const Buf& bo = e->bufs[a[0]];
+    int rc = b2_stem_u8(frames, e->B, src_h, src_w, e->H, e->W, pad_top, pad_left, (const float*)(wbase + (size_t)(uint32_t)a[3]),
+                        (const float*)(wbase + (size_t)(uint32_t)a[4]), a[2], e->buf_ptr(a[0]), bo.c, a[1], stream);
+    if (rc != B2_OK) return rc;
+    return run_tail(e, (cudaStream_t)stream);
+}
+
+extern "C" int b2_engine_forward_f32(b2_engine_t* e, const void* bchw, int dtype, void* stream) {
+    B2_REQUIRE(e && bchw, "engine_forward: null pointer");
+    const int* a = e->steps[0].a;
+    char* wbase = e->arena + e->weights_off;
+    const Buf& bo = e->bufs[a[0]];
+    int rc = b2_stem_f32(bchw, dtype, e->B, e->H, e->W, (const float*)(wbase + (size_t)(uint32_t)a[3]),
+                         (const float*)(wbase + (size_t)(uint32_t)a[4]), a[2], e->buf_ptr(a[0]), bo.c, a[1], stream);
+    if (rc != B2_OK) return rc;
+    return run_tail(e, (cudaStream_t)stream);
+}
+
+extern "C" int b2_engine_levels(b2_engine_t* e, int* n_levels, const void** logits, int* h, int* w, int* stride, int* lstride) {
+    B2_REQUIRE(e && n_levels, "engine_levels: null pointer");
+    *n_levels = e->n_levels;
+    for (int l = 0; l < e->n_levels; ++l) {
+        const Buf& b = e->bufs[e->level_buf[l]];
+        if (logits) logits[l] = e->buf_ptr(e->level_buf[l]);
+        if (h) h[l] = b.h;
+        if (w) w[l] = b.w;
+        if (stride) stride[l] = e->level_stride[l];
+    }
+    if (lstride) *lstride = e->lstride;
+    return B2_OK;
+}
+
+extern "C" int b2_engine_buffer(b2_engine_t* e, int buf, const void** ptr, int* h, int* w, int* c) {
+    B2_REQUIRE(e && buf >= 0 && buf < (int)e->bufs.size(), "engine_buffer: bad buffer id %d", buf);
+    if (ptr) *ptr = e->buf_ptr(buf);
+    if (h) *h = e->bufs[buf].h;
+    if (w) *w = e->bufs[buf].w;
+    if (c) *c = e->bufs[buf].c;
+    return B2_OK;
+}
+
+extern "C" size_t b2_engine_arena_bytes(b2_engine_t* e) { return e ? e->arena_bytes : 0; }
+extern "C" int b2_engine_num_launches(b2_engine_t* e) { return e ? e->n_launch : 0; }
+extern "C" int b2_engine_use_graph(b2_engine_t* e, int on) {
+    B2_REQUIRE(e, "engine_use_graph: null handle");
+    e->use_graph = on != 0;
+    return B2_OK;
+}
