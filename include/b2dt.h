@@ -95,6 +95,12 @@ int b2_decode(const void* const* level_logits, const int* level_h, const int* le
               int n_levels, int B, int nc, int lstride, float conf, const uint8_t* classes_mask,
               float* cand, int32_t* cand_idx, int32_t* cand_count, int cand_cap, float* dense_out, void* stream);
 
+/* Candidate stage of non_max_suppression for callers that hold the reference-shaped dense tensor
+ * pred (B, no = 4+nc(+extra), A) fp32 [cx,cy,w,h,scores...] (utils/nms.py:74 `amax > conf`, :85-87 xywh2xyxy,
+ * :111-113 best class, :120-124 classes filter).  Same candidate layout as b2_decode. */
+int b2_candidates_from_dense(const float* pred, int B, int nc, int no, int A, float conf, const uint8_t* classes_mask,
+                             float* cand, int32_t* cand_idx, int32_t* cand_count, int cand_cap, void* stream);
+
 /* non_max_suppression tail + scale_boxes/clip_boxes (utils/nms.py:129-160; torchvision.ops.nms or
  * TorchNMS.nms :237-304; utils/ops.py:105-138,157-183).  Per image: sort candidates by (score desc,
  * anchor asc), cap at max_nms, greedy NMS on class-offset fp32 boxes (cls*max_wh unless agnostic),
@@ -154,7 +160,8 @@ int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_cols, const in
                       float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, void* stream);
 /* Host-side inspection (synchronises): dense state of one stream.  x: [cap][8], P: [cap][64] (dense 8x8
  * rebuilt from the decoupled blocks), meta: [cap][8] int32 {id, age, hits, hit_streak, tsu, lost_frames, is_lost, n_vel},
- * stats: [6] int64 {created, terminated, active, long_term_predictions, recoveries, frame_count}. */
+ * stats: [8] int64 {created, terminated, active, long_term_predictions, recoveries, frame_count, next_track_id,
+ * dropped (detections that found no free slot)}.  Any of the host pointers may be NULL. */
 int b2_tracker_export(b2_tracker_t* t, int stream_idx, float* x_host, float* P_host, int32_t* meta_host,
                       int32_t* n_tracks_host, long long* stats_host);
 /* bytes of bank state read+written per live track by one predict / one update (for roofline accounting) */

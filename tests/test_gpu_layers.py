@@ -1,0 +1,164 @@
+"""GPU parity of the layer kernels (through the C ABI) against the numpy oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+import b200dt  # noqa: F401
+from b200dt import weights
+from oracle import net as onet
+from oracle import postprocess as pp
+
+pytestmark = pytest.mark.gpu
+
+
+def _t():
+    import torch
+
+    return torch
+
+
+def _bf16_tensor(a):
+    """numpy fp32 (already bf16-representable) NHWC -> CUDA bf16 tensor."""
+    torch = _t()
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda().to(torch.bfloat16)
+
+
+def _rand_bf16(g, shape, scale=1.0):
+    return onet.bf16_round((g.standard_normal(shape) * scale).astype(np.float32))
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, s, act, residual
+    (1, 16, 16, 16, 16, 1, 1, True, False),
+    (2, 24, 40, 32, 64, 3, 1, True, False),
+    (1, 20, 12, 64, 80, 3, 1, True, True),
+    (2, 17, 23, 48, 32, 3, 1, True, False),       # ragged spatial size, BK=16 chunks
+    (1, 32, 48, 64, 128, 3, 2, True, False),      # stride 2, even size
+    (2, 15, 21, 32, 48, 3, 2, True, False),       # stride 2, odd size
+    (1, 8, 8, 256, 512, 1, 1, True, False),       # two N tiles
+    (1, 12, 20, 128, 64, 1, 1, False, False),     # plain conv (Detect output), no activation
+    (1, 10, 10, 80, 1, 1, 1, False, False),       # nc = 1 output
+    (3, 6, 10, 96, 144, 1, 1, True, False),
+    (1, 40, 40, 16, 32, 3, 1, True, True),
+    (1, 64, 64, 192, 96, 1, 1, True, False),      # K = 3 chunks of 64
+    (4, 5, 7, 160, 160, 3, 1, True, False),       # x-scale widths, tiny maps, several images per tile
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_matches_oracle(case):
+    from b200dt import ops
+
+    torch = _t()
+    B, H, W, Cin, Cout, k, s, act, res = case
+    g = np.random.default_rng(hash(case) % (2 ** 31))
+    x = _rand_bf16(g, (B, H, W, Cin))
+    w = _rand_bf16(g, (Cout, Cin, k, k), 1.0 / np.sqrt(Cin * k * k))
+    b = g.standard_normal(Cout).astype(np.float32) * 0.1
+    ref = onet.conv2d(x.transpose(0, 3, 1, 2), w, b, s, k // 2)
+    if act:
+        ref = onet.silu(ref)
+    r = None
+    if res:
+        r = _rand_bf16(g, ref.transpose(0, 2, 3, 1).shape)
+        ref = ref + r.transpose(0, 3, 1, 2)
+    y = ops.conv2d_bf16(_bf16_tensor(x), _bf16_tensor(weights.pack_ohwi(w)), torch.from_numpy(b).cuda(), k, s, act,
+                        residual=_bf16_tensor(r) if res else None)
+    torch.cuda.synchronize()
+    got = y.float().cpu().numpy().transpose(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    # one bf16 rounding of the output (2^-9 relative) + fp32 accumulation-order noise
+    np.testing.assert_allclose(got, ref, rtol=6e-3, atol=6e-3)
+
+
+def test_conv_channel_slices_and_strides():
+    """Concat-by-offset: read a channel slice of a wider buffer, write into a slice of another, residual from a third."""
+    from b200dt import ops
+
+    torch = _t()
+    g = np.random.default_rng(5)
+    B, H, W = 2, 12, 20
+    xin = _rand_bf16(g, (B, H, W, 96))
+    w = _rand_bf16(g, (32, 32, 3, 3), 1 / 17.0)
+    b = g.standard_normal(32).astype(np.float32) * 0.1
+    out = _bf16_tensor(np.full((B, H, W, 128), 7.0, np.float32))
+    ops.conv2d_bf16(_bf16_tensor(xin), _bf16_tensor(weights.pack_ohwi(w)), torch.from_numpy(b).cuda(), 3, 1, True,
+                    out=out, out_coff=64, in_coff=32, cin=32, residual=_bf16_tensor(xin), res_coff=64)
+    torch.cuda.synchronize()
+    got = out.float().cpu().numpy()
+    ref = onet.silu(onet.conv2d(xin[..., 32:64].transpose(0, 3, 1, 2), w, b, 1, 1)) + xin[..., 64:96].transpose(0, 3, 1, 2)
+    np.testing.assert_allclose(got[..., 64:96].transpose(0, 3, 1, 2), ref, rtol=6e-3, atol=6e-3)
+    assert np.all(got[..., :64] == 7.0) and np.all(got[..., 96:] == 7.0)      # neighbours untouched
+
+
+def test_conv_rejects_bad_arguments():
+    from b200dt import ops
+
+    torch = _t()
+    x = torch.zeros((1, 8, 8, 24), dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros((16, 1, 1, 24), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        ops.conv2d_bf16(x, w, torch.zeros(16, device="cuda"), 1)            # Cin % 16 != 0
+    x = torch.zeros((1, 8, 8, 32), dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros((16, 5, 5, 32), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        ops.conv2d_bf16(x, w, torch.zeros(16, device="cuda"), 5)            # k = 5 unsupported
+
+
+@pytest.mark.parametrize("hw,src,pad", [((64, 96), (64, 96), (0, 0)), ((64, 96), (52, 96), (6, 0)), ((32, 64), (32, 50), (0, 7))])
+def test_stem_u8_matches_oracle(hw, src, pad):
+    """Letterbox pad (114) + BGR->RGB + /255 + Conv(3->C0, k3, s2) + SiLU on raw uint8 frames."""
+    from b200dt import ops
+
+    torch = _t()
+    g = np.random.default_rng(2)
+    H, W = hw
+    frames = g.integers(0, 256, (2, src[0], src[1], 3), dtype=np.uint8)
+    C0 = 16
+    w = (g.standard_normal((C0, 3, 3, 3)) / 3.0).astype(np.float32)
+    b = (0.1 * g.standard_normal(C0)).astype(np.float32)
+    canvas = np.full((2, H, W, 3), 114, np.uint8)
+    canvas[:, pad[0]:pad[0] + src[0], pad[1]:pad[1] + src[1]] = frames
+    x = pp.preprocess(list(canvas))
+    ref = onet.bf16_round(onet.silu(onet.conv2d(x, w, b, 2, 1)))
+    y = ops.stem_u8(torch.from_numpy(frames).cuda(), torch.from_numpy(weights.pack_ohwi(w)).cuda(), torch.from_numpy(b).cuda(),
+                    H, W, pad[0], pad[1])
+    got = y.float().cpu().numpy().transpose(0, 3, 1, 2)
+    np.testing.assert_allclose(got, ref, rtol=8e-3, atol=2e-3)
+    # stand-alone preprocess (BasePredictor.preprocess): exact
+    p = ops.preprocess_u8(torch.from_numpy(frames).cuda(), H, W, pad[0], pad[1]).cpu().numpy()
+    np.testing.assert_allclose(p, x, rtol=0, atol=1e-7)
+
+
+def test_sppf_pool_and_upsample_exact():
+    from b200dt import ops
+
+    g = np.random.default_rng(3)
+    B, H, W, C = 2, 9, 13, 16
+    x = _rand_bf16(g, (B, H, W, C))
+    buf = np.zeros((B, H, W, 4 * C), np.float32)
+    buf[..., :C] = x
+    t = ops.sppf_pool(_bf16_tensor(buf), 0, C)
+    got = t.float().cpu().numpy()
+    y = x.transpose(0, 3, 1, 2)
+    for j in range(1, 4):
+        y = onet.maxpool5(y)
+        np.testing.assert_array_equal(got[..., j * C:(j + 1) * C].transpose(0, 3, 1, 2), y)
+    out = _bf16_tensor(np.zeros((B, 2 * H, 2 * W, 48), np.float32))
+    ops.upsample_slice(_bf16_tensor(x), out, 2, out_coff=32)
+    o = out.float().cpu().numpy()
+    np.testing.assert_array_equal(o[..., 32:].transpose(0, 3, 1, 2), onet.upsample2(x.transpose(0, 3, 1, 2)))
+    assert np.all(o[..., :32] == 0)
+
+
+def test_resize_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    from b200dt import ops
+
+    torch = _t()
+    g = np.random.default_rng(4)
+    for (sh, sw), (dh, dw) in [((512, 640), (1024, 1280)), ((480, 640), (384, 512)), ((100, 130), (197, 256))]:
+        img = g.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        got = ops.resize_bilinear_u8(torch.from_numpy(img[None]).cuda(), dh, dw)[0].cpu().numpy()
+        diff = np.abs(got.astype(int) - ref.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (diff.max(), (diff > 0).mean())

@@ -1,0 +1,168 @@
+"""CPU-only checks of the host logic: the C-ABI library builds, loads and exports every symbol the header
+declares; the graph lowering is self-consistent; letterbox / scale geometry matches the oracle; stream
+sharding and the result gather work over a world_size-2 gloo group.  No compute entry point is called."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import b200dt  # noqa: F401
+from b200dt import _lib, cfg, engine, pipeline, predictor, tracker, weights
+from oracle import postprocess as pp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b2dt.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()                      # builds with nvcc (sm_100a cross-compile) if the .so is missing
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.b2_version() >= 100
+    assert lib.b2_launch_count() == 0      # nothing was launched: no GPU here
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma():
+    """SASS evidence (B200_PROFILING.md): UTC*MMA = tcgen05.mma, UTMALDG = TMA tensor loads, LDTM = tcgen05.ld."""
+    r = subprocess.run(["cuobjdump", "-sass", "-arch", "sm_100a", _lib.lib_path()], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "UTCHMMA" in r.stdout or "UTCMMA" in r.stdout
+    assert "UTMALDG" in r.stdout and "LDTM" in r.stdout
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        predictor.YOLO("yolov8n-p2.yaml")
+    with pytest.raises(RuntimeError):
+        tracker.EnhancedMultiTargetTracker()
+
+
+@pytest.mark.parametrize("name,hw", [("yolov8n-p2", (512, 640)), ("yolov8s-p2", (640, 640)), ("yolov8x-p2", (128, 160))])
+def test_lowering_is_consistent(name, hw):
+    spec = cfg.resolve(name)
+    sd = weights.synthetic_state_dict(spec, seed=0, calib=None)
+    P = engine.lower(spec, sd, *hw)
+    words = P.words()
+    assert words[0] == engine.MAGIC and len(words) == 6 + 3 * len(P.bufs) + 2 * len(P.levels) + engine.OP_WORDS * len(P.ops)
+    assert P.flops == cfg.conv_flops(spec, *hw)                       # SURVEY.md 8d algorithmic FLOPs
+    n_convs = sum(1 for o in P.ops if o[0] == engine.OP_CONV) + 1       # + stem
+    assert n_convs == len(cfg.conv_list(spec))
+    assert [s for _, s in P.levels] == [4, 8, 16, 32]
+    written = {}
+    for o in P.ops:
+        if o[0] == engine.OP_CONV:
+            _, ib, ioff, cin, ob, ooff, cout, k, s, act, rb, roff, woff, boff = o
+            assert ioff + cin <= P.bufs[ib][2] and ooff + cout <= P.bufs[ob][2]
+            assert cin % 16 == 0 and ioff % 8 == 0 and ooff % 8 == 0
+            assert woff % 256 == 0 and boff % 256 == 0
+            # every input channel was produced by an earlier op
+            assert all(c in written.get(ib, set()) for c in (ioff, ioff + cin - 1)), o
+            written.setdefault(ob, set()).update(range(ooff, ooff + cout))
+        elif o[0] == engine.OP_STEM:
+            written.setdefault(o[1], set()).update(range(o[2], o[2] + o[3]))
+        elif o[0] == engine.OP_POOL:
+            written.setdefault(o[1], set()).update(range(o[2] + o[3], o[2] + 4 * o[3]))
+        elif o[0] == engine.OP_UP:
+            written.setdefault(o[5], set()).update(range(o[6], o[6] + o[3]))
+    # weights: bf16 OHWI with BN folded
+    pfx = "model.1"
+    w, b = weights.fold_conv_bn(sd, pfx)
+    op = next(o for o in P.ops if o[0] == engine.OP_CONV)
+    blob = P.blob.bytes()
+    got = np.frombuffer(blob, np.uint16, count=w.size, offset=op[12])
+    np.testing.assert_array_equal(got, weights.f32_to_bf16_bits(weights.pack_ohwi(w)).ravel())
+    np.testing.assert_array_equal(np.frombuffer(blob, np.float32, count=b.size, offset=op[13]), b)
+
+
+def test_unsupported_widths_are_rejected():
+    spec = cfg.resolve("yolov8-small")          # scale n: C2f hidden width 12 is not a multiple of 16
+    sd = weights.synthetic_state_dict(spec, seed=0, calib=None)
+    with pytest.raises(NotImplementedError):
+        engine.lower(spec, sd, 64, 64)
+
+
+@pytest.mark.parametrize("h0,w0,imgsz,auto", [(512, 640, 640, True), (500, 640, 640, True), (480, 640, 640, True),
+                                                (512, 640, 1280, True), (300, 500, 640, False), (1080, 1920, 640, True)])
+def test_letterbox_and_scale_geometry_match_oracle(h0, w0, imgsz, auto):
+    (rh, rw), (H, W), top, left = predictor.letterbox_geometry(h0, w0, predictor.check_imgsz(imgsz), auto)
+    r, new_unpad, t, b, l, rr = pp.letterbox_geometry(h0, w0, (imgsz, imgsz), auto, 32)
+    assert (rw, rh) == new_unpad and (top, left) == (t, l) and (H, W) == (rh + t + b, rw + l + rr)
+    gain, px, py, ow, oh = predictor.scale_params((H, W), (h0, w0))
+    boxes = np.array([[10.0, 20.0, 300.0, 400.0], [-5.0, 3.0, 5000.0, 9.0]], np.float32)
+    ref = pp.scale_boxes((H, W), boxes, (h0, w0))
+    got = boxes.copy()
+    got[:, [0, 2]] = np.clip((got[:, [0, 2]] - np.float32(px)) / np.float32(gain), 0, ow)
+    got[:, [1, 3]] = np.clip((got[:, [1, 3]] - np.float32(py)) / np.float32(gain), 0, oh)
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_rows_to_dicts_and_boxes_api():
+    rows = np.zeros((2, _lib.TRACK_COLS), np.float32)
+    ir = rows.view(np.int32)
+    ir[0, 0], ir[1, 0] = 7, 3
+    rows[0, 1:5] = [1, 2, 3, 4]
+    ir[0, 6] = 1
+    ir[0, 10] = ir[0, 11] = 4
+    ir[0, 12] = 1
+    d = tracker.rows_to_dicts(rows)
+    assert [t["track_id"] for t in d] == ["T003", "T007"]
+    assert d[1]["status"] == "predicted" and d[1]["lost_frames"] == 4 and d[1]["is_lost"] is True
+    assert d[0]["status"] == "detected" and d[1]["bbox"].tolist() == [1, 2, 3, 4]
+    b = predictor.Boxes(np.array([[0, 0, 10, 20, 0.9, 2.0], [5, 5, 15, 25, 0.8, 1.0]], np.float32), (100, 200))
+    assert len(b) == 2 and b.id is None and b.cls.tolist() == [2.0, 1.0] and b.xywh[0].tolist() == [5, 10, 10, 20]
+    np.testing.assert_allclose(b.xyxyn[1], [5 / 200, 5 / 100, 15 / 200, 25 / 100])
+    r = predictor.Results(np.zeros((100, 200, 3), np.uint8), "image0.jpg", {0: "0", 1: "1", 2: "2"}, b.data)
+    assert r.orig_shape == (100, 200) and len(r) == 2 and "1 1, 1 2" in r.verbose().replace("s,", ",")
+    r.update(boxes=np.array([[0, 0, 10, 20, 5, 0.9, 2.0]], np.float32))
+    assert r.boxes.is_track and r.boxes.id.tolist() == [5.0]
+
+
+def test_shard_streams_partitions_exactly():
+    for n, w in [(256, 1), (256, 8), (10, 4), (3, 8)]:
+        parts = [pipeline.shard_streams(n, r, w) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+import b200dt
+from b200dt import pipeline
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+mine = pipeline.shard_streams(6, rank, 2)
+rows = torch.zeros((len(mine), 4, 20)); counts = torch.zeros((len(mine),), dtype=torch.int32)
+for j, s in enumerate(mine):
+    rows[j, :, 0] = s; counts[j] = s + 1
+ra, ca = pipeline.gather_results(rows, counts)
+allc = torch.cat(ca).tolist(); allr = torch.cat(ra)[:, 0, 0].tolist()
+assert allc == [1, 2, 3, 4, 5, 6] and allr == [0., 1., 2., 3., 4., 5.], (allc, allr)
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_result_gather_over_gloo_world_size_2(tmp_path):
+    import socket
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b2_sppf_pool": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "b2_upsample_slice": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "b2_decode": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int, _P, _P]),
+    "b2_candidates_from_dense": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int, _P]),
     "b2_nms": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_int, c_int, c_int, c_float, c_int,
                        c_float, c_float, c_float, c_float, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "b2_nms_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
             const int ci = ck * 8 + i;
             if (ci < p.nc) {
                 if (p.dense && active) p.dense[dense_base + (size_t)(4 + ci) * p.A] = 1.f / (1.f + __expf(-c[i]));
-                const bool allowed = !p.cmask || p.cmask[ci];
-                if (allowed && (c[i] > best)) { best = c[i]; bidx = ci; }
+                if (c[i] > best) { best = c[i]; bidx = ci; }
             }
         }
     }
@@ -103,7 +102,8 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     if (p.dense && active && sub < 4) p.dense[dense_base + (size_t)sub * p.A] = sub == 0 ? cx : sub == 1 ? cy : sub == 2 ? bw : bh;
 
     const float score = 1.f / (1.f + __expf(-best));
-    const bool is_cand = active && sub == 0 && bidx != 0x7fffffff && score > p.conf;
+    // best class over ALL classes first, then the `classes=` filter drops the anchor (nms.py:111-124)
+    const bool is_cand = active && sub == 0 && bidx != 0x7fffffff && score > p.conf && (!p.cmask || p.cmask[bidx]);
     const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
     if (ball) {
         int base = 0;
@@ -118,6 +118,39 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
                 o[0] = cx - hw; o[1] = cy - hh; o[2] = cx + hw; o[3] = cy + hh; o[4] = score; o[5] = (float)bidx;
                 p.cand_idx[(size_t)b * p.cand_cap + pos] = a;
             }
+        }
+    }
+}
+
+// Candidate extraction from the reference-shaped dense tensor (B, 4+nc, A) [cx,cy,w,h,scores...] fp32:
+// nms.py:74 (amax > conf), :85-87 (xywh2xyxy), :111-113 (best class), :120-124 (classes filter).
+// One thread per anchor; the class loop reads pred[b][4+c][a], coalesced across the warp.
+__global__ void __launch_bounds__(256) dense_candidates_kernel(const float* __restrict__ pred, int nc, int no, int A, float conf,
+                                                               const uint8_t* __restrict__ cmask, float* __restrict__ cand,
+                                                               int32_t* __restrict__ cand_idx, int32_t* __restrict__ cand_count, int cand_cap) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, lane = threadIdx.x & 31;
+    const float* base = pred + (size_t)b * no * A;
+    float best = -INFINITY; int bidx = -1;
+    if (a < A) {
+        for (int c = 0; c < nc; ++c) {
+            const float v = __ldg(base + (size_t)(4 + c) * A + a);
+            if (v > best) { best = v; bidx = c; }
+        }
+    }
+    const bool is_cand = a < A && bidx >= 0 && best > conf && (!cmask || cmask[bidx]);
+    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+    if (!ball) return;
+    int pos0 = 0;
+    const int leader = __ffs(ball) - 1;
+    if (lane == leader) pos0 = atomicAdd(cand_count + b, __popc(ball));
+    pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+    if (is_cand) {
+        const int pos = pos0 + __popc(ball & ((1u << lane) - 1));
+        if (pos < cand_cap) {
+            const float cx = base[a], cy = base[(size_t)A + a], hw = base[(size_t)2 * A + a] / 2.f, hh = base[(size_t)3 * A + a] / 2.f;
+            float* o = cand + ((size_t)b * cand_cap + pos) * 6;
+            o[0] = cx - hw; o[1] = cy - hh; o[2] = cx + hw; o[3] = cy + hh; o[4] = best; o[5] = (float)bidx;
+            cand_idx[(size_t)b * cand_cap + pos] = a;
         }
     }
 }
@@ -299,6 +332,18 @@ extern "C" int b2_decode(const void* const* level_logits, const int* level_h, co
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
     dim3 grid(b2_ceil_div(p.A * 8, 256), B);
     decode_kernel<<<grid, 256, 0, st>>>(p);
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch(1);
+    return B2_OK;
+}
+
+extern "C" int b2_candidates_from_dense(const float* pred, int B, int nc, int no, int A, float conf, const uint8_t* classes_mask,
+                                        float* cand, int32_t* cand_idx, int32_t* cand_count, int cand_cap, void* stream) {
+    B2_REQUIRE(pred && cand && cand_idx && cand_count, "candidates: null pointer");
+    B2_REQUIRE(B >= 1 && nc >= 1 && no >= 4 + nc && A >= 1 && cand_cap >= 1, "candidates: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
+    dense_candidates_kernel<<<dim3(b2_ceil_div(A, 256), B), 256, 0, st>>>(pred, nc, no, A, conf, classes_mask, cand, cand_idx, cand_count, cand_cap);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;

@@ -570,26 +570,31 @@ extern "C" int b2_tracker_export(b2_tracker_t* t, int stream_idx, float* x_host,
                                  int32_t* n_tracks_host, long long* stats_host) {
     B2_REQUIRE(t && stream_idx >= 0 && stream_idx < t->impl.b.S, "tracker_export: bad stream index");
     const Bank& b = t->impl.b;
-    float *dx, *dP; int32_t *dm, *dn;
-    B2_CUDA(cudaMalloc(&dx, (size_t)b.C * 8 * 4)); B2_CUDA(cudaMalloc(&dP, (size_t)b.C * 64 * 4));
-    B2_CUDA(cudaMalloc(&dm, (size_t)b.C * 8 * 4)); B2_CUDA(cudaMalloc(&dn, 4));
-    export_kernel<<<1, 256>>>(b, stream_idx, dx, dP, dm, dn);
-    b2_count_launch(1);
-    int n = 0;
-    B2_CUDA(cudaMemcpy(&n, dn, 4, cudaMemcpyDeviceToHost));
-    if (x_host) B2_CUDA(cudaMemcpy(x_host, dx, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
-    if (P_host) B2_CUDA(cudaMemcpy(P_host, dP, (size_t)n * 64 * 4, cudaMemcpyDeviceToHost));
-    if (meta_host) B2_CUDA(cudaMemcpy(meta_host, dm, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
-    if (n_tracks_host) *n_tracks_host = n;
+    B2_CUDA(cudaDeviceSynchronize());
+    if (x_host || P_host || meta_host || n_tracks_host) {
+        float *dx = nullptr, *dP = nullptr; int32_t *dm = nullptr, *dn = nullptr;
+        B2_CUDA(cudaMalloc(&dx, (size_t)b.C * 8 * 4)); B2_CUDA(cudaMalloc(&dP, (size_t)b.C * 64 * 4));
+        B2_CUDA(cudaMalloc(&dm, (size_t)b.C * 8 * 4)); B2_CUDA(cudaMalloc(&dn, 4));
+        export_kernel<<<1, 256>>>(b, stream_idx, dx, dP, dm, dn);
+        b2_count_launch(1);
+        int n = 0;
+        cudaError_t e = cudaMemcpy(&n, dn, 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && x_host) e = cudaMemcpy(x_host, dx, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && P_host) e = cudaMemcpy(P_host, dP, (size_t)n * 64 * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && meta_host) e = cudaMemcpy(meta_host, dm, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost);
+        cudaFree(dx); cudaFree(dP); cudaFree(dm); cudaFree(dn);
+        B2_CUDA(e);
+        if (n_tracks_host) *n_tracks_host = n;
+    }
     if (stats_host) {
         long long st[8];
         B2_CUDA(cudaMemcpy(st, b.stats + (size_t)stream_idx * 8, sizeof(st), cudaMemcpyDeviceToHost));
-        int32_t fc = 0;
+        int32_t fc = 0, nid = 0;
         B2_CUDA(cudaMemcpy(&fc, b.frame_count + stream_idx, 4, cudaMemcpyDeviceToHost));
+        B2_CUDA(cudaMemcpy(&nid, b.next_id + stream_idx, 4, cudaMemcpyDeviceToHost));
         for (int k = 0; k < 5; ++k) stats_host[k] = st[k];
-        stats_host[5] = fc;
+        stats_host[5] = fc; stats_host[6] = nid; stats_host[7] = st[5];
     }
-    cudaFree(dx); cudaFree(dP); cudaFree(dm); cudaFree(dn);
     return B2_OK;
 }
 

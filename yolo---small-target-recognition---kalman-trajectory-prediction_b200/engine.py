@@ -1,0 +1,326 @@
+"""Lowering of the resolved YOLOv8-P2 graph to the launch plan executed by ``b2_engine_*`` (csrc/engine.cu).
+
+Host-side counterpart of ``BaseModel._predict_once`` (ultralytics/nn/tasks.py:159-188) plus
+``BaseModel.fuse`` (:224-254): the layer list of :func:`cfg.resolve` is flattened into a program over NHWC
+bf16 buffers in which every ``torch.cat`` / ``chunk`` of C2f (block.py:315-319), SPPF (:237-241),
+``Concat`` (conv.py:673-683) and Detect (head.py:116-121) is a channel offset:
+
+  * a ``Concat`` layer owns one buffer; its producers write straight into their channel slice
+    (``nn.Upsample`` becomes the slice-writing copy kernel);
+  * a ``C2f`` owns a (2+n)*c buffer: ``cv1`` fills [0, 2c), bottleneck j reads slice 1+j and writes slice 2+j
+    (residual read from slice 1+j), ``cv2`` reads the whole buffer;
+  * ``SPPF`` owns a 4*c_ buffer filled by ``cv1`` and the pooling kernel;
+  * each Detect level owns a ``[B][h*w][64 + ceil8(nc)]`` logits buffer filled by ``cv2[l][2]`` / ``cv3[l][2]``.
+
+Plan layout (int32 words): ``[magic, n_bufs, n_ops, n_levels, nc, lstride]``, ``n_bufs x (h, w, c)``,
+``n_levels x (buf, stride)``, ``n_ops x 14`` (opcode + 13 arguments, see ``OP_*`` below).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, cfg, weights
+
+MAGIC = 0xB2D7
+OP_STEM, OP_CONV, OP_POOL, OP_UP = 1, 2, 3, 4
+OP_WORDS = 14
+ACT_NONE, ACT_SILU = 0, 1
+
+
+class _Blob:
+    """Weight blob builder: 256-byte aligned sections."""
+
+    def __init__(self):
+        self.parts, self.size = [], 0
+
+    def add(self, arr):
+        raw = np.ascontiguousarray(arr).tobytes()
+        off = self.size
+        pad = (-len(raw)) % 256
+        self.parts.append(raw + b"\0" * pad)
+        self.size += len(raw) + pad
+        return off
+
+    def bytes(self):
+        return b"".join(self.parts)
+
+
+class Plan:
+    """Result of :func:`lower`: the int32 program, the weight blob and where every tensor lives."""
+
+    def __init__(self):
+        self.bufs = []          # (h, w, c)
+        self.ops = []           # lists of OP_WORDS ints
+        self.levels = []        # (buf, stride)
+        self.loc = {}           # layer index -> (buf, coff, C)
+        self.named = {}         # module path (e.g. 'model.2.m.0.cv1') -> (buf, coff, C)
+        self.blob = _Blob()
+        self.nc = 0
+        self.lstride = 0
+        self.flops = 0
+
+    def new_buf(self, h, w, c):
+        self.bufs.append((int(h), int(w), int(c)))
+        return len(self.bufs) - 1
+
+    def words(self):
+        head = [MAGIC, len(self.bufs), len(self.ops), len(self.levels), self.nc, self.lstride]
+        flat = head + [v for b in self.bufs for v in b] + [v for l in self.levels for v in l] + [v for o in self.ops for v in o]
+        return np.asarray(flat, dtype=np.int32)
+
+
+def _shapes(spec, H, W):
+    """(h, w) of every layer output for an H x W input."""
+    hw, cur = {}, (H, W)
+    for L in spec["layers"]:
+        f = L["f"]
+        f0 = f[0] if isinstance(f, tuple) else f
+        h, w = cur if f0 == -1 else hw[f0]
+        if L["type"] == "Conv":
+            p = L["k"] // 2
+            h, w = (h + 2 * p - L["k"]) // L["s"] + 1, (w + 2 * p - L["k"]) // L["s"] + 1
+        elif L["type"] == "Upsample":
+            h, w = 2 * h, 2 * w
+        hw[L["i"]] = (h, w)
+        cur = (h, w)
+    return hw
+
+
+def lower(spec, state_dict, H, W):
+    """Lower ``spec`` (from :func:`cfg.resolve`) with weights ``state_dict`` for an ``H x W`` letterboxed input."""
+    if H % 32 or W % 32:
+        raise ValueError(f"input size {H}x{W} must be a multiple of the maximum stride 32")
+    sd = state_dict
+    layers = spec["layers"]
+    hw = _shapes(spec, H, W)
+    P = Plan()
+    nc = spec["nc"]
+    P.nc = nc
+    P.lstride = 64 + ((nc + 7) // 8) * 8
+
+    def src(i, f):
+        return i - 1 if f == -1 else f
+
+    # ---- placement: which concat slice does each layer write into? ----
+    placement = {}
+    extra_copies = []                     # (layer, concat buffer slice) when a layer feeds a second Concat
+    for L in layers:
+        if L["type"] != "Concat":
+            continue
+        i = L["i"]
+        h, w = hw[i]
+        buf = P.new_buf(h, w, L["c_out"])
+        off = 0
+        for f in L["f"]:
+            s = src(i, f)
+            c = layers[s]["c_out"]
+            if s in placement:
+                extra_copies.append((s, (buf, off, c)))
+            else:
+                placement[s] = (buf, off, c)
+            off += c
+        P.loc[i] = (buf, 0, L["c_out"])
+
+    def out_loc(L):
+        i = L["i"]
+        if i in placement:
+            return placement[i]
+        h, w = hw[i]
+        return (P.new_buf(h, w, L["c_out"]), 0, L["c_out"])
+
+    def check_c(c, what):
+        if c % 16:
+            raise NotImplementedError(f"{what}: {c} channels -- the tcgen05 conv path needs multiples of 16")
+
+    def emit_conv(prefix, inp, out, k, s, bn, res=None):
+        """inp/out/res: (buf, coff, C)."""
+        w, b = weights.folded(sd, prefix, bn)
+        cout, cin = w.shape[0], w.shape[1]
+        assert cin == inp[2] and cout == out[2], (prefix, w.shape, inp, out)
+        check_c(cin, prefix + " input")
+        woff = P.blob.add(weights.f32_to_bf16_bits(weights.pack_ohwi(w)))
+        boff = P.blob.add(b.astype(np.float32))
+        hb, wb, _ = P.bufs[out[0]]
+        P.flops += 2 * hb * wb * cout * cin * k * k
+        P.ops.append([OP_CONV, inp[0], inp[1], cin, out[0], out[1], cout, k, s, ACT_SILU if bn else ACT_NONE,
+                      res[0] if res else -1, res[1] if res else 0, woff, boff])
+        P.named[prefix] = out
+
+    for L in layers:
+        i, t = L["i"], L["type"]
+        p = f"model.{i}"
+        h, w = hw[i]
+        if t == "Conv":
+            out = out_loc(L)
+            if i == 0:
+                if L["k"] != 3 or L["s"] != 2 or L["c1"] != 3:
+                    raise NotImplementedError("stem must be Conv(3 -> C0, k=3, s=2)")
+                wf, bf = weights.fold_conv_bn(sd, p)
+                woff = P.blob.add(weights.pack_ohwi(wf).astype(np.float32))     # [C0][kh][kw][rgb] fp32
+                boff = P.blob.add(bf.astype(np.float32))
+                P.flops += 2 * h * w * L["c2"] * 27
+                P.ops.append([OP_STEM, out[0], out[1], L["c2"], woff, boff] + [0] * (OP_WORDS - 6))
+                P.named[p] = out
+            else:
+                emit_conv(p, P.loc[src(i, L["f"])], out, L["k"], L["s"], True)
+            P.loc[i] = out
+        elif t == "C2f":
+            c, n = L["c"], L["n"]
+            check_c(c, p + " hidden")
+            inp = P.loc[src(i, L["f"])]
+            cat = P.new_buf(h, w, (2 + n) * c)
+            tmp = P.new_buf(h, w, c)
+            emit_conv(p + ".cv1", inp, (cat, 0, 2 * c), 1, 1, True)
+            for j in range(n):
+                a = (cat, (1 + j) * c, c)
+                emit_conv(f"{p}.m.{j}.cv1", a, (tmp, 0, c), 3, 1, True)
+                emit_conv(f"{p}.m.{j}.cv2", (tmp, 0, c), (cat, (2 + j) * c, c), 3, 1, True, res=a if L["shortcut"] else None)
+            out = out_loc(L)
+            emit_conv(p + ".cv2", (cat, 0, (2 + n) * c), out, 1, 1, True)
+            P.loc[i] = out
+        elif t == "SPPF":
+            if L["k"] != 5:
+                raise NotImplementedError("SPPF: only k=5")
+            c_ = L["c1"] // 2
+            inp = P.loc[src(i, L["f"])]
+            cat = P.new_buf(h, w, 4 * c_)
+            emit_conv(p + ".cv1", inp, (cat, 0, c_), 1, 1, True)
+            P.ops.append([OP_POOL, cat, 0, c_] + [0] * (OP_WORDS - 4))
+            out = out_loc(L)
+            emit_conv(p + ".cv2", (cat, 0, 4 * c_), out, 1, 1, True)
+            P.loc[i] = out
+        elif t == "Upsample":
+            inp = P.loc[src(i, L["f"])]
+            out = out_loc(L)
+            P.ops.append([OP_UP, inp[0], inp[1], inp[2], 2, out[0], out[1]] + [0] * (OP_WORDS - 7))
+            P.loc[i] = out
+        elif t == "Concat":
+            pass                                  # producers already wrote their slices
+        elif t == "Detect":
+            cb, cc = L["c2_box"], L["c3_cls"]
+            for l, f in enumerate(L["f"]):
+                inp = P.loc[f]
+                hh, ww = hw[f]
+                logits = P.new_buf(hh, ww, P.lstride)
+                t1, t2 = P.new_buf(hh, ww, cb), P.new_buf(hh, ww, cb)
+                emit_conv(f"{p}.cv2.{l}.0", inp, (t1, 0, cb), 3, 1, True)
+                emit_conv(f"{p}.cv2.{l}.1", (t1, 0, cb), (t2, 0, cb), 3, 1, True)
+                emit_conv(f"{p}.cv2.{l}.2", (t2, 0, cb), (logits, 0, 64), 1, 1, False)
+                u1, u2 = P.new_buf(hh, ww, cc), P.new_buf(hh, ww, cc)
+                emit_conv(f"{p}.cv3.{l}.0", inp, (u1, 0, cc), 3, 1, True)
+                emit_conv(f"{p}.cv3.{l}.1", (u1, 0, cc), (u2, 0, cc), 3, 1, True)
+                emit_conv(f"{p}.cv3.{l}.2", (u2, 0, cc), (logits, 64, nc), 1, 1, False)
+                P.levels.append((logits, H // hh))
+        else:
+            raise NotImplementedError(t)
+        # a layer that feeds more than one Concat: copy its slice into the others
+        for s_, dst in extra_copies:
+            if s_ == i:
+                o = P.loc[i]
+                P.ops.append([OP_UP, o[0], o[1], o[2], 1, dst[0], dst[1]] + [0] * (OP_WORDS - 7))
+    for o in P.ops:
+        assert len(o) == OP_WORDS, o
+    return P
+
+
+class Engine:
+    """One compiled forward for a fixed (batch, H, W): owns the device arena, weights and CUDA graph.
+
+    Stands where ``AutoBackend(model=nn.Module, fuse=True)`` stands in the reference
+    (ultralytics/nn/autobackend.py:196-219, :608-637).
+    """
+
+    def __init__(self, spec, state_dict, batch, H, W):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.spec, self.B, self.H, self.W = spec, int(batch), int(H), int(W)
+        self.plan = lower(spec, state_dict, H, W)
+        words = self.plan.words()
+        blob = self.plan.blob.bytes()
+        self._h = C.c_void_p()
+        rc = self.lib.b2_engine_create(words.ctypes.data_as(C.c_void_p), len(words), blob, len(blob),
+                                       self.B, self.H, self.W, C.byref(self._h))
+        _lib.check(rc)
+        n = C.c_int()
+        ptrs = (C.c_void_p * 8)()
+        hs, ws, ss = (C.c_int * 8)(), (C.c_int * 8)(), (C.c_int * 8)()
+        ls = C.c_int()
+        _lib.check(self.lib.b2_engine_levels(self._h, C.byref(n), ptrs, hs, ws, ss, C.byref(ls)))
+        self.n_levels, self.lstride, self.nc = n.value, ls.value, spec["nc"]
+        self.level_ptrs = [ptrs[i] for i in range(n.value)]
+        self.level_h = [hs[i] for i in range(n.value)]
+        self.level_w = [ws[i] for i in range(n.value)]
+        self.level_stride = [ss[i] for i in range(n.value)]
+        self.num_anchors = sum(h * w for h, w in zip(self.level_h, self.level_w))
+        self.flops_per_image = self.plan.flops
+        self.stride = max(self.level_stride)
+        self.names = spec["names"]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.b2_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def arena_bytes(self):
+        return self.lib.b2_engine_arena_bytes(self._h)
+
+    @property
+    def launches_per_forward(self):
+        return self.lib.b2_engine_num_launches(self._h)
+
+    def use_graph(self, on):
+        _lib.check(self.lib.b2_engine_use_graph(self._h, int(bool(on))))
+
+    def forward_u8(self, frames, pad_top=0, pad_left=0, stream=None):
+        """frames: CUDA uint8 tensor [B][h][w][3] BGR; letterboxed (border 114) into the H x W canvas."""
+        assert frames.is_cuda and frames.dtype.itemsize == 1 and frames.is_contiguous()
+        b, sh, sw, ch = frames.shape
+        if b != self.B or ch != 3:
+            raise ValueError(f"expected {self.B} BGR frames, got {tuple(frames.shape)}")
+        _lib.check(self.lib.b2_engine_forward_u8(self._h, _lib.ptr(frames), sh, sw, pad_top, pad_left, _lib.stream_ptr(stream)))
+
+    def forward_tensor(self, x, stream=None):
+        """x: CUDA float32 / bfloat16 tensor [B][3][H][W] RGB in [0, 1] (data/loaders.py:566-638 LoadTensor)."""
+        import torch
+
+        assert x.is_cuda and x.is_contiguous()
+        if tuple(x.shape) != (self.B, 3, self.H, self.W):
+            raise ValueError(f"expected {(self.B, 3, self.H, self.W)}, got {tuple(x.shape)}")
+        dt = {torch.float32: 0, torch.bfloat16: 1}.get(x.dtype)
+        if dt is None:
+            raise NotImplementedError(f"dtype {x.dtype}")
+        _lib.check(self.lib.b2_engine_forward_f32(self._h, _lib.ptr(x), dt, _lib.stream_ptr(stream)))
+
+    def buffer(self, buf):
+        """Debug/parity view of activation buffer ``buf`` as a torch bf16 tensor [B][h][w][c] (no copy)."""
+        p, h, w, c = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self.lib.b2_engine_buffer(self._h, buf, C.byref(p), C.byref(h), C.byref(w), C.byref(c)))
+        return _view_bf16(p.value, (self.B, h.value, w.value, c.value))
+
+    def activation(self, name):
+        """NCHW float32 copy of a named module output (e.g. ``'model.2.m.0.cv1'``) or layer index."""
+        buf, off, c = self.plan.named[name] if isinstance(name, str) else self.plan.loc[name]
+        return self.buffer(buf)[..., off:off + c].float().permute(0, 3, 1, 2).contiguous()
+
+    def level_logits(self, l):
+        """[B][h*w][lstride] bf16 view of Detect level ``l`` (64 DFL bins, then nc class logits)."""
+        return _view_bf16(self.level_ptrs[l], (self.B, self.level_h[l] * self.level_w[l], self.lstride))
+
+
+def _view_bf16(ptr, shape):
+    """Wrap library-owned device memory as a torch tensor via ``__cuda_array_interface__`` (uint16 -> bf16 view)."""
+    import torch
+
+    class _Mem:
+        pass
+
+    m = _Mem()
+    n = int(np.prod(shape))
+    m.__cuda_array_interface__ = {"shape": (n,), "typestr": "<u2", "data": (int(ptr), False), "version": 2}
+    t = torch.as_tensor(m, device="cuda")
+    return t.view(torch.bfloat16).view(*shape)

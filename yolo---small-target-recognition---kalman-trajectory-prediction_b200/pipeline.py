@@ -1,0 +1,95 @@
+"""The per-frame detect+track step for many concurrent video streams on one GPU, and its sharding over GPUs.
+
+This is the loop body of the project driver (kalman/aircraft_detection_tracking.py:88-109:
+``model(frame)`` -> ``boxes.xyxy/conf`` -> ``tracker.update(dets)``) for S streams at once:
+
+    uint8 frames [S][h][w][3] --stem+forward--> head logits --decode--> candidates --NMS+scale--> dets [S][300][6]
+        --Kalman bank (predict / associate / update / lifecycle)--> track rows [S][capacity][20]
+
+Everything between the frame upload and the result download stays on the GPU, on one CUDA stream, with no
+host synchronisation.  Streams are independent (one tracker per stream in the reference), so multi-GPU
+execution shards streams across ranks with no collective on the data path; NCCL only gathers results.
+"""
+from __future__ import annotations
+
+from . import _lib, cfg, weights
+from .predictor import DetectPipeline, letterbox_geometry
+from .tracker import TrackerBank
+
+
+def shard_streams(n_streams, rank, world_size):
+    """Contiguous block of stream ids owned by ``rank``."""
+    base, rem = divmod(n_streams, world_size)
+    lo = rank * base + min(rank, rem)
+    return list(range(lo, lo + base + (1 if rank < rem else 0)))
+
+
+class DetectTrackPipeline:
+    def __init__(self, model="yolov8s-p2", n_streams=1, frame_hw=(512, 640), imgsz=640, conf=0.15, iou=0.6, max_det=300,
+                 max_lost_frames=150, min_hits=1, iou_threshold=0.1, capacity=512, state_dict=None, seed=0, nc=None,
+                 nms_mode="exact"):
+        import torch
+
+        self.device = _lib.require_cuda()
+        self.spec = cfg.resolve(model, nc=nc)
+        sd = weights.to_numpy_state_dict(state_dict) if state_dict is not None else weights.synthetic_state_dict(self.spec, seed)
+        self.S = int(n_streams)
+        self.h0, self.w0 = frame_hw
+        isz = [imgsz, imgsz] if isinstance(imgsz, int) else list(imgsz)
+        (rh, rw), (self.H, self.W), self.top, self.left = letterbox_geometry(self.h0, self.w0, isz, auto=True)
+        if (rh, rw) != (self.h0, self.w0):
+            raise NotImplementedError("pipeline frames must not need a resize (use YOLO.predict for the general letterbox)")
+        self.conf, self.iou, self.nms_mode = float(conf), float(iou), nms_mode
+        self.detect = DetectPipeline(self.spec, sd, self.S, self.H, self.W, max_det)
+        self.bank = TrackerBank(self.S, capacity, max_det, max_lost_frames, min_hits, iou_threshold)
+        self.flops_per_frame = self.detect.engine.flops_per_image
+        # double-buffered staging for the host-facing path
+        self._copy_stream = torch.cuda.Stream()
+        self._dev_frames = [torch.empty((self.S, self.h0, self.w0, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self._ready = [torch.cuda.Event() for _ in range(2)]
+        self._consumed = [torch.cuda.Event() for _ in range(2)]
+        self._slot = 0
+        self.host_rows = torch.empty((self.S, capacity, _lib.TRACK_COLS), dtype=torch.float32).pin_memory()
+        self.host_counts = torch.empty((self.S,), dtype=torch.int32).pin_memory()
+        self.h2d_bytes_per_step = self.S * self.h0 * self.w0 * 3
+        self.d2h_bytes_per_step = self.host_rows.numel() * 4 + self.host_counts.numel() * 4
+
+    def step_device(self, frames_u8, with_trajectory=False, stream=None):
+        """frames_u8: CUDA uint8 [S][h][w][3] BGR.  Returns (track rows [S][capacity][20], counts [S]) on the GPU."""
+        dets, counts = self.detect(frames_u8, self.conf, self.iou, self.top, self.left, (self.h0, self.w0), None, False,
+                                   self.nms_mode, stream)
+        return self.bank.update(dets, counts, with_trajectory=with_trajectory, stream=stream)
+
+    def step_host(self, frames_pinned):
+        """frames_pinned: pinned host uint8 [S][h][w][3].  Upload on the copy stream (overlaps the previous step's
+        compute), run the step, download rows + counts into pinned host buffers.  Returns the host buffers
+        (valid after ``torch.cuda.current_stream().synchronize()``)."""
+        import torch
+
+        cur = torch.cuda.current_stream()
+        k = self._slot
+        self._slot ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed[k])          # the step that last read this buffer is done
+            self._dev_frames[k].copy_(frames_pinned, non_blocking=True)
+            self._ready[k].record(self._copy_stream)
+        cur.wait_event(self._ready[k])
+        rows, counts = self.step_device(self._dev_frames[k])
+        self._consumed[k].record(cur)
+        self.host_rows.copy_(rows, non_blocking=True)
+        self.host_counts.copy_(counts, non_blocking=True)
+        return self.host_rows, self.host_counts
+
+
+def gather_results(rows, counts, group=None):
+    """All-gather fixed-stride per-stream result blocks across ranks (the only collective of the pipeline;
+    off the data path).  rows: [S_local][capacity][20], counts: [S_local]; returns lists indexed by rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rows_all = [torch.empty_like(rows) for _ in range(world)]
+    counts_all = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(rows_all, rows.contiguous(), group=group)
+    dist.all_gather(counts_all, counts.contiguous(), group=group)
+    return rows_all, counts_all

@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference's detect API: ``YOLO(cfg).predict(source, ...) -> list[Results]``.
+
+Follows, for the detect path only,
+  Model.predict / __call__             ultralytics/engine/model.py:158-187, :498-557
+  BasePredictor.preprocess/inference   ultralytics/engine/predictor.py:152-204 (LetterBox, data/augment.py:1667-1743)
+  DetectionPredictor.postprocess       ultralytics/models/yolo/detect/predict.py:34-125
+  Results / Boxes                      ultralytics/engine/results.py:192-290, :855-1072
+with the three stages executed by the CUDA library: stem-fused preprocess + forward (engine), DFL decode
++ candidate filter, NMS + scale_boxes.  The reference package is not imported; INTEGRATION.md shows the
+``DetectionPredictor`` subclass a maintainer would register through ``model.predict(predictor=...)``.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+
+from . import _lib, cfg, ops, weights
+from .engine import Engine
+
+
+# ---------------------------------------------------------------------------------------------------
+# Results containers (engine/results.py)
+# ---------------------------------------------------------------------------------------------------
+class Boxes:
+    """Detection boxes: ``data`` is (n, 6) [x1, y1, x2, y2, conf, cls] or (n, 7) with a track id in column 4."""
+
+    def __init__(self, boxes, orig_shape):
+        if boxes.ndim == 1:
+            boxes = boxes[None, :]
+        n = boxes.shape[-1]
+        assert n in {6, 7}, f"expected 6 or 7 values but got {n}"
+        self.data = boxes
+        self.orig_shape = orig_shape
+        self.is_track = n == 7
+
+    # -- BaseTensor protocol (results.py:23-190)
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def _wrap(self, d):
+        return self.__class__(d, self.orig_shape)
+
+    def cpu(self):
+        return self if isinstance(self.data, np.ndarray) else self._wrap(self.data.cpu())
+
+    def numpy(self):
+        return self if isinstance(self.data, np.ndarray) else self._wrap(self.data.cpu().numpy())
+
+    def cuda(self):
+        import torch
+
+        return self._wrap(torch.as_tensor(self.data).cuda())
+
+    def to(self, *a, **k):
+        import torch
+
+        return self._wrap(torch.as_tensor(self.data).to(*a, **k))
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return self._wrap(self.data[idx])
+
+    # -- views
+    @property
+    def xyxy(self):
+        return self.data[:, :4]
+
+    @property
+    def conf(self):
+        return self.data[:, -2]
+
+    @property
+    def cls(self):
+        return self.data[:, -1]
+
+    @property
+    def id(self):
+        return self.data[:, -3] if self.is_track else None
+
+    @property
+    def xywh(self):
+        d = self.xyxy
+        out = d.copy() if isinstance(d, np.ndarray) else d.clone()
+        out[:, 0] = (d[:, 0] + d[:, 2]) / 2
+        out[:, 1] = (d[:, 1] + d[:, 3]) / 2
+        out[:, 2] = d[:, 2] - d[:, 0]
+        out[:, 3] = d[:, 3] - d[:, 1]
+        return out
+
+    @property
+    def xyxyn(self):
+        d = self.xyxy
+        out = d.copy() if isinstance(d, np.ndarray) else d.clone()
+        out[:, [0, 2]] /= self.orig_shape[1]
+        out[:, [1, 3]] /= self.orig_shape[0]
+        return out
+
+    @property
+    def xywhn(self):
+        out = self.xywh
+        out[:, [0, 2]] /= self.orig_shape[1]
+        out[:, [1, 3]] /= self.orig_shape[0]
+        return out
+
+
+class Results:
+    """engine/results.py:192-290 restricted to the detect task."""
+
+    def __init__(self, orig_img, path, names, boxes=None, speed=None):
+        self.orig_img = orig_img
+        self.orig_shape = orig_img.shape[:2]
+        self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
+        self.masks = self.probs = self.keypoints = self.obb = None
+        self.speed = speed or {"preprocess": None, "inference": None, "postprocess": None}
+        self.names = names
+        self.path = path
+        self.save_dir = None
+
+    def __len__(self):
+        return 0 if self.boxes is None else len(self.boxes)
+
+    def update(self, boxes=None, **_):
+        """results.py:340-368: replace the boxes (used by trackers to attach ids)."""
+        if boxes is not None:
+            self.boxes = Boxes(boxes, self.orig_shape)
+
+    def cpu(self):
+        r = Results(self.orig_img, self.path, self.names, speed=self.speed)
+        r.boxes = self.boxes.cpu() if self.boxes is not None else None
+        return r
+
+    def numpy(self):
+        r = Results(self.orig_img, self.path, self.names, speed=self.speed)
+        r.boxes = self.boxes.numpy() if self.boxes is not None else None
+        return r
+
+    def verbose(self):
+        """results.py:663-693."""
+        if not len(self):
+            return "(no detections), "
+        cls = self.boxes.numpy().cls.astype(int)
+        counts = np.bincount(cls)
+        return "".join(f"{n} {self.names[c]}{'s' * int(n > 1)}, " for c, n in enumerate(counts) if n)
+
+
+# ---------------------------------------------------------------------------------------------------
+# letterbox geometry (data/augment.py:1692-1733)
+# ---------------------------------------------------------------------------------------------------
+def check_imgsz(imgsz, stride=32):
+    """utils/checks.py check_imgsz(min_dim=2): int -> [s, s]; every side rounded up to a stride multiple."""
+    if isinstance(imgsz, int):
+        imgsz = [imgsz, imgsz]
+    imgsz = [max(math.ceil(int(x) / stride) * stride, stride) for x in imgsz]
+    return imgsz if len(imgsz) == 2 else [imgsz[0], imgsz[0]]
+
+
+def letterbox_geometry(h0, w0, new_shape, auto, stride=32):
+    """Returns (resized (h, w), canvas (H, W), top, left) exactly as LetterBox computes them (scaleup, center)."""
+    r = min(new_shape[0] / h0, new_shape[1] / w0)
+    new_unpad = int(round(w0 * r)), int(round(h0 * r))
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = dw % stride, dh % stride
+    dw, dh = dw / 2, dh / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return (new_unpad[1], new_unpad[0]), (new_unpad[1] + top + bottom, new_unpad[0] + left + right), top, left
+
+
+def scale_params(canvas_hw, orig_hw):
+    """gain / pad of scale_boxes (utils/ops.py:105-138, ratio_pad=None) + clip bounds."""
+    gain = min(canvas_hw[0] / orig_hw[0], canvas_hw[1] / orig_hw[1])
+    pad_x = round((canvas_hw[1] - orig_hw[1] * gain) / 2 - 0.1)
+    pad_y = round((canvas_hw[0] - orig_hw[0] * gain) / 2 - 0.1)
+    return gain, pad_x, pad_y, orig_hw[1], orig_hw[0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# model facade
+# ---------------------------------------------------------------------------------------------------
+class DetectPipeline:
+    """Engine + decode + NMS for a fixed (batch, canvas H x W): every launch of one detect step."""
+
+    def __init__(self, spec, state_dict, batch, H, W, max_det=300):
+        self.engine = Engine(spec, state_dict, batch, H, W)
+        e = self.engine
+        self.post = ops.DetectPost(batch, e.level_h, e.level_w, e.level_stride, e.nc, e.lstride, max_det=max_det)
+        self.B, self.H, self.W = batch, H, W
+
+    def __call__(self, frames_u8, conf, iou, pad_top=0, pad_left=0, orig_hw=None, classes_mask=None, agnostic=False,
+                 mode="exact", stream=None):
+        """frames_u8: CUDA uint8 [B][h][w][3] BGR.  Returns (dets [B][max_det][6], counts [B]) device tensors."""
+        self.engine.forward_u8(frames_u8, pad_top, pad_left, stream=stream)
+        return self.finish(conf, iou, orig_hw, classes_mask, agnostic, mode, stream)
+
+    def run_tensor(self, x, conf, iou, orig_hw=None, classes_mask=None, agnostic=False, mode="exact", stream=None):
+        self.engine.forward_tensor(x, stream=stream)
+        return self.finish(conf, iou, orig_hw, classes_mask, agnostic, mode, stream)
+
+    def finish(self, conf, iou, orig_hw, classes_mask, agnostic, mode, stream):
+        self.post.decode(self.engine.level_ptrs, conf, classes_mask, stream=stream)
+        scale = scale_params((self.H, self.W), orig_hw) if orig_hw is not None else None
+        return self.post.nms(iou, agnostic=agnostic, mode=mode, scale=scale, stream=stream)
+
+
+class YOLO:
+    """``YOLO('yolov8s-p2.yaml')`` facade (models/yolo/model.py:26, engine/model.py:29) for the detect task.
+
+    ``model``: a model name / YAML path understood by :func:`cfg.resolve`.  Weights: ``state_dict`` (a torch or
+    numpy state_dict with the reference's key names) or, by default, the seeded synthetic recipe of
+    :mod:`weights` (the reference ships no checkpoint).
+    """
+
+    def __init__(self, model="yolov8n-p2.yaml", task="detect", verbose=False, state_dict=None, nc=None, seed=0):
+        if task not in (None, "detect"):
+            raise NotImplementedError(f"task {task!r}: only 'detect' is on the hot path")
+        _lib.require_cuda()
+        self.spec = cfg.resolve(model, nc=nc)
+        self.names = self.spec["names"]
+        self.state_dict = weights.to_numpy_state_dict(state_dict) if state_dict is not None else weights.synthetic_state_dict(self.spec, seed)
+        self.overrides = {"conf": 0.25, "iou": 0.7, "imgsz": 640, "max_det": 300, "agnostic_nms": False, "classes": None,
+                          "batch": 1, "verbose": verbose, "nms_mode": "exact"}
+        self._pipes = {}
+        self.task = "detect"
+
+    def load_state_dict(self, sd):
+        self.state_dict = weights.to_numpy_state_dict(sd)
+        self._pipes.clear()
+        return self
+
+    def _pipe(self, batch, H, W, max_det):
+        key = (batch, H, W, max_det)
+        if key not in self._pipes:
+            self._pipes[key] = DetectPipeline(self.spec, self.state_dict, batch, H, W, max_det)
+        return self._pipes[key]
+
+    def __call__(self, source=None, stream=False, **kwargs):
+        return self.predict(source, stream, **kwargs)
+
+    def predict(self, source=None, stream=False, **kwargs):
+        """engine/model.py:498-557.  source: HWC BGR uint8 ndarray, list of them, or a BCHW float tensor in [0,1]."""
+        import torch
+
+        a = {**self.overrides, **kwargs}
+        for k in ("half", "device", "save", "show", "rect", "mode", "augment", "visualize", "embed", "predictor"):
+            a.pop(k, None)
+        conf, iou, max_det = float(a["conf"]), float(a["iou"]), int(a["max_det"])
+        assert 0 <= conf <= 1, f"Invalid Confidence threshold {conf}, valid values are between 0.0 and 1.0"
+        assert 0 <= iou <= 1, f"Invalid IoU {iou}, valid values are between 0.0 and 1.0"
+        imgsz = check_imgsz(a["imgsz"])
+        dev = _lib.require_cuda()
+        cmask = ops._classes_mask(a["classes"], self.spec["nc"], dev)
+        results = []
+        if isinstance(source, torch.Tensor):
+            # LoadTensor (data/loaders.py:566-638): BCHW float 0-1, sides divisible by the stride
+            x = source[None] if source.ndim == 3 else source
+            if x.shape[2] % 32 or x.shape[3] % 32:
+                raise ValueError(f"input tensor shape {tuple(x.shape)} must be divisible by stride 32")
+            t0 = time.perf_counter()
+            x = x.to(dev).contiguous()
+            if x.dtype not in (torch.float32, torch.bfloat16):
+                x = x.float()
+            B, _, H, W = x.shape
+            pipe = self._pipe(B, H, W, max_det)
+            dets, counts = pipe.run_tensor(x, conf, iou, (H, W), cmask, a["agnostic_nms"], a["nms_mode"])
+            cnt = counts.cpu().tolist()
+            ms = (time.perf_counter() - t0) * 1e3 / B
+            imgs = (x.float().permute(0, 2, 3, 1).flip(-1) * 255).to(torch.uint8).cpu().numpy()    # loaders convert_torch2numpy_batch
+            for b in range(B):
+                results.append(Results(imgs[b], f"image{b}.jpg", self.names, dets[b, :cnt[b]].clone(),
+                                       {"preprocess": 0.0, "inference": ms, "postprocess": 0.0}))
+        else:
+            frames = [source] if isinstance(source, np.ndarray) else list(source)
+            if not frames:
+                return []
+            for f in frames:
+                if not (isinstance(f, np.ndarray) and f.ndim == 3 and f.shape[2] == 3 and f.dtype == np.uint8):
+                    raise TypeError("source must be HWC BGR uint8 ndarray(s) or a BCHW float tensor")
+            same = len({f.shape for f in frames}) == 1
+            groups = [list(range(len(frames)))] if same else [[i] for i in range(len(frames))]
+            out = [None] * len(frames)
+            for idxs in groups:
+                h0, w0 = frames[idxs[0]].shape[:2]
+                t0 = time.perf_counter()
+                (rh, rw), (H, W), top, left = letterbox_geometry(h0, w0, imgsz, auto=same)
+                batch = torch.from_numpy(np.ascontiguousarray(np.stack([frames[i] for i in idxs]))).to(dev, non_blocking=True)
+                if (rh, rw) != (h0, w0):
+                    batch = ops.resize_bilinear_u8(batch, rh, rw)
+                if H % 32 or W % 32:           # auto=False canvases are imgsz, already stride multiples
+                    raise ValueError(f"letterboxed size {H}x{W} is not a multiple of 32")
+                pipe = self._pipe(len(idxs), H, W, max_det)
+                dets, counts = pipe(batch, conf, iou, top, left, (h0, w0), cmask, a["agnostic_nms"], a["nms_mode"])
+                cnt = counts.cpu().tolist()
+                ms = (time.perf_counter() - t0) * 1e3 / len(idxs)
+                for j, i in enumerate(idxs):
+                    out[i] = Results(frames[i], f"image{i}.jpg", self.names, dets[j, :cnt[j]].clone(),
+                                     {"preprocess": 0.0, "inference": ms, "postprocess": 0.0})
+            results = out
+        if a.get("verbose"):
+            for r in results:
+                print(f"{r.orig_shape[0]}x{r.orig_shape[1]} {r.verbose()}{r.speed['inference']:.1f}ms")
+        return iter(results) if stream else results
+
+    def fuse(self):
+        return self          # BN is always folded at lowering time (engine.lower)
+
+    def to(self, *_a, **_k):
+        return self
+
+    def info(self):
+        return {"layers": len(self.spec["layers"]), "gflops_640": cfg.conv_flops(self.spec, 640, 640) / 1e9}
