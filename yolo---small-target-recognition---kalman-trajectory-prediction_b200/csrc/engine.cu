@@ -165,11 +165,17 @@ extern "C" int b2_engine_destroy(b2_engine_t* e) {
 static int run_tail(b2_engine* e, cudaStream_t st) {
     if (e->use_graph) {
         if (!e->graph) {
+            // capture on a private non-blocking stream (the caller's stream may be the legacy default stream,
+            // which cannot be captured); nothing executes during capture
             cudaGraph_t g = nullptr;
-            B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            cudaStream_t cap = nullptr;
+            B2_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+            cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
+            if (ce != cudaSuccess) { cudaStreamDestroy(cap); B2_CUDA(ce); }
             int rc = B2_OK;
-            for (size_t i = 1; i < e->steps.size() && rc == B2_OK; ++i) rc = run_step(e, e->steps[i], st);
-            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            for (size_t i = 1; i < e->steps.size() && rc == B2_OK; ++i) rc = run_step(e, e->steps[i], cap);
+            ce = cudaStreamEndCapture(cap, &g);
+            cudaStreamDestroy(cap);
             if (rc != B2_OK) { if (g) cudaGraphDestroy(g); return rc; }
             B2_CUDA(ce);
             ce = cudaGraphInstantiate(&e->graph, g, 0);

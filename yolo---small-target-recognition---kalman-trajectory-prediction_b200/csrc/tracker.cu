@@ -222,19 +222,20 @@ __device__ __forceinline__ void update_slot(const Bank& b, int g, const float4& 
     const float z0 = (d.x + d.z) / 2.f, z1 = (d.y + d.w) / 2.f, z2 = d.z - d.x, z3 = d.w - d.y;
     {   // position block (x, y share the covariance triple)
         const float pxx = FF(b, PPX, g), pxv = FF(b, PPV, g), pvv = FF(b, PVV, g);
-        const float S = pxx + R_MEAS, kx = pxx / S, kv = pxv / S;
+        // (I - K H) P with 1 - K_x evaluated as R / S: no cancellation when P_xx >> R (long coasting tracks)
+        const float S = pxx + R_MEAS, kx = pxx / S, kv = pxv / S, omk = R_MEAS / S;
         const float y0 = z0 - FF(b, X0, g), y1 = z1 - FF(b, X1, g);
         FF(b, X0, g) += kx * y0; FF(b, X4, g) += kv * y0;
         FF(b, X1, g) += kx * y1; FF(b, X5, g) += kv * y1;
-        FF(b, PPX, g) = (1.f - kx) * pxx; FF(b, PPV, g) = (1.f - kx) * pxv; FF(b, PVV, g) = pvv - kv * pxv;
+        FF(b, PPX, g) = omk * pxx; FF(b, PPV, g) = omk * pxv; FF(b, PVV, g) = pvv - kv * pxv;
     }
     {   // size block (w, h)
         const float pxx = FF(b, PSX, g), pxv = FF(b, PSV, g), pvv = FF(b, PSVV, g);
-        const float S = pxx + R_MEAS, kx = pxx / S, kv = pxv / S;
+        const float S = pxx + R_MEAS, kx = pxx / S, kv = pxv / S, omk = R_MEAS / S;
         const float y2 = z2 - FF(b, X2, g), y3 = z3 - FF(b, X3, g);
         FF(b, X2, g) += kx * y2; FF(b, X6, g) += kv * y2;
         FF(b, X3, g) += kx * y3; FF(b, X7, g) += kv * y3;
-        FF(b, PSX, g) = (1.f - kx) * pxx; FF(b, PSV, g) = (1.f - kx) * pxv; FF(b, PSVV, g) = pvv - kv * pxv;
+        FF(b, PSX, g) = omk * pxx; FF(b, PSV, g) = omk * pxv; FF(b, PSVV, g) = pvv - kv * pxv;
     }
     // velocity ring push, trajectory push, motion analysis
     int head = II(b, VHEAD, g);

@@ -171,10 +171,10 @@ def lower(spec, state_dict, H, W):
             check_c(c, p + " hidden")
             inp = P.loc[src(i, L["f"])]
             cat = P.new_buf(h, w, (2 + n) * c)
-            tmp = P.new_buf(h, w, c)
             emit_conv(p + ".cv1", inp, (cat, 0, 2 * c), 1, 1, True)
             for j in range(n):
                 a = (cat, (1 + j) * c, c)
+                tmp = P.new_buf(h, w, c)
                 emit_conv(f"{p}.m.{j}.cv1", a, (tmp, 0, c), 3, 1, True)
                 emit_conv(f"{p}.m.{j}.cv2", (tmp, 0, c), (cat, (2 + j) * c, c), 3, 1, True, res=a if L["shortcut"] else None)
             out = out_loc(L)
