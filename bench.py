@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the detect+track hot path (BASELINE.json metric: detect+track frames/sec, YOLOv8s-P2 640x512).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one rank per GPU
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+One "step" = one frame of every resident stream through the whole per-frame path
+(uint8 frame -> stem/forward -> DFL decode -> NMS -> Kalman track bank update).
+Workload = BASELINE.json configs[3] ("C4"): 256 concurrent synthetic 640x512 IR streams, yolov8s-p2 (nc=80,
+seeded synthetic weights), predict conf=0.15 iou=0.6, EnhancedMultiTargetTracker(150, min_hits=1, iou=0.1).
+Streams are independent: each rank owns its own 256 streams (weak scaling, no data-path collective).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "detect+track frames/sec (YOLOv8s-P2 640x512)"
+UNIT = "frames/s"
+MODEL = "yolov8s-p2"
+FRAME_HW = (512, 640)
+CONF, IOU = 0.15, 0.6
+TRACKER = dict(max_lost_frames=150, min_hits=1, iou_threshold=0.1)
+DISTINCT_STREAMS = 32          # distinct synthetic videos, tiled to the stream count
+POOL_FRAMES = 4                # consecutive frames per stream kept resident and cycled
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=256, help="streams per GPU")
+    ap.add_argument("--capacity", type=int, default=2048, help="track slots per stream")
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--ref-streams", type=int, default=2, help="streams per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-profile", default=None, help="write the per-launch table of the forward to this JSON file")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the stand-alone HBM-kernel measurements")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tc_burst": d["bf16_tflops"], "tc_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm": 6650.0, "tc_burst": 1590.0, "tc_sustained": 1400.0, "src": "fallback"}
+
+
+def make_frames(n_streams, n_frames, seed0=1000):
+    """uint8 [n_frames][n_streams][h][w][3]: DISTINCT_STREAMS seeded IR videos tiled over the streams."""
+    import numpy as np
+
+    from b200dt import synth
+
+    k = min(DISTINCT_STREAMS, n_streams)
+    vids = [synth.IRStream(seed=seed0 + s, h=FRAME_HW[0], w=FRAME_HW[1]) for s in range(k)]
+    out = np.empty((n_frames, n_streams, FRAME_HW[0], FRAME_HW[1], 3), np.uint8)
+    for t in range(n_frames):
+        fr = [v.frame() for v in vids]
+        for s in range(n_streams):
+            out[t, s] = fr[s % k]
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        self.t0 = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        self.t0 = time.time()
+
+    def stop(self):
+        t1 = time.time()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if self.t0 is not None and not (self.t0 - 0.1 <= ts <= t1 + 0.3):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the same per-frame path on host cores
+# ---------------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, model, n_streams):
+        import torch
+
+        from b200dt import cfg, weights
+        from oracle import net as onet
+        from oracle import tracker as otr
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.cores = torch.get_num_threads()
+        onet.set_conv_backend("aten")       # the conv primitive the reference itself calls on CPU (ATen/oneDNN)
+        spec = cfg.resolve(model)
+        self.nc = spec["nc"]
+        self.net = onet.Net(onet.build_spec(model), weights.synthetic_state_dict(spec, seed=0), "fp32")
+        self.trackers = [otr.MultiTracker(TRACKER["max_lost_frames"], TRACKER["min_hits"], TRACKER["iou_threshold"]) for _ in range(n_streams)]
+
+    def step(self, frames):
+        """frames: uint8 [n][h][w][3] -> per-stream track dict lists (predict conf/iou as the GPU arm)."""
+        from oracle import postprocess as pp
+
+        out = []
+        for s, f in enumerate(frames):
+            x = pp.preprocess([pp.letterbox_pad_only(f, (640, 640), auto=True, stride=32)])
+            y = pp.decode(self.net.forward(x), [4, 8, 16, 32], self.nc)
+            d = pp.non_max_suppression(y, CONF, IOU, mode="exact")[0]
+            d[:, :4] = pp.scale_boxes(x.shape[2:], d[:, :4], f.shape[:2])
+            out.append(self.trackers[s].update([r[:5] for r in d]))
+        return out
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+
+    n = a.ref_streams
+    frames = make_frames(n, POOL_FRAMES)
+    cpu = CpuPath(a.model, n)
+    for i in range(a.warmup):
+        cpu.step(frames[i % POOL_FRAMES])
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        cpu.step(frames[i % POOL_FRAMES])
+    dt = time.perf_counter() - t0
+    v = n * a.steps / dt
+    sample = f"{n} streams x {a.steps} frames of the 256-stream workload, oracle port (numpy + ATen conv, fp32), {cpu.cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(a, a.streams),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(a, streams):
+    return {"workload": f"C4: {streams} concurrent synthetic 640x512 IR streams per GPU, {a.model} (nc=80, seeded synthetic weights) + "
+                        f"Kalman tracker bank, predict conf={CONF} iou={IOU}, tracker(150, min_hits=1, iou=0.1)",
+            "streams_per_gpu": streams, "frame": "640x512x3 uint8", "model": a.model,
+            "l2": "inputs larger than L2 (252 MB of frames per step, 4-step resident pool)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# stand-alone HBM-kernel measurements: decode at the workload size, Kalman bank at C3 size
+# ---------------------------------------------------------------------------------------------------
+def time_cuda(fn, iters, flush=None):
+    import torch
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for s, e in ev:
+        if flush is not None:
+            flush()
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) for s, e in ev)
+    return ts[len(ts) // 2]
+
+
+def hbm_kernels(pipe, pk):
+    import torch
+
+    out = {}
+    eng, post = pipe.detect.engine, pipe.detect.post
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = lambda: flush_buf.fill_(1)
+    # DFL decode + confidence filter: reads (64+nc) bf16 logits per anchor once
+    ms = time_cuda(lambda: post.decode(eng.level_ptrs, CONF), 10, flush)
+    nbytes = pipe.S * eng.num_anchors * eng.lstride * 2
+    out["decode"] = {"ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / pk["hbm"]}
+    # NMS: latency-bound at realistic candidate counts -- report ms per batch
+    ms = time_cuda(lambda: post.nms(IOU), 10, flush)
+    out["nms"] = {"ms": ms, "images": pipe.S, "mean_candidates": float(post.cand_count.float().mean().item())}
+    del flush_buf
+    # Kalman bank at C3 scale: 256 streams x 4096 tracks = 1,048,576 live tracks, predict kernel
+    from b200dt.tracker import TrackerBank
+
+    S, C, D = 256, 4096, 1024
+    bank = TrackerBank(S, C, D, 150, 1, 0.1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for r in range(C // D):          # r-th batch of 1024 disjoint boxes per stream -> every box founds a track
+        idx = torch.arange(D, device="cuda") + r * D
+        x = (idx % 64).float() * 10.0
+        y = (idx // 64).float() * 10.0
+        boxes = torch.stack([x, y, x + 6, y + 6], 1)[None].repeat(S, 1, 1).contiguous()
+        bank.update(boxes, torch.full((S,), D, dtype=torch.int32, device="cuda"), with_trajectory=False)
+    torch.cuda.synchronize()
+    live = int(bank.export(0)[3][2])
+    pb, ub = TrackerBank.bytes_per_track()
+    ms = time_cuda(lambda: bank.predict_only(), 10)
+    nb = S * live * pb
+    out["kalman_predict"] = {"ms": ms, "tracks": S * live, "bytes_per_track": pb, "achieved_gbs": nb / ms / 1e6,
+                             "frac_of_hbm_peak": nb / ms / 1e6 / pk["hbm"], "tracks_per_s": S * live / ms * 1e3}
+    bank.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import b200dt  # noqa: F401
+    from b200dt import _lib
+    from b200dt.pipeline import DetectTrackPipeline, gather_results
+
+    pk = peaks()
+    S = a.streams
+    pipe = DetectTrackPipeline(a.model, S, FRAME_HW, 640, CONF, IOU, 300, capacity=a.capacity, **TRACKER)
+    host = torch.from_numpy(make_frames(S, POOL_FRAMES, seed0=1000 + 97 * rank)).pin_memory()
+    dev = host.cuda()
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident: inputs already in HBM -------------------------------------------------
+    for i in range(a.warmup):
+        pipe.step_device(dev[i % POOL_FRAMES])
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
+    l0 = lib.b2_launch_count()
+    ms_dev = timed(lambda i: pipe.step_device(dev[(a.warmup + i) % POOL_FRAMES]), a.steps)
+    launches = lib.b2_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    value = S * world * a.steps / ms_dev * 1e3
+
+    # ---- end to end through the host-facing call: pinned host frames in, track rows out --------------
+    for i in range(a.warmup):
+        pipe.step_host(host[i % POOL_FRAMES])
+    ms_e2e = timed(lambda i: pipe.step_host(host[(a.warmup + i) % POOL_FRAMES]), a.steps)
+    e2e = S * world * a.steps / ms_e2e * 1e3
+    rows, counts = pipe.host_rows, pipe.host_counts
+    st = pipe.bank.export(0)[3]
+
+    # the only collective: gather per-stream result blocks (off the data path; not in the timed region)
+    if world > 1:
+        gather_results(pipe.bank.rows[:, :64].contiguous(), pipe.bank.counts)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), per-launch CUDA events ----------
+    prof = pipe.detect.engine.profile_u8(dev[0], pipe.top, pipe.left)
+    prof = pipe.detect.engine.profile_u8(dev[1], pipe.top, pipe.left)
+    if a.dump_profile:
+        json.dump(prof, open(a.dump_profile, "w"), indent=0)
+    conv = [p for p in prof if p["op"] == "conv"]
+    conv_ms, conv_fl = sum(p["ms"] for p in conv), sum(p["flops"] for p in conv)
+    all_ms = sum(p["ms"] for p in prof)
+    achieved = conv_fl / conv_ms / 1e9
+    ms_step = ms_dev / a.steps
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, 78 launches/step)", "achieved": achieved,
+                "peak": pk["tc_sustained"], "peak_kind": f"bf16 dense sustained, {pk['src']}", "unit": "TFLOP/s",
+                "frac": achieved / pk["tc_sustained"], "traffic": None, "avg_launch_ms": conv_ms / len(conv),
+                "algorithmic_flops_per_step": conv_fl, "share_of_step": conv_ms / all_ms if all_ms else None,
+                "forward_ms_eager_events": all_ms, "end_to_end_tensor_frac": pipe.flops_per_frame * S / (ms_step * 1e-3) / 1e12 / pk["tc_sustained"]}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(a, S), "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step, "d2h_bytes_per_step": pipe.d2h_bytes_per_step,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": int(launches), "roofline": roofline,
+        "tracks": {"active_stream0": int(st[2]), "created_stream0": int(st[0]), "dropped_no_slot_stream0": int(st[7]),
+                   "mean_emitted_per_stream": float(counts.float().mean().item())},
+    }
+    if world == 1 and not a.no_kernels:
+        line["hbm_kernels"] = hbm_kernels(pipe, pk)
+    if world == 1 and not a.no_cpu_baseline:
+        n = a.ref_streams
+        cpu = CpuPath(a.model, n)
+        fr = host[:, :n].numpy()
+        cpu.step(fr[0])
+        t0, k = time.perf_counter(), 0
+        while k < 6 or (time.perf_counter() - t0 < 12.0 and k < 200):
+            cpu.step(fr[k % POOL_FRAMES])
+            k += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n * k / dt, "unit": UNIT, "cores": cpu.cores, "kind": "port",
+                                "sample": f"{n} streams x {k} frames of the same workload (oracle port: numpy + ATen conv fp32, exact NMS, float64 tracker)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

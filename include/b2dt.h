@@ -124,6 +124,10 @@ int b2_engine_create(const int32_t* plan, int plan_words, const void* weights_ho
 int b2_engine_destroy(b2_engine_t* e);
 /* frames: [B][src_h][src_w][3] uint8 BGR device memory, placed at (pad_top,pad_left) of the HxW canvas */
 int b2_engine_forward_u8(b2_engine_t* e, const uint8_t* frames, int src_h, int src_w, int pad_top, int pad_left, void* stream);
+/* Same forward, launched eagerly with a CUDA event between consecutive launches; fills the device time of each
+ * launch (ms_per_op: host, [b2_engine_num_launches]; op 0 = stem).  Synchronises.  For roofline accounting. */
+int b2_engine_profile_u8(b2_engine_t* e, const uint8_t* frames, int src_h, int src_w, int pad_top, int pad_left,
+                         float* ms_per_op, void* stream);
 /* x: BCHW RGB [0,1], dtype 0 fp32 / 1 bf16 */
 int b2_engine_forward_f32(b2_engine_t* e, const void* bchw, int dtype, void* stream);
 /* Per-level head logits of the last forward: device pointers, [B][h*w][lstride] bf16 */

@@ -127,6 +127,9 @@ def build_spec(name="yolov8n-p2", nc=None):
 # --------------------------------------------------------------------------------------
 # numerics
 # --------------------------------------------------------------------------------------
+_CONV_BACKEND = "numpy"
+
+
 def bf16_round(a):
     """Round-to-nearest-even fp32 -> bf16, returned as fp32."""
     a = np.ascontiguousarray(a, dtype=np.float32)
@@ -136,12 +139,33 @@ def bf16_round(a):
 
 
 def silu(x):
+    if _CONV_BACKEND == "aten":
+        import torch
+
+        return torch.nn.functional.silu(torch.from_numpy(np.ascontiguousarray(x, np.float32))).numpy()
     with np.errstate(over="ignore"):
         return (x / (1.0 + np.exp(-x, dtype=np.float32))).astype(np.float32)
 
 
+def set_conv_backend(name):
+    """"numpy" (default: explicit tap loop + matmul) or "aten": the same cross-correlation evaluated by the
+    third-party primitive the reference itself calls on CPU (torch.nn.functional.conv2d -> ATen/oneDNN,
+    ultralytics/nn/modules/conv.py:83-93).  "aten" is used only for the timed CPU-baseline leg of bench.py, so
+    that the baseline runs at the reference's real CPU speed; tests check both backends agree."""
+    global _CONV_BACKEND
+    assert name in ("numpy", "aten")
+    _CONV_BACKEND = name
+
+
 def conv2d(x, w, b, s=1, p=0):
     """Cross-correlation, NCHW, fp32 (torch.nn.functional.conv2d semantics, groups=1)."""
+    if _CONV_BACKEND == "aten":
+        import torch
+
+        with torch.no_grad():
+            y = torch.nn.functional.conv2d(torch.from_numpy(np.ascontiguousarray(x, np.float32)), torch.from_numpy(np.ascontiguousarray(w, np.float32)),
+                                           None if b is None else torch.from_numpy(np.ascontiguousarray(b, np.float32)), stride=s, padding=p)
+        return y.numpy()
     B, C, H, W = x.shape
     O, C2, k, _ = w.shape
     assert C == C2, (x.shape, w.shape)

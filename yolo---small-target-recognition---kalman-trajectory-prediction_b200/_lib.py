@@ -36,6 +36,7 @@ SIGNATURES = {
     "b2_engine_create": (c_int, [_P, c_int, _P, c_size_t, c_int, c_int, c_int, C.POINTER(_P)]),
     "b2_engine_destroy": (c_int, [_P]),
     "b2_engine_forward_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b2_engine_profile_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "b2_engine_forward_f32": (c_int, [_P, _P, c_int, _P]),
     "b2_engine_levels": (c_int, [_P, C.POINTER(c_int), C.POINTER(_P), C.POINTER(c_int), C.POINTER(c_int),
                                  C.POINTER(c_int), C.POINTER(c_int)]),

@@ -205,6 +205,35 @@ extern "C" int b2_engine_forward_u8(b2_engine_t* e, const uint8_t* frames, int s
     return run_tail(e, (cudaStream_t)stream);
 }
 
+// Eager replay with a CUDA event between consecutive launches (on the launch stream): per-launch device times
+// for roofline accounting (bench.py).  Synchronises.  ms_per_op: [b2_engine_num_launches] floats; op 0 = stem.
+extern "C" int b2_engine_profile_u8(b2_engine_t* e, const uint8_t* frames, int src_h, int src_w, int pad_top, int pad_left,
+                                    float* ms_per_op, void* stream) {
+    B2_REQUIRE(e && frames && ms_per_op, "engine_profile: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = e->steps.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& v : ev) B2_CUDA(cudaEventCreate(&v));
+    const int* a = e->steps[0].a;
+    char* wbase = e->arena + e->weights_off;
+    int rc = B2_OK;
+    cudaEventRecord(ev[0], st);
+    rc = b2_stem_u8(frames, e->B, src_h, src_w, e->H, e->W, pad_top, pad_left, (const float*)(wbase + (size_t)(uint32_t)a[3]),
+                    (const float*)(wbase + (size_t)(uint32_t)a[4]), a[2], e->buf_ptr(a[0]), e->bufs[a[0]].c, a[1], stream);
+    cudaEventRecord(ev[1], st);
+    for (size_t i = 1; i < n && rc == B2_OK; ++i) {
+        rc = run_step(e, e->steps[i], st);
+        cudaEventRecord(ev[i + 1], st);
+    }
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (rc == B2_OK && ce == cudaSuccess)
+        for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+    for (auto& v : ev) cudaEventDestroy(v);
+    if (rc != B2_OK) return rc;
+    B2_CUDA(ce);
+    return B2_OK;
+}
+
 extern "C" int b2_engine_forward_f32(b2_engine_t* e, const void* bchw, int dtype, void* stream) {
     B2_REQUIRE(e && bchw, "engine_forward: null pointer");
     const int* a = e->steps[0].a;

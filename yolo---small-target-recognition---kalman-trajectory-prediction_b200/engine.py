@@ -284,6 +284,38 @@ class Engine:
             raise ValueError(f"expected {self.B} BGR frames, got {tuple(frames.shape)}")
         _lib.check(self.lib.b2_engine_forward_u8(self._h, _lib.ptr(frames), sh, sw, pad_top, pad_left, _lib.stream_ptr(stream)))
 
+    def profile_u8(self, frames, pad_top=0, pad_left=0, stream=None):
+        """Per-launch device milliseconds of one eager forward (CUDA events on the launch stream) and the
+        algorithmic FLOPs of each launch: list of dicts {op, ms, flops, desc}."""
+        n = self.launches_per_forward
+        ms = (C.c_float * n)()
+        b, sh, sw, _ = frames.shape
+        _lib.check(self.lib.b2_engine_profile_u8(self._h, _lib.ptr(frames), sh, sw, pad_top, pad_left, ms, _lib.stream_ptr(stream)))
+        out = []
+        for i, op in enumerate(self.plan.ops):
+            kind = {OP_STEM: "stem", OP_CONV: "conv", OP_POOL: "pool", OP_UP: "upsample"}[op[0]]
+            fl, desc, nbytes = 0, "", 0
+            if op[0] == OP_CONV:
+                _, ib, ioff, cin, ob, ooff, cout, k, s, act, rb = op[:11]
+                h, w, _c = self.plan.bufs[ob]
+                hi, wi, _ci = self.plan.bufs[ib]
+                fl = 2 * h * w * cout * cin * k * k * self.B
+                nbytes = (hi * wi * cin + h * w * cout * (2 if rb >= 0 else 1)) * 2 * self.B + cout * cin * k * k * 2
+                desc = f"{cin}->{cout} k{k} s{s} @{h}x{w}"
+            elif op[0] == OP_STEM:
+                h, w, _c = self.plan.bufs[op[1]]
+                fl = 2 * h * w * op[3] * 27 * self.B
+                nbytes = (self.H * self.W * 3 + h * w * op[3] * 2) * self.B
+                desc = f"3->{op[3]} k3 s2 @{h}x{w}"
+            elif op[0] == OP_POOL:
+                h, w, _c = self.plan.bufs[op[1]]
+                nbytes = h * w * op[3] * 4 * 2 * self.B
+            elif op[0] == OP_UP:
+                h, w, _c = self.plan.bufs[op[1]]
+                nbytes = h * w * op[3] * 2 * (1 + op[4] * op[4]) * self.B
+            out.append({"op": kind, "ms": float(ms[i]), "flops": fl, "bytes": nbytes, "desc": desc})
+        return out
+
     def forward_tensor(self, x, stream=None):
         """x: CUDA float32 / bfloat16 tensor [B][3][H][W] RGB in [0, 1] (data/loaders.py:566-638 LoadTensor)."""
         import torch
