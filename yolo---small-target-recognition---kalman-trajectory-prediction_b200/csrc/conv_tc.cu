@@ -23,8 +23,10 @@
 
 namespace {
 
-constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int kMaxStages = 12;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, 16-column chunks interleaved
+constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kMaxNTile = 256;
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[4];
@@ -35,10 +37,17 @@ struct alignas(64) ConvParams {
     int n_tiles, n_tile, Cout;
     int Cin, ksize, stride, pad;
     int BK, kchunks, num_stages;
-    uint32_t a_bytes, b_bytes, b_stage_stride;
+    int halo;                 // 1: 3x3 stride-1 "halo" mode -- one (TH+2) x 8 pixel box per (kw, K chunk), shared by the 3 kh taps
+    int b_resident;           // 1: every weight block stays in shared memory for the lifetime of the CTA
+    uint32_t a_bytes;         // shared-memory stride of one A stage (1024-aligned)
+    uint32_t a_tx;            // bytes one A box delivers
+    uint32_t b_block_bytes;   // n_tile * BK * 2
+    uint32_t b_block_stride;  // rounded up to 1024
+    uint32_t b_stage_blocks;  // streamed weights: blocks per stage (1, or 3 in halo mode)
+    uint32_t kh_step;         // halo mode: bytes between the operand starts of consecutive kh taps (8 rows)
     uint32_t tmem_cols;
-    uint32_t swizzle_code;   // UMMA layout type: 2 = 128B, 4 = 64B, 6 = 32B
-    uint32_t sbo;            // 8 rows * row bytes
+    uint32_t swizzle_code;    // UMMA layout type: 2 = 128B, 4 = 64B, 6 = 32B
+    uint32_t sbo;             // 8 rows * row bytes
     __nv_bfloat16* out; int out_cstride, out_coff;
     const __nv_bfloat16* res; int res_cstride, res_coff;
     const float* bias;
@@ -51,13 +60,53 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo,
            ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+// bias + activation + residual + bf16 pack + store of one 16-column chunk held in registers
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], const float* __restrict__ sb, int act, int nv,
+                                               __nv_bfloat16* __restrict__ optr, const __nv_bfloat16* __restrict__ rptr) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + i);
+        f[i] = __uint_as_float(v[i]) + b4.x; f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+        f[i + 2] = __uint_as_float(v[i + 2]) + b4.z; f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+    }
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = silu_f(f[i]);
+    }
+    if (nv == 16) {
+        if (rptr) {
+            const uint4 r0 = *reinterpret_cast<const uint4*>(rptr);
+            const uint4 r1 = *reinterpret_cast<const uint4*>(rptr + 8);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { f[2 * i] += bf16_lo(rr[i]); f[2 * i + 1] += bf16_hi(rr[i]); }
+        }
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+        o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+        o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+        o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+        *reinterpret_cast<uint4*>(optr) = o0;
+        *reinterpret_cast<uint4*>(optr + 8) = o1;
+    } else {
+        for (int i = 0; i < nv; ++i) {
+            float x = f[i];
+            if (rptr) x += __bfloat162float(rptr[i]);
+            optr[i] = __float2bfloat16_rn(x);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t bres_bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[kMaxNTile];
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -71,13 +120,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (p.stride == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
         tma_prefetch_desc(&p.tmB);
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 32 * kEpiWarps); }
+        mbar_init(&bres_bar, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
         tmem_alloc(&tmem_base_s, p.tmem_cols);
         tmem_relinquish();
     }
+    if (p.n_tiles == 1)
+        for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -85,11 +137,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_nb;
     const int total_tiles = tiles_m * p.n_tiles;
-    const int ksteps = p.ksize * p.ksize * p.kchunks;
+    const int taps = p.ksize * p.ksize;
+    const int groups = p.halo ? 3 : taps;                 // pipeline stages consumed per K chunk
+    const int taps_per_group = p.halo ? 3 : 1;
 
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
+            if (p.b_resident) {
+                mbar_expect_tx(&bres_bar, (uint32_t)(taps * p.kchunks) * p.b_block_bytes);
+                for (int tap = 0; tap < taps; ++tap)
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        tma_load_2d(smem_b + (size_t)(tap * p.kchunks + kc) * p.b_block_stride, &p.tmB, &bres_bar, tap * p.Cin + kc * p.BK, 0);
+            }
+            const uint32_t stage_tx = p.a_tx + (p.b_resident ? 0u : p.b_stage_blocks * p.b_block_bytes);
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_idx = tile % p.n_tiles;
@@ -97,23 +158,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const int w0 = (m_idx % p.tiles_w) * p.TW; m_idx /= p.tiles_w;
                 const int h0 = (m_idx % p.tiles_h) * p.TH;
                 const int n0 = (m_idx / p.tiles_h) * p.NB;
-                for (int tap = 0; tap < p.ksize * p.ksize; ++tap) {
-                    const int kh = tap / p.ksize, kw = tap % p.ksize;
+                for (int g = 0; g < groups; ++g) {
                     int map = 0, cw, chh;
-                    if (p.stride == 1) {
-                        cw = w0 + kw - p.pad; chh = h0 + kh - p.pad;
+                    if (p.halo) {                       // g == kw: rows h0-1 .. h0+TH, columns w0+kw-1 .. +7
+                        cw = w0 + g - 1; chh = h0 - 1;
                     } else {
-                        const int ih0 = kh - p.pad, iw0 = kw - p.pad;       // input = 2*out + i?0
-                        const int ph = ih0 & 1, pw = iw0 & 1;
-                        map = ph * 2 + pw;
-                        chh = h0 + (ih0 - ph) / 2; cw = w0 + (iw0 - pw) / 2;
+                        const int kh = g / p.ksize, kw = g % p.ksize;
+                        if (p.stride == 1) {
+                            cw = w0 + kw - p.pad; chh = h0 + kh - p.pad;
+                        } else {
+                            const int ih0 = kh - p.pad, iw0 = kw - p.pad;       // input = 2*out + i?0
+                            const int ph = ih0 & 1, pw = iw0 & 1;
+                            map = ph * 2 + pw;
+                            chh = h0 + (ih0 - ph) / 2; cw = w0 + (iw0 - pw) / 2;
+                        }
                     }
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+                        mbar_expect_tx(&full_bar[stage], stage_tx);
                         tma_load_4d(smem_a + (size_t)stage * p.a_bytes, &p.tmA[map], &full_bar[stage], kc * p.BK, cw, chh, n0);
-                        tma_load_2d(smem_b + (size_t)stage * p.b_stage_stride, &p.tmB, &full_bar[stage],
-                                    tap * p.Cin + kc * p.BK, n_idx * p.n_tile);
+                        if (!p.b_resident) {
+                            uint8_t* bdst = smem_b + (size_t)stage * p.b_stage_blocks * p.b_block_stride;
+                            for (int t = 0; t < taps_per_group; ++t) {
+                                const int tap = p.halo ? t * 3 + g : g;
+                                tma_load_2d(bdst + (size_t)t * p.b_block_stride, &p.tmB, &full_bar[stage], tap * p.Cin + kc * p.BK, n_idx * p.n_tile);
+                            }
+                        }
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -127,29 +197,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             const int mma_per_step = p.BK / 16;
+            if (p.b_resident) { mbar_wait(&bres_bar, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.n_tile);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint64_t da = make_smem_desc(smem_u32(smem_a + (size_t)stage * p.a_bytes), p.sbo, p.swizzle_code);
-                    const uint64_t db = make_smem_desc(smem_u32(smem_b + (size_t)stage * p.b_stage_stride), p.sbo, p.swizzle_code);
-                    for (int j = 0; j < mma_per_step; ++j) {
-                        // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                        tc_mma_bf16(d_addr, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (ks | j) ? 1u : 0u);
+                uint32_t first = 1;
+                for (int g = 0; g < groups; ++g) {
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(smem_a + (size_t)stage * p.a_bytes);
+                        for (int t = 0; t < taps_per_group; ++t) {
+                            const int tap = p.halo ? t * 3 + g : g;
+                            const uint32_t b_addr = p.b_resident
+                                ? smem_u32(smem_b + (size_t)(tap * p.kchunks + kc) * p.b_block_stride)
+                                : smem_u32(smem_b + ((size_t)stage * p.b_stage_blocks + t) * p.b_block_stride);
+                            const uint64_t da = make_smem_desc(a_base + (uint32_t)t * p.kh_step, p.sbo, p.swizzle_code);
+                            const uint64_t db = make_smem_desc(b_addr, p.sbo, p.swizzle_code);
+                            for (int j = 0; j < mma_per_step; ++j) {
+                                // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                                tc_mma_bf16(d_addr, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                        }
+                        tc_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
+                tc_commit(&tfull_bar[acc]);                      // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                   // which of the two warps of the quadrant
         const int row = quad * 32 + lane;                   // row of the 128-row tile == TMEM lane
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, nb = row / (p.TW * p.TH);
         int acc = 0; uint32_t acc_phase = 0;
@@ -164,45 +247,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int n_base = n_idx * p.n_tile;
             __nv_bfloat16* optr = p.out + pix * p.out_cstride + p.out_coff + n_base;
             const __nv_bfloat16* rptr = p.res ? p.res + pix * p.res_cstride + p.res_coff + n_base : nullptr;
+            const int ncols = min(p.n_tile, p.Cout - n_base);
+            const int nchunks = (ncols + 15) >> 4;
+            if (p.n_tiles > 1) {
+                // per-tile bias slice (named barrier over the epilogue warps only)
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
+                for (int i = threadIdx.x - 64; i < p.n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < p.Cout ? __ldg(p.bias + n_base + i) : 0.f;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
+            }
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n_tile);
-            const int ncols = min(p.n_tile, p.Cout - n_base);
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(t_addr + c0, v);
+            // this warp's chunks: half, half+2, half+4, ... ; two chunks in flight per iteration
+            for (int j = half; j < nchunks; j += 4) {
+                const int j2 = j + 2;
+                const bool two = j2 < nchunks;
+                uint32_t v0[16], v1[16];
+                tmem_ld16(t_addr + j * 16, v0);
+                if (two) tmem_ld16(t_addr + j2 * 16, v1);
                 tmem_ld_wait();
                 if (valid) {
-                    float f[16];
-                    const int nv = min(16, ncols - c0);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float x = __uint_as_float(v[i]) + ((i < nv) ? __ldg(p.bias + n_base + c0 + i) : 0.f);
-                        f[i] = p.act ? silu_f(x) : x;
-                    }
-                    if (nv == 16) {
-                        if (rptr) {
-                            const uint4 r0 = *reinterpret_cast<const uint4*>(rptr + c0);
-                            const uint4 r1 = *reinterpret_cast<const uint4*>(rptr + c0 + 8);
-                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) { f[2 * i] += bf16_lo(rr[i]); f[2 * i + 1] += bf16_hi(rr[i]); }
-                        }
-                        uint4 o0, o1;
-                        o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-                        o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-                        o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-                        o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                        *reinterpret_cast<uint4*>(optr + c0) = o0;
-                        *reinterpret_cast<uint4*>(optr + c0 + 8) = o1;
-                    } else {
-                        for (int i = 0; i < nv; ++i) {
-                            float x = f[i];
-                            if (rptr) x += __bfloat162float(rptr[c0 + i]);
-                            optr[c0 + i] = __float2bfloat16_rn(x);
-                        }
-                    }
+                    epilogue_chunk(v0, s_bias + j * 16, p.act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                    if (two) epilogue_chunk(v1, s_bias + j2 * 16, p.act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
                 }
             }
             tc_fence_before();
@@ -282,7 +349,7 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     {   // opt in to the large dynamic shared memory carve-out once (not a stream operation: safe before graph capture)
         static std::once_flag once;
         static cudaError_t attr_err = cudaSuccess;
-        std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048); });
+        std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096); });
         B2_CUDA(attr_err);
     }
     EncodeTiledFn encode = get_encode();
@@ -293,42 +360,87 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     ConvParams& p = L->p;
     const int pad = ksize / 2;
     p.B = B; p.Ho = (H + 2 * pad - ksize) / stride + 1; p.Wo = (W + 2 * pad - ksize) / stride + 1;
-    b2_pick_tile(B, p.Ho, p.Wo, &p.TW, &p.TH, &p.NB);
-    p.tiles_w = b2_ceil_div(p.Wo, p.TW); p.tiles_h = b2_ceil_div(p.Ho, p.TH); p.tiles_nb = b2_ceil_div(B, p.NB);
     p.Cout = Cout; p.Cin = Cin; p.ksize = ksize; p.stride = stride; p.pad = pad;
+    // 3x3 stride-1 "halo" mode: 8 x 16 pixel tiles; each (kw, K chunk) loads one 18-row box that serves the 3 kh taps
+    p.halo = 0;
+    if (ksize == 3 && stride == 1) {
+        const double eff = (double)p.Wo * p.Ho / ((double)b2_ceil_div(p.Wo, 8) * 8 * b2_ceil_div(p.Ho, 16) * 16);
+        if (eff >= 0.6) p.halo = 1;
+    }
+    if (p.halo) { p.TW = 8; p.TH = 16; p.NB = 1; }
+    else b2_pick_tile(B, p.Ho, p.Wo, &p.TW, &p.TH, &p.NB);
+    p.tiles_w = b2_ceil_div(p.Wo, p.TW); p.tiles_h = b2_ceil_div(p.Ho, p.TH); p.tiles_nb = b2_ceil_div(B, p.NB);
     p.BK = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
     p.kchunks = Cin / p.BK;
     const int cout16 = b2_ceil_div(Cout, 16) * 16;
-    if (cout16 <= 256) { p.n_tiles = 1; p.n_tile = cout16; }
+    const uint32_t row_bytes0 = (uint32_t)p.BK * 2u;
+    int n_cap = 256;
+    // streamed-weight stage = A box + (3 in halo mode) weight blocks: shrink the N tile until two stages fit
+    while (n_cap > 16) {
+        const size_t a_st = ((p.halo ? (size_t)(p.TH + 2) * 8 : 128) * row_bytes0 + 1023) & ~(size_t)1023;
+        const int nt = cout16 < n_cap ? cout16 : n_cap;
+        const size_t b_st = (p.halo ? 3 : 1) * (((size_t)nt * row_bytes0 + 1023) & ~(size_t)1023);
+        if (2 * (a_st + b_st) <= 200 * 1024) break;
+        n_cap /= 2;
+    }
+    if (cout16 <= n_cap) { p.n_tiles = 1; p.n_tile = cout16; }
     else {
-        p.n_tiles = b2_ceil_div(cout16, 256);
+        p.n_tiles = b2_ceil_div(cout16, n_cap);
         p.n_tile = b2_ceil_div(b2_ceil_div(cout16, p.n_tiles), 16) * 16;
         p.n_tiles = b2_ceil_div(cout16, p.n_tile);
     }
-    p.a_bytes = 128u * p.BK * 2u;
-    p.b_bytes = (uint32_t)p.n_tile * p.BK * 2u;
-    p.b_stage_stride = (p.b_bytes + 1023u) & ~1023u;
+    const uint32_t row_bytes = (uint32_t)p.BK * 2u;
+    p.a_bytes = (p.halo ? (uint32_t)(p.TH + 2) * 8u : 128u) * row_bytes;
+    p.a_tx = p.a_bytes;
+    p.a_bytes = (p.a_bytes + 1023u) & ~1023u;
+    p.kh_step = p.halo ? 8u * row_bytes : 0u;
+    p.b_block_bytes = (uint32_t)p.n_tile * row_bytes;
+    p.b_block_stride = (p.b_block_bytes + 1023u) & ~1023u;
+    p.b_stage_blocks = p.halo ? 3u : 1u;
     p.swizzle_code = p.BK == 64 ? 2u : p.BK == 32 ? 4u : 6u;
-    p.sbo = 8u * p.BK * 2u;
+    p.sbo = 8u * row_bytes;
     uint32_t cols = 2u * p.n_tile, pw = 32;
     while (pw < cols) pw <<= 1;
     p.tmem_cols = pw;
-    const size_t per_stage = p.a_bytes + p.b_stage_stride;
-    int stages = (int)((200 * 1024) / per_stage);
+    // ---- shared memory plan: resident weights when they fit, 2 CTAs per SM when both fit ----
+    const size_t kTwoCta = 106 * 1024, kOneCta = 212 * 1024;
+    const int taps = ksize * ksize;
+    const size_t b_all = (size_t)taps * p.kchunks * p.b_block_stride;
+    const size_t a_stage = p.a_bytes;
+    const size_t ab_stage = a_stage + (size_t)p.b_stage_blocks * p.b_block_stride;
+    const int steps_per_tile = (p.halo ? 3 : taps) * p.kchunks;
+    int ctas = 1, stages = 0;
+    p.b_resident = 0;
+    auto fit = [&](size_t budget, bool resident) {
+        const size_t fixed = resident ? b_all : 0, per = resident ? a_stage : ab_stage;
+        if (fixed + 2 * per > budget) return 0;
+        size_t s_ = (budget - fixed) / per;
+        return (int)(s_ > (size_t)kMaxStages ? kMaxStages : s_);
+    };
+    const bool can_res = p.n_tiles == 1;
+    const bool tmem2 = p.tmem_cols * 2 <= 512;
+    const int want = steps_per_tile < 4 ? 4 : (steps_per_tile < kMaxStages ? steps_per_tile : kMaxStages);   // >= one tile of look-ahead
+    int s2r = (can_res && tmem2) ? fit(kTwoCta, true) : 0, s2s = tmem2 ? fit(kTwoCta, false) : 0;
+    int s1r = can_res ? fit(kOneCta, true) : 0, s1s = fit(kOneCta, false);
+    if (s2r >= 3) { ctas = 2; stages = s2r; p.b_resident = 1; }
+    else if (s1r >= 3) { ctas = 1; stages = s1r; p.b_resident = 1; }
+    else if (s2s >= 4) { ctas = 2; stages = s2s; }
+    else { ctas = 1; stages = s1s; }
+    if (stages > want + 2 && stages > 4) stages = want + 2 > 4 ? want + 2 : 4;
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) stages = 2;
+    B2_REQUIRE(stages >= 2, "conv: tile does not fit in shared memory (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
     p.num_stages = stages;
-    L->smem = per_stage * stages + 1024;
+    L->smem = (size_t)stages * (p.b_resident ? a_stage : ab_stage) + (p.b_resident ? b_all : 0) + 1024;
     p.out = (__nv_bfloat16*)out; p.out_cstride = out_cstride; p.out_coff = out_coff;
     p.res = (const __nv_bfloat16*)residual; p.res_cstride = res_cstride; p.res_coff = res_coff;
     p.bias = bias; p.act = act;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_nb * p.n_tiles;
-    const int sms = b2_num_sms();
-    L->grid = total_tiles < sms ? total_tiles : sms;
+    const int slots = b2_num_sms() * ctas;
+    L->grid = total_tiles < slots ? total_tiles : slots;
 
     // ---- A maps: (C, W', H', B) views of the NHWC input -------------------------------------------------
     const CUtensorMapSwizzle sw = swizzle_for(p.BK);
-    const cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.NB};
+    const cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)p.TW, (cuuint32_t)(p.halo ? p.TH + 2 : p.TH), (cuuint32_t)p.NB};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const char* base = (const char*)in + (size_t)in_coff * 2;
     const int nmaps = stride == 1 ? 1 : 4;
