@@ -52,6 +52,7 @@ struct alignas(64) ConvParams {
     const __nv_bfloat16* res; int res_cstride, res_coff;
     const float* bias;
     int act;
+    int wide;                 // 1: output (and residual) chunks are 32-byte aligned -> 256-bit accesses
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo, uint32_t layout) {
@@ -60,7 +61,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo,
            ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
 
-// bias + activation + residual + bf16 pack + store of one 16-column chunk held in registers
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// SiLU(x) = x / (1 + 2^(-x log2 e)): two MUFU ops and three FP32 ops, flush-to-zero (no denormal fix-up code)
+__device__ __forceinline__ float silu_fast(float x) { return x * rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&o)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&o)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]),
+                 "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "l"(p));
+}
+
+// bias + activation + residual + bf16 pack + store of one 16-column chunk held in registers.
+// WIDE: pointers are 32-byte aligned -> one 256-bit access per thread (a full L2 sector per instruction).
+template <bool WIDE>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], const float* __restrict__ sb, int act, int nv,
                                                __nv_bfloat16* __restrict__ optr, const __nv_bfloat16* __restrict__ rptr) {
     float f[16];
@@ -72,28 +89,36 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], const fl
     }
     if (act) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = silu_f(f[i]);
+        for (int i = 0; i < 16; ++i) f[i] = silu_fast(f[i]);
     }
     if (nv == 16) {
+        uint32_t o[8];
         if (rptr) {
-            const uint4 r0 = *reinterpret_cast<const uint4*>(rptr);
-            const uint4 r1 = *reinterpret_cast<const uint4*>(rptr + 8);
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            uint32_t rr[8];
+            if (WIDE) ld_global_v8(rptr, rr);
+            else {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(rptr);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(rptr + 8);
+                rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { f[2 * i] += bf16_lo(rr[i]); f[2 * i + 1] += bf16_hi(rr[i]); }
         }
-        uint4 o0, o1;
-        o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-        o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-        o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-        o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-        *reinterpret_cast<uint4*>(optr) = o0;
-        *reinterpret_cast<uint4*>(optr + 8) = o1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+        if (WIDE) st_global_v8(optr, o);
+        else {
+            *reinterpret_cast<uint4*>(optr) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(optr + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
     } else {
-        for (int i = 0; i < nv; ++i) {
-            float x = f[i];
-            if (rptr) x += __bfloat162float(rptr[i]);
-            optr[i] = __float2bfloat16_rn(x);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < nv) {
+                float x = f[i];
+                if (rptr) x += __bfloat162float(rptr[i]);
+                optr[i] = __float2bfloat16_rn(x);
+            }
         }
     }
 }
@@ -268,8 +293,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                 if (two) tmem_ld16(t_addr + j2 * 16, v1);
                 tmem_ld_wait();
                 if (valid) {
-                    epilogue_chunk(v0, s_bias + j * 16, p.act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
-                    if (two) epilogue_chunk(v1, s_bias + j2 * 16, p.act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                    if (p.wide) {
+                        epilogue_chunk<true>(v0, s_bias + j * 16, p.act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                        if (two) epilogue_chunk<true>(v1, s_bias + j2 * 16, p.act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                    } else {
+                        epilogue_chunk<false>(v0, s_bias + j * 16, p.act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                        if (two) epilogue_chunk<false>(v1, s_bias + j2 * 16, p.act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                    }
                 }
             }
             tc_fence_before();
@@ -434,6 +464,8 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     p.out = (__nv_bfloat16*)out; p.out_cstride = out_cstride; p.out_coff = out_coff;
     p.res = (const __nv_bfloat16*)residual; p.res_cstride = res_cstride; p.res_coff = res_coff;
     p.bias = bias; p.act = act;
+    p.wide = (out_cstride % 16 == 0 && out_coff % 16 == 0 && (uintptr_t)out % 32 == 0 &&
+              (!residual || (res_cstride % 16 == 0 && res_coff % 16 == 0 && (uintptr_t)residual % 32 == 0))) ? 1 : 0;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_nb * p.n_tiles;
     const int slots = b2_num_sms() * ctas;
     L->grid = total_tiles < slots ? total_tiles : slots;
