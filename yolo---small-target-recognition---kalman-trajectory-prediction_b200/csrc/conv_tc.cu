@@ -61,6 +61,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo,
            ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // SiLU(x) = x / (1 + 2^(-x log2 e)): two MUFU ops and three FP32 ops, flush-to-zero (no denormal fix-up code)
@@ -166,93 +171,109 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     const int groups = p.halo ? 3 : taps;                 // pipeline stages consumed per K chunk
     const int taps_per_group = p.halo ? 3 : 1;
 
+    // Producer and MMA warps run their loops with the whole warp (uniform control flow keeps descriptors and
+    // addresses in uniform registers); one elected lane issues the TMA / tcgen05 instructions.
     if (warp == 0) {
-        if (lane == 0) {
-            // ===================== TMA producer =====================
-            if (p.b_resident) {
-                mbar_expect_tx(&bres_bar, (uint32_t)(taps * p.kchunks) * p.b_block_bytes);
-                for (int tap = 0; tap < taps; ++tap)
-                    for (int kc = 0; kc < p.kchunks; ++kc)
-                        tma_load_2d(smem_b + (size_t)(tap * p.kchunks + kc) * p.b_block_stride, &p.tmB, &bres_bar, tap * p.Cin + kc * p.BK, 0);
-            }
-            const uint32_t stage_tx = p.a_tx + (p.b_resident ? 0u : p.b_stage_blocks * p.b_block_bytes);
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_idx = tile % p.n_tiles;
-                int m_idx = tile / p.n_tiles;
-                const int w0 = (m_idx % p.tiles_w) * p.TW; m_idx /= p.tiles_w;
-                const int h0 = (m_idx % p.tiles_h) * p.TH;
-                const int n0 = (m_idx / p.tiles_h) * p.NB;
-                for (int g = 0; g < groups; ++g) {
-                    int map = 0, cw, chh;
-                    if (p.halo) {                       // g == kw: rows h0-1 .. h0+TH, columns w0+kw-1 .. +7
-                        cw = w0 + g - 1; chh = h0 - 1;
+        // ===================== TMA producer =====================
+        const bool leader = elect_one();
+        const int halo = p.halo, b_res = p.b_resident, kchunks = p.kchunks, BK = p.BK, Cin = p.Cin, num_stages = p.num_stages;
+        const int ksz = p.ksize, pad = p.pad, stride = p.stride, n_tiles = p.n_tiles, n_tile = p.n_tile;
+        const int tiles_w = p.tiles_w, tiles_h = p.tiles_h, TW = p.TW, TH = p.TH, NB = p.NB;
+        const uint32_t a_bytes = p.a_bytes, b_blk = p.b_block_stride, b_stage_blocks = p.b_stage_blocks;
+        if (b_res && leader) {
+            mbar_expect_tx(&bres_bar, (uint32_t)(taps * kchunks) * p.b_block_bytes);
+            for (int tap = 0; tap < taps; ++tap)
+                for (int kc = 0; kc < kchunks; ++kc)
+                    tma_load_2d(smem_b + (size_t)(tap * kchunks + kc) * b_blk, &p.tmB, &bres_bar, tap * Cin + kc * BK, 0);
+        }
+        const uint32_t stage_tx = p.a_tx + (b_res ? 0u : b_stage_blocks * p.b_block_bytes);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_idx = tile % n_tiles;
+            int m_idx = tile / n_tiles;
+            const int w0 = (m_idx % tiles_w) * TW; m_idx /= tiles_w;
+            const int h0 = (m_idx % tiles_h) * TH;
+            const int n0 = (m_idx / tiles_h) * NB;
+            for (int g = 0; g < groups; ++g) {
+                int map = 0, cw, chh;
+                if (halo) {                       // g == kw: rows h0-1 .. h0+TH, columns w0+kw-1 .. +7
+                    cw = w0 + g - 1; chh = h0 - 1;
+                } else {
+                    const int kh = g / ksz, kw = g % ksz;
+                    if (stride == 1) {
+                        cw = w0 + kw - pad; chh = h0 + kh - pad;
                     } else {
-                        const int kh = g / p.ksize, kw = g % p.ksize;
-                        if (p.stride == 1) {
-                            cw = w0 + kw - p.pad; chh = h0 + kh - p.pad;
-                        } else {
-                            const int ih0 = kh - p.pad, iw0 = kw - p.pad;       // input = 2*out + i?0
-                            const int ph = ih0 & 1, pw = iw0 & 1;
-                            map = ph * 2 + pw;
-                            chh = h0 + (ih0 - ph) / 2; cw = w0 + (iw0 - pw) / 2;
-                        }
+                        const int ih0 = kh - pad, iw0 = kw - pad;       // input = 2*out + i?0
+                        const int ph = ih0 & 1, pw = iw0 & 1;
+                        map = ph * 2 + pw;
+                        chh = h0 + (ih0 - ph) / 2; cw = w0 + (iw0 - pw) / 2;
                     }
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                }
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (leader) {
                         mbar_expect_tx(&full_bar[stage], stage_tx);
-                        tma_load_4d(smem_a + (size_t)stage * p.a_bytes, &p.tmA[map], &full_bar[stage], kc * p.BK, cw, chh, n0);
-                        if (!p.b_resident) {
-                            uint8_t* bdst = smem_b + (size_t)stage * p.b_stage_blocks * p.b_block_stride;
+                        tma_load_4d(smem_a + (size_t)stage * a_bytes, &p.tmA[map], &full_bar[stage], kc * BK, cw, chh, n0);
+                        if (!b_res) {
+                            uint8_t* bdst = smem_b + (size_t)stage * b_stage_blocks * b_blk;
                             for (int t = 0; t < taps_per_group; ++t) {
-                                const int tap = p.halo ? t * 3 + g : g;
-                                tma_load_2d(bdst + (size_t)t * p.b_block_stride, &p.tmB, &full_bar[stage], tap * p.Cin + kc * p.BK, n_idx * p.n_tile);
+                                const int tap = halo ? t * 3 + g : g;
+                                tma_load_2d(bdst + (size_t)t * b_blk, &p.tmB, &full_bar[stage], tap * Cin + kc * BK, n_idx * n_tile);
                             }
                         }
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            // InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B, N>>3 at 17, M>>4 at 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            const int mma_per_step = p.BK / 16;
-            if (p.b_resident) { mbar_wait(&bres_bar, 0); tc_fence_after(); }
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_addr = tmem_base + (uint32_t)(acc * p.n_tile);
-                uint32_t first = 1;
-                for (int g = 0; g < groups; ++g) {
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_base = smem_u32(smem_a + (size_t)stage * p.a_bytes);
+        // ===================== MMA issuer =====================
+        const bool leader = elect_one();
+        // InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B, N>>3 at 17, M>>4 at 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        // shared-memory matrix descriptors: hi word is invariant, lo word = (address >> 4) | LBO field
+        const uint32_t desc_hi = ((p.sbo >> 4) & 0x3FFFu) | (1u << 14) | (p.swizzle_code << 29);
+        const uint32_t a_lo0 = ((smem_u32(smem_a) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t b_lo0 = ((smem_u32(smem_b) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t a_stage16 = p.a_bytes >> 4, kh16 = p.kh_step >> 4, b_blk16 = p.b_block_stride >> 4;
+        const int halo = p.halo, b_res = p.b_resident, kchunks = p.kchunks, num_stages = p.num_stages, n_tile = p.n_tile;
+        const uint32_t b_stage_blocks = p.b_stage_blocks;
+        const int mma_per_step = p.BK / 16;
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        if (b_res) { mbar_wait(&bres_bar, 0); tc_fence_after(); }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + (uint32_t)(acc * n_tile);
+            uint32_t accum = 0;
+            for (int g = 0; g < groups; ++g) {
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage16;
                         for (int t = 0; t < taps_per_group; ++t) {
-                            const int tap = p.halo ? t * 3 + g : g;
-                            const uint32_t b_addr = p.b_resident
-                                ? smem_u32(smem_b + (size_t)(tap * p.kchunks + kc) * p.b_block_stride)
-                                : smem_u32(smem_b + ((size_t)stage * p.b_stage_blocks + t) * p.b_block_stride);
-                            const uint64_t da = make_smem_desc(a_base + (uint32_t)t * p.kh_step, p.sbo, p.swizzle_code);
-                            const uint64_t db = make_smem_desc(b_addr, p.sbo, p.swizzle_code);
+                            const int tap = halo ? t * 3 + g : g;
+                            const uint32_t blk = b_res ? (uint32_t)(tap * kchunks + kc) : (uint32_t)stage * b_stage_blocks + (uint32_t)t;
+                            const uint32_t ta_lo = a_lo + (uint32_t)t * kh16, tb_lo = b_lo0 + blk * b_blk16;
                             for (int j = 0; j < mma_per_step; ++j) {
                                 // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                                tc_mma_bf16(d_addr, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, first ? 0u : 1u);
-                                first = 0;
+                                tc_mma_bf16(d_addr, ((uint64_t)desc_hi << 32) | (ta_lo + 2u * j), ((uint64_t)desc_hi << 32) | (tb_lo + 2u * j), idesc, accum);
+                                accum = 1;
                             }
                         }
                         tc_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    accum = 1;
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[acc]);                      // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (leader) tc_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
