@@ -5,16 +5,22 @@
 // 1x1 convs of Detect (head.py:93-96).
 //
 // GEMM view:  D[M = B*Ho*Wo pixels, N = Cout] = sum over (tap, channel chunk) A[M, BK] * W[N, BK]^T
-//   * M tile = 128 output pixels arranged as an (NB x TH x TW) patch, so that the A operand of filter tap
-//     (kh,kw) is ONE tiled 4-D TMA box of the NHWC input shifted by (kw-pad, kh-pad); image borders are
-//     the TMA's out-of-bounds zero fill (= conv zero padding).  Stride-2 convs read one of four
-//     parity-decimated views of the input (even/odd rows x even/odd columns), each again a plain tiled map.
-//   * The box's innermost extent is BK channels = 128/64/32 bytes -> SWIZZLE_128B/64B/32B K-major
-//     canonical UMMA layout, consumed by tcgen05.mma (M=128, N=n_tile, K=16) straight from shared memory.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..5 =
-//     epilogue (TMEM -> registers -> +bias -> SiLU -> (+residual) -> bf16 -> global channel slice).
-//   * Persistent CTAs (grid = min(tiles, #SM)), multi-stage smem ring (mbarrier full/empty), two TMEM
-//     accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * M tile = 128 output pixels.  "tap" mode (1x1, stride 2, small maps): the tile is an (NB x TH x TW)
+//     patch and the A operand of filter tap (kh,kw) is ONE tiled 4-D TMA box of the NHWC input shifted by
+//     (kw-pad, kh-pad).  "halo" mode (3x3 stride 1): the tile is 16 rows x 8 columns and ONE box of 18 rows
+//     per (kw, channel chunk) serves the three kh taps -- the tap operands are the same shared-memory tile
+//     at row offsets 0 / 8 / 16 (swizzle-atom aligned), so the input is fetched 3.4x instead of 9x.
+//     Image borders are the TMA's out-of-bounds zero fill (= conv zero padding).  Stride-2 convs read one
+//     of four parity-decimated views of the input, each again a plain tiled map.
+//   * Channels are cut into a "segment" of 64-channel chunks (128-byte rows, SWIZZLE_128B) and, when Cin is
+//     not a multiple of 64, a second segment of 32- or 16-channel chunks (SWIZZLE_64B / 32B), all in the
+//     K-major canonical UMMA layout consumed by tcgen05.mma (M=128, N=n_tile, K=16) from shared memory.
+//   * Weights stay resident in shared memory for the life of the CTA when they fit (all P2/P3-level layers).
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (whole warp runs the loop with
+//     uniform control flow, one elected lane issues), warps 2..9 = epilogue (TMEM -> registers -> +bias ->
+//     SiLU -> (+residual) -> bf16 -> 256-bit stores into the output channel slice).
+//   * Persistent CTAs (1 or 2 per SM), multi-stage smem ring (mbarrier full/empty), two TMEM accumulator
+//     stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * Output goes to a channel slice [coff, coff+Cout) of a wider NHWC buffer: torch.cat / chunk of
 //     C2f / SPPF / Concat / Detect become offset writes and offset reads.
 #include "common.cuh"
@@ -28,38 +34,40 @@ constexpr int kEpiWarps = 8;                       // two warps per TMEM lane qu
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int kMaxNTile = 256;
 
-struct alignas(64) ConvParams {
+// One K segment: `kchunks` chunks of `bk` channels starting at channel `c_off`.
+struct alignas(64) Seg {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
+    int c_off, bk, kchunks;
+    uint32_t a_tx;            // bytes one A box delivers
+    uint32_t b_block_bytes;   // n_tile * bk * 2
+    uint32_t b_block_stride;  // rounded up to 1024
+    uint32_t b_base;          // resident weights: offset of this segment's blocks inside the weight region
+    uint32_t kh_step16;       // halo mode: (8 rows * row bytes) >> 4
+    uint32_t desc_hi;         // high word of the shared-memory matrix descriptor (SBO, version, swizzle)
+};
+
+struct alignas(64) ConvParams {
+    Seg seg[2];
+    int nseg;
     int B, Ho, Wo;
     int TW, TH, NB;
     int tiles_w, tiles_h, tiles_nb;
     int n_tiles, n_tile, Cout;
     int Cin, ksize, stride, pad;
-    int BK, kchunks, num_stages;
-    int halo;                 // 1: 3x3 stride-1 "halo" mode -- one (TH+2) x 8 pixel box per (kw, K chunk), shared by the 3 kh taps
+    int num_stages;
+    int halo;                 // 1: 3x3 stride-1 "halo" mode
     int b_resident;           // 1: every weight block stays in shared memory for the lifetime of the CTA
     uint32_t a_bytes;         // shared-memory stride of one A stage (1024-aligned)
-    uint32_t a_tx;            // bytes one A box delivers
-    uint32_t b_block_bytes;   // n_tile * BK * 2
-    uint32_t b_block_stride;  // rounded up to 1024
-    uint32_t b_stage_blocks;  // streamed weights: blocks per stage (1, or 3 in halo mode)
-    uint32_t kh_step;         // halo mode: bytes between the operand starts of consecutive kh taps (8 rows)
+    uint32_t b_stage_stride;  // streamed weights: bytes of weight blocks per stage
+    uint32_t b_res_bytes;     // resident weights: total bytes delivered by the preload
     uint32_t tmem_cols;
-    uint32_t swizzle_code;    // UMMA layout type: 2 = 128B, 4 = 64B, 6 = 32B
-    uint32_t sbo;             // 8 rows * row bytes
     __nv_bfloat16* out; int out_cstride, out_coff;
     const __nv_bfloat16* res; int res_cstride, res_coff;
     const float* bias;
     int act;
     int wide;                 // 1: output (and residual) chunks are 32-byte aligned -> 256-bit accesses
 };
-
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo, uint32_t layout) {
-    // cute::UMMA::SmemDescriptor (sm100): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
-}
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -146,9 +154,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tmA[0]);
-        if (p.stride == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
-        tma_prefetch_desc(&p.tmB);
+        for (int s = 0; s < p.nseg; ++s) {
+            tma_prefetch_desc(&p.seg[s].tmA[0]);
+            if (p.stride == 2) { tma_prefetch_desc(&p.seg[s].tmA[1]); tma_prefetch_desc(&p.seg[s].tmA[2]); tma_prefetch_desc(&p.seg[s].tmA[3]); }
+            tma_prefetch_desc(&p.seg[s].tmB);
+        }
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 32 * kEpiWarps); }
         mbar_init(&bres_bar, 1);
@@ -170,23 +180,27 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     const int taps = p.ksize * p.ksize;
     const int groups = p.halo ? 3 : taps;                 // pipeline stages consumed per K chunk
     const int taps_per_group = p.halo ? 3 : 1;
+    const int nseg = p.nseg;
 
     // Producer and MMA warps run their loops with the whole warp (uniform control flow keeps descriptors and
     // addresses in uniform registers); one elected lane issues the TMA / tcgen05 instructions.
     if (warp == 0) {
         // ===================== TMA producer =====================
         const bool leader = elect_one();
-        const int halo = p.halo, b_res = p.b_resident, kchunks = p.kchunks, BK = p.BK, Cin = p.Cin, num_stages = p.num_stages;
+        const int halo = p.halo, b_res = p.b_resident, Cin = p.Cin, num_stages = p.num_stages;
         const int ksz = p.ksize, pad = p.pad, stride = p.stride, n_tiles = p.n_tiles, n_tile = p.n_tile;
         const int tiles_w = p.tiles_w, tiles_h = p.tiles_h, TW = p.TW, TH = p.TH, NB = p.NB;
-        const uint32_t a_bytes = p.a_bytes, b_blk = p.b_block_stride, b_stage_blocks = p.b_stage_blocks;
+        const uint32_t a_bytes = p.a_bytes, b_stage_stride = p.b_stage_stride;
         if (b_res && leader) {
-            mbar_expect_tx(&bres_bar, (uint32_t)(taps * kchunks) * p.b_block_bytes);
-            for (int tap = 0; tap < taps; ++tap)
-                for (int kc = 0; kc < kchunks; ++kc)
-                    tma_load_2d(smem_b + (size_t)(tap * kchunks + kc) * b_blk, &p.tmB, &bres_bar, tap * Cin + kc * BK, 0);
+            mbar_expect_tx(&bres_bar, p.b_res_bytes);
+            for (int s = 0; s < nseg; ++s) {
+                const Seg& sg = p.seg[s];
+                for (int tap = 0; tap < taps; ++tap)
+                    for (int kc = 0; kc < sg.kchunks; ++kc)
+                        tma_load_2d(smem_b + sg.b_base + (size_t)(tap * sg.kchunks + kc) * sg.b_block_stride, &sg.tmB, &bres_bar,
+                                    tap * Cin + sg.c_off + kc * sg.bk, 0);
+            }
         }
-        const uint32_t stage_tx = p.a_tx + (b_res ? 0u : b_stage_blocks * p.b_block_bytes);
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_idx = tile % n_tiles;
@@ -209,37 +223,49 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                         chh = h0 + (ih0 - ph) / 2; cw = w0 + (iw0 - pw) / 2;
                     }
                 }
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (leader) {
-                        mbar_expect_tx(&full_bar[stage], stage_tx);
-                        tma_load_4d(smem_a + (size_t)stage * a_bytes, &p.tmA[map], &full_bar[stage], kc * BK, cw, chh, n0);
-                        if (!b_res) {
-                            uint8_t* bdst = smem_b + (size_t)stage * b_stage_blocks * b_blk;
-                            for (int t = 0; t < taps_per_group; ++t) {
-                                const int tap = halo ? t * 3 + g : g;
-                                tma_load_2d(bdst + (size_t)t * b_blk, &p.tmB, &full_bar[stage], tap * Cin + kc * BK, n_idx * n_tile);
+                for (int s = 0; s < nseg; ++s) {
+                    const Seg& sg = p.seg[s];
+                    const int kchunks = sg.kchunks, bk = sg.bk, c_off = sg.c_off;
+                    const uint32_t b_blk = sg.b_block_stride;
+                    const uint32_t stage_tx = sg.a_tx + (b_res ? 0u : (uint32_t)taps_per_group * sg.b_block_bytes);
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (leader) {
+                            mbar_expect_tx(&full_bar[stage], stage_tx);
+                            tma_load_4d(smem_a + (size_t)stage * a_bytes, &sg.tmA[map], &full_bar[stage], c_off + kc * bk, cw, chh, n0);
+                            if (!b_res) {
+                                uint8_t* bdst = smem_b + (size_t)stage * b_stage_stride;
+                                for (int t = 0; t < taps_per_group; ++t) {
+                                    const int tap = halo ? t * 3 + g : g;
+                                    tma_load_2d(bdst + (size_t)t * b_blk, &sg.tmB, &full_bar[stage], tap * Cin + c_off + kc * bk, n_idx * n_tile);
+                                }
                             }
                         }
+                        __syncwarp();
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const bool leader = elect_one();
+        const uint32_t leader = elect_one() ? 1u : 0u;
         // InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B, N>>3 at 17, M>>4 at 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-        // shared-memory matrix descriptors: hi word is invariant, lo word = (address >> 4) | LBO field
-        const uint32_t desc_hi = ((p.sbo >> 4) & 0x3FFFu) | (1u << 14) | (p.swizzle_code << 29);
+        // shared-memory matrix descriptors: lo word = (address >> 4) | LBO field, hi word per segment
         const uint32_t a_lo0 = ((smem_u32(smem_a) >> 4) & 0x3FFFu) | (1u << 16);
         const uint32_t b_lo0 = ((smem_u32(smem_b) >> 4) & 0x3FFFu) | (1u << 16);
-        const uint32_t a_stage16 = p.a_bytes >> 4, kh16 = p.kh_step >> 4, b_blk16 = p.b_block_stride >> 4;
-        const int halo = p.halo, b_res = p.b_resident, kchunks = p.kchunks, num_stages = p.num_stages, n_tile = p.n_tile;
-        const uint32_t b_stage_blocks = p.b_stage_blocks;
-        const int mma_per_step = p.BK / 16;
+        const uint32_t a_stage16 = p.a_bytes >> 4, b_stage16 = p.b_stage_stride >> 4;
+        const int halo = p.halo, b_res = p.b_resident, num_stages = p.num_stages, n_tile = p.n_tile;
+        // per-segment constants in registers (nseg <= 2)
+        int sg_kch[2], sg_mps[2];
+        uint32_t sg_hi[2], sg_kh16[2], sg_blk16[2], sg_base16[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            sg_kch[s] = s < nseg ? p.seg[s].kchunks : 0; sg_mps[s] = p.seg[s].bk >> 4;
+            sg_hi[s] = p.seg[s].desc_hi; sg_kh16[s] = p.seg[s].kh_step16;
+            sg_blk16[s] = p.seg[s].b_block_stride >> 4; sg_base16[s] = p.seg[s].b_base >> 4;
+        }
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         if (b_res) { mbar_wait(&bres_bar, 0); tc_fence_after(); }
@@ -249,30 +275,32 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             const uint32_t d_addr = tmem_base + (uint32_t)(acc * n_tile);
             uint32_t accum = 0;
             for (int g = 0; g < groups; ++g) {
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    if (leader) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int kchunks = sg_kch[s], mma_per_step = sg_mps[s];
+                    const uint64_t desc_hi = (uint64_t)sg_hi[s] << 32;
+                    const uint32_t kh16 = sg_kh16[s], b_blk16 = sg_blk16[s], b_base16 = sg_base16[s];
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
                         const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage16;
                         for (int t = 0; t < taps_per_group; ++t) {
                             const int tap = halo ? t * 3 + g : g;
-                            const uint32_t blk = b_res ? (uint32_t)(tap * kchunks + kc) : (uint32_t)stage * b_stage_blocks + (uint32_t)t;
-                            const uint32_t ta_lo = a_lo + (uint32_t)t * kh16, tb_lo = b_lo0 + blk * b_blk16;
+                            const uint32_t tb_lo = b_res ? b_lo0 + b_base16 + (uint32_t)(tap * kchunks + kc) * b_blk16
+                                                         : b_lo0 + (uint32_t)stage * b_stage16 + (uint32_t)t * b_blk16;
+                            const uint32_t ta_lo = a_lo + (uint32_t)t * kh16;
                             for (int j = 0; j < mma_per_step; ++j) {
                                 // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                                tc_mma_bf16(d_addr, ((uint64_t)desc_hi << 32) | (ta_lo + 2u * j), ((uint64_t)desc_hi << 32) | (tb_lo + 2u * j), idesc, accum);
+                                tc_mma_bf16_if(leader, d_addr, desc_hi | (ta_lo + 2u * j), desc_hi | (tb_lo + 2u * j), idesc, accum);
                                 accum = 1;
                             }
                         }
-                        tc_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+                        tc_commit_if(leader, &empty_bar[stage]);     // frees the smem slot when these MMAs retire
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    accum = 1;
-                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
-            if (leader) tc_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
-            __syncwarp();
+            tc_commit_if(leader, &tfull_bar[acc]);               // accumulator complete -> epilogue
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
@@ -281,30 +309,35 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         const int half = (warp - 2) >> 2;                   // which of the two warps of the quadrant
         const int row = quad * 32 + lane;                   // row of the 128-row tile == TMEM lane
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, nb = row / (p.TW * p.TH);
+        const int n_tiles = p.n_tiles, n_tile = p.n_tile, tiles_w = p.tiles_w, tiles_h = p.tiles_h, TW = p.TW, TH = p.TH, NB = p.NB;
+        const int Wo = p.Wo, Ho = p.Ho, Bn = p.B, Cout = p.Cout, act = p.act, wide = p.wide;
+        const int out_cstride = p.out_cstride, res_cstride = p.res_cstride;
+        __nv_bfloat16* const out0 = p.out + p.out_coff;
+        const __nv_bfloat16* const res0 = p.res ? p.res + p.res_coff : nullptr;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_idx = tile % p.n_tiles;
-            int m_idx = tile / p.n_tiles;
-            const int w = (m_idx % p.tiles_w) * p.TW + tw; m_idx /= p.tiles_w;
-            const int h = (m_idx % p.tiles_h) * p.TH + th;
-            const int n = (m_idx / p.tiles_h) * p.NB + nb;
-            const bool valid = (w < p.Wo) && (h < p.Ho) && (n < p.B);
-            const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-            const int n_base = n_idx * p.n_tile;
-            __nv_bfloat16* optr = p.out + pix * p.out_cstride + p.out_coff + n_base;
-            const __nv_bfloat16* rptr = p.res ? p.res + pix * p.res_cstride + p.res_coff + n_base : nullptr;
-            const int ncols = min(p.n_tile, p.Cout - n_base);
+            const int n_idx = tile % n_tiles;
+            int m_idx = tile / n_tiles;
+            const int w = (m_idx % tiles_w) * TW + tw; m_idx /= tiles_w;
+            const int h = (m_idx % tiles_h) * TH + th;
+            const int n = (m_idx / tiles_h) * NB + nb;
+            const bool valid = (w < Wo) && (h < Ho) && (n < Bn);
+            const size_t pix = ((size_t)n * Ho + h) * Wo + w;
+            const int n_base = n_idx * n_tile;
+            __nv_bfloat16* optr = out0 + pix * out_cstride + n_base;
+            const __nv_bfloat16* rptr = res0 ? res0 + pix * res_cstride + n_base : nullptr;
+            const int ncols = min(n_tile, Cout - n_base);
             const int nchunks = (ncols + 15) >> 4;
-            if (p.n_tiles > 1) {
+            if (n_tiles > 1) {
                 // per-tile bias slice (named barrier over the epilogue warps only)
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
-                for (int i = threadIdx.x - 64; i < p.n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < p.Cout ? __ldg(p.bias + n_base + i) : 0.f;
+                for (int i = threadIdx.x - 64; i < n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < Cout ? __ldg(p.bias + n_base + i) : 0.f;
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
             }
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n_tile);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_tile);
             // this warp's chunks: half, half+2, half+4, ... ; two chunks in flight per iteration
             for (int j = half; j < nchunks; j += 4) {
                 const int j2 = j + 2;
@@ -314,12 +347,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                 if (two) tmem_ld16(t_addr + j2 * 16, v1);
                 tmem_ld_wait();
                 if (valid) {
-                    if (p.wide) {
-                        epilogue_chunk<true>(v0, s_bias + j * 16, p.act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
-                        if (two) epilogue_chunk<true>(v1, s_bias + j2 * 16, p.act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                    if (wide) {
+                        epilogue_chunk<true>(v0, s_bias + j * 16, act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                        if (two) epilogue_chunk<true>(v1, s_bias + j2 * 16, act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
                     } else {
-                        epilogue_chunk<false>(v0, s_bias + j * 16, p.act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
-                        if (two) epilogue_chunk<false>(v1, s_bias + j2 * 16, p.act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                        epilogue_chunk<false>(v0, s_bias + j * 16, act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                        if (two) epilogue_chunk<false>(v1, s_bias + j2 * 16, act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
                     }
                 }
             }
@@ -360,6 +393,8 @@ CUtensorMapSwizzle swizzle_for(int bk) {
     return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
+inline size_t up1k(size_t v) { return (v + 1023) & ~(size_t)1023; }
+
 }  // namespace
 
 // Choose the (TW, TH, NB) patch (product 128, powers of two) that wastes the fewest tile slots.
@@ -371,7 +406,6 @@ void b2_pick_tile(int B, int Ho, int Wo, int* TW, int* TH, int* NB) {
             const double slots = (double)b2_ceil_div(Wo, tw) * tw * b2_ceil_div(Ho, th) * th * b2_ceil_div(B, nb) * nb;
             double score = (double)B * Ho * Wo / slots;
             score += 1e-6 * tw - 1e-5 * nb;   // tie-break: wide rows, few images per tile
-            if (tw > 256 || th > 256 || nb > 256) continue;
             if (score > best) { best = score; bw = tw; bh = th; bn = nb; }
         }
     *TW = bw; *TH = bh; *NB = bn;
@@ -421,17 +455,25 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     if (p.halo) { p.TW = 8; p.TH = 16; p.NB = 1; }
     else b2_pick_tile(B, p.Ho, p.Wo, &p.TW, &p.TH, &p.NB);
     p.tiles_w = b2_ceil_div(p.Wo, p.TW); p.tiles_h = b2_ceil_div(p.Ho, p.TH); p.tiles_nb = b2_ceil_div(B, p.NB);
-    p.BK = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
-    p.kchunks = Cin / p.BK;
+
+    // ---- K segments: 64-channel chunks, then the remainder in 32- or 16-channel chunks ----
+    const int a_rows = p.halo ? (p.TH + 2) * 8 : 128;
+    const int taps = ksize * ksize, tpg = p.halo ? 3 : 1;
+    p.nseg = 0;
+    {
+        const int n64 = Cin / 64, rem = Cin % 64;
+        if (n64) { Seg& s = p.seg[p.nseg++]; s.c_off = 0; s.bk = 64; s.kchunks = n64; }
+        if (rem) { Seg& s = p.seg[p.nseg++]; s.c_off = n64 * 64; s.bk = (rem % 32 == 0) ? 32 : 16; s.kchunks = rem / s.bk; }
+    }
+    const int bk_max = p.seg[0].bk;
+    p.a_bytes = (uint32_t)up1k((size_t)a_rows * bk_max * 2);
+
+    // ---- N tiling: streamed-weight stage = A box + tpg weight blocks; shrink the N tile until two stages fit ----
     const int cout16 = b2_ceil_div(Cout, 16) * 16;
-    const uint32_t row_bytes0 = (uint32_t)p.BK * 2u;
     int n_cap = 256;
-    // streamed-weight stage = A box + (3 in halo mode) weight blocks: shrink the N tile until two stages fit
     while (n_cap > 16) {
-        const size_t a_st = ((p.halo ? (size_t)(p.TH + 2) * 8 : 128) * row_bytes0 + 1023) & ~(size_t)1023;
         const int nt = cout16 < n_cap ? cout16 : n_cap;
-        const size_t b_st = (p.halo ? 3 : 1) * (((size_t)nt * row_bytes0 + 1023) & ~(size_t)1023);
-        if (2 * (a_st + b_st) <= 200 * 1024) break;
+        if (2 * (p.a_bytes + tpg * up1k((size_t)nt * bk_max * 2)) <= 200 * 1024) break;
         n_cap /= 2;
     }
     if (cout16 <= n_cap) { p.n_tiles = 1; p.n_tile = cout16; }
@@ -440,26 +482,31 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
         p.n_tile = b2_ceil_div(b2_ceil_div(cout16, p.n_tiles), 16) * 16;
         p.n_tiles = b2_ceil_div(cout16, p.n_tile);
     }
-    const uint32_t row_bytes = (uint32_t)p.BK * 2u;
-    p.a_bytes = (p.halo ? (uint32_t)(p.TH + 2) * 8u : 128u) * row_bytes;
-    p.a_tx = p.a_bytes;
-    p.a_bytes = (p.a_bytes + 1023u) & ~1023u;
-    p.kh_step = p.halo ? 8u * row_bytes : 0u;
-    p.b_block_bytes = (uint32_t)p.n_tile * row_bytes;
-    p.b_block_stride = (p.b_block_bytes + 1023u) & ~1023u;
-    p.b_stage_blocks = p.halo ? 3u : 1u;
-    p.swizzle_code = p.BK == 64 ? 2u : p.BK == 32 ? 4u : 6u;
-    p.sbo = 8u * row_bytes;
+    size_t b_all = 0;
+    int steps_per_tile = 0;
+    p.b_res_bytes = 0;
+    for (int si = 0; si < p.nseg; ++si) {
+        Seg& s = p.seg[si];
+        const uint32_t row_bytes = (uint32_t)s.bk * 2u;
+        s.a_tx = (uint32_t)a_rows * row_bytes;
+        s.b_block_bytes = (uint32_t)p.n_tile * row_bytes;
+        s.b_block_stride = (uint32_t)up1k(s.b_block_bytes);
+        s.b_base = (uint32_t)b_all;
+        b_all += (size_t)taps * s.kchunks * s.b_block_stride;
+        p.b_res_bytes += (uint32_t)(taps * s.kchunks) * s.b_block_bytes;
+        s.kh_step16 = p.halo ? (8u * row_bytes) >> 4 : 0u;
+        const uint32_t sbo = 8u * row_bytes, swz = s.bk == 64 ? 2u : s.bk == 32 ? 4u : 6u;   // UMMA layout type: 128B / 64B / 32B swizzle
+        s.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
+        steps_per_tile += (p.halo ? 3 : taps) * s.kchunks;
+    }
+    p.b_stage_stride = (uint32_t)tpg * p.seg[0].b_block_stride;
     uint32_t cols = 2u * p.n_tile, pw = 32;
     while (pw < cols) pw <<= 1;
     p.tmem_cols = pw;
+
     // ---- shared memory plan: resident weights when they fit, 2 CTAs per SM when both fit ----
     const size_t kTwoCta = 106 * 1024, kOneCta = 212 * 1024;
-    const int taps = ksize * ksize;
-    const size_t b_all = (size_t)taps * p.kchunks * p.b_block_stride;
-    const size_t a_stage = p.a_bytes;
-    const size_t ab_stage = a_stage + (size_t)p.b_stage_blocks * p.b_block_stride;
-    const int steps_per_tile = (p.halo ? 3 : taps) * p.kchunks;
+    const size_t a_stage = p.a_bytes, ab_stage = a_stage + p.b_stage_stride;
     int ctas = 1, stages = 0;
     p.b_resident = 0;
     auto fit = [&](size_t budget, bool resident) {
@@ -471,8 +518,8 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     const bool can_res = p.n_tiles == 1;
     const bool tmem2 = p.tmem_cols * 2 <= 512;
     const int want = steps_per_tile < 4 ? 4 : (steps_per_tile < kMaxStages ? steps_per_tile : kMaxStages);   // >= one tile of look-ahead
-    int s2r = (can_res && tmem2) ? fit(kTwoCta, true) : 0, s2s = tmem2 ? fit(kTwoCta, false) : 0;
-    int s1r = can_res ? fit(kOneCta, true) : 0, s1s = fit(kOneCta, false);
+    const int s2r = (can_res && tmem2) ? fit(kTwoCta, true) : 0, s2s = tmem2 ? fit(kTwoCta, false) : 0;
+    const int s1r = can_res ? fit(kOneCta, true) : 0, s1s = fit(kOneCta, false);
     if (s2r >= 3) { ctas = 2; stages = s2r; p.b_resident = 1; }
     else if (s1r >= 3) { ctas = 1; stages = s1r; p.b_resident = 1; }
     else if (s2s >= 4) { ctas = 2; stages = s2s; }
@@ -491,39 +538,41 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     const int slots = b2_num_sms() * ctas;
     L->grid = total_tiles < slots ? total_tiles : slots;
 
-    // ---- A maps: (C, W', H', B) views of the NHWC input -------------------------------------------------
-    const CUtensorMapSwizzle sw = swizzle_for(p.BK);
-    const cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)p.TW, (cuuint32_t)(p.halo ? p.TH + 2 : p.TH), (cuuint32_t)p.NB};
+    // ---- tensor maps ---------------------------------------------------------------------------------
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const char* base = (const char*)in + (size_t)in_coff * 2;
     const int nmaps = stride == 1 ? 1 : 4;
-    for (int m = 0; m < nmaps; ++m) {
-        const int ph = m >> 1, pw_ = m & 1;
-        cuuint64_t dims[4], strides[3];
-        const char* ptr = base;
-        if (stride == 1) {
-            dims[0] = Cin; dims[1] = W; dims[2] = H; dims[3] = B;
-            strides[0] = (cuuint64_t)in_cstride * 2; strides[1] = (cuuint64_t)W * in_cstride * 2; strides[2] = (cuuint64_t)H * W * in_cstride * 2;
-        } else {
-            dims[0] = Cin; dims[1] = (W - pw_ + 1) / 2; dims[2] = (H - ph + 1) / 2; dims[3] = B;
-            if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
-            strides[0] = (cuuint64_t)in_cstride * 4; strides[1] = (cuuint64_t)W * in_cstride * 4; strides[2] = (cuuint64_t)H * W * in_cstride * 2;
-            ptr = base + ((size_t)ph * W + pw_) * in_cstride * 2;
+    for (int si = 0; si < p.nseg; ++si) {
+        Seg& s = p.seg[si];
+        const CUtensorMapSwizzle sw = swizzle_for(s.bk);
+        // A maps: (C, W', H', B) views of the NHWC input
+        const cuuint32_t box[4] = {(cuuint32_t)s.bk, (cuuint32_t)p.TW, (cuuint32_t)(p.halo ? p.TH + 2 : p.TH), (cuuint32_t)p.NB};
+        for (int m = 0; m < nmaps; ++m) {
+            const int ph = m >> 1, pw_ = m & 1;
+            cuuint64_t dims[4], strides[3];
+            const char* ptr = base;
+            if (stride == 1) {
+                dims[0] = Cin; dims[1] = W; dims[2] = H; dims[3] = B;
+                strides[0] = (cuuint64_t)in_cstride * 2; strides[1] = (cuuint64_t)W * in_cstride * 2; strides[2] = (cuuint64_t)H * W * in_cstride * 2;
+            } else {
+                dims[0] = Cin; dims[1] = (W - pw_ + 1) / 2; dims[2] = (H - ph + 1) / 2; dims[3] = B;
+                if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
+                strides[0] = (cuuint64_t)in_cstride * 4; strides[1] = (cuuint64_t)W * in_cstride * 4; strides[2] = (cuuint64_t)H * W * in_cstride * 2;
+                ptr = base + ((size_t)ph * W + pw_) * in_cstride * 2;
+            }
+            CUresult r = encode(&s.tmA[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(A, seg %d map %d) failed with %d", si, m, (int)r); return B2_ERR_CUDA; }
         }
-        CUresult r = encode(&p.tmA[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(A, map %d) failed with %d", m, (int)r); return B2_ERR_CUDA; }
-    }
-    // ---- B map: weights [Cout][K] K-major ---------------------------------------------------------------
-    {
+        // B map: weights [Cout][K] K-major
         const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
-        const cuuint64_t dims[2] = {K, (cuuint64_t)Cout};
-        const cuuint64_t strides[1] = {K * 2};
-        const cuuint32_t boxb[2] = {(cuuint32_t)p.BK, (cuuint32_t)p.n_tile};
+        const cuuint64_t dimsb[2] = {K, (cuuint64_t)Cout};
+        const cuuint64_t stridesb[1] = {K * 2};
+        const cuuint32_t boxb[2] = {(cuuint32_t)s.bk, (cuuint32_t)p.n_tile};
         const cuuint32_t es[2] = {1, 1};
-        CUresult r = encode(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, boxb, es,
+        CUresult r = encode(&s.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dimsb, stridesb, boxb, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(B) failed with %d", (int)r); return B2_ERR_CUDA; }
+        if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(B, seg %d) failed with %d", si, (int)r); return B2_ERR_CUDA; }
     }
     return B2_OK;
 }
