@@ -53,6 +53,15 @@ int b2_conv2d_bf16(const void* in, int B, int H, int W, int in_cstride, int in_c
                    void* out, int out_cstride, int out_coff,
                    const void* residual, int res_cstride, int res_coff, void* stream);
 
+/* Same conv over the channel concatenation [in0 | in1] (Concat, ultralytics/nn/modules/conv.py:673-683, folded into the
+ * conv's K loop).  up = 2 marks an input stored at HALF the conv's resolution: nn.Upsample(None, 2, 'nearest')
+ * (yolov8-p2.yaml:33,42,47) is folded into the TMA loads (1x1 stride-1 convs only).  H x W: conv input resolution.
+ * Weights [Cout][k][k][C0+C1].  in1 may be NULL (single input). */
+int b2_conv2d_cat_bf16(const void* in0, int cstride0, int coff0, int C0, int up0,
+                       const void* in1, int cstride1, int coff1, int C1, int up1,
+                       int B, int H, int W, const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                       void* out, int out_cstride, int out_coff, void* stream);
+
 /* Stem: letterbox-pad + BGR->RGB + /255 + Conv(3->C0, k3 s2) + SiLU in one pass over uint8 frames
  * (data/augment.py:1692-1733 LetterBox pad value 114; engine/predictor.py:152-175 preprocess;
  * model.0 of yolov8-p2.yaml).  frames: [B][src_h][src_w][3] uint8 BGR.  The letterboxed canvas is

@@ -66,10 +66,16 @@ def test_engine_every_layer_matches_oracle_on_identical_inputs(name, B, H, W):
     worst = 0.0
     for op in P.ops:
         if op[0] == eng_mod.OP_CONV:
-            _, ib, ioff, cin, ob, ooff, cout, k, s, act, rb, roff, woff, boff = op
+            _, ib, ioff, cin, ob, ooff, cout, k, s, act, rb, roff, woff, boff = op[:14]
+            ib2, ioff2, cin2, up0, up1 = op[14:19]
+            xin = buf(ib)[..., ioff:ioff + cin]
+            if ib2 >= 0:                                            # folded Concat([Upsample(a), b])
+                x2 = buf(ib2)[..., ioff2:ioff2 + cin2]
+                xin = np.concatenate([xin.repeat(up0, 1).repeat(up0, 2), x2.repeat(up1, 1).repeat(up1, 2)], -1)
+                cin = cin + cin2
             w = weights.bf16_bits_to_f32(np.frombuffer(blob, np.uint16, count=cout * k * k * cin, offset=woff)).reshape(cout, k, k, cin)
             bias = np.frombuffer(blob, np.float32, count=cout, offset=boff)
-            xin = buf(ib)[..., ioff:ioff + cin].transpose(0, 3, 1, 2)
+            xin = xin.transpose(0, 3, 1, 2)
             ref = onet.conv2d(xin, np.ascontiguousarray(w.transpose(0, 3, 1, 2)), bias, s, k // 2)
             if act:
                 ref = onet.silu(ref)

@@ -93,6 +93,33 @@ def test_conv_channel_slices_and_strides():
     assert np.all(got[..., :64] == 7.0) and np.all(got[..., 96:] == 7.0)      # neighbours untouched
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 24, 64, 32, 48), (1, 32, 40, 128, 64, 96), (3, 8, 8, 32, 80, 64), (1, 6, 10, 256, 128, 128)])
+def test_conv_over_upsample_concat_matches_oracle(shape):
+    """C2f.cv1 over Concat([Upsample(x_lo), skip]) (yolov8-p2.yaml:33-36) with the upsample and the concat folded
+    into the conv's TMA loads (zero-stride tensor-map dimensions replicate each low-resolution pixel 2x2)."""
+    from b200dt import ops
+
+    torch = _t()
+    B, H, W, C0, C1, Cout = shape
+    g = np.random.default_rng(sum(shape))
+    lo = _rand_bf16(g, (B, H // 2, W // 2, C0))
+    skip = _rand_bf16(g, (B, H, W, C1))
+    w = _rand_bf16(g, (Cout, C0 + C1, 1, 1), 1.0 / np.sqrt(C0 + C1))
+    b = g.standard_normal(Cout).astype(np.float32) * 0.1
+    cat = np.concatenate([lo.repeat(2, 1).repeat(2, 2), skip], -1)
+    ref = onet.silu(onet.conv2d(cat.transpose(0, 3, 1, 2), w, b, 1, 0))
+    y = ops.conv2d_cat_bf16(_bf16_tensor(lo), _bf16_tensor(skip), _bf16_tensor(weights.pack_ohwi(w)), torch.from_numpy(b).cuda(), up0=2)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y.float().cpu().numpy().transpose(0, 3, 1, 2), ref, rtol=6e-3, atol=6e-3)
+    # plain two-source concat (no upsample), 3x3
+    a0, a1 = _rand_bf16(g, (B, H, W, C0)), _rand_bf16(g, (B, H, W, C1))
+    w3 = _rand_bf16(g, (Cout, C0 + C1, 3, 3), 1.0 / np.sqrt(9 * (C0 + C1)))
+    ref = onet.silu(onet.conv2d(np.concatenate([a0, a1], -1).transpose(0, 3, 1, 2), w3, b, 1, 1))
+    y = ops.conv2d_cat_bf16(_bf16_tensor(a0), _bf16_tensor(a1), _bf16_tensor(weights.pack_ohwi(w3)), torch.from_numpy(b).cuda(), ksize=3)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y.float().cpu().numpy().transpose(0, 3, 1, 2), ref, rtol=6e-3, atol=6e-3)
+
+
 def test_conv_rejects_bad_arguments():
     from b200dt import ops
 

@@ -63,7 +63,11 @@ def test_lowering_is_consistent(name, hw):
     written = {}
     for o in P.ops:
         if o[0] == engine.OP_CONV:
-            _, ib, ioff, cin, ob, ooff, cout, k, s, act, rb, roff, woff, boff = o
+            _, ib, ioff, cin, ob, ooff, cout, k, s, act, rb, roff, woff, boff = o[:14]
+            ib2, ioff2, cin2, up0, up1 = o[14:19]
+            if ib2 >= 0:
+                assert up0 == 2 and up1 == 1 and k == 1 and cin2 % 16 == 0 and ioff2 + cin2 <= P.bufs[ib2][2]
+                assert all(c in written.get(ib2, set()) for c in (ioff2, ioff2 + cin2 - 1)), o
             assert ioff + cin <= P.bufs[ib][2] and ooff + cout <= P.bufs[ob][2]
             assert cin % 16 == 0 and ioff % 8 == 0 and ooff % 8 == 0
             assert woff % 256 == 0 and boff % 256 == 0
@@ -81,6 +85,7 @@ def test_lowering_is_consistent(name, hw):
     w, b = weights.fold_conv_bn(sd, pfx)
     op = next(o for o in P.ops if o[0] == engine.OP_CONV)
     blob = P.blob.bytes()
+    assert sum(1 for o in P.ops if o[0] == engine.OP_UP) == 0          # upsamples are folded into the consumer convs
     got = np.frombuffer(blob, np.uint16, count=w.size, offset=op[12])
     np.testing.assert_array_equal(got, weights.f32_to_bf16_bits(weights.pack_ohwi(w)).ravel())
     np.testing.assert_array_equal(np.frombuffer(blob, np.float32, count=b.size, offset=op[13]), b)

@@ -22,6 +22,8 @@ SIGNATURES = {
     "b2_launch_count": (C.c_longlong, []),
     "b2_conv2d_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int,
                                _P, c_int, c_int, _P, c_int, c_int, _P]),
+    "b2_conv2d_cat_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                   c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "b2_stem_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
     "b2_stem_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
     "b2_preprocess_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),

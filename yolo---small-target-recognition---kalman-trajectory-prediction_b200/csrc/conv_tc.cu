@@ -33,12 +33,16 @@ constexpr int kMaxStages = 12;
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, 16-column chunks interleaved
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int kMaxNTile = 256;
+constexpr int kMaxSeg = 4;                         // up to two sources (Concat folded into the conv) x two chunk widths
 
 // One K segment: `kchunks` chunks of `bk` channels starting at channel `c_off`.
 struct alignas(64) Seg {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
-    int c_off, bk, kchunks;
+    int c_off, bk, kchunks;   // c_off: first channel in the (concatenated) GEMM-K order; src_c: first channel inside its source
+    int src_c;
+    int up;                   // 2: the source is stored at half resolution (nearest-2x upsample folded into a 5-D tensor map)
+    int h_lo;                 // up == 2: rows of one low-resolution image
     uint32_t a_tx;            // bytes one A box delivers
     uint32_t b_block_bytes;   // n_tile * bk * 2
     uint32_t b_block_stride;  // rounded up to 1024
@@ -48,7 +52,7 @@ struct alignas(64) Seg {
 };
 
 struct alignas(64) ConvParams {
-    Seg seg[2];
+    Seg seg[kMaxSeg];
     int nseg;
     int B, Ho, Wo;
     int TW, TH, NB;
@@ -232,7 +236,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (leader) {
                             mbar_expect_tx(&full_bar[stage], stage_tx);
-                            tma_load_4d(smem_a + (size_t)stage * a_bytes, &sg.tmA[map], &full_bar[stage], c_off + kc * bk, cw, chh, n0);
+                            if (sg.up == 2)     // (c, dup_w, w/2, dup_h, image*h_lo + h/2): zero-stride dims replicate each low-res pixel 2x2
+                                tma_load_5d(smem_a + (size_t)stage * a_bytes, &sg.tmA[0], &full_bar[stage], sg.src_c + kc * bk, 0, cw >> 1, 0, n0 * sg.h_lo + (chh >> 1));
+                            else
+                                tma_load_4d(smem_a + (size_t)stage * a_bytes, &sg.tmA[map], &full_bar[stage], sg.src_c + kc * bk, cw, chh, n0);
                             if (!b_res) {
                                 uint8_t* bdst = smem_b + (size_t)stage * b_stage_stride;
                                 for (int t = 0; t < taps_per_group; ++t) {
@@ -258,10 +265,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         const uint32_t a_stage16 = p.a_bytes >> 4, b_stage16 = p.b_stage_stride >> 4;
         const int halo = p.halo, b_res = p.b_resident, num_stages = p.num_stages, n_tile = p.n_tile;
         // per-segment constants in registers (nseg <= 2)
-        int sg_kch[2], sg_mps[2];
-        uint32_t sg_hi[2], sg_kh16[2], sg_blk16[2], sg_base16[2];
+        int sg_kch[kMaxSeg], sg_mps[kMaxSeg];
+        uint32_t sg_hi[kMaxSeg], sg_kh16[kMaxSeg], sg_blk16[kMaxSeg], sg_base16[kMaxSeg];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kMaxSeg; ++s) {
             sg_kch[s] = s < nseg ? p.seg[s].kchunks : 0; sg_mps[s] = p.seg[s].bk >> 4;
             sg_hi[s] = p.seg[s].desc_hi; sg_kh16[s] = p.seg[s].kh_step16;
             sg_blk16[s] = p.seg[s].b_block_stride >> 4; sg_base16[s] = p.seg[s].b_base >> 4;
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             uint32_t accum = 0;
             for (int g = 0; g < groups; ++g) {
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
+                for (int s = 0; s < kMaxSeg; ++s) {
                     const int kchunks = sg_kch[s], mma_per_step = sg_mps[s];
                     const uint64_t desc_hi = (uint64_t)sg_hi[s] << 32;
                     const uint32_t kh16 = sg_kh16[s], b_blk16 = sg_blk16[s], b_base16 = sg_base16[s];
@@ -419,18 +426,31 @@ struct B2ConvLaunch {
 
 size_t b2_conv_launch_size() { return sizeof(B2ConvLaunch); }
 
-// Build the launch descriptor (tensor maps + geometry).  `storage` must hold b2_conv_launch_size() bytes, 64B aligned.
-int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
-                    const void* w, const float* bias, int Cout, int ksize, int stride, int act,
-                    void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff) {
+// One input of a convolution: channels [coff, coff+C) of an NHWC buffer with `cstride` channels per pixel, stored
+// at full resolution (up = 1) or at half resolution (up = 2: nearest-2x upsample folded into the loads).
+struct B2ConvSrc { const void* ptr; int cstride, coff, C, up; };
+
+// Build the launch descriptor (tensor maps + geometry) for a conv whose input is the channel concatenation of
+// `nsrc` sources.  `storage` must hold b2_conv_launch_size() bytes, 64B aligned.  H x W: conv input resolution.
+int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, int H, int W,
+                       const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                       void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff) {
     B2_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize %d unsupported (1 or 3)", ksize);
     B2_REQUIRE(stride == 1 || stride == 2, "conv: stride %d unsupported (1 or 2)", stride);
-    B2_REQUIRE(Cin % 16 == 0 && Cin > 0, "conv: Cin=%d must be a positive multiple of 16", Cin);
-    B2_REQUIRE(in_cstride % 8 == 0 && in_coff % 8 == 0 && out_cstride % 8 == 0 && out_coff % 8 == 0,
-               "conv: channel strides/offsets must be multiples of 8 (16-byte TMA / vector alignment)");
+    B2_REQUIRE(nsrc >= 1 && nsrc <= 2, "conv: 1 or 2 sources");
+    int Cin = 0; bool any_up = false;
+    for (int i = 0; i < nsrc; ++i) {
+        const B2ConvSrc& sc = srcs[i];
+        B2_REQUIRE(sc.ptr && sc.C > 0 && sc.C % 16 == 0, "conv: source %d: channels=%d must be a positive multiple of 16", i, sc.C);
+        B2_REQUIRE(sc.cstride % 8 == 0 && sc.coff % 8 == 0 && (uintptr_t)sc.ptr % 16 == 0, "conv: channel strides/offsets must be multiples of 8 (16-byte TMA / vector alignment)");
+        B2_REQUIRE(sc.up == 1 || sc.up == 2, "conv: source scale must be 1 or 2");
+        if (sc.up == 2) { any_up = true; B2_REQUIRE(ksize == 1 && stride == 1 && H % 2 == 0 && W % 2 == 0, "conv: an upsampled source needs a 1x1 stride-1 conv on an even-sized map"); }
+        Cin += sc.C;
+    }
+    B2_REQUIRE(out_cstride % 8 == 0 && out_coff % 8 == 0, "conv: channel strides/offsets must be multiples of 8 (16-byte TMA / vector alignment)");
     B2_REQUIRE(!residual || (res_cstride % 8 == 0 && res_coff % 8 == 0), "conv: residual stride/offset must be multiples of 8");
     B2_REQUIRE(Cout > 0 && B > 0 && H > 0 && W > 0, "conv: bad shape");
-    B2_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)w % 16 == 0), "conv: pointers must be 16-byte aligned");
+    B2_REQUIRE(((uintptr_t)out % 16 == 0) && ((uintptr_t)w % 16 == 0), "conv: pointers must be 16-byte aligned");
     {   // opt in to the large dynamic shared memory carve-out once (not a stream operation: safe before graph capture)
         static std::once_flag once;
         static cudaError_t attr_err = cudaSuccess;
@@ -453,19 +473,34 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
         if (eff >= 0.6) p.halo = 1;
     }
     if (p.halo) { p.TW = 8; p.TH = 16; p.NB = 1; }
-    else b2_pick_tile(B, p.Ho, p.Wo, &p.TW, &p.TH, &p.NB);
+    else if (any_up) {
+        // tiles of one image, even extents (each low-resolution pixel is replicated 2x2 inside the box)
+        double best = -1;
+        for (int tw = 2; tw <= 64; tw *= 2) {
+            const int th = 128 / tw;
+            const double score = (double)p.Wo * p.Ho / ((double)b2_ceil_div(p.Wo, tw) * tw * b2_ceil_div(p.Ho, th) * th) + 1e-6 * tw;
+            if (score > best) { best = score; p.TW = tw; p.TH = th; }
+        }
+        p.NB = 1;
+    } else b2_pick_tile(B, p.Ho, p.Wo, &p.TW, &p.TH, &p.NB);
     p.tiles_w = b2_ceil_div(p.Wo, p.TW); p.tiles_h = b2_ceil_div(p.Ho, p.TH); p.tiles_nb = b2_ceil_div(B, p.NB);
 
-    // ---- K segments: 64-channel chunks, then the remainder in 32- or 16-channel chunks ----
+    // ---- K segments: per source, 64-channel chunks, then the remainder in 32- or 16-channel chunks ----
     const int a_rows = p.halo ? (p.TH + 2) * 8 : 128;
     const int taps = ksize * ksize, tpg = p.halo ? 3 : 1;
     p.nseg = 0;
+    int src_of[kMaxSeg];
     {
-        const int n64 = Cin / 64, rem = Cin % 64;
-        if (n64) { Seg& s = p.seg[p.nseg++]; s.c_off = 0; s.bk = 64; s.kchunks = n64; }
-        if (rem) { Seg& s = p.seg[p.nseg++]; s.c_off = n64 * 64; s.bk = (rem % 32 == 0) ? 32 : 16; s.kchunks = rem / s.bk; }
+        int c_base = 0;
+        for (int i = 0; i < nsrc; ++i) {
+            const int n64 = srcs[i].C / 64, rem = srcs[i].C % 64;
+            if (n64) { Seg& s = p.seg[p.nseg]; src_of[p.nseg++] = i; s.c_off = c_base; s.src_c = 0; s.bk = 64; s.kchunks = n64; }
+            if (rem) { Seg& s = p.seg[p.nseg]; src_of[p.nseg++] = i; s.c_off = c_base + n64 * 64; s.src_c = n64 * 64; s.bk = (rem % 32 == 0) ? 32 : 16; s.kchunks = rem / s.bk; }
+            c_base += srcs[i].C;
+        }
     }
-    const int bk_max = p.seg[0].bk;
+    int bk_max = 16;
+    for (int si = 0; si < p.nseg; ++si) bk_max = p.seg[si].bk > bk_max ? p.seg[si].bk : bk_max;
     p.a_bytes = (uint32_t)up1k((size_t)a_rows * bk_max * 2);
 
     // ---- N tiling: streamed-weight stage = A box + tpg weight blocks; shrink the N tile until two stages fit ----
@@ -485,21 +520,25 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     size_t b_all = 0;
     int steps_per_tile = 0;
     p.b_res_bytes = 0;
+    uint32_t b_blk_max = 0;
     for (int si = 0; si < p.nseg; ++si) {
         Seg& s = p.seg[si];
         const uint32_t row_bytes = (uint32_t)s.bk * 2u;
         s.a_tx = (uint32_t)a_rows * row_bytes;
         s.b_block_bytes = (uint32_t)p.n_tile * row_bytes;
         s.b_block_stride = (uint32_t)up1k(s.b_block_bytes);
+        b_blk_max = s.b_block_stride > b_blk_max ? s.b_block_stride : b_blk_max;
         s.b_base = (uint32_t)b_all;
         b_all += (size_t)taps * s.kchunks * s.b_block_stride;
         p.b_res_bytes += (uint32_t)(taps * s.kchunks) * s.b_block_bytes;
         s.kh_step16 = p.halo ? (8u * row_bytes) >> 4 : 0u;
         const uint32_t sbo = 8u * row_bytes, swz = s.bk == 64 ? 2u : s.bk == 32 ? 4u : 6u;   // UMMA layout type: 128B / 64B / 32B swizzle
         s.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
+        s.up = srcs[src_of[si]].up;
+        s.h_lo = H / 2;
         steps_per_tile += (p.halo ? 3 : taps) * s.kchunks;
     }
-    p.b_stage_stride = (uint32_t)tpg * p.seg[0].b_block_stride;
+    p.b_stage_stride = (uint32_t)tpg * b_blk_max;
     uint32_t cols = 2u * p.n_tile, pw = 32;
     while (pw < cols) pw <<= 1;
     p.tmem_cols = pw;
@@ -539,30 +578,45 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     L->grid = total_tiles < slots ? total_tiles : slots;
 
     // ---- tensor maps ---------------------------------------------------------------------------------
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const char* base = (const char*)in + (size_t)in_coff * 2;
     const int nmaps = stride == 1 ? 1 : 4;
     for (int si = 0; si < p.nseg; ++si) {
         Seg& s = p.seg[si];
+        const B2ConvSrc& sc = srcs[src_of[si]];
         const CUtensorMapSwizzle sw = swizzle_for(s.bk);
-        // A maps: (C, W', H', B) views of the NHWC input
-        const cuuint32_t box[4] = {(cuuint32_t)s.bk, (cuuint32_t)p.TW, (cuuint32_t)(p.halo ? p.TH + 2 : p.TH), (cuuint32_t)p.NB};
-        for (int m = 0; m < nmaps; ++m) {
-            const int ph = m >> 1, pw_ = m & 1;
-            cuuint64_t dims[4], strides[3];
-            const char* ptr = base;
-            if (stride == 1) {
-                dims[0] = Cin; dims[1] = W; dims[2] = H; dims[3] = B;
-                strides[0] = (cuuint64_t)in_cstride * 2; strides[1] = (cuuint64_t)W * in_cstride * 2; strides[2] = (cuuint64_t)H * W * in_cstride * 2;
-            } else {
-                dims[0] = Cin; dims[1] = (W - pw_ + 1) / 2; dims[2] = (H - ph + 1) / 2; dims[3] = B;
-                if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
-                strides[0] = (cuuint64_t)in_cstride * 4; strides[1] = (cuuint64_t)W * in_cstride * 4; strides[2] = (cuuint64_t)H * W * in_cstride * 2;
-                ptr = base + ((size_t)ph * W + pw_) * in_cstride * 2;
-            }
-            CUresult r = encode(&s.tmA[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr,
+        const char* base = (const char*)sc.ptr + (size_t)sc.coff * 2;
+        const cuuint64_t cs2 = (cuuint64_t)sc.cstride * 2;
+        if (sc.up == 2) {
+            // (C, dup_w = 2, W/2, dup_h = 2, B*H/2) view of the half-resolution source: the two dup dims have stride 0,
+            // so a box (bk, 2, TW/2, 2, TH/2) lands in shared memory as TH rows x TW pixels of the upsampled image.
+            const int Wl = W / 2, Hl = H / 2;
+            const cuuint64_t dims[5] = {(cuuint64_t)sc.C, 2, (cuuint64_t)Wl, 2, (cuuint64_t)B * Hl};
+            const cuuint64_t strides[4] = {0, cs2, 0, (cuuint64_t)Wl * cs2};
+            const cuuint32_t box[5] = {(cuuint32_t)s.bk, 2, (cuuint32_t)(p.TW / 2), 2, (cuuint32_t)(p.TH / 2)};
+            const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+            CUresult r = encode(&s.tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, es,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(A, seg %d map %d) failed with %d", si, m, (int)r); return B2_ERR_CUDA; }
+            if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(A upsampled, seg %d) failed with %d", si, (int)r); return B2_ERR_UNSUPPORTED; }
+        } else {
+            // A maps: (C, W', H', B) views of the NHWC input
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            const cuuint32_t box[4] = {(cuuint32_t)s.bk, (cuuint32_t)p.TW, (cuuint32_t)(p.halo ? p.TH + 2 : p.TH), (cuuint32_t)p.NB};
+            for (int m = 0; m < nmaps; ++m) {
+                const int ph = m >> 1, pw_ = m & 1;
+                cuuint64_t dims[4], strides[3];
+                const char* ptr = base;
+                if (stride == 1) {
+                    dims[0] = sc.C; dims[1] = W; dims[2] = H; dims[3] = B;
+                    strides[0] = cs2; strides[1] = (cuuint64_t)W * cs2; strides[2] = (cuuint64_t)H * W * cs2;
+                } else {
+                    dims[0] = sc.C; dims[1] = (W - pw_ + 1) / 2; dims[2] = (H - ph + 1) / 2; dims[3] = B;
+                    if (dims[1] == 0 || dims[2] == 0) { dims[1] = dims[1] ? dims[1] : 1; dims[2] = dims[2] ? dims[2] : 1; }
+                    strides[0] = cs2 * 2; strides[1] = (cuuint64_t)W * cs2 * 2; strides[2] = (cuuint64_t)H * W * cs2;
+                    ptr = base + ((size_t)ph * W + pw_) * cs2;
+                }
+                CUresult r = encode(&s.tmA[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(A, seg %d map %d) failed with %d", si, m, (int)r); return B2_ERR_CUDA; }
+            }
         }
         // B map: weights [Cout][K] K-major
         const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
@@ -575,6 +629,14 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
         if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(B, seg %d) failed with %d", si, (int)r); return B2_ERR_CUDA; }
     }
     return B2_OK;
+}
+
+int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
+                    const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                    void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff) {
+    B2_REQUIRE(Cin % 16 == 0 && Cin > 0, "conv: Cin=%d must be a positive multiple of 16", Cin);
+    const B2ConvSrc src{in, in_cstride, in_coff, Cin, 1};
+    return b2_conv_prepare_ms(storage, &src, 1, B, H, W, w, bias, Cout, ksize, stride, act, out, out_cstride, out_coff, residual, res_cstride, res_coff);
 }
 
 void b2_count_launch(int n);
@@ -594,6 +656,19 @@ extern "C" int b2_conv2d_bf16(const void* in, int B, int H, int W, int in_cstrid
     alignas(64) unsigned char storage[sizeof(B2ConvLaunch)];
     int rc = b2_conv_prepare(storage, in, B, H, W, in_cstride, in_coff, Cin, w, bias, Cout, ksize, stride, act,
                              out, out_cstride, out_coff, residual, res_cstride, res_coff);
+    if (rc != B2_OK) return rc;
+    return b2_conv_launch(storage, (cudaStream_t)stream);
+}
+
+// Conv over the channel concatenation of two inputs (Concat folded into the conv; yolov8-p2.yaml:33-54):
+// in1 may be stored at half resolution (up1 = 2: nn.Upsample(None, 2, 'nearest') folded into the TMA loads).
+extern "C" int b2_conv2d_cat_bf16(const void* in0, int cstride0, int coff0, int C0, int up0,
+                                  const void* in1, int cstride1, int coff1, int C1, int up1,
+                                  int B, int H, int W, const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                                  void* out, int out_cstride, int out_coff, void* stream) {
+    alignas(64) unsigned char storage[sizeof(B2ConvLaunch)];
+    const B2ConvSrc srcs[2] = {{in0, cstride0, coff0, C0, up0}, {in1, cstride1, coff1, C1, up1}};
+    int rc = b2_conv_prepare_ms(storage, srcs, in1 ? 2 : 1, B, H, W, w, bias, Cout, ksize, stride, act, out, out_cstride, out_coff, nullptr, 0, 0);
     if (rc != B2_OK) return rc;
     return b2_conv_launch(storage, (cudaStream_t)stream);
 }

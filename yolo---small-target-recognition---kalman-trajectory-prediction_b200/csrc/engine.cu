@@ -18,6 +18,10 @@ size_t b2_conv_launch_size();
 int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
                     const void* w, const float* bias, int Cout, int ksize, int stride, int act,
                     void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff);
+struct B2ConvSrc { const void* ptr; int cstride, coff, C, up; };
+int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, int H, int W,
+                       const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                       void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff);
 int b2_conv_launch(const void* storage, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
@@ -50,7 +54,7 @@ extern "C" long long b2_launch_count(void) { return g_launches.load(); }
 // ------------------------------------------------------------------------------------------------
 namespace {
 constexpr int kMagic = 0xB2D7;
-constexpr int kOpWords = 14;
+constexpr int kOpWords = 20;
 enum Op { OP_STEM = 1, OP_CONV = 2, OP_POOL = 3, OP_UP = 4 };
 
 struct Buf { int h, w, c; size_t off; };
@@ -131,15 +135,26 @@ extern "C" int b2_engine_create(const int32_t* plan, int plan_words, const void*
         if (s.op == OP_STEM) {
             if (i != 0 || !buf_ok(a[0])) { b2_set_error("engine_create: stem must be op 0 with a valid buffer"); return fail(B2_ERR_ARG); }
         } else if (s.op == OP_CONV) {
-            if (!buf_ok(a[0]) || !buf_ok(a[3]) || (a[9] >= 0 && !buf_ok(a[9]))) { b2_set_error("engine_create: op %d: bad buffer id", i); return fail(B2_ERR_ARG); }
+            // a: 0 in buf, 1 in coff, 2 Cin, 3 out buf, 4 out coff, 5 Cout, 6 k, 7 stride, 8 act, 9 res buf, 10 res coff,
+            //    11 weights, 12 bias, 13 second input buf (-1: none), 14 its coff, 15 its channels, 16 up of input 0, 17 up of input 1
+            const bool two = a[13] >= 0;
+            if (!buf_ok(a[0]) || !buf_ok(a[3]) || (a[9] >= 0 && !buf_ok(a[9])) || (two && !buf_ok(a[13]))) { b2_set_error("engine_create: op %d: bad buffer id", i); return fail(B2_ERR_ARG); }
             const Buf& bi = e->bufs[a[0]]; const Buf& bo = e->bufs[a[3]];
+            const int up0 = a[16] == 2 ? 2 : 1, up1 = a[17] == 2 ? 2 : 1;
+            const int Hin = bi.h * up0, Win = bi.w * up0;
+            B2ConvSrc srcs[2] = {{e->buf_ptr(a[0]), bi.c, a[1], a[2], up0}, {nullptr, 0, 0, 0, 1}};
+            if (two) {
+                const Buf& b2 = e->bufs[a[13]];
+                srcs[1] = B2ConvSrc{e->buf_ptr(a[13]), b2.c, a[14], a[15], up1};
+                if (b2.h * up1 != Hin || b2.w * up1 != Win || a[14] + a[15] > b2.c) { b2_set_error("engine_create: op %d: second input geometry mismatch", i); return fail(B2_ERR_ARG); }
+            }
             s.conv.resize(b2_conv_launch_size() + 64);
-            rc = b2_conv_prepare(s.conv_ptr(), e->buf_ptr(a[0]), B, bi.h, bi.w, bi.c, a[1], a[2],
-                                 wbase + (size_t)(uint32_t)a[11], (const float*)(wbase + (size_t)(uint32_t)a[12]), a[5], a[6], a[7], a[8],
-                                 e->buf_ptr(a[3]), bo.c, a[4], a[9] >= 0 ? e->buf_ptr(a[9]) : nullptr,
-                                 a[9] >= 0 ? e->bufs[a[9]].c : 0, a[10]);
+            rc = b2_conv_prepare_ms(s.conv_ptr(), srcs, two ? 2 : 1, B, Hin, Win,
+                                    wbase + (size_t)(uint32_t)a[11], (const float*)(wbase + (size_t)(uint32_t)a[12]), a[5], a[6], a[7], a[8],
+                                    e->buf_ptr(a[3]), bo.c, a[4], a[9] >= 0 ? e->buf_ptr(a[9]) : nullptr,
+                                    a[9] >= 0 ? e->bufs[a[9]].c : 0, a[10]);
             if (rc != B2_OK) return fail(rc);
-            const int pad = a[6] / 2, ho = (bi.h + 2 * pad - a[6]) / a[7] + 1, wo = (bi.w + 2 * pad - a[6]) / a[7] + 1;
+            const int pad = a[6] / 2, ho = (Hin + 2 * pad - a[6]) / a[7] + 1, wo = (Win + 2 * pad - a[6]) / a[7] + 1;
             if (ho != bo.h || wo != bo.w || a[4] + a[5] > bo.c || a[1] + a[2] > bi.c) {
                 b2_set_error("engine_create: op %d: conv geometry does not match its buffers", i); return fail(B2_ERR_ARG);
             }

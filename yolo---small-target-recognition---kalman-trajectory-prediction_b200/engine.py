@@ -13,7 +13,11 @@ bf16 buffers in which every ``torch.cat`` / ``chunk`` of C2f (block.py:315-319),
   * each Detect level owns a ``[B][h*w][64 + ceil8(nc)]`` logits buffer filled by ``cv2[l][2]`` / ``cv3[l][2]``.
 
 Plan layout (int32 words): ``[magic, n_bufs, n_ops, n_levels, nc, lstride]``, ``n_bufs x (h, w, c)``,
-``n_levels x (buf, stride)``, ``n_ops x 14`` (opcode + 13 arguments, see ``OP_*`` below).
+``n_levels x (buf, stride)``, ``n_ops x 20`` (opcode + 19 arguments, see ``OP_*`` below).
+
+``Concat([Upsample(a), b])`` feeding a C2f is *virtual*: its ``cv1`` 1x1 conv takes both tensors as inputs and the
+nearest-2x upsample is folded into the conv's TMA loads (zero-stride tensor-map dimensions), so neither the upsampled
+tensor nor the concatenation is ever written.
 """
 from __future__ import annotations
 
@@ -25,7 +29,7 @@ from . import _lib, cfg, weights
 
 MAGIC = 0xB2D7
 OP_STEM, OP_CONV, OP_POOL, OP_UP = 1, 2, 3, 4
-OP_WORDS = 14
+OP_WORDS = 20
 ACT_NONE, ACT_SILU = 0, 1
 
 
@@ -106,8 +110,23 @@ def lower(spec, state_dict, H, W):
     # ---- placement: which concat slice does each layer write into? ----
     placement = {}
     extra_copies = []                     # (layer, concat buffer slice) when a layer feeds a second Concat
+    consumers = {}
     for L in layers:
-        if L["type"] != "Concat":
+        fs = L["f"] if isinstance(L["f"], tuple) else (L["f"],)
+        for f in fs:
+            consumers.setdefault(src(L["i"], f), []).append(L["i"])
+    virtual = {}                          # concat layer -> [(source layer, up)], upsample layers folded away
+    for L in layers:
+        if L["type"] != "Concat" or len(L["f"]) != 2:
+            continue
+        i = L["i"]
+        a, b = (src(i, f) for f in L["f"])
+        cons = consumers.get(i, [])
+        if (layers[a]["type"] == "Upsample" and consumers.get(a) == [i] and len(cons) == 1 and layers[cons[0]]["type"] == "C2f"
+                and layers[b]["type"] != "Upsample"):
+            virtual[i] = [(src(a, layers[a]["f"]), 2), (b, 1)]
+    for L in layers:
+        if L["type"] != "Concat" or L["i"] in virtual:
             continue
         i = L["i"]
         h, w = hw[i]
@@ -134,18 +153,21 @@ def lower(spec, state_dict, H, W):
         if c % 16:
             raise NotImplementedError(f"{what}: {c} channels -- the tcgen05 conv path needs multiples of 16")
 
-    def emit_conv(prefix, inp, out, k, s, bn, res=None):
-        """inp/out/res: (buf, coff, C)."""
+    def emit_conv(prefix, inp, out, k, s, bn, res=None, inp2=None, ups=(1, 1)):
+        """inp/out/res/inp2: (buf, coff, C).  inp2: second input of a folded Concat; ups: resolution factors of the inputs."""
         w, b = weights.folded(sd, prefix, bn)
         cout, cin = w.shape[0], w.shape[1]
-        assert cin == inp[2] and cout == out[2], (prefix, w.shape, inp, out)
-        check_c(cin, prefix + " input")
+        assert cin == inp[2] + (inp2[2] if inp2 else 0) and cout == out[2], (prefix, w.shape, inp, inp2, out)
+        check_c(inp[2], prefix + " input")
+        if inp2:
+            check_c(inp2[2], prefix + " second input")
         woff = P.blob.add(weights.f32_to_bf16_bits(weights.pack_ohwi(w)))
         boff = P.blob.add(b.astype(np.float32))
         hb, wb, _ = P.bufs[out[0]]
         P.flops += 2 * hb * wb * cout * cin * k * k
-        P.ops.append([OP_CONV, inp[0], inp[1], cin, out[0], out[1], cout, k, s, ACT_SILU if bn else ACT_NONE,
-                      res[0] if res else -1, res[1] if res else 0, woff, boff])
+        P.ops.append([OP_CONV, inp[0], inp[1], inp[2], out[0], out[1], cout, k, s, ACT_SILU if bn else ACT_NONE,
+                      res[0] if res else -1, res[1] if res else 0, woff, boff,
+                      inp2[0] if inp2 else -1, inp2[1] if inp2 else 0, inp2[2] if inp2 else 0, ups[0], ups[1], 0])
         P.named[prefix] = out
 
     for L in layers:
@@ -169,9 +191,13 @@ def lower(spec, state_dict, H, W):
         elif t == "C2f":
             c, n = L["c"], L["n"]
             check_c(c, p + " hidden")
-            inp = P.loc[src(i, L["f"])]
+            s_in = src(i, L["f"])
             cat = P.new_buf(h, w, (2 + n) * c)
-            emit_conv(p + ".cv1", inp, (cat, 0, 2 * c), 1, 1, True)
+            if s_in in virtual:                                   # Concat([Upsample(a), b]) folded into cv1
+                (la, ua), (lb, ub) = virtual[s_in]
+                emit_conv(p + ".cv1", P.loc[la], (cat, 0, 2 * c), 1, 1, True, inp2=P.loc[lb], ups=(ua, ub))
+            else:
+                emit_conv(p + ".cv1", P.loc[s_in], (cat, 0, 2 * c), 1, 1, True)
             for j in range(n):
                 a = (cat, (1 + j) * c, c)
                 tmp = P.new_buf(h, w, c)
@@ -192,6 +218,8 @@ def lower(spec, state_dict, H, W):
             emit_conv(p + ".cv2", (cat, 0, 4 * c_), out, 1, 1, True)
             P.loc[i] = out
         elif t == "Upsample":
+            if any(i == src(c_, layers[c_]["f"][0]) for c_ in virtual):
+                continue                              # folded into the consumer conv's loads
             inp = P.loc[src(i, L["f"])]
             out = out_loc(L)
             P.ops.append([OP_UP, inp[0], inp[1], inp[2], 2, out[0], out[1]] + [0] * (OP_WORDS - 7))
@@ -297,11 +325,17 @@ class Engine:
             fl, desc, nbytes = 0, "", 0
             if op[0] == OP_CONV:
                 _, ib, ioff, cin, ob, ooff, cout, k, s, act, rb = op[:11]
+                ib2, cin2 = op[14], op[16]
                 h, w, _c = self.plan.bufs[ob]
                 hi, wi, _ci = self.plan.bufs[ib]
-                fl = 2 * h * w * cout * cin * k * k * self.B
-                nbytes = (hi * wi * cin + h * w * cout * (2 if rb >= 0 else 1)) * 2 * self.B + cout * cin * k * k * 2
-                desc = f"{cin}->{cout} k{k} s{s} @{h}x{w}"
+                in_elems = hi * wi * cin
+                if ib2 >= 0:
+                    h2, w2, _c2 = self.plan.bufs[ib2]
+                    in_elems += h2 * w2 * cin2
+                ct = cin + (cin2 if ib2 >= 0 else 0)
+                fl = 2 * h * w * cout * ct * k * k * self.B
+                nbytes = (in_elems + h * w * cout * (2 if rb >= 0 else 1)) * 2 * self.B + cout * ct * k * k * 2
+                desc = f"{ct}->{cout} k{k} s{s} @{h}x{w}" + ("  [up2|cat]" if ib2 >= 0 else "")
             elif op[0] == OP_STEM:
                 h, w, _c = self.plan.bufs[op[1]]
                 fl = 2 * h * w * op[3] * 27 * self.B

@@ -49,6 +49,25 @@ def conv2d_bf16(x, w, bias, ksize, stride=1, act=True, out=None, out_coff=0, in_
     return out
 
 
+def conv2d_cat_bf16(x0, x1, w, bias, ksize=1, stride=1, act=True, up0=1, up1=1, out=None, out_coff=0, stream=None):
+    """Conv over cat([up(x0), up(x1)], channel) without materialising the upsample or the concat.
+    x0, x1: [B][h][w][C] bf16 (full NHWC tensors; up_i = 2 means stored at half the conv resolution)."""
+    torch = _torch()
+    lib = _lib.load()
+    B = x0.shape[0]
+    H, W = x0.shape[1] * up0, x0.shape[2] * up0
+    cout = w.shape[0]
+    pad = ksize // 2
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, cout), dtype=torch.bfloat16, device=x0.device)
+    _lib.check(lib.b2_conv2d_cat_bf16(_lib.ptr(x0), x0.shape[3], 0, x0.shape[3], up0,
+                                      _lib.ptr(x1), x1.shape[3] if x1 is not None else 0, 0, x1.shape[3] if x1 is not None else 0, up1,
+                                      B, H, W, _lib.ptr(w), _lib.ptr(bias), cout, ksize, stride, 1 if act else 0,
+                                      _lib.ptr(out), out.shape[3], out_coff, _lib.stream_ptr(stream)))
+    return out
+
+
 def stem_u8(frames, w, bias, H, W, pad_top=0, pad_left=0, stream=None):
     """frames [B][h][w][3] uint8 BGR -> SiLU(conv3x3 s2(letterbox(frames)/255)) as [B][H/2][W/2][C0] bf16."""
     torch = _torch()
