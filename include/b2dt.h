@@ -62,15 +62,16 @@ int b2_conv2d_cat_bf16(const void* in0, int cstride0, int coff0, int C0, int up0
                        int B, int H, int W, const void* w, const float* bias, int Cout, int ksize, int stride, int act,
                        void* out, int out_cstride, int out_coff, void* stream);
 
-/* Stem: letterbox-pad + BGR->RGB + /255 + Conv(3->C0, k3 s2) + SiLU in one pass over uint8 frames
- * (data/augment.py:1692-1733 LetterBox pad value 114; engine/predictor.py:152-175 preprocess;
- * model.0 of yolov8-p2.yaml).  frames: [B][src_h][src_w][3] uint8 BGR.  The letterboxed canvas is
- * H x W with the frame at (pad_top, pad_left).  w: [C0][3][3][3] fp32 (o,kh,kw,c_rgb) BN-folded,
- * NOT divided by 255 (the kernel scales).  out: [B][H/2][W/2][out_cstride] bf16. */
+/* Stem: letterbox-pad + BGR->RGB + /255 + Conv(3->C0, k3 s2) + SiLU in one pass over uint8 frames, on the tensor
+ * cores (data/augment.py:1692-1733 LetterBox pad value 114; engine/predictor.py:152-175 preprocess; model.0 of
+ * yolov8-p2.yaml).  frames: [B][src_h][src_w][3] uint8 BGR.  The letterboxed canvas is H x W with the frame at
+ * (pad_top, pad_left).  w: [C0][32] bf16, BN-folded, GEMM-K index (kh*3+kw)*3 + c_rgb, entries 27..31 zero, NOT
+ * divided by 255 (the epilogue scales in fp32).  bias: [C0] fp32.  out: [B][H/2][W/2][out_cstride] bf16. */
 int b2_stem_u8(const uint8_t* frames, int B, int src_h, int src_w, int H, int W, int pad_top, int pad_left,
-               const float* w, const float* bias, int C0, void* out, int out_cstride, int out_coff, void* stream);
-/* Same stem for float tensors BCHW RGB in [0,1] (data/loaders.py:566-638 LoadTensor). dtype: 0 fp32, 1 bf16 */
-int b2_stem_f32(const void* bchw, int dtype, int B, int H, int W, const float* w, const float* bias, int C0,
+               const void* w, const float* bias, int C0, void* out, int out_cstride, int out_coff, void* stream);
+/* Same stem for float tensors BCHW RGB in [0,1] (data/loaders.py:566-638 LoadTensor): the tensor core consumes
+ * bf16(255 x), exact for uint8-derived inputs.  dtype: 0 fp32, 1 bf16 */
+int b2_stem_f32(const void* bchw, int dtype, int B, int H, int W, const void* w, const float* bias, int C0,
                 void* out, int out_cstride, int out_coff, void* stream);
 
 /* Stand-alone preprocess (engine/predictor.py:152-175 + LetterBox pad-only path): uint8 HWC BGR ->

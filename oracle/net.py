@@ -22,8 +22,8 @@ Two numeric modes:
   "fp32"  the reference's arithmetic (pinned against the reference run in-process,
           tests/golden/net_*.npz).
   "bf16"  the same graph with the rounding points of the B200 engine: BN-folded weights rounded
-          to bf16 (except the stem, which the engine evaluates with fp32 weights on exact uint8
-          pixel values), fp32 accumulation, every stored activation rounded to bf16.
+          to bf16, the stem input taken as bf16(255 x) (exact uint8 pixel values), fp32
+          accumulation, every stored activation rounded to bf16.
 """
 from __future__ import annotations
 
@@ -225,7 +225,7 @@ class Net:
         """Conv.forward_fuse (conv.py:83-93): SiLU(conv(x)+b) with BN folded."""
         if prefix not in self._cache:
             w, b = fold_conv_bn(self.sd, prefix)
-            if self.mode == "bf16" and not stem:
+            if self.mode == "bf16":
                 w = bf16_round(w)
             self._cache[prefix] = (w, b)
         w, b = self._cache[prefix]
@@ -297,6 +297,9 @@ class Net:
     def forward(self, x, record=False):
         """x: (B,3,H,W) float32 in [0,1] (RGB).  Returns the per-level raw head maps."""
         x = np.asarray(x, np.float32)
+        if self.mode == "bf16":
+            # the engine's stem consumes bf16(255 x) (exact for uint8-derived inputs) and scales by 1/255 in fp32
+            x = (bf16_round(x * np.float32(255.0)) / np.float32(255.0)).astype(np.float32)
         ys = []
         for L in self.spec["layers"]:
             f = L["f"]

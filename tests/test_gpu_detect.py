@@ -88,7 +88,8 @@ def test_engine_every_layer_matches_oracle_on_identical_inputs(name, B, H, W):
             np.testing.assert_allclose(got, ref, rtol=1e-2, atol=1e-2 * max(1.0, float(np.abs(ref).max()) / 16))
         elif op[0] == eng_mod.OP_STEM:
             _, ob, ooff, c0, woff, boff = op[:6]
-            w = np.frombuffer(blob, np.float32, count=c0 * 27, offset=woff).reshape(c0, 3, 3, 3).transpose(0, 3, 1, 2)
+            w = weights.bf16_bits_to_f32(np.frombuffer(blob, np.uint16, count=c0 * 32, offset=woff)).reshape(c0, 32)[:, :27]
+            w = w.reshape(c0, 3, 3, 3).transpose(0, 3, 1, 2)
             bias = np.frombuffer(blob, np.float32, count=c0, offset=boff)
             ref = onet.silu(onet.conv2d(x, np.ascontiguousarray(w), bias, 2, 1))
             got = buf(ob)[..., ooff:ooff + c0].transpose(0, 3, 1, 2)

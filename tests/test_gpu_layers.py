@@ -149,9 +149,9 @@ def test_stem_u8_matches_oracle(hw, src, pad):
     canvas = np.full((2, H, W, 3), 114, np.uint8)
     canvas[:, pad[0]:pad[0] + src[0], pad[1]:pad[1] + src[1]] = frames
     x = pp.preprocess(list(canvas))
-    ref = onet.bf16_round(onet.silu(onet.conv2d(x, w, b, 2, 1)))
-    y = ops.stem_u8(torch.from_numpy(frames).cuda(), torch.from_numpy(weights.pack_ohwi(w)).cuda(), torch.from_numpy(b).cuda(),
-                    H, W, pad[0], pad[1])
+    ref = onet.bf16_round(onet.silu(onet.conv2d(x, onet.bf16_round(w), b, 2, 1)))     # bf16 weights, exact uint8 inputs
+    wp = torch.from_numpy(weights.pack_stem(w).view(np.int16)).cuda().view(torch.bfloat16)
+    y = ops.stem_u8(torch.from_numpy(frames).cuda(), wp, torch.from_numpy(b).cuda(), H, W, pad[0], pad[1])
     got = y.float().cpu().numpy().transpose(0, 3, 1, 2)
     np.testing.assert_allclose(got, ref, rtol=8e-3, atol=2e-3)
     # stand-alone preprocess (BasePredictor.preprocess): exact

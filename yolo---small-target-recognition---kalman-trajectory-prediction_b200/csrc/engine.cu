@@ -214,7 +214,7 @@ extern "C" int b2_engine_forward_u8(b2_engine_t* e, const uint8_t* frames, int s
     const int* a = e->steps[0].a;
     char* wbase = e->arena + e->weights_off;
     const Buf& bo = e->bufs[a[0]];
-    int rc = b2_stem_u8(frames, e->B, src_h, src_w, e->H, e->W, pad_top, pad_left, (const float*)(wbase + (size_t)(uint32_t)a[3]),
+    int rc = b2_stem_u8(frames, e->B, src_h, src_w, e->H, e->W, pad_top, pad_left, (const void*)(wbase + (size_t)(uint32_t)a[3]),
                         (const float*)(wbase + (size_t)(uint32_t)a[4]), a[2], e->buf_ptr(a[0]), bo.c, a[1], stream);
     if (rc != B2_OK) return rc;
     return run_tail(e, (cudaStream_t)stream);
@@ -233,7 +233,7 @@ extern "C" int b2_engine_profile_u8(b2_engine_t* e, const uint8_t* frames, int s
     char* wbase = e->arena + e->weights_off;
     int rc = B2_OK;
     cudaEventRecord(ev[0], st);
-    rc = b2_stem_u8(frames, e->B, src_h, src_w, e->H, e->W, pad_top, pad_left, (const float*)(wbase + (size_t)(uint32_t)a[3]),
+    rc = b2_stem_u8(frames, e->B, src_h, src_w, e->H, e->W, pad_top, pad_left, (const void*)(wbase + (size_t)(uint32_t)a[3]),
                     (const float*)(wbase + (size_t)(uint32_t)a[4]), a[2], e->buf_ptr(a[0]), e->bufs[a[0]].c, a[1], stream);
     cudaEventRecord(ev[1], st);
     for (size_t i = 1; i < n && rc == B2_OK; ++i) {
@@ -254,7 +254,7 @@ extern "C" int b2_engine_forward_f32(b2_engine_t* e, const void* bchw, int dtype
     const int* a = e->steps[0].a;
     char* wbase = e->arena + e->weights_off;
     const Buf& bo = e->bufs[a[0]];
-    int rc = b2_stem_f32(bchw, dtype, e->B, e->H, e->W, (const float*)(wbase + (size_t)(uint32_t)a[3]),
+    int rc = b2_stem_f32(bchw, dtype, e->B, e->H, e->W, (const void*)(wbase + (size_t)(uint32_t)a[3]),
                          (const float*)(wbase + (size_t)(uint32_t)a[4]), a[2], e->buf_ptr(a[0]), bo.c, a[1], stream);
     if (rc != B2_OK) return rc;
     return run_tail(e, (cudaStream_t)stream);

@@ -8,64 +8,114 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------
 // Stem: LetterBox pad (114) + BGR->RGB + /255 (engine/predictor.py:152-175, data/augment.py:1717-1728)
-// fused with model.0 = Conv(3 -> C0, k3, s2) + SiLU.  fp32 weights on exact uint8 pixel values.
-// One thread per output pixel, all C0 channels; weights broadcast from shared memory.
+// fused with model.0 = Conv(3 -> C0, k3, s2) + SiLU, on the tensor cores.
+//
+// Implicit GEMM with K = 27 (padded to 32): each of the 128 threads of a CTA builds the im2col row of ONE output
+// pixel (27 uint8 pixel values, exact in bf16) directly in shared memory in the SWIZZLE_64B K-major UMMA layout,
+// one thread issues two tcgen05.mma (M=128, N=C0, K=16) against the resident bf16 weight tile, and the same 128
+// threads read their accumulator row back from TMEM (thread r <-> TMEM lane r), apply 1/255 and the folded bias
+// in fp32, SiLU, and store C0 bf16 channels.  Several CTAs per SM overlap load / MMA / epilogue phases.
 // ------------------------------------------------------------------------------------------------
-template <int C0, typename Loader>
-__global__ void __launch_bounds__(256) stem_kernel(Loader ld, int H, int W, int Ho, int Wo, const float* __restrict__ w,
-                                                   const float* __restrict__ bias, float in_scale,
-                                                   __nv_bfloat16* __restrict__ out, int out_cstride, int out_coff) {
-    __shared__ __align__(16) float ws[27 * C0];
-    __shared__ float bs[C0];
-    // w: [C0][3][3][3] (o, kh, kw, c_rgb)  ->  ws[(kh*3+kw)*3+c][o]
-    for (int i = threadIdx.x; i < 27 * C0; i += blockDim.x) {
-        const int o = i / 27, t = i % 27;
-        ws[t * C0 + o] = w[i];
+constexpr int kStemThreads = 128;
+constexpr int kStemMaxC0 = 128;
+
+__device__ __forceinline__ uint32_t swz64_chunk_off(int row, int chunk) {   // byte offset of 16-byte chunk `chunk` of 64-byte row `row`
+    return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
+}
+
+template <typename Loader>
+__global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B, int H, int W, int Ho, int Wo,
+                                                               const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                                                               float in_scale, int C0, int n_tile, uint32_t tmem_cols,
+                                                               __nv_bfloat16* __restrict__ out, int out_cstride, int out_coff,
+                                                               int tiles_w, int tiles_h, int total_tiles) {
+    __shared__ __align__(1024) uint8_t s_a[128 * 64];
+    __shared__ __align__(1024) uint8_t s_b[kStemMaxC0 * 64];
+    __shared__ __align__(16) float s_bias[kStemMaxC0];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(&s_tmem, tmem_cols); tmem_relinquish(); }
+    // weights [C0][32] bf16 (k = (kh*3+kw)*3 + c_rgb, 27..31 zero) -> swizzled 64-byte rows; rows >= C0 zero
+    for (int i = tid; i < n_tile * 4; i += kStemThreads) {
+        const int n = i >> 2, c = i & 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (n < C0) v = *reinterpret_cast<const uint4*>(w + (size_t)n * 32 + c * 8);
+        *reinterpret_cast<uint4*>(s_b + swz64_chunk_off(n, c)) = v;
     }
-    for (int i = threadIdx.x; i < C0; i += blockDim.x) bs[i] = bias[i];
+    for (int i = tid; i < n_tile; i += kStemThreads) s_bias[i] = i < C0 ? bias[i] : 0.f;
+    fence_proxy_async();
+    tc_fence_before();
     __syncthreads();
-    const int wo = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ho = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const int b = blockIdx.z;
-    if (wo >= Wo || ho >= Ho) return;
-    float acc[C0];
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = (uint64_t)(((512u >> 4) & 0x3FFFu) | (1u << 14) | (4u << 29)) << 32;   // SBO = 8 rows x 64 B, SWIZZLE_64B
+    const uint32_t a_lo = ((smem_u32(s_a) >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((smem_u32(s_b) >> 4) & 0x3FFFu) | (1u << 16);
+    const int tw = tid & 15, th = tid >> 4;                 // 16 x 8 output pixels per tile
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int wo = (t % tiles_w) * 16 + tw; t /= tiles_w;
+        const int ho = (t % tiles_h) * 8 + th;
+        const int b = t / tiles_h;
+        // ---- im2col row of this thread's pixel ----
+        float v[27];
 #pragma unroll
-    for (int o = 0; o < C0; ++o) acc[o] = 0.f;
+        for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int y = 2 * ho + kh - 1;
+            for (int kw = 0; kw < 3; ++kw) {
+                float rgb[3];
+                ld.load(b, 2 * ho + kh - 1, 2 * wo + kw - 1, H, W, rgb);
+                v[(kh * 3 + kw) * 3 + 0] = rgb[0]; v[(kh * 3 + kw) * 3 + 1] = rgb[1]; v[(kh * 3 + kw) * 3 + 2] = rgb[2];
+            }
+        uint32_t pk[16];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int x = 2 * wo + kw - 1;
-            float rgb[3];
-            ld.load(b, y, x, H, W, rgb);
+        for (int i = 0; i < 13; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        pk[13] = pack_bf16x2(v[26], 0.f); pk[14] = 0u; pk[15] = 0u;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = rgb[c];
-                const float4* wp = reinterpret_cast<const float4*>(&ws[((kh * 3 + kw) * 3 + c) * C0]);
+        for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(s_a + swz64_chunk_off(tid, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            tc_mma_bf16(tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, 0u);
+            tc_mma_bf16(tmem, desc_hi | (a_lo + 2u), desc_hi | (b_lo + 2u), idesc, 1u);
+            tc_commit(&s_bar);
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        const bool valid = wo < Wo && ho < Ho;
+        __nv_bfloat16* op = out + (((size_t)b * Ho + ho) * Wo + wo) * out_cstride + out_coff;
+        const uint32_t t_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int j = 0; j < n_tile; j += 16) {
+            uint32_t a[16];
+            tmem_ld16(t_addr + j, a);
+            tmem_ld_wait();
+            if (valid) {
+                uint32_t o[8];
 #pragma unroll
-                for (int o4 = 0; o4 < C0 / 4; ++o4) {
-                    const float4 ww = wp[o4];
-                    acc[4 * o4 + 0] = fmaf(v, ww.x, acc[4 * o4 + 0]);
-                    acc[4 * o4 + 1] = fmaf(v, ww.y, acc[4 * o4 + 1]);
-                    acc[4 * o4 + 2] = fmaf(v, ww.z, acc[4 * o4 + 2]);
-                    acc[4 * o4 + 3] = fmaf(v, ww.w, acc[4 * o4 + 3]);
+                for (int i = 0; i < 8; ++i) {
+                    const float x0 = fmaf(__uint_as_float(a[2 * i]), in_scale, s_bias[j + 2 * i]);
+                    const float x1 = fmaf(__uint_as_float(a[2 * i + 1]), in_scale, s_bias[j + 2 * i + 1]);
+                    o[i] = pack_bf16x2(silu_f(x0), silu_f(x1));
+                }
+                if (j + 16 <= C0) {
+                    *reinterpret_cast<uint4*>(op + j) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(op + j + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                } else if (j + 8 <= C0) {
+                    *reinterpret_cast<uint4*>(op + j) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
         }
+        tc_fence_before();
+        __syncthreads();                                     // accumulator and A tile are free for the next tile
     }
-    __nv_bfloat16* op = out + (((size_t)b * Ho + ho) * Wo + wo) * out_cstride + out_coff;
-#pragma unroll
-    for (int o8 = 0; o8 < C0 / 8; ++o8) {
-        uint4 v;
-        uint32_t* vp = &v.x;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int o = 8 * o8 + 2 * i;
-            vp[i] = pack_bf16x2(silu_f(fmaf(acc[o], in_scale, bs[o])), silu_f(fmaf(acc[o + 1], in_scale, bs[o + 1])));
-        }
-        *reinterpret_cast<uint4*>(op + 8 * o8) = v;
-    }
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
 struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left) of the canvas, border 114, outside canvas 0
@@ -79,28 +129,31 @@ struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left
     }
 };
 template <typename T>
-struct LoadPlanar {   // [B][3][H][W] RGB in [0,1]
+struct LoadPlanar {   // [B][3][H][W] RGB in [0,1]; the tensor core consumes bf16(255 x) (exact for uint8-derived inputs)
     const T* p;
     __device__ __forceinline__ void load(int b, int y, int x, int H, int W, float (&rgb)[3]) const {
         if (y < 0 || x < 0 || y >= H || x >= W) { rgb[0] = rgb[1] = rgb[2] = 0.f; return; }
         const size_t plane = (size_t)H * W;
         const T* q = p + (size_t)b * 3 * plane + (size_t)y * W + x;
-        rgb[0] = (float)q[0]; rgb[1] = (float)q[plane]; rgb[2] = (float)q[2 * plane];
+        rgb[0] = 255.f * (float)q[0]; rgb[1] = 255.f * (float)q[plane]; rgb[2] = 255.f * (float)q[2 * plane];
     }
 };
 
 template <typename Loader>
-int launch_stem(Loader ld, int B, int H, int W, const float* w, const float* bias, int C0, float in_scale,
+int launch_stem(Loader ld, int B, int H, int W, const void* w, const float* bias, int C0,
                 void* out, int out_cstride, int out_coff, cudaStream_t st) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    dim3 grid(b2_ceil_div(Wo, 32), b2_ceil_div(Ho, 8), B), block(256);
-    __nv_bfloat16* o = (__nv_bfloat16*)out;
-#define B2_STEM_CASE(C) case C: stem_kernel<C, Loader><<<grid, block, 0, st>>>(ld, H, W, Ho, Wo, w, bias, in_scale, o, out_cstride, out_coff); break;
-    switch (C0) {
-        B2_STEM_CASE(16) B2_STEM_CASE(24) B2_STEM_CASE(32) B2_STEM_CASE(40) B2_STEM_CASE(48) B2_STEM_CASE(64) B2_STEM_CASE(80)
-        default: b2_set_error("stem: C0=%d not instantiated", C0); return B2_ERR_UNSUPPORTED;
-    }
-#undef B2_STEM_CASE
+    const int n_tile = b2_ceil_div(C0, 16) * 16;
+    if (n_tile > kStemMaxC0) { b2_set_error("stem: C0=%d exceeds %d", C0, kStemMaxC0); return B2_ERR_UNSUPPORTED; }
+    uint32_t cols = 32;
+    while (cols < (uint32_t)n_tile) cols <<= 1;
+    const int tiles_w = b2_ceil_div(Wo, 16), tiles_h = b2_ceil_div(Ho, 8);
+    const long long total = (long long)tiles_w * tiles_h * B;
+    const int per_sm = (int)(512 / cols) < 8 ? (int)(512 / cols) : 8;       // TMEM columns bound the co-resident CTAs
+    const long long slots = (long long)b2_num_sms() * per_sm;
+    const int grid = (int)(total < slots ? total : slots);
+    stem_tc_kernel<Loader><<<grid, kStemThreads, 0, st>>>(ld, B, H, W, Ho, Wo, (const __nv_bfloat16*)w, bias, 1.f / 255.f, C0, n_tile, cols,
+                                                          (__nv_bfloat16*)out, out_cstride, out_coff, tiles_w, tiles_h, (int)total);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
@@ -215,20 +268,21 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* 
 }  // namespace
 
 extern "C" int b2_stem_u8(const uint8_t* frames, int B, int src_h, int src_w, int H, int W, int pad_top, int pad_left,
-                          const float* w, const float* bias, int C0, void* out, int out_cstride, int out_coff, void* stream) {
+                          const void* w, const float* bias, int C0, void* out, int out_cstride, int out_coff, void* stream) {
     B2_REQUIRE(frames && w && bias && out, "stem: null pointer");
     B2_REQUIRE(C0 % 8 == 0 && out_cstride % 8 == 0 && out_coff % 8 == 0, "stem: channel counts must be multiples of 8");
     B2_REQUIRE(pad_top >= 0 && pad_left >= 0 && pad_top + src_h <= H && pad_left + src_w <= W, "stem: frame does not fit the canvas");
+    B2_REQUIRE((uintptr_t)w % 16 == 0 && (uintptr_t)out % 16 == 0, "stem: pointers must be 16-byte aligned");
     LoadU8 ld{frames, src_h, src_w, pad_top, pad_left};
-    return launch_stem(ld, B, H, W, w, bias, C0, 1.f / 255.f, out, out_cstride, out_coff, (cudaStream_t)stream);
+    return launch_stem(ld, B, H, W, w, bias, C0, out, out_cstride, out_coff, (cudaStream_t)stream);
 }
 
-extern "C" int b2_stem_f32(const void* bchw, int dtype, int B, int H, int W, const float* w, const float* bias, int C0,
+extern "C" int b2_stem_f32(const void* bchw, int dtype, int B, int H, int W, const void* w, const float* bias, int C0,
                            void* out, int out_cstride, int out_coff, void* stream) {
     B2_REQUIRE(bchw && w && bias && out, "stem: null pointer");
     B2_REQUIRE(C0 % 8 == 0 && out_cstride % 8 == 0 && out_coff % 8 == 0, "stem: channel counts must be multiples of 8");
-    if (dtype == 0) return launch_stem(LoadPlanar<float>{(const float*)bchw}, B, H, W, w, bias, C0, 1.f, out, out_cstride, out_coff, (cudaStream_t)stream);
-    if (dtype == 1) return launch_stem(LoadPlanar<__nv_bfloat16>{(const __nv_bfloat16*)bchw}, B, H, W, w, bias, C0, 1.f, out, out_cstride, out_coff, (cudaStream_t)stream);
+    if (dtype == 0) return launch_stem(LoadPlanar<float>{(const float*)bchw}, B, H, W, w, bias, C0, out, out_cstride, out_coff, (cudaStream_t)stream);
+    if (dtype == 1) return launch_stem(LoadPlanar<__nv_bfloat16>{(const __nv_bfloat16*)bchw}, B, H, W, w, bias, C0, out, out_cstride, out_coff, (cudaStream_t)stream);
     b2_set_error("stem: dtype %d unsupported", dtype);
     return B2_ERR_UNSUPPORTED;
 }

@@ -180,7 +180,7 @@ def lower(spec, state_dict, H, W):
                 if L["k"] != 3 or L["s"] != 2 or L["c1"] != 3:
                     raise NotImplementedError("stem must be Conv(3 -> C0, k=3, s=2)")
                 wf, bf = weights.fold_conv_bn(sd, p)
-                woff = P.blob.add(weights.pack_ohwi(wf).astype(np.float32))     # [C0][kh][kw][rgb] fp32
+                woff = P.blob.add(weights.pack_stem(wf))                       # [C0][32] bf16, K = (kh,kw,rgb) padded
                 boff = P.blob.add(bf.astype(np.float32))
                 P.flops += 2 * h * w * L["c2"] * 27
                 P.ops.append([OP_STEM, out[0], out[1], L["c2"], woff, boff] + [0] * (OP_WORDS - 6))

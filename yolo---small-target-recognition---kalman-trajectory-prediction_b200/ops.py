@@ -69,7 +69,8 @@ def conv2d_cat_bf16(x0, x1, w, bias, ksize=1, stride=1, act=True, up0=1, up1=1, 
 
 
 def stem_u8(frames, w, bias, H, W, pad_top=0, pad_left=0, stream=None):
-    """frames [B][h][w][3] uint8 BGR -> SiLU(conv3x3 s2(letterbox(frames)/255)) as [B][H/2][W/2][C0] bf16."""
+    """frames [B][h][w][3] uint8 BGR -> SiLU(conv3x3 s2(letterbox(frames)/255)) as [B][H/2][W/2][C0] bf16.
+    w: [C0][32] bf16 from ``weights.pack_stem`` (CUDA tensor)."""
     torch = _torch()
     lib = _lib.load()
     B, sh, sw, _ = frames.shape

@@ -117,3 +117,11 @@ def bf16_bits_to_f32(b):
 def pack_ohwi(w):
     """[O, I, kh, kw] -> [O, kh, kw, I] (GEMM-K index = (kh*k + kw)*I + c, K-major rows per output channel)."""
     return np.ascontiguousarray(np.transpose(w, (0, 2, 3, 1)))
+
+
+def pack_stem(w):
+    """[C0, 3, kh, kw] fp32 (RGB input order) -> [C0][32] bf16 bits, GEMM-K index (kh*3+kw)*3 + c, zero padded."""
+    c0 = w.shape[0]
+    k = np.zeros((c0, 32), np.float32)
+    k[:, :27] = np.transpose(w, (0, 2, 3, 1)).reshape(c0, 27)
+    return f32_to_bf16_bits(k)
