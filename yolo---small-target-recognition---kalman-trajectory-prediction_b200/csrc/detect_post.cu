@@ -43,13 +43,18 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     const int W = p.w[lvl], H = p.h[lvl];
     const __nv_bfloat16* row = p.lv[lvl] + ((size_t)b * H * W + la) * p.lstride;
 
+    // ---- all loads first (memory-level parallelism): DFL chunk + up to two class chunks per lane ----
+    const int nchunks = (p.nc + 7) >> 3;
+    const uint4 ninf4 = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // bf16 -inf pairs
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = ninf4, q2 = ninf4;
+    if (active) {
+        q0 = ldg_nc_v4(row + sub * 8);
+        if (sub < nchunks) q1 = ldg_nc_v4(row + 64 + sub * 8);
+        if (sub + 8 < nchunks) q2 = ldg_nc_v4(row + 64 + (sub + 8) * 8);
+    }
     // ---- DFL: softmax expectation over 16 bins per side ----
     float f[8];
-    if (active) unpack8(ldg_nc_v4(row + sub * 8), f);
-    else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = 0.f;
-    }
+    unpack8(q0, f);
     float m = f[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
@@ -70,11 +75,12 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
 
     // ---- classes: max logit / argmax over nc ----
     float best = -INFINITY; int bidx = 0x7fffffff;
-    const int nchunks = (p.nc + 7) >> 3;
     const size_t dense_base = (size_t)b * (4 + p.nc) * p.A + a;
     for (int ck = sub; ck < nchunks; ck += 8) {
         float c[8];
-        if (active) unpack8(ldg_nc_v4(row + 64 + ck * 8), c);
+        if (ck == sub) unpack8(q1, c);
+        else if (ck == sub + 8) unpack8(q2, c);
+        else if (active) unpack8(ldg_nc_v4(row + 64 + ck * 8), c);
         else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) c[i] = -INFINITY;
@@ -162,6 +168,7 @@ constexpr int kNmsThreads = 1024;
 constexpr int kSmemSort = 2048;      // pairs sorted entirely in shared memory
 constexpr int kMaxCand = 65536;      // alive bitmask (shared memory) covers this many sorted candidates
 constexpr int kMaxKeep = 1024;
+constexpr int kFastN = 704;          // bit-matrix path: 704 boxes (11 KB) + 704 x 22 words (62 KB) of dynamic shared memory
 
 struct NmsParams {
     const float* cand; const int32_t* cand_idx; const int32_t* cand_count; int cand_cap, B;
@@ -218,6 +225,55 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
     }
     n = min(n, p.max_nms);
 
+    const int max_keep = min(p.max_det, kMaxKeep);
+    if (p.mode == 0 && n <= kFastN) {
+        // ---- fast path (exact greedy NMS): all pairwise tests in parallel into an n x n bit matrix, then one warp
+        //      walks the candidates in score order OR-ing the suppression rows of the boxes it keeps ----
+        extern __shared__ uint32_t s_dyn[];
+        float4* fbox = reinterpret_cast<float4*>(s_dyn);                  // [kFastN]
+        uint32_t* mat = s_dyn + kFastN * 4;                                 // [n][W]
+        const int Wd = (n + 31) >> 5;
+        for (int i = tid; i < n; i += kNmsThreads) {
+            const float* c = cand + (size_t)pay[i] * 6;
+            const float off = p.agnostic ? 0.f : __fmul_rn(c[5], p.max_wh);
+            fbox[i] = make_float4(__fadd_rn(c[0], off), __fadd_rn(c[1], off), __fadd_rn(c[2], off), __fadd_rn(c[3], off));
+        }
+        __syncthreads();
+        for (int t = tid; t < n * Wd; t += kNmsThreads) {
+            const int i = t / Wd, wj = t - i * Wd;
+            uint32_t bits = 0;
+            if (wj * 32 + 31 > i) {
+                const float4 bi = fbox[i];
+                const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+                const int j0 = max(wj * 32, i + 1), j1 = min(wj * 32 + 32, n);
+                for (int j = j0; j < j1; ++j) {
+                    const float4 bj = fbox[j];
+                    const float iw = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
+                    const float ih = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
+                    const float inter = __fmul_rn(iw, ih);
+                    const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+                    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
+                    if (iou > p.iou_thres) bits |= 1u << (j & 31);
+                }
+            }
+            mat[t] = bits;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t removed = 0;                                           // lane l owns word l (Wd <= 32)
+            int nk = 0;
+            for (int i = 0; i < n && nk < max_keep; ++i) {
+                const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
+                if (!((r >> (i & 31)) & 1u)) {
+                    if (tid == 0) s_keep[nk] = i;
+                    ++nk;
+                    if (tid < Wd) removed |= mat[i * Wd + tid];
+                }
+            }
+            if (tid == 0) s_nkeep = nk;
+        }
+        __syncthreads();
+    } else {
     // sorted, class-offset boxes (nms.py:144,150: boxes = x[:, :4] + cls * max_wh, fp32) + alive bitmask
     float4* sbox = p.ws_box + (size_t)b * p.P_max;
     for (int i = tid; i < n; i += kNmsThreads) {
@@ -232,7 +288,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
     if (tid == 0) { s_cur = 0; s_nkeep = 0; s_done = 0; }
     __syncthreads();
 
-    const int max_keep = min(p.max_det, kMaxKeep);
     while (true) {
         // -- next alive index >= s_cur (warp 0 scans the bitmask) --
         if (tid < 32) {
@@ -287,6 +342,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
             }
         }
         __syncthreads();
+    }
     }
 
     const int nk = s_nkeep;
@@ -375,7 +431,12 @@ extern "C" int b2_nms(const float* cand, const int32_t* cand_idx, const int32_t*
     p.ws_keys = (unsigned long long*)ws; ws += (size_t)B * P * 8;
     p.ws_pay = (int32_t*)ws;
     p.P_max = (int)P;
-    nms_kernel<<<B, kNmsThreads, 0, (cudaStream_t)stream>>>(p);
+    const size_t dyn = (size_t)kFastN * 16 + (size_t)kFastN * ((kFastN + 31) / 32) * 4;
+    {
+        static cudaError_t attr_err = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        B2_CUDA(attr_err);
+    }
+    nms_kernel<<<B, kNmsThreads, dyn, (cudaStream_t)stream>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;

@@ -172,32 +172,40 @@ __device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
     return r;
 }
 
+// One CTA per (image, 8-channel chunk): the whole H x W map of that chunk sits in shared memory; each MaxPool2d(5,1,2)
+// is a row pass then a column pass (2 x 4 comparisons per pixel instead of 24), chained three times.
 __global__ void __launch_bounds__(256) sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int cstride, int coff, int C) {
-    const int chunks = C / 8;
-    const size_t total = (size_t)B * H * W * chunks;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int ck = (int)(idx % chunks);
-    size_t pix = idx / chunks;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
-    const uint32_t ninf = 0xFF80FF80u;   // bf16 -inf pair
-    uint4 m5 = make_uint4(ninf, ninf, ninf, ninf), m9 = m5, m13 = m5;
-    for (int dy = -6; dy <= 6; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= H) continue;
-        for (int dx = -6; dx <= 6; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= W) continue;
-            const uint4 v = *reinterpret_cast<const uint4*>(buf + (((size_t)b * H + yy) * W + xx) * cstride + coff + ck * 8);
-            m13 = max_bf16x8(m13, v);
-            if (abs(dy) <= 4 && abs(dx) <= 4) m9 = max_bf16x8(m9, v);
-            if (abs(dy) <= 2 && abs(dx) <= 2) m5 = max_bf16x8(m5, v);
+    extern __shared__ uint4 s_pool[];              // [2][H*W]
+    const int ck = blockIdx.x, b = blockIdx.y, HW = H * W;
+    uint4* cur = s_pool;
+    uint4* tmp = s_pool + HW;
+    __nv_bfloat16* base = buf + (size_t)b * HW * cstride + coff + ck * 8;
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) cur[p] = *reinterpret_cast<const uint4*>(base + (size_t)p * cstride);
+    __syncthreads();
+    for (int level = 1; level <= 3; ++level) {
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) {      // row pass: max over x-2..x+2
+            const int x = p % W, r0 = p - x;
+            uint4 m = cur[p];
+            if (x >= 1) m = max_bf16x8(m, cur[p - 1]);
+            if (x >= 2) m = max_bf16x8(m, cur[p - 2]);
+            if (x + 1 < W) m = max_bf16x8(m, cur[p + 1]);
+            if (x + 2 < W) m = max_bf16x8(m, cur[p + 2]);
+            (void)r0;
+            tmp[p] = m;
         }
+        __syncthreads();
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) {      // column pass: max over y-2..y+2
+            const int y = p / W;
+            uint4 m = tmp[p];
+            if (y >= 1) m = max_bf16x8(m, tmp[p - W]);
+            if (y >= 2) m = max_bf16x8(m, tmp[p - 2 * W]);
+            if (y + 1 < H) m = max_bf16x8(m, tmp[p + W]);
+            if (y + 2 < H) m = max_bf16x8(m, tmp[p + 2 * W]);
+            cur[p] = m;
+            *reinterpret_cast<uint4*>(base + (size_t)p * cstride + (size_t)level * C) = m;
+        }
+        __syncthreads();
     }
-    __nv_bfloat16* o = buf + (((size_t)b * H + y) * W + x) * cstride + coff + ck * 8;
-    *reinterpret_cast<uint4*>(o + C) = m5;
-    *reinterpret_cast<uint4*>(o + 2 * C) = m9;
-    *reinterpret_cast<uint4*>(o + 3 * C) = m13;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,8 +297,10 @@ extern "C" int b2_stem_f32(const void* bchw, int dtype, int B, int H, int W, con
 
 extern "C" int b2_sppf_pool(void* buf, int B, int H, int W, int cstride, int coff, int C, void* stream) {
     B2_REQUIRE(C % 8 == 0 && cstride % 8 == 0 && coff % 8 == 0 && coff + 4 * C <= cstride, "sppf_pool: bad channel layout");
-    const size_t total = (size_t)B * H * W * (C / 8);
-    sppf_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, B, H, W, cstride, coff, C);
+    const size_t smem = (size_t)2 * H * W * sizeof(uint4);
+    B2_REQUIRE(smem <= 200 * 1024, "sppf_pool: %dx%d map does not fit in shared memory", H, W);
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sppf_pool_kernel<<<dim3(C / 8, B), 256, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, B, H, W, cstride, coff, C);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;

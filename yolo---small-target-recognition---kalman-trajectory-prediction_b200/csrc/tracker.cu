@@ -105,12 +105,33 @@ __device__ __forceinline__ float iou_ref(const float4& d, const float4& t) {
     return uni <= 0.f ? 0.f : inter / uni;
 }
 
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        s_warp[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const int warp_off = warp ? s_warp[warp - 1] : 0;
+    *total = s_warp[(blockDim.x >> 5) - 1];
+    const int r = warp_off + inc - v;
+    __syncthreads();
+    return r;
+}
+
 constexpr int kAssocThreads = 512;
 constexpr int kMaxDetsSmem = 1024;
 
 // One CTA per stream.  Greedy descending-IoU matching == repeat { every free detection picks its best free
 // track (row max); a pair is accepted iff no other free detection beats it on that track (column max) }.
-__global__ void __launch_bounds__(kAssocThreads) associate_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
+__global__ void __launch_bounds__(kAssocThreads) associate_global_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
                                                                 const int32_t* __restrict__ det_counts) {
     __shared__ float4 s_det[kMaxDetsSmem];
     __shared__ int s_dmatch[kMaxDetsSmem];
@@ -170,6 +191,92 @@ __global__ void __launch_bounds__(kAssocThreads) associate_kernel(const Bank b, 
         __syncthreads();
     }
     for (int d = tid; d < b.max_dets; d += kAssocThreads) b.det_match[(size_t)s * b.max_dets + d] = d < D ? s_dmatch[d] : -2;
+}
+
+// Same algorithm with the stream's LIVE tracks compacted into shared memory first (box, id, slot): the rounds then
+// touch no global memory.  Dynamic shared memory: C * 28 bytes.
+__global__ void __launch_bounds__(kAssocThreads) associate_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
+                                                                const int32_t* __restrict__ det_counts) {
+    extern __shared__ uint8_t s_raw[];
+    float4* l_box = reinterpret_cast<float4*>(s_raw);                    // [C]
+    int* l_id = reinterpret_cast<int*>(l_box + b.C);                      // [C]
+    int* l_slot = l_id + b.C;                                             // [C]
+    int* l_match = l_slot + b.C;                                          // [C]
+    __shared__ float4 s_det[kMaxDetsSmem];
+    __shared__ int s_dmatch[kMaxDetsSmem];
+    __shared__ int s_best_t[kMaxDetsSmem];
+    __shared__ float s_best_iou[kMaxDetsSmem];
+    __shared__ int s_warp[32];
+    __shared__ int s_progress, s_nlive;
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kAssocThreads / 32;
+    const int D = min(det_counts[s], b.max_dets);
+    const int g0 = s * b.C;
+    for (int d = tid; d < D; d += kAssocThreads) {
+        const float* r = dets + ((size_t)s * b.max_dets + d) * det_cols;
+        s_det[d] = make_float4(r[0], r[1], r[2], r[3]);
+        s_dmatch[d] = -1;
+    }
+    // ---- compact the live tracks (slot order) ----
+    int base_live = 0;
+    for (int base = 0; base < b.C; base += kAssocThreads) {
+        const int t = base + tid;
+        const int id = t < b.C ? II(b, ID, g0 + t) : 0;
+        int total;
+        const int off = block_exclusive_scan(id != 0 ? 1 : 0, s_warp, &total);
+        if (id != 0) {
+            const int k = base_live + off;
+            l_box[k] = b.pbox[g0 + t]; l_id[k] = id; l_slot[k] = t; l_match[k] = -1;
+        }
+        base_live += total;
+    }
+    const int L = base_live;
+    __syncthreads();
+    const float thr = b.iou_thr;
+    if (D > 0 && L > 0) {
+        while (true) {
+            if (tid == 0) s_progress = 0;
+            // ---- row pass: best free track per free detection (warp per detection) ----
+            for (int d = warp; d < D; d += nwarps) {
+                if (s_dmatch[d] >= 0) continue;
+                const float4 db = s_det[d];
+                float best = -1.f; int bt = -1, bid = 0x7fffffff;
+                for (int t = lane; t < L; t += 32) {
+                    if (l_match[t] >= 0) continue;
+                    const float v = iou_ref(db, l_box[t]);
+                    const int id = l_id[t];
+                    if (v >= thr && (v > best || (v == best && id < bid))) { best = v; bt = t; bid = id; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int ot = __shfl_xor_sync(0xffffffffu, bt, o), oid = __shfl_xor_sync(0xffffffffu, bid, o);
+                    if (ob > best || (ob == best && oid < bid)) { best = ob; bt = ot; bid = oid; }
+                }
+                if (lane == 0) { s_best_t[d] = bt; s_best_iou[d] = best; }
+            }
+            __syncthreads();
+            // ---- column check: is (d, t) also the best free detection for t? ----
+            for (int d = tid; d < D; d += kAssocThreads) {
+                if (s_dmatch[d] >= 0) continue;
+                const int t = s_best_t[d];
+                if (t < 0) continue;
+                const float v = s_best_iou[d];
+                const float4 tb = l_box[t];
+                bool dominated = false;
+                for (int e = 0; e < D && !dominated; ++e) {
+                    if (e == d || s_dmatch[e] >= 0) continue;
+                    const float ve = iou_ref(s_det[e], tb);
+                    if (ve >= thr && (ve > v || (ve == v && e < d))) dominated = true;
+                }
+                if (!dominated) { l_match[t] = d; s_dmatch[d] = t; s_progress = 1; }
+            }
+            __syncthreads();
+            if (!s_progress) break;
+            __syncthreads();
+        }
+    }
+    for (int t = tid; t < L; t += kAssocThreads) if (l_match[t] >= 0) b.match[g0 + l_slot[t]] = l_match[t];
+    for (int d = tid; d < b.max_dets; d += kAssocThreads) b.det_match[(size_t)s * b.max_dets + d] = d < D ? (s_dmatch[d] >= 0 ? l_slot[s_dmatch[d]] : -1) : -2;
 }
 
 // analyze_motion_pattern (:137-163) + _calculate_direction_consistency (:165-182) over the velocity ring
@@ -309,27 +416,6 @@ __device__ void emit_slot(const Bank& b, int g, float* row, float* traj_out, int
 }
 
 constexpr int kFinishThreads = 256;
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-        s_warp[lane] = w;   // inclusive over warps
-    }
-    __syncthreads();
-    const int warp_off = warp ? s_warp[warp - 1] : 0;
-    *total = s_warp[(blockDim.x >> 5) - 1];
-    const int r = warp_off + inc - v;
-    __syncthreads();
-    return r;
-}
 
 // One CTA per stream: update / mark lost / delete / emit for existing tracks (slot order), then create.
 __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
@@ -560,7 +646,16 @@ extern "C" int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_col
     const Bank& b = t->impl.b;
     cudaStream_t st = (cudaStream_t)stream;
     bank_predict_kernel<<<b2_ceil_div(b.N, 256), 256, 0, st>>>(b);
-    associate_kernel<<<b.S, kAssocThreads, 0, st>>>(b, dets, det_cols, det_counts);
+    const size_t assoc_smem = (size_t)b.C * 28;
+    if (assoc_smem <= 160 * 1024) {
+        if (assoc_smem > 16 * 1024) {
+            static size_t granted = 0;
+            if (assoc_smem > granted) { B2_CUDA(cudaFuncSetAttribute(associate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assoc_smem)); granted = assoc_smem; }
+        }
+        associate_kernel<<<b.S, kAssocThreads, assoc_smem, st>>>(b, dets, det_cols, det_counts);
+    } else {
+        associate_global_kernel<<<b.S, kAssocThreads, 0, st>>>(b, dets, det_cols, det_counts);
+    }
     finish_kernel<<<b.S, kFinishThreads, 0, st>>>(b, dets, det_cols, det_counts, out_rows, out_counts, out_traj, out_traj_len);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(3);
