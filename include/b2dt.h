@@ -105,6 +105,13 @@ int b2_decode(const void* const* level_logits, const int* level_h, const int* le
               int n_levels, int B, int nc, int lstride, float conf, const uint8_t* classes_mask,
               float* cand, int32_t* cand_idx, int32_t* cand_count, int cand_cap, float* dense_out, void* stream);
 
+/* Candidate stage fed by the FUSED Detect head (b2_engine_head): per level, dist [B][h*w][4] fp32 (DFL expectations
+ * l,t,r,b in grid units) and cls [B][h*w][2] fp32 {best class logit, class}; the DFL softmax / class max run in the
+ * epilogue of the head's last convs, so the (64+nc)-channel logits are never written.  Same outputs as b2_decode. */
+int b2_candidates_from_head(const float* const* level_dist, const float* const* level_cls, const int* level_h, const int* level_w,
+                            const int* level_stride, int n_levels, int B, float conf, const uint8_t* classes_mask,
+                            float* cand, int32_t* cand_idx, int32_t* cand_count, int cand_cap, void* stream);
+
 /* Candidate stage of non_max_suppression for callers that hold the reference-shaped dense tensor
  * pred (B, no = 4+nc(+extra), A) fp32 [cx,cy,w,h,scores...] (utils/nms.py:74 `amax > conf`, :85-87 xywh2xyxy,
  * :111-113 best class, :120-124 classes filter).  Same candidate layout as b2_decode. */
@@ -142,6 +149,9 @@ int b2_engine_profile_u8(b2_engine_t* e, const uint8_t* frames, int src_h, int s
 int b2_engine_forward_f32(b2_engine_t* e, const void* bchw, int dtype, void* stream);
 /* Per-level head logits of the last forward: device pointers, [B][h*w][lstride] bf16 */
 int b2_engine_levels(b2_engine_t* e, int* n_levels, const void** logits, int* h, int* w, int* stride, int* lstride);
+/* Fused Detect head outputs of the last forward (engines lowered with the fused head): per level device pointers
+ * dist [B][h*w][4] fp32, cls [B][h*w][2] fp32.  B2_ERR_STATE if the engine writes plain logits instead. */
+int b2_engine_head(b2_engine_t* e, const float** dist, const float** cls);
 /* Debug/parity: device pointer + geometry of activation buffer `buf` (NHWC bf16) */
 int b2_engine_buffer(b2_engine_t* e, int buf, const void** ptr, int* h, int* w, int* c);
 size_t b2_engine_arena_bytes(b2_engine_t* e);

@@ -149,6 +149,46 @@ def test_engine_graph_and_end_to_end_drift(n_p2):
         assert torch.equal(first[l], eng.level_logits(l))
 
 
+@pytest.mark.parametrize("name,nc", [("yolov8n-p2", 80), ("yolov8n-p2", 1), ("yolov8s-p2", 80)])
+def test_fused_head_equals_unfused_decode(name, nc):
+    """DFL + class max inside the conv epilogue (fused head) vs plain logits + decode kernel: same candidates, same bits."""
+    from b200dt import ops
+    from b200dt.engine import Engine
+
+    torch = _torch()
+    spec = cfg.resolve(name, nc=nc)
+    sd = weights.synthetic_state_dict(spec, seed=0)
+    B, H, W = 2, 96, 160
+    frames = torch.from_numpy(np.stack([synth.IRStream(seed=60 + b, h=H, w=W, n_targets=5).frame() for b in range(B)])).cuda()
+    res = []
+    conf = None
+    for fused in (False, True):
+        eng = Engine(spec, sd, B, H, W, fuse_head=fused)
+        eng.forward_u8(frames)
+        post = ops.DetectPost(B, eng.level_h, eng.level_w, eng.level_stride, eng.nc, eng.lstride)
+        for c in ([0.15, 0.02, 1e-3, 1e-5] if conf is None else [conf]):      # first threshold that leaves candidates (nc = 1 scores are low)
+            if fused:
+                post.candidates_from_head(eng.head_dist, eng.head_cls, c)
+            else:
+                post.decode(eng.level_ptrs, c)
+            torch.cuda.synchronize()
+            cnt = post.cand_count.cpu().numpy()
+            if cnt.min() > 0:
+                conf = c
+                break
+        out = []
+        for b in range(B):
+            idx = post.cand_idx[b, :cnt[b]].cpu().numpy()
+            rows = post.cand[b, :cnt[b]].cpu().numpy()
+            o = np.argsort(idx)
+            out.append((idx[o], rows[o]))
+        res.append(out)
+    for b in range(B):
+        assert len(res[0][b][0]) > 0
+        np.testing.assert_array_equal(res[0][b][0], res[1][b][0])
+        np.testing.assert_array_equal(res[0][b][1], res[1][b][1])
+
+
 def test_engine_vs_reference_fp32_golden(n_p2):
     """bf16 engine vs the reference's own fp32 forward (tests/golden/net_n_p2_small.npz, uniform-noise input).
 

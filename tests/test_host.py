@@ -55,11 +55,14 @@ def test_lowering_is_consistent(name, hw):
     sd = weights.synthetic_state_dict(spec, seed=0, calib=None)
     P = engine.lower(spec, sd, *hw)
     words = P.words()
-    assert words[0] == engine.MAGIC and len(words) == 6 + 3 * len(P.bufs) + 2 * len(P.levels) + engine.OP_WORDS * len(P.ops)
+    assert words[0] == engine.MAGIC and len(words) == 6 + 3 * len(P.bufs) + 4 * len(P.levels) + engine.OP_WORDS * len(P.ops)
     assert P.flops == cfg.conv_flops(spec, *hw)                       # SURVEY.md 8d algorithmic FLOPs
     n_convs = sum(1 for o in P.ops if o[0] == engine.OP_CONV) + 1       # + stem
     assert n_convs == len(cfg.conv_list(spec))
-    assert [s for _, s in P.levels] == [4, 8, 16, 32]
+    assert [l[1] for l in P.levels] == [4, 8, 16, 32]
+    Pf = engine.lower(spec, sd, *hw, fuse_head=True)
+    assert Pf.flops == P.flops and len(Pf.ops) == len(P.ops) and all(l[0] < 0 and l[2] >= 0 for l in Pf.levels)
+    assert sum(1 for o in Pf.ops if o[19] == 1) == 4 and sum(1 for o in Pf.ops if o[19] == 2) == 4
     written = {}
     for o in P.ops:
         if o[0] == engine.OP_CONV:
@@ -68,7 +71,7 @@ def test_lowering_is_consistent(name, hw):
             if ib2 >= 0:
                 assert up0 == 2 and up1 == 1 and k == 1 and cin2 % 16 == 0 and ioff2 + cin2 <= P.bufs[ib2][2]
                 assert all(c in written.get(ib2, set()) for c in (ioff2, ioff2 + cin2 - 1)), o
-            assert ioff + cin <= P.bufs[ib][2] and ooff + cout <= P.bufs[ob][2]
+            assert ioff + cin <= P.bufs[ib][2] and ooff + cout <= P.bufs[ob][2] and o[19] == 0
             assert cin % 16 == 0 and ioff % 8 == 0 and ooff % 8 == 0
             assert woff % 256 == 0 and boff % 256 == 0
             # every input channel was produced by an earlier op

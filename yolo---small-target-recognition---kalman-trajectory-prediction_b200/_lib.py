@@ -31,6 +31,7 @@ SIGNATURES = {
     "b2_sppf_pool": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "b2_upsample_slice": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "b2_decode": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int, _P, _P]),
+    "b2_candidates_from_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P, _P, c_int, _P]),
     "b2_candidates_from_dense": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int, _P]),
     "b2_nms": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_int, c_int, c_int, c_float, c_int,
                        c_float, c_float, c_float, c_float, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
@@ -42,6 +43,7 @@ SIGNATURES = {
     "b2_engine_forward_f32": (c_int, [_P, _P, c_int, _P]),
     "b2_engine_levels": (c_int, [_P, C.POINTER(c_int), C.POINTER(_P), C.POINTER(c_int), C.POINTER(c_int),
                                  C.POINTER(c_int), C.POINTER(c_int)]),
+    "b2_engine_head": (c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "b2_engine_buffer": (c_int, [_P, c_int, C.POINTER(_P), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
     "b2_engine_arena_bytes": (c_size_t, [_P]),
     "b2_engine_num_launches": (c_int, [_P]),

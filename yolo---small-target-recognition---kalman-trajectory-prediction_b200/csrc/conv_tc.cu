@@ -71,6 +71,9 @@ struct alignas(64) ConvParams {
     const float* bias;
     int act;
     int wide;                 // 1: output (and residual) chunks are 32-byte aligned -> 256-bit accesses
+    int epi;                  // 0: bf16 channel-slice store; 1: DFL head (N = 64 -> 4 fp32 distances per pixel);
+                              // 2: class head (N = nc -> fp32 {best logit, class} per pixel)   [Detect._inference fused]
+    float* out_f32;           // epi 1: [pixels][4], epi 2: [pixels][2]
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -136,6 +139,36 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], const fl
                 if (rptr) x += __bfloat162float(rptr[i]);
                 optr[i] = __float2bfloat16_rn(x);
             }
+        }
+    }
+}
+
+// ---- Detect head fused into the epilogue (ultralytics/nn/modules/head.py:152-187, block.py:78-81 DFL) ----
+// Logits are rounded to bf16 first, exactly as the unfused path stores them, so both paths give the same bits.
+__device__ __forceinline__ float bf16_rt(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// one DFL side: softmax expectation over 16 bins (same summation order as decode_kernel: bins 0-7, bins 8-15, add)
+__device__ __forceinline__ float dfl_side(const uint32_t (&v)[16], const float* __restrict__ sb) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = bf16_rt(__uint_as_float(v[i]) + sb[i]);
+    float m = f[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, f[i]);
+    float se0 = 0.f, sw0 = 0.f, se1 = 0.f, sw1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float e = __expf(f[i] - m); se0 += e; sw0 = fmaf(e, (float)i, sw0); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float e = __expf(f[8 + i] - m); se1 += e; sw1 = fmaf(e, 8.f + (float)i, sw1); }
+    return (sw0 + sw1) / (se0 + se1);
+}
+// running (max logit, lowest index) over one 16-class chunk
+__device__ __forceinline__ void cls_chunk(const uint32_t (&v)[16], const float* __restrict__ sb, int c0, int nv, float& best, int& bidx) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (i < nv) {
+            const float x = bf16_rt(__uint_as_float(v[i]) + sb[i]);
+            if (x > best) { best = x; bidx = c0 + i; }
         }
     }
 }
@@ -317,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         const int row = quad * 32 + lane;                   // row of the 128-row tile == TMEM lane
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, nb = row / (p.TW * p.TH);
         const int n_tiles = p.n_tiles, n_tile = p.n_tile, tiles_w = p.tiles_w, tiles_h = p.tiles_h, TW = p.TW, TH = p.TH, NB = p.NB;
-        const int Wo = p.Wo, Ho = p.Ho, Bn = p.B, Cout = p.Cout, act = p.act, wide = p.wide;
+        const int Wo = p.Wo, Ho = p.Ho, Bn = p.B, Cout = p.Cout, act = p.act, wide = p.wide, epi = p.epi;
         const int out_cstride = p.out_cstride, res_cstride = p.res_cstride;
         __nv_bfloat16* const out0 = p.out + p.out_coff;
         const __nv_bfloat16* const res0 = p.res ? p.res + p.res_coff : nullptr;
@@ -345,23 +378,49 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_tile);
-            // this warp's chunks: half, half+2, half+4, ... ; two chunks in flight per iteration
-            for (int j = half; j < nchunks; j += 4) {
-                const int j2 = j + 2;
-                const bool two = j2 < nchunks;
-                uint32_t v0[16], v1[16];
-                tmem_ld16(t_addr + j * 16, v0);
-                if (two) tmem_ld16(t_addr + j2 * 16, v1);
-                tmem_ld_wait();
-                if (valid) {
-                    if (wide) {
-                        epilogue_chunk<true>(v0, s_bias + j * 16, act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
-                        if (two) epilogue_chunk<true>(v1, s_bias + j2 * 16, act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
-                    } else {
-                        epilogue_chunk<false>(v0, s_bias + j * 16, act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
-                        if (two) epilogue_chunk<false>(v1, s_bias + j2 * 16, act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+            if (epi == 0) {
+                // this warp's chunks: half, half+2, half+4, ... ; two chunks in flight per iteration
+                for (int j = half; j < nchunks; j += 4) {
+                    const int j2 = j + 2;
+                    const bool two = j2 < nchunks;
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(t_addr + j * 16, v0);
+                    if (two) tmem_ld16(t_addr + j2 * 16, v1);
+                    tmem_ld_wait();
+                    if (valid) {
+                        if (wide) {
+                            epilogue_chunk<true>(v0, s_bias + j * 16, act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                            if (two) epilogue_chunk<true>(v1, s_bias + j2 * 16, act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                        } else {
+                            epilogue_chunk<false>(v0, s_bias + j * 16, act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                            if (two) epilogue_chunk<false>(v1, s_bias + j2 * 16, act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                        }
                     }
                 }
+            } else if (epi == 1) {
+                // DFL head: chunk j == box side j (l, t, r, b); this warp takes sides half and half + 2
+                uint32_t v0[16], v1[16];
+                tmem_ld16(t_addr + half * 16, v0);
+                tmem_ld16(t_addr + (half + 2) * 16, v1);
+                tmem_ld_wait();
+                if (valid) {
+                    float* o = p.out_f32 + pix * 4;
+                    o[half] = dfl_side(v0, s_bias + half * 16);
+                    o[half + 2] = dfl_side(v1, s_bias + (half + 2) * 16);
+                }
+            } else if (half == 0) {
+                // class head: best logit and its (lowest) class index over all nc columns
+                float best = -INFINITY; int bidx = 0;
+                for (int j = 0; j < nchunks; j += 2) {
+                    const bool two = j + 1 < nchunks;
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(t_addr + j * 16, v0);
+                    if (two) tmem_ld16(t_addr + (j + 1) * 16, v1);
+                    tmem_ld_wait();
+                    cls_chunk(v0, s_bias + j * 16, j * 16, min(16, ncols - j * 16), best, bidx);
+                    if (two) cls_chunk(v1, s_bias + (j + 1) * 16, (j + 1) * 16, min(16, ncols - (j + 1) * 16), best, bidx);
+                }
+                if (valid) *reinterpret_cast<float2*>(p.out_f32 + pix * 2) = make_float2(best, (float)bidx);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
@@ -637,6 +696,15 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
     B2_REQUIRE(Cin % 16 == 0 && Cin > 0, "conv: Cin=%d must be a positive multiple of 16", Cin);
     const B2ConvSrc src{in, in_cstride, in_coff, Cin, 1};
     return b2_conv_prepare_ms(storage, &src, 1, B, H, W, w, bias, Cout, ksize, stride, act, out, out_cstride, out_coff, residual, res_cstride, res_coff);
+}
+
+// Switch a prepared conv to a fused Detect-head epilogue (see ConvParams::epi).
+int b2_conv_set_head_epilogue(void* storage, int epi, float* out_f32) {
+    B2ConvLaunch* L = reinterpret_cast<B2ConvLaunch*>(storage);
+    B2_REQUIRE(epi == 1 || epi == 2, "conv: head epilogue mode must be 1 (DFL) or 2 (classes)");
+    B2_REQUIRE(L->p.n_tiles == 1 && (epi != 1 || L->p.Cout == 64) && out_f32, "conv: head epilogue needs one N tile (DFL: exactly 64 channels)");
+    L->p.epi = epi; L->p.out_f32 = out_f32;
+    return B2_OK;
 }
 
 void b2_count_launch(int n);

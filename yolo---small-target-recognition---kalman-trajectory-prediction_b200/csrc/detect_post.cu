@@ -128,6 +128,58 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     }
 }
 
+// Candidate extraction from the fused Detect-head outputs (conv epilogue modes 1 / 2): per anchor 4 fp32 DFL distances
+// and {best class logit, class}.  Same box arithmetic, threshold test and candidate layout as decode_kernel.
+struct HeadParams {
+    const float* dist[kMaxLevels]; const float* cls[kMaxLevels];
+    int h[kMaxLevels], w[kMaxLevels], stride[kMaxLevels], a_off[kMaxLevels + 1];
+    int n_levels, A;
+    float conf; const uint8_t* cmask;
+    float* cand; int32_t* cand_idx; int32_t* cand_count; int cand_cap;
+};
+
+__global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, lane = threadIdx.x & 31;
+    bool is_cand = false;
+    float cx = 0.f, cy = 0.f, bw = 0.f, bh = 0.f, score = 0.f; int bidx = 0;
+    if (a < p.A) {
+        int lvl = 0;
+#pragma unroll
+        for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && a >= p.a_off[l]) lvl = l;
+        int W = p.w[0], H = p.h[0], st_i = p.stride[0], off = 0;
+        const float* dp = p.dist[0]; const float* cp = p.cls[0];
+#pragma unroll
+        for (int l = 1; l < kMaxLevels; ++l) if (l == lvl) { W = p.w[l]; H = p.h[l]; st_i = p.stride[l]; off = p.a_off[l]; dp = p.dist[l]; cp = p.cls[l]; }
+        const int la = a - off;
+        const size_t pix = (size_t)b * H * W + la;
+        const float2 c = __ldg(reinterpret_cast<const float2*>(cp) + pix);
+        bidx = (int)c.y;
+        score = 1.f / (1.f + __expf(-c.x));
+        if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dp) + pix);
+            const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f, st = (float)st_i;
+            const float x1 = ax - d.x, y1 = ay - d.y, x2 = ax + d.z, y2 = ay + d.w;
+            cx = (x1 + x2) / 2.f * st; cy = (y1 + y2) / 2.f * st; bw = (x2 - x1) * st; bh = (y2 - y1) * st;
+            is_cand = true;
+        }
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+    if (!ball) return;
+    int base = 0;
+    const int leader = __ffs(ball) - 1;
+    if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (is_cand) {
+        const int pos = base + __popc(ball & ((1u << lane) - 1));
+        if (pos < p.cand_cap) {
+            float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
+            const float hw = bw / 2.f, hh = bh / 2.f;
+            o[0] = cx - hw; o[1] = cy - hh; o[2] = cx + hw; o[3] = cy + hh; o[4] = score; o[5] = (float)bidx;
+            p.cand_idx[(size_t)b * p.cand_cap + pos] = a;
+        }
+    }
+}
+
 // Candidate extraction from the reference-shaped dense tensor (B, 4+nc, A) [cx,cy,w,h,scores...] fp32:
 // nms.py:74 (amax > conf), :85-87 (xywh2xyxy), :111-113 (best class), :120-124 (classes filter).
 // One thread per anchor; the class loop reads pred[b][4+c][a], coalesced across the warp.
@@ -388,6 +440,29 @@ extern "C" int b2_decode(const void* const* level_logits, const int* level_h, co
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
     dim3 grid(b2_ceil_div(p.A * 8, 256), B);
     decode_kernel<<<grid, 256, 0, st>>>(p);
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch(1);
+    return B2_OK;
+}
+
+extern "C" int b2_candidates_from_head(const float* const* level_dist, const float* const* level_cls, const int* level_h, const int* level_w,
+                                       const int* level_stride, int n_levels, int B, float conf, const uint8_t* classes_mask,
+                                       float* cand, int32_t* cand_idx, int32_t* cand_count, int cand_cap, void* stream) {
+    B2_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "candidates: n_levels=%d out of range", n_levels);
+    B2_REQUIRE(cand && cand_idx && cand_count && cand_cap > 0, "candidates: candidate buffers required");
+    HeadParams p{};
+    p.a_off[0] = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        B2_REQUIRE(level_dist[l] && level_cls[l], "candidates: level %d pointer null", l);
+        p.dist[l] = level_dist[l]; p.cls[l] = level_cls[l];
+        p.h[l] = level_h[l]; p.w[l] = level_w[l]; p.stride[l] = level_stride[l];
+        p.a_off[l + 1] = p.a_off[l] + level_h[l] * level_w[l];
+    }
+    p.n_levels = n_levels; p.A = p.a_off[n_levels]; p.conf = conf; p.cmask = classes_mask;
+    p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count; p.cand_cap = cand_cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
+    head_candidates_kernel<<<dim3(b2_ceil_div(p.A, 256), B), 256, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;

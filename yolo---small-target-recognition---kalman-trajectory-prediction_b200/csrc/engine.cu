@@ -22,6 +22,7 @@ struct B2ConvSrc { const void* ptr; int cstride, coff, C, up; };
 int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, int H, int W,
                        const void* w, const float* bias, int Cout, int ksize, int stride, int act,
                        void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff);
+int b2_conv_set_head_epilogue(void* storage, int epi, float* out_f32);
 int b2_conv_launch(const void* storage, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
@@ -70,7 +71,7 @@ struct b2_engine {
     int B, H, W, nc, lstride, n_levels;
     std::vector<Buf> bufs;
     std::vector<Step> steps;
-    std::vector<int> level_buf, level_stride;
+    std::vector<int> level_buf, level_stride, level_dist, level_cls;   // dist/cls: fused-head fp32 buffers (-1: unfused)
     char* arena = nullptr;
     size_t arena_bytes = 0, weights_off = 0;
     cudaGraphExec_t graph = nullptr;
@@ -99,7 +100,7 @@ extern "C" int b2_engine_create(const int32_t* plan, int plan_words, const void*
     B2_REQUIRE(plan_words >= 6 && plan[0] == kMagic, "engine_create: bad plan header");
     B2_REQUIRE(B >= 1 && H % 32 == 0 && W % 32 == 0 && H > 0 && W > 0, "engine_create: H and W must be positive multiples of 32 (got %dx%d)", H, W);
     const int n_bufs = plan[1], n_ops = plan[2], n_levels = plan[3];
-    B2_REQUIRE(plan_words == 6 + 3 * n_bufs + 2 * n_levels + kOpWords * n_ops, "engine_create: plan length mismatch");
+    B2_REQUIRE(plan_words == 6 + 3 * n_bufs + 4 * n_levels + kOpWords * n_ops, "engine_create: plan length mismatch");
     b2_engine* e = new (std::nothrow) b2_engine();
     if (!e) { b2_set_error("out of host memory"); return B2_ERR_STATE; }
     e->B = B; e->H = H; e->W = W; e->n_levels = n_levels; e->nc = plan[4]; e->lstride = plan[5];
@@ -111,7 +112,7 @@ extern "C" int b2_engine_create(const int32_t* plan, int plan_words, const void*
         off += up((size_t)B * b.h * b.w * b.c * 2);
         e->bufs.push_back(b);
     }
-    for (int l = 0; l < n_levels; ++l, p += 2) { e->level_buf.push_back(p[0]); e->level_stride.push_back(p[1]); }
+    for (int l = 0; l < n_levels; ++l, p += 4) { e->level_buf.push_back(p[0]); e->level_stride.push_back(p[1]); e->level_dist.push_back(p[2]); e->level_cls.push_back(p[3]); }
     e->weights_off = off;
     off += up(weight_bytes);
     e->arena_bytes = off;
@@ -151,11 +152,17 @@ extern "C" int b2_engine_create(const int32_t* plan, int plan_words, const void*
             s.conv.resize(b2_conv_launch_size() + 64);
             rc = b2_conv_prepare_ms(s.conv_ptr(), srcs, two ? 2 : 1, B, Hin, Win,
                                     wbase + (size_t)(uint32_t)a[11], (const float*)(wbase + (size_t)(uint32_t)a[12]), a[5], a[6], a[7], a[8],
-                                    e->buf_ptr(a[3]), bo.c, a[4], a[9] >= 0 ? e->buf_ptr(a[9]) : nullptr,
+                                    e->buf_ptr(a[3]), a[18] ? 16 : bo.c, a[18] ? 0 : a[4],   // head epilogues write fp32 records, not a bf16 slice
+                                    a[9] >= 0 ? e->buf_ptr(a[9]) : nullptr,
                                     a[9] >= 0 ? e->bufs[a[9]].c : 0, a[10]);
             if (rc != B2_OK) return fail(rc);
             const int pad = a[6] / 2, ho = (Hin + 2 * pad - a[6]) / a[7] + 1, wo = (Win + 2 * pad - a[6]) / a[7] + 1;
-            if (ho != bo.h || wo != bo.w || a[4] + a[5] > bo.c || a[1] + a[2] > bi.c) {
+            if (a[18] != 0) {      // fused Detect-head epilogue: the output buffer holds fp32 {4 distances} or {logit, class} per pixel
+                rc = b2_conv_set_head_epilogue(s.conv_ptr(), a[18], (float*)e->buf_ptr(a[3]));
+                if (rc != B2_OK) return fail(rc);
+                if (bo.c != (a[18] == 1 ? 8 : 4)) { b2_set_error("engine_create: op %d: head buffer has the wrong width", i); return fail(B2_ERR_ARG); }
+            }
+            if (ho != bo.h || wo != bo.w || (a[18] == 0 && a[4] + a[5] > bo.c) || a[1] + a[2] > bi.c) {
                 b2_set_error("engine_create: op %d: conv geometry does not match its buffers", i); return fail(B2_ERR_ARG);
             }
         } else if (s.op == OP_POOL) {
@@ -264,13 +271,24 @@ extern "C" int b2_engine_levels(b2_engine_t* e, int* n_levels, const void** logi
     B2_REQUIRE(e && n_levels, "engine_levels: null pointer");
     *n_levels = e->n_levels;
     for (int l = 0; l < e->n_levels; ++l) {
-        const Buf& b = e->bufs[e->level_buf[l]];
-        if (logits) logits[l] = e->buf_ptr(e->level_buf[l]);
+        const bool fused = e->level_buf[l] < 0;
+        const Buf& b = e->bufs[fused ? e->level_dist[l] : e->level_buf[l]];
+        if (logits) logits[l] = fused ? nullptr : e->buf_ptr(e->level_buf[l]);
         if (h) h[l] = b.h;
         if (w) w[l] = b.w;
         if (stride) stride[l] = e->level_stride[l];
     }
     if (lstride) *lstride = e->lstride;
+    return B2_OK;
+}
+
+extern "C" int b2_engine_head(b2_engine_t* e, const float** dist, const float** cls) {
+    B2_REQUIRE(e && dist && cls, "engine_head: null pointer");
+    for (int l = 0; l < e->n_levels; ++l) {
+        if (e->level_dist[l] < 0 || e->level_cls[l] < 0) { b2_set_error("engine_head: this engine was lowered without the fused Detect head"); return B2_ERR_STATE; }
+        dist[l] = (const float*)e->buf_ptr(e->level_dist[l]);
+        cls[l] = (const float*)e->buf_ptr(e->level_cls[l]);
+    }
     return B2_OK;
 }
 

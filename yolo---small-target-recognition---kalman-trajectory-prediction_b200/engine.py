@@ -57,7 +57,7 @@ class Plan:
     def __init__(self):
         self.bufs = []          # (h, w, c)
         self.ops = []           # lists of OP_WORDS ints
-        self.levels = []        # (buf, stride)
+        self.levels = []        # (buf, stride, dist_buf, cls_buf); the last two are -1 without the fused head
         self.loc = {}           # layer index -> (buf, coff, C)
         self.named = {}         # module path (e.g. 'model.2.m.0.cv1') -> (buf, coff, C)
         self.blob = _Blob()
@@ -92,8 +92,12 @@ def _shapes(spec, H, W):
     return hw
 
 
-def lower(spec, state_dict, H, W):
-    """Lower ``spec`` (from :func:`cfg.resolve`) with weights ``state_dict`` for an ``H x W`` letterboxed input."""
+def lower(spec, state_dict, H, W, fuse_head=False):
+    """Lower ``spec`` (from :func:`cfg.resolve`) with weights ``state_dict`` for an ``H x W`` letterboxed input.
+
+    ``fuse_head``: run DFL (softmax expectation) and the class max inside the epilogue of each Detect level's last
+    two convs (head.py:152-187 fused into head.py:93-96): the ``64 + nc`` logits are never written; the engine then
+    exposes ``b2_engine_head`` buffers instead of ``b2_engine_levels`` logits."""
     if H % 32 or W % 32:
         raise ValueError(f"input size {H}x{W} must be a multiple of the maximum stride 32")
     sd = state_dict
@@ -153,11 +157,11 @@ def lower(spec, state_dict, H, W):
         if c % 16:
             raise NotImplementedError(f"{what}: {c} channels -- the tcgen05 conv path needs multiples of 16")
 
-    def emit_conv(prefix, inp, out, k, s, bn, res=None, inp2=None, ups=(1, 1)):
+    def emit_conv(prefix, inp, out, k, s, bn, res=None, inp2=None, ups=(1, 1), epi=0):
         """inp/out/res/inp2: (buf, coff, C).  inp2: second input of a folded Concat; ups: resolution factors of the inputs."""
         w, b = weights.folded(sd, prefix, bn)
         cout, cin = w.shape[0], w.shape[1]
-        assert cin == inp[2] + (inp2[2] if inp2 else 0) and cout == out[2], (prefix, w.shape, inp, inp2, out)
+        assert cin == inp[2] + (inp2[2] if inp2 else 0) and (epi or cout == out[2]), (prefix, w.shape, inp, inp2, out)
         check_c(inp[2], prefix + " input")
         if inp2:
             check_c(inp2[2], prefix + " second input")
@@ -167,7 +171,7 @@ def lower(spec, state_dict, H, W):
         P.flops += 2 * hb * wb * cout * cin * k * k
         P.ops.append([OP_CONV, inp[0], inp[1], inp[2], out[0], out[1], cout, k, s, ACT_SILU if bn else ACT_NONE,
                       res[0] if res else -1, res[1] if res else 0, woff, boff,
-                      inp2[0] if inp2 else -1, inp2[1] if inp2 else 0, inp2[2] if inp2 else 0, ups[0], ups[1], 0])
+                      inp2[0] if inp2 else -1, inp2[1] if inp2 else 0, inp2[2] if inp2 else 0, ups[0], ups[1], epi])
         P.named[prefix] = out
 
     for L in layers:
@@ -231,16 +235,23 @@ def lower(spec, state_dict, H, W):
             for l, f in enumerate(L["f"]):
                 inp = P.loc[f]
                 hh, ww = hw[f]
-                logits = P.new_buf(hh, ww, P.lstride)
                 t1, t2 = P.new_buf(hh, ww, cb), P.new_buf(hh, ww, cb)
+                u1, u2 = P.new_buf(hh, ww, cc), P.new_buf(hh, ww, cc)
                 emit_conv(f"{p}.cv2.{l}.0", inp, (t1, 0, cb), 3, 1, True)
                 emit_conv(f"{p}.cv2.{l}.1", (t1, 0, cb), (t2, 0, cb), 3, 1, True)
-                emit_conv(f"{p}.cv2.{l}.2", (t2, 0, cb), (logits, 0, 64), 1, 1, False)
-                u1, u2 = P.new_buf(hh, ww, cc), P.new_buf(hh, ww, cc)
                 emit_conv(f"{p}.cv3.{l}.0", inp, (u1, 0, cc), 3, 1, True)
                 emit_conv(f"{p}.cv3.{l}.1", (u1, 0, cc), (u2, 0, cc), 3, 1, True)
-                emit_conv(f"{p}.cv3.{l}.2", (u2, 0, cc), (logits, 64, nc), 1, 1, False)
-                P.levels.append((logits, H // hh))
+                if fuse_head and nc <= 256:
+                    dist = P.new_buf(hh, ww, 8)                       # 4 fp32 per pixel
+                    clsb = P.new_buf(hh, ww, 4)                       # 2 fp32 per pixel
+                    emit_conv(f"{p}.cv2.{l}.2", (t2, 0, cb), (dist, 0, 8), 1, 1, False, epi=1)
+                    emit_conv(f"{p}.cv3.{l}.2", (u2, 0, cc), (clsb, 0, 4), 1, 1, False, epi=2)
+                    P.levels.append((-1, H // hh, dist, clsb))
+                else:
+                    logits = P.new_buf(hh, ww, P.lstride)
+                    emit_conv(f"{p}.cv2.{l}.2", (t2, 0, cb), (logits, 0, 64), 1, 1, False)
+                    emit_conv(f"{p}.cv3.{l}.2", (u2, 0, cc), (logits, 64, nc), 1, 1, False)
+                    P.levels.append((logits, H // hh, -1, -1))
         else:
             raise NotImplementedError(t)
         # a layer that feeds more than one Concat: copy its slice into the others
@@ -260,11 +271,12 @@ class Engine:
     (ultralytics/nn/autobackend.py:196-219, :608-637).
     """
 
-    def __init__(self, spec, state_dict, batch, H, W):
+    def __init__(self, spec, state_dict, batch, H, W, fuse_head=False):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.spec, self.B, self.H, self.W = spec, int(batch), int(H), int(W)
-        self.plan = lower(spec, state_dict, H, W)
+        self.plan = lower(spec, state_dict, H, W, fuse_head=fuse_head)
+        self.fused_head = self.plan.levels[0][0] < 0
         words = self.plan.words()
         blob = self.plan.blob.bytes()
         self._h = C.c_void_p()
@@ -275,13 +287,19 @@ class Engine:
         ptrs = (C.c_void_p * 8)()
         hs, ws, ss = (C.c_int * 8)(), (C.c_int * 8)(), (C.c_int * 8)()
         ls = C.c_int()
-        _lib.check(self.lib.b2_engine_levels(self._h, C.byref(n), ptrs, hs, ws, ss, C.byref(ls)))
+        _lib.check(self.lib.b2_engine_levels(self._h, C.byref(n), ptrs, hs, ws, ss, C.byref(ls)))   # logits pointers are NULL with the fused head
         self.n_levels, self.lstride, self.nc = n.value, ls.value, spec["nc"]
         self.level_ptrs = [ptrs[i] for i in range(n.value)]
         self.level_h = [hs[i] for i in range(n.value)]
         self.level_w = [ws[i] for i in range(n.value)]
         self.level_stride = [ss[i] for i in range(n.value)]
         self.num_anchors = sum(h * w for h, w in zip(self.level_h, self.level_w))
+        self.head_dist = self.head_cls = None
+        if self.fused_head:
+            dp, cp = (C.c_void_p * 8)(), (C.c_void_p * 8)()
+            _lib.check(self.lib.b2_engine_head(self._h, dp, cp))
+            self.head_dist = [dp[i] for i in range(n.value)]
+            self.head_cls = [cp[i] for i in range(n.value)]
         self.flops_per_image = self.plan.flops
         self.stride = max(self.level_stride)
         self.names = spec["names"]
@@ -336,6 +354,9 @@ class Engine:
                 fl = 2 * h * w * cout * ct * k * k * self.B
                 nbytes = (in_elems + h * w * cout * (2 if rb >= 0 else 1)) * 2 * self.B + cout * ct * k * k * 2
                 desc = f"{ct}->{cout} k{k} s{s} @{h}x{w}" + ("  [up2|cat]" if ib2 >= 0 else "")
+                if op[19]:
+                    nbytes = (in_elems * 2 + h * w * (16 if op[19] == 1 else 8)) * self.B + cout * ct * 2
+                    desc += "  [DFL]" if op[19] == 1 else "  [cls max]"
             elif op[0] == OP_STEM:
                 h, w, _c = self.plan.bufs[op[1]]
                 fl = 2 * h * w * op[3] * 27 * self.B

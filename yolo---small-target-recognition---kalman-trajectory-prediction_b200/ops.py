@@ -148,6 +148,14 @@ class DetectPost:
                                       _lib.ptr(classes_mask), _lib.ptr(self.cand), _lib.ptr(self.cand_idx), _lib.ptr(self.cand_count),
                                       self.cand_cap, _lib.ptr(dense_out), _lib.stream_ptr(stream)))
 
+    def candidates_from_head(self, dist_ptrs, cls_ptrs, conf, classes_mask=None, stream=None):
+        """Candidate stage on the fused Detect-head outputs of an ``Engine(fuse_head=True)``."""
+        dp = (C.c_void_p * self.n_levels)(*dist_ptrs)
+        cp = (C.c_void_p * self.n_levels)(*cls_ptrs)
+        _lib.check(self.lib.b2_candidates_from_head(dp, cp, self.h, self.w, self.s, self.n_levels, self.B, float(conf), _lib.ptr(classes_mask),
+                                                    _lib.ptr(self.cand), _lib.ptr(self.cand_idx), _lib.ptr(self.cand_count), self.cand_cap,
+                                                    _lib.stream_ptr(stream)))
+
     def nms(self, iou, agnostic=False, mode="exact", max_nms=MAX_NMS, scale=None, stream=None):
         """scale: None or (gain, pad_x, pad_y, orig_w, orig_h) for the fused scale_boxes/clip_boxes epilogue."""
         g = scale or (1.0, 0.0, 0.0, 0.0, 0.0)

@@ -186,8 +186,8 @@ def scale_params(canvas_hw, orig_hw):
 class DetectPipeline:
     """Engine + decode + NMS for a fixed (batch, canvas H x W): every launch of one detect step."""
 
-    def __init__(self, spec, state_dict, batch, H, W, max_det=300):
-        self.engine = Engine(spec, state_dict, batch, H, W)
+    def __init__(self, spec, state_dict, batch, H, W, max_det=300, fuse_head=True):
+        self.engine = Engine(spec, state_dict, batch, H, W, fuse_head=fuse_head)
         e = self.engine
         self.post = ops.DetectPost(batch, e.level_h, e.level_w, e.level_stride, e.nc, e.lstride, max_det=max_det)
         self.B, self.H, self.W = batch, H, W
@@ -203,7 +203,10 @@ class DetectPipeline:
         return self.finish(conf, iou, orig_hw, classes_mask, agnostic, mode, stream)
 
     def finish(self, conf, iou, orig_hw, classes_mask, agnostic, mode, stream):
-        self.post.decode(self.engine.level_ptrs, conf, classes_mask, stream=stream)
+        if self.engine.fused_head:
+            self.post.candidates_from_head(self.engine.head_dist, self.engine.head_cls, conf, classes_mask, stream=stream)
+        else:
+            self.post.decode(self.engine.level_ptrs, conf, classes_mask, stream=stream)
         scale = scale_params((self.H, self.W), orig_hw) if orig_hw is not None else None
         return self.post.nms(iou, agnostic=agnostic, mode=mode, scale=scale, stream=stream)
 
