@@ -7,6 +7,8 @@
 // All tensor maps are built once at create time; the layer launches are replayed from a CUDA graph.
 #include "common.cuh"
 
+#include <cuda_profiler_api.h>
+
 #include <stdarg.h>
 
 #include <atomic>
@@ -239,12 +241,27 @@ extern "C" int b2_engine_profile_u8(b2_engine_t* e, const uint8_t* frames, int s
     const int* a = e->steps[0].a;
     char* wbase = e->arena + e->weights_off;
     int rc = B2_OK;
+    // B2_NCU_OPS="3,57,59": bracket these launches with cudaProfilerStart/Stop (ncu --profile-from-start off captures only them)
+    std::vector<char> mark(n, 0);
+    if (const char* sel = getenv("B2_NCU_OPS")) {
+        for (const char* q = sel; *q;) {
+            char* end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v >= 0 && (size_t)v < n) mark[(size_t)v] = 1;
+            q = *end ? end + 1 : end;
+        }
+    }
     cudaEventRecord(ev[0], st);
+    if (mark[0]) cudaProfilerStart();
     rc = b2_stem_u8(frames, e->B, src_h, src_w, e->H, e->W, pad_top, pad_left, (const void*)(wbase + (size_t)(uint32_t)a[3]),
                     (const float*)(wbase + (size_t)(uint32_t)a[4]), a[2], e->buf_ptr(a[0]), e->bufs[a[0]].c, a[1], stream);
+    if (mark[0]) { cudaStreamSynchronize(st); cudaProfilerStop(); }
     cudaEventRecord(ev[1], st);
     for (size_t i = 1; i < n && rc == B2_OK; ++i) {
+        if (mark[i]) cudaProfilerStart();
         rc = run_step(e, e->steps[i], st);
+        if (mark[i]) { cudaStreamSynchronize(st); cudaProfilerStop(); }
         cudaEventRecord(ev[i + 1], st);
     }
     cudaError_t ce = cudaStreamSynchronize(st);
