@@ -44,6 +44,24 @@ CONV_CASES = [
 ]
 
 
+TS_CASES = [c for c in CONV_CASES if c[5] == 3] + [
+    (2, 33, 19, 128, 64, 3, 1, True, True),       # 4 taps in tensor memory, 5 as SS MMAs from shared memory
+    (1, 48, 24, 80, 80, 3, 1, True, False),       # K segments 64 + 16, 6 resident taps
+    (2, 16, 32, 256, 80, 3, 1, True, False),      # 2 resident taps
+    (1, 31, 45, 32, 128, 3, 2, True, False),      # stride 2 through the transposed kernel (B2_CONV_TS=2)
+    (5, 8, 8, 64, 64, 3, 1, False, True),         # several images per tile, no activation
+]
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("case", TS_CASES)
+def test_conv_kernel_variants_match_oracle(case, mode, monkeypatch):
+    """Both conv kernels on the same shapes: B2_CONV_TS=0 forces conv_tc_kernel (pixels x weights, SS MMAs),
+    B2_CONV_TS=2 forces conv_ts_kernel (weights in tensor memory, transposed accumulator) for every 3x3 conv."""
+    monkeypatch.setenv("B2_CONV_TS", mode)
+    test_conv_matches_oracle(case)
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_matches_oracle(case):
     from b200dt import ops
