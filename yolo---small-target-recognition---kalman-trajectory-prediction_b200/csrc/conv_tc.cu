@@ -202,6 +202,9 @@ __device__ __forceinline__ float2 cls_unkey(int key) {
     return make_float2(__int_as_float(b), (float)(0xFFFF - (key & 0xFFFF)));
 }
 
+// EPI: epilogue variant (ConvParams::epi), HALO: ConvParams::halo -- compile-time copies of the two fields, so that each
+// instance carries only its own loops (the kernel is sensitive to registers / code size in the issue and epilogue paths)
+template <int EPI, int HALO>
 __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -247,8 +250,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     const int taps = p.ksize * p.ksize;
     // pipeline stages consumed per K chunk / filter taps served by one stage:
     //   halo 1: one 18-row box per kw serves the three kh taps; halo 2: ONE (TW+2) x (TH+2) box serves all nine taps
-    const int groups = p.halo == 2 ? 1 : p.halo ? 3 : taps;
-    const int taps_per_group = p.halo == 2 ? 9 : p.halo ? 3 : 1;
+    const int groups = HALO == 2 ? 1 : HALO ? 3 : taps;
+    const int taps_per_group = HALO == 2 ? 9 : HALO ? 3 : 1;
     const int nseg = p.nseg;
 
     // Producer and MMA warps run their loops with the whole warp (uniform control flow keeps descriptors and
@@ -256,7 +259,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     if (warp == 0) {
         // ===================== TMA producer =====================
         const bool leader = elect_one();
-        const int halo = p.halo, b_res = p.b_resident, Cin = p.Cin, num_stages = p.num_stages;
+        constexpr int halo = HALO;
+        const int b_res = p.b_resident, Cin = p.Cin, num_stages = p.num_stages;
         const int ksz = p.ksize, pad = p.pad, stride = p.stride, n_tiles = p.n_tiles, n_tile = p.n_tile;
         const int tiles_w = p.tiles_w, tiles_h = p.tiles_h, TW = p.TW, TH = p.TH, NB = p.NB;
         const uint32_t a_bytes = p.a_bytes, b_stage_stride = p.b_stage_stride;
@@ -330,7 +334,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         const uint32_t a_lo0 = ((smem_u32(smem_a) >> 4) & 0x3FFFu) | (1u << 16);
         const uint32_t b_lo0 = ((smem_u32(smem_b) >> 4) & 0x3FFFu) | (1u << 16);
         const uint32_t a_stage16 = p.a_bytes >> 4, b_stage16 = p.b_stage_stride >> 4;
-        const int halo = p.halo, b_res = p.b_resident, num_stages = p.num_stages, n_tile = p.n_tile;
+        constexpr int halo = HALO;
+        const int b_res = p.b_resident, num_stages = p.num_stages, n_tile = p.n_tile;
         // per-segment constants in registers (nseg <= 2)
         int sg_kch[kMaxSeg], sg_mps[kMaxSeg];
         uint32_t sg_hi[kMaxSeg], sg_hiw[kMaxSeg], sg_kh16[kMaxSeg], sg_blk16[kMaxSeg], sg_base16[kMaxSeg];
@@ -401,7 +406,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         const int row = quad * 32 + lane;                   // row of the 128-row tile == TMEM lane
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, nb = row / (p.TW * p.TH);
         const int n_tiles = p.n_tiles, n_tile = p.n_tile, tiles_w = p.tiles_w, tiles_h = p.tiles_h, TW = p.TW, TH = p.TH, NB = p.NB;
-        const int Wo = p.Wo, Ho = p.Ho, Bn = p.B, Cout = p.Cout, act = p.act, wide = p.wide, epi = p.epi;
+        constexpr int epi = EPI;
+        const int Wo = p.Wo, Ho = p.Ho, Bn = p.B, Cout = p.Cout, act = p.act, wide = p.wide;
         const int out_cstride = p.out_cstride, res_cstride = p.res_cstride;
         __nv_bfloat16* const out0 = p.out + p.out_coff;
         const __nv_bfloat16* const res0 = p.res ? p.res + p.res_coff : nullptr;
@@ -944,7 +950,14 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     {   // opt in to the large dynamic shared memory carve-out once (not a stream operation: safe before graph capture)
         static std::once_flag once;
         static cudaError_t attr_err = cudaSuccess;
-        std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096); });
+        std::call_once(once, [] {
+            const int bytes = 227 * 1024 - 4096;
+            cudaError_t e = cudaSuccess;
+            auto set = [&](const void* fn) { cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); if (r != cudaSuccess) e = r; };
+            set((const void*)conv_tc_kernel<0, 0>); set((const void*)conv_tc_kernel<0, 1>); set((const void*)conv_tc_kernel<0, 2>);
+            set((const void*)conv_tc_kernel<1, 0>); set((const void*)conv_tc_kernel<2, 0>);
+            attr_err = e;
+        });
         B2_CUDA(attr_err);
     }
     EncodeTiledFn encode = get_encode();
@@ -1219,7 +1232,7 @@ int b2_conv_set_head_epilogue(void* storage, int epi, float* out_f32) {
     B2ConvLaunch* L = reinterpret_cast<B2ConvLaunch*>(storage);
     B2_REQUIRE(epi == 1 || epi == 2, "conv: head epilogue mode must be 1 (DFL) or 2 (classes)");
     B2_REQUIRE(L->p.n_tiles == 1 && (epi != 1 || L->p.Cout == 64) && out_f32, "conv: head epilogue needs one N tile (DFL: exactly 64 channels)");
-    B2_REQUIRE(!L->p.ts, "conv: head epilogues are implemented by conv_tc_kernel only");
+    B2_REQUIRE(!L->p.ts && L->p.halo == 0, "conv: head epilogues are implemented for 1x1 convs in conv_tc_kernel only");
     L->p.epi = epi; L->p.out_f32 = out_f32;
     return B2_OK;
 }
@@ -1229,7 +1242,11 @@ void b2_count_launch(int n);
 int b2_conv_launch(const void* storage, cudaStream_t stream) {
     const B2ConvLaunch* L = reinterpret_cast<const B2ConvLaunch*>(storage);
     if (L->p.ts) conv_ts_kernel<<<L->grid, kTsThreads, L->smem, stream>>>(L->p);
-    else conv_tc_kernel<<<L->grid, kThreads, L->smem, stream>>>(L->p);
+    else if (L->p.epi == 1) conv_tc_kernel<1, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
+    else if (L->p.epi == 2) conv_tc_kernel<2, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
+    else if (L->p.halo == 2) conv_tc_kernel<0, 2><<<L->grid, kThreads, L->smem, stream>>>(L->p);
+    else if (L->p.halo == 1) conv_tc_kernel<0, 1><<<L->grid, kThreads, L->smem, stream>>>(L->p);
+    else conv_tc_kernel<0, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
