@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
     __shared__ __align__(1024) uint8_t s_a[128 * 64];
     __shared__ __align__(1024) uint8_t s_b[kStemMaxC0 * 64];
     __shared__ __align__(16) float s_bias[kStemMaxC0];
+    __shared__ __align__(16) uint8_t s_in[17 * 128 + 32];      // staged input patch: 17 rows x 128 bytes, then the 17 row offsets (0..15)
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -62,14 +63,39 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
         const int b = t / tiles_h;
         // ---- im2col row of this thread's pixel ----
         float v[27];
+        bool staged = false;
+        if (Loader::kStaged) {
+            // Interior tiles of uint8 frames: the 17 x 33-pixel input patch (99 bytes per row) is copied into shared memory
+            // with aligned 16-byte loads (<= 8 per row; one or two per thread) and each thread then reads its 27 bytes
+            // from there -- 136 vector loads and no per-byte bounds checks instead of 3456 byte loads per tile.
+            const int t2 = tile;
+            const int wo0 = (t2 % tiles_w) * 16, ho0 = ((t2 / tiles_w) % tiles_h) * 8;
+            staged = ld.stage(b, 2 * ho0 - 1, 2 * wo0 - 1, H, W, s_in, tid, kStemThreads);      // uniform across the CTA
+            if (staged) {
+                __syncthreads();
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int r = 2 * th + kh;
+                    const uint8_t* q = s_in + r * 128 + s_in[17 * 128 + r] + 6 * tw;
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                float rgb[3];
-                ld.load(b, 2 * ho + kh - 1, 2 * wo + kw - 1, H, W, rgb);
-                v[(kh * 3 + kw) * 3 + 0] = rgb[0]; v[(kh * 3 + kw) * 3 + 1] = rgb[1]; v[(kh * 3 + kw) * 3 + 2] = rgb[2];
+                    for (int kw = 0; kw < 3; ++kw) {
+                        v[(kh * 3 + kw) * 3 + 2] = (float)q[kw * 3 + 0];       // B
+                        v[(kh * 3 + kw) * 3 + 1] = (float)q[kw * 3 + 1];       // G
+                        v[(kh * 3 + kw) * 3 + 0] = (float)q[kw * 3 + 2];       // R
+                    }
+                }
             }
+        }
+        if (!staged) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    float rgb[3];
+                    ld.load(b, 2 * ho + kh - 1, 2 * wo + kw - 1, H, W, rgb);
+                    v[(kh * 3 + kw) * 3 + 0] = rgb[0]; v[(kh * 3 + kw) * 3 + 1] = rgb[1]; v[(kh * 3 + kw) * 3 + 2] = rgb[2];
+                }
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 13; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -102,7 +128,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
                 for (int i = 0; i < 8; ++i) {
                     const float x0 = fmaf(__uint_as_float(a[2 * i]), in_scale, s_bias[j + 2 * i]);
                     const float x1 = fmaf(__uint_as_float(a[2 * i + 1]), in_scale, s_bias[j + 2 * i + 1]);
-                    o[i] = pack_bf16x2(silu_f(x0), silu_f(x1));
+                    o[i] = pack_bf16x2(silu_fast(x0), silu_fast(x1));
                 }
                 if (j + 16 <= C0) {
                     *reinterpret_cast<uint4*>(op + j) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -119,7 +145,25 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
 }
 
 struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left) of the canvas, border 114, outside canvas 0
+    static constexpr bool kStaged = true;
     const uint8_t* p; int sh, sw, pt, pl;
+    long long total_bytes;      // B * sh * sw * 3 (vector loads must stay inside the buffer)
+    // Copy canvas rows y0 .. y0+16, columns x0 .. x0+32 into s_in (row r at r * 128 + off[r], off[r] = s_in[17 * 128 + r]).
+    // Returns false (nothing written) unless the whole patch lies inside the frame: border tiles take the per-byte path.
+    __device__ __forceinline__ bool stage(int b, int y0, int x0, int H, int W, uint8_t* s_in, int tid, int nthreads) const {
+        const int fy0 = y0 - pt, fx0 = x0 - pl;
+        if (fy0 < 0 || fx0 < 0 || fy0 + 16 >= sh || fx0 + 32 >= sw) return false;
+        const long long g_first = (((long long)b * sh + fy0) * sw + fx0) * 3;
+        if (g_first + 16ll * sw * 3 + 99 + 16 > total_bytes) return false;
+        for (int i = tid; i < 17 * 8; i += nthreads) {
+            const int r = i >> 3, c = i & 7;
+            const long long g0 = g_first + (long long)r * sw * 3;
+            const long long ga = (g0 & ~15ll) + c * 16;
+            if (ga < g0 + 99) *reinterpret_cast<uint4*>(s_in + r * 128 + c * 16) = __ldg(reinterpret_cast<const uint4*>(p + ga));
+            if (c == 0) s_in[17 * 128 + r] = (uint8_t)(g0 & 15);
+        }
+        return true;
+    }
     __device__ __forceinline__ void load(int b, int y, int x, int H, int W, float (&rgb)[3]) const {
         if (y < 0 || x < 0 || y >= H || x >= W) { rgb[0] = rgb[1] = rgb[2] = 0.f; return; }
         const int fy = y - pt, fx = x - pl;
@@ -130,7 +174,9 @@ struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left
 };
 template <typename T>
 struct LoadPlanar {   // [B][3][H][W] RGB in [0,1]; the tensor core consumes bf16(255 x) (exact for uint8-derived inputs)
+    static constexpr bool kStaged = false;
     const T* p;
+    __device__ __forceinline__ bool stage(int, int, int, int, int, uint8_t*, int, int) const { return false; }
     __device__ __forceinline__ void load(int b, int y, int x, int H, int W, float (&rgb)[3]) const {
         if (y < 0 || x < 0 || y >= H || x >= W) { rgb[0] = rgb[1] = rgb[2] = 0.f; return; }
         const size_t plane = (size_t)H * W;
@@ -281,7 +327,8 @@ extern "C" int b2_stem_u8(const uint8_t* frames, int B, int src_h, int src_w, in
     B2_REQUIRE(C0 % 8 == 0 && out_cstride % 8 == 0 && out_coff % 8 == 0, "stem: channel counts must be multiples of 8");
     B2_REQUIRE(pad_top >= 0 && pad_left >= 0 && pad_top + src_h <= H && pad_left + src_w <= W, "stem: frame does not fit the canvas");
     B2_REQUIRE((uintptr_t)w % 16 == 0 && (uintptr_t)out % 16 == 0, "stem: pointers must be 16-byte aligned");
-    LoadU8 ld{frames, src_h, src_w, pad_top, pad_left};
+    B2_REQUIRE((uintptr_t)frames % 16 == 0, "stem: the frame buffer must be 16-byte aligned");
+    LoadU8 ld{frames, src_h, src_w, pad_top, pad_left, (long long)B * src_h * src_w * 3};
     return launch_stem(ld, B, H, W, w, bias, C0, out, out_cstride, out_coff, (cudaStream_t)stream);
 }
 
