@@ -50,6 +50,8 @@ TS_CASES = [c for c in CONV_CASES if c[5] == 3] + [
     (2, 16, 32, 256, 80, 3, 1, True, False),      # 2 resident taps
     (1, 31, 45, 32, 128, 3, 2, True, False),      # stride 2 through the transposed kernel (B2_CONV_TS=2)
     (5, 8, 8, 64, 64, 3, 1, False, True),         # several images per tile, no activation
+    (3, 64, 48, 96, 64, 3, 2, True, False),       # stride 2 parity boxes, K segments 64 + 32, several images
+    (2, 34, 62, 16, 32, 3, 2, True, False),       # stride 2 parity boxes, ragged 17 x 31 output, 32-byte rows
 ]
 
 

@@ -57,7 +57,9 @@ struct alignas(64) Seg {
     uint32_t b_base;          // resident weights: offset of this segment's blocks inside the weight region
     uint32_t kh_step16;       // halo mode: (8 rows * row bytes) >> 4
     uint32_t desc_hi;         // high word of the shared-memory matrix descriptor (SBO, version, swizzle)
-    uint32_t desc_hi_w;       // conv_ts_kernel: the same for the weight blocks of the SS fallback taps (8-row pitch)
+    uint32_t desc_hi_w;       // the same for weight blocks (8-row pitch) where the pixel operand has another pitch (halo 2 / 3, conv_ts_kernel)
+    uint32_t a_tx4[4];        // halo 3 (stride 2): bytes delivered by the box of parity view 0..3
+    uint32_t desc_hi9;        // halo 3: pixel-operand descriptor high word for the 9-pixel-wide boxes (pw = 1)
 };
 
 struct alignas(64) ConvParams {
@@ -70,7 +72,8 @@ struct alignas(64) ConvParams {
     int Cin, ksize, stride, pad;
     int num_stages;
     int halo;                 // 3x3 stride-1: 1 = one 18-row box per (kw, K chunk) serves the 3 kh taps (conv_tc_kernel);
-                              // 2 = one (TW+2) x (TH+2) box per K chunk serves all 9 taps by descriptor start row (conv_ts_kernel)
+                              // 2 = one (TW+2) x (TH+2) box per K chunk serves all 9 taps by descriptor start row;
+                              // 3 = 3x3 stride 2: one box per input parity (row, column) serves the 1 / 2 / 2 / 4 taps that read it
     int b_resident;           // 1: every weight block stays in shared memory for the lifetime of the CTA
     uint32_t a_bytes;         // shared-memory stride of one A stage (1024-aligned)
     uint32_t b_stage_stride;  // streamed weights: bytes of weight blocks per stage
@@ -246,8 +249,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     const int taps = p.ksize * p.ksize;
     // pipeline stages consumed per K chunk / filter taps served by one stage:
     //   halo 1: one 18-row box per kw serves the three kh taps; halo 2: ONE (TW+2) x (TH+2) box serves all nine taps
-    const int groups = HALO == 2 ? 1 : HALO ? 3 : taps;
-    const int taps_per_group = HALO == 2 ? 9 : HALO ? 3 : 1;
+    const int groups = HALO == 3 ? 4 : HALO == 2 ? 1 : HALO ? 3 : taps;
+    const int taps_per_group = HALO == 2 ? 9 : HALO == 1 ? 3 : 1;
     const int nseg = p.nseg;
 
     // Producer and MMA warps run their loops with the whole warp (uniform control flow keeps descriptors and
@@ -279,7 +282,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             const int n0 = (m_idx / tiles_h) * NB;
             for (int g = 0; g < groups; ++g) {
                 int map = 0, cw, chh;
-                if (halo == 2) {                  // the tile's whole halo box
+                if (halo == 3) {                  // stride 2: g = input parity (row parity * 2 + column parity); odd views start one earlier
+                    map = g; cw = w0 - (g & 1); chh = h0 - (g >> 1);
+                } else if (halo == 2) {           // the tile's whole halo box
                     cw = w0 - 1; chh = h0 - 1;
                 } else if (halo) {                // g == kw: rows h0-1 .. h0+TH, columns w0+kw-1 .. +7
                     cw = w0 + g - 1; chh = h0 - 1;
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                     const Seg& sg = p.seg[s];
                     const int kchunks = sg.kchunks, bk = sg.bk, c_off = sg.c_off;
                     const uint32_t b_blk = sg.b_block_stride;
-                    const uint32_t stage_tx = sg.a_tx + (b_res ? 0u : (uint32_t)taps_per_group * sg.b_block_bytes);
+                    const uint32_t stage_tx = (halo == 3 ? sg.a_tx4[g] : sg.a_tx) + (b_res ? 0u : (uint32_t)taps_per_group * sg.b_block_bytes);
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (leader) {
@@ -334,11 +339,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         const int b_res = p.b_resident, num_stages = p.num_stages, n_tile = p.n_tile;
         // per-segment constants in registers (nseg <= 2)
         int sg_kch[kMaxSeg], sg_mps[kMaxSeg];
-        uint32_t sg_hi[kMaxSeg], sg_hiw[kMaxSeg], sg_kh16[kMaxSeg], sg_blk16[kMaxSeg], sg_base16[kMaxSeg];
+        uint32_t sg_hi[kMaxSeg], sg_hiw[kMaxSeg], sg_hi9[kMaxSeg], sg_kh16[kMaxSeg], sg_blk16[kMaxSeg], sg_base16[kMaxSeg];
 #pragma unroll
         for (int s = 0; s < kMaxSeg; ++s) {
             sg_kch[s] = s < nseg ? p.seg[s].kchunks : 0; sg_mps[s] = p.seg[s].bk >> 4;
-            sg_hi[s] = p.seg[s].desc_hi; sg_hiw[s] = p.seg[s].desc_hi_w; sg_kh16[s] = p.seg[s].kh_step16;
+            sg_hi[s] = p.seg[s].desc_hi; sg_hiw[s] = p.seg[s].desc_hi_w; sg_hi9[s] = p.seg[s].desc_hi9; sg_kh16[s] = p.seg[s].kh_step16;
             sg_blk16[s] = p.seg[s].b_block_stride >> 4; sg_base16[s] = p.seg[s].b_base >> 4;
         }
         int stage = 0; uint32_t phase = 0;
@@ -359,7 +364,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage16;
-                        if (halo == 2) {
+                        if (halo == 3) {
+                            // stride 2: this stage holds the (TW + pw) x (TH + ph) box of input parity (ph, pw) = (g >> 1, g & 1); it
+                            // serves taps kh in {0, 2} (box rows 0 / 1) or {1}, kw likewise (kh16 = one row); resident weights
+                            const int ph = g >> 1, pw = g & 1;
+                            const uint64_t hi_a = pw ? (uint64_t)sg_hi9[s] << 32 : desc_hi_w;
+                            const uint32_t row_pitch = (uint32_t)(8 + pw) * kh16;
+                            for (int a = 0; a <= ph; ++a) {
+                                const int kh = ph ? 2 * a : 1;
+                                for (int c = 0; c <= pw; ++c) {
+                                    const int kw = pw ? 2 * c : 1;
+                                    const uint32_t ta_lo = a_lo + (uint32_t)a * row_pitch + (uint32_t)c * kh16;
+                                    const uint32_t tb_lo = b_lo0 + b_base16 + (uint32_t)((kh * 3 + kw) * kchunks + kc) * b_blk16;
+                                    for (int j = 0; j < mma_per_step; ++j) {
+                                        tc_mma_bf16_if(leader, d_addr, hi_a | (ta_lo + 2u * j), desc_hi_w | (tb_lo + 2u * j), idesc, accum);
+                                        accum = 1;
+                                    }
+                                }
+                            }
+                        } else if (halo == 2) {
                             // one box, nine taps: tap (kh, kw) is the same tile kh * (TW+2) + kw rows further in (kh16 = one row);
                             // weights are resident: block (tap, kc)
                             uint32_t tb_lo = b_lo0 + b_base16 + (uint32_t)kc * b_blk16;
@@ -951,6 +974,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
             cudaError_t e = cudaSuccess;
             auto set = [&](const void* fn) { cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); if (r != cudaSuccess) e = r; };
             set((const void*)conv_tc_kernel<0, 0>); set((const void*)conv_tc_kernel<0, 1>); set((const void*)conv_tc_kernel<0, 2>);
+            set((const void*)conv_tc_kernel<0, 3>);
             set((const void*)conv_tc_kernel<1, 0>); set((const void*)conv_tc_kernel<2, 0>);
             attr_err = e;
         });
@@ -1002,13 +1026,31 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     for (int si = 0; si < p.nseg; ++si) bk_max = p.seg[si].bk > bk_max ? p.seg[si].bk : bk_max;
     p.a_bytes = (uint32_t)up1k((size_t)a_rows * bk_max * 2);
 
+    // ---- 3x3 stride 2 with resident weights: parity boxes (halo 3).  Each of the four (row, column) parity views of the
+    //      input is loaded once per K chunk as a (8 + pw) x (16 + ph) box and serves every tap that reads it by
+    //      descriptor start row: 561 box rows instead of 9 x 128 per tile and K chunk ----
+    if (ksize == 3 && stride == 2 && nsrc == 1 && !any_up && Cout <= 256) {
+        const double eff = (double)p.Wo * p.Ho / ((double)b2_ceil_div(p.Wo, 8) * 8 * b2_ceil_div(p.Ho, 16) * 16);
+        size_t w_all = 0;
+        for (int si = 0; si < p.nseg; ++si) w_all += (size_t)taps * p.seg[si].kchunks * up1k((size_t)b2_ceil_div(Cout, 16) * 16 * p.seg[si].bk * 2);
+        const size_t a3 = up1k((size_t)9 * 17 * bk_max * 2);
+        int mode3 = 1;
+        if (const char* hv = getenv("B2_CONV_S2BOX")) mode3 = atoi(hv);
+        if (mode3 && eff >= 0.6 && w_all + 3 * a3 <= kOneCtaSmem) {
+            p.halo = 3; p.TW = 8; p.TH = 16; p.NB = 1;
+            p.tiles_w = b2_ceil_div(p.Wo, p.TW); p.tiles_h = b2_ceil_div(p.Ho, p.TH); p.tiles_nb = b2_ceil_div(B, p.NB);
+            a_rows = 9 * 17;
+            p.a_bytes = (uint32_t)a3;
+        }
+    }
+
     // ---- kernel variant: transposed "TS" kernel (weights in tensor memory) for MMA-issue-bound layers with Cout <= 128 ----
     const int cout16 = b2_ceil_div(Cout, 16) * 16;
     int ts_mode = 0;                                   // B2_CONV_TS: 0 never (default: conv_tc_kernel's single-box halo mode is faster today), 1 heuristic, 2 every 3x3 conv with Cout <= 128
     if (const char* ev = getenv("B2_CONV_TS")) ts_mode = atoi(ev);
     const int res_taps = Cin <= (int)kTsWeightK ? (taps < (int)kTsWeightK / Cin ? taps : (int)kTsWeightK / Cin) : 0;
     p.ts = 0;
-    if (cout16 <= 128 && ksize == 3 && res_taps >= 1 && p.nseg <= kTsMaxSeg) {
+    if (cout16 <= 128 && ksize == 3 && res_taps >= 1 && p.nseg <= kTsMaxSeg && p.halo != 3) {
         if (ts_mode == 2) p.ts = 1;
         else if (ts_mode == 1) p.ts = (p.halo && res_taps >= 3) ? 1 : 0;
         size_t fb = 0;                                  // shared memory for the weights of the taps served by SS MMAs
@@ -1076,7 +1118,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     } else {
     // ---- resident-weight 3x3 stride-1 layers: single halo box per K chunk (halo 2, see the TS branch) when the weights and
     //      >= 3 box stages fit; decided on the resident footprint, which does not depend on the stage layout ----
-    if (p.halo && cout16 <= 256) {
+    if (p.halo == 1 && cout16 <= 256) {
         size_t w_all = 0;
         for (int si = 0; si < p.nseg; ++si) w_all += (size_t)taps * p.seg[si].kchunks * up1k((size_t)cout16 * p.seg[si].bk * 2);
         const size_t a2 = up1k((size_t)(p.TW + 2) * (p.TH + 2) * bk_max * 2);
@@ -1084,10 +1126,10 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
         if (const char* hv = getenv("B2_CONV_HALO2")) halo2_mode = atoi(hv);
         if (halo2_mode && w_all + 3 * a2 <= kOneCtaSmem) { p.halo = 2; a_rows = (p.TW + 2) * (p.TH + 2); p.a_bytes = (uint32_t)a2; }
     }
-    const int tpg = p.halo == 2 ? 9 : p.halo ? 3 : 1;
+    const int tpg = p.halo == 2 ? 9 : p.halo == 1 ? 3 : 1;
     // ---- N tiling: streamed-weight stage = A box + tpg weight blocks; shrink the N tile until two stages fit ----
     int n_cap = 256;
-    while (n_cap > 16 && p.halo != 2) {          // halo 2 implies resident weights: one N tile
+    while (n_cap > 16 && p.halo < 2) {           // halo 2 / 3 imply resident weights: one N tile
         const int nt = cout16 < n_cap ? cout16 : n_cap;
         if (2 * (p.a_bytes + tpg * up1k((size_t)nt * bk_max * 2)) <= 200 * 1024) break;
         n_cap /= 2;
@@ -1112,14 +1154,16 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
         s.b_base = (uint32_t)b_all;
         b_all += (size_t)taps * s.kchunks * s.b_block_stride;
         p.b_res_bytes += (uint32_t)(taps * s.kchunks) * s.b_block_bytes;
-        s.kh_step16 = p.halo == 2 ? row_bytes >> 4 : p.halo ? (8u * row_bytes) >> 4 : 0u;
+        s.kh_step16 = p.halo >= 2 ? row_bytes >> 4 : p.halo ? (8u * row_bytes) >> 4 : 0u;
+        for (int m = 0; m < 4; ++m) s.a_tx4[m] = (uint32_t)((8 + (m & 1)) * (16 + (m >> 1))) * row_bytes;
         const uint32_t sbo = 8u * row_bytes, swz = s.bk == 64 ? 2u : s.bk == 32 ? 4u : 6u;   // UMMA layout type: 128B / 64B / 32B swizzle
         const uint32_t sbo_a = p.halo == 2 ? (uint32_t)(p.TW + 2) * row_bytes : sbo;        // pixel operand: 8-row groups (TW+2) rows apart in the halo box
         s.desc_hi = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
         s.desc_hi_w = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
+        s.desc_hi9 = (((9u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
         s.up = srcs[src_of[si]].up;
         s.h_lo = H / 2;
-        steps_per_tile += (p.halo == 2 ? 1 : p.halo ? 3 : taps) * s.kchunks;
+        steps_per_tile += (p.halo == 3 ? 4 : p.halo == 2 ? 1 : p.halo ? 3 : taps) * s.kchunks;
     }
     p.b_stage_stride = (uint32_t)tpg * b_blk_max;
     uint32_t cols = 2u * p.n_tile, pw = 32;
@@ -1183,9 +1227,10 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
         } else {
             // A maps: (C, W', H', B) views of the NHWC input
             const cuuint32_t estr[4] = {1, 1, 1, 1};
-            const cuuint32_t box[4] = {(cuuint32_t)s.bk, (cuuint32_t)(p.halo == 2 ? p.TW + 2 : p.TW), (cuuint32_t)(p.halo ? p.TH + 2 : p.TH), (cuuint32_t)p.NB};
+            cuuint32_t box[4] = {(cuuint32_t)s.bk, (cuuint32_t)(p.halo == 2 ? p.TW + 2 : p.TW), (cuuint32_t)(p.halo == 1 || p.halo == 2 ? p.TH + 2 : p.TH), (cuuint32_t)p.NB};
             for (int m = 0; m < nmaps; ++m) {
                 const int ph = m >> 1, pw_ = m & 1;
+                if (p.halo == 3) { box[1] = (cuuint32_t)(p.TW + pw_); box[2] = (cuuint32_t)(p.TH + ph); }
                 cuuint64_t dims[4], strides[3];
                 const char* ptr = base;
                 if (stride == 1) {
@@ -1240,6 +1285,7 @@ int b2_conv_launch(const void* storage, cudaStream_t stream) {
     if (L->p.ts) conv_ts_kernel<<<L->grid, kTsThreads, L->smem, stream>>>(L->p);
     else if (L->p.epi == 1) conv_tc_kernel<1, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
     else if (L->p.epi == 2) conv_tc_kernel<2, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
+    else if (L->p.halo == 3) conv_tc_kernel<0, 3><<<L->grid, kThreads, L->smem, stream>>>(L->p);
     else if (L->p.halo == 2) conv_tc_kernel<0, 2><<<L->grid, kThreads, L->smem, stream>>>(L->p);
     else if (L->p.halo == 1) conv_tc_kernel<0, 1><<<L->grid, kThreads, L->smem, stream>>>(L->p);
     else conv_tc_kernel<0, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
