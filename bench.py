@@ -363,9 +363,18 @@ def run_b200(a):
     all_ms = sum(p["ms"] for p in prof)
     achieved = conv_fl / conv_ms / 1e9
     ms_step = ms_dev / a.steps
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, 78 launches/step)", "achieved": achieved,
+    # DRAM traffic per launch of the same kernel: dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one
+    # forward of this workload, from the committed ncu capture (profiles/; per-launch list beside it), averaged per launch
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic_v17.json")
+    if os.path.exists(tp) and S == 256 and a.model == MODEL:
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["conv_dram_bytes_per_launch"], "profiles/r01_conv_traffic_v17.json (ncu, %d launches)" % tj["conv_launches"]
+    conv_bytes = sum(p["bytes"] for p in conv)
+    roofline = {"bound": "tensor", "kernel": f"conv_tc_kernel (tcgen05 implicit GEMM, {len(conv)} launches/step)", "achieved": achieved,
                 "peak": pk["tc_sustained"], "peak_kind": f"bf16 dense sustained, {pk['src']}", "unit": "TFLOP/s",
-                "frac": achieved / pk["tc_sustained"], "traffic": None, "avg_launch_ms": conv_ms / len(conv),
+                "frac": achieved / pk["tc_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": conv_bytes / len(conv), "avg_launch_ms": conv_ms / len(conv),
                 "algorithmic_flops_per_step": conv_fl, "share_of_step": conv_ms / all_ms if all_ms else None,
                 "forward_ms_eager_events": all_ms, "end_to_end_tensor_frac": pipe.flops_per_frame * S / (ms_step * 1e-3) / 1e12 / pk["tc_sustained"]}
     line = {
