@@ -6,6 +6,9 @@ import torch
 import b200dt
 from b200dt import ops
 
+ACT = os.environ.get("CB_ACT", "1") == "1"
+
+
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     iters = 5
@@ -23,12 +26,12 @@ def main():
         Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
         y = torch.empty((B, Ho, Wo, max(Cout, 8)), device="cuda", dtype=torch.bfloat16)
         r = torch.randn((B, Ho, Wo, Cout), device="cuda").to(torch.bfloat16) if res else None
-        ops.conv2d_bf16(x, w, b, k, s, True, out=y, residual=r)
+        ops.conv2d_bf16(x, w, b, k, s, ACT, out=y, residual=r)
         ts = []
         for _ in range(iters):
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); ops.conv2d_bf16(x, w, b, k, s, True, out=y, residual=r); e1.record()
+            e0.record(); ops.conv2d_bf16(x, w, b, k, s, ACT, out=y, residual=r); e1.record()
             torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
         fl = 2 * B * Ho * Wo * Cout * Cin * k * k

@@ -32,8 +32,7 @@
 namespace {
 
 constexpr int kMaxStages = 12;
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, 16-column chunks interleaved
-constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kThreadsMw1 = 32 * (1 + 1 + 8), kThreadsMw2 = 32 * (1 + 2 + 8);   // warp 0 TMA, 1 or 2 MMA warps, 8 epilogue warps
 constexpr int kMaxNTile = 256;
 constexpr int kMaxSeg = 4;                         // up to two sources (Concat folded into the conv) x two chunk widths
 
@@ -96,6 +95,7 @@ struct alignas(64) ConvParams {
     int stg_bufs;             // 2: double buffered (one named barrier per tile), 1: single (two barriers)
     uint32_t chunk_magic;     // ceil(2^32 / (cout16 / 16)): item -> pixel by a multiply-high
     int ts_steps;             // pipeline stages one tile consumes
+    int mma_warps;            // conv_tc_kernel: 1 or 2 MMA-issuing warps (2: alternate tiles, two stage rings)
     int dbg_skip_mma;         // B2_CONV_DEBUG=1: issue no MMAs (timing of the TMA / epilogue paths alone; results are garbage)
 };
 
@@ -203,8 +203,11 @@ __device__ __forceinline__ float2 cls_unkey(int key) {
 
 // EPI: epilogue variant (ConvParams::epi), HALO: ConvParams::halo -- compile-time copies of the two fields, so that each
 // instance carries only its own loops (the kernel is sensitive to registers / code size in the issue and epilogue paths)
-template <int EPI, int HALO>
-__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+// MW: MMA-issuing warps.  1: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, up to two CTAs per SM.  2 (plans with ONE CTA per SM):
+// warps 1 and 2 issue alternate tiles, each with its own accumulator stage and its own ring of pipeline stages.
+template <int EPI, int HALO, int MW>
+__global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int kEpiWarps = 8, kMmaWarps = MW, kThreads = 32 * (1 + MW + 8), kSub = 2;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -273,7 +276,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                                     tap * Cin + sg.c_off + kc * sg.bk, 0);
             }
         }
-        int stage = 0; uint32_t phase = 0;
+        // p.mma_warps == 2: two stage rings of num_stages / 2 slots; ring r holds the tiles issued by MMA warp r (a ring with
+        // two consumers would let one of them run a whole revolution ahead, which mbarrier phase parity cannot tell apart)
+        const int ring_stages = MW == 2 ? num_stages >> 1 : num_stages;
+        int stage = 0; uint32_t phase = 0;                  // MW == 1: the one ring; MW == 2: the ring of the current tile
+        int ostage = ring_stages; uint32_t ophase = 0;      // MW == 2: saved position in the other ring
+        int stage_lo = 0, stage_hi = ring_stages;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_idx = tile % n_tiles;
             int m_idx = tile / n_tiles;
@@ -321,13 +329,24 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                             }
                         }
                         __syncwarp();
-                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                        if (++stage == stage_hi) { stage = stage_lo; phase ^= 1; }
                     }
                 }
             }
+            if (MW == 2) {                                  // the next tile belongs to the other MMA warp: switch rings
+                const int ts_ = stage; stage = ostage; ostage = ts_;
+                const uint32_t tp_ = phase; phase = ophase; ophase = tp_;
+                stage_lo = stage_lo ? 0 : ring_stages; stage_hi = stage_lo + ring_stages;
+            }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp <= kMmaWarps) {
+        // ===================== MMA issuers (warps 1, 2) =====================
+        // Measured (tools/cp_probe.cu): ONE issuing stream gets at most one tcgen05.mma per ~64 cycles whatever N is, two
+        // streams together reach the operand-fetch rate (max(N/2, 32 + N/4) cycles per MMA per SM: 48 at N = 64).  Layers whose
+        // resident weights leave room for one CTA per SM therefore run two issuing warps: warp r takes tiles r, r+2, ...,
+        // owns accumulator stage r and its own ring of pipeline stages.
+        const int mw = warp - 1;
+        {
         const uint32_t leader = elect_one() ? 1u : 0u;
         // InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B, N>>3 at 17, M>>4 at 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
@@ -346,10 +365,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             sg_hi[s] = p.seg[s].desc_hi; sg_hiw[s] = p.seg[s].desc_hi_w; sg_hi9[s] = p.seg[s].desc_hi9; sg_kh16[s] = p.seg[s].kh_step16;
             sg_blk16[s] = p.seg[s].b_block_stride >> 4; sg_base16[s] = p.seg[s].b_base >> 4;
         }
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
+        constexpr bool two = MW == 2;
+        const int ring_stages = two ? num_stages >> 1 : num_stages;
+        const int stage_lo = mw * ring_stages, stage_hi = stage_lo + ring_stages;
+        int stage = stage_lo; uint32_t phase = 0;
+        int acc = mw; uint32_t acc_phase = 0;
         if (b_res) { mbar_wait(&bres_bar, 0); tc_fence_after(); }
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x + mw * gridDim.x; tile < total_tiles; tile += (two ? 2 : 1) * gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_addr = tmem_base + (uint32_t)(acc * n_tile);
@@ -411,17 +433,19 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                         }
                         }
                         tc_commit_if(leader, &empty_bar[stage]);     // frees the smem slot when these MMAs retire
-                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                        if (++stage == stage_hi) { stage = stage_lo; phase ^= 1; }
                     }
                 }
             }
             tc_commit_if(leader, &tfull_bar[acc]);               // accumulator complete -> epilogue
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (two) acc_phase ^= 1;
+            else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;                   // which of the two warps of the quadrant
+        const int half = (warp - 1 - kMmaWarps) >> 2;       // which of the kSub warps of the quadrant
         const int row = quad * 32 + lane;                   // row of the 128-row tile == TMEM lane
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, nb = row / (p.TW * p.TH);
         const int n_tiles = p.n_tiles, n_tile = p.n_tile, tiles_w = p.tiles_w, tiles_h = p.tiles_h, TW = p.TW, TH = p.TH, NB = p.NB;
@@ -447,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             if (n_tiles > 1) {
                 // per-tile bias slice (named barrier over the epilogue warps only)
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
-                for (int i = threadIdx.x - 64; i < n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < Cout ? __ldg(p.bias + n_base + i) : 0.f;
+                for (int i = threadIdx.x - 32 * (1 + kMmaWarps); i < n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < Cout ? __ldg(p.bias + n_base + i) : 0.f;
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
             }
 
@@ -455,9 +479,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_tile);
             if (epi == 0) {
-                // this warp's chunks: half, half+2, half+4, ... ; two chunks in flight per iteration
-                for (int j = half; j < nchunks; j += 4) {
-                    const int j2 = j + 2;
+                // this warp's chunks: half, half + kSub, half + 2 kSub, ... ; two chunks in flight per iteration
+                for (int j = half; j < nchunks; j += 2 * kSub) {
+                    const int j2 = j + kSub;
                     const bool two = j2 < nchunks;
                     uint32_t v0[16], v1[16];
                     tmem_ld16(t_addr + j * 16, v0);
@@ -973,9 +997,9 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
             const int bytes = 227 * 1024 - 4096;
             cudaError_t e = cudaSuccess;
             auto set = [&](const void* fn) { cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); if (r != cudaSuccess) e = r; };
-            set((const void*)conv_tc_kernel<0, 0>); set((const void*)conv_tc_kernel<0, 1>); set((const void*)conv_tc_kernel<0, 2>);
-            set((const void*)conv_tc_kernel<0, 3>);
-            set((const void*)conv_tc_kernel<1, 0>); set((const void*)conv_tc_kernel<2, 0>);
+            set((const void*)conv_tc_kernel<0, 0, 1>); set((const void*)conv_tc_kernel<0, 1, 1>); set((const void*)conv_tc_kernel<0, 2, 1>);
+            set((const void*)conv_tc_kernel<0, 3, 1>); set((const void*)conv_tc_kernel<1, 0, 1>); set((const void*)conv_tc_kernel<2, 0, 1>);
+            set((const void*)conv_tc_kernel<0, 2, 2>); set((const void*)conv_tc_kernel<0, 3, 2>);
             attr_err = e;
         });
         B2_CUDA(attr_err);
@@ -1192,6 +1216,13 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     if (stages > want + 2 && stages > 4) stages = want + 2 > 4 ? want + 2 : 4;
     if (stages > kMaxStages) stages = kMaxStages;
     B2_REQUIRE(stages >= 2, "conv: tile does not fit in shared memory (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
+    // two MMA-issuing warps when each can have a ring of >= 2 stages (B2_CONV_MMAW=1 forces one)
+    int mmaw = 2;
+    if (const char* mv = getenv("B2_CONV_MMAW")) mmaw = atoi(mv);
+    // measured: pays on the resident-weight single-box layers that run one CTA per SM (one issuing stream per SM otherwise);
+    // streamed-weight layers lose more from the halved look-ahead of each ring than they gain
+    p.mma_warps = (mmaw >= 2 && stages >= 4 && p.halo >= 2 && ctas == 1) ? 2 : 1;
+    if (p.mma_warps == 2) stages &= ~1;
     p.num_stages = stages;
     L->smem = (size_t)stages * (p.b_resident ? a_stage : ab_stage) + (p.b_resident ? b_all : 0) + 1024;
     }
@@ -1274,6 +1305,7 @@ int b2_conv_set_head_epilogue(void* storage, int epi, float* out_f32) {
     B2_REQUIRE(epi == 1 || epi == 2, "conv: head epilogue mode must be 1 (DFL) or 2 (classes)");
     B2_REQUIRE(L->p.n_tiles == 1 && (epi != 1 || L->p.Cout == 64) && out_f32, "conv: head epilogue needs one N tile (DFL: exactly 64 channels)");
     B2_REQUIRE(!L->p.ts && L->p.halo == 0, "conv: head epilogues are implemented for 1x1 convs in conv_tc_kernel only");
+    L->p.mma_warps = 1;
     L->p.epi = epi; L->p.out_f32 = out_f32;
     return B2_OK;
 }
@@ -1283,12 +1315,14 @@ void b2_count_launch(int n);
 int b2_conv_launch(const void* storage, cudaStream_t stream) {
     const B2ConvLaunch* L = reinterpret_cast<const B2ConvLaunch*>(storage);
     if (L->p.ts) conv_ts_kernel<<<L->grid, kTsThreads, L->smem, stream>>>(L->p);
-    else if (L->p.epi == 1) conv_tc_kernel<1, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
-    else if (L->p.epi == 2) conv_tc_kernel<2, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
-    else if (L->p.halo == 3) conv_tc_kernel<0, 3><<<L->grid, kThreads, L->smem, stream>>>(L->p);
-    else if (L->p.halo == 2) conv_tc_kernel<0, 2><<<L->grid, kThreads, L->smem, stream>>>(L->p);
-    else if (L->p.halo == 1) conv_tc_kernel<0, 1><<<L->grid, kThreads, L->smem, stream>>>(L->p);
-    else conv_tc_kernel<0, 0><<<L->grid, kThreads, L->smem, stream>>>(L->p);
+    else if (L->p.epi == 1) conv_tc_kernel<1, 0, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
+    else if (L->p.epi == 2) conv_tc_kernel<2, 0, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
+    else if (L->p.mma_warps == 2 && L->p.halo == 3) conv_tc_kernel<0, 3, 2><<<L->grid, kThreadsMw2, L->smem, stream>>>(L->p);
+    else if (L->p.mma_warps == 2) conv_tc_kernel<0, 2, 2><<<L->grid, kThreadsMw2, L->smem, stream>>>(L->p);
+    else if (L->p.halo == 3) conv_tc_kernel<0, 3, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
+    else if (L->p.halo == 2) conv_tc_kernel<0, 2, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
+    else if (L->p.halo == 1) conv_tc_kernel<0, 1, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
+    else conv_tc_kernel<0, 0, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
