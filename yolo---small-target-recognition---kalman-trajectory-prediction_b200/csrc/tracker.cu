@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kAssocThreads) associate_global_kernel(const B
 // Same algorithm with the stream's LIVE tracks compacted into shared memory first (box, id, slot): the rounds then
 // touch no global memory.  Dynamic shared memory: C * 28 bytes.
 __global__ void __launch_bounds__(kAssocThreads) associate_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
-                                                                const int32_t* __restrict__ det_counts) {
+                                                                const int32_t* __restrict__ det_counts, int cand_cap) {
     extern __shared__ uint8_t s_raw[];
     float4* l_box = reinterpret_cast<float4*>(s_raw);                    // [C]
     int* l_id = reinterpret_cast<int*>(l_box + b.C);                      // [C]
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kAssocThreads) associate_kernel(const Bank b, 
     __shared__ int s_best_t[kMaxDetsSmem];
     __shared__ float s_best_iou[kMaxDetsSmem];
     __shared__ int s_warp[32];
-    __shared__ int s_progress, s_nlive;
+    __shared__ int s_progress, s_ncand;
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kAssocThreads / 32;
     const int D = min(det_counts[s], b.max_dets);
     const int g0 = s * b.C;
@@ -232,6 +232,73 @@ __global__ void __launch_bounds__(kAssocThreads) associate_kernel(const Bank b, 
     const int L = base_live;
     __syncthreads();
     const float thr = b.iou_thr;
+    // ---- fast path: list every pair with IoU >= thr ONCE (sparse: a detection overlaps a handful of tracks), then run the
+    //      mutual-best rounds on that list with 64-bit shared-memory atomicMax keys instead of re-evaluating D x L IoUs per
+    //      round.  A pair is accepted when the track is the detection's best free candidate by (IoU, lowest track id) and
+    //      the detection is the track's best free candidate by (IoU, lowest detection index): exactly the pairs the
+    //      reference's descending-IoU greedy walk takes (enhanced_multi_target_tracker.py:234-270).  Falls back to the
+    //      dense rounds below if the list overflows. ----
+    uint8_t* dyn = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(l_match + b.C) + 7) & ~uintptr_t(7));
+    unsigned long long* t_best = reinterpret_cast<unsigned long long*>(dyn);               // [C]
+    unsigned long long* d_best = t_best + b.C;                                              // [kMaxDetsSmem]
+    float* c_iou = reinterpret_cast<float*>(d_best + kMaxDetsSmem);                         // [cand_cap]
+    uint32_t* c_pair = reinterpret_cast<uint32_t*>(c_iou + cand_cap);                       // [cand_cap]: det << 16 | track
+    if (tid == 0) s_ncand = 0;
+    __syncthreads();
+    if (D > 0 && L > 0 && cand_cap > 0) {
+        for (int d0 = 0; d0 < D; d0 += nwarps) {
+            const int d = d0 + warp;
+            if (d < D) {
+                const float4 db = s_det[d];
+                for (int t = lane; t < L; t += 32) {
+                    const float v = iou_ref(db, l_box[t]);
+                    if (v >= thr) {
+                        const int pos = atomicAdd(&s_ncand, 1);
+                        if (pos < cand_cap) { c_iou[pos] = v; c_pair[pos] = ((uint32_t)d << 16) | (uint32_t)t; }
+                    }
+                }
+            }
+            if (d0 == 0) {
+                // dense scene (the first nwarps detections already project past the list capacity): do not finish a list
+                // that will be thrown away, go to the dense rounds
+                __syncthreads();
+                const int seen = min(D, nwarps);
+                if ((long long)s_ncand * D > (long long)cand_cap * seen) { if (tid == 0) s_ncand = cand_cap + 1; break; }
+            }
+        }
+    }
+    __syncthreads();
+    const int M = s_ncand;
+    if (M <= cand_cap && b.C <= 65536) {
+        while (M > 0) {
+            for (int d = tid; d < D; d += kAssocThreads) d_best[d] = 0ull;
+            for (int t = tid; t < L; t += kAssocThreads) t_best[t] = 0ull;
+            if (tid == 0) s_progress = 0;
+            __syncthreads();
+            for (int e = tid; e < M; e += kAssocThreads) {
+                const uint32_t pr = c_pair[e];
+                const int d = (int)(pr >> 16), t = (int)(pr & 0xFFFFu);
+                if (s_dmatch[d] >= 0 || l_match[t] >= 0) continue;
+                const unsigned long long hi = (unsigned long long)__float_as_uint(c_iou[e]) << 32;   // IoU > 0: bits order like the float
+                atomicMax(&d_best[d], hi | (unsigned)(0xFFFFFFFFu - (unsigned)l_id[t]));
+                atomicMax(&t_best[t], hi | (unsigned)(0xFFFFFFFFu - (unsigned)d));
+            }
+            __syncthreads();
+            for (int e = tid; e < M; e += kAssocThreads) {
+                const uint32_t pr = c_pair[e];
+                const int d = (int)(pr >> 16), t = (int)(pr & 0xFFFFu);
+                if (s_dmatch[d] >= 0 || l_match[t] >= 0) continue;
+                const unsigned long long hi = (unsigned long long)__float_as_uint(c_iou[e]) << 32;
+                if (d_best[d] == (hi | (unsigned)(0xFFFFFFFFu - (unsigned)l_id[t])) && t_best[t] == (hi | (unsigned)(0xFFFFFFFFu - (unsigned)d))) {
+                    // unique per d and per t within a round: no two entries share (d, best t) or (t, best d)
+                    s_dmatch[d] = t; l_match[t] = d; s_progress = 1;
+                }
+            }
+            __syncthreads();
+            if (!s_progress) break;
+            __syncthreads();
+        }
+    } else
     if (D > 0 && L > 0) {
         while (true) {
             if (tid == 0) s_progress = 0;
@@ -646,13 +713,22 @@ extern "C" int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_col
     const Bank& b = t->impl.b;
     cudaStream_t st = (cudaStream_t)stream;
     bank_predict_kernel<<<b2_ceil_div(b.N, 256), 256, 0, st>>>(b);
-    const size_t assoc_smem = (size_t)b.C * 28;
-    if (assoc_smem <= 160 * 1024) {
+    const size_t track_smem = (size_t)b.C * 28;
+    if (track_smem <= 160 * 1024) {
+        // sparse matching: best-candidate keys (8 B per track, 8 KB for the detections) + the pair list (8 B per pair) in what
+        // is left of ~190 KB of shared memory, up to 8192 pairs
+        const size_t fixed = track_smem + (size_t)b.C * 8 + kMaxDetsSmem * 8 + 16;
+        size_t cap = fixed < 190 * 1024 ? (190 * 1024 - fixed) / 8 : 0;
+        cap = cap > 8192 ? 8192 : (cap < 512 ? 0 : cap);
+        // the list must not cost occupancy: banks whose track arrays still allow two CTAs per SM (and have more streams than
+        // SMs) keep the small footprint and the dense rounds
+        if (track_smem + 30 * 1024 <= 113 * 1024 && b.S > b2_num_sms()) cap = 0;
+        const size_t assoc_smem = cap ? fixed + cap * 8 : track_smem;
         if (assoc_smem > 16 * 1024) {
             static size_t granted = 0;
             if (assoc_smem > granted) { B2_CUDA(cudaFuncSetAttribute(associate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assoc_smem)); granted = assoc_smem; }
         }
-        associate_kernel<<<b.S, kAssocThreads, assoc_smem, st>>>(b, dets, det_cols, det_counts);
+        associate_kernel<<<b.S, kAssocThreads, assoc_smem, st>>>(b, dets, det_cols, det_counts, (int)cap);
     } else {
         associate_global_kernel<<<b.S, kAssocThreads, 0, st>>>(b, dets, det_cols, det_counts);
     }
