@@ -43,39 +43,45 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     const int W = p.w[lvl], H = p.h[lvl];
     const __nv_bfloat16* row = p.lv[lvl] + ((size_t)b * H * W + la) * p.lstride;
 
-    // ---- all loads first (memory-level parallelism): DFL chunk + up to two class chunks per lane ----
+    // ---- class loads first (memory-level parallelism): up to two class chunks per lane; the DFL chunk only when needed ----
     const int nchunks = (p.nc + 7) >> 3;
     const uint4 ninf4 = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // bf16 -inf pairs
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = ninf4, q2 = ninf4;
     if (active) {
-        q0 = ldg_nc_v4(row + sub * 8);
+        if (p.dense) q0 = ldg_nc_v4(row + sub * 8);
         if (sub < nchunks) q1 = ldg_nc_v4(row + 64 + sub * 8);
         if (sub + 8 < nchunks) q2 = ldg_nc_v4(row + 64 + (sub + 8) * 8);
     }
-    // ---- DFL: softmax expectation over 16 bins per side ----
-    float f[8];
-    unpack8(q0, f);
-    float m = f[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    float se = 0.f, sw = 0.f;
-    const float bin0 = (float)((sub & 1) * 8);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float e = __expf(f[i] - m);
-        se += e; sw = fmaf(e, bin0 + (float)i, sw);
-    }
-    se += __shfl_xor_sync(0xffffffffu, se, 1);
-    sw += __shfl_xor_sync(0xffffffffu, sw, 1);
-    const float dist = sw / se;
-    const int gbase = lane & ~7;
-    const float dl = __shfl_sync(0xffffffffu, dist, gbase + 0), dt = __shfl_sync(0xffffffffu, dist, gbase + 2);
-    const float dr = __shfl_sync(0xffffffffu, dist, gbase + 4), db = __shfl_sync(0xffffffffu, dist, gbase + 6);
 
     // ---- classes: max logit / argmax over nc ----
     float best = -INFINITY; int bidx = 0x7fffffff;
     const size_t dense_base = (size_t)b * (4 + p.nc) * p.A + a;
+    if (!p.dense) {
+        // Pass 1: only the MAX logit of the anchor, with packed bf16x2 max instructions (exact: max of bf16 values).  The class
+        // index is looked up afterwards, and only in warps that hold a candidate.
+        __nv_bfloat162 m2 = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+        for (int ck = sub; ck < nchunks; ck += 8) {
+            uint4 q = ck == sub ? q1 : ck == sub + 8 ? q2 : (active ? ldg_nc_v4(row + 64 + ck * 8) : ninf4);
+            const int nvalid = p.nc - ck * 8;                       // < 8 only in the last chunk: padding channels are not classes
+            if (nvalid < 8) {
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (2 * i >= nvalid) w[i] = 0xFF80FF80u;
+                    else if (2 * i + 1 >= nvalid) w[i] = (w[i] & 0x0000FFFFu) | 0xFF800000u;
+                }
+                q = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            m2 = __hmax2(m2, *reinterpret_cast<const __nv_bfloat162*>(&q.x)); m2 = __hmax2(m2, *reinterpret_cast<const __nv_bfloat162*>(&q.y));
+            m2 = __hmax2(m2, *reinterpret_cast<const __nv_bfloat162*>(&q.z)); m2 = __hmax2(m2, *reinterpret_cast<const __nv_bfloat162*>(&q.w));
+        }
+        best = fmaxf(__low2float(m2), __high2float(m2));
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        const bool maybe = active && (1.f / (1.f + __expf(-best))) > p.conf;
+        if (!__any_sync(0xffffffffu, maybe)) return;
+    }
+    best = -INFINITY;
     for (int ck = sub; ck < nchunks; ck += 8) {
         float c[8];
         if (ck == sub) unpack8(q1, c);
@@ -100,6 +106,36 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
         const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
         if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
     }
+    const float score = 1.f / (1.f + __expf(-best));
+    // best class over ALL classes first, then the `classes=` filter drops the anchor (nms.py:111-124)
+    const bool anchor_cand = active && bidx != 0x7fffffff && score > p.conf && (!p.cmask || p.cmask[bidx]);
+    // Boxes are only needed for candidates (a per cent of the anchors at conf 0.15) unless the dense tensor is asked for:
+    // warps without a candidate stop here -- 128 of the 288 bytes per anchor are never read, 64 exponentials never taken.
+    if (!p.dense) {
+        if (!__any_sync(0xffffffffu, anchor_cand)) return;
+        if (active) q0 = ldg_nc_v4(row + sub * 8);
+    }
+
+    // ---- DFL: softmax expectation over 16 bins per side ----
+    float f[8];
+    unpack8(q0, f);
+    float m = f[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    float se = 0.f, sw = 0.f;
+    const float bin0 = (float)((sub & 1) * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float e = __expf(f[i] - m);
+        se += e; sw = fmaf(e, bin0 + (float)i, sw);
+    }
+    se += __shfl_xor_sync(0xffffffffu, se, 1);
+    sw += __shfl_xor_sync(0xffffffffu, sw, 1);
+    const float dist = sw / se;
+    const int gbase = lane & ~7;
+    const float dl = __shfl_sync(0xffffffffu, dist, gbase + 0), dt = __shfl_sync(0xffffffffu, dist, gbase + 2);
+    const float dr = __shfl_sync(0xffffffffu, dist, gbase + 4), db = __shfl_sync(0xffffffffu, dist, gbase + 6);
 
     // ---- box (tal.py:382-391 then * stride; xywh2xyxy ops.py:277-294), same fp32 operation order ----
     const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f, st = (float)p.stride[lvl];
@@ -107,9 +143,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     const float cx = (x1 + x2) / 2.f * st, cy = (y1 + y2) / 2.f * st, bw = (x2 - x1) * st, bh = (y2 - y1) * st;
     if (p.dense && active && sub < 4) p.dense[dense_base + (size_t)sub * p.A] = sub == 0 ? cx : sub == 1 ? cy : sub == 2 ? bw : bh;
 
-    const float score = 1.f / (1.f + __expf(-best));
-    // best class over ALL classes first, then the `classes=` filter drops the anchor (nms.py:111-124)
-    const bool is_cand = active && sub == 0 && bidx != 0x7fffffff && score > p.conf && (!p.cmask || p.cmask[bidx]);
+    const bool is_cand = anchor_cand && sub == 0;
     const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
     if (ball) {
         int base = 0;
