@@ -304,6 +304,12 @@ def test_nms_edge_cases():
     got = ops.non_max_suppression(torch.from_numpy(big).cuda(), 0.05, 0.5, max_det=300)[0].cpu().numpy()
     ref = pp.non_max_suppression(big, 0.05, 0.5, max_det=300, mode="exact")[0]
     np.testing.assert_array_equal(got, ref)
+    # several NMS blocks with a long kept list (blocked exact path: members are tested against earlier blocks' kept boxes)
+    big2 = synth_pred(11, 2, 2, 9000, frac=0.4)
+    got2 = ops.non_max_suppression(torch.from_numpy(big2).cuda(), 0.05, 0.3, max_det=1000)
+    ref2 = pp.non_max_suppression(big2, 0.05, 0.3, max_det=1000, mode="exact")
+    for b in range(2):
+        np.testing.assert_array_equal(got2[b].cpu().numpy(), ref2[b])
 
 
 @pytest.mark.parametrize("tag,hw", [("512x640", (512, 640)), ("500x640", (500, 640))])

@@ -312,53 +312,86 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
     n = min(n, p.max_nms);
 
     const int max_keep = min(p.max_det, kMaxKeep);
-    if (p.mode == 0 && n <= kFastN) {
-        // ---- fast path (exact greedy NMS): all pairwise tests in parallel into an n x n bit matrix, then one warp
-        //      walks the candidates in score order OR-ing the suppression rows of the boxes it keeps ----
+    if (p.mode == 0) {
+        // ---- exact greedy NMS, blocked: candidates are taken in score order in blocks of kFastN.  Per block: (1) every
+        //      member is tested against the boxes kept so far, (2) all pairwise tests inside the block go in parallel into
+        //      an nb x nb bit matrix, (3) one warp walks the block in score order OR-ing the suppression rows of the boxes
+        //      it keeps.  One block covers the usual case; dense scenes (thousands of candidates) take a few blocks instead
+        //      of one block-wide pass per kept box. ----
         extern __shared__ uint32_t s_dyn[];
-        float4* fbox = reinterpret_cast<float4*>(s_dyn);                  // [kFastN]
-        uint32_t* mat = s_dyn + kFastN * 4;                                 // [n][W]
-        const int Wd = (n + 31) >> 5;
-        for (int i = tid; i < n; i += kNmsThreads) {
-            const float* c = cand + (size_t)pay[i] * 6;
-            const float off = p.agnostic ? 0.f : __fmul_rn(c[5], p.max_wh);
-            fbox[i] = make_float4(__fadd_rn(c[0], off), __fadd_rn(c[1], off), __fadd_rn(c[2], off), __fadd_rn(c[3], off));
-        }
+        float4* fbox = reinterpret_cast<float4*>(s_dyn);                  // [kFastN] boxes of the block (class offset applied)
+        uint32_t* mat = s_dyn + kFastN * 4;                                 // [nb][Wd]
+        float4* kbox = reinterpret_cast<float4*>(mat + kFastN * ((kFastN + 31) / 32));   // [kMaxKeep] kept boxes
+        uint32_t* dead = alive;                                            // [kFastN / 32] members suppressed by earlier blocks
+        if (tid == 0) s_nkeep = 0;
         __syncthreads();
-        for (int t = tid; t < n * Wd; t += kNmsThreads) {
-            const int i = t / Wd, wj = t - i * Wd;
-            uint32_t bits = 0;
-            if (wj * 32 + 31 > i) {
-                const float4 bi = fbox[i];
-                const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-                const int j0 = max(wj * 32, i + 1), j1 = min(wj * 32 + 32, n);
-                for (int j = j0; j < j1; ++j) {
-                    const float4 bj = fbox[j];
-                    const float iw = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
-                    const float ih = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
-                    const float inter = __fmul_rn(iw, ih);
-                    const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-                    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
-                    if (iou > p.iou_thres) bits |= 1u << (j & 31);
-                }
+        for (int s0 = 0; s0 < n; s0 += kFastN) {
+            const int nb = min(kFastN, n - s0), nk0 = s_nkeep;
+            if (nk0 >= max_keep) break;
+            const int Wd = (nb + 31) >> 5;
+            for (int i = tid; i < nb; i += kNmsThreads) {
+                const float* c = cand + (size_t)pay[s0 + i] * 6;
+                const float off = p.agnostic ? 0.f : __fmul_rn(c[5], p.max_wh);
+                fbox[i] = make_float4(__fadd_rn(c[0], off), __fadd_rn(c[1], off), __fadd_rn(c[2], off), __fadd_rn(c[3], off));
             }
-            mat[t] = bits;
-        }
-        __syncthreads();
-        if (tid < 32) {
-            uint32_t removed = 0;                                           // lane l owns word l (Wd <= 32)
-            int nk = 0;
-            for (int i = 0; i < n && nk < max_keep; ++i) {
-                const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
-                if (!((r >> (i & 31)) & 1u)) {
-                    if (tid == 0) s_keep[nk] = i;
-                    ++nk;
-                    if (tid < Wd) removed |= mat[i * Wd + tid];
+            __syncthreads();
+            // (1) against the kept boxes of earlier blocks (warp-coalesced: lane <-> member, ballot -> one word per warp step)
+            for (int i0 = (tid >> 5) * 32; i0 < Wd * 32; i0 += kNmsThreads) {
+                const int i = i0 + (tid & 31);
+                bool sup = false;
+                if (i < nb && nk0 > 0) {
+                    const float4 bi = fbox[i];
+                    const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+                    for (int k = 0; k < nk0 && !sup; ++k) {
+                        const float4 bj = kbox[k];
+                        const float iw = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
+                        const float ih = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
+                        const float inter = __fmul_rn(iw, ih);
+                        const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+                        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_j, area_i), inter));
+                        sup = iou > p.iou_thres;
+                    }
                 }
+                const unsigned word = __ballot_sync(0xffffffffu, sup || i >= nb);
+                if ((tid & 31) == 0) dead[i0 >> 5] = word;
             }
-            if (tid == 0) s_nkeep = nk;
+            // (2) pairwise tests inside the block
+            for (int t = tid; t < nb * Wd; t += kNmsThreads) {
+                const int i = t / Wd, wj = t - i * Wd;
+                uint32_t bits = 0;
+                if (wj * 32 + 31 > i) {
+                    const float4 bi = fbox[i];
+                    const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+                    const int j0 = max(wj * 32, i + 1), j1 = min(wj * 32 + 32, nb);
+                    for (int j = j0; j < j1; ++j) {
+                        const float4 bj = fbox[j];
+                        const float iw = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
+                        const float ih = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
+                        const float inter = __fmul_rn(iw, ih);
+                        const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+                        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
+                        if (iou > p.iou_thres) bits |= 1u << (j & 31);
+                    }
+                }
+                mat[t] = bits;
+            }
+            __syncthreads();
+            // (3) greedy walk of the block by one warp
+            if (tid < 32) {
+                uint32_t removed = tid < Wd ? dead[tid] : 0xffffffffu;        // lane l owns word l (Wd <= 32)
+                int nk = nk0;
+                for (int i = 0; i < nb && nk < max_keep; ++i) {
+                    const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
+                    if (!((r >> (i & 31)) & 1u)) {
+                        if (tid == 0) { s_keep[nk] = s0 + i; kbox[nk] = fbox[i]; }
+                        ++nk;
+                        if (tid < Wd) removed |= mat[i * Wd + tid];
+                    }
+                }
+                if (tid == 0) s_nkeep = nk;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     } else {
     // sorted, class-offset boxes (nms.py:144,150: boxes = x[:, :4] + cls * max_wh, fp32) + alive bitmask
     float4* sbox = p.ws_box + (size_t)b * p.P_max;
@@ -540,7 +573,7 @@ extern "C" int b2_nms(const float* cand, const int32_t* cand_idx, const int32_t*
     p.ws_keys = (unsigned long long*)ws; ws += (size_t)B * P * 8;
     p.ws_pay = (int32_t*)ws;
     p.P_max = (int)P;
-    const size_t dyn = (size_t)kFastN * 16 + (size_t)kFastN * ((kFastN + 31) / 32) * 4;
+    const size_t dyn = (size_t)kFastN * 16 + (size_t)kFastN * ((kFastN + 31) / 32) * 4 + (size_t)kMaxKeep * 16;
     {
         static cudaError_t attr_err = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         B2_CUDA(attr_err);
