@@ -317,6 +317,7 @@ def run_b200(a):
         e0.record()
         for i in range(steps):
             step_fn(i)
+        pipe.join()                 # the last step's download (own stream) is inside the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")

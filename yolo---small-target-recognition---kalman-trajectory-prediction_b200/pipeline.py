@@ -49,6 +49,10 @@ class DetectTrackPipeline:
         self._ready = [torch.cuda.Event() for _ in range(2)]
         self._consumed = [torch.cuda.Event() for _ in range(2)]
         self._slot = 0
+        self._d2h_stream = torch.cuda.Stream()
+        self._step_done = torch.cuda.Event()
+        self._rows_downloaded = torch.cuda.Event()
+        self._rows_downloaded.record()
         self.host_rows = torch.empty((self.S, capacity, _lib.TRACK_COLS), dtype=torch.float32).pin_memory()
         self.host_counts = torch.empty((self.S,), dtype=torch.int32).pin_memory()
         self.h2d_bytes_per_step = self.S * self.h0 * self.w0 * 3
@@ -56,14 +60,18 @@ class DetectTrackPipeline:
 
     def step_device(self, frames_u8, with_trajectory=False, stream=None):
         """frames_u8: CUDA uint8 [S][h][w][3] BGR.  Returns (track rows [S][capacity][20], counts [S]) on the GPU."""
+        import torch
+
         dets, counts = self.detect(frames_u8, self.conf, self.iou, self.top, self.left, (self.h0, self.w0), None, False,
                                    self.nms_mode, stream)
+        # the bank's row block is about to be rewritten: a download of the previous step's rows (step_host) must be over
+        (stream or torch.cuda.current_stream()).wait_event(self._rows_downloaded)
         return self.bank.update(dets, counts, with_trajectory=with_trajectory, stream=stream)
 
     def step_host(self, frames_pinned):
         """frames_pinned: pinned host uint8 [S][h][w][3].  Upload on the copy stream (overlaps the previous step's
-        compute), run the step, download rows + counts into pinned host buffers.  Returns the host buffers
-        (valid after ``torch.cuda.current_stream().synchronize()``)."""
+        compute), run the step, download rows + counts into pinned host buffers on a third stream (overlaps the next
+        step).  Returns the host buffers (valid after ``join()`` + ``torch.cuda.current_stream().synchronize()``)."""
         import torch
 
         cur = torch.cuda.current_stream()
@@ -76,9 +84,21 @@ class DetectTrackPipeline:
         cur.wait_event(self._ready[k])
         rows, counts = self.step_device(self._dev_frames[k])
         self._consumed[k].record(cur)
-        self.host_rows.copy_(rows, non_blocking=True)
-        self.host_counts.copy_(counts, non_blocking=True)
+        # download on its own stream: it overlaps the next step's forward (which only waits for it before the tracker
+        # rewrites the rows, see step_device)
+        self._step_done.record(cur)
+        with torch.cuda.stream(self._d2h_stream):
+            self._d2h_stream.wait_event(self._step_done)
+            self.host_rows.copy_(rows, non_blocking=True)
+            self.host_counts.copy_(counts, non_blocking=True)
+            self._rows_downloaded.record(self._d2h_stream)
         return self.host_rows, self.host_counts
+
+    def join(self):
+        """Make the current stream wait for the last download of step_host (host buffers are valid after it synchronises)."""
+        import torch
+
+        torch.cuda.current_stream().wait_event(self._rows_downloaded)
 
 
 def gather_results(rows, counts, group=None):
