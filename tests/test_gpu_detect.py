@@ -39,7 +39,7 @@ def _diag(msg):
             fh.write(msg + "\n")
 
 
-@pytest.mark.parametrize("name,B,H,W", [("yolov8n-p2", 2, 64, 96), ("yolov8s-p2", 1, 96, 64)])
+@pytest.mark.parametrize("name,B,H,W", [("yolov8n-p2", 2, 64, 96), ("yolov8s-p2", 1, 96, 64), ("yolov8x-p2", 1, 64, 64), ("yolov8s-p2", 3, 128, 160)])
 def test_engine_every_layer_matches_oracle_on_identical_inputs(name, B, H, W):
     """Primary kernel gate: after one engine forward, EVERY launch of the plan is re-evaluated by
     the oracle on the engine's own input buffer (bf16 values, bf16 weights, fp32 accumulate) and must agree with
