@@ -45,6 +45,25 @@ __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* A, const __nv_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
     const uint32_t a_tm = tmem + 128;                    // ring of 8-column slots (N <= 128 in modes that use it)
+    if (mode == 5 && warp == 0) {
+        uint32_t is_leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        const uint64_t hi = (uint64_t)(((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29)) << 32;
+        const uint32_t a_lo = ((smem_u32(sA) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t b_lo = ((smem_u32(sB) >> 4) & 0x3FFFu) | (1u << 16);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t j = (uint32_t)(i & 3) * 2u, acc = i > 0;
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem), "l"(hi | (a_lo + j)), "l"(hi | (b_lo + j)), "r"(idesc), "r"(acc), "r"(is_leader) : "memory");
+        }
+        if (is_leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[0])) : "memory");
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar2[0])) : "memory");
+        if (lane == 0) cyc[blockIdx.x] = clock64() - t0;
+    } else
     if (threadIdx.x == 0 || (mode == 4 && threadIdx.x == 32)) {
         const uint32_t dcol = threadIdx.x ? 128u : 0u;     // mode 4: second issuer accumulates into columns 128..
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -122,16 +141,15 @@ int main() {
     const int iters = 2048;
     printf("mode N blocks cycles/iter\n");
     for (int blocks : {1, 148, 296})
-        for (int mode : {2, 4})
+        for (int mode : {2, 5})
             for (int N : {32, 64, 128}) {
-                if (mode == 4 && blocks == 296) continue;
                 probe<<<blocks, 128, 56 * 1024>>>(dA, dB, dD, N, mode, iters, dC);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("mode %d N %d: %s\n", mode, N, cudaGetErrorString(e)); return 1; }
                 cudaMemcpy(h, dC, blocks * 8, cudaMemcpyDeviceToHost);
                 double mx = 0;
                 for (int b = 0; b < blocks; ++b) mx = h[b] > mx ? (double)h[b] : mx;
-                printf("%s %3d %3d %8.1f\n", mode == 1 ? "cp+mmaTS" : mode == 2 ? "mmaSS   " : mode == 4 ? "2warpsSS" : "cp only ", N, blocks, mx / iters);
+                printf("%s %3d %3d %8.1f\n", mode == 1 ? "cp+mmaTS" : mode == 2 ? "mmaSS   " : mode == 4 ? "2warpsSS" : mode == 5 ? "uniformSS" : "cp only ", N, blocks, mx / iters);
             }
     return 0;
 }

@@ -96,6 +96,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Warp-collective wait: every lane polls and a vote makes the loop condition warp-uniform, so the compiler may keep the
+// caller's loop state in uniform registers across the wait (a per-lane spin loop is a divergent region: everything live
+// across it falls back to vector registers + R2UR, which made the MMA issue loops 2x slower than the tensor pipe).
+__device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (++spins > (1u << 22)) {
+            if ((threadIdx.x & 31) == 0) printf("b2dt: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // ---- TMA (tiled tensor maps) ------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
@@ -171,6 +184,21 @@ __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint4& a, const ui
                  ::"r"(addr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Same as tc_mma_bf16_if with the two descriptors given as 32-bit halves (packed inside the asm): the issue loop then
+// only does 32-bit uniform adds on the low words, the high words are loop constants.
+__device__ __forceinline__ void tc_mma_bf16_lohi_if(uint32_t issue, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                    uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+}
 __device__ __forceinline__ void tc_commit_if(uint32_t issue, uint64_t* bar) {
     asm volatile(
         "{\n\t"

@@ -345,9 +345,12 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
         // streams together reach the operand-fetch rate (max(N/2, 32 + N/4) cycles per MMA per SM: 48 at N = 64).  Layers whose
         // resident weights leave room for one CTA per SM therefore run two issuing warps: warp r takes tiles r, r+2, ...,
         // owns accumulator stage r and its own ring of pipeline stages.
-        const int mw = warp - 1;
+        // everything the issue loop computes with must be provably warp-uniform for the compiler (else it falls back to vector
+        // registers + R2UR per MMA): the warp index comes through a shuffle (MW == 2) or is a constant (MW == 1)
+        const int mw = MW == 1 ? 0 : (int)__reduce_max_sync(0xffffffffu, (unsigned)warp) - 1;      // REDUX: result lives in a uniform register
         {
         const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t tmem_base_u = __reduce_or_sync(0xffffffffu, tmem_base);
         // InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B, N>>3 at 17, M>>4 at 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
         // shared-memory matrix descriptors: lo word = (address >> 4) | LBO field, hi word per segment
@@ -370,11 +373,11 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
         const int stage_lo = mw * ring_stages, stage_hi = stage_lo + ring_stages;
         int stage = stage_lo; uint32_t phase = 0;
         int acc = mw; uint32_t acc_phase = 0;
-        if (b_res) { mbar_wait(&bres_bar, 0); tc_fence_after(); }
+        if (b_res) { mbar_wait_uniform(&bres_bar, 0); tc_fence_after(); }
         for (int tile = blockIdx.x + mw * gridDim.x; tile < total_tiles; tile += (two ? 2 : 1) * gridDim.x) {
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            mbar_wait_uniform(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t d_addr = tmem_base + (uint32_t)(acc * n_tile);
+            const uint32_t d_addr = tmem_base_u + (uint32_t)(acc * n_tile);
             uint32_t accum = 0;
             for (int g = 0; g < groups; ++g) {
 #pragma unroll
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
                     const uint64_t desc_hi = (uint64_t)sg_hi[s] << 32, desc_hi_w = (uint64_t)sg_hiw[s] << 32;
                     const uint32_t kh16 = sg_kh16[s], b_blk16 = sg_blk16[s], b_base16 = sg_base16[s];
                     for (int kc = 0; kc < kchunks; ++kc) {
-                        mbar_wait(&full_bar[stage], phase);
+                        mbar_wait_uniform(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage16;
                         if (halo == 3) {
