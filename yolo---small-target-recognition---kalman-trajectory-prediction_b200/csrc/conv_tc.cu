@@ -203,6 +203,41 @@ __device__ __forceinline__ float2 cls_unkey(int key) {
 
 // EPI: epilogue variant (ConvParams::epi), HALO: ConvParams::halo -- compile-time copies of the two fields, so that each
 // instance carries only its own loops (the kernel is sensitive to registers / code size in the issue and epilogue paths)
+// All 9 x MPS MMAs of one single-box (halo 2) stage, fully unrolled: every descriptor is one uniform add away from the
+// stage's pixel-box base (tap (kh, kw) starts (kh * 10 + kw) rows in, one row = 2 * MPS descriptor units) and from the
+// weight block of (tap 0, this K chunk) (taps are tb_step apart).
+template <int MPS>
+__device__ __forceinline__ void ss_issue_halo2(uint32_t leader, uint32_t d_addr, uint32_t idesc, uint64_t hi_a, uint64_t hi_b,
+                                               uint32_t a_lo, uint32_t tb_lo, uint32_t tb_step, uint32_t& accum) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const uint32_t ta = a_lo + (uint32_t)(((t / 3) * 10 + (t % 3)) * 2 * MPS);
+        const uint32_t tb = tb_lo + (uint32_t)t * tb_step;
+#pragma unroll
+        for (int j = 0; j < MPS; ++j) {
+            tc_mma_bf16_if(leader, d_addr, hi_a | (uint64_t)(ta + 2u * j), hi_b | (uint64_t)(tb + 2u * j), idesc, accum);
+            accum = 1;
+        }
+    }
+}
+
+// TPG taps x MPS K-steps of one stage of the tap / three-box modes, unrolled: tap t reads the stage's A tile t * a_step further
+// in (halo 1: 8 rows = 16 * MPS units; tap mode: TPG == 1) and weight block t * b_step further (resident: tap stride in blocks;
+// streamed: the stage's t-th block).
+template <int MPS, int TPG>
+__device__ __forceinline__ void ss_issue_taps(uint32_t leader, uint32_t d_addr, uint32_t idesc, uint64_t hi, uint32_t a_lo, uint32_t tb_lo,
+                                              uint32_t b_step, uint32_t& accum) {
+#pragma unroll
+    for (int t = 0; t < TPG; ++t) {
+        const uint32_t ta = a_lo + (uint32_t)(t * 16 * MPS), tb = tb_lo + (uint32_t)t * b_step;
+#pragma unroll
+        for (int j = 0; j < MPS; ++j) {
+            tc_mma_bf16_if(leader, d_addr, hi | (uint64_t)(ta + 2u * j), hi | (uint64_t)(tb + 2u * j), idesc, accum);
+            accum = 1;
+        }
+    }
+}
+
 // MW: MMA-issuing warps.  1: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, up to two CTAs per SM.  2 (plans with ONE CTA per SM):
 // warps 1 and 2 issue alternate tiles, each with its own accumulator stage and its own ring of pipeline stages.
 template <int EPI, int HALO, int MW>
@@ -408,32 +443,26 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
                                 }
                             }
                         } else if (halo == 2) {
-                            // one box, nine taps: tap (kh, kw) is the same tile kh * (TW+2) + kw rows further in (kh16 = one row);
-                            // weights are resident: block (tap, kc)
-                            uint32_t tb_lo = b_lo0 + b_base16 + (uint32_t)kc * b_blk16;
-                            const uint32_t tb_step = (uint32_t)kchunks * b_blk16;
-                            uint32_t ta_row = a_lo;
-                            for (int kh = 0; kh < 3; ++kh, ta_row += 10u * kh16) {
-                                uint32_t ta_lo = ta_row;
-                                for (int kw = 0; kw < 3; ++kw, ta_lo += kh16, tb_lo += tb_step) {
-                                    for (int j = 0; j < mma_per_step; ++j) {
-                                        tc_mma_bf16_if(leader, d_addr, desc_hi | (ta_lo + 2u * j), desc_hi_w | (tb_lo + 2u * j), idesc, accum);
-                                        accum = 1;
-                                    }
-                                }
-                            }
+                            // one box, nine taps, resident weights: block (tap, kc)
+                            const uint32_t tb_lo = b_lo0 + b_base16 + (uint32_t)kc * b_blk16, tb_step = (uint32_t)kchunks * b_blk16;
+                            if (mma_per_step == 4) ss_issue_halo2<4>(leader, d_addr, idesc, desc_hi, desc_hi_w, a_lo, tb_lo, tb_step, accum);
+                            else if (mma_per_step == 2) ss_issue_halo2<2>(leader, d_addr, idesc, desc_hi, desc_hi_w, a_lo, tb_lo, tb_step, accum);
+                            else ss_issue_halo2<1>(leader, d_addr, idesc, desc_hi, desc_hi_w, a_lo, tb_lo, tb_step, accum);
                         } else {
-                        for (int t = 0; t < taps_per_group; ++t) {
-                            const int tap = halo ? t * 3 + g : g;
-                            const uint32_t tb_lo = b_res ? b_lo0 + b_base16 + (uint32_t)(tap * kchunks + kc) * b_blk16
-                                                         : b_lo0 + (uint32_t)stage * b_stage16 + (uint32_t)t * b_blk16;
-                            const uint32_t ta_lo = a_lo + (uint32_t)t * kh16;
-                            for (int j = 0; j < mma_per_step; ++j) {
-                                // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                                tc_mma_bf16_if(leader, d_addr, desc_hi | (ta_lo + 2u * j), desc_hi | (tb_lo + 2u * j), idesc, accum);
-                                accum = 1;
+                            // tap mode (one tap per stage, tap g) / halo 1 (taps g, 3 + g, 6 + g of the stage's 18-row box); weights
+                            // resident: block (tap, kc); streamed: the stage's own blocks.  K steps advance 32 bytes inside the
+                            // swizzle atom: +2 in the >>4 address field.
+                            const uint32_t tb_lo = b_res ? b_lo0 + b_base16 + (uint32_t)(g * kchunks + kc) * b_blk16 : b_lo0 + (uint32_t)stage * b_stage16;
+                            const uint32_t b_step = b_res ? 3u * (uint32_t)kchunks * b_blk16 : b_blk16;
+                            if (halo == 1) {
+                                if (mma_per_step == 4) ss_issue_taps<4, 3>(leader, d_addr, idesc, desc_hi, a_lo, tb_lo, b_step, accum);
+                                else if (mma_per_step == 2) ss_issue_taps<2, 3>(leader, d_addr, idesc, desc_hi, a_lo, tb_lo, b_step, accum);
+                                else ss_issue_taps<1, 3>(leader, d_addr, idesc, desc_hi, a_lo, tb_lo, b_step, accum);
+                            } else {
+                                if (mma_per_step == 4) ss_issue_taps<4, 1>(leader, d_addr, idesc, desc_hi, a_lo, tb_lo, b_step, accum);
+                                else if (mma_per_step == 2) ss_issue_taps<2, 1>(leader, d_addr, idesc, desc_hi, a_lo, tb_lo, b_step, accum);
+                                else ss_issue_taps<1, 1>(leader, d_addr, idesc, desc_hi, a_lo, tb_lo, b_step, accum);
                             }
-                        }
                         }
                         tc_commit_if(leader, &empty_bar[stage]);     // frees the smem slot when these MMAs retire
                         if (++stage == stage_hi) { stage = stage_lo; phase ^= 1; }
