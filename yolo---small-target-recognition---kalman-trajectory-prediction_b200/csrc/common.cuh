@@ -48,7 +48,16 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // SiLU(x) = x / (1 + 2^(-x log2 e)): two MUFU ops and three FP32 ops, flush-to-zero (no denormal fix-up code)
-__device__ __forceinline__ float silu_fast(float x) { return x * rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+__device__ __forceinline__ float silu_ex2(float x) { return x * rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+// SiLU(x) = h + h tanh(h), h = x / 2: ONE MUFU op (tanh.approx.f32, max relative error 2^-11 on the tanh) and two FP32 ops.
+// Absolute error <= |h| * 2^-11 (reached on the negative lobe, |SiLU| <= 0.28 there): below the bf16 rounding of the stored
+// activation for every x > -1.5 and <= 1.2e-3 absolute beyond; the epilogues were MUFU / issue bound with the two-MUFU form.
+__device__ __forceinline__ float silu_fast(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
