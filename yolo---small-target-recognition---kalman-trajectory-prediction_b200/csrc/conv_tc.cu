@@ -507,6 +507,10 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
             }
 
+            // Bottleneck shortcut: pull this thread's residual chunks towards L2 while the tile's MMAs still run (no registers held)
+            if (rptr && valid)
+                for (int j = half; j < nchunks; j += kSub) asm volatile("prefetch.global.L2 [%0];" ::"l"(rptr + j * 16));
+
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_tile);
