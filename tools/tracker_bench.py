@@ -55,6 +55,23 @@ def main():
         bank.update(d2, c2, with_trajectory=False)
     out["pipe_sparse_update_ms"] = time_cuda(lambda: bank.update(d2, c2, with_trajectory=False))
     bank.close()
+    # dense scene (what a random-weight detector emits): 300 large overlapping boxes per frame, ~25 k pairs with IoU >= 0.1
+    bank = TrackerBank(S, C, D, 150, 1, 0.1)
+    def dense():
+        cx = torch.rand((S, D), device="cuda", generator=g) * 640.0
+        cy = torch.rand((S, D), device="cuda", generator=g) * 512.0
+        w = 30.0 + torch.rand((S, D), device="cuda", generator=g) * 60.0
+        h = 30.0 + torch.rand((S, D), device="cuda", generator=g) * 80.0
+        d = torch.zeros((S, D, 6), device="cuda")
+        d[..., 0], d[..., 1], d[..., 2], d[..., 3], d[..., 4] = cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2, 0.9
+        return d
+    base = dense()
+    for _ in range(3):
+        bank.update((base + torch.randn((S, D, 1), device="cuda", generator=g) * 2.0).contiguous(), c2, with_trajectory=False)
+    frames = [(base + torch.randn((S, D, 1), device="cuda", generator=g) * 2.0).contiguous() for _ in range(10)]
+    it = iter(frames)
+    out["pipe_dense_update_ms"] = time_cuda(lambda: bank.update(next(it), c2, with_trajectory=False))
+    bank.close()
     print(out)
 
 
