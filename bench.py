@@ -291,6 +291,11 @@ def run_b200(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL prints its version banner on the first
+    # communicator) are diverted to stderr until the line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -402,7 +407,10 @@ def run_b200(a):
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": n * k / dt, "unit": UNIT, "cores": cpu.cores, "kind": "port",
                                 "sample": f"{n} streams x {k} frames of the same workload (oracle port: numpy + ATen conv fp32, exact NMS, float64 tracker)"}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
