@@ -172,44 +172,63 @@ struct HeadParams {
     float* cand; int32_t* cand_idx; int32_t* cand_count; int cand_cap;
 };
 
+// kHcPer anchors per thread, a block apart (coalesced), all class records loaded before any is used: the kernel moves 8 bytes per
+// anchor and is latency bound otherwise.
+constexpr int kHcPer = 4;
+
 __global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, lane = threadIdx.x & 31;
-    bool is_cand = false;
-    float cx = 0.f, cy = 0.f, bw = 0.f, bh = 0.f, score = 0.f; int bidx = 0;
-    if (a < p.A) {
-        int lvl = 0;
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int a0 = blockIdx.x * (256 * kHcPer) + threadIdx.x;
+    float2 c[kHcPer];
+    size_t pix[kHcPer]; int la[kHcPer], lv[kHcPer];
 #pragma unroll
-        for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && a >= p.a_off[l]) lvl = l;
-        int W = p.w[0], H = p.h[0], st_i = p.stride[0], off = 0;
-        const float* dp = p.dist[0]; const float* cp = p.cls[0];
+    for (int k = 0; k < kHcPer; ++k) {
+        const int a = a0 + k * 256;
+        c[k] = make_float2(-INFINITY, 0.f); pix[k] = 0; la[k] = 0; lv[k] = 0;
+        if (a < p.A) {
+            int lvl = 0;
 #pragma unroll
-        for (int l = 1; l < kMaxLevels; ++l) if (l == lvl) { W = p.w[l]; H = p.h[l]; st_i = p.stride[l]; off = p.a_off[l]; dp = p.dist[l]; cp = p.cls[l]; }
-        const int la = a - off;
-        const size_t pix = (size_t)b * H * W + la;
-        const float2 c = __ldg(reinterpret_cast<const float2*>(cp) + pix);
-        bidx = (int)c.y;
-        score = 1.f / (1.f + __expf(-c.x));
-        if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
-            const float4 d = __ldg(reinterpret_cast<const float4*>(dp) + pix);
-            const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f, st = (float)st_i;
+            for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && a >= p.a_off[l]) lvl = l;
+            int W = p.w[0], H = p.h[0], off = 0;
+            const float* cp = p.cls[0];
+#pragma unroll
+            for (int l = 1; l < kMaxLevels; ++l) if (l == lvl) { W = p.w[l]; H = p.h[l]; off = p.a_off[l]; cp = p.cls[l]; }
+            la[k] = a - off; lv[k] = lvl;
+            pix[k] = (size_t)b * H * W + la[k];
+            c[k] = __ldg(reinterpret_cast<const float2*>(cp) + pix[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kHcPer; ++k) {
+        const int a = a0 + k * 256;
+        bool is_cand = false;
+        float cx = 0.f, cy = 0.f, bw = 0.f, bh = 0.f; int bidx = (int)c[k].y;
+        const float score = 1.f / (1.f + __expf(-c[k].x));
+        if (a < p.A && score > p.conf && (!p.cmask || p.cmask[bidx])) {
+            int W = p.w[0], st_i = p.stride[0];
+            const float* dp = p.dist[0];
+#pragma unroll
+            for (int l = 1; l < kMaxLevels; ++l) if (l == lv[k]) { W = p.w[l]; st_i = p.stride[l]; dp = p.dist[l]; }
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dp) + pix[k]);
+            const float ax = (float)(la[k] % W) + 0.5f, ay = (float)(la[k] / W) + 0.5f, st = (float)st_i;
             const float x1 = ax - d.x, y1 = ay - d.y, x2 = ax + d.z, y2 = ay + d.w;
             cx = (x1 + x2) / 2.f * st; cy = (y1 + y2) / 2.f * st; bw = (x2 - x1) * st; bh = (y2 - y1) * st;
             is_cand = true;
         }
-    }
-    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
-    if (!ball) return;
-    int base = 0;
-    const int leader = __ffs(ball) - 1;
-    if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (is_cand) {
-        const int pos = base + __popc(ball & ((1u << lane) - 1));
-        if (pos < p.cand_cap) {
-            float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
-            const float hw = bw / 2.f, hh = bh / 2.f;
-            o[0] = cx - hw; o[1] = cy - hh; o[2] = cx + hw; o[3] = cy + hh; o[4] = score; o[5] = (float)bidx;
-            p.cand_idx[(size_t)b * p.cand_cap + pos] = a;
+        const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+        if (!ball) continue;
+        int base = 0;
+        const int leader = __ffs(ball) - 1;
+        if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (is_cand) {
+            const int pos = base + __popc(ball & ((1u << lane) - 1));
+            if (pos < p.cand_cap) {
+                float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
+                const float hw = bw / 2.f, hh = bh / 2.f;
+                o[0] = cx - hw; o[1] = cy - hh; o[2] = cx + hw; o[3] = cy + hh; o[4] = score; o[5] = (float)bidx;
+                p.cand_idx[(size_t)b * p.cand_cap + pos] = a;
+            }
         }
     }
 }
@@ -529,7 +548,7 @@ extern "C" int b2_candidates_from_head(const float* const* level_dist, const flo
     p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count; p.cand_cap = cand_cap;
     cudaStream_t st = (cudaStream_t)stream;
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
-    head_candidates_kernel<<<dim3(b2_ceil_div(p.A, 256), B), 256, 0, st>>>(p);
+    head_candidates_kernel<<<dim3(b2_ceil_div(p.A, 256 * kHcPer), B), 256, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
