@@ -46,6 +46,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// exp(f - m), f <= m, for the DFL softmax: one FFMA + one MUFU (ml = m * log2 e).  decode_kernel and the fused Detect
+// epilogue of conv_tc_kernel both use it, so the two paths give the same bits.
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float dfl_exp(float f, float ml) { return ex2_ftz(fmaf(f, kLog2e, -ml)); }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // SiLU(x) = x / (1 + 2^(-x log2 e)): two MUFU ops and three FP32 ops, flush-to-zero (no denormal fix-up code)
 __device__ __forceinline__ float silu_ex2(float x) { return x * rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }

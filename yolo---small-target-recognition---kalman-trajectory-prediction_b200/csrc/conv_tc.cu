@@ -171,29 +171,50 @@ __device__ __forceinline__ float bf16_rt(float x) { return __bfloat162float(__fl
 __device__ __forceinline__ float dfl_side(const uint32_t (&v)[16], const float* __restrict__ sb) {
     float f[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = bf16_rt(__uint_as_float(v[i]) + sb[i]);
+    for (int q = 0; q < 4; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * q);
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[4 * q]) + b4.x, __uint_as_float(v[4 * q + 1]) + b4.y);
+        const __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[4 * q + 2]) + b4.z, __uint_as_float(v[4 * q + 3]) + b4.w);
+        const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&p0), u1 = *reinterpret_cast<const uint32_t*>(&p1);
+        f[4 * q] = __uint_as_float(u0 << 16); f[4 * q + 1] = __uint_as_float(u0 & 0xFFFF0000u);
+        f[4 * q + 2] = __uint_as_float(u1 << 16); f[4 * q + 3] = __uint_as_float(u1 & 0xFFFF0000u);
+    }
     float m = f[0];
 #pragma unroll
     for (int i = 1; i < 16; ++i) m = fmaxf(m, f[i]);
+    const float ml = m * kLog2e;
     float se0 = 0.f, sw0 = 0.f, se1 = 0.f, sw1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float e = __expf(f[i] - m); se0 += e; sw0 = fmaf(e, (float)i, sw0); }
+    for (int i = 0; i < 8; ++i) { const float e = dfl_exp(f[i], ml); se0 += e; sw0 = fmaf(e, (float)i, sw0); }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float e = __expf(f[8 + i] - m); se1 += e; sw1 = fmaf(e, 8.f + (float)i, sw1); }
+    for (int i = 0; i < 8; ++i) { const float e = dfl_exp(f[8 + i], ml); se1 += e; sw1 = fmaf(e, 8.f + (float)i, sw1); }
     return (sw0 + sw1) / (se0 + se1);
 }
 // Class head: running argmax as ONE integer max per element.  The logit is rounded to bf16 first (as the unfused path
 // stores it), so the low 16 bits of its fp32 pattern are free: key = order-preserving integer image of the value in
 // the high half, 0xFFFF - class in the low half (ties -> lowest class, as torch.max / decode_kernel).
-__device__ __forceinline__ int cls_key(float x, int cls) {
-    const int b = __float_as_int(bf16_rt(x));
-    const int k = b ^ ((b >> 31) & 0x7FFFFFFF);                       // signed-int order == float order
-    return (k & (int)0xFFFF0000) | (0xFFFF - cls);
+// Two logits per conversion (one packed cvt.rn.bf16x2), no per-element predicate: channels past Cout carry a bias of
+// -inf (set where s_bias is filled), so they never win.
+__device__ __forceinline__ int cls_key_bits(int t, int low) {            // t: bf16 pattern in the high half, low half anything
+    const int k = t ^ ((t >> 31) & 0x7FFF0000);                          // signed-int order == float order (high half)
+    return (k & (int)0xFFFF0000) | low;
 }
-__device__ __forceinline__ void cls_chunk(const uint32_t (&v)[16], const float* __restrict__ sb, int c0, int nv, int (&best)[4]) {
+// chunk = 16 classes starting at c0 (a multiple of 16): inside the chunk the low bits are the immediates 15 - i, the
+// chunk's own 12 bits are OR-ed in once after the 16-way max.
+__device__ __forceinline__ void cls_chunk(const uint32_t (&v)[16], const float* __restrict__ sb, int c0, int& best) {
+    int m[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if (i < nv) best[i & 3] = max(best[i & 3], cls_key(__uint_as_float(v[i]) + sb[i], c0 + i));
+    for (int q = 0; q < 4; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * q);
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[4 * q]) + b4.x, __uint_as_float(v[4 * q + 1]) + b4.y);
+        const __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[4 * q + 2]) + b4.z, __uint_as_float(v[4 * q + 3]) + b4.w);
+        const int u0 = *reinterpret_cast<const int*>(&p0), u1 = *reinterpret_cast<const int*>(&p1);
+        const int k0 = cls_key_bits(u0 << 16, 15 - 4 * q), k1 = cls_key_bits(u0, 14 - 4 * q);
+        const int k2 = cls_key_bits(u1 << 16, 13 - 4 * q), k3 = cls_key_bits(u1, 12 - 4 * q);
+        m[q] = max(max(k0, k1), max(k2, k3));
+    }
+    const int m16 = max(max(m[0], m[1]), max(m[2], m[3])) | (0xFFF0 - c0);
+    best = max(best, m16);
 }
 __device__ __forceinline__ float2 cls_unkey(int key) {
     const int kb = key & (int)0xFFFF0000;
@@ -276,7 +297,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
         tmem_relinquish();
     }
     if (p.n_tiles == 1)
-        for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
+        for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = i < p.Cout ? __ldg(p.bias + i) : (EPI == 2 ? -INFINITY : 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -503,7 +524,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
             if (n_tiles > 1) {
                 // per-tile bias slice (named barrier over the epilogue warps only)
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
-                for (int i = threadIdx.x - 32 * (1 + kMmaWarps); i < n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < Cout ? __ldg(p.bias + n_base + i) : 0.f;
+                for (int i = threadIdx.x - 32 * (1 + kMmaWarps); i < n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < Cout ? __ldg(p.bias + n_base + i) : (EPI == 2 ? -INFINITY : 0.f);
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
             }
 
@@ -547,17 +568,17 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
             } else {
                 // class head: the two warps of a lane quadrant take alternate pairs of 16-class chunks, then combine
                 // through shared memory (double buffered by tile parity: one named barrier per tile and quadrant)
-                int best[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+                int best = INT_MIN;
                 for (int j = 2 * half; j < nchunks; j += 4) {
                     const bool two = j + 1 < nchunks;
                     uint32_t v0[16], v1[16];
                     tmem_ld16(t_addr + j * 16, v0);
                     if (two) tmem_ld16(t_addr + (j + 1) * 16, v1);
                     tmem_ld_wait();
-                    cls_chunk(v0, s_bias + j * 16, j * 16, min(16, ncols - j * 16), best);
-                    if (two) cls_chunk(v1, s_bias + (j + 1) * 16, (j + 1) * 16, min(16, ncols - (j + 1) * 16), best);
+                    cls_chunk(v0, s_bias + j * 16, j * 16, best);
+                    if (two) cls_chunk(v1, s_bias + (j + 1) * 16, (j + 1) * 16, best);
                 }
-                const int key = max(max(best[0], best[1]), max(best[2], best[3]));
+                const int key = best;
                 int* const slot = &s_key[acc][row];
                 if (half) *slot = key;
                 asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");

@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
     float se = 0.f, sw = 0.f;
-    const float bin0 = (float)((sub & 1) * 8);
+    const float bin0 = (float)((sub & 1) * 8), ml = m * kLog2e;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float e = __expf(f[i] - m);
+        const float e = dfl_exp(f[i], ml);
         se += e; sw = fmaf(e, bin0 + (float)i, sw);
     }
     se += __shfl_xor_sync(0xffffffffu, se, 1);
