@@ -1,0 +1,95 @@
+"""The multi-stream detect+track step (pipeline.DetectTrackPipeline) through its three entry points: device frames on one
+stream, device frames with NMS + tracker overlapped under the next forward, and pinned host frames with uploads / downloads on
+their own streams.  All three must produce the same track rows, bit for bit, step after step, and the single-stream result
+must equal YOLO.predict + EnhancedMultiTargetTracker.update called frame by frame (the reference driver's loop,
+kalman/aircraft_detection_tracking.py:88-109)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+H, W = 96, 128
+KW = dict(max_lost_frames=150, min_hits=1, iou_threshold=0.1)
+
+
+def _frames(S, T):
+    from b200dt import synth
+
+    vids = [synth.IRStream(seed=40 + s, h=H, w=W, n_targets=4) for s in range(S)]
+    return [np.stack([v.frame() for v in vids]) for _ in range(T)]
+
+
+def _pipe(S, **kw):
+    from b200dt.pipeline import DetectTrackPipeline
+
+    return DetectTrackPipeline("yolov8n-p2", S, (H, W), 128, 0.15, 0.6, 300, capacity=1024, **KW, **kw)
+
+
+def _snap(rows, counts):
+    c = counts.cpu().numpy().copy()
+    r = rows.cpu().numpy().copy()
+    return [r[s, :c[s]].view(np.int32).copy() for s in range(len(c))]
+
+
+def _sorted(block):
+    return block[np.argsort(block[:, 0], kind="stable")]
+
+
+def test_overlapped_and_host_steps_match_single_stream_step():
+    S, T = 3, 6
+    frames = _frames(S, T)
+    plain, over, host = _pipe(S), _pipe(S, overlap_post=True), _pipe(S, overlap_post=True)
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    dev = [torch.from_numpy(f).cuda() for f in frames]
+    ref = []
+    for t in range(T):
+        ref.append(_snap(*plain.step_device(dev[t])))
+    torch.cuda.synchronize()
+    # overlapped: results of step t are read after join(); the next step is already queued behind it on purpose
+    for t in range(T):
+        rows, counts = over.step_device(dev[t])
+        over.join()
+        got = _snap(rows, counts)
+        for s in range(S):
+            np.testing.assert_array_equal(_sorted(got[s]), _sorted(ref[t][s]))
+    # back-to-back overlapped steps with no join in between: only the final state is compared
+    over2 = _pipe(S, overlap_post=True)
+    for t in range(T):
+        rows, counts = over2.step_device(dev[t])
+    over2.join()
+    torch.cuda.synchronize()
+    got = _snap(rows, counts)
+    for s in range(S):
+        np.testing.assert_array_equal(_sorted(got[s]), _sorted(ref[-1][s]))
+    # host entry point (uploads and downloads on their own streams)
+    for t in range(T):
+        hr, hc = host.step_host(pinned[t])
+    host.join()
+    torch.cuda.synchronize()
+    c = hc.numpy()
+    for s in range(S):
+        np.testing.assert_array_equal(_sorted(hr.numpy()[s, :c[s]].view(np.int32)), _sorted(ref[-1][s]))
+
+
+def test_pipeline_step_equals_predict_plus_tracker_update_per_frame():
+    from b200dt.predictor import YOLO
+    from b200dt.tracker import EnhancedMultiTargetTracker, rows_to_dicts
+
+    S, T = 2, 4
+    frames = _frames(S, T)
+    pipe = _pipe(S)
+    model = YOLO("yolov8n-p2.yaml")
+    trks = [EnhancedMultiTargetTracker(150, 1, 0.1, capacity=1024, max_dets=300) for _ in range(S)]
+    for t in range(T):
+        rows, counts = pipe.step_device(torch.from_numpy(frames[t]).cuda())
+        c = counts.cpu().numpy()
+        for s in range(S):
+            res = model.predict(frames[t][s], conf=0.15, iou=0.6, imgsz=128)[0]
+            d = res.boxes.data.cpu().numpy()
+            want = trks[s].update([[*r[:4], r[4]] for r in d])
+            got = rows_to_dicts(rows[s, :c[s]].cpu().numpy())
+            assert [g["track_id"] for g in got] == [w["track_id"] for w in want]
+            for g, w in zip(got, want):
+                np.testing.assert_allclose(g["bbox"], w["bbox"], rtol=1e-5, atol=1e-3)

@@ -27,7 +27,10 @@ def shard_streams(n_streams, rank, world_size):
 class DetectTrackPipeline:
     def __init__(self, model="yolov8s-p2", n_streams=1, frame_hw=(512, 640), imgsz=640, conf=0.15, iou=0.6, max_det=300,
                  max_lost_frames=150, min_hits=1, iou_threshold=0.1, capacity=512, state_dict=None, seed=0, nc=None,
-                 nms_mode="exact"):
+                 nms_mode="exact", overlap_post=False):
+        """overlap_post: run NMS + tracker of step t on a second CUDA stream while the forward of step t+1 runs on the
+        caller's stream (the small latency-bound launches fill the tails of the conv kernels).  The returned device
+        tensors are then valid only after ``join()``."""
         import torch
 
         self.device = _lib.require_cuda()
@@ -50,6 +53,11 @@ class DetectTrackPipeline:
         self._consumed = [torch.cuda.Event() for _ in range(2)]
         self._slot = 0
         self._d2h_stream = torch.cuda.Stream()
+        self.overlap_post = bool(overlap_post)
+        self._post_stream = torch.cuda.Stream()
+        self._cand_done = torch.cuda.Event()
+        self._post_done = torch.cuda.Event()
+        self._post_done.record()
         self._step_done = torch.cuda.Event()
         self._rows_downloaded = torch.cuda.Event()
         self._rows_downloaded.record()
@@ -62,11 +70,24 @@ class DetectTrackPipeline:
         """frames_u8: CUDA uint8 [S][h][w][3] BGR.  Returns (track rows [S][capacity][20], counts [S]) on the GPU."""
         import torch
 
-        dets, counts = self.detect(frames_u8, self.conf, self.iou, self.top, self.left, (self.h0, self.w0), None, False,
-                                   self.nms_mode, stream)
-        # the bank's row block is about to be rewritten: a download of the previous step's rows (step_host) must be over
-        (stream or torch.cuda.current_stream()).wait_event(self._rows_downloaded)
-        return self.bank.update(dets, counts, with_trajectory=with_trajectory, stream=stream)
+        cur = stream or torch.cuda.current_stream()
+        if not self.overlap_post:
+            dets, counts = self.detect(frames_u8, self.conf, self.iou, self.top, self.left, (self.h0, self.w0), None, False,
+                                       self.nms_mode, stream)
+            # the bank's row block is about to be rewritten: a download of the previous step's rows (step_host) must be over
+            cur.wait_event(self._rows_downloaded)
+            return self.bank.update(dets, counts, with_trajectory=with_trajectory, stream=stream)
+        d, ps = self.detect, self._post_stream
+        d.engine.forward_u8(frames_u8, self.top, self.left, stream=stream)
+        cur.wait_event(self._post_done)               # NMS of the previous step has read the candidate lists
+        d.candidates(self.conf, None, stream)
+        self._cand_done.record(cur)
+        ps.wait_event(self._cand_done)
+        ps.wait_event(self._rows_downloaded)
+        dets, counts = d.nms(self.iou, (self.h0, self.w0), False, self.nms_mode, ps)
+        out = self.bank.update(dets, counts, with_trajectory=with_trajectory, stream=ps)
+        self._post_done.record(ps)
+        return out
 
     def step_host(self, frames_pinned):
         """frames_pinned: pinned host uint8 [S][h][w][3].  Upload on the copy stream (overlaps the previous step's
@@ -86,19 +107,23 @@ class DetectTrackPipeline:
         self._consumed[k].record(cur)
         # download on its own stream: it overlaps the next step's forward (which only waits for it before the tracker
         # rewrites the rows, see step_device)
-        self._step_done.record(cur)
+        done = self._post_done if self.overlap_post else self._step_done
+        if not self.overlap_post:
+            self._step_done.record(cur)
         with torch.cuda.stream(self._d2h_stream):
-            self._d2h_stream.wait_event(self._step_done)
+            self._d2h_stream.wait_event(done)
             self.host_rows.copy_(rows, non_blocking=True)
             self.host_counts.copy_(counts, non_blocking=True)
             self._rows_downloaded.record(self._d2h_stream)
         return self.host_rows, self.host_counts
 
     def join(self):
-        """Make the current stream wait for the last download of step_host (host buffers are valid after it synchronises)."""
+        """Make the current stream wait for the last download of step_host and, with overlap_post, for the last step's NMS +
+        tracker (host buffers / returned device tensors are valid after it synchronises)."""
         import torch
 
         torch.cuda.current_stream().wait_event(self._rows_downloaded)
+        torch.cuda.current_stream().wait_event(self._post_done)
 
 
 def gather_results(rows, counts, group=None):

@@ -203,10 +203,17 @@ class DetectPipeline:
         return self.finish(conf, iou, orig_hw, classes_mask, agnostic, mode, stream)
 
     def finish(self, conf, iou, orig_hw, classes_mask, agnostic, mode, stream):
+        self.candidates(conf, classes_mask, stream)
+        return self.nms(iou, orig_hw, agnostic, mode, stream)
+
+    def candidates(self, conf, classes_mask=None, stream=None):
+        """Head outputs -> per-image candidate lists (the only post-processing launch that reads engine buffers)."""
         if self.engine.fused_head:
             self.post.candidates_from_head(self.engine.head_dist, self.engine.head_cls, conf, classes_mask, stream=stream)
         else:
             self.post.decode(self.engine.level_ptrs, conf, classes_mask, stream=stream)
+
+    def nms(self, iou, orig_hw=None, agnostic=False, mode="exact", stream=None):
         scale = scale_params((self.H, self.W), orig_hw) if orig_hw is not None else None
         return self.post.nms(iou, agnostic=agnostic, mode=mode, scale=scale, stream=stream)
 
