@@ -46,6 +46,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (prologue: barrier init, TMEM allocation, weight preload) while its predecessor in the stream still runs its last tiles;
+// pdl_wait() returns once the predecessor grid has completed and its writes are visible, pdl_launch_dependents() lets the
+// successor's CTAs be scheduled as soon as SM resources free up.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // exp(f - m), f <= m, for the DFL softmax: one FFMA + one MUFU (ml = m * log2 e).  decode_kernel and the fused Detect
 // epilogue of conv_tc_kernel both use it, so the two paths give the same bits.
 constexpr float kLog2e = 1.4426950408889634f;

@@ -27,6 +27,7 @@
 
 #include <limits.h>
 
+#include <algorithm>
 #include <mutex>
 
 namespace {
@@ -34,6 +35,7 @@ namespace {
 constexpr int kMaxStages = 12;
 constexpr int kThreadsMw1 = 32 * (1 + 1 + 8), kThreadsMw2 = 32 * (1 + 2 + 8);   // warp 0 TMA, 1 or 2 MMA warps, 8 epilogue warps
 constexpr int kMaxNTile = 256;
+constexpr int kMaxAcc = 4;                         // accumulator stages in tensor memory
 constexpr int kMaxSeg = 4;                         // up to two sources (Concat folded into the conv) x two chunk widths
 
 // transposed (TS) kernel: TMEM columns of one accumulator stage / of the weight region, K-elements the weight region holds
@@ -96,8 +98,13 @@ struct alignas(64) ConvParams {
     uint32_t chunk_magic;     // ceil(2^32 / (cout16 / 16)): item -> pixel by a multiply-high
     int ts_steps;             // pipeline stages one tile consumes
     int mma_warps;            // conv_tc_kernel: 1 or 2 MMA-issuing warps (2: alternate tiles, two stage rings)
+    int acc_stages;           // conv_tc_kernel: accumulator stages in tensor memory (2..4): tile t uses stage t % acc_stages
+    uint32_t magic_nt, magic_tw, magic_th;   // ceil(2^32 / d) for d = n_tiles, tiles_w, tiles_h (0: d == 1) -- tile index -> coordinates
     int dbg_skip_mma;         // B2_CONV_DEBUG=1: issue no MMAs (timing of the TMA / epilogue paths alone; results are garbage)
 };
+
+// x / d by one multiply-high (magic = ceil(2^32 / d), exact while x * d < 2^32 -- checked on the host); magic 0 means d == 1
+__device__ __forceinline__ int fast_div(int x, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)x, magic) : x; }
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -119,17 +126,26 @@ __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&o)[8]) {
 template <bool WIDE, bool BIAS = true>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], const float* __restrict__ sb, int act, int nv,
                                                __nv_bfloat16* __restrict__ optr, const __nv_bfloat16* __restrict__ rptr) {
+    // act: sb holds HALF the bias, h = (acc + bias) / 2 comes out of one FFMA (bit-identical to 0.5f * (acc + bias): scaling by
+    // a power of two commutes with rounding) and SiLU(x) = h + h tanh(h) (silu_fast) is one MUFU + one FFMA more
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (BIAS) b4 = *reinterpret_cast<const float4*>(sb + i);
-        f[i] = __uint_as_float(v[i]) + b4.x; f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-        f[i + 2] = __uint_as_float(v[i + 2]) + b4.z; f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
-    }
-    if (act) {
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = silu_fast(f[i]);
+        for (int k = 0; k < 4; ++k) {
+            const float a = __uint_as_float(v[i + k]);
+            if (act) {
+                const float h = fmaf(a, 0.5f, bb[k]);
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+                f[i + k] = fmaf(h, t, h);
+            } else {
+                f[i + k] = a + bb[k];
+            }
+        }
     }
     if (nv == 16) {
         uint32_t o[8];
@@ -267,8 +283,8 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tfull_bar[2];
-    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t tfull_bar[kMaxAcc];
+    __shared__ __align__(8) uint64_t tempty_bar[kMaxAcc];
     __shared__ __align__(8) uint64_t bres_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_bias[kMaxNTile];
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
             tma_prefetch_desc(&p.seg[s].tmB);
         }
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 32 * kEpiWarps); }
+        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 32 * kEpiWarps); }
         mbar_init(&bres_bar, 1);
         fence_mbar_init();
     }
@@ -296,12 +312,14 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
         tmem_alloc(&tmem_base_s, p.tmem_cols);
         tmem_relinquish();
     }
+    const float bias_scale = (EPI == 0 && p.act) ? 0.5f : 1.f;      // SiLU layers keep bias / 2 (epilogue_chunk)
     if (p.n_tiles == 1)
-        for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = i < p.Cout ? __ldg(p.bias + i) : (EPI == 2 ? -INFINITY : 0.f);
+        for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = i < p.Cout ? __ldg(p.bias + i) * bias_scale : (EPI == 2 ? -INFINITY : 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_launch_dependents();        // the next conv of the stream may begin its prologue on SMs this grid has left
 
     const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_nb;
     const int total_tiles = tiles_m * p.n_tiles;
@@ -332,6 +350,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
                                     tap * Cin + sg.c_off + kc * sg.bk, 0);
             }
         }
+        pdl_wait();                 // activations of the previous layer: only after the predecessor grid has completed
         // p.mma_warps == 2: two stage rings of num_stages / 2 slots; ring r holds the tiles issued by MMA warp r (a ring with
         // two consumers would let one of them run a whole revolution ahead, which mbarrier phase parity cannot tell apart)
         const int ring_stages = MW == 2 ? num_stages >> 1 : num_stages;
@@ -339,11 +358,11 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
         int ostage = ring_stages; uint32_t ophase = 0;      // MW == 2: saved position in the other ring
         int stage_lo = 0, stage_hi = ring_stages;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_idx = tile % n_tiles;
-            int m_idx = tile / n_tiles;
-            const int w0 = (m_idx % tiles_w) * TW; m_idx /= tiles_w;
-            const int h0 = (m_idx % tiles_h) * TH;
-            const int n0 = (m_idx / tiles_h) * NB;
+            const int m0 = fast_div(tile, p.magic_nt), n_idx = tile - m0 * n_tiles;
+            const int m1 = fast_div(m0, p.magic_tw), m2 = fast_div(m1, p.magic_th);
+            const int w0 = (m0 - m1 * tiles_w) * TW;
+            const int h0 = (m1 - m2 * tiles_h) * TH;
+            const int n0 = m2 * NB;
             for (int g = 0; g < groups; ++g) {
                 int map = 0, cw, chh;
                 if (halo == 3) {                  // stride 2: g = input parity (row parity * 2 + column parity); odd views start one earlier
@@ -404,6 +423,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
         // everything the issue loop computes with must be provably warp-uniform for the compiler (else it falls back to vector
         // registers + R2UR per MMA): the warp index comes through a shuffle (MW == 2) or is a constant (MW == 1)
         const int mw = MW == 1 ? 0 : (int)__reduce_max_sync(0xffffffffu, (unsigned)warp) - 1;      // REDUX: result lives in a uniform register
+        pdl_wait();
         {
         const uint32_t leader = elect_one() ? 1u : 0u;
         const uint32_t tmem_base_u = __reduce_or_sync(0xffffffffu, tmem_base);
@@ -429,6 +449,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
         const int stage_lo = mw * ring_stages, stage_hi = stage_lo + ring_stages;
         int stage = stage_lo; uint32_t phase = 0;
         int acc = mw; uint32_t acc_phase = 0;
+        const int acc_stages = p.acc_stages;
         if (b_res) { mbar_wait_uniform(&bres_bar, 0); tc_fence_after(); }
         for (int tile = blockIdx.x + mw * gridDim.x; tile < total_tiles; tile += (two ? 2 : 1) * gridDim.x) {
             mbar_wait_uniform(&tempty_bar[acc], acc_phase ^ 1);
@@ -491,12 +512,13 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
                 }
             }
             tc_commit_if(leader, &tfull_bar[acc]);               // accumulator complete -> epilogue
-            if (two) acc_phase ^= 1;
-            else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc += MW;
+            if (acc >= acc_stages) { acc -= acc_stages; acc_phase ^= 1; }
         }
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
+        pdl_wait();                                         // residual reads and output writes: after the predecessor grid
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
         const int half = (warp - 1 - kMmaWarps) >> 2;       // which of the kSub warps of the quadrant
         const int row = quad * 32 + lane;                   // row of the 128-row tile == TMEM lane
@@ -507,13 +529,15 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
         const int out_cstride = p.out_cstride, res_cstride = p.res_cstride;
         __nv_bfloat16* const out0 = p.out + p.out_coff;
         const __nv_bfloat16* const res0 = p.res ? p.res + p.res_coff : nullptr;
-        int acc = 0; uint32_t acc_phase = 0;
+        int acc = 0; uint32_t acc_phase = 0; int par = 0;
+        const int acc_stages = p.acc_stages;
+        const uint32_t magic_nt = p.magic_nt, magic_tw = p.magic_tw, magic_th = p.magic_th;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_idx = tile % n_tiles;
-            int m_idx = tile / n_tiles;
-            const int w = (m_idx % tiles_w) * TW + tw; m_idx /= tiles_w;
-            const int h = (m_idx % tiles_h) * TH + th;
-            const int n = (m_idx / tiles_h) * NB + nb;
+            const int m0 = fast_div(tile, magic_nt), n_idx = tile - m0 * n_tiles;
+            const int m1 = fast_div(m0, magic_tw), m2 = fast_div(m1, magic_th);
+            const int w = (m0 - m1 * tiles_w) * TW + tw;
+            const int h = (m1 - m2 * tiles_h) * TH + th;
+            const int n = m2 * NB + nb;
             const bool valid = (w < Wo) && (h < Ho) && (n < Bn);
             const size_t pix = ((size_t)n * Ho + h) * Wo + w;
             const int n_base = n_idx * n_tile;
@@ -524,7 +548,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
             if (n_tiles > 1) {
                 // per-tile bias slice (named barrier over the epilogue warps only)
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
-                for (int i = threadIdx.x - 32 * (1 + kMmaWarps); i < n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < Cout ? __ldg(p.bias + n_base + i) : (EPI == 2 ? -INFINITY : 0.f);
+                for (int i = threadIdx.x - 32 * (1 + kMmaWarps); i < n_tile; i += 32 * kEpiWarps) s_bias[i] = (n_base + i) < Cout ? __ldg(p.bias + n_base + i) * bias_scale : (EPI == 2 ? -INFINITY : 0.f);
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps));
             }
 
@@ -579,14 +603,15 @@ __global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_ke
                     if (two) cls_chunk(v1, s_bias + (j + 1) * 16, (j + 1) * 16, best);
                 }
                 const int key = best;
-                int* const slot = &s_key[acc][row];
+                int* const slot = &s_key[par][row];
                 if (half) *slot = key;
                 asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
                 if (!half && valid) *reinterpret_cast<float2*>(p.out_f32 + pix * 2) = cls_unkey(max(key, *slot));
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+            par ^= 1;
         }
     }
 
@@ -1281,6 +1306,17 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     p.mma_warps = (mmaw >= 2 && stages >= 4 && p.halo >= 2 && ctas == 1) ? 2 : 1;
     if (p.mma_warps == 2) stages &= ~1;
     p.num_stages = stages;
+    // accumulator stages: as many (<= kMaxAcc) as this CTA's share of the 512 tensor-memory columns holds -- the epilogue of a
+    // tile is latency bound (tcgen05.ld -> SiLU -> stores), so the MMA warps need more than one tile of run-ahead
+    {
+        int acc = 512 / ctas / p.n_tile;
+        if (const char* av = getenv("B2_CONV_ACC")) { const int cap = atoi(av); if (cap >= 2 && cap < acc) acc = cap; }   // experiments only
+        p.acc_stages = acc > kMaxAcc ? kMaxAcc : acc < 2 ? 2 : acc;
+        if (p.mma_warps == 2 && (p.acc_stages & 1)) --p.acc_stages;
+        uint32_t c2 = 32;
+        while (c2 < (uint32_t)(p.acc_stages * p.n_tile)) c2 <<= 1;
+        p.tmem_cols = c2;
+    }
     L->smem = (size_t)stages * (p.b_resident ? a_stage : ab_stage) + (p.b_resident ? b_all : 0) + 1024;
     }
     p.out = (__nv_bfloat16*)out; p.out_cstride = out_cstride; p.out_coff = out_coff;
@@ -1289,6 +1325,12 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     p.wide = (out_cstride % 16 == 0 && out_coff % 16 == 0 && (uintptr_t)out % 32 == 0 &&
               (!residual || (res_cstride % 16 == 0 && res_coff % 16 == 0 && (uintptr_t)residual % 32 == 0))) ? 1 : 0;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_nb * p.n_tiles;
+    {
+        auto magic = [&](int d) -> uint32_t { return d == 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+        const int dmax = std::max(p.n_tiles, std::max(p.tiles_w, p.tiles_h));
+        B2_REQUIRE((uint64_t)total_tiles * (uint64_t)dmax < ((uint64_t)1 << 32), "conv: %d tiles exceed the tile-index arithmetic", total_tiles);
+        p.magic_nt = magic(p.n_tiles); p.magic_tw = magic(p.tiles_w); p.magic_th = magic(p.tiles_h);
+    }
     const int slots = b2_num_sms() * ctas;
     L->grid = total_tiles < slots ? total_tiles : slots;
     if (const char* gv = getenv("B2_CONV_GRID")) { const int gcap = atoi(gv); if (gcap > 0 && gcap < L->grid) L->grid = gcap; }   // experiments only
@@ -1371,15 +1413,27 @@ void b2_count_launch(int n);
 
 int b2_conv_launch(const void* storage, cudaStream_t stream) {
     const B2ConvLaunch* L = reinterpret_cast<const B2ConvLaunch*>(storage);
-    if (L->p.ts) conv_ts_kernel<<<L->grid, kTsThreads, L->smem, stream>>>(L->p);
-    else if (L->p.epi == 1) conv_tc_kernel<1, 0, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
-    else if (L->p.epi == 2) conv_tc_kernel<2, 0, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
-    else if (L->p.mma_warps == 2 && L->p.halo == 3) conv_tc_kernel<0, 3, 2><<<L->grid, kThreadsMw2, L->smem, stream>>>(L->p);
-    else if (L->p.mma_warps == 2) conv_tc_kernel<0, 2, 2><<<L->grid, kThreadsMw2, L->smem, stream>>>(L->p);
-    else if (L->p.halo == 3) conv_tc_kernel<0, 3, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
-    else if (L->p.halo == 2) conv_tc_kernel<0, 2, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
-    else if (L->p.halo == 1) conv_tc_kernel<0, 1, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
-    else conv_tc_kernel<0, 0, 1><<<L->grid, kThreadsMw1, L->smem, stream>>>(L->p);
+    if (L->p.ts) { conv_ts_kernel<<<L->grid, kTsThreads, L->smem, stream>>>(L->p); B2_CUDA(cudaGetLastError()); b2_count_launch(1); return B2_OK; }
+    // programmatic dependent launch: this grid's prologue overlaps the tail of the previous kernel of the stream when that
+    // kernel is a conv_tc_kernel too (it calls griddepcontrol.launch_dependents); otherwise the attribute changes nothing
+    static const bool pdl = [] { const char* v = getenv("B2_CONV_PDL"); return !(v && atoi(v) == 0); }();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)L->grid); cfg.dynamicSmemBytes = L->smem; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    auto go = [&](auto kernel, int threads) { cfg.blockDim = dim3((unsigned)threads); return cudaLaunchKernelEx(&cfg, kernel, L->p); };
+    cudaError_t e;
+    if (L->p.epi == 1) e = go(conv_tc_kernel<1, 0, 1>, kThreadsMw1);
+    else if (L->p.epi == 2) e = go(conv_tc_kernel<2, 0, 1>, kThreadsMw1);
+    else if (L->p.mma_warps == 2 && L->p.halo == 3) e = go(conv_tc_kernel<0, 3, 2>, kThreadsMw2);
+    else if (L->p.mma_warps == 2) e = go(conv_tc_kernel<0, 2, 2>, kThreadsMw2);
+    else if (L->p.halo == 3) e = go(conv_tc_kernel<0, 3, 1>, kThreadsMw1);
+    else if (L->p.halo == 2) e = go(conv_tc_kernel<0, 2, 1>, kThreadsMw1);
+    else if (L->p.halo == 1) e = go(conv_tc_kernel<0, 1, 1>, kThreadsMw1);
+    else e = go(conv_tc_kernel<0, 0, 1>, kThreadsMw1);
+    B2_CUDA(e);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
