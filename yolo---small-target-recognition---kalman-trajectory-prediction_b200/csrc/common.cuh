@@ -70,6 +70,13 @@ __device__ __forceinline__ float silu_fast(float x) {
     return fmaf(h, t, h);
 }
 
+// the same with h = x / 2 already formed (epilogues fold the halving into the bias FFMA)
+__device__ __forceinline__ float silu_half(float h) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

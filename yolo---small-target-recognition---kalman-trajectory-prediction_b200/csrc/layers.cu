@@ -15,9 +15,16 @@ namespace {
 // one thread issues two tcgen05.mma (M=128, N=C0, K=16) against the resident bf16 weight tile, and the same 128
 // threads read their accumulator row back from TMEM (thread r <-> TMEM lane r), apply 1/255 and the folded bias
 // in fp32, SiLU, and store C0 bf16 channels.  Several CTAs per SM overlap load / MMA / epilogue phases.
+//
+// uint8 frames (Loader::kMagic): no integer -> float conversion at all.  The operand is FP16 and byte n is stored as
+// 0x6400 | n == 1024 + n (exact: one PRMT makes two operands), the weights are the bf16 weights converted to FP16, and
+// the constant 1024 * sum_k w[n][k] is taken out again through the bias in the fp32 epilogue.  The im2col row is laid out
+// as the bytes lie in memory -- K index = kh * 10 + kw * 3 + c (c in B, G, R order, index 9 of every kh a zero weight) --
+// so a row is three runs of 10 consecutive frame bytes: 3 aligned word loads, 3 funnel shifts and 5 PRMT per run.
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemThreads = 128;
 constexpr int kStemMaxC0 = 128;
+constexpr int kStemPitch = 144;          // bytes between staged patch rows (16-byte multiple, not a multiple of 128: rows 2 apart hit other banks)
 
 __device__ __forceinline__ uint32_t swz64_chunk_off(int row, int chunk) {   // byte offset of 16-byte chunk `chunk` of 64-byte row `row`
     return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
@@ -32,26 +39,56 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
     __shared__ __align__(1024) uint8_t s_a[128 * 64];
     __shared__ __align__(1024) uint8_t s_b[kStemMaxC0 * 64];
     __shared__ __align__(16) float s_bias[kStemMaxC0];
-    __shared__ __align__(16) uint8_t s_in[17 * 128 + 32];      // staged input patch: 17 rows x 128 bytes, then the 17 row offsets (0..15)
+    __shared__ __align__(16) uint8_t s_in[17 * kStemPitch + 32];      // staged input patch: 17 rows x kStemPitch bytes, then the 17 row offsets (0..15)
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(&s_tmem, tmem_cols); tmem_relinquish(); }
     // weights [C0][32] bf16 (k = (kh*3+kw)*3 + c_rgb, 27..31 zero) -> swizzled 64-byte rows; rows >= C0 zero
+    constexpr bool kMagic = Loader::kMagic;
     for (int i = tid; i < n_tile * 4; i += kStemThreads) {
         const int n = i >> 2, c = i & 3;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (n < C0) v = *reinterpret_cast<const uint4*>(w + (size_t)n * 32 + c * 8);
+        if (n < C0) {
+            if (!kMagic) v = *reinterpret_cast<const uint4*>(w + (size_t)n * 32 + c * 8);
+            else {
+                // FP16 copy in memory-byte order: k' = kh * 10 + kw * 3 + c_mem  <-  k = (kh * 3 + kw) * 3 + (2 - c_mem)
+                uint32_t h[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int kp = c * 8 + e, kh = kp / 10, j = kp - kh * 10;
+                    float x = 0.f;
+                    if (kp < 30 && j < 9) x = __bfloat162float(w[(size_t)n * 32 + (kh * 3 + j / 3) * 3 + (2 - j % 3)]);
+                    h[e] = (uint32_t)__half_as_ushort(__float2half_rn(x));
+                }
+                v = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+            }
+        }
         *reinterpret_cast<uint4*>(s_b + swz64_chunk_off(n, c)) = v;
     }
-    for (int i = tid; i < n_tile; i += kStemThreads) s_bias[i] = i < C0 ? bias[i] : 0.f;
+    // s_bias holds HALF the effective bias (SiLU(x) = h + h tanh(h), h = x / 2 comes out of one FFMA); kMagic: the
+    // 1024 carried by every operand is removed here: x = in_scale * (acc - 1024 * sum_k w16[k]) + bias
+    for (int i = tid; i < n_tile; i += kStemThreads) {
+        float b = 0.f;
+        if (i < C0) {
+            b = bias[i];
+            if (kMagic) {
+                float sw = 0.f;
+                for (int k = 0; k < 27; ++k) sw += __half2float(__float2half_rn(__bfloat162float(w[(size_t)i * 32 + k])));
+                b -= in_scale * 1024.f * sw;
+            }
+        }
+        s_bias[i] = 0.5f * b;
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    // c_format F32 (bit 4); a/b format BF16 (1 at bits 7, 10) or F16 (0)
+    const uint32_t idesc = (1u << 4) | (kMagic ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    const float half_scale = 0.5f * in_scale;
     const uint64_t desc_hi = (uint64_t)(((512u >> 4) & 0x3FFFu) | (1u << 14) | (4u << 29)) << 32;   // SBO = 8 rows x 64 B, SWIZZLE_64B
     const uint32_t a_lo = ((smem_u32(s_a) >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((smem_u32(s_b) >> 4) & 0x3FFFu) | (1u << 16);
     const int tw = tid & 15, th = tid >> 4;                 // 16 x 8 output pixels per tile
@@ -62,12 +99,12 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
         const int ho = (t % tiles_h) * 8 + th;
         const int b = t / tiles_h;
         // ---- im2col row of this thread's pixel ----
-        float v[27];
         bool staged = false;
+        uint32_t pk[16];
         if (Loader::kStaged) {
             // Interior tiles of uint8 frames: the 17 x 33-pixel input patch (99 bytes per row) is copied into shared memory
-            // with aligned 16-byte loads (<= 8 per row; one or two per thread) and each thread then reads its 27 bytes
-            // from there -- 136 vector loads and no per-byte bounds checks instead of 3456 byte loads per tile.
+            // with aligned 16-byte loads (<= 8 per row; one or two per thread) and each thread then takes its three runs of
+            // 10 bytes from there -- 136 vector loads and no per-byte bounds checks instead of 3456 byte loads per tile.
             const int t2 = tile;
             const int wo0 = (t2 % tiles_w) * 16, ho0 = ((t2 / tiles_w) % tiles_h) * 8;
             staged = ld.stage(b, 2 * ho0 - 1, 2 * wo0 - 1, H, W, s_in, tid, kStemThreads);      // uniform across the CTA
@@ -76,17 +113,21 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     const int r = 2 * th + kh;
-                    const uint8_t* q = s_in + r * 128 + s_in[17 * 128 + r] + 6 * tw;
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        v[(kh * 3 + kw) * 3 + 2] = (float)q[kw * 3 + 0];       // B
-                        v[(kh * 3 + kw) * 3 + 1] = (float)q[kw * 3 + 1];       // G
-                        v[(kh * 3 + kw) * 3 + 0] = (float)q[kw * 3 + 2];       // R
-                    }
+                    const uint32_t e = (uint32_t)s_in[17 * kStemPitch + r] + 6u * (uint32_t)tw;      // first byte of the run
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(s_in + r * kStemPitch + (e & ~3u));
+                    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], sh = (e & 3u) * 8u;
+                    const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = w2 >> sh;
+                    pk[kh * 5 + 0] = __byte_perm(a0, 0x64646464u, 0x4140);     // {1024 + b0, 1024 + b1} as two FP16
+                    pk[kh * 5 + 1] = __byte_perm(a0, 0x64646464u, 0x4342);
+                    pk[kh * 5 + 2] = __byte_perm(a1, 0x64646464u, 0x4140);
+                    pk[kh * 5 + 3] = __byte_perm(a1, 0x64646464u, 0x4342);
+                    pk[kh * 5 + 4] = __byte_perm(a2, 0x64646464u, 0x4140);     // b9 belongs to the next pixel: its weight is zero
                 }
+                pk[15] = 0u;
             }
         }
         if (!staged) {
+            float v[27];
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
@@ -95,11 +136,24 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
                     ld.load(b, 2 * ho + kh - 1, 2 * wo + kw - 1, H, W, rgb);
                     v[(kh * 3 + kw) * 3 + 0] = rgb[0]; v[(kh * 3 + kw) * 3 + 1] = rgb[1]; v[(kh * 3 + kw) * 3 + 2] = rgb[2];
                 }
-        }
-        uint32_t pk[16];
+            if (kMagic) {
+                // integer-valued 0..255 floats -> 0x6400 | n, in memory-byte order (B, G, R)
 #pragma unroll
-        for (int i = 0; i < 13; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        pk[13] = pack_bf16x2(v[26], 0.f); pk[14] = 0u; pk[15] = 0u;
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const int j0 = 2 * i, j1 = 2 * i + 1;
+                        const uint32_t lo = 0x6400u | (uint32_t)v[(kh * 3 + j0 / 3) * 3 + (2 - j0 % 3)];
+                        const uint32_t hi = j1 < 9 ? 0x6400u | (uint32_t)v[(kh * 3 + j1 / 3) * 3 + (2 - j1 % 3)] : 0x6400u;
+                        pk[kh * 5 + i] = lo | (hi << 16);
+                    }
+                pk[15] = 0u;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 13; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                pk[13] = pack_bf16x2(v[26], 0.f); pk[14] = 0u; pk[15] = 0u;
+            }
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(s_a + swz64_chunk_off(tid, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
@@ -126,9 +180,9 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
                 uint32_t o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float x0 = fmaf(__uint_as_float(a[2 * i]), in_scale, s_bias[j + 2 * i]);
-                    const float x1 = fmaf(__uint_as_float(a[2 * i + 1]), in_scale, s_bias[j + 2 * i + 1]);
-                    o[i] = pack_bf16x2(silu_fast(x0), silu_fast(x1));
+                    const float h0 = fmaf(__uint_as_float(a[2 * i]), half_scale, s_bias[j + 2 * i]);
+                    const float h1 = fmaf(__uint_as_float(a[2 * i + 1]), half_scale, s_bias[j + 2 * i + 1]);
+                    o[i] = pack_bf16x2(silu_half(h0), silu_half(h1));
                 }
                 if (j + 16 <= C0) {
                     *reinterpret_cast<uint4*>(op + j) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -145,10 +199,10 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
 }
 
 struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left) of the canvas, border 114, outside canvas 0
-    static constexpr bool kStaged = true;
+    static constexpr bool kStaged = true, kMagic = true;
     const uint8_t* p; int sh, sw, pt, pl;
     long long total_bytes;      // B * sh * sw * 3 (vector loads must stay inside the buffer)
-    // Copy canvas rows y0 .. y0+16, columns x0 .. x0+32 into s_in (row r at r * 128 + off[r], off[r] = s_in[17 * 128 + r]).
+    // Copy canvas rows y0 .. y0+16, columns x0 .. x0+32 into s_in (row r at r * kStemPitch + off[r], off[r] = s_in[17 * kStemPitch + r]).
     // Returns false (nothing written) unless the whole patch lies inside the frame: border tiles take the per-byte path.
     __device__ __forceinline__ bool stage(int b, int y0, int x0, int H, int W, uint8_t* s_in, int tid, int nthreads) const {
         const int fy0 = y0 - pt, fx0 = x0 - pl;
@@ -159,8 +213,8 @@ struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left
             const int r = i >> 3, c = i & 7;
             const long long g0 = g_first + (long long)r * sw * 3;
             const long long ga = (g0 & ~15ll) + c * 16;
-            if (ga < g0 + 99) *reinterpret_cast<uint4*>(s_in + r * 128 + c * 16) = __ldg(reinterpret_cast<const uint4*>(p + ga));
-            if (c == 0) s_in[17 * 128 + r] = (uint8_t)(g0 & 15);
+            if (ga < g0 + 99) *reinterpret_cast<uint4*>(s_in + r * kStemPitch + c * 16) = __ldg(reinterpret_cast<const uint4*>(p + ga));
+            if (c == 0) s_in[17 * kStemPitch + r] = (uint8_t)(g0 & 15);
         }
         return true;
     }
@@ -174,7 +228,7 @@ struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left
 };
 template <typename T>
 struct LoadPlanar {   // [B][3][H][W] RGB in [0,1]; the tensor core consumes bf16(255 x) (exact for uint8-derived inputs)
-    static constexpr bool kStaged = false;
+    static constexpr bool kStaged = false, kMagic = false;
     const T* p;
     __device__ __forceinline__ bool stage(int, int, int, int, int, uint8_t*, int, int) const { return false; }
     __device__ __forceinline__ void load(int b, int y, int x, int H, int W, float (&rgb)[3]) const {
