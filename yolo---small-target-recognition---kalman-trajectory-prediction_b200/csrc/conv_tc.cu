@@ -98,6 +98,7 @@ struct alignas(64) ConvParams {
     uint32_t chunk_magic;     // ceil(2^32 / (cout16 / 16)): item -> pixel by a multiply-high
     int ts_steps;             // pipeline stages one tile consumes
     int mma_warps;            // conv_tc_kernel: 1 or 2 MMA-issuing warps (2: alternate tiles, two stage rings)
+    int epi_warps;            // conv_tc_kernel: 8 or 16 epilogue warps (16 only with two MMA warps, one CTA per SM)
     int acc_stages;           // conv_tc_kernel: accumulator stages in tensor memory (2..4): tile t uses stage t % acc_stages
     uint32_t magic_nt, magic_tw, magic_th;   // ceil(2^32 / d) for d = n_tiles, tiles_w, tiles_h (0: d == 1) -- tile index -> coordinates
     int dbg_skip_mma;         // B2_CONV_DEBUG=1: issue no MMAs (timing of the TMA / epilogue paths alone; results are garbage)
@@ -277,9 +278,11 @@ __device__ __forceinline__ void ss_issue_taps(uint32_t leader, uint32_t d_addr, 
 
 // MW: MMA-issuing warps.  1: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, up to two CTAs per SM.  2 (plans with ONE CTA per SM):
 // warps 1 and 2 issue alternate tiles, each with its own accumulator stage and its own ring of pipeline stages.
-template <int EPI, int HALO, int MW>
-__global__ void __launch_bounds__(32 * (1 + MW + 8), MW == 1 ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-    constexpr int kEpiWarps = 8, kMmaWarps = MW, kThreads = 32 * (1 + MW + 8), kSub = 2;
+template <int EPI, int HALO, int MW, int EW = 8>
+__global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    // EW epilogue warps, kSub per TMEM lane quadrant (the epilogue is latency bound -- TMEM load, MUFU, stores -- so the
+    // one-CTA-per-SM plans run 16: four warps per scheduler hide each other's stalls)
+    constexpr int kEpiWarps = EW, kMmaWarps = MW, kThreads = 32 * (1 + MW + EW), kSub = EW / 4;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -1082,6 +1085,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
             set((const void*)conv_tc_kernel<0, 0, 1>); set((const void*)conv_tc_kernel<0, 1, 1>); set((const void*)conv_tc_kernel<0, 2, 1>);
             set((const void*)conv_tc_kernel<0, 3, 1>); set((const void*)conv_tc_kernel<1, 0, 1>); set((const void*)conv_tc_kernel<2, 0, 1>);
             set((const void*)conv_tc_kernel<0, 2, 2>); set((const void*)conv_tc_kernel<0, 3, 2>);
+            set((const void*)conv_tc_kernel<0, 2, 2, 16>); set((const void*)conv_tc_kernel<0, 3, 2, 16>);
             attr_err = e;
         });
         B2_CUDA(attr_err);
@@ -1306,6 +1310,13 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     p.mma_warps = (mmaw >= 2 && stages >= 4 && p.halo >= 2 && ctas == 1) ? 2 : 1;
     if (p.mma_warps == 2) stages &= ~1;
     p.num_stages = stages;
+    p.epi_warps = 8;
+    if (p.mma_warps == 2) {
+        // measured (tools/conv_bench.py --ab B2_CONV_EPIW=8,16): 16 warps pay when a quadrant has more than four 16-column
+        // chunks to drain or the epilogue also reads the shortcut tensor (80->80 3x3 at P2: 0.53 -> 0.47 ms); 8 otherwise
+        p.epi_warps = (p.n_tile > 64 || residual) ? 16 : 8;
+        if (const char* ev = getenv("B2_CONV_EPIW")) p.epi_warps = atoi(ev) == 8 ? 8 : atoi(ev) == 16 ? 16 : p.epi_warps;   // experiments only
+    }
     // accumulator stages: as many (<= kMaxAcc) as this CTA's share of the 512 tensor-memory columns holds -- the epilogue of a
     // tile is latency bound (tcgen05.ld -> SiLU -> stores), so the MMA warps need more than one tile of run-ahead
     {
@@ -1427,6 +1438,8 @@ int b2_conv_launch(const void* storage, cudaStream_t stream) {
     cudaError_t e;
     if (L->p.epi == 1) e = go(conv_tc_kernel<1, 0, 1>, kThreadsMw1);
     else if (L->p.epi == 2) e = go(conv_tc_kernel<2, 0, 1>, kThreadsMw1);
+    else if (L->p.mma_warps == 2 && L->p.halo == 3 && L->p.epi_warps == 16) e = go(conv_tc_kernel<0, 3, 2, 16>, kThreadsMw2 + 256);
+    else if (L->p.mma_warps == 2 && L->p.epi_warps == 16) e = go(conv_tc_kernel<0, 2, 2, 16>, kThreadsMw2 + 256);
     else if (L->p.mma_warps == 2 && L->p.halo == 3) e = go(conv_tc_kernel<0, 3, 2>, kThreadsMw2);
     else if (L->p.mma_warps == 2) e = go(conv_tc_kernel<0, 2, 2>, kThreadsMw2);
     else if (L->p.halo == 3) e = go(conv_tc_kernel<0, 3, 1>, kThreadsMw1);
