@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) dense_candidates_kernel(const float* __re
 // NMS: one CTA per image
 // ------------------------------------------------------------------------------------------------
 constexpr int kNmsThreads = 1024;
-constexpr int kSmemSort = 2048;      // pairs sorted entirely in shared memory
+constexpr int kSmemSort = 4096;      // pairs sorted entirely in (dynamic) shared memory: one dense image among hundreds sets the kernel's time
 constexpr int kMaxCand = 65536;      // alive bitmask (shared memory) covers this many sorted candidates
 constexpr int kMaxKeep = 1024;
 constexpr int kFastN = 704;          // bit-matrix path: 704 boxes (11 KB) + 704 x 22 words (62 KB) of dynamic shared memory
@@ -281,6 +281,7 @@ struct NmsParams {
     float gain, pad_x, pad_y, orig_w, orig_h; int do_scale;
     float* out; int32_t* out_count; int32_t* out_idx;
     unsigned long long* ws_keys; int32_t* ws_pay; float4* ws_box; int P_max;
+    int debug;          // B2_NMS_DEBUG=1: thread 0 of every CTA leaves clock64() stamps of its phases in its ws_box slice (exact mode only)
 };
 
 __device__ __forceinline__ void bitonic_exchange(unsigned long long* keys, int32_t* pay, int i, int j, bool desc_block) {
@@ -292,20 +293,56 @@ __device__ __forceinline__ void bitonic_exchange(unsigned long long* keys, int32
     }
 }
 
+// iou(bi, bj) > thr with the reference's fp32 operation order (torchvision nms / TorchNMS.nms), written so that the common case
+// -- no overlap along x (always true for boxes of different classes: the class offset is 7680 px) -- costs three instructions.
+// Exactly equivalent to the clamped form: iw <= 0 or ih <= 0 makes inter 0, and 0 / union is 0, -0 or NaN, never > thr >= 0.
+__device__ __forceinline__ bool iou_exceeds(const float4 bi, const float area_i, const float4 bj, const float thr, bool* touches = nullptr) {
+    const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
+    if (!(iw > 0.f)) return false;
+    const float ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+    if (!(ih > 0.f)) return false;
+    const float inter = __fmul_rn(iw, ih);
+    if (touches && inter != 0.f) *touches = true;
+    const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter)) > thr;
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) {
-    __shared__ unsigned long long s_keys[kSmemSort];
-    __shared__ int32_t s_pay[kSmemSort];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long* const s_keys = reinterpret_cast<unsigned long long*>(s_raw);          // [kSmemSort]
+    int32_t* const s_pay = reinterpret_cast<int32_t*>(s_raw + (size_t)kSmemSort * 8);          // [kSmemSort]
     __shared__ int32_t s_keep[kMaxKeep];
     __shared__ uint32_t alive[kMaxCand / 32];
     __shared__ int s_cur, s_nkeep, s_any, s_done;
 
-    const int b = blockIdx.x, tid = threadIdx.x;
+    // Heaviest images first: CTA r takes the image of rank r by candidate count (ties: lower index).  The kernel lasts as long
+    // as its slowest image (one dense frame among hundreds has 10x the candidates), which must not start in the second wave.
+    const int tid = threadIdx.x;
+    int b = blockIdx.x;
+    if (p.B <= kNmsThreads) {
+        int* s_cnt = reinterpret_cast<int*>(alive);                       // alive[] is not in use yet
+        if (tid < p.B) s_cnt[tid] = p.cand_count[tid];
+        __syncthreads();
+        if (tid < p.B) {
+            const int mine = s_cnt[tid];
+            int rank = 0;
+            for (int j = 0; j < p.B; ++j) { const int c = s_cnt[j]; rank += (c > mine) || (c == mine && j < tid); }
+            if (rank == (int)blockIdx.x) s_cur = tid;
+        }
+        __syncthreads();
+        b = s_cur;
+        __syncthreads();
+    }
     int n = min(p.cand_count[b], p.cand_cap);
     const float* cand = p.cand + (size_t)b * p.cand_cap * 6;
     const int32_t* cidx = p.cand_idx + (size_t)b * p.cand_cap;
     float* out = p.out + (size_t)b * p.max_det * 6;
     if (n == 0) { if (tid == 0) p.out_count[b] = 0; return; }
 
+    long long* const stamp = reinterpret_cast<long long*>(p.ws_box + (size_t)b * p.P_max);
+    int n_stamp = 0;
+#define NMS_STAMP() do { if (p.debug && tid == 0) stamp[n_stamp++] = clock64(); } while (0)
+    NMS_STAMP();
     int P = 32;
     while (P < n) P <<= 1;
     const bool in_smem = P <= kSmemSort;
@@ -329,6 +366,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
         }
     }
     n = min(n, p.max_nms);
+    NMS_STAMP();          // [1] sorted
 
     const int max_keep = min(p.max_det, kMaxKeep);
     if (p.mode == 0) {
@@ -337,7 +375,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
         //      an nb x nb bit matrix, (3) one warp walks the block in score order OR-ing the suppression rows of the boxes
         //      it keeps.  One block covers the usual case; dense scenes (thousands of candidates) take a few blocks instead
         //      of one block-wide pass per kept box. ----
-        extern __shared__ uint32_t s_dyn[];
+        uint32_t* const s_dyn = reinterpret_cast<uint32_t*>(s_raw + (size_t)kSmemSort * 12);
         float4* fbox = reinterpret_cast<float4*>(s_dyn);                  // [kFastN] boxes of the block (class offset applied)
         uint32_t* mat = s_dyn + kFastN * 4;                                 // [nb][Wd]
         float4* kbox = reinterpret_cast<float4*>(mat + kFastN * ((kFastN + 31) / 32));   // [kMaxKeep] kept boxes
@@ -354,6 +392,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
                 fbox[i] = make_float4(__fadd_rn(c[0], off), __fadd_rn(c[1], off), __fadd_rn(c[2], off), __fadd_rn(c[3], off));
             }
             __syncthreads();
+            NMS_STAMP();
             // (1) against the kept boxes of earlier blocks (warp-coalesced: lane <-> member, ballot -> one word per warp step)
             for (int i0 = (tid >> 5) * 32; i0 < Wd * 32; i0 += kNmsThreads) {
                 const int i = i0 + (tid & 31);
@@ -361,55 +400,68 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
                 if (i < nb && nk0 > 0) {
                     const float4 bi = fbox[i];
                     const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-                    for (int k = 0; k < nk0 && !sup; ++k) {
-                        const float4 bj = kbox[k];
-                        const float iw = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
-                        const float ih = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
-                        const float inter = __fmul_rn(iw, ih);
-                        const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-                        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_j, area_i), inter));
-                        sup = iou > p.iou_thres;
-                    }
+                    for (int k = 0; k < nk0 && !sup; ++k) sup = iou_exceeds(bi, area_i, kbox[k], p.iou_thres);
                 }
                 const unsigned word = __ballot_sync(0xffffffffu, sup || i >= nb);
                 if ((tid & 31) == 0) dead[i0 >> 5] = word;
             }
-            // (2) pairwise tests inside the block
-            for (int t = tid; t < nb * Wd; t += kNmsThreads) {
-                const int i = t / Wd, wj = t - i * Wd;
-                uint32_t bits = 0;
-                if (wj * 32 + 31 > i) {
+            // (2) pairwise tests inside the block, one warp per (row i, 32-column word wj >= i / 32): lane <-> column, so the
+            //     box loads are consecutive (the per-thread form read fbox at a 512-byte stride: a 22-way bank conflict per
+            //     load, 250 k cycles for a full block) and the word is one ballot
+            {
+                const int warp = tid >> 5, lane = tid & 31;
+                for (int i = warp; i < nb; i += kNmsThreads / 32) {
                     const float4 bi = fbox[i];
                     const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-                    const int j0 = max(wj * 32, i + 1), j1 = min(wj * 32 + 32, nb);
-                    for (int j = j0; j < j1; ++j) {
-                        const float4 bj = fbox[j];
-                        const float iw = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
-                        const float ih = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
-                        const float inter = __fmul_rn(iw, ih);
-                        const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-                        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
-                        if (iou > p.iou_thres) bits |= 1u << (j & 31);
+                    const int w0 = i >> 5;
+                    if (lane < w0) mat[i * Wd + lane] = 0u;                       // below the diagonal: never set, but OR-ed by the walk
+                    for (int wj = w0; wj < Wd; ++wj) {
+                        const int j = wj * 32 + lane;
+                        const bool sup = j > i && j < nb && iou_exceeds(bi, area_i, fbox[j], p.iou_thres);
+                        const uint32_t word = __ballot_sync(0xffffffffu, sup);
+                        if (lane == 0) mat[i * Wd + wj] = word;
                     }
                 }
-                mat[t] = bits;
             }
             __syncthreads();
-            // (3) greedy walk of the block by one warp
+            NMS_STAMP();
+            // (3) greedy walk of the block by one warp, 32 members at a time: the keep decisions inside a group need only the
+            //     group's 32 x 32 diagonal block (32 broadcast loads up front: the sequential chain is register arithmetic); the rows of the kept members are then OR-ed into the other words with independent loads
             if (tid < 32) {
                 uint32_t removed = tid < Wd ? dead[tid] : 0xffffffffu;        // lane l owns word l (Wd <= 32)
                 int nk = nk0;
-                for (int i = 0; i < nb && nk < max_keep; ++i) {
-                    const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
-                    if (!((r >> (i & 31)) & 1u)) {
-                        if (tid == 0) { s_keep[nk] = s0 + i; kbox[nk] = fbox[i]; }
-                        ++nk;
-                        if (tid < Wd) removed |= mat[i * Wd + tid];
+                for (int w = 0; w < Wd && nk < max_keep; ++w) {
+                    const int base = w * 32, row = base + tid;
+                    // the group's diagonal words and its removal word straight from shared memory (same address in every lane:
+                    // broadcast loads, all independent of the decision chain; no shuffles)
+                    uint32_t d[32];
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) d[jj] = mat[(base + jj) * Wd + w];
+                    uint32_t cur = dead[w], kmask = 0;
+                    int room = max_keep - nk;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const bool keep = !((cur >> jj) & 1u) && room > 0;
+                        if (keep) { kmask |= 1u << jj; cur |= d[jj]; --room; }
                     }
+                    if ((kmask >> tid) & 1u) {
+                        const int pos = nk + __popc(kmask & ((1u << tid) - 1u));
+                        s_keep[pos] = s0 + row; kbox[pos] = fbox[row];
+                    }
+                    nk += __popc(kmask);
+                    // branch-free (a data-dependent loop with a divergent body costs a convergence barrier per iteration, far
+                    // more than 32 predicated loads): rows past nb are inside the allocation and masked by kmask
+                    uint32_t acc = 0;
+                    const uint32_t* mrow = mat + base * Wd + min(tid, Wd - 1);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) acc |= mrow[jj * Wd] & (0u - ((kmask >> jj) & 1u));
+                    if (tid < Wd) { removed |= acc; dead[tid] = removed; }
+                    __syncwarp();
                 }
                 if (tid == 0) s_nkeep = nk;
             }
             __syncthreads();
+            NMS_STAMP();
         }
     } else {
     // sorted, class-offset boxes (nms.py:144,150: boxes = x[:, :4] + cls * max_wh, fp32) + alive bitmask
@@ -455,14 +507,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
         int any = 0;
         for (int j = i + 1 + tid; j < n; j += kNmsThreads) {
             if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;
-            const float4 bj = sbox[j];
-            const float iw = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
-            const float ih = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
-            const float inter = __fmul_rn(iw, ih);
-            if (inter != 0.f) any = 1;
-            const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
-            if (iou > p.iou_thres) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
+            bool touches = false;
+            const bool sup = iou_exceeds(bi, area_i, sbox[j], p.iou_thres, &touches);
+            if (touches) any = 1;
+            if (sup) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
         }
         if (p.mode == 1) {
             if (any) s_any = 1;      // benign race: all writers store 1
@@ -498,7 +546,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
         o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = c[4]; o[5] = c[5];
         if (p.out_idx) p.out_idx[(size_t)b * p.max_det + k] = cidx[src];
     }
+    NMS_STAMP();
+    if (p.debug && tid == 0) stamp[15] = n_stamp;
     if (tid == 0) p.out_count[b] = nk;
+#undef NMS_STAMP
 }
 
 inline int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
@@ -592,7 +643,8 @@ extern "C" int b2_nms(const float* cand, const int32_t* cand_idx, const int32_t*
     p.ws_keys = (unsigned long long*)ws; ws += (size_t)B * P * 8;
     p.ws_pay = (int32_t*)ws;
     p.P_max = (int)P;
-    const size_t dyn = (size_t)kFastN * 16 + (size_t)kFastN * ((kFastN + 31) / 32) * 4 + (size_t)kMaxKeep * 16;
+    { static const bool dbg = [] { const char* v = getenv("B2_NMS_DEBUG"); return v && atoi(v) != 0; }(); p.debug = dbg ? 1 : 0; }
+    const size_t dyn = (size_t)kSmemSort * 12 + (size_t)kFastN * 16 + (size_t)kFastN * ((kFastN + 31) / 32) * 4 + (size_t)kMaxKeep * 16;
     {
         static cudaError_t attr_err = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         B2_CUDA(attr_err);
