@@ -88,3 +88,27 @@ def stamps():
 
 if len(sys.argv) > 2 and sys.argv[2] == "stamps":
     stamps()
+
+
+def insitu():
+    """Per-stage CUDA-event times of the post-processing on the varying frames of the bench loop."""
+    S = 256
+    pipe = DetectTrackPipeline(bench.MODEL, S, bench.FRAME_HW, 640, bench.CONF, bench.IOU, 300, capacity=2048, **bench.TRACKER)
+    fr = torch.from_numpy(bench.make_frames(S, 4)).cuda()
+    d = pipe.detect
+    acc = {"forward": 0.0, "candidates": 0.0, "nms": 0.0, "tracker": 0.0}
+    N = 16
+    for k in range(N + 6):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record(); d.engine.forward_u8(fr[k % 4], pipe.top, pipe.left)
+        ev[1].record(); d.candidates(pipe.conf)
+        ev[2].record(); dets, counts = d.nms(pipe.iou, (pipe.h0, pipe.w0), False, "exact")
+        ev[3].record(); pipe.bank.update(dets, counts, with_trajectory=False)
+        ev[4].record(); torch.cuda.synchronize()
+        if k >= 6:
+            for i, key in enumerate(acc): acc[key] += ev[i].elapsed_time(ev[i + 1]) / N
+    print({k: round(v, 4) for k, v in acc.items()})
+
+
+if len(sys.argv) > 2 and sys.argv[2] == "insitu":
+    insitu()

@@ -93,6 +93,14 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
     const uint32_t a_lo = ((smem_u32(s_a) >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((smem_u32(s_b) >> 4) & 0x3FFFu) | (1u << 16);
     const int tw = tid & 15, th = tid >> 4;                 // 16 x 8 output pixels per tile
     uint32_t phase = 0;
+    // patch of the first tile (see LoadU8::fetch)
+    uint4 pv0 = make_uint4(0, 0, 0, 0), pv1 = make_uint4(0, 0, 0, 0);
+    long long pg = 0;
+    bool pok = false;
+    if (Loader::kStaged && (int)blockIdx.x < total_tiles) {
+        const int t0 = blockIdx.x;
+        pok = ld.fetch(t0 / (tiles_w * tiles_h), 2 * (((t0 / tiles_w) % tiles_h) * 8) - 1, 2 * ((t0 % tiles_w) * 16) - 1, tid, pv0, pv1, pg);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int t = tile;
         const int wo = (t % tiles_w) * 16 + tw; t /= tiles_w;
@@ -105,9 +113,14 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
             // Interior tiles of uint8 frames: the 17 x 33-pixel input patch (99 bytes per row) is copied into shared memory
             // with aligned 16-byte loads (<= 8 per row; one or two per thread) and each thread then takes its three runs of
             // 10 bytes from there -- 136 vector loads and no per-byte bounds checks instead of 3456 byte loads per tile.
-            const int t2 = tile;
-            const int wo0 = (t2 % tiles_w) * 16, ho0 = ((t2 / tiles_w) % tiles_h) * 8;
-            staged = ld.stage(b, 2 * ho0 - 1, 2 * wo0 - 1, H, W, s_in, tid, kStemThreads);      // uniform across the CTA
+            staged = pok;                                                                        // uniform across the CTA
+            if (staged) ld.commit(s_in, tid, pv0, pv1, pg);
+            {   // loads of the next tile's patch: consumed at the top of the next iteration
+                const int t2 = tile + gridDim.x;
+                pok = false;
+                if (t2 < total_tiles)
+                    pok = ld.fetch(t2 / (tiles_w * tiles_h), 2 * (((t2 / tiles_w) % tiles_h) * 8) - 1, 2 * ((t2 % tiles_w) * 16) - 1, tid, pv0, pv1, pg);
+            }
             if (staged) {
                 __syncthreads();
 #pragma unroll
@@ -204,19 +217,37 @@ struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left
     long long total_bytes;      // B * sh * sw * 3 (vector loads must stay inside the buffer)
     // Copy canvas rows y0 .. y0+16, columns x0 .. x0+32 into s_in (row r at r * kStemPitch + off[r], off[r] = s_in[17 * kStemPitch + r]).
     // Returns false (nothing written) unless the whole patch lies inside the frame: border tiles take the per-byte path.
-    __device__ __forceinline__ bool stage(int b, int y0, int x0, int H, int W, uint8_t* s_in, int tid, int nthreads) const {
+    // fetch(): the loads of one patch into registers (chunk tid, and chunk 128 + tid for tid < 8); commit(): registers -> s_in.
+    // The kernel fetches the patch of its NEXT tile before it works on the current one, so the global-memory latency of the
+    // patch is hidden behind a whole tile of build / MMA / epilogue instead of being paid at the top of every tile.
+    __device__ __forceinline__ bool fetch(int b, int y0, int x0, int tid, uint4& v0, uint4& v1, long long& g_first) const {
         const int fy0 = y0 - pt, fx0 = x0 - pl;
         if (fy0 < 0 || fx0 < 0 || fy0 + 16 >= sh || fx0 + 32 >= sw) return false;
-        const long long g_first = (((long long)b * sh + fy0) * sw + fx0) * 3;
+        g_first = (((long long)b * sh + fy0) * sw + fx0) * 3;
         if (g_first + 16ll * sw * 3 + 99 + 16 > total_bytes) return false;
-        for (int i = tid; i < 17 * 8; i += nthreads) {
-            const int r = i >> 3, c = i & 7;
-            const long long g0 = g_first + (long long)r * sw * 3;
-            const long long ga = (g0 & ~15ll) + c * 16;
-            if (ga < g0 + 99) *reinterpret_cast<uint4*>(s_in + r * kStemPitch + c * 16) = __ldg(reinterpret_cast<const uint4*>(p + ga));
-            if (c == 0) s_in[17 * kStemPitch + r] = (uint8_t)(g0 & 15);
+        {
+            const int r = tid >> 3, c = tid & 7;
+            const long long g0 = g_first + (long long)r * sw * 3, ga = (g0 & ~15ll) + c * 16;
+            if (ga < g0 + 99) v0 = __ldg(reinterpret_cast<const uint4*>(p + ga));
+        }
+        if (tid < 8) {
+            const long long g0 = g_first + 16ll * sw * 3, ga = (g0 & ~15ll) + tid * 16;
+            if (ga < g0 + 99) v1 = __ldg(reinterpret_cast<const uint4*>(p + ga));
         }
         return true;
+    }
+    __device__ __forceinline__ void commit(uint8_t* s_in, int tid, const uint4& v0, const uint4& v1, long long g_first) const {
+        {
+            const int r = tid >> 3, c = tid & 7;
+            const long long g0 = g_first + (long long)r * sw * 3, ga = (g0 & ~15ll) + c * 16;
+            if (ga < g0 + 99) *reinterpret_cast<uint4*>(s_in + r * kStemPitch + c * 16) = v0;
+            if (c == 0) s_in[17 * kStemPitch + r] = (uint8_t)(g0 & 15);
+        }
+        if (tid < 8) {
+            const long long g0 = g_first + 16ll * sw * 3, ga = (g0 & ~15ll) + tid * 16;
+            if (ga < g0 + 99) *reinterpret_cast<uint4*>(s_in + 16 * kStemPitch + tid * 16) = v1;
+            if (tid == 0) s_in[17 * kStemPitch + 16] = (uint8_t)(g0 & 15);
+        }
     }
     __device__ __forceinline__ void load(int b, int y, int x, int H, int W, float (&rgb)[3]) const {
         if (y < 0 || x < 0 || y >= H || x >= W) { rgb[0] = rgb[1] = rgb[2] = 0.f; return; }
@@ -230,7 +261,8 @@ template <typename T>
 struct LoadPlanar {   // [B][3][H][W] RGB in [0,1]; the tensor core consumes bf16(255 x) (exact for uint8-derived inputs)
     static constexpr bool kStaged = false, kMagic = false;
     const T* p;
-    __device__ __forceinline__ bool stage(int, int, int, int, int, uint8_t*, int, int) const { return false; }
+    __device__ __forceinline__ bool fetch(int, int, int, int, uint4&, uint4&, long long&) const { return false; }
+    __device__ __forceinline__ void commit(uint8_t*, int, const uint4&, const uint4&, long long) const {}
     __device__ __forceinline__ void load(int b, int y, int x, int H, int W, float (&rgb)[3]) const {
         if (y < 0 || x < 0 || y >= H || x >= W) { rgb[0] = rgb[1] = rgb[2] = 0.f; return; }
         const size_t plane = (size_t)H * W;
