@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) dense_candidates_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 constexpr int kNmsThreads = 1024;
 constexpr int kSmemSort = 4096;      // pairs sorted entirely in (dynamic) shared memory: one dense image among hundreds sets the kernel's time
-constexpr int kMaxCand = 65536;      // alive bitmask (shared memory) covers this many sorted candidates
+constexpr int kMaxCand = 65536;      // alive bitmask (shared memory) covers this many sorted candidates (max_nms <= kMaxCand)
 constexpr int kMaxKeep = 1024;
 constexpr int kFastN = 704;          // bit-matrix path: 704 boxes (11 KB) + 704 x 22 words (62 KB) of dynamic shared memory
 
@@ -629,7 +629,10 @@ extern "C" int b2_nms(const float* cand, const int32_t* cand_idx, const int32_t*
     B2_REQUIRE(cand && cand_idx && cand_count && out && out_count && workspace, "nms: null pointer");
     B2_REQUIRE(max_det >= 1 && max_det <= kMaxKeep, "nms: max_det=%d out of range [1,%d]", max_det, kMaxKeep);
     B2_REQUIRE(mode == 0 || mode == 1, "nms: mode must be 0 (exact) or 1 (legacy TorchNMS)");
-    B2_REQUIRE(cand_cap >= 1 && cand_cap <= kMaxCand, "nms: cand_cap=%d out of range [1,%d]", cand_cap, kMaxCand);
+    // cand_cap bounds the candidate LIST (callers size it to the anchor count, so the conf filter can never overflow it and the
+    // result never depends on the order candidates were appended in); the bitmask of the legacy walk covers max_nms sorted entries
+    B2_REQUIRE(cand_cap >= 1 && cand_cap <= (1 << 22), "nms: cand_cap=%d out of range [1,%d]", cand_cap, 1 << 22);
+    B2_REQUIRE(max_nms >= 1 && max_nms <= kMaxCand, "nms: max_nms=%d out of range [1,%d]", max_nms, kMaxCand);
     B2_REQUIRE(workspace_bytes >= b2_nms_workspace_bytes(B, cand_cap), "nms: workspace too small");
     B2_REQUIRE(iou_thres >= 0.f && iou_thres <= 1.f, "Invalid IoU %f, valid values are between 0.0 and 1.0", iou_thres);
     NmsParams p{};

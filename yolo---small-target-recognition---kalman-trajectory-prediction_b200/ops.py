@@ -131,7 +131,8 @@ class DetectPost:
         self.w = (C.c_int * self.n_levels)(*level_w)
         self.s = (C.c_int * self.n_levels)(*level_stride)
         self.A = sum(a * b for a, b in zip(level_h, level_w))
-        self.cand_cap = min(int(cand_cap or self.A), 65536)
+        # one slot per anchor by default: the conf filter cannot overflow, so results never depend on append order
+        self.cand_cap = int(cand_cap or self.A)
         self.max_det = max_det
         self.cand = torch.empty((batch, self.cand_cap, 6), dtype=torch.float32, device=dev)
         self.cand_idx = torch.empty((batch, self.cand_cap), dtype=torch.int32, device=dev)
@@ -202,7 +203,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     B, no, A = pred.shape
     nc = nc or no - 4
     dev = pred.device
-    cap = min(A, 65536)
+    cap = A
     cand = torch.empty((B, cap, 6), dtype=torch.float32, device=dev)
     cidx = torch.empty((B, cap), dtype=torch.int32, device=dev)
     ccnt = torch.zeros((B,), dtype=torch.int32, device=dev)
