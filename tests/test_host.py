@@ -58,7 +58,13 @@ def test_lowering_is_consistent(name, hw):
     assert words[0] == engine.MAGIC and len(words) == 6 + 3 * len(P.bufs) + 4 * len(P.levels) + engine.OP_WORDS * len(P.ops)
     assert P.flops == cfg.conv_flops(spec, *hw)                       # SURVEY.md 8d algorithmic FLOPs
     n_convs = sum(1 for o in P.ops if o[0] == engine.OP_CONV) + 1       # + stem
-    assert n_convs == len(cfg.conv_list(spec))
+    # the first convs of Detect's box and class branches (same input) run as one GEMM per level
+    assert n_convs == len(cfg.conv_list(spec)) - 4
+    P1 = engine.lower(spec, sd, *hw, merge_head=False)
+    assert sum(1 for o in P1.ops if o[0] == engine.OP_CONV) + 1 == len(cfg.conv_list(spec)) and P1.flops == P.flops
+    for l in range(4):
+        a, b_ = P.named[f"model.{len(spec['layers']) - 1}.cv2.{l}.0"], P.named[f"model.{len(spec['layers']) - 1}.cv3.{l}.0"]
+        assert a[0] == b_[0] and a[1] == 0 and b_[1] == a[2]             # two channel slices of one buffer
     assert [l[1] for l in P.levels] == [4, 8, 16, 32]
     Pf = engine.lower(spec, sd, *hw, fuse_head=True)
     assert Pf.flops == P.flops and len(Pf.ops) == len(P.ops) and all(l[0] < 0 and l[2] >= 0 for l in Pf.levels)

@@ -1234,7 +1234,10 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
         const size_t a2 = up1k((size_t)(p.TW + 2) * (p.TH + 2) * bk_max * 2);
         int halo2_mode = 1;
         if (const char* hv = getenv("B2_CONV_HALO2")) halo2_mode = atoi(hv);
-        if (halo2_mode && w_all + 3 * a2 <= kOneCtaSmem) { p.halo = 2; a_rows = (p.TW + 2) * (p.TH + 2); p.a_bytes = (uint32_t)a2; }
+        // three box stages, or two when the weights leave no room for a third (64 -> 144 at P2: a stage is a whole tile here,
+        // so two stages still overlap the loads of tile i+1 with the MMAs of tile i)
+        const size_t min_stages = halo2_mode >= 2 ? 2 : 3;
+        if (halo2_mode && w_all + min_stages * a2 <= kOneCtaSmem) { p.halo = 2; a_rows = (p.TW + 2) * (p.TH + 2); p.a_bytes = (uint32_t)a2; }
     }
     const int tpg = p.halo == 2 ? 9 : p.halo == 1 ? 3 : 1;
     // ---- N tiling: streamed-weight stage = A box + tpg weight blocks; shrink the N tile until two stages fit ----
@@ -1296,7 +1299,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     const int s2r = (can_res && tmem2) ? fit(kTwoCta, true) : 0, s2s = tmem2 ? fit(kTwoCta, false) : 0;
     const int s1r = can_res ? fit(kOneCta, true) : 0, s1s = fit(kOneCta, false);
     if (s2r >= 3) { ctas = 2; stages = s2r; p.b_resident = 1; }
-    else if (s1r >= 3) { ctas = 1; stages = s1r; p.b_resident = 1; }
+    else if (s1r >= 3 || (p.halo == 2 && s1r >= 2)) { ctas = 1; stages = s1r; p.b_resident = 1; }
     else if (s2s >= 4) { ctas = 2; stages = s2s; }
     else { ctas = 1; stages = s1s; }
     if (stages > want + 2 && stages > 4) stages = want + 2 > 4 ? want + 2 : 4;

@@ -21,6 +21,8 @@ tensor nor the concatenation is ever written.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import numpy as np
@@ -92,7 +94,7 @@ def _shapes(spec, H, W):
     return hw
 
 
-def lower(spec, state_dict, H, W, fuse_head=False):
+def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
     """Lower ``spec`` (from :func:`cfg.resolve`) with weights ``state_dict`` for an ``H x W`` letterboxed input.
 
     ``fuse_head``: run DFL (softmax expectation) and the class max inside the epilogue of each Detect level's last
@@ -158,8 +160,20 @@ def lower(spec, state_dict, H, W, fuse_head=False):
             raise NotImplementedError(f"{what}: {c} channels -- the tcgen05 conv path needs multiples of 16")
 
     def emit_conv(prefix, inp, out, k, s, bn, res=None, inp2=None, ups=(1, 1), epi=0):
-        """inp/out/res/inp2: (buf, coff, C).  inp2: second input of a folded Concat; ups: resolution factors of the inputs."""
-        w, b = weights.folded(sd, prefix, bn)
+        """inp/out/res/inp2: (buf, coff, C).  inp2: second input of a folded Concat; ups: resolution factors of the inputs.
+        prefix: one module name, or a tuple of modules that read the same input -- their filters are stacked along Cout and run
+        as ONE GEMM (the input tile is fetched once, and a wider N uses the tensor pipe better: N = 144 runs at the pipe's
+        N/2 cycles per MMA where N = 64 and N = 80 are bound by the operand fetch); ``out`` then covers all their channels."""
+        if isinstance(prefix, tuple):
+            ws, bs = zip(*(weights.folded(sd, q, bn) for q in prefix))
+            w, b = np.concatenate(ws, 0), np.concatenate(bs, 0)
+            c0 = out[1]
+            for q, wq in zip(prefix, ws):
+                P.named[q] = (out[0], c0, wq.shape[0])
+                c0 += wq.shape[0]
+            prefix = "+".join(prefix)
+        else:
+            w, b = weights.folded(sd, prefix, bn)
         cout, cin = w.shape[0], w.shape[1]
         assert cin == inp[2] + (inp2[2] if inp2 else 0) and (epi or cout == out[2]), (prefix, w.shape, inp, inp2, out)
         check_c(inp[2], prefix + " input")
@@ -235,12 +249,19 @@ def lower(spec, state_dict, H, W, fuse_head=False):
             for l, f in enumerate(L["f"]):
                 inp = P.loc[f]
                 hh, ww = hw[f]
-                t1, t2 = P.new_buf(hh, ww, cb), P.new_buf(hh, ww, cb)
-                u1, u2 = P.new_buf(hh, ww, cc), P.new_buf(hh, ww, cc)
-                emit_conv(f"{p}.cv2.{l}.0", inp, (t1, 0, cb), 3, 1, True)
-                emit_conv(f"{p}.cv2.{l}.1", (t1, 0, cb), (t2, 0, cb), 3, 1, True)
-                emit_conv(f"{p}.cv3.{l}.0", inp, (u1, 0, cc), 3, 1, True)
-                emit_conv(f"{p}.cv3.{l}.1", (u1, 0, cc), (u2, 0, cc), 3, 1, True)
+                t2, u2 = P.new_buf(hh, ww, cb), P.new_buf(hh, ww, cc)
+                if merge_head and (cb + cc) <= 256 and cb % 8 == 0:
+                    # the first conv of the box branch and of the class branch read the same feature map: one conv, Cout = cb + cc
+                    tu = P.new_buf(hh, ww, cb + cc)
+                    emit_conv((f"{p}.cv2.{l}.0", f"{p}.cv3.{l}.0"), inp, (tu, 0, cb + cc), 3, 1, True)
+                    t1_loc, u1_loc = (tu, 0, cb), (tu, cb, cc)
+                else:
+                    t1, u1 = P.new_buf(hh, ww, cb), P.new_buf(hh, ww, cc)
+                    emit_conv(f"{p}.cv2.{l}.0", inp, (t1, 0, cb), 3, 1, True)
+                    emit_conv(f"{p}.cv3.{l}.0", inp, (u1, 0, cc), 3, 1, True)
+                    t1_loc, u1_loc = (t1, 0, cb), (u1, 0, cc)
+                emit_conv(f"{p}.cv2.{l}.1", t1_loc, (t2, 0, cb), 3, 1, True)
+                emit_conv(f"{p}.cv3.{l}.1", u1_loc, (u2, 0, cc), 3, 1, True)
                 if fuse_head and nc <= 256:
                     dist = P.new_buf(hh, ww, 8)                       # 4 fp32 per pixel
                     clsb = P.new_buf(hh, ww, 4)                       # 2 fp32 per pixel
@@ -275,7 +296,8 @@ class Engine:
         _lib.require_cuda()
         self.lib = _lib.load()
         self.spec, self.B, self.H, self.W = spec, int(batch), int(H), int(W)
-        self.plan = lower(spec, state_dict, H, W, fuse_head=fuse_head)
+        # B2_MERGE_HEAD=0: keep Detect's first box / class convs as two launches (A/B experiments)
+        self.plan = lower(spec, state_dict, H, W, fuse_head=fuse_head, merge_head=os.environ.get("B2_MERGE_HEAD", "1") != "0")
         self.fused_head = self.plan.levels[0][0] < 0
         words = self.plan.words()
         blob = self.plan.blob.bytes()
