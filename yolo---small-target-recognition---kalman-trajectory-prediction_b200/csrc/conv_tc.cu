@@ -1350,6 +1350,11 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     if (const char* gv = getenv("B2_CONV_GRID")) { const int gcap = atoi(gv); if (gcap > 0 && gcap < L->grid) L->grid = gcap; }   // experiments only
 
     // ---- tensor maps ---------------------------------------------------------------------------------
+    CUtensorMapL2promotion a_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* pv = getenv("B2_CONV_L2PROMO")) {      // experiments only: 0 none, 1 64 B, 2 128 B, 3 256 B
+        const int v = atoi(pv);
+        a_promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : a_promo;
+    }
     const int nmaps = stride == 1 ? 1 : 4;
     for (int si = 0; si < p.nseg; ++si) {
         Seg& s = p.seg[si];
@@ -1366,7 +1371,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
             const cuuint32_t box[5] = {(cuuint32_t)s.bk, 2, (cuuint32_t)(p.TW / 2), 2, (cuuint32_t)(p.TH / 2)};
             const cuuint32_t es[5] = {1, 1, 1, 1, 1};
             CUresult r = encode(&s.tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, es,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, a_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(A upsampled, seg %d) failed with %d", si, (int)r); return B2_ERR_UNSUPPORTED; }
         } else {
             // A maps: (C, W', H', B) views of the NHWC input
@@ -1387,7 +1392,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
                     ptr = base + ((size_t)ph * W + pw_) * cs2;
                 }
                 CUresult r = encode(&s.tmA[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, a_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(A, seg %d map %d) failed with %d", si, m, (int)r); return B2_ERR_CUDA; }
             }
         }
