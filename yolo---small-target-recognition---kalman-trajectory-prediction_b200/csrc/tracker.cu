@@ -450,8 +450,69 @@ __device__ void analyze_slot(const Bank& b, int g) {
     FF(b, PCONF, g) = stab * fminf((float)n / 30.f, 1.f);
 }
 
+// The same analysis by one warp (lane <-> ring entry, two entries per lane): the serial form walks the 50-entry ring three
+// times with dependent global loads -- ~100 k cycles for ONE matched track, and every 256-slot sweep of finish_kernel that
+// held a matched track waited for it.  Sums become shuffle trees (fp32, different summation order than the serial loop:
+// within the 2e-4 / 1e-3 gates of tests/test_gpu_tracker.py against the float64 reference).
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ void analyze_slot_warp(const Bank& b, int g, int lane) {
+    const int n = II(b, NVEL, g);
+    if (n < 5) return;                                      // uniform: every lane reads the same slot
+    const int head = II(b, VHEAD, g);
+    int start = head - n; if (start < 0) start += kVelRing;
+    float vx[2], vy[2]; bool ok[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int k = lane + 32 * e;                        // chronological index
+        ok[e] = k < n;
+        int r = start + k; if (r >= kVelRing) r -= kVelRing;
+        vx[e] = ok[e] ? b.vel[(size_t)(2 * r) * b.N + g] : 0.f;
+        vy[e] = ok[e] ? b.vel[(size_t)(2 * r + 1) * b.N + g] : 0.f;
+    }
+    const float mx = warp_sum(vx[0] + vx[1]) / n, my = warp_sum(vy[0] + vy[1]) / n;
+    float qx = 0.f, qy = 0.f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) if (ok[e]) { const float dx = vx[e] - mx, dy = vy[e] - my; qx += dx * dx; qy += dy * dy; }
+    const float sdx = sqrtf(warp_sum(qx) / n), sdy = sqrtf(warp_sum(qy) / n);
+    const float PI = 3.14159265358979323846f;
+    float ang[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) ang[e] = ok[e] ? atan2f(vy[e], vx[e]) : 0.f;
+    // angle of the chronologically previous entry: lane - 1 of the same half, or lane 31 of the first half for entry 32
+    const float up0 = __shfl_up_sync(0xffffffffu, ang[0], 1), up1 = __shfl_up_sync(0xffffffffu, ang[1], 1);
+    const float last0 = __shfl_sync(0xffffffffu, ang[0], 31);
+    const float prev[2] = {up0, lane == 0 ? last0 : up1};
+    float c[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int k = lane + 32 * e;
+        float d = ang[e] - prev[e];
+        if (!(fabsf(d) < PI)) d = d - 2.f * PI * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        c[e] = (ok[e] && k > 0) ? d : 0.f;
+    }
+    const float dmean = warp_sum(c[0] + c[1]) / (n - 1);
+    float qv = 0.f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) { const int k = lane + 32 * e; if (ok[e] && k > 0) { const float t = c[e] - dmean; qv += t * t; } }
+    const float dstd = sqrtf(warp_sum(qv) / (n - 1));
+    if (lane == 0) {
+        const float speed_stab = 1.f / (1.f + (sdx + sdy) / 2.f);
+        const float dir_cons = 1.f / (1.f + dstd * 10.f);
+        const float stab = (speed_stab + dir_cons) / 2.f;
+        FF(b, VAVGX, g) = mx; FF(b, VAVGY, g) = my;
+        FF(b, SPEED, g) = sqrtf(mx * mx + my * my);
+        FF(b, DIRN, g) = atan2f(my, mx);
+        FF(b, STAB, g) = stab;
+        FF(b, PCONF, g) = stab * fminf((float)n / 30.f, 1.f);
+    }
+}
+
 // Kalman update with measurement z = bbox_to_state(det)  (:249-297)
-__device__ __forceinline__ void update_slot(const Bank& b, int g, const float4& d) {
+__device__ __forceinline__ void update_slot(const Bank& b, int g, const float4& d, bool analyze = true) {
     II(b, TSU, g) = 0; II(b, HITS, g) += 1; II(b, STREAK, g) += 1;
     if (II(b, ISLOST, g)) { II(b, ISLOST, g) = 0; II(b, LOSTF, g) = 0; }
     const float z0 = (d.x + d.z) / 2.f, z1 = (d.y + d.w) / 2.f, z2 = d.z - d.x, z3 = d.w - d.y;
@@ -479,7 +540,7 @@ __device__ __forceinline__ void update_slot(const Bank& b, int g, const float4& 
     II(b, VHEAD, g) = head + 1 == kVelRing ? 0 : head + 1;
     II(b, NVEL, g) = min(II(b, NVEL, g) + 1, kVelRing);
     push_traj(b, g, FF(b, X0, g), FF(b, X1, g));
-    analyze_slot(b, g);
+    if (analyze) analyze_slot(b, g);
 }
 
 // AircraftKalmanTracker.__init__ (:23-101)
@@ -543,7 +604,14 @@ __device__ void emit_slot(const Bank& b, int g, float* row, float* traj_out, int
     }
 }
 
-constexpr int kFinishThreads = 256;
+constexpr int kFinishThreads = 512;
+
+// n staged rows (80 bytes each, contiguous) -> global, 16 bytes per thread and step
+__device__ __forceinline__ void flush_rows(const float* s_rows, float* dst, int n, int tid) {
+    const float4* src4 = reinterpret_cast<const float4*>(s_rows);
+    float4* dst4 = reinterpret_cast<float4*>(dst);
+    for (int i = tid; i < n * (B2_TRACK_COLS / 4); i += kFinishThreads) dst4[i] = src4[i];
+}
 
 // One CTA per stream: update / mark lost / delete / emit for existing tracks (slot order), then create.
 __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
@@ -551,28 +619,30 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const Bank b, co
                                                                int32_t* __restrict__ out_counts, float* __restrict__ out_traj,
                                                                int32_t* __restrict__ out_traj_len) {
     __shared__ int s_warp[32];
-    __shared__ int s_emit_base, s_free_base, s_created;
+    __shared__ int s_emit_base, s_free_base, s_created, s_an;
+    __shared__ int s_alist[kMaxDetsSmem];                  // slots updated this frame (<= detections of the stream)
+    __shared__ __align__(16) float s_rows[kFinishThreads * B2_TRACK_COLS];   // emitted rows of one sweep
     __shared__ long long s_stats[6];
     const int s = blockIdx.x, tid = threadIdx.x;
     const int g0 = s * b.C;
     const int D = min(det_counts[s], b.max_dets);
-    if (tid == 0) { s_emit_base = 0; s_free_base = 0; s_created = 0; }
+    if (tid == 0) { s_emit_base = 0; s_free_base = 0; s_created = 0; s_an = 0; }
     if (tid < 6) s_stats[tid] = 0;
     const int frame = b.frame_count[s] + 1;
     __syncthreads();
     int terminated = 0, recoveries = 0, long_term = 0;
     float* rows = out_rows + (size_t)s * b.C * B2_TRACK_COLS;
 
-    // ---- pass 1: existing tracks ----
+    // ---- pass 1a: existing tracks: Kalman update / mark lost / delete; matched slots are listed for the motion analysis ----
     for (int base = 0; base < b.C; base += kFinishThreads) {
         const int t = base + tid, g = g0 + t;
-        int emit = 0;
         if (t < b.C && II(b, ID, g) != 0) {
             const int m = b.match[g];
             if (m >= 0) {
                 if (II(b, ISLOST, g)) recoveries++;
                 const float* r = dets + ((size_t)s * b.max_dets + m) * det_cols;
-                update_slot(b, g, make_float4(r[0], r[1], r[2], r[3]));
+                update_slot(b, g, make_float4(r[0], r[1], r[2], r[3]), false);
+                s_alist[atomicAdd(&s_an, 1)] = t;
             } else {                                           // mark_as_lost (:299-317)
                 if (!II(b, ISLOST, g)) { II(b, ISLOST, g) = 1; II(b, LOSTF, g) = 0; }
                 II(b, LOSTF, g) += 1; II(b, STREAK, g) = 0;
@@ -580,18 +650,32 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const Bank b, co
             const int tsu = II(b, TSU, g), age = II(b, AGE, g), hs = II(b, STREAK, g);
             const bool del = tsu > b.max_lost || (age < 5 && hs == 0 && tsu > 15) || (age < 10 && hs <= 1 && tsu > 30);   // :385-405
             if (del) { II(b, ID, g) = 0; terminated++; }
-            else emit = (hs >= b.min_hits || frame <= b.min_hits || II(b, ISLOST, g)) ? 1 : 0;   // multi_target_tracker.py:117-126
         }
+    }
+    __syncthreads();
+    // ---- pass 1b: motion analysis of the updated tracks, one warp per track (analyze_slot_warp) ----
+    for (int i = tid >> 5; i < s_an; i += kFinishThreads / 32) analyze_slot_warp(b, g0 + s_alist[i], tid & 31);
+    __syncthreads();
+    // ---- pass 1c: emit in slot order ----
+    for (int base = 0; base < b.C; base += kFinishThreads) {
+        const int t = base + tid, g = g0 + t;
+        int emit = 0;
+        if (t < b.C && II(b, ID, g) != 0)
+            emit = (II(b, STREAK, g) >= b.min_hits || frame <= b.min_hits || II(b, ISLOST, g)) ? 1 : 0;   // multi_target_tracker.py:117-126
         int total;
         const int off = block_exclusive_scan(emit, s_warp, &total);
+        const int ebase = s_emit_base;
         if (emit) {
-            const int pos = s_emit_base + off;
-            emit_slot(b, g, rows + (size_t)pos * B2_TRACK_COLS,
+            // the row goes to shared memory: the emitted rows of a sweep are contiguous in the output, so the block writes
+            // them with coalesced 16-byte stores instead of twenty 4-byte stores per thread at an 80-byte stride
+            const int pos = ebase + off;
+            emit_slot(b, g, s_rows + off * B2_TRACK_COLS,
                       out_traj ? out_traj + ((size_t)s * b.C + pos) * kTraj * 2 : nullptr,
                       out_traj_len ? out_traj_len + (size_t)s * b.C + pos : nullptr, t, &long_term);
         }
         __syncthreads();
-        if (tid == 0) s_emit_base += total;
+        flush_rows(s_rows, rows + (size_t)ebase * B2_TRACK_COLS, total, tid);
+        if (tid == 0) s_emit_base = ebase + total;
         __syncthreads();
     }
 
@@ -641,14 +725,16 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const Bank b, co
                 const int emit = (t < b.C && II(b, ID, g) != 0 && b.match[g] == -3) ? 1 : 0;
                 int total;
                 const int off = block_exclusive_scan(emit, s_warp, &total);
+                const int ebase = s_emit_base;
                 if (emit) {
-                    const int pos = s_emit_base + off;
-                    emit_slot(b, g, rows + (size_t)pos * B2_TRACK_COLS,
+                    const int pos = ebase + off;
+                    emit_slot(b, g, s_rows + off * B2_TRACK_COLS,
                               out_traj ? out_traj + ((size_t)s * b.C + pos) * kTraj * 2 : nullptr,
                               out_traj_len ? out_traj_len + (size_t)s * b.C + pos : nullptr, t, &long_term);
                 }
                 __syncthreads();
-                if (tid == 0) s_emit_base += total;
+                flush_rows(s_rows, rows + (size_t)ebase * B2_TRACK_COLS, total, tid);
+                if (tid == 0) s_emit_base = ebase + total;
                 __syncthreads();
             }
         }
