@@ -304,37 +304,41 @@ __device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
     return r;
 }
 
-// One CTA per (image, 8-channel chunk): the whole H x W map of that chunk sits in shared memory; each MaxPool2d(5,1,2)
-// is a row pass then a column pass (2 x 4 comparisons per pixel instead of 24), chained three times.
-__global__ void __launch_bounds__(256) sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int cstride, int coff, int C) {
-    extern __shared__ uint4 s_pool[];              // [2][H*W]
-    const int ck = blockIdx.x, b = blockIdx.y, HW = H * W;
+// One CTA per (image, group of CK 8-channel chunks): the whole H x W map of the group sits in shared memory, pixel-major with
+// the CK chunks of a pixel adjacent (global accesses are CK * 16 contiguous bytes per pixel instead of one 16-byte piece per
+// 2 KB); each MaxPool2d(5,1,2) is a row pass then a column pass (2 x 4 comparisons per pixel instead of 24), chained three times.
+__global__ void __launch_bounds__(256) sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int cstride, int coff, int C, int CK) {
+    extern __shared__ uint4 s_pool[];              // [2][H*W*CK]
+    const int b = blockIdx.y, HW = H * W, n = HW * CK;
     uint4* cur = s_pool;
-    uint4* tmp = s_pool + HW;
-    __nv_bfloat16* base = buf + (size_t)b * HW * cstride + coff + ck * 8;
-    for (int p = threadIdx.x; p < HW; p += blockDim.x) cur[p] = *reinterpret_cast<const uint4*>(base + (size_t)p * cstride);
+    uint4* tmp = s_pool + n;
+    __nv_bfloat16* base = buf + (size_t)b * HW * cstride + coff + blockIdx.x * CK * 8;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const int p = q / CK, c = q - p * CK;
+        cur[q] = *reinterpret_cast<const uint4*>(base + (size_t)p * cstride + c * 8);
+    }
     __syncthreads();
+    const int rw = W * CK;                         // one image row in staged elements
     for (int level = 1; level <= 3; ++level) {
-        for (int p = threadIdx.x; p < HW; p += blockDim.x) {      // row pass: max over x-2..x+2
-            const int x = p % W, r0 = p - x;
-            uint4 m = cur[p];
-            if (x >= 1) m = max_bf16x8(m, cur[p - 1]);
-            if (x >= 2) m = max_bf16x8(m, cur[p - 2]);
-            if (x + 1 < W) m = max_bf16x8(m, cur[p + 1]);
-            if (x + 2 < W) m = max_bf16x8(m, cur[p + 2]);
-            (void)r0;
-            tmp[p] = m;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {      // row pass: max over x-2..x+2
+            const int x = (q / CK) % W;
+            uint4 m = cur[q];
+            if (x >= 1) m = max_bf16x8(m, cur[q - CK]);
+            if (x >= 2) m = max_bf16x8(m, cur[q - 2 * CK]);
+            if (x + 1 < W) m = max_bf16x8(m, cur[q + CK]);
+            if (x + 2 < W) m = max_bf16x8(m, cur[q + 2 * CK]);
+            tmp[q] = m;
         }
         __syncthreads();
-        for (int p = threadIdx.x; p < HW; p += blockDim.x) {      // column pass: max over y-2..y+2
-            const int y = p / W;
-            uint4 m = tmp[p];
-            if (y >= 1) m = max_bf16x8(m, tmp[p - W]);
-            if (y >= 2) m = max_bf16x8(m, tmp[p - 2 * W]);
-            if (y + 1 < H) m = max_bf16x8(m, tmp[p + W]);
-            if (y + 2 < H) m = max_bf16x8(m, tmp[p + 2 * W]);
-            cur[p] = m;
-            *reinterpret_cast<uint4*>(base + (size_t)p * cstride + (size_t)level * C) = m;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {      // column pass: max over y-2..y+2
+            const int p = q / CK, c = q - p * CK, y = p / W;
+            uint4 m = tmp[q];
+            if (y >= 1) m = max_bf16x8(m, tmp[q - rw]);
+            if (y >= 2) m = max_bf16x8(m, tmp[q - 2 * rw]);
+            if (y + 1 < H) m = max_bf16x8(m, tmp[q + rw]);
+            if (y + 2 < H) m = max_bf16x8(m, tmp[q + 2 * rw]);
+            cur[q] = m;
+            *reinterpret_cast<uint4*>(base + (size_t)p * cstride + (size_t)level * C + c * 8) = m;
         }
         __syncthreads();
     }
@@ -430,10 +434,13 @@ extern "C" int b2_stem_f32(const void* bchw, int dtype, int B, int H, int W, con
 
 extern "C" int b2_sppf_pool(void* buf, int B, int H, int W, int cstride, int coff, int C, void* stream) {
     B2_REQUIRE(C % 8 == 0 && cstride % 8 == 0 && coff % 8 == 0 && coff + 4 * C <= cstride, "sppf_pool: bad channel layout");
-    const size_t smem = (size_t)2 * H * W * sizeof(uint4);
+    // chunks per CTA: 64 contiguous bytes per pixel when the map and the chunk count allow it
+    int CK = 4;
+    while (CK > 1 && ((C / 8) % CK != 0 || (size_t)2 * H * W * CK * sizeof(uint4) > 96 * 1024)) CK >>= 1;
+    const size_t smem = (size_t)2 * H * W * CK * sizeof(uint4);
     B2_REQUIRE(smem <= 200 * 1024, "sppf_pool: %dx%d map does not fit in shared memory", H, W);
-    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sppf_pool_kernel<<<dim3(C / 8, B), 256, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, B, H, W, cstride, coff, C);
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    sppf_pool_kernel<<<dim3(C / 8 / CK, B), 256, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, B, H, W, cstride, coff, C, CK);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
