@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--ref-streams", type=int, default=2, help="streams per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch table of the forward to this JSON file")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's local CPU cores")
     ap.add_argument("--no-overlap", action="store_true", help="run NMS + tracker on the forward's stream (no cross-step overlap)")
     ap.add_argument("--no-kernels", action="store_true", help="skip the stand-alone HBM-kernel measurements")
     return ap.parse_args()
@@ -305,7 +306,10 @@ def run_b200(a):
 
     import b200dt  # noqa: F401
     from b200dt import _lib
-    from b200dt.pipeline import DetectTrackPipeline, gather_results
+    from b200dt.pipeline import DetectTrackPipeline, bind_host_to_gpu, gather_results
+
+    if not a.no_numa_bind:
+        bind_host_to_gpu(local)          # before any pinned allocation
 
     pk = peaks()
     S = a.streams
