@@ -1232,10 +1232,11 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
         size_t w_all = 0;
         for (int si = 0; si < p.nseg; ++si) w_all += (size_t)taps * p.seg[si].kchunks * up1k((size_t)cout16 * p.seg[si].bk * 2);
         const size_t a2 = up1k((size_t)(p.TW + 2) * (p.TH + 2) * bk_max * 2);
-        int halo2_mode = 1;
+        int halo2_mode = 2;       // 1: only with three box stages (the rule before the two-stage plans were measured)
         if (const char* hv = getenv("B2_CONV_HALO2")) halo2_mode = atoi(hv);
-        // three box stages, or two when the weights leave no room for a third (64 -> 144 at P2: a stage is a whole tile here,
-        // so two stages still overlap the loads of tile i+1 with the MMAs of tile i)
+        // three box stages, or two when the weights leave no room for a third (64 -> 144 at P2, 162 KB of weights: with two
+        // issuing warps and a one-stage ring each, ring B loads tile i+1 while warp A works on tile i -- 0.69 ms against 0.77 ms
+        // for the streamed-weight plan, tools/conv_bench.py)
         const size_t min_stages = halo2_mode >= 2 ? 2 : 3;
         if (halo2_mode && w_all + min_stages * a2 <= kOneCtaSmem) { p.halo = 2; a_rows = (p.TW + 2) * (p.TH + 2); p.a_bytes = (uint32_t)a2; }
     }
@@ -1310,7 +1311,8 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     if (const char* mv = getenv("B2_CONV_MMAW")) mmaw = atoi(mv);
     // measured: pays on the resident-weight single-box layers that run one CTA per SM (one issuing stream per SM otherwise);
     // streamed-weight layers lose more from the halved look-ahead of each ring than they gain
-    p.mma_warps = (mmaw >= 2 && stages >= 4 && p.halo >= 2 && ctas == 1) ? 2 : 1;
+    // (a ring of ONE stage per issuing warp still double-buffers: ring B loads tile i+1 while warp A works on tile i)
+    p.mma_warps = (mmaw >= 2 && (stages >= 4 || (p.halo == 2 && stages == 2)) && p.halo >= 2 && ctas == 1) ? 2 : 1;
     if (p.mma_warps == 2) stages &= ~1;
     p.num_stages = stages;
     p.epi_warps = 8;
