@@ -233,6 +233,52 @@ def gold_predict():
     np.savez_compressed(os.path.join(HERE, "predict_n_p2.npz"), **out)
 
 
+def motion_reset_script(n=140, seed=11):
+    """One target: smooth drift, a 70 px jump (camera shake), a second jump inside the cooldown, a size jump, two detection
+    gaps (one of them right after a reset), noise of 0.5 px.  Returns a list of bbox-or-None per frame."""
+    rng = np.random.default_rng(seed)
+    cx, cy, w, h = 120.0, 90.0, 14.0, 10.0
+    out = []
+    for t in range(n):
+        cx += 1.5; cy += 0.7
+        if t == 30: cx += 70.0                       # position jump
+        if t == 36: cy -= 55.0                       # inside the cooldown of the first reset
+        if t == 60: w *= 1.6; h *= 1.5               # size jump
+        if t == 85: cx -= 48.0; cy += 30.0           # jump + velocity change
+        if t == 110: cx += 200.0                     # large jump (factor capped at 2)
+        miss = (44 <= t < 49) or (86 <= t < 90) or (t % 23 == 22)
+        n4 = rng.normal(0.0, 0.5, 4)
+        out.append(None if miss else [float(cx - w / 2 + n4[0]), float(cy - h / 2 + n4[1]), float(cx + w / 2 + n4[2]), float(cy + h / 2 + n4[3])])
+    return out
+
+
+def gold_motion_reset():
+    """camera_motion_compensation/motion_reset_kalman_tracker.py driven frame by frame the way the multi-tracker drives a
+    track: predict(); update(det) or mark_as_lost(); get_track_info()."""
+    sys.path.insert(0, REF)
+    from camera_motion_compensation.motion_reset_kalman_tracker import MotionResetKalmanTracker
+
+    script = motion_reset_script()
+    rows = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        trk = MotionResetKalmanTracker(script[0], track_id="T001", max_lost_frames=150)
+        for det in script[1:]:
+            pb = np.asarray(trk.predict(), np.float64)
+            if det is not None:
+                trk.update(det)
+            else:
+                trk.mark_as_lost()
+            info = trk.get_track_info()
+            rows.append(np.concatenate([pb, trk.x, trk.P.ravel(), np.asarray(info["bbox"], np.float64),
+                                        [info["confidence"], trk.reset_count, trk.last_reset_frame, trk.age, trk.hits, trk.hit_streak,
+                                         trk.time_since_update, float(trk.is_lost), trk.lost_frames, trk.motion_consistency,
+                                         len(trk.position_history), len(trk.motion_scores), info["frames_since_reset"]]]))
+    rows = np.array(rows)
+    np.savez_compressed(os.path.join(HERE, "motion_reset.npz"), rows=rows,
+                        dets=np.array([d if d is not None else [np.nan] * 4 for d in script]))
+    print("motion_reset", rows.shape, "resets", int(rows[-1, 4 + 8 + 64 + 4 + 1]))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tracker", "kf", "nms", "net", "predict"]
     for w in which:

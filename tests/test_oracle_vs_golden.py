@@ -212,3 +212,31 @@ def test_predict_end_to_end_matches_reference(tag, hw, mode):
             if len(c) and np.min(np.abs(c[:, :4] - r[:4]).max(1) + np.abs(c[:, 4] - r[4])) < 5e-2:
                 matched += 1
         assert matched >= len(ref) - 3
+
+
+# ----------------------------------------------------------------------------- N1: motion-reset tracker
+def test_motion_reset_track_matches_reference():
+    """oracle.motion_reset.MotionResetTrack against camera_motion_compensation/motion_reset_kalman_tracker.py driven
+    frame by frame (predict; update or mark_as_lost; get_track_info) over a script with jumps, a size change and gaps."""
+    from oracle.motion_reset import MotionResetTrack
+
+    g = _load("motion_reset.npz")
+    dets, rows = g["dets"], g["rows"]
+    trk = MotionResetTrack([float(v) for v in dets[0]], "T001", 150)
+    assert int(rows[-1, 4 + 8 + 64 + 4 + 1]) >= 3                      # the script does trigger resets
+    for t in range(1, len(dets)):
+        pb = np.asarray(trk.predict(), np.float64)
+        if np.isnan(dets[t][0]):
+            trk.mark_lost()
+        else:
+            trk.update([float(v) for v in dets[t]])
+        info = trk.info()
+        r = rows[t - 1]
+        np.testing.assert_allclose(pb, r[0:4], rtol=1e-12, atol=1e-9, err_msg=f"predict() frame {t}")
+        np.testing.assert_allclose(trk.x, r[4:12], rtol=1e-12, atol=1e-9, err_msg=f"x frame {t}")
+        np.testing.assert_allclose(trk.P.ravel(), r[12:76], rtol=1e-11, atol=1e-9, err_msg=f"P frame {t}")
+        np.testing.assert_allclose(np.asarray(info["bbox"], np.float64), r[76:80], rtol=1e-12, atol=1e-9, err_msg=f"bbox frame {t}")
+        got = [info["confidence"], trk.reset_count, trk.last_reset_frame, trk.age, trk.hits, trk.hit_streak, trk.time_since_update,
+               float(trk.is_lost), trk.lost_frames, trk.motion_consistency, len(trk.position_history), len(trk.motion_scores),
+               info["frames_since_reset"]]
+        np.testing.assert_allclose(got, r[80:93], rtol=1e-12, atol=1e-12, err_msg=f"scalars frame {t}")
