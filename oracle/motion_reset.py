@@ -160,3 +160,79 @@ class MotionResetTrack(Track):
         d["frames_since_reset"] = self.age - self.last_reset_frame
         d["motion_consistency"] = self.motion_consistency
         return d
+
+
+# ------------------------------------------------------------------------------------------------
+# camera_motion_compensation/motion_compensated_multi_tracker.py (:18-394), the path taken when no frame is passed
+# (global motion detection needs the optical-flow GlobalMotionDetector, global_motion_detector.py: not restated).
+# Differences from the hot path's EnhancedMultiTargetTracker that matter for parity:
+#   * its own association (:240-283): candidates iou > thr (strict), sorted as (iou, d, t) tuples in DESCENDING order, so
+#     exact ties go to the larger detection index, then the larger tracker index;
+#   * tracks are MotionResetKalmanTrackers created with track_id=None (random uuid ids in the reference: compare by list
+#     position); every live track is reported (no min_hits gate);
+#   * stats: individual_resets (+1 per matched update that reset), tracking_recoveries (+1 per deleted track that had reset).
+# ------------------------------------------------------------------------------------------------
+def _iou(a, b):
+    x1, y1, x2, y2 = max(a[0], b[0]), max(a[1], b[1]), min(a[2], b[2]), min(a[3], b[3])
+    if x2 <= x1 or y2 <= y1:
+        return 0.0
+    inter = (x2 - x1) * (y2 - y1)
+    union = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+    return 0.0 if union <= 0 else inter / union
+
+
+class MotionCompensatedMultiTracker:
+    def __init__(self, max_lost_frames=150, min_hits=1, iou_threshold=0.1):
+        self.max_lost_frames, self.min_hits, self.iou_threshold = max_lost_frames, min_hits, iou_threshold
+        self.trackers = []
+        self.frame_count = 0
+        self.stats = {"total_frames": 0, "individual_resets": 0, "tracking_recoveries": 0}
+        self._next = 1
+
+    def _new(self, bbox):
+        t = MotionResetTrack(bbox, f"N{self._next:04d}", self.max_lost_frames)
+        self._next += 1
+        return t
+
+    def associate(self, dets, preds):                     # :240-283
+        if len(dets) == 0:
+            return [], [], list(range(len(preds)))
+        if len(preds) == 0:
+            return [], list(range(len(dets))), []
+        cand = []
+        for d, det in enumerate(dets):
+            for t, p in enumerate(preds):
+                v = _iou(det[:4], p)
+                if v > self.iou_threshold:
+                    cand.append((v, d, t))
+        cand.sort(reverse=True)
+        used_d, used_t, matched = set(), set(), []
+        for _, d, t in cand:
+            if d not in used_d and t not in used_t:
+                matched.append([d, t]); used_d.add(d); used_t.add(t)
+        return matched, [d for d in range(len(dets)) if d not in used_d], [t for t in range(len(preds)) if t not in used_t]
+
+    def update(self, detections):                         # :76-117 (frame is None) + :168-238
+        self.frame_count += 1
+        self.stats["total_frames"] += 1
+        preds = [t.predict() for t in self.trackers]
+        if len(detections) > 0 and len(self.trackers) > 0:
+            matched, um_d, um_t = self.associate(detections, preds)
+        else:
+            matched, um_d, um_t = [], list(range(len(detections))), list(range(len(self.trackers)))
+        for d, t in matched:
+            before = self.trackers[t].reset_count
+            self.trackers[t].update(detections[d][:4])
+            self.stats["individual_resets"] += int(self.trackers[t].reset_count > before)
+        for t in um_t:
+            self.trackers[t].mark_lost()
+        for d in um_d:
+            self.trackers.append(self._new(detections[d][:4]))
+        keep = []
+        for t in self.trackers:
+            if t.should_delete(self.max_lost_frames):
+                self.stats["tracking_recoveries"] += int(t.reset_count > 0)
+            else:
+                keep.append(t)
+        self.trackers = keep
+        return [t.info() for t in self.trackers]

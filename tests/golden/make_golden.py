@@ -279,6 +279,54 @@ def gold_motion_reset():
     print("motion_reset", rows.shape, "resets", int(rows[-1, 4 + 8 + 64 + 4 + 1]))
 
 
+def motion_multi_script(n=160, seed=21):
+    """Multi-target detections (synth.DetectionSequence) with camera shakes: at a few frames every detection of the frame and of
+    all later frames is shifted by a common offset (what a panning / shaking camera does), python floats."""
+    seq = synth.DetectionSequence(seed=seed, n_targets=6, p_detect=0.9, clutter=0.15, burst=(70, 85))
+    # boxes are blown up 3x (12..72 px) so that a 45 px shake still overlaps the predicted box (IoU > 0.1: the track is matched
+    # and its jump detector fires) while smaller ones lose the association and found new tracks
+    shakes = {25: (45.0, 0.0), 26: (10.0, -8.0), 60: (-32.0, 34.0), 95: (0.0, 44.0), 130: (-43.0, -10.0), 132: (-6.0, 2.0)}
+    off = np.zeros(2)
+    out = []
+    for t in range(n):
+        if t in shakes:
+            off = off + np.array(shakes[t])
+        d = seq.step().astype(np.float64)
+        if len(d):
+            cx, cy = (d[:, 0] + d[:, 2]) / 2, (d[:, 1] + d[:, 3]) / 2
+            hw, hh = 1.5 * (d[:, 2] - d[:, 0]), 1.5 * (d[:, 3] - d[:, 1])
+            if t == 100:
+                hw, hh = hw * 1.5, hh * 1.5                      # zoom: size-change detector
+            d[:, 0], d[:, 2] = cx - hw + off[0], cx + hw + off[0]
+            d[:, 1], d[:, 3] = cy - hh + off[1], cy + hh + off[1]
+        out.append([[float(v) for v in r] for r in d])
+    return out
+
+
+def gold_motion_multi():
+    """camera_motion_compensation/motion_compensated_multi_tracker.py, update(detections) without a frame."""
+    sys.path.insert(0, REF)
+    from camera_motion_compensation.motion_compensated_multi_tracker import MotionCompensatedMultiTracker
+
+    script = motion_multi_script()
+    rows, counts = [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        trk = MotionCompensatedMultiTracker(150, 1, 0.1)
+        for dets in script:
+            res = trk.update([list(r) for r in dets])
+            assert len(res) == len(trk.trackers)
+            counts.append(len(res))
+            for info, t in zip(res, trk.trackers):
+                rows.append(np.concatenate([np.asarray(info["bbox"], np.float64), t.x, [info["confidence"], t.reset_count, t.age, t.hits,
+                                            t.hit_streak, t.time_since_update, float(t.is_lost), t.lost_frames, t.motion_consistency,
+                                            info["frames_since_reset"]]]))
+    stats = [trk.stats["total_frames"], trk.stats["individual_resets"], trk.stats["tracking_recoveries"], trk.stats["global_resets"]]
+    flat = np.array([[v for r in dets for v in r] + [np.nan] * (5 * 16 - 5 * len(dets)) for dets in script])
+    np.savez_compressed(os.path.join(HERE, "motion_multi.npz"), rows=np.array(rows), counts=np.array(counts), stats=np.array(stats),
+                        dets=flat, ndets=np.array([len(d) for d in script]))
+    print("motion_multi", np.array(rows).shape, "stats", stats, "max tracks", max(counts))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tracker", "kf", "nms", "net", "predict"]
     for w in which:

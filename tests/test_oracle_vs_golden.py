@@ -240,3 +240,27 @@ def test_motion_reset_track_matches_reference():
                float(trk.is_lost), trk.lost_frames, trk.motion_consistency, len(trk.position_history), len(trk.motion_scores),
                info["frames_since_reset"]]
         np.testing.assert_allclose(got, r[80:93], rtol=1e-12, atol=1e-12, err_msg=f"scalars frame {t}")
+
+
+def test_motion_compensated_multi_tracker_matches_reference():
+    """oracle.motion_reset.MotionCompensatedMultiTracker against camera_motion_compensation/motion_compensated_multi_tracker.py
+    (update without a frame) on 160 frames of multi-target detections with camera shakes: same number of live tracks every
+    frame, same per-track state in list order (the reference's ids are random uuids), same reset / recovery counters."""
+    from oracle.motion_reset import MotionCompensatedMultiTracker
+
+    g = _load("motion_multi.npz")
+    dets, ndets, rows, counts, stats = g["dets"], g["ndets"], g["rows"], g["counts"], g["stats"]
+    assert stats[1] >= 5                                                    # the script triggers individual resets
+    trk = MotionCompensatedMultiTracker(150, 1, 0.1)
+    k = 0
+    for f in range(len(ndets)):
+        d = [[float(v) for v in dets[f, 5 * i:5 * i + 5]] for i in range(int(ndets[f]))]
+        res = trk.update(d)
+        assert len(res) == counts[f], f"frame {f}"
+        for info, t in zip(res, trk.trackers):
+            got = np.concatenate([np.asarray(info["bbox"], np.float64), t.x, [info["confidence"], t.reset_count, t.age, t.hits, t.hit_streak,
+                                  t.time_since_update, float(t.is_lost), t.lost_frames, t.motion_consistency, info["frames_since_reset"]]])
+            np.testing.assert_allclose(got, rows[k], rtol=1e-11, atol=1e-8, err_msg=f"frame {f} track {t.track_id}")
+            k += 1
+    assert k == len(rows)
+    assert [trk.stats["total_frames"], trk.stats["individual_resets"], trk.stats["tracking_recoveries"]] == list(stats[:3])
