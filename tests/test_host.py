@@ -180,3 +180,14 @@ def test_result_gather_over_gloo_world_size_2(tmp_path):
              for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_bind_host_to_gpu_is_harmless_without_nvml():
+    """pipeline.bind_host_to_gpu: a core list when NVML answers, None otherwise -- never raises, never empties the affinity."""
+    import os
+
+    before = os.sched_getaffinity(0)
+    got = pipeline.bind_host_to_gpu(0)
+    assert got is None or (isinstance(got, list) and len(got) > 0 and set(got) <= before)
+    assert len(os.sched_getaffinity(0)) > 0
+    os.sched_setaffinity(0, before)
