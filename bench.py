@@ -308,6 +308,7 @@ def run_b200(a):
     from b200dt import _lib
     from b200dt.pipeline import DetectTrackPipeline, bind_host_to_gpu, gather_results
 
+    affinity0 = os.sched_getaffinity(0)
     if not a.no_numa_bind:
         bind_host_to_gpu(local)          # before any pinned allocation
 
@@ -403,6 +404,7 @@ def run_b200(a):
     if world == 1 and not a.no_kernels:
         line["hbm_kernels"] = hbm_kernels(pipe, pk)
     if world == 1 and not a.no_cpu_baseline:
+        os.sched_setaffinity(0, affinity0)       # the CPU leg may use every core the process started with
         n = a.ref_streams
         cpu = CpuPath(a.model, n)
         fr = host[:, :n].numpy()
