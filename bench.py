@@ -8,7 +8,8 @@ One "step" = one frame of every resident stream through the whole per-frame path
 (uint8 frame -> stem/forward -> DFL decode -> NMS -> Kalman track bank update).
 Workload = BASELINE.json configs[3] ("C4"): 256 concurrent synthetic 640x512 IR streams, yolov8s-p2 (nc=80,
 seeded synthetic weights), predict conf=0.15 iou=0.6, EnhancedMultiTargetTracker(150, min_hits=1, iou=0.1).
-Streams are independent: each rank owns its own 256 streams (weak scaling, no data-path collective).
+Streams are independent: each rank owns its own 256 streams (weak scaling, no data-path collective); the same line
+carries a second record, "strong_scaling": BASELINE config 4 as written, 256 streams in total sharded 256/N per GPU.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -31,7 +32,16 @@ FRAME_HW = (512, 640)
 CONF, IOU = 0.15, 0.6
 TRACKER = dict(max_lost_frames=150, min_hits=1, iou_threshold=0.1)
 DISTINCT_STREAMS = 32          # distinct synthetic videos, tiled to the stream count
-POOL_FRAMES = 4                # consecutive frames per stream kept resident and cycled
+POOL_FRAMES = 6                # consecutive frames per stream kept resident, played forth and back (0..5,4..1,0..): motion
+                               # stays continuous, so tracks persist as they do on a real video
+MAX_TRACKS_OUT = 256           # rows per stream of the downloaded result block (asserted sufficient)
+
+
+def pool_index(i):
+    """Ping-pong walk over the resident frame pool."""
+    period = 2 * POOL_FRAMES - 2
+    k = i % period
+    return k if k < POOL_FRAMES else period - k
 
 
 def parse():
@@ -49,6 +59,8 @@ def parse():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's local CPU cores")
     ap.add_argument("--no-overlap", action="store_true", help="run NMS + tracker on the forward's stream (no cross-step overlap)")
     ap.add_argument("--no-kernels", action="store_true", help="skip the stand-alone HBM-kernel measurements")
+    ap.add_argument("--total-streams", type=int, default=256, help="streams of the strong-scaling record (sharded over the GPUs)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record")
     return ap.parse_args()
 
 
@@ -167,10 +179,10 @@ def run_reference(a):
     frames = make_frames(n, POOL_FRAMES)
     cpu = CpuPath(a.model, n)
     for i in range(a.warmup):
-        cpu.step(frames[i % POOL_FRAMES])
+        cpu.step(frames[pool_index(i)])
     t0 = time.perf_counter()
     for i in range(a.steps):
-        cpu.step(frames[i % POOL_FRAMES])
+        cpu.step(frames[pool_index(a.warmup + i)])
     dt = time.perf_counter() - t0
     v = n * a.steps / dt
     sample = f"{n} streams x {a.steps} frames of the 256-stream workload, oracle port (numpy + ATen conv, fp32), {cpu.cores} threads"
@@ -187,7 +199,7 @@ def workload_config(a, streams):
     return {"workload": f"C4: {streams} concurrent synthetic 640x512 IR streams per GPU, {a.model} (nc=80, seeded synthetic weights) + "
                         f"Kalman tracker bank, predict conf={CONF} iou={IOU}, tracker(150, min_hits=1, iou=0.1)",
             "streams_per_gpu": streams, "frame": "640x512x3 uint8", "model": a.model,
-            "l2": "inputs larger than L2 (252 MB of frames per step, 4-step resident pool)",
+            "l2": f"inputs larger than L2 ({streams * 640 * 512 * 3 / 1e6:.0f} MB of frames per step, {POOL_FRAMES}-frame resident pool played forth and back)",
             "pipelining": "NMS + tracker of step t on a second stream under the forward of step t+1; all K steps' work, downloads "
                           "included, is joined inside the timed region" if not getattr(a, "no_overlap", False) else "single stream"}
 
@@ -244,14 +256,14 @@ def hbm_kernels(pipe, pk):
     # NMS: latency-bound at realistic candidate counts -- report ms per batch
     ms = time_cuda(lambda: post.nms(IOU), 10, flush)
     out["nms"] = {"ms": ms, "images": pipe.S, "mean_candidates": float(post.cand_count.float().mean().item())}
-    del flush_buf
-    # Kalman bank at C3 scale: 256 streams x 4096 tracks = 1,048,576 live tracks, predict kernel
+    # Kalman bank at C3 scale (BASELINE.json configs[2]): 256 streams x 4096 live tracks = 1,048,576 tracks in a bank of
+    # 256 x 4608 slots (room for the tracks that clutter detections found), L2 flushed before every timed launch pair
     from b200dt.tracker import TrackerBank
 
-    S, C, D = 256, 4096, 1024
+    S, C, L, D = 256, 4608, 4096, 1024
     bank = TrackerBank(S, C, D, 150, 1, 0.1)
     g = torch.Generator(device="cuda").manual_seed(0)
-    for r in range(C // D):          # r-th batch of 1024 disjoint boxes per stream -> every box founds a track
+    for r in range(L // D):          # r-th batch of 1024 disjoint boxes per stream -> every box founds a track
         idx = torch.arange(D, device="cuda") + r * D
         x = (idx % 64).float() * 10.0
         y = (idx // 64).float() * 10.0
@@ -259,28 +271,41 @@ def hbm_kernels(pipe, pk):
         bank.update(boxes, torch.full((S,), D, dtype=torch.int32, device="cuda"), with_trajectory=False)
     torch.cuda.synchronize()
     live = int(bank.export(0)[3][2])
+    assert live == L
     pb, ub = TrackerBank.bytes_per_track()
-    ms = time_cuda(lambda: bank.predict_only(), 10)
-    nb = S * live * pb
-    out["kalman_predict"] = {"ms": ms, "tracks": S * live, "bytes_per_track": pb, "achieved_gbs": nb / ms / 1e6,
-                             "frac_of_hbm_peak": nb / ms / 1e6 / pk["hbm"], "tracks_per_s": S * live / ms * 1e3}
-    # full C3 frame (BASELINE.json configs[2]): 10,240 detections per frame = 40 per stream, 70 % drawn from existing
-    # tracks (+N(0,1) px), 30 % clutter; predict + IoU association + update + lifecycle + emit of all 1M tracks
-    Dn = 40
+    # (a) a frame without detections: every track coasts -- predict, mark lost, delete test, reported row: the sweep kernel
+    zero = torch.zeros((S,), dtype=torch.int32, device="cuda")
     dets = torch.zeros((S, D, 6), device="cuda")
-    pick = torch.randint(0, C, (S, Dn), device="cuda", generator=g)
+    ms = time_cuda(lambda: bank.update(dets, zero, with_trajectory=False), 10, flush)
+    nb = S * live * pb
+    out["kalman_sweep_coast"] = {"ms": ms, "tracks": S * live, "bytes_per_track": pb, "achieved_gbs": nb / ms / 1e6,
+                                 "frac_of_hbm_peak": nb / ms / 1e6 / pk["hbm"], "tracks_per_s": S * live / ms * 1e3,
+                                 "what": "1,048,576 coasting tracks: predict + lifecycle + reported row (sweep_kernel), resolve_kernel idle; "
+                                         "L2 flushed before every launch"}
+    # (b) the full C3 frame: 10,240 detections per frame = 40 per stream, 70 % drawn from existing tracks (+N(0,1) px),
+    # 30 % clutter; predict + IoU candidates + greedy association + update + lifecycle + rows of all 1M tracks
+    Dn = 40
+    pick = torch.randint(0, L, (S, Dn), device="cuda", generator=g)
     px, py = (pick % 64).float() * 10.0, (pick // 64).float() * 10.0
     clutter = torch.rand((S, Dn), device="cuda", generator=g) < 0.3
     px = torch.where(clutter, torch.rand((S, Dn), device="cuda", generator=g) * 634.0, px + torch.randn((S, Dn), device="cuda", generator=g))
     py = torch.where(clutter, torch.rand((S, Dn), device="cuda", generator=g) * 634.0, py + torch.randn((S, Dn), device="cuda", generator=g))
     dets[:, :Dn, 0], dets[:, :Dn, 1], dets[:, :Dn, 2], dets[:, :Dn, 3], dets[:, :Dn, 4] = px, py, px + 6, py + 6, 0.9
     cnt = torch.full((S,), Dn, dtype=torch.int32, device="cuda")
-    ms = time_cuda(lambda: bank.update(dets, cnt, with_trajectory=False), 10)
-    nb = S * live * (pb + 16) + S * Dn * (16 + ub)
-    out["kalman_frame_c3"] = {"ms": ms, "tracks": S * live, "detections": S * Dn, "algorithmic_bytes": nb,
+    ms = time_cuda(lambda: bank.update(dets, cnt, with_trajectory=False), 10, flush)
+    live2 = int(bank.stats_async().cpu()[:, 2].sum())
+    nb = live2 * pb + S * Dn * (16 + ub)
+    out["kalman_frame_c3"] = {"ms": ms, "tracks": live2, "detections": S * Dn, "algorithmic_bytes": nb,
                               "achieved_gbs": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / pk["hbm"],
-                              "tracks_per_s": S * live / ms * 1e3,
-                              "what": "predict + per-stream IoU association + update + lifecycle + emitted rows, 256 streams x 4096 tracks x 40 dets"}
+                              "tracks_per_s": live2 / ms * 1e3, "dropped": int(bank.stats_async().cpu()[:, 5].sum()),
+                              "what": "sweep (predict + IoU candidates + coasting tracks' rows) + resolve (greedy association, Kalman "
+                                      "update, motion analysis, new tracks), 256 streams x 4096+ tracks x 40 dets; L2 flushed"}
+    # (c) AircraftKalmanTracker.predict alone (x, P, counters, trajectory push: 35 words per track)
+    ms = time_cuda(lambda: bank.predict_only(), 10, flush)
+    nb = live2 * 35 * 4
+    out["kalman_predict_only"] = {"ms": ms, "tracks": live2, "bytes_per_track": 140, "achieved_gbs": nb / ms / 1e6,
+                                  "frac_of_hbm_peak": nb / ms / 1e6 / pk["hbm"]}
+    del flush_buf
     bank.close()
     return out
 
@@ -306,7 +331,7 @@ def run_b200(a):
 
     import b200dt  # noqa: F401
     from b200dt import _lib
-    from b200dt.pipeline import DetectTrackPipeline, bind_host_to_gpu, gather_results
+    from b200dt.pipeline import DetectTrackPipeline, bind_host_to_gpu, gather_results, shard_streams
 
     affinity0 = os.sched_getaffinity(0)
     if not a.no_numa_bind:
@@ -314,7 +339,9 @@ def run_b200(a):
 
     pk = peaks()
     S = a.streams
-    pipe = DetectTrackPipeline(a.model, S, FRAME_HW, 640, CONF, IOU, 300, capacity=a.capacity, overlap_post=not a.no_overlap, **TRACKER)
+    pipe = DetectTrackPipeline(a.model, S, FRAME_HW, 640, CONF, IOU, 300, capacity=a.capacity, overlap_post=not a.no_overlap,
+                               max_tracks_out=MAX_TRACKS_OUT, **TRACKER)
+    main_pipe = pipe
     host = torch.from_numpy(make_frames(S, POOL_FRAMES, seed0=1000 + 97 * rank)).pin_memory()
     dev = host.cuda()
     lib = _lib.load()
@@ -324,7 +351,8 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
+    def timed(step_fn, steps, pipe=None):
+        pipe = pipe or main_pipe
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -340,23 +368,54 @@ def run_b200(a):
 
     # ---- device-resident: inputs already in HBM -------------------------------------------------
     for i in range(a.warmup):
-        pipe.step_device(dev[i % POOL_FRAMES])
+        pipe.step_device(dev[pool_index(i)])
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.mark()
     l0 = lib.b2_launch_count()
-    ms_dev = timed(lambda i: pipe.step_device(dev[(a.warmup + i) % POOL_FRAMES]), a.steps)
+    ms_dev = timed(lambda i: pipe.step_device(dev[pool_index(a.warmup + i)]), a.steps)
     launches = lib.b2_launch_count() - l0
     clocks = sampler.stop() if sampler else None
     value = S * world * a.steps / ms_dev * 1e3
 
     # ---- end to end through the host-facing call: pinned host frames in, track rows out --------------
     for i in range(a.warmup):
-        pipe.step_host(host[i % POOL_FRAMES])
-    ms_e2e = timed(lambda i: pipe.step_host(host[(a.warmup + i) % POOL_FRAMES]), a.steps)
+        pipe.step_host(host[pool_index(a.warmup + a.steps + i)])
+    ms_e2e = timed(lambda i: pipe.step_host(host[pool_index(2 * a.warmup + a.steps + i)]), a.steps)
     e2e = S * world * a.steps / ms_e2e * 1e3
-    rows, counts = pipe.host_rows, pipe.host_counts
+    # the host block of the last step, after the checks that make it the reference's result: no detection was dropped for
+    # lack of a track slot (the reference's track list is unbounded) and no stream reported more rows than were downloaded
+    rows, counts = pipe.results()
+    stats = pipe.host_stats.numpy().copy()
     st = pipe.bank.export(0)[3]
+    assert int(stats[:, 5].sum()) == 0 and int(st[7]) == 0, "the track bank dropped detections: not the reference's computation"
+    n_dets = pipe.detect.post.out_count.float()
+
+    # ---- BASELINE config 4 as written: 256 streams in total, sharded 256 / N per GPU (strong scaling) ----
+    strong = None
+    if not a.no_strong:
+        total = a.total_streams
+        if world == 1 and S == total:
+            strong = {"streams_total": total, "streams_per_gpu": S, "value": value, "ms_per_step": ms_dev / a.steps,
+                      "e2e": e2e, "e2e_ms_per_step": ms_e2e / a.steps, "note": "same run as the weak-scaling record at N=1"}
+        else:
+            mine = shard_streams(total, rank, world)
+            Ss = len(mine)
+            sp = DetectTrackPipeline(a.model, Ss, FRAME_HW, 640, CONF, IOU, 300, capacity=a.capacity, overlap_post=not a.no_overlap,
+                                     max_tracks_out=MAX_TRACKS_OUT, **TRACKER)
+            sdev = dev[:, :Ss].contiguous()
+            shost = host[:, :Ss].contiguous().pin_memory()
+            for i in range(a.warmup):
+                sp.step_device(sdev[pool_index(i)])
+            ms_s = timed(lambda i: sp.step_device(sdev[pool_index(a.warmup + i)]), a.steps, sp)
+            for i in range(a.warmup):
+                sp.step_host(shost[pool_index(a.warmup + a.steps + i)])
+            ms_se = timed(lambda i: sp.step_host(shost[pool_index(2 * a.warmup + a.steps + i)]), a.steps, sp)
+            sp.results()
+            strong = {"streams_total": total, "streams_per_gpu": Ss, "value": total * a.steps / ms_s * 1e3, "ms_per_step": ms_s / a.steps,
+                      "e2e": total * a.steps / ms_se * 1e3, "e2e_ms_per_step": ms_se / a.steps,
+                      "note": "256 streams sharded contiguously over the ranks (pipeline.shard_streams); max over ranks"}
+            del sp, sdev, shost
 
     # the only collective: gather per-stream result blocks (off the data path; not in the timed region)
     if world > 1:
@@ -397,9 +456,13 @@ def run_b200(a):
         "config": workload_config(a, S), "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes_per_step, "d2h_bytes_per_step": pipe.d2h_bytes_per_step,
                 "ms_per_step": ms_e2e / a.steps},
-        "gpu_launches": int(launches), "roofline": roofline,
-        "tracks": {"active_stream0": int(st[2]), "created_stream0": int(st[0]), "dropped_no_slot_stream0": int(st[7]),
-                   "mean_emitted_per_stream": float(counts.float().mean().item())},
+        "gpu_launches": int(launches), "roofline": roofline, "strong_scaling": strong,
+        "tracks": {"active_stream0": int(st[2]), "created_stream0": int(st[0]), "dropped_no_slot_all_streams": int(stats[:, 5].sum()),
+                   "active_max_over_streams": int(stats[:, 2].max()), "recoveries_stream0": int(st[4]),
+                   "mean_emitted_per_stream": float(counts.float().mean().item()), "max_emitted_per_stream": int(counts.max().item()),
+                   "rows_downloaded_per_stream": MAX_TRACKS_OUT,
+                   "mean_detections_per_frame": float(n_dets.mean().item()), "max_detections_per_frame": int(n_dets.max().item()),
+                   "frames_per_stream": int(st[5])},
     }
     if world == 1 and not a.no_kernels:
         line["hbm_kernels"] = hbm_kernels(pipe, pk)

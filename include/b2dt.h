@@ -175,23 +175,39 @@ int b2_tracker_create(int n_streams, int capacity, int max_dets, int max_lost_fr
                       float iou_threshold, b2_tracker_t** out);
 int b2_tracker_destroy(b2_tracker_t* t);
 int b2_tracker_reset(b2_tracker_t* t, void* stream);
+/* The reference's track list is unbounded (enhanced_multi_target_tracker.py:92-101 appends); the bank is not.  A caller that
+ * sees `active + max_dets > capacity` (b2_tracker_stats / b2_tracker_export) enlarges the bank in place: every slot keeps its
+ * index, state and id.  Synchronises `stream`.  Output buffers of b2_tracker_update must be re-sized by the caller. */
+int b2_tracker_capacity(b2_tracker_t* t);
+int b2_tracker_grow(b2_tracker_t* t, int new_capacity, void* stream);
+/* Device-side snapshot of the per-stream counters, [n_streams][8] int64 {created, terminated, active, long_term_predictions,
+ * recoveries, dropped (detections that found no free slot; the reference never drops), 0, 0}, ordered on `stream`:
+ * a pipeline downloads it with its rows instead of synchronising on b2_tracker_export. */
+int b2_tracker_stats(b2_tracker_t* t, long long* stats_dev_out, void* stream);
 /* One frame for every stream.  dets: [n_streams][max_dets][det_cols] fp32 rows starting with
  * x1,y1,x2,y2 (det_cols >= 4, e.g. 6 for NMS output rows); det_counts: [n_streams] int32.
- * out_rows: [n_streams][capacity][B2_TRACK_COLS]; out_counts: [n_streams] int32;
- * out_traj (may be NULL): [n_streams][capacity][B2_TRAJ_LEN][2] fp32 last centres, oldest first,
- * out_traj_len (may be NULL): [n_streams][capacity] int32. */
+ * out_rows: [n_streams][out_cap][B2_TRACK_COLS]; out_counts: [n_streams] int32 = tracks reported (rows beyond out_cap are
+ * counted but not written: out_counts[s] > out_cap tells the caller its buffer was too small);
+ * out_traj (may be NULL): [n_streams][out_cap][B2_TRAJ_LEN][2] fp32 last centres, oldest first,
+ * out_traj_len (NULL iff out_traj is): [n_streams][out_cap] int32.
+ * Row order per stream is deterministic but not by id (tracks no detection overlaps first, slot order; then the tracks with a
+ * candidate detection; then new tracks): order by column 0 for the reference's list order. */
 int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_cols, const int32_t* det_counts,
-                      float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, void* stream);
+                      float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, int out_cap, void* stream);
 /* Host-side inspection (synchronises): dense state of one stream.  x: [cap][8], P: [cap][64] (dense 8x8
  * rebuilt from the decoupled blocks), meta: [cap][8] int32 {id, age, hits, hit_streak, tsu, lost_frames, is_lost, n_vel},
  * stats: [8] int64 {created, terminated, active, long_term_predictions, recoveries, frame_count, next_track_id,
  * dropped (detections that found no free slot)}.  Any of the host pointers may be NULL. */
 int b2_tracker_export(b2_tracker_t* t, int stream_idx, float* x_host, float* P_host, int32_t* meta_host,
                       int32_t* n_tracks_host, long long* stats_host);
-/* bytes of bank state read+written per live track by one predict / one update (for roofline accounting) */
+/* Motion analysis of one stream's live tracks (analyze_motion_pattern, enhanced_aircraft_kalman_tracker.py:137-163; read by
+ * get_statistics :288-304): motion_host [cap][8] fp32 {id (i32 bits), velocity_avg x, y, direction, speed, stability_score,
+ * prediction_confidence, n_velocities (i32 bits)}, slot order.  Synchronises. */
+int b2_tracker_export_motion(b2_tracker_t* t, int stream_idx, float* motion_host, int32_t* n_tracks_host);
+/* bytes of bank state + output row read and written per track and frame (roofline accounting): `predict_bytes` for a
+ * coasting track (finished by the sweep: predict, mark lost, delete test, row), `update_bytes` for a matched one */
 int b2_tracker_bytes_per_track(int* predict_bytes, int* update_bytes);
-/* Bank-only kernels for roofline measurement at C3 scale: predict every live track;
- * update tracks whose match[slot] >= 0 with dets[match]; no association/lifecycle. */
+/* AircraftKalmanTracker.predict (enhanced_aircraft_kalman_tracker.py:184-203) alone on every live track of the bank */
 int b2_tracker_bank_predict(b2_tracker_t* t, void* stream);
 int b2_tracker_seed(b2_tracker_t* t, const float* boxes, const int32_t* counts, int max_rows, void* stream);
 

@@ -211,7 +211,9 @@ class MultiTracker:
         self.frame_count, self.next_track_id = 0, 1
         self.stats = {"total_tracks_created": 0, "total_tracks_terminated": 0, "current_active_tracks": 0,
                       "long_term_predictions": 0, "successful_recoveries": 0}
-        self.last_min_iou_gap = np.inf   # diagnostic for near-tie fixtures
+        self.last_min_iou_gap = np.inf   # diagnostic for near-tie fixtures: all candidates
+        self.min_competing_gap = np.inf  # smallest IoU difference between two candidates that share a detection or a track
+        self.min_thr_gap = np.inf        # smallest |IoU - threshold| over overlapping pairs
 
     def update(self, detections):
         self.frame_count += 1
@@ -222,6 +224,7 @@ class MultiTracker:
             cand = np.sort(iou[iou >= self.iou_threshold])
             if len(cand) > 1:
                 self.last_min_iou_gap = min(self.last_min_iou_gap, float(np.diff(cand).min()))
+            self._fixture_gaps(iou)
             matched = greedy_match(iou, self.iou_threshold)
             md, mt = {m[0] for m in matched}, {m[1] for m in matched}
             um_d = [d for d in range(D) if d not in md]
@@ -256,6 +259,19 @@ class MultiTracker:
                 if info["status"] == "predicted" and info["lost_frames"] > 30:
                     self.stats["long_term_predictions"] += 1
         return out
+
+    def _fixture_gaps(self, iou):
+        """How far the frame is from a decision an fp32 IoU could flip: only candidates that COMPETE (same detection or same
+        track) can reorder the greedy walk; a pair near the threshold can enter or leave the candidate set."""
+        pos = iou[iou > 0]
+        if pos.size:
+            self.min_thr_gap = min(self.min_thr_gap, float(np.abs(pos - self.iou_threshold).min()))
+        m = np.where(iou >= self.iou_threshold, iou, np.nan)
+        for axis in (0, 1):
+            a = np.sort(m, axis=axis)
+            d = np.diff(a, axis=axis)
+            if np.isfinite(d).any():
+                self.min_competing_gap = min(self.min_competing_gap, float(np.nanmin(d)))
 
     def get_statistics(self):
         return {**self.stats, "frame_count": self.frame_count,

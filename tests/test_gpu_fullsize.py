@@ -153,6 +153,85 @@ def test_c3_full_size_bank_properties():
     bank.close()
 
 
+def _same_tracks(got, ref, where, box_rtol=1e-5):
+    assert [t["track_id"] for t in got] == [t["track_id"] for t in ref], where
+    for ta, tb in zip(got, ref):
+        key = ("status", "age", "hits", "hit_streak", "time_since_update", "lost_frames", "is_lost")
+        assert tuple(ta[k] for k in key) == tuple(tb[k] for k in key), (where, ta["track_id"])
+        scale = max(1.0, float(np.abs(tb["bbox"]).max()))
+        assert np.abs(np.asarray(ta["bbox"]) - np.asarray(tb["bbox"])).max() / scale < box_rtol, (where, ta["track_id"])
+
+
+def test_c3_sized_stream_matches_oracle():
+    """One stream of the C3 shape -- a 4096-slot bank holding 3072 tracks, 40 detections per frame of which 70 % come from
+    existing tracks (+N(0,1) px) and 30 % are clutter -- against the float64 oracle, frame by frame: ids and
+    lifecycle bit-exact, boxes to 1e-5.  Four streams run together (16 sweep chunks each); streams 0 and 3 are checked."""
+    from b200dt.tracker import TrackerBank, rows_to_dicts
+    from oracle import tracker as otr
+
+    S, C, D, params = 4, 4096, 1024, (150, 1, 0.1)
+    bank = TrackerBank(S, C, D, *params)
+    g = np.random.default_rng(11)
+    oracles = {0: otr.MultiTracker(*params), 3: otr.MultiTracker(*params)}
+    frames = []
+    for r in range(3):                                       # 3 x 1024 founding detections on a 10 px grid (6x6 boxes)
+        idx = np.arange(D) + r * D
+        x, y = (idx % 64) * 10.0, (idx // 64) * 10.0
+        frames.append(np.stack([x, y, x + 6, y + 6, np.full(D, 0.9)], 1).astype(np.float32))
+    for _ in range(8):
+        pick = g.permutation(3 * D)[:40]
+        x, y = (pick % 64) * 10.0, (pick // 64) * 10.0
+        clutter = g.random(40) < 0.3
+        x = np.where(clutter, g.uniform(0, 634, 40), x + g.normal(0, 1, 40))
+        y = np.where(clutter, g.uniform(0, 474, 40), y + g.normal(0, 1, 40))
+        frames.append(np.stack([x, y, x + 6, y + 6, np.full(40, 0.8)], 1).astype(np.float32))
+    for f, d in enumerate(frames):
+        dets = torch.zeros((S, D, 5), dtype=torch.float32)
+        dets[:, :len(d)] = torch.from_numpy(d)[None]
+        rows, counts = bank.update(dets.cuda(), torch.full((S,), len(d), dtype=torch.int32).cuda(), with_trajectory=False)
+        c = counts.cpu().numpy()
+        for s, o in oracles.items():
+            _same_tracks(rows_to_dicts(rows[s, :c[s]].cpu().numpy()), o.update([r for r in d]), (s, f))
+    for s, o in oracles.items():
+        assert o.min_competing_gap > 1e-5 and o.min_thr_gap > 1e-6, (o.min_competing_gap, o.min_thr_gap)
+        assert int(bank.export(s)[3][7]) == 0
+    bank.close()
+
+
+def test_c4_pipeline_tracker_matches_oracle_on_its_own_detections():
+    """The headline workload's tracker stage (256 streams, capacity 2048, the synthetic IR frames bench.py uses): the NMS
+    output the GPU itself produced for streams 0, 17 and 255 is fed, frame by frame, to the float64 oracle; ids / lifecycle
+    must agree bit for bit and boxes to 1e-5 (kalman/enhanced_multi_target_tracker.py:42-132)."""
+    from b200dt import synth
+    from b200dt.pipeline import DetectTrackPipeline
+    from b200dt.tracker import rows_to_dicts
+    from oracle import tracker as otr
+
+    S, T = 256, 14
+    params = dict(max_lost_frames=150, min_hits=1, iou_threshold=0.1)
+    vids = [synth.IRStream(seed=1000 + s, h=H, w=W) for s in range(32)]
+    pipe = DetectTrackPipeline("yolov8s-p2", S, (H, W), 640, CONF, IOU, 300, capacity=2048, **params)
+    sample = (0, 17, 255)
+    oracles = {s: otr.MultiTracker(150, 1, 0.1) for s in sample}
+    for t in range(T):
+        fr = [v.frame() for v in vids]
+        rows, counts = pipe.step_device(torch.from_numpy(np.stack([fr[s % 32] for s in range(S)])).cuda())
+        torch.cuda.synchronize()
+        dets, cnt = pipe.detect.post.out, pipe.detect.post.out_count
+        c = counts.cpu().numpy()
+        for s, o in oracles.items():
+            d = dets[s, :int(cnt[s])].cpu().numpy()
+            ref = o.update([np.asarray(r[:5], np.float32) for r in d])
+            _same_tracks(rows_to_dicts(rows[s, :c[s]].cpu().numpy()), ref, (s, t))
+    st = pipe.bank.stats_async().cpu().numpy()
+    assert int(st[:, 5].sum()) == 0, "no detection may be dropped"
+    for s, o in oracles.items():
+        assert o.min_competing_gap > 1e-6, (s, o.min_competing_gap)
+        assert [int(v) for v in st[s, :5]] == [o.stats[k] for k in ("total_tracks_created", "total_tracks_terminated",
+                                                                     "current_active_tracks", "long_term_predictions",
+                                                                     "successful_recoveries")]
+
+
 @pytest.mark.parametrize("name,B,HW", [("yolov8s-p2", 64, (640, 640)), ("yolov8x-p2", 32, (1280, 1280))], ids=["C2", "C5"])
 def test_c2_c5_full_size_forward_decode_nms_properties(name, B, HW):
     """C2 / C5: BCHW tensors in [0,1) -> forward + decode + NMS at the quoted batch and resolution.

@@ -11,13 +11,21 @@
 // per track and evaluates the exact closed-form 2x2 recurrences (verified in
 // tests/test_oracle_vs_golden.py::test_tracker_known_answer).
 //
-// Per frame: (1) bank_predict  -- every live slot, grid-wide, coalesced (HBM-bound)
-//            (2) associate     -- one CTA per stream: IoU rows on the fly, greedy matching by repeated
-//                                 mutual-best (== the reference's descending-IoU greedy, ties -> lowest
-//                                 (det, track id))
-//            (3) finish        -- one CTA per stream: Kalman update / mark lost / delete / create /
-//                                 emit rows (with the reference's extra predict on the first lost frame)
-// List order of the reference (= ascending track id) is carried by the id column; slots are recycled.
+// Per frame, TWO launches:
+//   (1) sweep_kernel   -- grid-wide, one slot per thread, a block = one 256-slot chunk of one stream (HBM-bound).
+//         Every live track is predicted in registers and its predicted box tested against the stream's detections
+//         (staged in shared memory).  A track that NO detection overlaps with IoU >= thr cannot be matched whatever the
+//         greedy order is, so its frame is finished on the spot: mark lost, delete test, the reference's extra predict on
+//         the first lost frame, and the emitted row -- every field of the slot is read once and written once.  Tracks that
+//         do have a candidate pair are written back predicted and listed (slot, box, id) together with their pairs
+//         (IoU, detection, track).  Row / list positions come from a block scan plus the aggregates of the stream's
+//         preceding chunks (published per chunk, no atomics on the data path): the output is deterministic.
+//   (2) resolve_kernel -- one CTA per stream, works on the short lists only: greedy matching == repeated mutual-best rounds
+//         (exactly the pairs the reference's descending-IoU walk takes, ties -> lowest (det, track id)), Kalman update +
+//         motion analysis of the matched tracks, lost / delete for the rest, new tracks for unmatched detections
+//         (ascending detection index -> ascending ids, k-th new track takes the k-th free slot), rows, stats.
+// Row order per stream: untouched tracks in slot order, then candidate tracks in slot order, then new tracks in slot
+// order.  List order of the reference (= ascending track id) is carried by the id column; slots are recycled.
 #include "common.cuh"
 
 #include <new>
@@ -30,6 +38,10 @@ enum FField { X0 = 0, X1, X2, X3, X4, X5, X6, X7, PPX, PPV, PVV, PSX, PSV, PSVV,
 enum IField { ID = 0, AGE, HITS, STREAK, TSU, LOSTF, ISLOST, NVEL, VHEAD, TLEN, THEAD, NIF };
 constexpr int kVelRing = 50;       // deque(maxlen=50)  enhanced_aircraft_kalman_tracker.py:79
 constexpr int kTraj = B2_TRAJ_LEN; // only the last 30 trajectory points are ever read (:377)
+constexpr int kChunk = 256;        // slots per sweep block
+constexpr int kMaxDetsSmem = 1024;
+constexpr int kResolveThreads = 512;
+constexpr int kCtSmem = 1024;      // candidate tracks whose match keys live in shared memory (more -> dense fallback)
 
 // noise constants, enhanced_aircraft_kalman_tracker.py:44-71
 constexpr float P0_POS = 50.f, P0_VEL = 100.f, P0_SVEL = 1.f;
@@ -40,14 +52,27 @@ struct Bank {
     int32_t* i;     // [NIF][N]
     float* vel;     // [kVelRing*2][N]
     float* traj;    // [kTraj*2][N]
-    float4* pbox;   // [N] predicted boxes of this frame
-    int32_t* match; // [N] matched detection index or -1
-    int32_t* det_match;   // [S][max_dets]
-    int32_t* next_id;     // [S]
-    int32_t* frame_count; // [S]
-    long long* stats;     // [S][8]: created, terminated, active, long_term, recoveries, overflow
-    int S, C, N, max_dets;
+    // ---- per-frame scratch ----
+    unsigned long long* agg;   // [S][nchunks] chunk aggregates of the sweep: bit 63 valid | pairs << 32 | cand << 16 | emitted
+    int32_t* chunk_free;       // [S][nchunks] free slots per chunk after the sweep
+    int32_t* fcnt;             // [S][4] sweep counters: terminated, long-term rows, live after
+    unsigned int* ticket;      // [1] dynamic block id of the sweep (chunk order == scheduling order)
+    int32_t* ctrk_slot;        // [S][C] candidate tracks (slot order): slot
+    float4* cbox;              // [S][C]   predicted box
+    int32_t* cid;              // [S][C]   track id
+    int32_t* cmatch;           // [S][C]   matched detection (dense fallback / > kCtSmem candidates)
+    uint4* pairs;              // [S][pair_cap] {iou bits, det, candidate index, track id}
+    int32_t* next_id;          // [S]
+    int32_t* frame_count;      // [S]
+    long long* stats;          // [S][8]: created, terminated, active, long_term, recoveries, dropped (no free slot)
+    int S, C, N, max_dets, nchunks, pair_cap;
     int max_lost, min_hits; float iou_thr;
+};
+
+struct Frame {
+    const float* dets; int det_cols; const int32_t* det_counts;
+    float* out_rows; int32_t* out_counts; float* out_traj; int32_t* out_traj_len;
+    int out_cap;   // rows per stream the output buffers hold (<= capacity); rows beyond are counted, not written
 };
 
 struct b2_tracker_impl {
@@ -85,18 +110,13 @@ __device__ __forceinline__ void predict_slot(const Bank& b, int g) {
     push_traj(b, g, cx, cy);
 }
 
+// Bank-only predict (b2_tracker_bank_predict): four consecutive slots per thread with 16-byte accesses (N % 4 == 0), the same
+// arithmetic as predict_slot element-wise; dead slots (id == 0) are written back unchanged.
 __global__ void __launch_bounds__(256) bank_predict_kernel(const Bank b) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= b.N) return;
-    b.match[g] = -1;
-    if (II(b, ID, g) == 0) return;
+    if (g >= b.N || II(b, ID, g) == 0) return;
     predict_slot(b, g);
-    const float cx = FF(b, X0, g), cy = FF(b, X1, g), w = FF(b, X2, g), h = FF(b, X3, g);
-    b.pbox[g] = make_float4(cx - w / 2.f, cy - h / 2.f, cx + w / 2.f, cy + h / 2.f);   // state_to_bbox :121-135
 }
-
-// Four consecutive slots per thread with 16-byte accesses (N % 4 == 0): the same arithmetic as predict_slot, element-wise;
-// dead slots (id == 0) are written back unchanged.  512 bytes per warp per access instead of 128.
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float sel(bool c, float a, float b) { return c ? a : b; }
@@ -106,7 +126,6 @@ __global__ void __launch_bounds__(256) bank_predict4_kernel(const Bank b) {
     if (g >= b.N) return;
     const size_t N = b.N;
     const int4 id = *reinterpret_cast<const int4*>(b.i + (size_t)ID * N + g);
-    *reinterpret_cast<int4*>(b.match + g) = make_int4(-1, -1, -1, -1);
     const bool l0 = id.x != 0, l1 = id.y != 0, l2 = id.z != 0, l3 = id.w != 0;
     if (!(l0 || l1 || l2 || l3)) return;
     float* F = b.f + g;
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(256) bank_predict4_kernel(const Bank b) {
     tsu.x += l0; tsu.y += l1; tsu.z += l2; tsu.w += l3;
     *reinterpret_cast<int4*>(I + (size_t)AGE * N) = age; *reinterpret_cast<int4*>(I + (size_t)TSU * N) = tsu;
     int4 head = *reinterpret_cast<const int4*>(I + (size_t)THEAD * N), len = *reinterpret_cast<const int4*>(I + (size_t)TLEN * N);
-    const float cx[4] = {x0.x, x0.y, x0.z, x0.w}, cy[4] = {x1.x, x1.y, x1.z, x1.w}, w[4] = {x2.x, x2.y, x2.z, x2.w}, h[4] = {x3.x, x3.y, x3.z, x3.w};
+    const float cx[4] = {x0.x, x0.y, x0.z, x0.w}, cy[4] = {x1.x, x1.y, x1.z, x1.w};
     const bool live[4] = {l0, l1, l2, l3};
     int hd[4] = {head.x, head.y, head.z, head.w}, ln[4] = {len.x, len.y, len.z, len.w};
 #pragma unroll
@@ -144,16 +163,10 @@ __global__ void __launch_bounds__(256) bank_predict4_kernel(const Bank b) {
             b.traj[(size_t)(2 * hd[k] + 1) * N + g + k] = cy[k];
             hd[k] = hd[k] + 1 == kTraj ? 0 : hd[k] + 1;
             ln[k] = min(ln[k] + 1, kTraj);
-            b.pbox[g + k] = make_float4(cx[k] - w[k] / 2.f, cy[k] - h[k] / 2.f, cx[k] + w[k] / 2.f, cy[k] + h[k] / 2.f);
         }
     }
     *reinterpret_cast<int4*>(I + (size_t)THEAD * N) = make_int4(hd[0], hd[1], hd[2], hd[3]);
     *reinterpret_cast<int4*>(I + (size_t)TLEN * N) = make_int4(ln[0], ln[1], ln[2], ln[3]);
-}
-
-static inline void launch_bank_predict(const Bank& b, cudaStream_t st) {
-    if (b.N % 4 == 0) bank_predict4_kernel<<<b2_ceil_div(b.N / 4, 256), 256, 0, st>>>(b);
-    else bank_predict_kernel<<<b2_ceil_div(b.N, 256), 256, 0, st>>>(b);
 }
 
 // _calculate_iou (enhanced_multi_target_tracker.py:200-232)
@@ -166,294 +179,224 @@ __device__ __forceinline__ float iou_ref(const float4& d, const float4& t) {
     return uni <= 0.f ? 0.f : inter / uni;
 }
 
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
+// exclusive scan over the block of a 64-bit (packed) value; *total = block sum.  s_warp: >= blockDim/32 entries
+__device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned long long v, unsigned long long* s_warp, unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long inc = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+        unsigned long long w = lane < nw ? s_warp[lane] : 0ull;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-        s_warp[lane] = w;   // inclusive over warps
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < nw) s_warp[lane] = w;   // inclusive over warps
     }
     __syncthreads();
-    const int warp_off = warp ? s_warp[warp - 1] : 0;
-    *total = s_warp[(blockDim.x >> 5) - 1];
-    const int r = warp_off + inc - v;
+    const unsigned long long warp_off = warp ? s_warp[warp - 1] : 0ull;
+    *total = s_warp[nw - 1];
+    const unsigned long long r = warp_off + inc - v;
     __syncthreads();
     return r;
 }
+__device__ __forceinline__ int block_exclusive_scan(int v, unsigned long long* s_warp, int* total) {
+    unsigned long long t;
+    const unsigned long long r = block_exclusive_scan64((unsigned long long)(unsigned)v, s_warp, &t);
+    *total = (int)t;
+    return (int)r;
+}
 
-constexpr int kAssocThreads = 512;
-constexpr int kMaxDetsSmem = 1024;
+constexpr unsigned long long kAggValid = 1ull << 63;
+__device__ __forceinline__ void agg_publish(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.global.release.gpu.u64 [%0], %1;" ::"l"(p), "l"(v | kAggValid) : "memory");
+}
+__device__ __forceinline__ unsigned long long agg_wait(const unsigned long long* p) {
+    unsigned long long v;
+    unsigned spins = 0;
+    do {
+        asm volatile("ld.global.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (!(v & kAggValid) && ++spins > (1u << 24)) { printf("b2dt: sweep aggregate wait timed out\n"); __trap(); }
+    } while (!(v & kAggValid));
+    return v & ~kAggValid;
+}
 
-// One CTA per stream.  Greedy descending-IoU matching == repeat { every free detection picks its best free
-// track (row max); a pair is accepted iff no other free detection beats it on that track (column max) }.
-__global__ void __launch_bounds__(kAssocThreads) associate_global_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
-                                                                const int32_t* __restrict__ det_counts) {
+// ------------------------------------------------------------------------------------------------------------------
+// (1) sweep
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kChunk) sweep_kernel(const Bank b, const Frame fr) {
     __shared__ float4 s_det[kMaxDetsSmem];
-    __shared__ int s_dmatch[kMaxDetsSmem];
-    __shared__ int s_best_t[kMaxDetsSmem];
-    __shared__ float s_best_iou[kMaxDetsSmem];
-    __shared__ int s_progress;
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kAssocThreads / 32;
-    const int D = min(det_counts[s], b.max_dets);
-    const int g0 = s * b.C;
-    for (int d = tid; d < D; d += kAssocThreads) {
-        const float* r = dets + ((size_t)s * b.max_dets + d) * det_cols;
+    __shared__ __align__(16) float s_rows[kChunk * B2_TRACK_COLS];
+    __shared__ unsigned long long s_warp[kChunk / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_ticket;
+    __shared__ int s_cnt[3];
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_ticket = atomicAdd(b.ticket, 1u); s_prefix = 0ull; }
+    if (tid < 3) s_cnt[tid] = 0;
+    __syncthreads();
+    const int s = (int)(s_ticket / (unsigned)b.nchunks), c = (int)(s_ticket % (unsigned)b.nchunks);
+    const int t = c * kChunk + tid;
+    const bool in = t < b.C;
+    const int g = s * b.C + (in ? t : 0);
+    const size_t N = b.N;
+    const int id = in ? II(b, ID, g) : 0;
+    const bool live = id != 0;
+    unsigned long long* agg = b.agg + (size_t)s * b.nchunks;
+    if (!__syncthreads_or(live)) {
+        // an empty chunk: nothing to predict, nothing to emit
+        if (tid == 0) { b.chunk_free[(size_t)s * b.nchunks + c] = min(kChunk, b.C - c * kChunk); agg_publish(agg + c, 0ull); }
+        return;
+    }
+    // ---- state of the slot into registers (every load independent: ~30 coalesced 4-byte loads in flight per thread) ----
+    float x[8], p[6], m[6];
+    int age = 0, hits = 0, tsu = 0, lostf = 0, islost = 0, tlen = 0, thead = 0;
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = b.f[(size_t)(X0 + k) * N + g];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) p[k] = b.f[(size_t)(PPX + k) * N + g];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) m[k] = b.f[(size_t)(VAVGX + k) * N + g];
+        age = II(b, AGE, g); hits = II(b, HITS, g); tsu = II(b, TSU, g);
+        lostf = II(b, LOSTF, g); islost = II(b, ISLOST, g); tlen = II(b, TLEN, g); thead = II(b, THEAD, g);
+    }
+    const int D = min(fr.det_counts[s], b.max_dets);
+    for (int d = tid; d < D; d += kChunk) {
+        const float* r = fr.dets + ((size_t)s * b.max_dets + d) * fr.det_cols;
         s_det[d] = make_float4(r[0], r[1], r[2], r[3]);
-        s_dmatch[d] = -1;
     }
     __syncthreads();
-    const float thr = b.iou_thr;
-    while (true) {
-        if (tid == 0) s_progress = 0;
-        // ---- row pass: best free track per free detection (warp per detection) ----
-        for (int d = warp; d < D; d += nwarps) {
-            if (s_dmatch[d] >= 0) continue;
+
+    // ---- predict (:184-203) ----
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    int npairs = 0;
+    if (live) {
+        x[0] += x[4]; x[1] += x[5]; x[2] += x[6]; x[3] += x[7];
+        p[0] = p[0] + 2.f * p[1] + p[2] + Q_POS; p[1] = p[1] + p[2]; p[2] = p[2] + Q_VEL;
+        p[3] = p[3] + 2.f * p[4] + p[5] + Q_SIZE; p[4] = p[4] + p[5]; p[5] = p[5] + Q_SVEL;
+        age += 1; tsu += 1;
+        b.traj[(size_t)(2 * thead) * N + g] = x[0]; b.traj[(size_t)(2 * thead + 1) * N + g] = x[1];
+        thead = thead + 1 == kTraj ? 0 : thead + 1; tlen = min(tlen + 1, kTraj);
+        box = make_float4(x[0] - x[2] / 2.f, x[1] - x[3] / 2.f, x[0] + x[2] / 2.f, x[1] + x[3] / 2.f);   // state_to_bbox :121-135
+        const float thr = b.iou_thr;
+        for (int d = 0; d < D; ++d) {
             const float4 db = s_det[d];
-            float best = -1.f; int bt = -1, bid = 0x7fffffff;
-            for (int t = lane; t < b.C; t += 32) {
-                const int g = g0 + t;
-                const int id = II(b, ID, g);
-                if (id == 0 || b.match[g] >= 0) continue;
-                const float v = iou_ref(db, b.pbox[g]);
-                if (v >= thr && (v > best || (v == best && id < bid))) { best = v; bt = t; bid = id; }
+            if (fminf(db.z, box.z) > fmaxf(db.x, box.x) && fminf(db.w, box.w) > fmaxf(db.y, box.y))
+                npairs += iou_ref(db, box) >= thr ? 1 : 0;
+        }
+    }
+    const bool cand = npairs > 0;
+    int emit = 0, terminated = 0, long_term = 0, freed = in && !live ? 1 : 0;
+    float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f, conf = 0.f;
+    if (live && !cand) {
+        // ---- no detection can match this track: mark_as_lost (:299-317), should_delete (:385-405), get_track_info (:335-383) ----
+        if (!islost) { islost = 1; lostf = 0; }
+        lostf += 1;
+        const bool del = tsu > b.max_lost || (age < 5 && tsu > 15) || (age < 10 && tsu > 30);
+        if (del) { II(b, ID, g) = 0; terminated = 1; freed = 1; }
+        else {
+            emit = 1;                                            // a lost track is always reported (multi_target_tracker.py:117-126)
+            const int k = lostf;
+            if (k <= 1) {                                        // enhanced_long_term_predict(1) -> self.predict(), 1.0 (:216-217)
+                x[0] += x[4]; x[1] += x[5]; x[2] += x[6]; x[3] += x[7];
+                p[0] = p[0] + 2.f * p[1] + p[2] + Q_POS; p[1] = p[1] + p[2]; p[2] = p[2] + Q_VEL;
+                p[3] = p[3] + 2.f * p[4] + p[5] + Q_SIZE; p[4] = p[4] + p[5]; p[5] = p[5] + Q_SVEL;
+                age += 1; tsu += 1;
+                b.traj[(size_t)(2 * thead) * N + g] = x[0]; b.traj[(size_t)(2 * thead + 1) * N + g] = x[1];
+                thead = thead + 1 == kTraj ? 0 : thead + 1; tlen = min(tlen + 1, kTraj);
+                bx = x[0]; by = x[1]; bw = x[2]; bh = x[3]; conf = 1.f;
+            } else if (m[PCONF - VAVGX] > 0.3f) {                // high confidence: mean-velocity extrapolation (:224-236)
+                bx = x[0] + m[0] * (float)k; by = x[1] + m[1] * (float)k; bw = x[2]; bh = x[3];
+                conf = m[PCONF - VAVGX] * fmaxf(0.1f, 1.f - (float)k / (float)b.max_lost);
+            } else {                                             // F^k x (:238-245)
+                bx = x[0] + (float)k * x[4]; by = x[1] + (float)k * x[5];
+                bw = x[2] + (float)k * x[6]; bh = x[3] + (float)k * x[7];
+                conf = fmaxf(0.1f, 1.f - (float)k / ((float)b.max_lost * 0.5f));
             }
+            long_term = tsu > 30 ? 1 : 0;
+        }
+    }
+    // ---- write the slot back ----
+    if (live && !terminated) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ot = __shfl_xor_sync(0xffffffffu, bt, o), oid = __shfl_xor_sync(0xffffffffu, bid, o);
-                if (ob > best || (ob == best && oid < bid)) { best = ob; bt = ot; bid = oid; }
-            }
-            if (lane == 0) { s_best_t[d] = bt; s_best_iou[d] = best; }
-        }
-        __syncthreads();
-        // ---- column check: is (d, t) also the best free detection for t? ----
-        for (int d = tid; d < D; d += kAssocThreads) {
-            if (s_dmatch[d] >= 0) continue;
-            const int t = s_best_t[d];
-            if (t < 0) continue;
-            const float v = s_best_iou[d];
-            const float4 tb = b.pbox[g0 + t];
-            bool dominated = false;
-            for (int e = 0; e < D && !dominated; ++e) {
-                if (e == d || s_dmatch[e] >= 0) continue;
-                const float ve = iou_ref(s_det[e], tb);
-                if (ve >= thr && (ve > v || (ve == v && e < d))) dominated = true;
-            }
-            if (!dominated) { b.match[g0 + t] = d; s_dmatch[d] = t; s_progress = 1; }
-        }
-        __syncthreads();
-        if (!s_progress) break;
-        __syncthreads();
-    }
-    for (int d = tid; d < b.max_dets; d += kAssocThreads) b.det_match[(size_t)s * b.max_dets + d] = d < D ? s_dmatch[d] : -2;
-}
-
-// Same algorithm with the stream's LIVE tracks compacted into shared memory first (box, id, slot): the rounds then
-// touch no global memory.  Dynamic shared memory: C * 28 bytes.
-__global__ void __launch_bounds__(kAssocThreads) associate_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
-                                                                const int32_t* __restrict__ det_counts, int cand_cap) {
-    extern __shared__ uint8_t s_raw[];
-    float4* l_box = reinterpret_cast<float4*>(s_raw);                    // [C]
-    int* l_id = reinterpret_cast<int*>(l_box + b.C);                      // [C]
-    int* l_slot = l_id + b.C;                                             // [C]
-    int* l_match = l_slot + b.C;                                          // [C]
-    __shared__ float4 s_det[kMaxDetsSmem];
-    __shared__ int s_dmatch[kMaxDetsSmem];
-    __shared__ int s_best_t[kMaxDetsSmem];
-    __shared__ float s_best_iou[kMaxDetsSmem];
-    __shared__ int s_warp[32];
-    __shared__ int s_progress, s_ncand;
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kAssocThreads / 32;
-    const int D = min(det_counts[s], b.max_dets);
-    const int g0 = s * b.C;
-    for (int d = tid; d < D; d += kAssocThreads) {
-        const float* r = dets + ((size_t)s * b.max_dets + d) * det_cols;
-        s_det[d] = make_float4(r[0], r[1], r[2], r[3]);
-        s_dmatch[d] = -1;
-    }
-    // ---- compact the live tracks (slot order) ----
-    int base_live = 0;
-    for (int base = 0; base < b.C; base += kAssocThreads) {
-        const int t = base + tid;
-        const int id = t < b.C ? II(b, ID, g0 + t) : 0;
-        int total;
-        const int off = block_exclusive_scan(id != 0 ? 1 : 0, s_warp, &total);
-        if (id != 0) {
-            const int k = base_live + off;
-            l_box[k] = b.pbox[g0 + t]; l_id[k] = id; l_slot[k] = t; l_match[k] = -1;
-        }
-        base_live += total;
-    }
-    const int L = base_live;
-    __syncthreads();
-    const float thr = b.iou_thr;
-    // ---- fast path: list every pair with IoU >= thr ONCE (sparse: a detection overlaps a handful of tracks), then run the
-    //      mutual-best rounds on that list with 64-bit shared-memory atomicMax keys instead of re-evaluating D x L IoUs per
-    //      round.  A pair is accepted when the track is the detection's best free candidate by (IoU, lowest track id) and
-    //      the detection is the track's best free candidate by (IoU, lowest detection index): exactly the pairs the
-    //      reference's descending-IoU greedy walk takes (enhanced_multi_target_tracker.py:234-270).  Falls back to the
-    //      dense rounds below if the list overflows. ----
-    uint8_t* dyn = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(l_match + b.C) + 7) & ~uintptr_t(7));
-    unsigned long long* t_best = reinterpret_cast<unsigned long long*>(dyn);               // [C]
-    unsigned long long* d_best = t_best + b.C;                                              // [kMaxDetsSmem]
-    float* c_iou = reinterpret_cast<float*>(d_best + kMaxDetsSmem);                         // [cand_cap]
-    uint32_t* c_pair = reinterpret_cast<uint32_t*>(c_iou + cand_cap);                       // [cand_cap]: det << 16 | track
-    if (tid == 0) s_ncand = 0;
-    __syncthreads();
-    if (D > 0 && L > 0 && cand_cap > 0) {
-        for (int d0 = 0; d0 < D; d0 += nwarps) {
-            const int d = d0 + warp;
-            if (d < D) {
-                const float4 db = s_det[d];
-                for (int t = lane; t < L; t += 32) {
-                    const float v = iou_ref(db, l_box[t]);
-                    if (v >= thr) {
-                        const int pos = atomicAdd(&s_ncand, 1);
-                        if (pos < cand_cap) { c_iou[pos] = v; c_pair[pos] = ((uint32_t)d << 16) | (uint32_t)t; }
-                    }
-                }
-            }
-            if (d0 == 0) {
-                // dense scene (the first nwarps detections already project past the list capacity): do not finish a list
-                // that will be thrown away, go to the dense rounds
-                __syncthreads();
-                const int seen = min(D, nwarps);
-                if ((long long)s_ncand * D > (long long)cand_cap * seen) { if (tid == 0) s_ncand = cand_cap + 1; break; }
-            }
-        }
-    }
-    __syncthreads();
-    const int M = s_ncand;
-    if (M <= cand_cap && b.C <= 65536) {
-        while (M > 0) {
-            for (int d = tid; d < D; d += kAssocThreads) d_best[d] = 0ull;
-            for (int t = tid; t < L; t += kAssocThreads) t_best[t] = 0ull;
-            if (tid == 0) s_progress = 0;
-            __syncthreads();
-            for (int e = tid; e < M; e += kAssocThreads) {
-                const uint32_t pr = c_pair[e];
-                const int d = (int)(pr >> 16), t = (int)(pr & 0xFFFFu);
-                if (s_dmatch[d] >= 0 || l_match[t] >= 0) continue;
-                const unsigned long long hi = (unsigned long long)__float_as_uint(c_iou[e]) << 32;   // IoU > 0: bits order like the float
-                atomicMax(&d_best[d], hi | (unsigned)(0xFFFFFFFFu - (unsigned)l_id[t]));
-                atomicMax(&t_best[t], hi | (unsigned)(0xFFFFFFFFu - (unsigned)d));
-            }
-            __syncthreads();
-            for (int e = tid; e < M; e += kAssocThreads) {
-                const uint32_t pr = c_pair[e];
-                const int d = (int)(pr >> 16), t = (int)(pr & 0xFFFFu);
-                if (s_dmatch[d] >= 0 || l_match[t] >= 0) continue;
-                const unsigned long long hi = (unsigned long long)__float_as_uint(c_iou[e]) << 32;
-                if (d_best[d] == (hi | (unsigned)(0xFFFFFFFFu - (unsigned)l_id[t])) && t_best[t] == (hi | (unsigned)(0xFFFFFFFFu - (unsigned)d))) {
-                    // unique per d and per t within a round: no two entries share (d, best t) or (t, best d)
-                    s_dmatch[d] = t; l_match[t] = d; s_progress = 1;
-                }
-            }
-            __syncthreads();
-            if (!s_progress) break;
-            __syncthreads();
-        }
-    } else
-    if (D > 0 && L > 0) {
-        while (true) {
-            if (tid == 0) s_progress = 0;
-            // ---- row pass: best free track per free detection (warp per detection) ----
-            for (int d = warp; d < D; d += nwarps) {
-                if (s_dmatch[d] >= 0) continue;
-                const float4 db = s_det[d];
-                float best = -1.f; int bt = -1, bid = 0x7fffffff;
-                for (int t = lane; t < L; t += 32) {
-                    if (l_match[t] >= 0) continue;
-                    const float v = iou_ref(db, l_box[t]);
-                    const int id = l_id[t];
-                    if (v >= thr && (v > best || (v == best && id < bid))) { best = v; bt = t; bid = id; }
-                }
+        for (int k = 0; k < 4; ++k) b.f[(size_t)(X0 + k) * N + g] = x[k];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int ot = __shfl_xor_sync(0xffffffffu, bt, o), oid = __shfl_xor_sync(0xffffffffu, bid, o);
-                    if (ob > best || (ob == best && oid < bid)) { best = ob; bt = ot; bid = oid; }
+        for (int k = 0; k < 6; ++k) b.f[(size_t)(PPX + k) * N + g] = p[k];
+        II(b, AGE, g) = age; II(b, TSU, g) = tsu; II(b, TLEN, g) = tlen; II(b, THEAD, g) = thead;
+        if (!cand) { II(b, STREAK, g) = 0; II(b, LOSTF, g) = lostf; II(b, ISLOST, g) = 1; }
+    }
+    // ---- positions: block scan + the aggregates of the stream's preceding chunks ----
+    unsigned long long total;
+    const unsigned long long mine = (unsigned long long)emit | ((unsigned long long)(cand ? 1 : 0) << 16) | ((unsigned long long)npairs << 32);
+    const unsigned long long off = block_exclusive_scan64(mine, s_warp, &total);
+    if (tid == 0) agg_publish(agg + c, total);
+    {
+        unsigned long long before = 0ull;
+        for (int i = tid; i < c; i += kChunk) before += agg_wait(agg + i);
+        if (before) atomicAdd(&s_prefix, before);
+    }
+    if (terminated) atomicAdd(&s_cnt[0], 1);
+    if (long_term) atomicAdd(&s_cnt[1], 1);
+    if (freed) atomicAdd(&s_cnt[2], 1);
+    if (emit) {
+        float4* sr = reinterpret_cast<float4*>(s_rows + (int)(off & 0xFFFFu) * B2_TRACK_COLS);
+        sr[0] = make_float4(__int_as_float(id), bx - bw / 2.f, by - bh / 2.f, bx + bw / 2.f);
+        sr[1] = make_float4(by + bh / 2.f, conf, __int_as_float(1), __int_as_float(age));
+        sr[2] = make_float4(__int_as_float(hits), __int_as_float(0), __int_as_float(tsu), __int_as_float(tsu));
+        sr[3] = make_float4(__int_as_float(1), x[4], x[5], m[PCONF - VAVGX]);
+        sr[4] = make_float4(__int_as_float(m[STAB - VAVGX] > 0.5f ? 1 : 0), m[SPEED - VAVGX], m[DIRN - VAVGX], __int_as_float(t));
+    }
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    const int n_emit = (int)(total & 0xFFFFu), n_cand = (int)((total >> 16) & 0xFFFFu);
+    const int e0 = (int)(prefix & 0xFFFFu) + 0, c0 = (int)((prefix >> 16) & 0xFFFFu);
+    // emitted rows of the chunk are contiguous in the output: coalesced 16-byte stores
+    {
+        const float4* src4 = reinterpret_cast<const float4*>(s_rows);
+        float4* dst4 = reinterpret_cast<float4*>(fr.out_rows + ((size_t)s * fr.out_cap + e0) * B2_TRACK_COLS);
+        const int n4 = (min(e0 + n_emit, fr.out_cap) - e0) * (B2_TRACK_COLS / 4);
+        for (int i = tid; i < n4; i += kChunk) dst4[i] = src4[i];
+    }
+    if (emit && fr.out_traj && e0 + (int)(off & 0xFFFFu) < fr.out_cap) {
+        const int pos = e0 + (int)(off & 0xFFFFu);
+        float* to = fr.out_traj + ((size_t)s * fr.out_cap + pos) * kTraj * 2;
+        int start = thead - tlen; if (start < 0) start += kTraj;
+        for (int k = 0; k < tlen; ++k) {
+            int r = start + k; if (r >= kTraj) r -= kTraj;
+            to[2 * k] = b.traj[(size_t)(2 * r) * N + g]; to[2 * k + 1] = b.traj[(size_t)(2 * r + 1) * N + g];
+        }
+        fr.out_traj_len[(size_t)s * fr.out_cap + pos] = tlen;
+    }
+    if (cand) {
+        const int ci = c0 + (int)((off >> 16) & 0xFFFFu);
+        const size_t cb = (size_t)s * b.C + ci;
+        b.ctrk_slot[cb] = t; b.cbox[cb] = box; b.cid[cb] = id;
+        unsigned long long pp = (prefix >> 32) + (off >> 32);
+        const float thr = b.iou_thr;
+        for (int d = 0; d < D; ++d) {
+            const float4 db = s_det[d];
+            if (fminf(db.z, box.z) > fmaxf(db.x, box.x) && fminf(db.w, box.w) > fmaxf(db.y, box.y)) {
+                const float v = iou_ref(db, box);
+                if (v >= thr) {
+                    if (pp < (unsigned long long)b.pair_cap)
+                        b.pairs[(size_t)s * b.pair_cap + pp] = make_uint4(__float_as_uint(v), (unsigned)d, (unsigned)ci, (unsigned)id);
+                    ++pp;
                 }
-                if (lane == 0) { s_best_t[d] = bt; s_best_iou[d] = best; }
             }
-            __syncthreads();
-            // ---- column check: is (d, t) also the best free detection for t? ----
-            for (int d = tid; d < D; d += kAssocThreads) {
-                if (s_dmatch[d] >= 0) continue;
-                const int t = s_best_t[d];
-                if (t < 0) continue;
-                const float v = s_best_iou[d];
-                const float4 tb = l_box[t];
-                bool dominated = false;
-                for (int e = 0; e < D && !dominated; ++e) {
-                    if (e == d || s_dmatch[e] >= 0) continue;
-                    const float ve = iou_ref(s_det[e], tb);
-                    if (ve >= thr && (ve > v || (ve == v && e < d))) dominated = true;
-                }
-                if (!dominated) { l_match[t] = d; s_dmatch[d] = t; s_progress = 1; }
-            }
-            __syncthreads();
-            if (!s_progress) break;
-            __syncthreads();
         }
     }
-    for (int t = tid; t < L; t += kAssocThreads) if (l_match[t] >= 0) b.match[g0 + l_slot[t]] = l_match[t];
-    for (int d = tid; d < b.max_dets; d += kAssocThreads) b.det_match[(size_t)s * b.max_dets + d] = d < D ? (s_dmatch[d] >= 0 ? l_slot[s_dmatch[d]] : -1) : -2;
+    (void)n_cand;
+    if (tid == 0) {
+        b.chunk_free[(size_t)s * b.nchunks + c] = s_cnt[2];
+        if (s_cnt[0]) atomicAdd(b.fcnt + s * 4 + 0, s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(b.fcnt + s * 4 + 1, s_cnt[1]);
+    }
 }
 
-// analyze_motion_pattern (:137-163) + _calculate_direction_consistency (:165-182) over the velocity ring
-__device__ void analyze_slot(const Bank& b, int g) {
-    const int n = II(b, NVEL, g);
-    if (n < 5) return;
-    const int head = II(b, VHEAD, g);                      // next write position; oldest = head - n
-    float sx = 0.f, sy = 0.f;
-    for (int k = 0; k < n; ++k) { sx += b.vel[(size_t)(2 * k) * b.N + g]; sy += b.vel[(size_t)(2 * k + 1) * b.N + g]; }
-    const float mx = sx / n, my = sy / n;
-    float vx2 = 0.f, vy2 = 0.f;
-    for (int k = 0; k < n; ++k) {
-        const float dx = b.vel[(size_t)(2 * k) * b.N + g] - mx, dy = b.vel[(size_t)(2 * k + 1) * b.N + g] - my;
-        vx2 += dx * dx; vy2 += dy * dy;
-    }
-    const float sdx = sqrtf(vx2 / n), sdy = sqrtf(vy2 / n);
-    // direction changes in chronological order
-    const float PI = 3.14159265358979323846f;
-    float dsum = 0.f, prev = 0.f;
-    float dch[kVelRing];
-    int start = head - n; if (start < 0) start += kVelRing;
-    for (int k = 0; k < n; ++k) {
-        int r = start + k; if (r >= kVelRing) r -= kVelRing;
-        const float ang = atan2f(b.vel[(size_t)(2 * r + 1) * b.N + g], b.vel[(size_t)(2 * r) * b.N + g]);
-        if (k > 0) {
-            float c = ang - prev;
-            if (!(fabsf(c) < PI)) c = c - 2.f * PI * (c > 0.f ? 1.f : (c < 0.f ? -1.f : 0.f));
-            dch[k - 1] = c; dsum += c;
-        }
-        prev = ang;
-    }
-    const float dmean = dsum / (n - 1);
-    float dvar = 0.f;
-    for (int k = 0; k < n - 1; ++k) { const float e = dch[k] - dmean; dvar += e * e; }
-    const float dstd = sqrtf(dvar / (n - 1));
-    const float speed_stab = 1.f / (1.f + (sdx + sdy) / 2.f);
-    const float dir_cons = 1.f / (1.f + dstd * 10.f);
-    const float stab = (speed_stab + dir_cons) / 2.f;
-    FF(b, VAVGX, g) = mx; FF(b, VAVGY, g) = my;
-    FF(b, SPEED, g) = sqrtf(mx * mx + my * my);
-    FF(b, DIRN, g) = atan2f(my, mx);
-    FF(b, STAB, g) = stab;
-    FF(b, PCONF, g) = stab * fminf((float)n / 30.f, 1.f);
-}
-
-// The same analysis by one warp (lane <-> ring entry, two entries per lane): the serial form walks the 50-entry ring three
-// times with dependent global loads -- ~100 k cycles for ONE matched track, and every 256-slot sweep of finish_kernel that
-// held a matched track waited for it.  Sums become shuffle trees (fp32, different summation order than the serial loop:
-// within the 2e-4 / 1e-3 gates of tests/test_gpu_tracker.py against the float64 reference).
+// analyze_motion_pattern (:137-163) + _calculate_direction_consistency (:165-182) over the velocity ring, by one warp
+// (lane <-> ring entry, two entries per lane).  Sums are shuffle trees in fp32: within the 2e-4 / 1e-3 gates of
+// tests/test_gpu_tracker.py against the float64 reference.
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -511,8 +454,8 @@ __device__ void analyze_slot_warp(const Bank& b, int g, int lane) {
     }
 }
 
-// Kalman update with measurement z = bbox_to_state(det)  (:249-297)
-__device__ __forceinline__ void update_slot(const Bank& b, int g, const float4& d, bool analyze = true) {
+// Kalman update with measurement z = bbox_to_state(det)  (:249-297); the motion analysis follows separately (one warp per track)
+__device__ __forceinline__ void update_slot(const Bank& b, int g, const float4& d) {
     II(b, TSU, g) = 0; II(b, HITS, g) += 1; II(b, STREAK, g) += 1;
     if (II(b, ISLOST, g)) { II(b, ISLOST, g) = 0; II(b, LOSTF, g) = 0; }
     const float z0 = (d.x + d.z) / 2.f, z1 = (d.y + d.w) / 2.f, z2 = d.z - d.x, z3 = d.w - d.y;
@@ -533,14 +476,13 @@ __device__ __forceinline__ void update_slot(const Bank& b, int g, const float4& 
         FF(b, X3, g) += kx * y3; FF(b, X7, g) += kv * y3;
         FF(b, PSX, g) = omk * pxx; FF(b, PSV, g) = omk * pxv; FF(b, PSVV, g) = pvv - kv * pxv;
     }
-    // velocity ring push, trajectory push, motion analysis
+    // velocity ring push, trajectory push
     int head = II(b, VHEAD, g);
     b.vel[(size_t)(2 * head) * b.N + g] = FF(b, X4, g);
     b.vel[(size_t)(2 * head + 1) * b.N + g] = FF(b, X5, g);
     II(b, VHEAD, g) = head + 1 == kVelRing ? 0 : head + 1;
     II(b, NVEL, g) = min(II(b, NVEL, g) + 1, kVelRing);
     push_traj(b, g, FF(b, X0, g), FF(b, X1, g));
-    if (analyze) analyze_slot(b, g);
 }
 
 // AircraftKalmanTracker.__init__ (:23-101)
@@ -556,8 +498,9 @@ __device__ __forceinline__ void init_slot(const Bank& b, int g, const float4& d,
     push_traj(b, g, cx, cy);
 }
 
-// get_track_info (:335-383) incl. get_lost_prediction / enhanced_long_term_predict side effects
-__device__ void emit_slot(const Bank& b, int g, float* row, float* traj_out, int32_t* traj_len_out, int slot, int* long_term) {
+// get_track_info (:335-383) incl. get_lost_prediction / enhanced_long_term_predict side effects; the row goes to global
+// memory as five 16-byte stores
+__device__ void emit_slot(const Bank& b, int g, float* out_row, float* traj_out, int32_t* traj_len_out, int slot, int* long_term) {
     float bx, by, bw, bh, conf; int predicted = II(b, TSU, g) > 0;
     if (predicted) {
         if (II(b, ISLOST, g)) {
@@ -582,16 +525,14 @@ __device__ void emit_slot(const Bank& b, int g, float* row, float* traj_out, int
         bx = FF(b, X0, g); by = FF(b, X1, g); bw = FF(b, X2, g); bh = FF(b, X3, g); conf = 1.f;
     }
     const int tsu = II(b, TSU, g);
-    int32_t* irow = reinterpret_cast<int32_t*>(row);
-    irow[0] = II(b, ID, g);
-    row[1] = bx - bw / 2.f; row[2] = by - bh / 2.f; row[3] = bx + bw / 2.f; row[4] = by + bh / 2.f;
-    row[5] = conf; irow[6] = predicted;
-    irow[7] = II(b, AGE, g); irow[8] = II(b, HITS, g); irow[9] = II(b, STREAK, g); irow[10] = tsu; irow[11] = tsu;
-    irow[12] = predicted;
-    row[13] = FF(b, X4, g); row[14] = FF(b, X5, g); row[15] = FF(b, PCONF, g);
-    irow[16] = FF(b, STAB, g) > 0.5f ? 1 : 0;
-    row[17] = FF(b, SPEED, g); row[18] = FF(b, DIRN, g); irow[19] = slot;
     if (predicted && tsu > 30) *long_term += 1;
+    if (!out_row) return;                                    // beyond the caller's row capacity: state side effects only
+    float4* o = reinterpret_cast<float4*>(out_row);
+    o[0] = make_float4(__int_as_float(II(b, ID, g)), bx - bw / 2.f, by - bh / 2.f, bx + bw / 2.f);
+    o[1] = make_float4(by + bh / 2.f, conf, __int_as_float(predicted), __int_as_float(II(b, AGE, g)));
+    o[2] = make_float4(__int_as_float(II(b, HITS, g)), __int_as_float(II(b, STREAK, g)), __int_as_float(tsu), __int_as_float(tsu));
+    o[3] = make_float4(__int_as_float(predicted), FF(b, X4, g), FF(b, X5, g), FF(b, PCONF, g));
+    o[4] = make_float4(__int_as_float(FF(b, STAB, g) > 0.5f ? 1 : 0), FF(b, SPEED, g), FF(b, DIRN, g), __int_as_float(slot));
     if (traj_out) {
         const int len = II(b, TLEN, g), head = II(b, THEAD, g);
         int start = head - len; if (start < 0) start += kTraj;
@@ -604,165 +545,254 @@ __device__ void emit_slot(const Bank& b, int g, float* row, float* traj_out, int
     }
 }
 
-constexpr int kFinishThreads = 512;
-
-// n staged rows (80 bytes each, contiguous) -> global, 16 bytes per thread and step
-__device__ __forceinline__ void flush_rows(const float* s_rows, float* dst, int n, int tid) {
-    const float4* src4 = reinterpret_cast<const float4*>(s_rows);
-    float4* dst4 = reinterpret_cast<float4*>(dst);
-    for (int i = tid; i < n * (B2_TRACK_COLS / 4); i += kFinishThreads) dst4[i] = src4[i];
-}
-
-// One CTA per stream: update / mark lost / delete / emit for existing tracks (slot order), then create.
-__global__ void __launch_bounds__(kFinishThreads) finish_kernel(const Bank b, const float* __restrict__ dets, int det_cols,
-                                                               const int32_t* __restrict__ det_counts, float* __restrict__ out_rows,
-                                                               int32_t* __restrict__ out_counts, float* __restrict__ out_traj,
-                                                               int32_t* __restrict__ out_traj_len) {
-    __shared__ int s_warp[32];
-    __shared__ int s_emit_base, s_free_base, s_created, s_an;
-    __shared__ int s_alist[kMaxDetsSmem];                  // slots updated this frame (<= detections of the stream)
-    __shared__ __align__(16) float s_rows[kFinishThreads * B2_TRACK_COLS];   // emitted rows of one sweep
-    __shared__ long long s_stats[6];
-    const int s = blockIdx.x, tid = threadIdx.x;
+// ------------------------------------------------------------------------------------------------------------------
+// (2) resolve: one CTA per stream on the candidate lists
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, const Frame fr) {
+    __shared__ float4 s_det[kMaxDetsSmem];
+    __shared__ int s_dmatch[kMaxDetsSmem];
+    __shared__ unsigned long long d_best[kMaxDetsSmem];      // sparse rounds: best key per detection; dense rounds: {best track, IoU}
+    __shared__ int s_list[kMaxDetsSmem];                     // dense rounds: staged acceptances; then matched tracks; then new detections
+    __shared__ unsigned long long t_best[kCtSmem];
+    __shared__ int l_match[kCtSmem];
+    __shared__ unsigned long long s_warp[kResolveThreads / 32];
+    __shared__ unsigned long long s_tot;
+    __shared__ int s_progress, s_an, s_emit_base, s_cnt[4];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kResolveThreads / 32;
     const int g0 = s * b.C;
-    const int D = min(det_counts[s], b.max_dets);
-    if (tid == 0) { s_emit_base = 0; s_free_base = 0; s_created = 0; s_an = 0; }
-    if (tid < 6) s_stats[tid] = 0;
-    const int frame = b.frame_count[s] + 1;
+    const int D = min(fr.det_counts[s], b.max_dets);
+    if (s == 0 && tid == 0) *b.ticket = 0u;
+    if (tid == 0) { s_tot = 0ull; s_an = 0; }
+    if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
-    int terminated = 0, recoveries = 0, long_term = 0;
-    float* rows = out_rows + (size_t)s * b.C * B2_TRACK_COLS;
+    {   // totals of the sweep; the aggregates are consumed (zero = not yet published, for the next frame)
+        unsigned long long* agg = b.agg + (size_t)s * b.nchunks;
+        unsigned long long sum = 0ull;
+        for (int i = tid; i < b.nchunks; i += kResolveThreads) { sum += agg[i] & ~kAggValid; agg[i] = 0ull; }
+        if (sum) atomicAdd(&s_tot, sum);
+    }
+    for (int d = tid; d < D; d += kResolveThreads) {
+        const float* r = fr.dets + ((size_t)s * b.max_dets + d) * fr.det_cols;
+        s_det[d] = make_float4(r[0], r[1], r[2], r[3]);
+        s_dmatch[d] = -1;
+    }
+    __syncthreads();
+    const int E1 = (int)(s_tot & 0xFFFFu), T = (int)((s_tot >> 16) & 0xFFFFu);
+    const unsigned long long M64 = s_tot >> 32;
+    const int frame = b.frame_count[s] + 1;
+    const float thr = b.iou_thr;
+    const int32_t* cslot = b.ctrk_slot + (size_t)g0;
+    const float4* cbox = b.cbox + (size_t)g0;
+    const int32_t* cid = b.cid + (size_t)g0;
+    const bool sparse = M64 <= (unsigned long long)b.pair_cap && T <= kCtSmem;
+    int* match = sparse ? l_match : b.cmatch + (size_t)g0;
+    for (int i = tid; i < T; i += kResolveThreads) match[i] = -1;
+    __syncthreads();
 
-    // ---- pass 1a: existing tracks: Kalman update / mark lost / delete; matched slots are listed for the motion analysis ----
-    for (int base = 0; base < b.C; base += kFinishThreads) {
-        const int t = base + tid, g = g0 + t;
-        if (t < b.C && II(b, ID, g) != 0) {
-            const int m = b.match[g];
-            if (m >= 0) {
-                if (II(b, ISLOST, g)) recoveries++;
-                const float* r = dets + ((size_t)s * b.max_dets + m) * det_cols;
-                update_slot(b, g, make_float4(r[0], r[1], r[2], r[3]), false);
-                s_alist[atomicAdd(&s_an, 1)] = t;
-            } else {                                           // mark_as_lost (:299-317)
-                if (!II(b, ISLOST, g)) { II(b, ISLOST, g) = 1; II(b, LOSTF, g) = 0; }
-                II(b, LOSTF, g) += 1; II(b, STREAK, g) = 0;
+    if (T > 0 && D > 0) {
+        if (sparse) {
+            // ---- mutual-best rounds on the pair list.  A pair is accepted when the track is the detection's best free candidate
+            //      by (IoU, lowest track id) and the detection is the track's best free candidate by (IoU, lowest detection
+            //      index): exactly the pairs the reference's descending-IoU greedy walk takes
+            //      (enhanced_multi_target_tracker.py:234-270).  Decisions of a round read only the state of the round's start. ----
+            const int M = (int)M64;
+            const uint4* pairs = b.pairs + (size_t)s * b.pair_cap;
+            while (true) {
+                for (int d = tid; d < D; d += kResolveThreads) { d_best[d] = 0ull; s_list[d] = -1; }
+                for (int i = tid; i < T; i += kResolveThreads) t_best[i] = 0ull;
+                if (tid == 0) s_progress = 0;
+                __syncthreads();
+                for (int e = tid; e < M; e += kResolveThreads) {
+                    const uint4 pr = pairs[e];
+                    const int d = (int)pr.y, i = (int)pr.z;
+                    if (s_dmatch[d] >= 0 || l_match[i] >= 0) continue;
+                    const unsigned long long hi = (unsigned long long)pr.x << 32;   // IoU > 0: bits order like the float
+                    atomicMax(&d_best[d], hi | (unsigned)(0xFFFFFFFFu - pr.w));
+                    atomicMax(&t_best[i], hi | (unsigned)(0xFFFFFFFFu - (unsigned)d));
+                }
+                __syncthreads();
+                // an accepted pair is the unique entry whose key is the maximum of both its detection and its track; it is only
+                // STAGED here (s_list[d]) and committed after a barrier, so every decision of the round reads the round-start state
+                for (int e = tid; e < M; e += kResolveThreads) {
+                    const uint4 pr = pairs[e];
+                    const int d = (int)pr.y, i = (int)pr.z;
+                    if (s_dmatch[d] >= 0 || l_match[i] >= 0) continue;
+                    const unsigned long long hi = (unsigned long long)pr.x << 32;
+                    if (d_best[d] == (hi | (unsigned)(0xFFFFFFFFu - pr.w)) && t_best[i] == (hi | (unsigned)(0xFFFFFFFFu - (unsigned)d))) {
+                        s_list[d] = i; s_progress = 1;
+                    }
+                }
+                __syncthreads();
+                for (int d = tid; d < D; d += kResolveThreads)
+                    if (s_list[d] >= 0) { s_dmatch[d] = s_list[d]; l_match[s_list[d]] = d; }
+                const int progress = s_progress;
+                __syncthreads();
+                if (!progress) break;
             }
-            const int tsu = II(b, TSU, g), age = II(b, AGE, g), hs = II(b, STREAK, g);
-            const bool del = tsu > b.max_lost || (age < 5 && hs == 0 && tsu > 15) || (age < 10 && hs <= 1 && tsu > 30);   // :385-405
-            if (del) { II(b, ID, g) = 0; terminated++; }
+        } else {
+            // ---- dense fallback (pair list overflow / very many candidate tracks): the same rounds with the IoUs recomputed ----
+            int* s_bt = reinterpret_cast<int*>(d_best);
+            float* s_bv = reinterpret_cast<float*>(d_best) + kMaxDetsSmem;
+            while (true) {
+                if (tid == 0) s_progress = 0;
+                for (int d = warp; d < D; d += nwarps) {              // row pass: best free track per free detection
+                    if (s_dmatch[d] >= 0) continue;
+                    const float4 db = s_det[d];
+                    float best = -1.f; int bt = -1, bid = 0x7fffffff;
+                    for (int i = lane; i < T; i += 32) {
+                        if (match[i] >= 0) continue;
+                        const float v = iou_ref(db, cbox[i]);
+                        const int id = cid[i];
+                        if (v >= thr && (v > best || (v == best && id < bid))) { best = v; bt = i; bid = id; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int ot = __shfl_xor_sync(0xffffffffu, bt, o), oid = __shfl_xor_sync(0xffffffffu, bid, o);
+                        if (ob > best || (ob == best && oid < bid)) { best = ob; bt = ot; bid = oid; }
+                    }
+                    if (lane == 0) { s_bt[d] = bt; s_bv[d] = best; }
+                }
+                __syncthreads();
+                for (int d = tid; d < D; d += kResolveThreads) {      // column check against the round-start state
+                    int acc = -1;
+                    if (s_dmatch[d] < 0 && s_bt[d] >= 0) {
+                        const int i = s_bt[d];
+                        const float v = s_bv[d];
+                        const float4 tb = cbox[i];
+                        bool dominated = false;
+                        for (int e = 0; e < D && !dominated; ++e) {
+                            if (e == d || s_dmatch[e] >= 0) continue;
+                            const float ve = iou_ref(s_det[e], tb);
+                            if (ve >= thr && (ve > v || (ve == v && e < d))) dominated = true;
+                        }
+                        if (!dominated) acc = i;
+                    }
+                    s_list[d] = acc;
+                }
+                __syncthreads();
+                for (int d = tid; d < D; d += kResolveThreads)
+                    if (s_list[d] >= 0) { s_dmatch[d] = s_list[d]; match[s_list[d]] = d; s_progress = 1; }
+                __syncthreads();
+                const int progress = s_progress;
+                __syncthreads();
+                if (!progress) break;
+            }
         }
     }
     __syncthreads();
-    // ---- pass 1b: motion analysis of the updated tracks, one warp per track (analyze_slot_warp) ----
-    for (int i = tid >> 5; i < s_an; i += kFinishThreads / 32) analyze_slot_warp(b, g0 + s_alist[i], tid & 31);
+
+    // ---- candidate tracks: Kalman update (:249-297) or mark_as_lost (:299-317); should_delete (:385-405) ----
+    for (int i = tid; i < T; i += kResolveThreads) {
+        const int t = cslot[i], g = g0 + t;
+        const int md = match[i];
+        if (md >= 0) {
+            if (II(b, ISLOST, g)) atomicAdd(&s_cnt[2], 1);                              // successful recovery (:73-79)
+            update_slot(b, g, s_det[md]);
+            s_list[atomicAdd(&s_an, 1)] = t;
+        } else {
+            if (!II(b, ISLOST, g)) { II(b, ISLOST, g) = 1; II(b, LOSTF, g) = 0; }
+            II(b, LOSTF, g) += 1; II(b, STREAK, g) = 0;
+        }
+        const int tsu = II(b, TSU, g), age = II(b, AGE, g), hs = II(b, STREAK, g);
+        const bool del = tsu > b.max_lost || (age < 5 && hs == 0 && tsu > 15) || (age < 10 && hs <= 1 && tsu > 30);
+        if (del) { II(b, ID, g) = 0; atomicAdd(&s_cnt[0], 1); atomicAdd(b.chunk_free + (size_t)s * b.nchunks + t / kChunk, 1); }
+    }
     __syncthreads();
-    // ---- pass 1c: emit in slot order ----
-    for (int base = 0; base < b.C; base += kFinishThreads) {
-        const int t = base + tid, g = g0 + t;
-        int emit = 0;
-        if (t < b.C && II(b, ID, g) != 0)
-            emit = (II(b, STREAK, g) >= b.min_hits || frame <= b.min_hits || II(b, ISLOST, g)) ? 1 : 0;   // multi_target_tracker.py:117-126
+    for (int i = warp; i < s_an; i += nwarps) analyze_slot_warp(b, g0 + s_list[i], lane);
+    __syncthreads();
+    // ---- rows of the candidate tracks, in list (= slot) order, after the sweep's rows ----
+    if (tid == 0) s_emit_base = E1;
+    __syncthreads();
+    int long_term = 0;
+    float* rows = fr.out_rows + (size_t)s * fr.out_cap * B2_TRACK_COLS;
+    const size_t o0 = (size_t)s * fr.out_cap;
+    for (int base = 0; base < T; base += kResolveThreads) {
+        const int i = base + tid;
+        int emit = 0, t = 0, g = 0;
+        if (i < T) {
+            t = cslot[i]; g = g0 + t;
+            if (II(b, ID, g) != 0)
+                emit = (II(b, STREAK, g) >= b.min_hits || frame <= b.min_hits || II(b, ISLOST, g)) ? 1 : 0;   // multi_target_tracker.py:117-126
+        }
         int total;
         const int off = block_exclusive_scan(emit, s_warp, &total);
         const int ebase = s_emit_base;
         if (emit) {
-            // the row goes to shared memory: the emitted rows of a sweep are contiguous in the output, so the block writes
-            // them with coalesced 16-byte stores instead of twenty 4-byte stores per thread at an 80-byte stride
             const int pos = ebase + off;
-            emit_slot(b, g, s_rows + off * B2_TRACK_COLS,
-                      out_traj ? out_traj + ((size_t)s * b.C + pos) * kTraj * 2 : nullptr,
-                      out_traj_len ? out_traj_len + (size_t)s * b.C + pos : nullptr, t, &long_term);
+            const bool fits = pos < fr.out_cap;
+            emit_slot(b, g, fits ? rows + (size_t)pos * B2_TRACK_COLS : nullptr, fits && fr.out_traj ? fr.out_traj + (o0 + pos) * kTraj * 2 : nullptr,
+                      fits && fr.out_traj_len ? fr.out_traj_len + o0 + pos : nullptr, t, &long_term);
         }
         __syncthreads();
-        flush_rows(s_rows, rows + (size_t)ebase * B2_TRACK_COLS, total, tid);
         if (tid == 0) s_emit_base = ebase + total;
         __syncthreads();
     }
 
-    // ---- pass 2: new tracks for unmatched detections, ascending detection index -> ascending ids,
-    //      k-th new track takes the k-th free slot ----
-    const int32_t* dm = b.det_match + (size_t)s * b.max_dets;
+    // ---- new tracks for unmatched detections, ascending detection index -> ascending ids; the k-th new track takes the k-th
+    //      free slot of the stream ----
     const int id0 = b.next_id[s];
-    // rank of each unmatched detection
     int n_new = 0;
-    {
-        // D <= max_dets; serial ranks via scan over chunks
-        for (int base = 0; base < D; base += kFinishThreads) {
-            const int d = base + tid;
-            const int um = (d < D && dm[d] == -1) ? 1 : 0;
-            int total;
-            (void)block_exclusive_scan(um, s_warp, &total);
-            n_new += total;
-        }
+    for (int base = 0; base < D; base += kResolveThreads) {
+        const int d = base + tid;
+        const int um = (d < D && s_dmatch[d] < 0) ? 1 : 0;
+        int total;
+        const int off = block_exclusive_scan(um, s_warp, &total);
+        if (um) s_list[n_new + off] = d;
+        n_new += total;
     }
+    __syncthreads();
+    int created = 0;
     if (n_new > 0) {
-        int det_base = 0;   // rank offset over detection chunks
-        // walk free slots chunk by chunk; for every chunk find which ranks its free slots serve
-        int free_seen = 0;
-        for (int base = 0; base < b.C && free_seen < n_new; base += kFinishThreads) {
+        const bool emit_new = (1 >= b.min_hits) || (frame <= b.min_hits);     // hit_streak = 1
+        const int32_t* cfree = b.chunk_free + (size_t)s * b.nchunks;
+        for (int base = 0; base < b.C && created < n_new; base += kResolveThreads) {
+            // chunks without a free slot (the common case in a full bank) are skipped without touching the slots
+            const int c0 = base / kChunk;
+            int any = 0;
+            for (int k = 0; k < kResolveThreads / kChunk; ++k) if (c0 + k < b.nchunks) any += cfree[c0 + k];
+            if (!any) continue;
             const int t = base + tid, g = g0 + t;
             const int is_free = (t < b.C && II(b, ID, g) == 0) ? 1 : 0;
             int total;
             const int off = block_exclusive_scan(is_free, s_warp, &total);
-            const int rank = free_seen + off;
+            const int rank = created + off;
+            const int ebase = s_emit_base;
+            const int take = min(total, n_new - created);
             if (is_free && rank < n_new) {
-                // find the rank-th unmatched detection (ascending)
-                int cnt = 0, dsel = -1;
-                for (int d = 0; d < D; ++d) { if (dm[d] == -1) { if (cnt == rank) { dsel = d; break; } ++cnt; } }
-                const float* r = dets + ((size_t)s * b.max_dets + dsel) * det_cols;
-                init_slot(b, g, make_float4(r[0], r[1], r[2], r[3]), id0 + rank);
-                b.match[g] = -3;   // marks "created this frame" for the emit pass below
-            }
-            free_seen += total;
-        }
-        (void)det_base;
-        const int created = min(n_new, free_seen);
-        // emit new tracks (hit_streak = 1): condition identical to pass 1
-        const bool emit_new = (1 >= b.min_hits) || (frame <= b.min_hits);
-        if (emit_new) {
-            for (int base = 0; base < b.C; base += kFinishThreads) {
-                const int t = base + tid, g = g0 + t;
-                const int emit = (t < b.C && II(b, ID, g) != 0 && b.match[g] == -3) ? 1 : 0;
-                int total;
-                const int off = block_exclusive_scan(emit, s_warp, &total);
-                const int ebase = s_emit_base;
-                if (emit) {
+                init_slot(b, g, s_det[s_list[rank]], id0 + rank);
+                if (emit_new) {
                     const int pos = ebase + off;
-                    emit_slot(b, g, s_rows + off * B2_TRACK_COLS,
-                              out_traj ? out_traj + ((size_t)s * b.C + pos) * kTraj * 2 : nullptr,
-                              out_traj_len ? out_traj_len + (size_t)s * b.C + pos : nullptr, t, &long_term);
+                    const bool fits = pos < fr.out_cap;
+                    emit_slot(b, g, fits ? rows + (size_t)pos * B2_TRACK_COLS : nullptr, fits && fr.out_traj ? fr.out_traj + (o0 + pos) * kTraj * 2 : nullptr,
+                              fits && fr.out_traj_len ? fr.out_traj_len + o0 + pos : nullptr, t, &long_term);
                 }
-                __syncthreads();
-                flush_rows(s_rows, rows + (size_t)ebase * B2_TRACK_COLS, total, tid);
-                if (tid == 0) s_emit_base = ebase + total;
-                __syncthreads();
             }
+            created += take;
+            __syncthreads();
+            if (tid == 0 && emit_new) s_emit_base = ebase + take;
+            __syncthreads();
         }
-        if (tid == 0) { s_created = created; s_stats[5] = n_new - created; }
     }
+    if (long_term) atomicAdd(&s_cnt[1], long_term);
     __syncthreads();
 
-    // ---- stats (enhanced_multi_target_tracker.py:32-38) ----
-    atomicAdd((unsigned long long*)&s_stats[1], (unsigned long long)terminated);
-    atomicAdd((unsigned long long*)&s_stats[3], (unsigned long long)long_term);
-    atomicAdd((unsigned long long*)&s_stats[4], (unsigned long long)recoveries);
-    // active count
-    int active = 0;
-    for (int t = tid; t < b.C; t += kFinishThreads) active += II(b, ID, g0 + t) != 0;
-    atomicAdd((unsigned long long*)&s_stats[2], (unsigned long long)active);
-    __syncthreads();
+    // ---- stats (enhanced_multi_target_tracker.py:32-38), counters ----
     if (tid == 0) {
+        int32_t* fc = b.fcnt + s * 4;
         long long* st = b.stats + (size_t)s * 8;
-        st[0] += s_created; st[1] += s_stats[1]; st[2] = s_stats[2]; st[3] += s_stats[3]; st[4] += s_stats[4]; st[5] += s_stats[5];
+        const int terminated = fc[0] + s_cnt[0], lt = fc[1] + s_cnt[1];
+        fc[0] = 0; fc[1] = 0;
+        st[0] += created; st[1] += terminated; st[2] += created - terminated; st[3] += lt; st[4] += s_cnt[2]; st[5] += n_new - created;
         // the reference numbers every unmatched detection; ids keep advancing even if the bank overflowed
         b.next_id[s] = id0 + n_new;
         b.frame_count[s] = frame;
-        out_counts[s] = s_emit_base;
+        fr.out_counts[s] = s_emit_base;
     }
 }
 
 __global__ void export_kernel(const Bank b, int s, float* x, float* P, int32_t* meta, int32_t* n_out) {
-    // single thread block; serialise in ascending id order is done on the host -- here slot order
+    // single thread block, slot order (the host orders by id)
     __shared__ int cnt;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
@@ -786,6 +816,69 @@ __global__ void export_kernel(const Bank b, int s, float* x, float* P, int32_t* 
     if (threadIdx.x == 0) *n_out = cnt;
 }
 
+__global__ void export_motion_kernel(const Bank b, int s, float* out, int32_t* n_out) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < b.C; t += blockDim.x) {
+        const int g = s * b.C + t;
+        if (II(b, ID, g) == 0) continue;
+        float* o = out + (size_t)atomicAdd(&cnt, 1) * 8;
+        o[0] = __int_as_float(II(b, ID, g));
+        for (int j = 0; j < 6; ++j) o[1 + j] = FF(b, VAVGX + j, g);
+        o[7] = __int_as_float(II(b, NVEL, g));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *n_out = cnt;
+}
+
+// bank regrid for b2_tracker_grow: rows of a field-major [rows][S*C] array move to [rows][S*C2]
+__global__ void regrid_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int rows, int S, int C, int C2) {
+    const size_t n = (size_t)rows * S * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / ((size_t)S * C), rem = i % ((size_t)S * C);
+        const size_t s = rem / C, t = rem % C;
+        dst[(r * S + s) * C2 + t] = src[i];
+    }
+}
+__global__ void fill_i32(int32_t* p, int n, int v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+struct Layout { size_t f, i, v, t, agg, cf, fc, tk, cs, cb, ci, cm, pr, ni, fcn, st, total; };
+
+Layout bank_layout(int S, int C, int max_dets, int nchunks, int pair_cap) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t N = (size_t)S * C;
+    Layout L;
+    size_t off = 0;
+    L.f = off; off += up(N * NFF * 4);
+    L.i = off; off += up(N * NIF * 4);
+    L.v = off; off += up(N * kVelRing * 2 * 4);
+    L.t = off; off += up(N * kTraj * 2 * 4);
+    L.agg = off; off += up((size_t)S * nchunks * 8);
+    L.cf = off; off += up((size_t)S * nchunks * 4);
+    L.fc = off; off += up((size_t)S * 4 * 4);
+    L.tk = off; off += up(4);
+    L.cs = off; off += up(N * 4);
+    L.cb = off; off += up(N * 16);
+    L.ci = off; off += up(N * 4);
+    L.cm = off; off += up(N * 4);
+    L.pr = off; off += up((size_t)S * pair_cap * 16);
+    L.ni = off; off += up((size_t)S * 4);
+    L.fcn = off; off += up((size_t)S * 4);
+    L.st = off; off += up((size_t)S * 8 * 8);
+    L.total = off;
+    (void)max_dets;
+    return L;
+}
+
+void bank_bind(Bank& b, char* a, const Layout& L) {
+    b.f = (float*)(a + L.f); b.i = (int32_t*)(a + L.i); b.vel = (float*)(a + L.v); b.traj = (float*)(a + L.t);
+    b.agg = (unsigned long long*)(a + L.agg); b.chunk_free = (int32_t*)(a + L.cf); b.fcnt = (int32_t*)(a + L.fc);
+    b.ticket = (unsigned int*)(a + L.tk); b.ctrk_slot = (int32_t*)(a + L.cs); b.cbox = (float4*)(a + L.cb);
+    b.cid = (int32_t*)(a + L.ci); b.cmatch = (int32_t*)(a + L.cm); b.pairs = (uint4*)(a + L.pr);
+    b.next_id = (int32_t*)(a + L.ni); b.frame_count = (int32_t*)(a + L.fcn); b.stats = (long long*)(a + L.st);
+}
+
 }  // namespace
 
 struct b2_tracker { b2_tracker_impl impl; };
@@ -793,33 +886,21 @@ struct b2_tracker { b2_tracker_impl impl; };
 extern "C" int b2_tracker_create(int n_streams, int capacity, int max_dets, int max_lost_frames, int min_hits,
                                  float iou_threshold, b2_tracker_t** out) {
     B2_REQUIRE(out, "tracker_create: out is null");
-    B2_REQUIRE(n_streams >= 1 && capacity >= 1 && max_dets >= 1 && max_dets <= kMaxDetsSmem,
-               "tracker_create: need n_streams>=1, capacity>=1, 1<=max_dets<=%d", kMaxDetsSmem);
+    B2_REQUIRE(n_streams >= 1 && capacity >= 1 && capacity <= 65535 && max_dets >= 1 && max_dets <= kMaxDetsSmem,
+               "tracker_create: need n_streams>=1, 1<=capacity<=65535, 1<=max_dets<=%d", kMaxDetsSmem);
+    B2_REQUIRE((long long)n_streams * capacity < (1ll << 31), "tracker_create: n_streams*capacity must be below 2^31");
     b2_tracker* t = new (std::nothrow) b2_tracker();
     if (!t) { b2_set_error("out of host memory"); return B2_ERR_STATE; }
     Bank& b = t->impl.b;
     b.S = n_streams; b.C = capacity; b.N = n_streams * capacity; b.max_dets = max_dets;
+    b.nchunks = b2_ceil_div(capacity, kChunk);
+    b.pair_cap = 16 * max_dets < 1024 ? 1024 : 16 * max_dets;
     b.max_lost = max_lost_frames; b.min_hits = min_hits; b.iou_thr = iou_threshold;
-    const size_t N = (size_t)b.N;
-    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    size_t off = 0;
-    const size_t o_f = off; off += up(N * NFF * 4);
-    const size_t o_i = off; off += up(N * NIF * 4);
-    const size_t o_v = off; off += up(N * kVelRing * 2 * 4);
-    const size_t o_t = off; off += up(N * kTraj * 2 * 4);
-    const size_t o_b = off; off += up(N * 16);
-    const size_t o_m = off; off += up(N * 4);
-    const size_t o_dm = off; off += up((size_t)n_streams * max_dets * 4);
-    const size_t o_ni = off; off += up((size_t)n_streams * 4);
-    const size_t o_fc = off; off += up((size_t)n_streams * 4);
-    const size_t o_st = off; off += up((size_t)n_streams * 8 * 8);
-    cudaError_t e = cudaMalloc(&t->impl.arena, off);
-    if (e != cudaSuccess) { b2_set_error("tracker_create: cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(e)); delete t; return B2_ERR_CUDA; }
-    t->impl.arena_bytes = off;
-    char* a = (char*)t->impl.arena;
-    b.f = (float*)(a + o_f); b.i = (int32_t*)(a + o_i); b.vel = (float*)(a + o_v); b.traj = (float*)(a + o_t);
-    b.pbox = (float4*)(a + o_b); b.match = (int32_t*)(a + o_m); b.det_match = (int32_t*)(a + o_dm);
-    b.next_id = (int32_t*)(a + o_ni); b.frame_count = (int32_t*)(a + o_fc); b.stats = (long long*)(a + o_st);
+    const Layout L = bank_layout(b.S, b.C, max_dets, b.nchunks, b.pair_cap);
+    cudaError_t e = cudaMalloc(&t->impl.arena, L.total);
+    if (e != cudaSuccess) { b2_set_error("tracker_create: cudaMalloc(%zu) failed: %s", L.total, cudaGetErrorString(e)); delete t; return B2_ERR_CUDA; }
+    t->impl.arena_bytes = L.total;
+    bank_bind(b, (char*)t->impl.arena, L);
     *out = t;
     return b2_tracker_reset(t, nullptr);
 }
@@ -829,10 +910,6 @@ extern "C" int b2_tracker_destroy(b2_tracker_t* t) {
     cudaFree(t->impl.arena);
     delete t;
     return B2_OK;
-}
-
-namespace {
-__global__ void fill_i32(int32_t* p, int n, int v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 }
 
 extern "C" int b2_tracker_reset(b2_tracker_t* t, void* stream) {
@@ -845,43 +922,63 @@ extern "C" int b2_tracker_reset(b2_tracker_t* t, void* stream) {
     return B2_OK;
 }
 
+extern "C" int b2_tracker_capacity(b2_tracker_t* t) { return t ? t->impl.b.C : 0; }
+
+extern "C" int b2_tracker_grow(b2_tracker_t* t, int new_capacity, void* stream) {
+    B2_REQUIRE(t, "tracker_grow: null handle");
+    Bank& b = t->impl.b;
+    B2_REQUIRE(new_capacity > b.C && new_capacity <= 65535, "tracker_grow: new capacity %d must be in (%d, 65535]", new_capacity, b.C);
+    B2_REQUIRE((long long)b.S * new_capacity < (1ll << 31), "tracker_grow: n_streams*capacity must be below 2^31");
+    cudaStream_t st = (cudaStream_t)stream;
+    Bank nb = b;
+    nb.C = new_capacity; nb.N = b.S * new_capacity; nb.nchunks = b2_ceil_div(new_capacity, kChunk);
+    const Layout L = bank_layout(nb.S, nb.C, nb.max_dets, nb.nchunks, nb.pair_cap);
+    void* arena = nullptr;
+    cudaError_t e = cudaMalloc(&arena, L.total);
+    if (e != cudaSuccess) { b2_set_error("tracker_grow: cudaMalloc(%zu) failed: %s", L.total, cudaGetErrorString(e)); return B2_ERR_CUDA; }
+    bank_bind(nb, (char*)arena, L);
+    B2_CUDA(cudaMemsetAsync(arena, 0, L.total, st));
+    const int grid = b2_num_sms() * 8;
+    regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.f, (uint32_t*)nb.f, NFF, b.S, b.C, nb.C);
+    regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.i, (uint32_t*)nb.i, NIF, b.S, b.C, nb.C);
+    regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.vel, (uint32_t*)nb.vel, kVelRing * 2, b.S, b.C, nb.C);
+    regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.traj, (uint32_t*)nb.traj, kTraj * 2, b.S, b.C, nb.C);
+    B2_CUDA(cudaMemcpyAsync(nb.next_id, b.next_id, (size_t)b.S * 4, cudaMemcpyDeviceToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(nb.frame_count, b.frame_count, (size_t)b.S * 4, cudaMemcpyDeviceToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(nb.stats, b.stats, (size_t)b.S * 64, cudaMemcpyDeviceToDevice, st));
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaStreamSynchronize(st));
+    b2_count_launch(4);
+    cudaFree(t->impl.arena);
+    t->impl.arena = arena; t->impl.arena_bytes = L.total;
+    b = nb;
+    return B2_OK;
+}
+
 extern "C" int b2_tracker_bank_predict(b2_tracker_t* t, void* stream) {
     B2_REQUIRE(t, "tracker: null handle");
-    launch_bank_predict(t->impl.b, (cudaStream_t)stream);
+    const Bank& b = t->impl.b;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b.N % 4 == 0) bank_predict4_kernel<<<b2_ceil_div(b.N / 4, 256), 256, 0, st>>>(b);
+    else bank_predict_kernel<<<b2_ceil_div(b.N, 256), 256, 0, st>>>(b);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
 }
 
 extern "C" int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_cols, const int32_t* det_counts,
-                                 float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, void* stream) {
+                                 float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, int out_cap, void* stream) {
     B2_REQUIRE(t && dets && det_counts && out_rows && out_counts, "tracker_update: null pointer");
+    B2_REQUIRE(out_cap >= 1, "tracker_update: out_cap must be >= 1");
     B2_REQUIRE(det_cols >= 4, "tracker_update: det_cols must be >= 4");
+    B2_REQUIRE((out_traj == nullptr) == (out_traj_len == nullptr), "tracker_update: out_traj and out_traj_len go together");
     const Bank& b = t->impl.b;
     cudaStream_t st = (cudaStream_t)stream;
-    launch_bank_predict(b, st);
-    const size_t track_smem = (size_t)b.C * 28;
-    if (track_smem <= 160 * 1024) {
-        // sparse matching: best-candidate keys (8 B per track, 8 KB for the detections) + the pair list (8 B per pair) in what
-        // is left of ~190 KB of shared memory, up to 8192 pairs
-        const size_t fixed = track_smem + (size_t)b.C * 8 + kMaxDetsSmem * 8 + 16;
-        size_t cap = fixed < 190 * 1024 ? (190 * 1024 - fixed) / 8 : 0;
-        cap = cap > 8192 ? 8192 : (cap < 512 ? 0 : cap);
-        // the list must not cost occupancy: banks whose track arrays still allow two CTAs per SM (and have more streams than
-        // SMs) keep the small footprint and the dense rounds
-        if (track_smem + 30 * 1024 <= 113 * 1024 && b.S > b2_num_sms()) cap = 0;
-        const size_t assoc_smem = cap ? fixed + cap * 8 : track_smem;
-        if (assoc_smem > 16 * 1024) {
-            static size_t granted = 0;
-            if (assoc_smem > granted) { B2_CUDA(cudaFuncSetAttribute(associate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assoc_smem)); granted = assoc_smem; }
-        }
-        associate_kernel<<<b.S, kAssocThreads, assoc_smem, st>>>(b, dets, det_cols, det_counts, (int)cap);
-    } else {
-        associate_global_kernel<<<b.S, kAssocThreads, 0, st>>>(b, dets, det_cols, det_counts);
-    }
-    finish_kernel<<<b.S, kFinishThreads, 0, st>>>(b, dets, det_cols, det_counts, out_rows, out_counts, out_traj, out_traj_len);
+    const Frame fr{dets, det_cols, det_counts, out_rows, out_counts, out_traj, out_traj_len, out_cap};
+    sweep_kernel<<<b.S * b.nchunks, kChunk, 0, st>>>(b, fr);
+    resolve_kernel<<<b.S, kResolveThreads, 0, st>>>(b, fr);
     B2_CUDA(cudaGetLastError());
-    b2_count_launch(3);
+    b2_count_launch(2);
     return B2_OK;
 }
 
@@ -917,11 +1014,38 @@ extern "C" int b2_tracker_export(b2_tracker_t* t, int stream_idx, float* x_host,
     return B2_OK;
 }
 
+extern "C" int b2_tracker_export_motion(b2_tracker_t* t, int stream_idx, float* motion_host, int32_t* n_tracks_host) {
+    B2_REQUIRE(t && stream_idx >= 0 && stream_idx < t->impl.b.S && motion_host && n_tracks_host, "tracker_export_motion: bad argument");
+    const Bank& b = t->impl.b;
+    B2_CUDA(cudaDeviceSynchronize());
+    float* dm = nullptr; int32_t* dn = nullptr;
+    B2_CUDA(cudaMalloc(&dm, (size_t)b.C * 8 * 4)); B2_CUDA(cudaMalloc(&dn, 4));
+    export_motion_kernel<<<1, 256>>>(b, stream_idx, dm, dn);
+    b2_count_launch(1);
+    int n = 0;
+    cudaError_t e = cudaMemcpy(&n, dn, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(motion_host, dm, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dm); cudaFree(dn);
+    B2_CUDA(e);
+    *n_tracks_host = n;
+    return B2_OK;
+}
+
+extern "C" int b2_tracker_stats(b2_tracker_t* t, long long* stats_dev_out, void* stream) {
+    // device-to-device snapshot of the [S][8] counters (created, terminated, active, long_term, recoveries, dropped, -, -):
+    // lets a pipeline download them with its rows instead of synchronising on b2_tracker_export
+    B2_REQUIRE(t && stats_dev_out, "tracker_stats: null pointer");
+    B2_CUDA(cudaMemcpyAsync(stats_dev_out, t->impl.b.stats, (size_t)t->impl.b.S * 64, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B2_OK;
+}
+
 extern "C" int b2_tracker_bytes_per_track(int* predict_bytes, int* update_bytes) {
-    // predict: read x[8] P[6] id age tsu thead tlen (19 words) ; write x[4] P[6] age tsu thead tlen + 2 traj + pbox(4) + match (21 words)
-    if (predict_bytes) *predict_bytes = (19 + 21) * 4;
-    // update (matched): read match, id, islost, x[8], P[6], counters(4), vhead, nvel, thead, tlen, det(4) + ring re-scan 2*50*... (up to 3 passes of 100 floats)
-    if (update_bytes) *update_bytes = (1 + 2 + 14 + 4 + 4 + 4) * 4 + (14 + 6 + 4 + 2 + 2 + 6) * 4 + 100 * 4;
+    // sweep, per coasting (unmatched, reported) track: read id x[8] P[6] motion[6] age hits tsu lostf islost tlen thead
+    // (28 words), write x[4] P[6] age tsu tlen thead streak lostf islost + 2 trajectory floats + the 20-word row (39 words)
+    if (predict_bytes) *predict_bytes = (28 + 39) * 4;
+    // update (matched): the candidate lists (slot, box, id, pair 16 B), the Kalman update of x[8] P[6], counters, ring and
+    // trajectory pushes, the ring re-scan of the motion analysis (up to 100 floats) and the row
+    if (update_bytes) *update_bytes = (6 + 4) * 4 + (14 + 14 + 8 + 4) * 4 + 100 * 4 + 6 * 4 + 20 * 4;
     return B2_OK;
 }
 

@@ -4,7 +4,8 @@ This is the loop body of the project driver (kalman/aircraft_detection_tracking.
 ``model(frame)`` -> ``boxes.xyxy/conf`` -> ``tracker.update(dets)``) for S streams at once:
 
     uint8 frames [S][h][w][3] --stem+forward--> head logits --decode--> candidates --NMS+scale--> dets [S][300][6]
-        --Kalman bank (predict / associate / update / lifecycle)--> track rows [S][capacity][20]
+        --Kalman bank (sweep: predict / IoU candidates / coasting tracks; resolve: match / update / create)-->
+        track rows [S][max_tracks_out][20] + counts [S] + bank counters [S][8]
 
 Everything between the frame upload and the result download stays on the GPU, on one CUDA stream, with no
 host synchronisation.  Streams are independent (one tracker per stream in the reference), so multi-GPU
@@ -49,10 +50,14 @@ def shard_streams(n_streams, rank, world_size):
 class DetectTrackPipeline:
     def __init__(self, model="yolov8s-p2", n_streams=1, frame_hw=(512, 640), imgsz=640, conf=0.15, iou=0.6, max_det=300,
                  max_lost_frames=150, min_hits=1, iou_threshold=0.1, capacity=512, state_dict=None, seed=0, nc=None,
-                 nms_mode="exact", overlap_post=False):
+                 nms_mode="exact", overlap_post=False, max_tracks_out=None):
         """overlap_post: run NMS + tracker of step t on a second CUDA stream while the forward of step t+1 runs on the
         caller's stream (the small latency-bound launches fill the tails of the conv kernels).  The returned device
-        tensors are then valid only after ``join()``."""
+        tensors are then valid only after ``join()``.
+        capacity: track slots per stream.  The reference's track list is unbounded; ``results()`` raises if a detection was
+        ever dropped for lack of a slot and grows the bank (x2) once a stream uses more than half of it.
+        max_tracks_out: rows per stream of the result block (default: capacity).  The download moves exactly this block,
+        so a caller that expects tens of tracks per stream keeps it small; ``results()`` raises if a stream reported more."""
         import torch
 
         self.device = _lib.require_cuda()
@@ -66,7 +71,10 @@ class DetectTrackPipeline:
             raise NotImplementedError("pipeline frames must not need a resize (use YOLO.predict for the general letterbox)")
         self.conf, self.iou, self.nms_mode = float(conf), float(iou), nms_mode
         self.detect = DetectPipeline(self.spec, sd, self.S, self.H, self.W, max_det)
-        self.bank = TrackerBank(self.S, capacity, max_det, max_lost_frames, min_hits, iou_threshold)
+        self.max_det = int(max_det)
+        self.bank = TrackerBank(self.S, capacity, max_det, max_lost_frames, min_hits, iou_threshold,
+                                max_out=min(int(max_tracks_out), int(capacity)) if max_tracks_out else None)
+        self._fixed_out = bool(max_tracks_out)
         self.flops_per_frame = self.detect.engine.flops_per_image
         # double-buffered staging for the host-facing path
         self._copy_stream = torch.cuda.Stream()
@@ -83,10 +91,16 @@ class DetectTrackPipeline:
         self._step_done = torch.cuda.Event()
         self._rows_downloaded = torch.cuda.Event()
         self._rows_downloaded.record()
-        self.host_rows = torch.empty((self.S, capacity, _lib.TRACK_COLS), dtype=torch.float32).pin_memory()
-        self.host_counts = torch.empty((self.S,), dtype=torch.int32).pin_memory()
         self.h2d_bytes_per_step = self.S * self.h0 * self.w0 * 3
-        self.d2h_bytes_per_step = self.host_rows.numel() * 4 + self.host_counts.numel() * 4
+        self._alloc_host()
+
+    def _alloc_host(self):
+        import torch
+
+        self.host_rows = torch.empty((self.S, self.bank.max_out, _lib.TRACK_COLS), dtype=torch.float32).pin_memory()
+        self.host_counts = torch.zeros((self.S,), dtype=torch.int32).pin_memory()
+        self.host_stats = torch.zeros((self.S, 8), dtype=torch.int64).pin_memory()
+        self.d2h_bytes_per_step = self.host_rows.numel() * 4 + self.host_counts.numel() * 4 + self.host_stats.numel() * 8
 
     def step_device(self, frames_u8, with_trajectory=False, stream=None):
         """frames_u8: CUDA uint8 [S][h][w][3] BGR.  Returns (track rows [S][capacity][20], counts [S]) on the GPU."""
@@ -136,6 +150,7 @@ class DetectTrackPipeline:
             self._d2h_stream.wait_event(done)
             self.host_rows.copy_(rows, non_blocking=True)
             self.host_counts.copy_(counts, non_blocking=True)
+            self.host_stats.copy_(self.bank.stats_async(self._d2h_stream), non_blocking=True)
             self._rows_downloaded.record(self._d2h_stream)
         return self.host_rows, self.host_counts
 
@@ -146,6 +161,33 @@ class DetectTrackPipeline:
 
         torch.cuda.current_stream().wait_event(self._rows_downloaded)
         torch.cuda.current_stream().wait_event(self._post_done)
+
+
+    def results(self):
+        """Synchronise the last ``step_host`` and return its host block (rows [S][max_tracks_out][20], counts [S]) after
+        checking that it is the reference's result: no detection was dropped for lack of a track slot (the reference's list
+        is unbounded, enhanced_multi_target_tracker.py:92-101) and no stream reported more rows than the block holds.
+        Grows the bank ahead of need (a stream above half its capacity doubles it)."""
+        self._rows_downloaded.synchronize()
+        self._post_done.synchronize()
+        check_bank(self.host_stats, self.host_counts, self.bank.capacity, self.bank.max_out)
+        if int(self.host_stats[:, 2].max()) + 2 * self.max_det > self.bank.capacity and self.bank.capacity < 65535:
+            self.bank.grow(min(65535, 2 * self.bank.capacity))
+            if not self._fixed_out:
+                self._alloc_host()
+        return self.host_rows, self.host_counts
+
+
+def check_bank(stats, counts, capacity, max_out):
+    """stats: [S][8] int64 bank counters, counts: [S] rows reported.  Raises if the bank lost a detection or rows."""
+    dropped = int(stats[:, 5].sum())
+    if dropped:
+        s = int(stats[:, 5].argmax())
+        raise RuntimeError(f"track bank overflow: {dropped} detections found no free slot (first in stream {s}, capacity={capacity}); "
+                           "the reference never drops a detection -- raise `capacity`")
+    over = int(counts.max()) if counts.numel() else 0
+    if over > max_out:
+        raise RuntimeError(f"result block too small: a stream reported {over} tracks, max_tracks_out={max_out}")
 
 
 def gather_results(rows, counts, group=None):

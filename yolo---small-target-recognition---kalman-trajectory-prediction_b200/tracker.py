@@ -24,22 +24,34 @@ _STAT_KEYS = ("total_tracks_created", "total_tracks_terminated", "current_active
 
 
 class TrackerBank:
-    """S independent multi-target trackers (one per video stream) resident on one GPU."""
+    """S independent multi-target trackers (one per video stream) resident on one GPU.
 
-    def __init__(self, n_streams, capacity=256, max_dets=300, max_lost_frames=450, min_hits=3, iou_threshold=0.3, device=None):
-        import torch
+    ``capacity`` bounds the simultaneously live tracks per stream (the reference's list is unbounded,
+    enhanced_multi_target_tracker.py:92-101): ``grow()`` enlarges the bank in place, ``stats_async()`` /
+    ``export()`` expose the ``dropped`` counter, and the callers in this package (EnhancedMultiTargetTracker,
+    DetectTrackPipeline) grow ahead of need and raise if a detection was ever dropped.
+    ``max_out`` (default: capacity) is the number of rows per stream the output block holds."""
 
+    def __init__(self, n_streams, capacity=256, max_dets=300, max_lost_frames=450, min_hits=3, iou_threshold=0.3, device=None,
+                 max_out=None):
         self.device = device or _lib.require_cuda()
         self.lib = _lib.load()
         self.S, self.capacity, self.max_dets = int(n_streams), int(capacity), int(max_dets)
         self.max_lost_frames, self.min_hits, self.iou_threshold = int(max_lost_frames), int(min_hits), float(iou_threshold)
+        self._follow_capacity = max_out is None
+        self.max_out = self.capacity if max_out is None else int(max_out)
         self._h = C.c_void_p()
         _lib.check(self.lib.b2_tracker_create(self.S, self.capacity, self.max_dets, self.max_lost_frames, self.min_hits,
                                               self.iou_threshold, C.byref(self._h)))
-        self.rows = torch.zeros((self.S, self.capacity, TRACK_COLS), dtype=torch.float32, device=self.device)
+        self._alloc_outputs()
+
+    def _alloc_outputs(self):
+        import torch
+
+        self.rows = torch.zeros((self.S, self.max_out, TRACK_COLS), dtype=torch.float32, device=self.device)
         self.counts = torch.zeros((self.S,), dtype=torch.int32, device=self.device)
-        self.traj = torch.zeros((self.S, self.capacity, TRAJ_LEN, 2), dtype=torch.float32, device=self.device)
-        self.traj_len = torch.zeros((self.S, self.capacity), dtype=torch.int32, device=self.device)
+        self.traj = self.traj_len = None
+        self.stats_dev = torch.zeros((self.S, 8), dtype=torch.int64, device=self.device)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -51,17 +63,36 @@ class TrackerBank:
     def reset(self):
         _lib.check(self.lib.b2_tracker_reset(self._h, _lib.stream_ptr()))
 
+    def grow(self, new_capacity):
+        """Enlarge every stream's bank to ``new_capacity`` slots (state, ids and slot indices are kept; synchronises)."""
+        _lib.check(self.lib.b2_tracker_grow(self._h, int(new_capacity), _lib.stream_ptr()))
+        self.capacity = int(new_capacity)
+        if self._follow_capacity:
+            self.max_out = self.capacity
+            self._alloc_outputs()
+
     def update(self, dets, det_counts, with_trajectory=True, stream=None):
         """dets: CUDA float32 [S][max_dets][cols>=4] rows x1,y1,x2,y2,...; det_counts: CUDA int32 [S].
-        Returns (rows [S][capacity][20], counts [S]) device tensors (views of internal buffers)."""
+        Returns (rows [S][max_out][20], counts [S]) device tensors (views of internal buffers)."""
+        import torch
+
         assert dets.is_cuda and dets.is_contiguous() and dets.shape[0] == self.S and dets.shape[1] == self.max_dets
+        if with_trajectory and self.traj is None:
+            self.traj = torch.zeros((self.S, self.max_out, TRAJ_LEN, 2), dtype=torch.float32, device=self.device)
+            self.traj_len = torch.zeros((self.S, self.max_out), dtype=torch.int32, device=self.device)
         _lib.check(self.lib.b2_tracker_update(self._h, _lib.ptr(dets), dets.shape[2], _lib.ptr(det_counts), _lib.ptr(self.rows),
                                               _lib.ptr(self.counts), _lib.ptr(self.traj) if with_trajectory else None,
-                                              _lib.ptr(self.traj_len) if with_trajectory else None, _lib.stream_ptr(stream)))
+                                              _lib.ptr(self.traj_len) if with_trajectory else None, self.max_out,
+                                              _lib.stream_ptr(stream)))
         return self.rows, self.counts
 
+    def stats_async(self, stream=None):
+        """[S][8] int64 device snapshot {created, terminated, active, long_term, recoveries, dropped, 0, 0}, stream-ordered."""
+        _lib.check(self.lib.b2_tracker_stats(self._h, _lib.ptr(self.stats_dev), _lib.stream_ptr(stream)))
+        return self.stats_dev
+
     def predict_only(self, stream=None):
-        """Bank predict kernel alone (roofline measurement)."""
+        """AircraftKalmanTracker.predict alone on every live track."""
         _lib.check(self.lib.b2_tracker_bank_predict(self._h, _lib.stream_ptr(stream)))
 
     def export(self, stream_idx=0):
@@ -77,6 +108,14 @@ class TrackerBank:
         k = n.value
         order = np.argsort(meta[:k, 0], kind="stable")          # reference list order == ascending track id
         return x[:k][order], P[:k].reshape(k, 8, 8)[order], meta[:k][order], np.array(list(stats), np.int64)
+
+    def export_motion(self, stream_idx=0):
+        """prediction_confidence of one stream's live tracks, ascending track id (synchronises)."""
+        m = np.zeros((self.capacity, 8), np.float32)
+        n = C.c_int32()
+        _lib.check(self.lib.b2_tracker_export_motion(self._h, stream_idx, m.ctypes.data_as(C.c_void_p), C.byref(n)))
+        m = m[:n.value]
+        return m[np.argsort(m[:, 0].copy().view(np.int32), kind="stable"), 6]
 
     @staticmethod
     def bytes_per_track():
@@ -124,8 +163,9 @@ class _TrackView:
 class EnhancedMultiTargetTracker:
     """Drop-in for kalman/enhanced_multi_target_tracker.py:4 (single stream).
 
-    ``capacity`` / ``max_dets`` bound the number of simultaneously live tracks and detections per frame
-    (the reference lists are unbounded); exceeding them raises instead of silently dropping.
+    The reference's track list is unbounded; the bank behind this class starts at ``capacity`` slots and doubles
+    (``TrackerBank.grow``) before a frame could overflow it, so no detection is ever dropped.  ``max_dets`` bounds the
+    detections of one frame (the NMS cap of the detector, 300); more raise ``ValueError``.
     """
 
     def __init__(self, max_lost_frames=450, min_hits=3, iou_threshold=0.3, capacity=512, max_dets=300, verbose=False):
@@ -148,6 +188,10 @@ class EnhancedMultiTargetTracker:
         n = len(detections)
         if n > self.bank.max_dets:
             raise ValueError(f"{n} detections exceed max_dets={self.bank.max_dets}")
+        # every detection may found a track: make room first (the reference appends without bound, :92-101)
+        need = self.stats["current_active_tracks"] + n
+        if need > self.bank.capacity:
+            self.bank.grow(min(65535, max(2 * self.bank.capacity, need)))
         if n:
             self._host[:n] = torch.as_tensor(np.asarray([list(d)[:4] for d in detections], dtype=np.float32))
             self._dets[0, :n].copy_(self._host[:n], non_blocking=True)
@@ -161,14 +205,12 @@ class EnhancedMultiTargetTracker:
         return rows_to_dicts(r, tr, tl)
 
     def _refresh_stats(self):
-        import torch  # noqa: F401
-
         st = (C.c_longlong * 8)()
         _lib.check(self.bank.lib.b2_tracker_export(self.bank._h, 0, None, None, None, None, st))
         for k, v in zip(_STAT_KEYS, list(st)[:5]):
             self.stats[k] = int(v)
         self.frame_count, self.next_track_id = int(st[5]), int(st[6])
-        if st[7]:
+        if st[7]:      # cannot happen below 65535 live tracks: update() grows the bank first
             raise RuntimeError(f"track bank overflow: {int(st[7])} detections found no free slot (capacity={self.bank.capacity})")
 
     @property
@@ -179,10 +221,11 @@ class EnhancedMultiTargetTracker:
     def get_statistics(self):
         """enhanced_multi_target_tracker.py:288-304."""
         x, P, meta, stats = self.bank.export(0)
+        conf = self.bank.export_motion(0)
         d = dict(self.stats)
         d["frame_count"] = self.frame_count
         d["tracker_details"] = [{"track_id": f"T{int(m[0]):03d}", "age": int(m[1]), "hits": int(m[2]), "lost_frames": int(m[5]),
-                                 "is_lost": bool(m[6])} for m in meta]
+                                 "is_lost": bool(m[6]), "confidence": float(c)} for m, c in zip(meta, conf)]
         return d
 
 
