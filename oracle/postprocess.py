@@ -3,6 +3,10 @@
 Restates:
   letterbox geometry      ultralytics/data/augment.py:1692-1733 (LetterBox.__call__), pad value 114,
                           engine/predictor.py:152-175 (BGR->RGB, HWC->CHW, /255)
+  cv2.resize INTER_LINEAR third-party (opencv-python>=4.6, pyproject.toml:66; call site augment.py:1718): uint8 path of
+                          cv::resize -- 11-bit fixed-point coefficients, horizontal pass in int32, vertical pass
+                          ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2; pinned against cv2 itself in
+                          tests/test_oracle_vs_golden.py::test_resize_oracle_is_cv2
   Detect._inference       ultralytics/nn/modules/head.py:152-187
   DFL.forward             ultralytics/nn/modules/block.py:78-81
   make_anchors/dist2bbox  ultralytics/utils/tal.py:367-391
@@ -49,6 +53,40 @@ def letterbox_pad_only(img, new_shape=(640, 640), auto=True, stride=32):
     assert (w0, h0) == new_unpad, "resize path not covered by letterbox_pad_only"
     out = np.full((h0 + top + bottom, w0 + left + right, img.shape[2]), 114, img.dtype)
     out[top:top + h0, left:left + w0] = img
+    return out
+
+
+def resize_bilinear_u8(img, dh, dw):
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR) for uint8 HWC, bit for bit."""
+    sh, sw = img.shape[:2]
+    scale_x, scale_y = 1.0 / (dw / sw), 1.0 / (dh / sh)              # scale = 1 / inv_scale, as cv::resize forms it
+    fx = ((np.arange(dw) + 0.5) * scale_x - 0.5).astype(F)            # double arithmetic, rounded to float once
+    sx = np.floor(fx).astype(np.int64)
+    fx = fx - sx.astype(F)
+    lo, hi = sx < 0, sx >= sw - 1
+    fx[lo | hi] = 0
+    sx[lo], sx[hi] = 0, sw - 1
+    fy = ((np.arange(dh) + 0.5) * scale_y - 0.5).astype(F)
+    sy = np.floor(fy).astype(np.int64)
+    fy = fy - sy.astype(F)
+    a0, a1 = np.rint((F(1) - fx) * F(2048)).astype(np.int64), np.rint(fx * F(2048)).astype(np.int64)   # saturate_cast<short>(rint)
+    b0, b1 = np.rint((F(1) - fy) * F(2048)).astype(np.int64), np.rint(fy * F(2048)).astype(np.int64)
+    sx1, sy0, sy1 = np.minimum(sx + 1, sw - 1), np.clip(sy, 0, sh - 1), np.clip(sy + 1, 0, sh - 1)
+    im = img.astype(np.int64)
+    s0 = im[sy0][:, sx] * a0[None, :, None] + im[sy0][:, sx1] * a1[None, :, None]
+    s1 = im[sy1][:, sx] * a0[None, :, None] + im[sy1][:, sx1] * a1[None, :, None]
+    v = (((b0[:, None, None] * (s0 >> 4)) >> 16) + ((b1[:, None, None] * (s1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(v, 0, 255).astype(np.uint8)
+
+
+def letterbox(img, new_shape=(640, 640), auto=True, stride=32):
+    """LetterBox.__call__ (augment.py:1692-1733) in full: resize when the shape changes, then the 114 border."""
+    h0, w0 = img.shape[:2]
+    r, new_unpad, top, bottom, left, right = letterbox_geometry(h0, w0, new_shape, auto, stride)
+    if (w0, h0) != new_unpad:
+        img = resize_bilinear_u8(img, new_unpad[1], new_unpad[0])
+    out = np.full((img.shape[0] + top + bottom, img.shape[1] + left + right, img.shape[2]), 114, img.dtype)
+    out[top:top + img.shape[0], left:left + img.shape[1]] = img
     return out
 
 

@@ -206,9 +206,9 @@ def test_resize_matches_cv2():
 
     torch = _t()
     g = np.random.default_rng(4)
-    for (sh, sw), (dh, dw) in [((512, 640), (1024, 1280)), ((480, 640), (384, 512)), ((100, 130), (197, 256))]:
+    for (sh, sw), (dh, dw) in [((512, 640), (1024, 1280)), ((480, 640), (384, 512)), ((100, 130), (197, 256)), ((512, 640), (640, 800)),
+                               ((720, 1280), (360, 640)), ((333, 517), (640, 640))]:
         img = g.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
         got = ops.resize_bilinear_u8(torch.from_numpy(img[None]).cuda(), dh, dw)[0].cpu().numpy()
-        diff = np.abs(got.astype(int) - ref.astype(int))
-        assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (diff.max(), (diff > 0).mean())
+        np.testing.assert_array_equal(got, ref)          # byte work: bit-exact (cv2's 11-bit fixed-point bilinear)

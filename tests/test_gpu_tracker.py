@@ -319,19 +319,21 @@ def test_ultralytics_kf_matches_reference(kind):
     means, covs = kf.initiate(z0)
     np.testing.assert_allclose(means, g[f"{kind}_init_mean"], rtol=1e-6)
     np.testing.assert_allclose(covs, g[f"{kind}_init_cov"], rtol=1e-5, atol=1e-12)
+    # free-running for all 12 steps (no re-seeding from the reference): fp32 state against the float64 reference
     for t in range(meas.shape[0]):
         means, covs = kf.multi_predict(means, covs)
         gd = kf.gating_distance(means, covs, meas[t])
         gp = kf.gating_distance(means, covs, meas[t], only_position=True)
-        np.testing.assert_allclose(gd, g[f"{kind}_gating"][t, 0], rtol=2e-3)
-        np.testing.assert_allclose(gp, g[f"{kind}_gating"][t, 1], rtol=2e-3)
+        # squared Mahalanobis distance of (z - mean): the difference of two fp32-rounded coordinates of a few hundred pixels
+        # carries ~3e-5 px of rounding, i.e. up to ~1e-4 relative on d^2 for the nearest measurements (measured 1.3e-4 in an
+        # fp32 emulation of the reference arithmetic); this is the input rounding, not the filter
+        np.testing.assert_allclose(gd, g[f"{kind}_gating"][t, 0], rtol=5e-4)
+        np.testing.assert_allclose(gp, g[f"{kind}_gating"][t, 1], rtol=5e-4)
         means, covs = kf.update(means, covs, meas[t], mask=hit[t])
         scale_m = np.maximum(np.abs(g[f"{kind}_means"][t]).max(1, keepdims=True), 1.0)
-        assert (np.abs(means - g[f"{kind}_means"][t]) / scale_m).max() < 2e-5
+        assert (np.abs(means - g[f"{kind}_means"][t]) / scale_m).max() < STATE_RTOL
         scale_c = np.abs(g[f"{kind}_covs"][t]).reshape(len(z0), -1).max(1)[:, None, None]
-        assert (np.abs(covs - g[f"{kind}_covs"][t]) / scale_c).max() < 2e-4
-        # keep following the reference trajectory so that fp32 drift does not compound across 12 steps
-        means, covs = g[f"{kind}_means"][t].copy(), g[f"{kind}_covs"][t].copy()
+        assert (np.abs(covs - g[f"{kind}_covs"][t]) / scale_c).max() < STATE_RTOL
 
 
 def test_ultralytics_kf_known_answer():

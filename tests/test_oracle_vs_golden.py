@@ -264,3 +264,19 @@ def test_motion_compensated_multi_tracker_matches_reference():
             k += 1
     assert k == len(rows)
     assert [trk.stats["total_frames"], trk.stats["individual_resets"], trk.stats["tracking_recoveries"]] == list(stats[:3])
+
+
+def test_resize_oracle_is_cv2():
+    """The oracle's fixed-point bilinear is cv2.resize(INTER_LINEAR) on uint8, byte for byte (the letterbox resize of
+    data/augment.py:1718); cv2 is the third-party implementation the reference calls, present in both containers."""
+    cv2 = pytest.importorskip("cv2")
+    g = np.random.default_rng(4)
+    for (sh, sw), (dh, dw) in [((512, 640), (1024, 1280)), ((480, 640), (384, 512)), ((100, 130), (197, 256)), ((512, 640), (640, 800)),
+                               ((720, 1280), (360, 640)), ((333, 517), (640, 640)), ((1080, 1920), (384, 640)), ((50, 60), (640, 512))]:
+        img = g.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(pp.resize_bilinear_u8(img, dh, dw), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR))
+    # LetterBox in full against the reference's geometry + cv2
+    img = g.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    out = pp.letterbox(img, (1280, 1280), auto=True, stride=32)
+    assert out.shape == (960, 1280, 3)
+    np.testing.assert_array_equal(out, cv2.resize(img, (1280, 960), interpolation=cv2.INTER_LINEAR))

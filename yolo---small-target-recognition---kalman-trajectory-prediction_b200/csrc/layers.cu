@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __res
     o[0] = r / 255.f; o[plane] = g / 255.f; o[2 * plane] = bl / 255.f;
 }
 
-// cv2.resize(INTER_LINEAR) for uint8: 11-bit fixed-point coefficients (INTER_RESIZE_COEF_BITS = 11),
+// cv2.resize(INTER_LINEAR) for uint8, bit-exact: 11-bit fixed-point coefficients (INTER_RESIZE_COEF_BITS = 11),
 // coefficients rounded with saturate_cast<short>(rint(f * 2048)), vertical pass result
 // (x >> 4 * beta >> 16 ...) reproduced with the 8u formula  ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2.
 __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* __restrict__ src, int B, int sh, int sw,
@@ -387,11 +387,12 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* 
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int x = (int)(idx % dw), y = (int)((idx / dw) % dh), b = (int)(idx / ((size_t)dw * dh));
-    float sxf = (float)((x + 0.5) * fx - 0.5);
+    // cv::resize: fx = (float)((dx + 0.5) * scale_x - 0.5) in double, rounded once -- no fused multiply-add
+    float sxf = (float)__dsub_rn(__dmul_rn((double)x + 0.5, fx), 0.5);
     int sx = (int)floorf(sxf); sxf -= sx;
     if (sx < 0) { sxf = 0; sx = 0; }
     if (sx >= sw - 1) { sxf = 0; sx = sw - 1; }
-    float syf = (float)((y + 0.5) * fy - 0.5);
+    float syf = (float)__dsub_rn(__dmul_rn((double)y + 0.5, fy), 0.5);
     int sy = (int)floorf(syf); syf -= sy;
     int sy0 = min(max(sy, 0), sh - 1), sy1 = min(max(sy + 1, 0), sh - 1);
     const int a0 = __float2int_rn((1.f - sxf) * 2048.f), a1 = __float2int_rn(sxf * 2048.f);
@@ -472,7 +473,7 @@ extern "C" int b2_resize_bilinear_u8(const uint8_t* src, int B, int sh, int sw, 
     B2_REQUIRE(sh > 0 && sw > 0 && dh > 0 && dw > 0, "resize: bad shape");
     const size_t total = (size_t)B * dh * dw;
     resize_bilinear_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        src, B, sh, sw, dst, dh, dw, (double)sh / dh, (double)sw / dw);
+        src, B, sh, sw, dst, dh, dw, 1.0 / ((double)dh / sh), 1.0 / ((double)dw / sw));   // scale = 1 / inv_scale as cv::resize forms it
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
