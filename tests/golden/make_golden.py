@@ -12,7 +12,7 @@ Files written:
   kf_ultra.npz                                KalmanFilterXYAH / XYWH initiate/predict/update/gating
   nms_cases.npz                               non_max_suppression, both branches (TorchNMS.nms / torchvision)
   net_n_p2_small.npz                          yolov8n-p2 head maps + decoded tensor on a 64x96 input
-  predict_n_p2.npz                            YOLO('yolov8n-p2.yaml').predict on 512x640 and 500x640 frames
+  predict_n_p2.npz / predict_s_p2.npz         YOLO(cfg).predict on 512x640 (and 500x640) frames + the NMS candidate lists
 """
 import contextlib
 import importlib.util
@@ -206,31 +206,51 @@ def gold_net():
     print("net", y.shape, [h.shape for h in heads])
 
 
-def gold_predict():
+def gold_predict(names=("yolov8n-p2", "yolov8s-p2")):
+    """YOLO(cfg).predict of the unmodified reference (fp32, CPU) on synthetic IR frames, both NMS branches, plus the
+    candidate list the NMS saw (every anchor with best-class score > conf, boxes in original-frame pixels): the tests
+    derive their exclusion band (near-ties an fp32-vs-bf16 comparison cannot decide) from it."""
     from ultralytics import YOLO
+    from ultralytics.utils import ops as uops
 
-    spec = cfg.resolve("yolov8n-p2")
-    sd = weights.synthetic_state_dict(spec, seed=0)
-    out = {}
-    for tag, (h, w) in (("512x640", (512, 640)), ("500x640", (500, 640))):
-        frames = [synth.IRStream(seed=7, h=h, w=w).frame(), synth.IRStream(seed=8, h=h, w=w).frame()]
-        for mode in ("legacy", "exact"):
-            tv = sys.modules.pop("torchvision", None) if mode == "legacy" else None
-            try:
-                if mode == "exact":
-                    import torchvision  # noqa: F401
-                yolo = YOLO("yolov8n-p2.yaml", verbose=False)
-                yolo.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
-                raw = {}
-                res = yolo.predict(frames, conf=0.15, iou=0.6, device="cpu", verbose=False)
-            finally:
-                if tv is not None:
-                    sys.modules["torchvision"] = tv
-            for b, r in enumerate(res):
-                out[f"{tag}_{mode}_{b}"] = r.boxes.data.numpy()
-                assert r.orig_shape == (h, w)
-            print("predict", tag, mode, [len(r.boxes) for r in res])
-    np.savez_compressed(os.path.join(HERE, "predict_n_p2.npz"), **out)
+    for name in names:
+        spec = cfg.resolve(name)
+        sd = weights.synthetic_state_dict(spec, seed=0)
+        out = {}
+        shapes = (("512x640", (512, 640)), ("500x640", (500, 640))) if name == "yolov8n-p2" else (("512x640", (512, 640)),)
+        for tag, (h, w) in shapes:
+            frames = [synth.IRStream(seed=7, h=h, w=w).frame(), synth.IRStream(seed=8, h=h, w=w).frame()]
+            f3 = synth.IRStream(seed=1001, h=h, w=w)            # a later frame of a third stream
+            frames.append([f3.frame() for _ in range(4)][-1])
+            for mode in ("legacy", "exact"):
+                tv = sys.modules.pop("torchvision", None) if mode == "legacy" else None
+                try:
+                    if mode == "exact":
+                        import torchvision  # noqa: F401
+                    yolo = YOLO(name + ".yaml", verbose=False)
+                    yolo.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+                    res = yolo.predict(frames, conf=0.15, iou=0.6, device="cpu", verbose=False)
+                finally:
+                    if tv is not None:
+                        sys.modules["torchvision"] = tv
+                for b, r in enumerate(res):
+                    out[f"{tag}_{mode}_{b}"] = r.boxes.data.numpy()
+                    assert r.orig_shape == (h, w)
+                print("predict", name, tag, mode, [len(r.boxes) for r in res])
+            # candidates of the fp32 reference (the predictor's own preprocess + inference, then nms.py:74-113 by hand)
+            pr = yolo.predictor
+            im = pr.preprocess([f.copy() for f in frames])
+            with torch.no_grad():
+                preds = pr.inference(im)
+            y = preds[0] if isinstance(preds, (list, tuple)) else preds
+            for b in range(len(frames)):
+                yb = y[b].T                                       # (A, 4 + nc)
+                sc, cl = yb[:, 4:].max(1)
+                keep = sc > 0.15
+                box = uops.xywh2xyxy(yb[keep, :4])
+                box = uops.scale_boxes(im.shape[2:], box.clone(), (h, w))
+                out[f"{tag}_cand_{b}"] = torch.cat([box, sc[keep, None], cl[keep, None].float()], 1).numpy()
+        np.savez_compressed(os.path.join(HERE, f"predict_{name[6:].replace('-', '_')}.npz"), **out)
 
 
 def motion_reset_script(n=140, seed=11):

@@ -312,32 +312,46 @@ def test_nms_edge_cases():
         np.testing.assert_array_equal(got2[b].cpu().numpy(), ref2[b])
 
 
-@pytest.mark.parametrize("tag,hw", [("512x640", (512, 640)), ("500x640", (500, 640))])
-def test_predict_matches_reference_golden(tag, hw, n_p2):
-    """YOLO(...).predict on uint8 frames vs the reference's predict() (fp32 CPU): same detection set up to the
-    bf16 noise floor of a random-weight net -- most rows matched within 1e-2 relative box error."""
+def _golden_frames(hw):
+    f3 = synth.IRStream(seed=1001, h=hw[0], w=hw[1])
+    return [synth.IRStream(seed=7, h=hw[0], w=hw[1]).frame(), synth.IRStream(seed=8, h=hw[0], w=hw[1]).frame(),
+            [f3.frame() for _ in range(4)][-1]]
+
+
+@pytest.mark.parametrize("name,gfile,tag,hw", [("yolov8n-p2", "predict_n_p2.npz", "512x640", (512, 640)),
+                                               ("yolov8n-p2", "predict_n_p2.npz", "500x640", (500, 640)),
+                                               ("yolov8s-p2", "predict_s_p2.npz", "512x640", (512, 640))])
+def test_predict_matches_reference_golden(name, gfile, tag, hw):
+    """North-star gate: YOLO(cfg).predict on uint8 frames returns the SAME detection set as the reference's predict()
+    (fp32, CPU; tests/golden/predict_*.npz) at conf 0.15 / iou 0.6 -- every decided reference detection present with its box
+    within 1e-2 relative and its score within 5e-2, nothing the reference decidedly suppresses -- outside the stated
+    exclusion band (golden_common.detection_set_report: candidates whose NMS fate flips when the reference's own logits
+    move by +-0.12 and its boxes by +-0.1 px, the measured reach of bf16 activation storage)."""
     from b200dt.predictor import YOLO
 
-    g = np.load(os.path.join(G, "predict_n_p2.npz"))
-    frames = [synth.IRStream(seed=7, h=hw[0], w=hw[1]).frame(), synth.IRStream(seed=8, h=hw[0], w=hw[1]).frame()]
-    model = YOLO("yolov8n-p2.yaml")
+    from golden_common import detection_set_report
+
+    g = np.load(os.path.join(G, gfile))
+    frames = _golden_frames(hw)
+    model = YOLO(name + ".yaml")
     res = model.predict(frames, conf=0.15, iou=0.6, verbose=False)
-    assert len(res) == 2
+    assert len(res) == 3
+    strict = total = band = 0
     for b, r in enumerate(res):
-        ref = g[f"{tag}_exact_{b}"]
+        ref, cand = g[f"{tag}_exact_{b}"], g[f"{tag}_cand_{b}"]
         d = r.boxes.data.cpu().numpy()
         assert r.orig_shape == hw and d.shape[1] == 6
         assert np.all(np.diff(d[:, 4]) <= 0)                              # sorted by descending confidence
         assert d[:, [0, 2]].min() >= 0 and d[:, [0, 2]].max() <= hw[1] and d[:, [1, 3]].max() <= hw[0]
-        matched = 0
-        for row in ref:
-            c = d[d[:, 5] == row[5]]
-            if len(c):
-                scale = max(row[2] - row[0], row[3] - row[1], 1.0)
-                e = np.abs(c[:, :4] - row[:4]).max(1) / scale
-                if e.min() < 1e-2 * 4:
-                    matched += 1
-        assert matched >= 0.6 * len(ref), (matched, len(ref), len(d))
+        rep = detection_set_report(d, ref, cand, 0.15, 0.6)
+        _diag(f"predict {name} {tag} frame {b}: reference {rep['n_ref']} detections ({rep['n_ref_strict']} decided, {rep['n_ref_in_band']} in the "
+              f"band), engine {rep['n_det']}, violations {len(rep['errors'])}")
+        assert not rep["errors"], (b, rep["errors"][:5])
+        # outside the band: the same set -- every decided reference row is there, and every engine row is either a decided
+        # reference row or a band candidate
+        strict += rep["n_ref_strict"]; total += rep["n_ref"]; band += rep["n_ref_in_band"]
+    if tag == "512x640":
+        assert strict >= 0.6 * total, (strict, total)        # the band must not swallow the comparison
     # the reference API surface
     r = res[0]
     assert r.boxes.xyxy.shape[1] == 4 and r.boxes.conf.ndim == 1 and r.boxes.cls.ndim == 1 and r.boxes.id is None
@@ -345,41 +359,33 @@ def test_predict_matches_reference_golden(tag, hw, n_p2):
     assert xy.dtype == np.float32
 
 
-def _match_fraction(d, ref, tol):
-    """Fraction of reference rows with a same-class detection whose box is within tol (relative to the largest
-    coordinate) and whose score is within 5e-2."""
-    if not len(ref):
-        return 1.0
-    m = 0
-    for row in ref:
-        c = d[d[:, 5] == row[5]]
-        if len(c):
-            e = np.abs(c[:, :4] - row[:4]).max(1) / np.maximum(np.abs(row[:4]).max(), 1.0)
-            m += bool(np.any((e < tol) & (np.abs(c[:, 4] - row[4]) < 5e-2)))
-    return m / len(ref)
-
-
-def test_predict_vs_fp32_reference_at_noise_floor(n_p2):
-    """North-star gate: post-NMS boxes within 1e-2 relative of the fp32 reference after bf16.  Measured on the
-    reference's own predict() output (tests/golden/predict_n_p2.npz, 512x640 IR frames); the engine must match at
-    least as large a fraction of the reference's detections as the oracle run at the same rounding points does,
-    minus a small slack (both sit at the bf16 noise floor of a random-weight network)."""
+def test_predict_engine_agrees_with_bf16_oracle(n_p2):
+    """The engine against the oracle evaluated at the same rounding points: the two differ only by summation order and the
+    fast SiLU / exp, an order of magnitude below the bf16 storage noise, so outside a band a quarter as wide the sets are
+    identical."""
+    import golden_common as gc
     from b200dt.predictor import YOLO
 
     spec, ospec, sd = n_p2
-    g = np.load(os.path.join(G, "predict_n_p2.npz"))
     hw = (512, 640)
-    frames = [synth.IRStream(seed=7, h=hw[0], w=hw[1]).frame(), synth.IRStream(seed=8, h=hw[0], w=hw[1]).frame()]
+    frames = _golden_frames(hw)
     res = YOLO("yolov8n-p2.yaml").predict(frames, conf=0.15, iou=0.6)
-    x = pp.preprocess(frames)
-    yb = pp.decode(onet.Net(ospec, sd, "bf16").forward(x), [4, 8, 16, 32], 80)
+    yb = pp.decode(onet.Net(ospec, sd, "bf16").forward(pp.preprocess(frames)), [4, 8, 16, 32], 80)
     ob = pp.non_max_suppression(yb, 0.15, 0.6, mode="exact")
-    for b in range(2):
-        ref = g[f"512x640_exact_{b}"]
-        d = res[b].boxes.data.cpu().numpy()
-        o = ob[b].copy()
-        o[:, :4] = pp.scale_boxes(hw, o[:, :4], hw)
-        f_gpu, f_floor = _match_fraction(d, ref, 1e-2), _match_fraction(o, ref, 1e-2)
-        _diag(f"predict 512x640 frame {b}: {len(ref)} reference detections; matched within 1e-2: engine {f_gpu:.3f}, bf16-oracle floor {f_floor:.3f}; "
-              f"engine vs bf16 oracle {_match_fraction(d, o, 1e-2):.3f}")
-        assert f_gpu >= f_floor - 0.1 and f_gpu > 0.5, (f_gpu, f_floor)
+    saved = gc.BAND_LOGIT, gc.BAND_BOX
+    gc.BAND_LOGIT, gc.BAND_BOX = 0.03, 0.03
+    try:
+        for b in range(3):
+            t = yb[b].T
+            sc, cl = t[:, 4:].max(1), t[:, 4:].argmax(1)
+            k = sc > 0.15
+            xy = np.stack([t[k, 0] - t[k, 2] / 2, t[k, 1] - t[k, 3] / 2, t[k, 0] + t[k, 2] / 2, t[k, 1] + t[k, 3] / 2], 1)
+            cand = np.concatenate([pp.scale_boxes(hw, xy, hw), sc[k, None], cl[k, None]], 1)
+            o = ob[b].copy()
+            o[:, :4] = pp.scale_boxes(hw, o[:, :4], hw)
+            rep = gc.detection_set_report(res[b].boxes.data.cpu().numpy(), o, cand, 0.15, 0.6)
+            _diag(f"engine vs bf16 oracle frame {b}: oracle {rep['n_ref']} ({rep['n_ref_strict']} decided), engine {rep['n_det']}, violations {len(rep['errors'])}")
+            assert not rep["errors"], (b, rep["errors"][:5])
+            assert rep["n_ref_strict"] >= 0.8 * rep["n_ref"]
+    finally:
+        gc.BAND_LOGIT, gc.BAND_BOX = saved

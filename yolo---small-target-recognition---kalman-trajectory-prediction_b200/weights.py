@@ -25,12 +25,141 @@ def _rng(seed, key):
     return np.random.default_rng([int(seed), zlib.crc32(key.encode())])
 
 
-def synthetic_state_dict(spec, seed=0, calib="auto"):
-    """Seeded random weights (numpy float32) keyed like the reference ``state_dict``.
+# ---- the "blob highway": a designed small-target detector embedded in the random network ------------------------------
+# Random weights make a detector whose candidates are, by construction, the anchors closest to the confidence threshold:
+# they flicker from frame to frame, bf16 rounding moves them in and out of the detection set, and the tracker downstream sees
+# hundreds of unrelated boxes.  The recipe therefore reserves a few channels along the P2 path
+#   model.0 -> model.1 -> C2f(model.2).cv1/.cv2 -> Concat -> C2f(P2 head).cv1/.cv2 -> Detect.cv3[0][0..2]
+# (three from the first C2f on) for a hand-made bright-blob detector; every other weight stays seeded-random, so the arithmetic (dense convolutions of the
+# same shapes) is unchanged.  Stages (pre-activation -> SiLU):
+#   0  stem      h = G0 * mean3x3(pixel)                      local brightness (roughly linear range of SiLU)
+#   1  model.1   h = G1 * mean3x3(h) + b1                     b1 puts the background at about -5.5 sigma (set by the calibration
+#                                                             pass from the median / MAD of the pre-activation) -> blobs only
+#   2  cv1       u_k = C - A_k h, k = 0, 1, 2                 three inverted copies with steep / medium / shallow slopes ...
+#   3  cv2       v_k = C - u_k                                ... so that v_k ~ min(A_k h, C): a concave three-segment response
+#   4..7         pass-through (1x1 taps / centre taps)
+#   class 0 logit = sum_k W_k v_k + B                         ~ logarithmic in the blob energy h: small blobs clear conf = 0.15,
+#                                                             large ones stay far from sigmoid saturation, and the peak anchor
+#                                                             of a blob leads its neighbours by a margin that does not depend
+#                                                             on the blob's brightness (stable NMS order under bf16)
+# All other class logits are shrunk and biased far below the threshold by the calibration pass; the box branch keeps its
+# random features around a DFL bias peaked at bin HW_BOX_BIN (boxes of ~8 * bin pixels at P2).
+HW_G0, HW_G1 = 12.0, 3.0
+HW_BG_SIGMAS = 5.5
+HW_C, HW_A = 4.0, (1.0, 0.4, 0.1)
+HW_LOGIT_BG, HW_LOGIT_AT = -4.2, ((2.8, 1.0), (10.0, 3.9), (30.0, 6.4))   # class-0 logit of the background; (h, logit) anchors
+HW_BOX_BIN, HW_BOX_SLOPE = 3.0, 0.6
 
-    ``calib``: ``"auto"`` loads ``calib/<name>_nc<nc>_seed<seed>.npz`` if it exists (BN running
-    statistics and head gains measured once by ``tools/calibrate_synthetic.py``), ``None`` leaves
-    BN statistics at identity, or a dict of arrays.
+
+def _silu(x):
+    return x / (1.0 + np.exp(-x))
+
+
+def _highway_response(h, a):
+    """Scalar response of stages 2..7 to a stage-1 activation h (float64)."""
+    v = _silu(HW_C - _silu(HW_C - a * h))
+    for _ in range(4):
+        v = _silu(v)
+    return v
+
+
+def highway_path(spec):
+    """[(state_dict prefix, kernel size, input channel of the highway)] for the eight stages, in execution order."""
+    layers = {L["i"]: L for L in spec["layers"]}
+    det = spec["layers"][-1]
+    path, i = [], det["f"][0]
+    while True:
+        path.append(i)
+        L = layers[i]
+        if i == 0:
+            break
+        f = L["f"]
+        if L["type"] == "Concat":
+            srcs = [i - 1 if j == -1 else j for j in f]
+            i = [j for j in srcs if layers[j]["type"] != "Upsample"][0]
+        else:
+            i = i - 1 if f == -1 else f
+    out, ch = [], 0
+    for i in reversed(path):
+        L = layers[i]
+        p = f"model.{i}"
+        if L["type"] == "Conv":
+            out.append((p, L["k"], ch)); ch = 0
+        elif L["type"] == "C2f":
+            out.append((p + ".cv1", 1, ch)); out.append((p + ".cv2", 1, 0)); ch = 0
+        elif L["type"] == "Concat":
+            srcs = [i - 1 if j == -1 else j for j in L["f"]]
+            off = 0
+            for j in srcs:
+                if layers[j]["type"] != "Upsample":
+                    break
+                off += layers[j]["c_out"]
+            ch += off
+        else:
+            raise ValueError(f"unexpected {L['type']} on the P2 path")
+    dp = f"model.{det['i']}"
+    out.append((dp + ".cv3.0.0", 3, ch)); out.append((dp + ".cv3.0.1", 3, 0))
+    assert len(out) == 8, out
+    return out
+
+
+def highway_channels(spec):
+    """{bn prefix: [channels]} whose BN statistics stay at identity (the calibration pass must not rescale them)."""
+    st = highway_path(spec)
+    return {p: ([0] if k < 2 else list(range(len(HW_A)))) for k, (p, _, _) in enumerate(st)}
+
+
+def _install_highway(spec, sd, b1=-8.6):
+    """b1: background bias of stage 1 (refined by the calibration pass)."""
+    st = highway_path(spec)
+
+    def row(prefix, r, incol, taps, beta):
+        w = sd[prefix + ".conv.weight"]
+        w[r] = 0
+        w[r, incol] = taps
+        sd[prefix + ".bn.weight"][r] = 1.0
+        sd[prefix + ".bn.bias"][r] = beta
+
+    p0, k0, _ = st[0]
+    sd[p0 + ".conv.weight"][0] = HW_G0 / (3 * k0 * k0)
+    sd[p0 + ".bn.weight"][0], sd[p0 + ".bn.bias"][0] = 1.0, 0.0
+    p1, k1, c1 = st[1]
+    row(p1, 0, c1, np.full((k1, k1), HW_G1 / (k1 * k1), np.float32), b1)
+    p2, _, c2 = st[2]
+    K = range(len(HW_A))
+    for r in K:
+        row(p2, r, c2, np.full((1, 1), -HW_A[r], np.float32), HW_C)
+    p3, _, _ = st[3]
+    for r in K:
+        row(p3, r, r, np.full((1, 1), -1.0, np.float32), HW_C)
+    for k in range(4, 8):
+        pk, kk, ck = st[k]
+        taps = np.zeros((kk, kk), np.float32)
+        taps[kk // 2, kk // 2] = 1.0
+        for r in K:
+            row(pk, r, ck + r, taps, 0.0)
+    # final linear map: one equation per anchor of HW_LOGIT_AT in the gains
+    A = np.array([[_highway_response(h, a) for a in HW_A] for h, _ in HW_LOGIT_AT])
+    g = np.linalg.solve(A, np.array([l - HW_LOGIT_BG for _, l in HW_LOGIT_AT]))
+    det = spec["layers"][-1]
+    dp = f"model.{det['i']}"
+    w, b = sd[dp + ".cv3.0.2.weight"], sd[dp + ".cv3.0.2.bias"]
+    w[0] = 0
+    w[0, :len(g), 0, 0] = g
+    b[0] = HW_LOGIT_BG
+
+
+def synthetic_state_dict(spec, seed=0, calib="auto", bake=True):
+    """Seeded synthetic weights (numpy float32) keyed like the reference ``state_dict``: random everywhere except the two
+    blob-highway channels described above.
+
+    ``calib``: ``"auto"`` loads ``calib/<name>_nc<nc>_seed<seed>.npz`` if it exists (BN running statistics, head gains and the
+    background bias of the highway, measured once by ``tools/calibrate_synthetic.py``), ``None`` leaves them uncalibrated, or
+    a dict of arrays.
+    ``bake`` (default): the calibrated BN scale gamma / sqrt(var + eps) is multiplied into the conv weights, which are then
+    rounded to bf16-representable values, and the BN is left as the identity scale (gamma = 1, var = 1 - eps, mean = 0; beta
+    kept).  The fp32 reference and the bf16 engine then hold bit-identical weights -- what separates them is the rounding of
+    the stored activations alone (SURVEY.md H1 iv).
     """
     sd = {}
     det = spec["layers"][-1]
@@ -55,20 +184,41 @@ def synthetic_state_dict(spec, seed=0, calib="auto"):
             gain = 0.6 if is_box else 1.0
             sd[prefix + ".weight"] = (gain * g.standard_normal((c2, c1, 1, 1)) / np.sqrt(_SILU_M2 * fan_in)).astype(np.float32)
             if is_box:
-                # DFL logits biased towards short distances: small boxes, as for IR small targets
-                b = np.tile(-0.45 * np.arange(REG_MAX, dtype=np.float64), 4)
+                # DFL logits peaked at bin HW_BOX_BIN: boxes of about 2 * bin * stride pixels
+                b = np.tile(-HW_BOX_SLOPE * np.abs(np.arange(REG_MAX, dtype=np.float64) - HW_BOX_BIN), 4)
             else:
-                level = int(prefix.split(".")[-2])
-                b = np.full(nc, -3.2 + 0.15 * level)   # puts O(1e2) anchors per frame above conf=0.15
+                b = np.full(nc, -9.0)              # the random classes never fire (gains shrunk by the calibration pass)
             sd[prefix + ".bias"] = b.astype(np.float32)
     sd[f"model.{det['i']}.dfl.conv.weight"] = np.arange(REG_MAX, dtype=np.float32).reshape(1, REG_MAX, 1, 1)
+    _install_highway(spec, sd)
     if calib == "auto":
         path = calib_path(spec, seed)
         calib = dict(np.load(path)) if os.path.exists(path) else None
     if calib:
         for k_, v in calib.items():
-            if k_ in sd:
+            if k_ in sd and not k_.endswith(".2.bias"):        # head biases are the recipe's, not measured
                 sd[k_] = np.asarray(v, sd[k_].dtype).reshape(sd[k_].shape)
+        # the highway rows are the recipe's as well (the calibrated head gains above cover whole weight matrices); only the
+        # background bias of stage 1 is measured
+        b1_key = highway_path(spec)[1][0] + ".bn.bias"
+        _install_highway(spec, sd, float(calib[b1_key][0]) if b1_key in calib else -8.6)
+    # BN running_var of the highway channels: exactly 1 - eps, so that the folded scale is exactly gamma = 1
+    for prefix, chans in highway_channels(spec).items():
+        for c in chans:
+            sd[prefix + ".bn.running_var"][c] = 1.0 - BN_EPS
+            sd[prefix + ".bn.running_mean"][c] = 0.0
+    if bake:
+        for prefix, c1, c2, k, s, bn in conv_list(spec):
+            if bn:
+                w, b = fold_conv_bn(sd, prefix)
+                sd[prefix + ".conv.weight"] = bf16_bits_to_f32(f32_to_bf16_bits(w)).reshape(w.shape)
+                sd[prefix + ".bn.weight"] = np.ones(c2, np.float32)
+                sd[prefix + ".bn.bias"] = b
+                sd[prefix + ".bn.running_mean"] = np.zeros(c2, np.float32)
+                sd[prefix + ".bn.running_var"] = np.full(c2, 1.0 - BN_EPS, np.float32)
+            else:
+                w = sd[prefix + ".weight"]
+                sd[prefix + ".weight"] = bf16_bits_to_f32(f32_to_bf16_bits(w)).reshape(w.shape)
     return sd
 
 
