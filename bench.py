@@ -249,10 +249,13 @@ def hbm_kernels(pipe, pk):
                      "size": "C2: 64 x 34000 anchors x 144 bf16 logits", "mean_candidates": float(post2.cand_count.float().mean().item())}
     del logits, post2
     if eng.fused_head:
-        # in-pipeline candidate stage of the fused Detect head: 24 B per anchor (4 fp32 distances + {logit, class})
+        # in-pipeline candidate stage of the fused Detect head: the 8-byte {logit, class} record of every anchor is read; the
+        # 16-byte distance record is read and a 28-byte candidate written only for anchors that clear conf
         ms = time_cuda(lambda: post.candidates_from_head(eng.head_dist, eng.head_cls, CONF), 10, flush)
-        nbytes = pipe.S * eng.num_anchors * 24
-        out["head_candidates"] = {"ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / pk["hbm"]}
+        ncand = int(post.cand_count.sum().item())
+        nbytes = pipe.S * eng.num_anchors * 8 + ncand * (16 + 28)
+        out["head_candidates"] = {"ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / pk["hbm"],
+                                  "what": f"{pipe.S} x {eng.num_anchors} anchors x 8 B + {ncand} candidates x 44 B"}
     # NMS: latency-bound at realistic candidate counts -- report ms per batch
     ms = time_cuda(lambda: post.nms(IOU), 10, flush)
     out["nms"] = {"ms": ms, "images": pipe.S, "mean_candidates": float(post.cand_count.float().mean().item())}

@@ -103,13 +103,16 @@ def detection_set_report(dets, ref, cand, conf, iou_thres, seed=0):
     always, never = kept_count == BAND_TRIALS, kept_count == 0
 
     def cand_index(row):
-        """index of the reference candidate this row corresponds to (same class, box within BOX_RTOL), or -1"""
+        """index of the reference candidate this row corresponds to (same class, box within BOX_RTOL; boxes clipped to the same
+        frame border can coincide, then the closest score decides), or -1"""
         if not m:
             return -1
         e = np.abs(cand[:, :4] - row[:4]).max(1) / max(np.abs(row[:4]).max(), 1.0)
         e[cand[:, 5] != row[5]] = np.inf
-        k = int(e.argmin())
-        return k if e[k] < BOX_RTOL else -1
+        if not e.min() < BOX_RTOL:
+            return -1
+        near = np.nonzero(e <= e.min() + 1e-3)[0]               # coinciding boxes: the closest score decides
+        return int(near[np.abs(cand[near, 4] - row[4]).argmin()])
 
     ref_idx = [cand_index(r) for r in ref]
     assert all(k >= 0 for k in ref_idx), "every reference detection must be one of the reference candidates"

@@ -353,3 +353,30 @@ def test_ultralytics_kf_known_answer():
                                [0.7272727273, 13.6198347107], rtol=1e-4)
     with pytest.raises(ValueError):
         kf.gating_distance(m, c, np.zeros((1, 4)), metric="cosine")
+
+
+@pytest.mark.parametrize("kind", ["xyah", "xywh"])
+def test_ultralytics_kf_general_covariance_matches_oracle(kind):
+    """A caller may hand update() any SPD covariance (not only the block pattern the filter itself produces): the dense
+    Cholesky path against the float64 oracle (oracle/kalman_filter.py, pinned to the reference by kf_ultra.npz)."""
+    from b200dt.kalman_filter import KalmanFilterXYAH, KalmanFilterXYWH
+    from oracle import kalman_filter as okf
+
+    g = np.random.default_rng(3)
+    kf = KalmanFilterXYAH() if kind == "xyah" else KalmanFilterXYWH()
+    N = 12
+    mean = np.concatenate([g.uniform(50, 500, (N, 2)), g.uniform(0.3, 2.0, (N, 1)) if kind == "xyah" else g.uniform(10, 60, (N, 1)),
+                           g.uniform(20, 80, (N, 1)), g.normal(0, 1, (N, 4))], 1)
+    A = g.normal(0, 1, (N, 8, 8))
+    cov = A @ A.transpose(0, 2, 1) + 4 * np.eye(8)[None]
+    meas = mean[:, :4] + g.normal(0, 1.0, (N, 4))
+    m1, c1 = kf.multi_predict(mean, cov)
+    m2, c2 = kf.update(m1, c1, meas)
+    for n in range(N):
+        rm, rc = okf.predict(kind, mean[n], cov[n])
+        scale = np.abs(rc).max()
+        assert np.abs(m1[n] - rm).max() / max(np.abs(rm).max(), 1.0) < STATE_RTOL
+        assert np.abs(c1[n] - rc).max() / scale < STATE_RTOL
+        um, uc = okf.update(kind, rm, rc, meas[n])
+        assert np.abs(m2[n] - um).max() / max(np.abs(um).max(), 1.0) < 5e-5      # dense fp32 Cholesky solve of a general S
+        assert np.abs(c2[n] - uc).max() / np.abs(uc).max() < 5e-5

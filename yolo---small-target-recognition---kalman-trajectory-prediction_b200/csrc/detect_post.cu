@@ -17,8 +17,9 @@ constexpr int kMaxLevels = 8;
 struct DecodeParams {
     const __nv_bfloat16* lv[kMaxLevels];
     int h[kMaxLevels], w[kMaxLevels], stride[kMaxLevels], a_off[kMaxLevels + 1];
+    int blk_off[kMaxLevels + 1];       // first block of each level: the level is block-uniform
     int n_levels, B, nc, lstride, A;
-    float conf;
+    float conf, logit_lo;              // logit_lo = logit(conf) - 0.05: below it the exact test `score > conf` cannot pass
     const uint8_t* cmask;
     float* cand; int32_t* cand_idx; int32_t* cand_count; int cand_cap;
     float* dense;
@@ -35,12 +36,14 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     const int lane = threadIdx.x & 31, sub = lane & 7;
     const int b = blockIdx.y;
-    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const bool active = a < p.A;
     int lvl = 0;
-    if (active) { while (lvl + 1 < p.n_levels && a >= p.a_off[lvl + 1]) ++lvl; }
-    const int la = active ? a - p.a_off[lvl] : 0;
+#pragma unroll
+    for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && (int)blockIdx.x >= p.blk_off[l]) lvl = l;
     const int W = p.w[lvl], H = p.h[lvl];
+    const int la_raw = (((int)blockIdx.x - p.blk_off[lvl]) * (int)blockDim.x + (int)threadIdx.x) >> 3;
+    const bool active = la_raw < H * W;
+    const int la = active ? la_raw : 0;
+    const int a = p.a_off[lvl] + la;
     const __nv_bfloat16* row = p.lv[lvl] + ((size_t)b * H * W + la) * p.lstride;
 
     // ---- class loads first (memory-level parallelism): up to two class chunks per lane; the DFL chunk only when needed ----
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
         best = fmaxf(__low2float(m2), __high2float(m2));
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-        const bool maybe = active && (1.f / (1.f + __expf(-best))) > p.conf;
+        const bool maybe = active && best > p.logit_lo;
         if (!__any_sync(0xffffffffu, maybe)) return;
     }
     best = -INFINITY;
@@ -167,75 +170,78 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
 struct HeadParams {
     const float* dist[kMaxLevels]; const float* cls[kMaxLevels];
     int h[kMaxLevels], w[kMaxLevels], stride[kMaxLevels], a_off[kMaxLevels + 1];
-    int n_levels, A;
-    float conf; const uint8_t* cmask;
+    int blk_off[kMaxLevels + 1];       // first block of each level (blocks never straddle a level: the level is block-uniform)
+    int n_levels, A, B;
+    float conf, logit_lo;              // logit_lo: logit(conf) - 0.05; below it the exact score test cannot pass
+    const uint8_t* cmask;
     float* cand; int32_t* cand_idx; int32_t* cand_count; int cand_cap;
 };
 
-// kHcPer anchors per thread, a block apart (coalesced), all class records loaded before any is used: the kernel moves 8 bytes per
-// anchor and is latency bound otherwise.
-constexpr int kHcPer = 4;
+// One thread tests kHcPer * 2 anchors of one (level, image): two 16-byte loads of {logit, class} records per step, all of them
+// issued before any is used.  The kernel moves 8 bytes per anchor; the sigmoid, the box and the 16-byte distance record are
+// touched only for the per-cent of anchors whose logit clears logit_lo (then the reference's exact test `score > conf`).
+constexpr int kHcPer = 4;              // 16-byte loads per thread (2 anchors each)
 
 __global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p) {
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
-    const int a0 = blockIdx.x * (256 * kHcPer) + threadIdx.x;
-    float2 c[kHcPer];
-    size_t pix[kHcPer]; int la[kHcPer], lv[kHcPer];
+    const int lane = threadIdx.x & 31;
+    int lvl = 0;
+#pragma unroll
+    for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && (int)blockIdx.x >= p.blk_off[l]) lvl = l;
+    const int W = p.w[lvl], HW = p.h[lvl] * W, b = blockIdx.y;
+    const float4* cp = reinterpret_cast<const float4*>(p.cls[lvl] + (size_t)b * HW * 2);       // two anchors per float4
+    const int pair0 = ((int)blockIdx.x - p.blk_off[lvl]) * (256 * kHcPer) + threadIdx.x, npair = HW >> 1;   // HW is even (stride-32 grids)
+    float4 c[kHcPer];
 #pragma unroll
     for (int k = 0; k < kHcPer; ++k) {
-        const int a = a0 + k * 256;
-        c[k] = make_float2(-INFINITY, 0.f); pix[k] = 0; la[k] = 0; lv[k] = 0;
-        if (a < p.A) {
-            int lvl = 0;
-#pragma unroll
-            for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && a >= p.a_off[l]) lvl = l;
-            int W = p.w[0], H = p.h[0], off = 0;
-            const float* cp = p.cls[0];
-#pragma unroll
-            for (int l = 1; l < kMaxLevels; ++l) if (l == lvl) { W = p.w[l]; H = p.h[l]; off = p.a_off[l]; cp = p.cls[l]; }
-            la[k] = a - off; lv[k] = lvl;
-            pix[k] = (size_t)b * H * W + la[k];
-            c[k] = __ldg(reinterpret_cast<const float2*>(cp) + pix[k]);
-        }
+        const int q = pair0 + k * 256;
+        c[k] = q < npair ? __ldg(cp + q) : make_float4(-INFINITY, 0.f, -INFINITY, 0.f);
     }
+    const float lo = p.logit_lo;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < kHcPer; ++k) any |= (c[k].x > lo) | (c[k].z > lo);
+    if (!__any_sync(0xffffffffu, any)) return;
+    const float st = (float)p.stride[lvl];
+    const float4* dp = reinterpret_cast<const float4*>(p.dist[lvl]) + (size_t)b * HW;
 #pragma unroll
     for (int k = 0; k < kHcPer; ++k) {
-        const int a = a0 + k * 256;
-        bool is_cand = false;
-        float cx = 0.f, cy = 0.f, bw = 0.f, bh = 0.f; int bidx = (int)c[k].y;
-        const float score = 1.f / (1.f + __expf(-c[k].x));
-        if (a < p.A && score > p.conf && (!p.cmask || p.cmask[bidx])) {
-            int W = p.w[0], st_i = p.stride[0];
-            const float* dp = p.dist[0];
 #pragma unroll
-            for (int l = 1; l < kMaxLevels; ++l) if (l == lv[k]) { W = p.w[l]; st_i = p.stride[l]; dp = p.dist[l]; }
-            const float4 d = __ldg(reinterpret_cast<const float4*>(dp) + pix[k]);
-            const float ax = (float)(la[k] % W) + 0.5f, ay = (float)(la[k] / W) + 0.5f, st = (float)st_i;
-            const float x1 = ax - d.x, y1 = ay - d.y, x2 = ax + d.z, y2 = ay + d.w;
-            cx = (x1 + x2) / 2.f * st; cy = (y1 + y2) / 2.f * st; bw = (x2 - x1) * st; bh = (y2 - y1) * st;
-            is_cand = true;
-        }
-        const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
-        if (!ball) continue;
-        int base = 0;
-        const int leader = __ffs(ball) - 1;
-        if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (is_cand) {
-            const int pos = base + __popc(ball & ((1u << lane) - 1));
-            if (pos < p.cand_cap) {
-                float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
-                const float hw = bw / 2.f, hh = bh / 2.f;
-                o[0] = cx - hw; o[1] = cy - hh; o[2] = cx + hw; o[3] = cy + hh; o[4] = score; o[5] = (float)bidx;
-                p.cand_idx[(size_t)b * p.cand_cap + pos] = a;
+        for (int e = 0; e < 2; ++e) {
+            const float logit = e ? c[k].z : c[k].x;
+            const int bidx = (int)(e ? c[k].w : c[k].y);
+            const int la = 2 * (pair0 + k * 256) + e;
+            bool is_cand = false;
+            float score = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+            if (logit > lo) {
+                score = 1.f / (1.f + __expf(-logit));
+                if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
+                    const float4 d = __ldg(dp + la);
+                    const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f;
+                    const float u1 = ax - d.x, v1 = ay - d.y, u2 = ax + d.z, v2 = ay + d.w;
+                    const float cx = (u1 + u2) / 2.f * st, cy = (v1 + v2) / 2.f * st, bw = (u2 - u1) * st, bh = (v2 - v1) * st;
+                    const float hw = bw / 2.f, hh = bh / 2.f;
+                    x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
+                    is_cand = true;
+                }
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+            if (!ball) continue;
+            int base = 0;
+            const int leader = __ffs(ball) - 1;
+            if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (is_cand) {
+                const int pos = base + __popc(ball & ((1u << lane) - 1));
+                if (pos < p.cand_cap) {
+                    float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
+                    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = score; o[5] = (float)bidx;
+                    p.cand_idx[(size_t)b * p.cand_cap + pos] = p.a_off[lvl] + la;
+                }
             }
         }
     }
 }
 
-// Candidate extraction from the reference-shaped dense tensor (B, 4+nc, A) [cx,cy,w,h,scores...] fp32:
-// nms.py:74 (amax > conf), :85-87 (xywh2xyxy), :111-113 (best class), :120-124 (classes filter).
-// One thread per anchor; the class loop reads pred[b][4+c][a], coalesced across the warp.
 __global__ void __launch_bounds__(256) dense_candidates_kernel(const float* __restrict__ pred, int nc, int no, int A, float conf,
                                                                const uint8_t* __restrict__ cmask, float* __restrict__ cand,
                                                                int32_t* __restrict__ cand_idx, int32_t* __restrict__ cand_count, int cand_cap) {
@@ -575,7 +581,11 @@ extern "C" int b2_decode(const void* const* level_logits, const int* level_h, co
     p.cand_cap = cand_cap; p.dense = dense_out;
     cudaStream_t st = (cudaStream_t)stream;
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
-    dim3 grid(b2_ceil_div(p.A * 8, 256), B);
+    // conf outside (0, 1) (0 keeps everything, the dense-output callers use it): no pre-filter
+    p.logit_lo = (conf > 0.f && conf < 1.f) ? logf(conf / (1.f - conf)) - 0.05f : -INFINITY;
+    p.blk_off[0] = 0;
+    for (int l = 0; l < n_levels; ++l) p.blk_off[l + 1] = p.blk_off[l] + b2_ceil_div(level_h[l] * level_w[l] * 8, 256);
+    dim3 grid(p.blk_off[n_levels], B);
     decode_kernel<<<grid, 256, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
@@ -595,11 +605,18 @@ extern "C" int b2_candidates_from_head(const float* const* level_dist, const flo
         p.h[l] = level_h[l]; p.w[l] = level_w[l]; p.stride[l] = level_stride[l];
         p.a_off[l + 1] = p.a_off[l] + level_h[l] * level_w[l];
     }
-    p.n_levels = n_levels; p.A = p.a_off[n_levels]; p.conf = conf; p.cmask = classes_mask;
+    p.n_levels = n_levels; p.A = p.a_off[n_levels]; p.B = B; p.conf = conf; p.cmask = classes_mask;
+    B2_REQUIRE(conf > 0.f && conf < 1.f, "candidates: conf must be in (0, 1)");
+    p.logit_lo = logf(conf / (1.f - conf)) - 0.05f;
+    p.blk_off[0] = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        B2_REQUIRE((level_h[l] * level_w[l]) % 2 == 0, "candidates: level %d must hold an even number of anchors", l);
+        p.blk_off[l + 1] = p.blk_off[l] + b2_ceil_div(level_h[l] * level_w[l] / 2, 256 * kHcPer);
+    }
     p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count; p.cand_cap = cand_cap;
     cudaStream_t st = (cudaStream_t)stream;
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
-    head_candidates_kernel<<<dim3(b2_ceil_div(p.A, 256 * kHcPer), B), 256, 0, st>>>(p);
+    head_candidates_kernel<<<dim3(p.blk_off[n_levels], B), 256, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;

@@ -101,6 +101,32 @@ __global__ void __launch_bounds__(128) kf_update_kernel(int kind, float* __restr
     float* Pg = cov + (size_t)n * 64;
 #pragma unroll
     for (int i = 0; i < 64; ++i) P[i] = Pg[i];
+    // Covariances that come out of initiate / predict / update keep the pattern P[i][j] != 0 <=> i == j (mod 4) (diagonal P0, Q, R
+    // and H = [I 0]: four independent (position, velocity) filters).  Then S is diagonal and the update has a closed
+    // form per coordinate, with 1 - K_x evaluated as r / S: no cancellation, no Cholesky.  Anything else takes the dense path.
+    bool structured = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (((i - j) & 3) != 0 && P[i * 8 + j] != 0.f) structured = false;
+    if (structured) {
+        float s[4]; scales(kind, m, s);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float sd = W_POS * s[i]; if (kind == 0 && i == 2) sd = 1e-1f;
+            const float r = sd * sd;
+            const float pxx = P[i * 9], pxv = P[i * 8 + i + 4], pvv = P[(i + 4) * 9];
+            const float S = pxx + r, kx = pxx / S, kv = pxv / S, omk = r / S;
+            const float y = meas[n * 4 + i] - m[i];
+            mean[n * 8 + i] = m[i] + kx * y;
+            mean[n * 8 + i + 4] = m[i + 4] + kv * y;
+            Pg[i * 9] = omk * pxx;
+            Pg[i * 8 + i + 4] = omk * pxv; Pg[(i + 4) * 8 + i] = omk * pxv;
+            Pg[(i + 4) * 9] = pvv - kv * pxv;
+        }
+        return;
+    }
     float pm[4], S[16], L[16];
     project_dev(kind, m, P, pm, S);
     chol(S, 4, 4, L);

@@ -224,43 +224,60 @@ __device__ __forceinline__ unsigned long long agg_wait(const unsigned long long*
 // ------------------------------------------------------------------------------------------------------------------
 // (1) sweep
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kChunk) sweep_kernel(const Bank b, const Frame fr) {
-    __shared__ float4 s_det[kMaxDetsSmem];
+// 64-bit inclusive warp scan + one barrier: every thread adds the totals of the warps before its own (s_warp: [2][8], the
+// caller alternates the half so that no trailing barrier is needed)
+__device__ __forceinline__ unsigned long long sweep_scan(unsigned long long v, unsigned long long* s_warp, unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0ull, all = 0ull;
+#pragma unroll
+    for (int w = 0; w < kChunk / 32; ++w) { const unsigned long long t = s_warp[w]; all += t; if (w < warp) before += t; }
+    *total = all;
+    return before + inc - v;
+}
+
+// Block b = chunk (b % nchunks) of stream (b / nchunks).  The aggregate look-back below waits for blocks with a LOWER block
+// index only; the hardware dispatches the blocks of a 1-D grid in index order, so a waiting block's predecessors are always
+// resident or finished (a bounded spin traps instead of hanging should that ever not hold).
+__global__ void __launch_bounds__(kChunk, 4) sweep_kernel(const Bank b, const Frame fr) {
+    extern __shared__ float4 s_det[];                              // [D] detections of the stream
     __shared__ __align__(16) float s_rows[kChunk * B2_TRACK_COLS];
     __shared__ unsigned long long s_warp[kChunk / 32];
     __shared__ unsigned long long s_prefix;
-    __shared__ unsigned int s_ticket;
     __shared__ int s_cnt[3];
     const int tid = threadIdx.x;
-    if (tid == 0) { s_ticket = atomicAdd(b.ticket, 1u); s_prefix = 0ull; }
-    if (tid < 3) s_cnt[tid] = 0;
-    __syncthreads();
-    const int s = (int)(s_ticket / (unsigned)b.nchunks), c = (int)(s_ticket % (unsigned)b.nchunks);
-    const int t = c * kChunk + tid;
-    const bool in = t < b.C;
-    const int g = s * b.C + (in ? t : 0);
-    const size_t N = b.N;
-    const int id = in ? II(b, ID, g) : 0;
-    const bool live = id != 0;
+    const int s = (int)(blockIdx.x / (unsigned)b.nchunks), c = (int)(blockIdx.x % (unsigned)b.nchunks);
     unsigned long long* agg = b.agg + (size_t)s * b.nchunks;
-    if (!__syncthreads_or(live)) {
-        // an empty chunk: nothing to predict, nothing to emit
-        if (tid == 0) { b.chunk_free[(size_t)s * b.nchunks + c] = min(kChunk, b.C - c * kChunk); agg_publish(agg + c, 0ull); }
+    const int chunk_slots = min(kChunk, b.C - c * kChunk);
+    // a chunk that was entirely free after the previous frame has nothing to predict or emit: one word read, no slot touched
+    if (b.chunk_free[(size_t)s * b.nchunks + c] == chunk_slots) {
+        if (tid == 0) agg_publish(agg + c, 0ull);
         return;
     }
-    // ---- state of the slot into registers (every load independent: ~30 coalesced 4-byte loads in flight per thread) ----
+    if (tid == 0) s_prefix = 0ull;
+    if (tid < 3) s_cnt[tid] = 0;
+    const int t = c * kChunk + tid;
+    const bool in = tid < chunk_slots;
+    const int g = s * b.C + (in ? t : c * kChunk);
+    const size_t N = b.N;
+    // ---- state of the slot into registers: every load is independent of every other (no look at the id first), ~29 coalesced
+    //      4-byte loads in flight per thread; dead slots of a live chunk are read and ignored ----
     float x[8], p[6], m[6];
-    int age = 0, hits = 0, tsu = 0, lostf = 0, islost = 0, tlen = 0, thead = 0;
-    if (live) {
+    int id = II(b, ID, g);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = b.f[(size_t)(X0 + k) * N + g];
+    for (int k = 0; k < 8; ++k) x[k] = b.f[(size_t)(X0 + k) * N + g];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) p[k] = b.f[(size_t)(PPX + k) * N + g];
+    for (int k = 0; k < 6; ++k) p[k] = b.f[(size_t)(PPX + k) * N + g];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) m[k] = b.f[(size_t)(VAVGX + k) * N + g];
-        age = II(b, AGE, g); hits = II(b, HITS, g); tsu = II(b, TSU, g);
-        lostf = II(b, LOSTF, g); islost = II(b, ISLOST, g); tlen = II(b, TLEN, g); thead = II(b, THEAD, g);
-    }
+    for (int k = 0; k < 6; ++k) m[k] = b.f[(size_t)(VAVGX + k) * N + g];
+    int age = II(b, AGE, g), hits = II(b, HITS, g), tsu = II(b, TSU, g);
+    int lostf = II(b, LOSTF, g), islost = II(b, ISLOST, g), tlen = II(b, TLEN, g), thead = II(b, THEAD, g);
+    if (!in) id = 0;
+    const bool live = id != 0;
     const int D = min(fr.det_counts[s], b.max_dets);
     for (int d = tid; d < D; d += kChunk) {
         const float* r = fr.dets + ((size_t)s * b.max_dets + d) * fr.det_cols;
@@ -329,7 +346,7 @@ __global__ void __launch_bounds__(kChunk) sweep_kernel(const Bank b, const Frame
     // ---- positions: block scan + the aggregates of the stream's preceding chunks ----
     unsigned long long total;
     const unsigned long long mine = (unsigned long long)emit | ((unsigned long long)(cand ? 1 : 0) << 16) | ((unsigned long long)npairs << 32);
-    const unsigned long long off = block_exclusive_scan64(mine, s_warp, &total);
+    const unsigned long long off = sweep_scan(mine, s_warp, &total);
     if (tid == 0) agg_publish(agg + c, total);
     {
         unsigned long long before = 0ull;
@@ -349,8 +366,8 @@ __global__ void __launch_bounds__(kChunk) sweep_kernel(const Bank b, const Frame
     }
     __syncthreads();
     const unsigned long long prefix = s_prefix;
-    const int n_emit = (int)(total & 0xFFFFu), n_cand = (int)((total >> 16) & 0xFFFFu);
-    const int e0 = (int)(prefix & 0xFFFFu) + 0, c0 = (int)((prefix >> 16) & 0xFFFFu);
+    const int n_emit = (int)(total & 0xFFFFu);
+    const int e0 = (int)(prefix & 0xFFFFu), c0 = (int)((prefix >> 16) & 0xFFFFu);
     // emitted rows of the chunk are contiguous in the output: coalesced 16-byte stores
     {
         const float4* src4 = reinterpret_cast<const float4*>(s_rows);
@@ -386,7 +403,6 @@ __global__ void __launch_bounds__(kChunk) sweep_kernel(const Bank b, const Frame
             }
         }
     }
-    (void)n_cand;
     if (tid == 0) {
         b.chunk_free[(size_t)s * b.nchunks + c] = s_cnt[2];
         if (s_cnt[0]) atomicAdd(b.fcnt + s * 4 + 0, s_cnt[0]);
@@ -561,7 +577,6 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kResolveThreads / 32;
     const int g0 = s * b.C;
     const int D = min(fr.det_counts[s], b.max_dets);
-    if (s == 0 && tid == 0) *b.ticket = 0u;
     if (tid == 0) { s_tot = 0ull; s_an = 0; }
     if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
@@ -745,7 +760,7 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
     int created = 0;
     if (n_new > 0) {
         const bool emit_new = (1 >= b.min_hits) || (frame <= b.min_hits);     // hit_streak = 1
-        const int32_t* cfree = b.chunk_free + (size_t)s * b.nchunks;
+        int32_t* cfree = b.chunk_free + (size_t)s * b.nchunks;
         for (int base = 0; base < b.C && created < n_new; base += kResolveThreads) {
             // chunks without a free slot (the common case in a full bank) are skipped without touching the slots
             const int c0 = base / kChunk;
@@ -761,6 +776,7 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
             const int take = min(total, n_new - created);
             if (is_free && rank < n_new) {
                 init_slot(b, g, s_det[s_list[rank]], id0 + rank);
+                atomicSub(b.chunk_free + (size_t)s * b.nchunks + t / kChunk, 1);     // the sweep skips chunks it believes empty
                 if (emit_new) {
                     const int pos = ebase + off;
                     const bool fits = pos < fr.out_cap;
@@ -975,7 +991,7 @@ extern "C" int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_col
     const Bank& b = t->impl.b;
     cudaStream_t st = (cudaStream_t)stream;
     const Frame fr{dets, det_cols, det_counts, out_rows, out_counts, out_traj, out_traj_len, out_cap};
-    sweep_kernel<<<b.S * b.nchunks, kChunk, 0, st>>>(b, fr);
+    sweep_kernel<<<b.S * b.nchunks, kChunk, (size_t)b.max_dets * sizeof(float4), st>>>(b, fr);
     resolve_kernel<<<b.S, kResolveThreads, 0, st>>>(b, fr);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(2);
