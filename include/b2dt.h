@@ -62,6 +62,22 @@ int b2_conv2d_cat_bf16(const void* in0, int cstride0, int coff0, int C0, int up0
                        int B, int H, int W, const void* w, const float* bias, int Cout, int ksize, int stride, int act,
                        void* out, int out_cstride, int out_coff, void* stream);
 
+/* A 3x3 conv (BN folded, SiLU, optional shortcut) and the 1x1 conv that reads its output, as ONE launch: the intermediate tile
+ * stays in shared memory as the second GEMM's operand.  Replaces the module pairs Conv -> C2f.cv1 (nn/tasks.py:172-188 with
+ * block.py:315-316), Bottleneck.cv2 (+ x) -> C2f.cv2 over cat(y0, y1, m_1..m_n) (block.py:317-319, :493-495; the channels the
+ * 1x1 conv reads besides this conv's output are `xC` channels [x_coff, x_coff + xC) of `xsrc`, stored at the conv's OUTPUT
+ * resolution, first in the 1x1 conv's K order) and Detect's cv2[l][1] -> cv2[l][2], cv3[l][1] -> cv3[l][2] (head.py:93-100).
+ * w: [Cout][3][3][Cin], w2: [Cout2][xC + Cout] bf16; act / act2: B2_ACT_*.  xsrc may be NULL (xC = 0).
+ * Returns B2_ERR_UNSUPPORTED when the pair does not fit the chained kernel (b2_conv_chain_plan_ok tells beforehand, without
+ * needing a device): run b2_conv2d_bf16 twice then. */
+int b2_conv2d_chain_bf16(const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
+                         const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                         const void* residual, int res_cstride, int res_coff,
+                         const void* xsrc, int x_cstride, int x_coff, int xC,
+                         const void* w2, const float* bias2, int Cout2, int act2,
+                         void* out, int out_cstride, int out_coff, void* stream);
+int b2_conv_chain_plan_ok(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int has_residual, int xC, int Cout2);
+
 /* Stem: letterbox-pad + BGR->RGB + /255 + Conv(3->C0, k3 s2) + SiLU in one pass over uint8 frames, on the tensor
  * cores (data/augment.py:1692-1733 LetterBox pad value 114; engine/predictor.py:152-175 preprocess; model.0 of
  * yolov8-p2.yaml).  frames: [B][src_h][src_w][3] uint8 BGR.  The letterboxed canvas is H x W with the frame at

@@ -81,6 +81,19 @@ def test_engine_every_layer_matches_oracle_on_identical_inputs(name, B, H, W):
                 ref = onet.silu(ref)
             if rb >= 0:
                 ref = ref + buf(rb)[..., roff:roff + cout].transpose(0, 3, 1, 2)
+            if op[20]:
+                # chained 1x1 conv (engine.py, ConvParams::chain): the main conv's tile is rounded to bf16 (as the unchained
+                # path stores it), concatenated behind the extra source's channels, and fed to the 1x1 conv
+                w2off, b2off, cout2, act2, xb, xoff, xc = op[21:28]
+                mid = onet.bf16_round(ref)
+                if xb >= 0:
+                    mid = np.concatenate([buf(xb)[..., xoff:xoff + xc].transpose(0, 3, 1, 2), mid], 1)
+                k2 = cout + (xc if xb >= 0 else 0)
+                w2 = weights.bf16_bits_to_f32(np.frombuffer(blob, np.uint16, count=cout2 * k2, offset=w2off)).reshape(cout2, k2, 1, 1)
+                ref = onet.conv2d(mid, w2, np.frombuffer(blob, np.float32, count=cout2, offset=b2off), 1, 0)
+                if act2:
+                    ref = onet.silu(ref)
+                cout = cout2
             got = buf(ob)[..., ooff:ooff + cout].transpose(0, 3, 1, 2)
             err = _rel_l2(got, ref)
             worst = max(worst, err)

@@ -55,6 +55,56 @@ TS_CASES = [c for c in CONV_CASES if c[5] == 3] + [
 ]
 
 
+CHAIN_CASES = [
+    # B, H, W, Cin, Cout, stride, residual, Cx (extra source), Cout2, act2
+    (2, 64, 96, 32, 64, 2, False, 0, 64, True),          # Conv(k3 s2) -> C2f.cv1 (P2 of yolov8s-p2)
+    (2, 32, 48, 32, 32, 1, True, 64, 64, True),          # Bottleneck.cv2 + shortcut -> C2f.cv2 over cat(y0, y1 | m)
+    (1, 40, 24, 32, 32, 1, False, 64, 64, True),         # head C2f (no shortcut)
+    (2, 33, 47, 64, 64, 1, False, 0, 64, False),         # Detect box tail (plain 1x1, no activation), ragged map
+    (1, 48, 32, 80, 80, 1, False, 0, 80, False),         # Detect class tail: K blocks 64 + 16
+    (3, 16, 24, 16, 16, 1, True, 32, 32, True),          # yolov8n widths: 32-byte rows, extra source of 32
+    (1, 130, 70, 32, 64, 2, False, 0, 64, True),         # stride 2, ragged 65 x 35 output, many tiles per CTA
+    (2, 24, 24, 48, 48, 1, True, 96, 96, True),          # K blocks 64 + 32 (extra) and 32 + 16 (main)
+]
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES)
+def test_chained_conv_matches_oracle(case):
+    """conv3x3 (+ shortcut) -> bf16 -> [extra | .] -> conv1x1 in one launch vs the oracle evaluating the two convs with the
+    intermediate rounded to bf16 (exactly what the unchained path stores)."""
+    from b200dt import ops
+
+    torch = _t()
+    B, H, W, cin, cout, stride, has_res, cx, cout2, act2 = case
+    g = np.random.default_rng(hash(case) % (2 ** 31))
+    if not ops.conv_chain_plan_ok(H, W, cin, cout, 3, stride, has_res, cx, cout2, B=B):
+        pytest.skip("pair not taken by the chained kernel's plan")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    x = _rand_bf16(g, (B, H, W, cin))
+    w = _rand_bf16(g, (cout, 3, 3, cin), 1.0 / np.sqrt(9 * cin * 0.36))
+    b = g.standard_normal(cout).astype(np.float32) * 0.1
+    res = _rand_bf16(g, (B, Ho, Wo, cout)) if has_res else None
+    ex = _rand_bf16(g, (B, Ho, Wo, cx)) if cx else None
+    w2 = _rand_bf16(g, (cout2, cx + cout), 1.0 / np.sqrt((cx + cout) * 0.36))
+    b2 = g.standard_normal(cout2).astype(np.float32) * 0.1
+    got = ops.conv2d_chain_bf16(_dev(x), _dev(w), torch.from_numpy(b).cuda(), stride, _dev(w2), torch.from_numpy(b2).cuda(), act=True, act2=act2,
+                                residual=None if res is None else _dev(res), extra=None if ex is None else _dev(ex)).float().cpu().numpy()
+    mid = onet.silu(onet.conv2d(x.transpose(0, 3, 1, 2), np.ascontiguousarray(w.transpose(0, 3, 1, 2)), b, stride, 1))
+    if has_res:
+        mid = mid + res.transpose(0, 3, 1, 2)
+    mid = onet.bf16_round(mid)
+    if cx:
+        mid = np.concatenate([ex.transpose(0, 3, 1, 2), mid], 1)
+    ref = onet.conv2d(mid, w2.reshape(cout2, cx + cout, 1, 1), b2, 1, 0)
+    if act2:
+        ref = onet.silu(ref)
+    ref = ref.transpose(0, 2, 3, 1)
+    assert got.shape == ref.shape
+    err = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    assert err < 4e-3, err
+    np.testing.assert_allclose(got, ref, rtol=1e-2, atol=1e-2 * max(1.0, float(np.abs(ref).max()) / 16))
+
+
 @pytest.mark.parametrize("mode", ["0", "2"])
 @pytest.mark.parametrize("case", TS_CASES)
 def test_conv_kernel_variants_match_oracle(case, mode, monkeypatch):

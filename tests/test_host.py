@@ -53,22 +53,46 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
 def test_lowering_is_consistent(name, hw):
     spec = cfg.resolve(name)
     sd = weights.synthetic_state_dict(spec, seed=0, calib=None)
-    P = engine.lower(spec, sd, *hw)
+    P = engine.lower(spec, sd, *hw, chain=False)
     words = P.words()
     assert words[0] == engine.MAGIC and len(words) == 6 + 3 * len(P.bufs) + 4 * len(P.levels) + engine.OP_WORDS * len(P.ops)
     assert P.flops == cfg.conv_flops(spec, *hw)                       # SURVEY.md 8d algorithmic FLOPs
     n_convs = sum(1 for o in P.ops if o[0] == engine.OP_CONV) + 1       # + stem
     # the first convs of Detect's box and class branches (same input) run as one GEMM per level
     assert n_convs == len(cfg.conv_list(spec)) - 4
-    P1 = engine.lower(spec, sd, *hw, merge_head=False)
+    P1 = engine.lower(spec, sd, *hw, merge_head=False, chain=False)
     assert sum(1 for o in P1.ops if o[0] == engine.OP_CONV) + 1 == len(cfg.conv_list(spec)) and P1.flops == P.flops
     for l in range(4):
         a, b_ = P.named[f"model.{len(spec['layers']) - 1}.cv2.{l}.0"], P.named[f"model.{len(spec['layers']) - 1}.cv3.{l}.0"]
         assert a[0] == b_[0] and a[1] == 0 and b_[1] == a[2]             # two channel slices of one buffer
     assert [l[1] for l in P.levels] == [4, 8, 16, 32]
-    Pf = engine.lower(spec, sd, *hw, fuse_head=True)
+    Pf = engine.lower(spec, sd, *hw, fuse_head=True, chain=False)
     assert Pf.flops == P.flops and len(Pf.ops) == len(P.ops) and all(l[0] < 0 and l[2] >= 0 for l in Pf.levels)
     assert sum(1 for o in Pf.ops if o[19] == 1) == 4 and sum(1 for o in Pf.ops if o[19] == 2) == 4
+    # chained launches (default): same arithmetic, one launch less per chained pair, every chained op well formed
+    for fh in (False, True):
+        Pc = engine.lower(spec, sd, *hw, fuse_head=fh)
+        nch = sum(1 for o in Pc.ops if o[0] == engine.OP_CONV and o[20])
+        assert Pc.flops == P.flops and len(Pc.ops) == len(P.ops) - nch
+        if name == "yolov8s-p2":
+            assert nch >= (9 if fh else 3)           # Conv -> C2f.cv1 and two C2f tails at P2, plus the Detect tails of the larger levels
+        done = {}
+        for o in Pc.ops:
+            if o[0] == engine.OP_CONV:
+                ib, ioff, cin, ob, ooff, cout = o[1:7]
+                assert all(c in done.get(ib, set()) for c in (ioff, ioff + cin - 1)), o
+                if o[20]:
+                    cout2, xb, xoff, xc = o[23], o[25], o[26], o[27]
+                    assert o[7] == 3 and o[14] < 0 and o[21] % 256 == 0 and o[22] % 256 == 0
+                    if xb >= 0:
+                        assert xc % 16 == 0 and all(c in done.get(xb, set()) for c in (xoff, xoff + xc - 1)), o
+                        assert Pc.bufs[xb][:2] == Pc.bufs[ob][:2]
+                    cout = cout2
+                done.setdefault(ob, set()).update(range(ooff, ooff + (Pc.bufs[ob][2] if o[19] else cout)))
+            elif o[0] == engine.OP_STEM:
+                done.setdefault(o[1], set()).update(range(o[2], o[2] + o[3]))
+            elif o[0] == engine.OP_POOL:
+                done.setdefault(o[1], set()).update(range(o[2] + o[3], o[2] + 4 * o[3]))
     written = {}
     for o in P.ops:
         if o[0] == engine.OP_CONV:

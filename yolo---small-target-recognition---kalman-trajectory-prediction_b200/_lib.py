@@ -24,6 +24,9 @@ SIGNATURES = {
                                _P, c_int, c_int, _P, c_int, c_int, _P]),
     "b2_conv2d_cat_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P,
                                    c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    "b2_conv2d_chain_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int,
+                                     _P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, c_int, _P]),
+    "b2_conv_chain_plan_ok": (c_int, [c_int] * 10),
     "b2_stem_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
     "b2_stem_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
     "b2_preprocess_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),

@@ -37,6 +37,7 @@ constexpr int kThreadsMw1 = 32 * (1 + 1 + 8), kThreadsMw2 = 32 * (1 + 2 + 8);   
 constexpr int kMaxNTile = 256;
 constexpr int kMaxAcc = 4;                         // accumulator stages in tensor memory
 constexpr int kMaxSeg = 4;                         // up to two sources (Concat folded into the conv) x two chunk widths
+constexpr int kMaxChainBlk = 6;                    // K blocks of a chained 1x1 conv (<= 384 channels)
 
 // transposed (TS) kernel: TMEM columns of one accumulator stage / of the weight region, K-elements the weight region holds
 constexpr uint32_t kTsAccCols = 128, kTsWeightCol = 256, kTsWeightK = 512;
@@ -102,6 +103,29 @@ struct alignas(64) ConvParams {
     int acc_stages;           // conv_tc_kernel: accumulator stages in tensor memory (2..4): tile t uses stage t % acc_stages
     uint32_t magic_nt, magic_tw, magic_th;   // ceil(2^32 / d) for d = n_tiles, tiles_w, tiles_h (0: d == 1) -- tile index -> coordinates
     int dbg_skip_mma;         // B2_CONV_DEBUG=1: issue no MMAs (timing of the TMA / epilogue paths alone; results are garbage)
+    // ---- chained 1x1 conv (conv_tc_kernel<.., CH = 1>): the activated bf16 tile of this conv never leaves the SM.  Half of the
+    //      epilogue warps ("E1") write it into shared memory in the UMMA operand layout, the MMA warps run a second GEMM on it
+    //      against the resident weights of the following 1x1 conv -- optionally together with K blocks loaded by TMA from the
+    //      channels that the 1x1 conv reads besides this conv's output (C2f: cat(y0, y1, m_1..m_n-1) | m_n, block.py:315-319) --
+    //      and the other half ("E2") runs the final epilogue (EPI) on the second accumulator.  out / out_f32 / epi describe the
+    //      CHAINED conv's output; bias / act / res stay this conv's. ----
+    int chain;
+    int c2_n, c2_cout, c2_act;            // N tile (padded to 16), real Cout and activation of the chained conv
+    const float* c2_bias;
+    int c2_nblk;                          // K blocks of the chained GEMM, in K order: TMA-fed ("x") blocks first, then E1's blocks
+    int c2_nx;                            // how many of them are TMA-fed
+    int c2_bk[kMaxChainBlk];              // channels of block i (64 / 32 / 16)
+    int c2_src_c[kMaxChainBlk];           // x blocks: first channel inside the extra source; E1 blocks: first channel of the main conv's tile
+    uint32_t c2_a_off[kMaxChainBlk];      // byte offset of the block inside one staged-tile buffer
+    uint32_t c2_w_off[kMaxChainBlk];      // byte offset of the block's weights inside the W2 region
+    uint32_t c2_desc_hi[kMaxChainBlk];    // descriptor high word (8-row pitch, swizzle of the block's row width)
+    uint32_t c2_w_bytes[kMaxChainBlk];    // bytes the block's weight box delivers
+    CUtensorMap tmW2[kMaxChainBlk];       // [Cout2][K2] weights, box (bk, c2_n)
+    CUtensorMap tmX[kMaxChainBlk];        // x blocks: (C, W, H, B) view of the extra source, box (bk, TW, TH, NB)
+    uint32_t c2_x_tx;                     // bytes the x blocks of one tile deliver
+    uint32_t c2_buf_off, c2_buf_bytes;    // shared-memory offset of the two staged-tile buffers, bytes per buffer
+    uint32_t c2_wreg_off;                 // shared-memory offset of the W2 region
+    uint32_t c2_tmem_col;                 // first tensor-memory column of the two chained accumulators
 };
 
 // x / d by one multiply-high (magic = ceil(2^32 / d), exact while x * d < 2^32 -- checked on the host); magic 0 means d == 1
@@ -178,6 +202,47 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], const fl
             }
         }
     }
+}
+
+// E1 of a chained conv: bias + activation (+ residual) + bf16 pack of one 16-column chunk, stored as two 16-byte units of
+// row `row` of a K-major operand block with `row_bytes`-byte rows (128 / 64 / 32: SWIZZLE_128B / 64B / 32B).  The swizzle is a
+// function of the absolute shared-memory address: unit index ^= address bits [7, 7 + log2(row_bytes / 16)).
+__device__ __forceinline__ void epilogue_chunk_smem(const uint32_t (&v)[16], const float* __restrict__ sb, int act,
+                                                    const __nv_bfloat16* __restrict__ rptr, uint32_t blk_addr, int row, uint32_t row_bytes, uint32_t unit0) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + i);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = __uint_as_float(v[i + k]);
+            if (act) {
+                const float h = fmaf(a, 0.5f, bb[k]);
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+                f[i + k] = fmaf(h, t, h);
+            } else {
+                f[i + k] = a + bb[k];
+            }
+        }
+    }
+    if (rptr) {
+        const uint4 r0 = *reinterpret_cast<const uint4*>(rptr);
+        const uint4 r1 = *reinterpret_cast<const uint4*>(rptr + 8);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { f[2 * i] += bf16_lo(rr[i]); f[2 * i + 1] += bf16_hi(rr[i]); }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+    const uint32_t mask = (row_bytes >> 4) - 1u;                      // 7 / 3 / 1
+    const uint32_t off0 = (uint32_t)row * row_bytes + unit0 * 16u, off1 = off0 + 16u;
+    const uint32_t a0 = blk_addr + off0, a1 = blk_addr + off1;
+    const uint32_t p0 = a0 ^ (((a0 >> 7) & mask) << 4), p1 = a1 ^ (((a1 >> 7) & mask) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(p0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(p1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
 }
 
 // ---- Detect head fused into the epilogue (ultralytics/nn/modules/head.py:152-187, block.py:78-81 DFL) ----
@@ -278,7 +343,7 @@ __device__ __forceinline__ void ss_issue_taps(uint32_t leader, uint32_t d_addr, 
 
 // MW: MMA-issuing warps.  1: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, up to two CTAs per SM.  2 (plans with ONE CTA per SM):
 // warps 1 and 2 issue alternate tiles, each with its own accumulator stage and its own ring of pipeline stages.
-template <int EPI, int HALO, int MW, int EW = 8>
+template <int EPI, int HALO, int MW, int EW = 8, int CH = 0>
 __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     // EW epilogue warps, kSub per TMEM lane quadrant (the epilogue is latency bound -- TMEM load, MUFU, stores -- so the
     // one-CTA-per-SM plans run 16: four warps per scheduler hide each other's stalls)
@@ -292,6 +357,14 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_bias[kMaxNTile];
     __shared__ int s_key[2][128];                      // class-head epilogue: partial argmax keys of the second warp of each quadrant
+    // chained conv (CH): staged-tile buffers k & 1 (k = ordinal of the tile inside this CTA)
+    __shared__ __align__(8) uint64_t a2_full[2];       // E1 has written its blocks            (E1 threads arrive)
+    __shared__ __align__(8) uint64_t a2_empty[2];      // the chained MMAs have read the buffer (tcgen05.commit)
+    __shared__ __align__(8) uint64_t x_full[2];        // the TMA-fed blocks have landed
+    __shared__ __align__(8) uint64_t t2_full[2];       // chained accumulator complete          (tcgen05.commit)
+    __shared__ __align__(8) uint64_t t2_empty[2];      // E2 has drained it                     (E2 threads arrive)
+    __shared__ __align__(16) float s_bias2[CH ? kMaxNTile : 4];
+    constexpr int kE1Warps = CH ? EW / 2 : EW;         // warps that drain the main accumulator
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -307,17 +380,27 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
             tma_prefetch_desc(&p.seg[s].tmB);
         }
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 32 * kEpiWarps); }
+        for (int s = 0; s < kMaxAcc; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 32 * kE1Warps); }
         mbar_init(&bres_bar, 1);
+        if (CH) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&a2_full[s], 32 * kE1Warps); mbar_init(&a2_empty[s], 1); mbar_init(&x_full[s], 1);
+                mbar_init(&t2_full[s], 1); mbar_init(&t2_empty[s], 32 * (EW - kE1Warps));
+            }
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
         tmem_alloc(&tmem_base_s, p.tmem_cols);
         tmem_relinquish();
     }
-    const float bias_scale = (EPI == 0 && p.act) ? 0.5f : 1.f;      // SiLU layers keep bias / 2 (epilogue_chunk)
+    const float bias_scale = ((EPI == 0 || CH) && p.act) ? 0.5f : 1.f;      // SiLU layers keep bias / 2 (epilogue_chunk)
     if (p.n_tiles == 1)
-        for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = i < p.Cout ? __ldg(p.bias + i) * bias_scale : (EPI == 2 ? -INFINITY : 0.f);
+        for (int i = threadIdx.x; i < p.n_tile; i += kThreads) s_bias[i] = i < p.Cout ? __ldg(p.bias + i) * bias_scale : ((EPI == 2 && !CH) ? -INFINITY : 0.f);
+    if (CH) {
+        const float scale2 = (EPI == 0 && p.c2_act) ? 0.5f : 1.f;
+        for (int i = threadIdx.x; i < p.c2_n; i += kThreads) s_bias2[i] = i < p.c2_cout ? __ldg(p.c2_bias + i) * scale2 : (EPI == 2 ? -INFINITY : 0.f);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -352,8 +435,13 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                         tma_load_2d(smem_b + sg.b_base + (size_t)(tap * sg.kchunks + kc) * sg.b_block_stride, &sg.tmB, &bres_bar,
                                     tap * Cin + sg.c_off + kc * sg.bk, 0);
             }
+            if (CH) {               // weights of the chained conv: block i = K columns [k0, k0 + bk) of [Cout2][K2]
+                int k0 = 0;
+                for (int i = 0; i < p.c2_nblk; ++i) { tma_load_2d(smem + p.c2_wreg_off + p.c2_w_off[i], &p.tmW2[i], &bres_bar, k0, 0); k0 += p.c2_bk[i]; }
+            }
         }
         pdl_wait();                 // activations of the previous layer: only after the predecessor grid has completed
+        int kk = 0;                 // CH: ordinal of the tile inside this CTA
         // p.mma_warps == 2: two stage rings of num_stages / 2 slots; ring r holds the tiles issued by MMA warp r (a ring with
         // two consumers would let one of them run a whole revolution ahead, which mbarrier phase parity cannot tell apart)
         const int ring_stages = MW == 2 ? num_stages >> 1 : num_stages;
@@ -411,6 +499,21 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                     }
                 }
             }
+            if (CH) {
+                // TMA-fed K blocks of the chained GEMM (the tile's own pixels, no halo), into staged-tile buffer kk & 1 once the
+                // chained MMAs of tile kk - 2 have read it.  Issued after this tile's main loads so that those are not held up.
+                if (p.c2_nx) {
+                    const int buf = kk & 1;
+                    mbar_wait(&a2_empty[buf], ((uint32_t)(kk >> 1) & 1u) ^ 1u);
+                    if (leader) {
+                        mbar_expect_tx(&x_full[buf], p.c2_x_tx);
+                        for (int i = 0; i < p.c2_nx; ++i)
+                            tma_load_4d(smem + p.c2_buf_off + (size_t)buf * p.c2_buf_bytes + p.c2_a_off[i], &p.tmX[i], &x_full[buf], p.c2_src_c[i], w0, h0, n0);
+                    }
+                    __syncwarp();
+                }
+                ++kk;
+            }
             if (MW == 2) {                                  // the next tile belongs to the other MMA warp: switch rings
                 const int ts_ = stage; stage = ostage; ostage = ts_;
                 const uint32_t tp_ = phase; phase = ophase; ophase = tp_;
@@ -454,6 +557,32 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
         int acc = mw; uint32_t acc_phase = 0;
         const int acc_stages = p.acc_stages;
         if (b_res) { mbar_wait_uniform(&bres_bar, 0); tc_fence_after(); }
+        // CH: the chained GEMM of this warp's previous tile is issued right after the main MMAs of the current one -- by then
+        // E1 has had a whole tile of tensor-pipe time to stage it, and the pipe never idles waiting for the epilogue
+        const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c2_n >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t smem_lo0 = smem_u32(smem);
+        auto chain_issue = [&](int k) {
+            const int buf = k & 1;
+            const uint32_t par = (uint32_t)(k >> 1) & 1u;
+            mbar_wait_uniform(&a2_full[buf], par);
+            if (p.c2_nx) mbar_wait_uniform(&x_full[buf], par);
+            mbar_wait_uniform(&t2_empty[buf], par ^ 1u);
+            tc_fence_after();
+            const uint32_t d2 = tmem_base_u + p.c2_tmem_col + (uint32_t)(buf * p.c2_n);
+            uint32_t accum2 = 0;
+            for (int i = 0; i < p.c2_nblk; ++i) {
+                const uint32_t a_lo = (((smem_lo0 + p.c2_buf_off + (uint32_t)buf * p.c2_buf_bytes + p.c2_a_off[i]) >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t w_lo = (((smem_lo0 + p.c2_wreg_off + p.c2_w_off[i]) >> 4) & 0x3FFFu) | (1u << 16);
+                const uint64_t hi = (uint64_t)p.c2_desc_hi[i] << 32;
+                for (int j = 0; j < (p.c2_bk[i] >> 4); ++j) {
+                    tc_mma_bf16_if(leader, d2, hi | (uint64_t)(a_lo + 2u * j), hi | (uint64_t)(w_lo + 2u * j), idesc2, accum2);
+                    accum2 = 1;
+                }
+            }
+            tc_commit_if(leader, &t2_full[buf]);
+            tc_commit_if(leader, &a2_empty[buf]);
+        };
+        int it = 0;
         for (int tile = blockIdx.x + mw * gridDim.x; tile < total_tiles; tile += (two ? 2 : 1) * gridDim.x) {
             mbar_wait_uniform(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
@@ -517,13 +646,18 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
             tc_commit_if(leader, &tfull_bar[acc]);               // accumulator complete -> epilogue
             acc += MW;
             if (acc >= acc_stages) { acc -= acc_stages; acc_phase ^= 1; }
+            if (CH) { if (it > 0) chain_issue((it - 1) * MW + mw); ++it; }
         }
+        if (CH && it > 0) chain_issue((it - 1) * MW + mw);
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
         pdl_wait();                                         // residual reads and output writes: after the predecessor grid
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
-        const int half = (warp - 1 - kMmaWarps) >> 2;       // which of the kSub warps of the quadrant
+        const int ew = warp - 1 - kMmaWarps;                // epilogue warp index; CH: the first kE1Warps drain the main accumulator
+        const bool is_e1 = CH && ew < kE1Warps;
+        constexpr int kSubR = CH ? kSub / 2 : kSub;         // warps of one role per lane quadrant
+        const int half = (CH ? (ew % kE1Warps) : ew) >> 2;  // which of the kSubR warps of the quadrant
         const int row = quad * 32 + lane;                   // row of the 128-row tile == TMEM lane
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, nb = row / (p.TW * p.TH);
         const int n_tiles = p.n_tiles, n_tile = p.n_tile, tiles_w = p.tiles_w, tiles_h = p.tiles_h, TW = p.TW, TH = p.TH, NB = p.NB;
@@ -535,7 +669,9 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
         int acc = 0; uint32_t acc_phase = 0; int par = 0;
         const int acc_stages = p.acc_stages;
         const uint32_t magic_nt = p.magic_nt, magic_tw = p.magic_tw, magic_th = p.magic_th;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int kk = 0;                                         // CH: ordinal of the tile inside this CTA (buffer kk & 1, parity (kk >> 1) & 1)
+        const uint32_t smem_lo = smem_u32(smem);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++kk) {
             const int m0 = fast_div(tile, magic_nt), n_idx = tile - m0 * n_tiles;
             const int m1 = fast_div(m0, magic_tw), m2 = fast_div(m1, magic_th);
             const int w = (m0 - m1 * tiles_w) * TW + tw;
@@ -545,8 +681,46 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
             const size_t pix = ((size_t)n * Ho + h) * Wo + w;
             const int n_base = n_idx * n_tile;
             __nv_bfloat16* optr = out0 + pix * out_cstride + n_base;
-            const __nv_bfloat16* rptr = res0 ? res0 + pix * res_cstride + n_base : nullptr;
-            const int ncols = min(n_tile, Cout - n_base);
+            const __nv_bfloat16* rptr = (res0 && (!CH || is_e1)) ? res0 + pix * res_cstride + n_base : nullptr;
+            if (CH && is_e1) {
+                // ===== E1: main accumulator -> bias / SiLU (+ shortcut) -> bf16 -> staged operand tile kk & 1 in shared memory =====
+                const int buf = kk & 1;
+                const int nch1 = n_tile >> 4;               // padding channels (>= Cout) carry zero weights and bias: they stage SiLU(0) = 0
+                if (rptr && valid)
+                    for (int j = half; j < nch1; j += kSubR) asm volatile("prefetch.global.L2 [%0];" ::"l"(rptr + j * 16));
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                mbar_wait(&a2_empty[buf], ((uint32_t)(kk >> 1) & 1u) ^ 1u);     // the chained MMAs of tile kk - 2 have read this buffer
+                tc_fence_after();
+                const uint32_t t_addr1 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_tile);
+                const uint32_t buf_addr = smem_lo + p.c2_buf_off + (uint32_t)buf * p.c2_buf_bytes;
+                for (int j = half; j < nch1; j += 2 * kSubR) {
+                    const int j2 = j + kSubR;
+                    const bool two = j2 < nch1;
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(t_addr1 + j * 16, v0);
+                    if (two) tmem_ld16(t_addr1 + j2 * 16, v1);
+                    tmem_ld_wait();
+                    // chunk j -> E1 block holding main channel 16 j (blocks c2_nx.. are E1's, in channel order)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int jj = e ? j2 : j;
+                        if (e && !two) break;
+                        int bi = p.c2_nx;
+                        while (bi + 1 < p.c2_nblk && jj * 16 >= p.c2_src_c[bi + 1]) ++bi;
+                        const uint32_t rb = (uint32_t)p.c2_bk[bi] * 2u;
+                        const bool have_res = rptr && valid && jj * 16 < Cout;
+                        epilogue_chunk_smem(e ? v1 : v0, s_bias + jj * 16, act, have_res ? rptr + jj * 16 : nullptr,
+                                            buf_addr + p.c2_a_off[bi], row, rb, (uint32_t)(jj * 16 - p.c2_src_c[bi]) >> 3);
+                    }
+                }
+                fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&a2_full[buf]);
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+            const int ncols = CH ? p.c2_cout : min(n_tile, Cout - n_base);
             const int nchunks = (ncols + 15) >> 4;
             if (n_tiles > 1) {
                 // per-tile bias slice (named barrier over the epilogue warps only)
@@ -557,15 +731,19 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
 
             // Bottleneck shortcut: pull this thread's residual chunks towards L2 while the tile's MMAs still run (no registers held)
             if (rptr && valid)
-                for (int j = half; j < nchunks; j += kSub) asm volatile("prefetch.global.L2 [%0];" ::"l"(rptr + j * 16));
+                for (int j = half; j < nchunks; j += kSubR) asm volatile("prefetch.global.L2 [%0];" ::"l"(rptr + j * 16));
 
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            // final epilogue: the conv's own accumulator, or (CH) the chained accumulator kk & 1
+            const float* const s_bias_f = CH ? s_bias2 : s_bias;
+            const int act_f = CH ? p.c2_act : act;
+            if (CH) mbar_wait(&t2_full[kk & 1], (uint32_t)(kk >> 1) & 1u);
+            else mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_tile);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (CH ? p.c2_tmem_col + (uint32_t)((kk & 1) * p.c2_n) : (uint32_t)(acc * n_tile));
             if (epi == 0) {
-                // this warp's chunks: half, half + kSub, half + 2 kSub, ... ; two chunks in flight per iteration
-                for (int j = half; j < nchunks; j += 2 * kSub) {
-                    const int j2 = j + kSub;
+                // this warp's chunks: half, half + kSubR, half + 2 kSubR, ... ; two chunks in flight per iteration
+                for (int j = half; j < nchunks; j += 2 * kSubR) {
+                    const int j2 = j + kSubR;
                     const bool two = j2 < nchunks;
                     uint32_t v0[16], v1[16];
                     tmem_ld16(t_addr + j * 16, v0);
@@ -573,11 +751,11 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                     tmem_ld_wait();
                     if (valid) {
                         if (wide) {
-                            epilogue_chunk<true>(v0, s_bias + j * 16, act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
-                            if (two) epilogue_chunk<true>(v1, s_bias + j2 * 16, act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                            epilogue_chunk<true>(v0, s_bias_f + j * 16, act_f, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                            if (two) epilogue_chunk<true>(v1, s_bias_f + j2 * 16, act_f, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
                         } else {
-                            epilogue_chunk<false>(v0, s_bias + j * 16, act, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
-                            if (two) epilogue_chunk<false>(v1, s_bias + j2 * 16, act, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
+                            epilogue_chunk<false>(v0, s_bias_f + j * 16, act_f, min(16, ncols - j * 16), optr + j * 16, rptr ? rptr + j * 16 : nullptr);
+                            if (two) epilogue_chunk<false>(v1, s_bias_f + j2 * 16, act_f, min(16, ncols - j2 * 16), optr + j2 * 16, rptr ? rptr + j2 * 16 : nullptr);
                         }
                     }
                 }
@@ -589,8 +767,8 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                 tmem_ld_wait();
                 if (valid) {
                     float* o = p.out_f32 + pix * 4;
-                    o[half] = dfl_side(v0, s_bias + half * 16);
-                    o[half + 2] = dfl_side(v1, s_bias + (half + 2) * 16);
+                    o[half] = dfl_side(v0, s_bias_f + half * 16);
+                    o[half + 2] = dfl_side(v1, s_bias_f + (half + 2) * 16);
                 }
             } else {
                 // class head: the two warps of a lane quadrant take alternate pairs of 16-class chunks, then combine
@@ -602,8 +780,8 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                     tmem_ld16(t_addr + j * 16, v0);
                     if (two) tmem_ld16(t_addr + (j + 1) * 16, v1);
                     tmem_ld_wait();
-                    cls_chunk(v0, s_bias + j * 16, j * 16, best);
-                    if (two) cls_chunk(v1, s_bias + (j + 1) * 16, (j + 1) * 16, best);
+                    cls_chunk(v0, s_bias_f + j * 16, j * 16, best);
+                    if (two) cls_chunk(v1, s_bias_f + (j + 1) * 16, (j + 1) * 16, best);
                 }
                 const int key = best;
                 int* const slot = &s_key[par][row];
@@ -612,8 +790,11 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                 if (!half && valid) *reinterpret_cast<float2*>(p.out_f32 + pix * 2) = cls_unkey(max(key, *slot));
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
-            if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+            if (CH) mbar_arrive(&t2_empty[kk & 1]);
+            else {
+                mbar_arrive(&tempty_bar[acc]);
+                if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+            }
             par ^= 1;
         }
     }
@@ -1053,12 +1234,34 @@ size_t b2_conv_launch_size() { return sizeof(B2ConvLaunch); }
 // One input of a convolution: channels [coff, coff+C) of an NHWC buffer with `cstride` channels per pixel, stored
 // at full resolution (up = 1) or at half resolution (up = 2: nearest-2x upsample folded into the loads).
 struct B2ConvSrc { const void* ptr; int cstride, coff, C, up; };
+// A 1x1 conv chained onto the conv being prepared (ConvParams::chain): weights [Cout2][xC + Cout] (K order: the extra source's
+// channels, then the main conv's), the extra source = channels [x_coff, x_coff + xC) of an NHWC buffer at the main conv's OUTPUT
+// resolution (xsrc may be NULL: the 1x1 conv reads the main conv's output alone).
+struct B2ConvChain { const void* w2; const float* bias2; int Cout2, act2; const void* xsrc; int x_cstride, x_coff, xC; };
 
 // Build the launch descriptor (tensor maps + geometry) for a conv whose input is the channel concatenation of
 // `nsrc` sources.  `storage` must hold b2_conv_launch_size() bytes, 64B aligned.  H x W: conv input resolution.
+int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B, int H, int W,
+                          const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                          void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff,
+                          const B2ConvChain* chain);
+
 int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, int H, int W,
                        const void* w, const float* bias, int Cout, int ksize, int stride, int act,
                        void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff) {
+    return b2_conv_prepare_chain(storage, srcs, nsrc, B, H, W, w, bias, Cout, ksize, stride, act, out, out_cstride, out_coff,
+                                 residual, res_cstride, res_coff, nullptr);
+}
+
+// `chain` != NULL: out / out_cstride / out_coff describe the CHAINED conv's output (Cout2 channels); B2_ERR_UNSUPPORTED when the
+// pair does not fit the chained kernel's plan (the caller then launches the two convs separately).
+static thread_local bool g_plan_only = false;     // b2_conv_chain_plan_ok: geometry / shared-memory plan only, no CUDA call
+
+int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B, int H, int W,
+                          const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                          void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff,
+                          const B2ConvChain* chain) {
+    const bool plan_only = g_plan_only;
     B2_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize %d unsupported (1 or 3)", ksize);
     B2_REQUIRE(stride == 1 || stride == 2, "conv: stride %d unsupported (1 or 2)", stride);
     B2_REQUIRE(nsrc >= 1 && nsrc <= 2, "conv: 1 or 2 sources");
@@ -1075,7 +1278,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     B2_REQUIRE(!residual || (res_cstride % 8 == 0 && res_coff % 8 == 0), "conv: residual stride/offset must be multiples of 8");
     B2_REQUIRE(Cout > 0 && B > 0 && H > 0 && W > 0, "conv: bad shape");
     B2_REQUIRE(((uintptr_t)out % 16 == 0) && ((uintptr_t)w % 16 == 0), "conv: pointers must be 16-byte aligned");
-    {   // opt in to the large dynamic shared memory carve-out once (not a stream operation: safe before graph capture)
+    if (!plan_only) {   // opt in to the large dynamic shared memory carve-out once (not a stream operation: safe before graph capture)
         static std::once_flag once;
         static cudaError_t attr_err = cudaSuccess;
         std::call_once(once, [] {
@@ -1086,12 +1289,14 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
             set((const void*)conv_tc_kernel<0, 3, 1>); set((const void*)conv_tc_kernel<1, 0, 1>); set((const void*)conv_tc_kernel<2, 0, 1>);
             set((const void*)conv_tc_kernel<0, 2, 2>); set((const void*)conv_tc_kernel<0, 3, 2>);
             set((const void*)conv_tc_kernel<0, 2, 2, 16>); set((const void*)conv_tc_kernel<0, 3, 2, 16>);
+            set((const void*)conv_tc_kernel<0, 2, 2, 16, 1>); set((const void*)conv_tc_kernel<0, 3, 2, 16, 1>);
+            set((const void*)conv_tc_kernel<1, 2, 2, 16, 1>); set((const void*)conv_tc_kernel<2, 2, 2, 16, 1>);
             attr_err = e;
         });
         B2_CUDA(attr_err);
     }
-    EncodeTiledFn encode = get_encode();
-    if (!encode) { b2_set_error("cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_CUDA; }
+    EncodeTiledFn encode = plan_only ? nullptr : get_encode();
+    if (!plan_only && !encode) { b2_set_error("cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_CUDA; }
 
     B2ConvLaunch* L = reinterpret_cast<B2ConvLaunch*>(storage);
     memset(L, 0, sizeof(*L));
@@ -1136,6 +1341,43 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     for (int si = 0; si < p.nseg; ++si) bk_max = p.seg[si].bk > bk_max ? p.seg[si].bk : bk_max;
     p.a_bytes = (uint32_t)up1k((size_t)a_rows * bk_max * 2);
 
+    const int cout16 = b2_ceil_div(Cout, 16) * 16;
+    // ---- chained 1x1 conv: K blocks (TMA-fed extra source first, then this conv's own channels), their shared-memory cost ----
+    size_t chain_bytes = 0;
+    int c2n = 0;
+    if (chain) {
+        B2_REQUIRE(chain->w2 && chain->bias2 && chain->Cout2 > 0 && (uintptr_t)chain->w2 % 16 == 0, "conv(chain): bad chained conv");
+        B2_REQUIRE(!chain->xsrc || (chain->xC > 0 && chain->xC % 16 == 0 && chain->x_cstride % 8 == 0 && chain->x_coff % 8 == 0 && (uintptr_t)chain->xsrc % 16 == 0),
+                   "conv(chain): extra source channels / strides must be multiples of 16 / 8");
+        c2n = b2_ceil_div(chain->Cout2, 16) * 16;
+        if (cout16 > 256 || c2n > 256 || ksize != 3 || any_up || nsrc != 1 || !(p.halo == 1 || stride == 2)) { b2_set_error("conv(chain): unsupported shape"); return B2_ERR_UNSUPPORTED; }
+        p.chain = 1; p.c2_n = c2n; p.c2_cout = chain->Cout2; p.c2_act = chain->act2; p.c2_bias = chain->bias2;
+        p.c2_nblk = 0; p.c2_nx = 0;
+        uint32_t a_off = 0, w_off = 0;
+        auto add_blocks = [&](int C, bool is_x) {
+            int c = 0;
+            while (c < C) {
+                const int rem = C - c, bk = rem >= 64 ? 64 : (rem % 32 == 0 ? 32 : 16);
+                if (p.c2_nblk >= kMaxChainBlk) return false;
+                const int i = p.c2_nblk++;
+                if (is_x) p.c2_nx = p.c2_nblk;
+                p.c2_bk[i] = bk; p.c2_src_c[i] = c;
+                p.c2_a_off[i] = a_off; a_off += (uint32_t)up1k((size_t)128 * bk * 2);
+                p.c2_w_off[i] = w_off; w_off += (uint32_t)up1k((size_t)c2n * bk * 2);
+                p.c2_w_bytes[i] = (uint32_t)c2n * bk * 2u;
+                const uint32_t rb = (uint32_t)bk * 2u, swz = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
+                p.c2_desc_hi[i] = (((8u * rb) >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
+                c += bk;
+            }
+            return true;
+        };
+        if ((chain->xsrc && !add_blocks(chain->xC, true)) || !add_blocks(cout16, false)) { b2_set_error("conv(chain): too many K blocks"); return B2_ERR_UNSUPPORTED; }
+        p.c2_buf_bytes = a_off;
+        p.c2_x_tx = 0;
+        for (int i = 0; i < p.c2_nx; ++i) p.c2_x_tx += 128u * (uint32_t)p.c2_bk[i] * 2u;
+        chain_bytes = (size_t)w_off + 2 * (size_t)a_off;
+    }
+    const size_t one_cta_budget = kOneCtaSmem - chain_bytes;
     // ---- 3x3 stride 2 with resident weights: parity boxes (halo 3).  Each of the four (row, column) parity views of the
     //      input is loaded once per K chunk as a (8 + pw) x (16 + ph) box and serves every tap that reads it by
     //      descriptor start row: 561 box rows instead of 9 x 128 per tile and K chunk ----
@@ -1146,7 +1388,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
         const size_t a3 = up1k((size_t)9 * 17 * bk_max * 2);
         int mode3 = 1;
         if (const char* hv = getenv("B2_CONV_S2BOX")) mode3 = atoi(hv);
-        if (mode3 && eff >= 0.6 && w_all + 3 * a3 <= kOneCtaSmem) {
+        if (mode3 && eff >= 0.6 && w_all + 3 * a3 <= one_cta_budget) {
             p.halo = 3; p.TW = 8; p.TH = 16; p.NB = 1;
             p.tiles_w = b2_ceil_div(p.Wo, p.TW); p.tiles_h = b2_ceil_div(p.Ho, p.TH); p.tiles_nb = b2_ceil_div(B, p.NB);
             a_rows = 9 * 17;
@@ -1155,12 +1397,11 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     }
 
     // ---- kernel variant: transposed "TS" kernel (weights in tensor memory) for MMA-issue-bound layers with Cout <= 128 ----
-    const int cout16 = b2_ceil_div(Cout, 16) * 16;
     int ts_mode = 0;                                   // B2_CONV_TS: 0 never (default: conv_tc_kernel's single-box halo mode is faster today), 1 heuristic, 2 every 3x3 conv with Cout <= 128
     if (const char* ev = getenv("B2_CONV_TS")) ts_mode = atoi(ev);
     const int res_taps = Cin <= (int)kTsWeightK ? (taps < (int)kTsWeightK / Cin ? taps : (int)kTsWeightK / Cin) : 0;
     p.ts = 0;
-    if (cout16 <= 128 && ksize == 3 && res_taps >= 1 && p.nseg <= kTsMaxSeg && p.halo != 3) {
+    if (!chain && cout16 <= 128 && ksize == 3 && res_taps >= 1 && p.nseg <= kTsMaxSeg && p.halo != 3) {
         if (ts_mode == 2) p.ts = 1;
         else if (ts_mode == 1) p.ts = (p.halo && res_taps >= 3) ? 1 : 0;
         size_t fb = 0;                                  // shared memory for the weights of the taps served by SS MMAs
@@ -1238,7 +1479,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
         // issuing warps and a one-stage ring each, ring B loads tile i+1 while warp A works on tile i -- 0.69 ms against 0.77 ms
         // for the streamed-weight plan, tools/conv_bench.py)
         const size_t min_stages = halo2_mode >= 2 ? 2 : 3;
-        if (halo2_mode && w_all + min_stages * a2 <= kOneCtaSmem) { p.halo = 2; a_rows = (p.TW + 2) * (p.TH + 2); p.a_bytes = (uint32_t)a2; }
+        if (halo2_mode && w_all + min_stages * a2 <= one_cta_budget) { p.halo = 2; a_rows = (p.TW + 2) * (p.TH + 2); p.a_bytes = (uint32_t)a2; }
     }
     const int tpg = p.halo == 2 ? 9 : p.halo == 1 ? 3 : 1;
     // ---- N tiling: streamed-weight stage = A box + tpg weight blocks; shrink the N tile until two stages fit ----
@@ -1285,7 +1526,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     p.tmem_cols = pw;
 
     // ---- shared memory plan: resident weights when they fit, 2 CTAs per SM when both fit ----
-    const size_t kTwoCta = 106 * 1024, kOneCta = kOneCtaSmem;
+    const size_t kTwoCta = chain ? 0 : 106 * 1024, kOneCta = one_cta_budget;       // a chained conv runs one CTA per SM (16 epilogue warps)
     const size_t a_stage = p.a_bytes, ab_stage = a_stage + p.b_stage_stride;
     p.b_resident = 0;
     auto fit = [&](size_t budget, bool resident) {
@@ -1322,18 +1563,33 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
         p.epi_warps = (p.n_tile > 64 || residual) ? 16 : 8;
         if (const char* ev = getenv("B2_CONV_EPIW")) p.epi_warps = atoi(ev) == 8 ? 8 : atoi(ev) == 16 ? 16 : p.epi_warps;   // experiments only
     }
+    if (chain) {
+        // the chained kernel exists for resident weights, one CTA per SM, two issuing warps and 8 + 8 epilogue warps
+        if (ctas != 1 || !p.b_resident || p.halo < 2 || p.mma_warps != 2 || p.n_tiles != 1 || 2 * p.n_tile + 2 * c2n > 512) {
+            b2_set_error("conv(chain): plan not supported (ctas=%d resident=%d halo=%d mma_warps=%d n_tile=%d)", ctas, p.b_resident, p.halo, p.mma_warps, p.n_tile);
+            return B2_ERR_UNSUPPORTED;
+        }
+        p.epi_warps = 16;
+    }
     // accumulator stages: as many (<= kMaxAcc) as this CTA's share of the 512 tensor-memory columns holds -- the epilogue of a
     // tile is latency bound (tcgen05.ld -> SiLU -> stores), so the MMA warps need more than one tile of run-ahead
     {
-        int acc = 512 / ctas / p.n_tile;
+        int acc = (512 - 2 * c2n) / ctas / p.n_tile;
         if (const char* av = getenv("B2_CONV_ACC")) { const int cap = atoi(av); if (cap >= 2 && cap < acc) acc = cap; }   // experiments only
         p.acc_stages = acc > kMaxAcc ? kMaxAcc : acc < 2 ? 2 : acc;
         if (p.mma_warps == 2 && (p.acc_stages & 1)) --p.acc_stages;
         uint32_t c2 = 32;
-        while (c2 < (uint32_t)(p.acc_stages * p.n_tile)) c2 <<= 1;
+        while (c2 < (uint32_t)(p.acc_stages * p.n_tile + 2 * c2n)) c2 <<= 1;
         p.tmem_cols = c2;
+        p.c2_tmem_col = (uint32_t)(p.acc_stages * p.n_tile);
     }
     L->smem = (size_t)stages * (p.b_resident ? a_stage : ab_stage) + (p.b_resident ? b_all : 0) + 1024;
+    if (chain) {
+        p.c2_wreg_off = (uint32_t)((size_t)stages * a_stage + b_all);
+        p.c2_buf_off = (uint32_t)(p.c2_wreg_off + (chain_bytes - 2 * (size_t)p.c2_buf_bytes));
+        for (int i = 0; i < p.c2_nblk; ++i) p.b_res_bytes += p.c2_w_bytes[i];
+        L->smem += chain_bytes;
+    }
     }
     p.out = (__nv_bfloat16*)out; p.out_cstride = out_cstride; p.out_coff = out_coff;
     p.res = (const __nv_bfloat16*)residual; p.res_cstride = res_cstride; p.res_coff = res_coff;
@@ -1351,6 +1607,7 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
     L->grid = total_tiles < slots ? total_tiles : slots;
     if (const char* gv = getenv("B2_CONV_GRID")) { const int gcap = atoi(gv); if (gcap > 0 && gcap < L->grid) L->grid = gcap; }   // experiments only
 
+    if (plan_only) return B2_OK;
     // ---- tensor maps ---------------------------------------------------------------------------------
     CUtensorMapL2promotion a_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     if (const char* pv = getenv("B2_CONV_L2PROMO")) {      // experiments only: 0 none, 1 64 B, 2 128 B, 3 256 B
@@ -1408,6 +1665,35 @@ int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, in
                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(B, seg %d) failed with %d", si, (int)r); return B2_ERR_CUDA; }
     }
+    if (chain) {
+        const cuuint64_t K2 = (cuuint64_t)((chain->xsrc ? chain->xC : 0) + Cout);
+        int k0 = 0;
+        for (int i = 0; i < p.c2_nblk; ++i) {
+            const CUtensorMapSwizzle sw = swizzle_for(p.c2_bk[i]);
+            // weights [Cout2][K2]: box (bk, c2_n) at K column k0 (columns / rows past the matrix are zero fill)
+            const cuuint64_t dimsb[2] = {K2, (cuuint64_t)chain->Cout2};
+            const cuuint64_t stridesb[1] = {K2 * 2};
+            const cuuint32_t boxb[2] = {(cuuint32_t)p.c2_bk[i], (cuuint32_t)p.c2_n};
+            const cuuint32_t es[2] = {1, 1};
+            CUresult r = encode(&p.tmW2[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)chain->w2, dimsb, stridesb, boxb, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(W2, block %d) failed with %d", i, (int)r); return B2_ERR_CUDA; }
+            if (i < p.c2_nx) {
+                // extra source: (C, Wo, Ho, B) view at the conv's output resolution, the tile's own pixels
+                const char* base = (const char*)chain->xsrc + (size_t)chain->x_coff * 2;
+                const cuuint64_t cs2 = (cuuint64_t)chain->x_cstride * 2;
+                const cuuint64_t dims[4] = {(cuuint64_t)chain->xC, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)B};
+                const cuuint64_t strides[3] = {cs2, (cuuint64_t)p.Wo * cs2, (cuuint64_t)p.Ho * p.Wo * cs2};
+                const cuuint32_t box[4] = {(cuuint32_t)p.c2_bk[i], (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.NB};
+                const cuuint32_t estr[4] = {1, 1, 1, 1};
+                r = encode(&p.tmX[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, a_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { b2_set_error("cuTensorMapEncodeTiled(X, block %d) failed with %d", i, (int)r); return B2_ERR_CUDA; }
+            }
+            k0 += p.c2_bk[i];
+        }
+        (void)k0;
+    }
     return B2_OK;
 }
 
@@ -1423,6 +1709,11 @@ int b2_conv_prepare(void* storage, const void* in, int B, int H, int W, int in_c
 int b2_conv_set_head_epilogue(void* storage, int epi, float* out_f32) {
     B2ConvLaunch* L = reinterpret_cast<B2ConvLaunch*>(storage);
     B2_REQUIRE(epi == 1 || epi == 2, "conv: head epilogue mode must be 1 (DFL) or 2 (classes)");
+    if (L->p.chain) {          // the head epilogue runs on the chained 1x1 conv's accumulator
+        B2_REQUIRE((epi != 1 || L->p.c2_cout == 64) && out_f32 && L->p.halo == 2, "conv(chain): head epilogue needs a 3x3 stride-1 main conv (DFL: exactly 64 channels)");
+        L->p.epi = epi; L->p.out_f32 = out_f32;
+        return B2_OK;
+    }
     B2_REQUIRE(L->p.n_tiles == 1 && (epi != 1 || L->p.Cout == 64) && out_f32, "conv: head epilogue needs one N tile (DFL: exactly 64 channels)");
     B2_REQUIRE(!L->p.ts && L->p.halo == 0, "conv: head epilogues are implemented for 1x1 convs in conv_tc_kernel only");
     L->p.mma_warps = 1;
@@ -1446,7 +1737,14 @@ int b2_conv_launch(const void* storage, cudaStream_t stream) {
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     auto go = [&](auto kernel, int threads) { cfg.blockDim = dim3((unsigned)threads); return cudaLaunchKernelEx(&cfg, kernel, L->p); };
     cudaError_t e;
-    if (L->p.epi == 1) e = go(conv_tc_kernel<1, 0, 1>, kThreadsMw1);
+    if (L->p.chain) {
+        constexpr int kThreadsChain = kThreadsMw2 + 256;
+        if (L->p.epi == 1) e = go(conv_tc_kernel<1, 2, 2, 16, 1>, kThreadsChain);
+        else if (L->p.epi == 2) e = go(conv_tc_kernel<2, 2, 2, 16, 1>, kThreadsChain);
+        else if (L->p.halo == 3) e = go(conv_tc_kernel<0, 3, 2, 16, 1>, kThreadsChain);
+        else e = go(conv_tc_kernel<0, 2, 2, 16, 1>, kThreadsChain);
+    }
+    else if (L->p.epi == 1) e = go(conv_tc_kernel<1, 0, 1>, kThreadsMw1);
     else if (L->p.epi == 2) e = go(conv_tc_kernel<2, 0, 1>, kThreadsMw1);
     else if (L->p.mma_warps == 2 && L->p.halo == 3 && L->p.epi_warps == 16) e = go(conv_tc_kernel<0, 3, 2, 16>, kThreadsMw2 + 256);
     else if (L->p.mma_warps == 2 && L->p.epi_warps == 16) e = go(conv_tc_kernel<0, 2, 2, 16>, kThreadsMw2 + 256);
@@ -1484,4 +1782,39 @@ extern "C" int b2_conv2d_cat_bf16(const void* in0, int cstride0, int coff0, int 
     int rc = b2_conv_prepare_ms(storage, srcs, in1 ? 2 : 1, B, H, W, w, bias, Cout, ksize, stride, act, out, out_cstride, out_coff, nullptr, 0, 0);
     if (rc != B2_OK) return rc;
     return b2_conv_launch(storage, (cudaStream_t)stream);
+}
+
+// Conv (3x3, BN folded, SiLU, optional shortcut) immediately followed by a 1x1 conv (+ SiLU) that reads the first conv's output
+// -- optionally concatenated behind `xC` channels of another tensor -- as ONE launch: the intermediate tile stays in shared
+// memory (ConvParams::chain).  Covers Conv -> C2f.cv1 (nn/tasks.py:172-188 + block.py:315-316), Bottleneck.cv2 -> C2f.cv2
+// (block.py:317-319, :493-495) and Detect's 3x3 -> 1x1 tails (head.py:93-100).  w2: [Cout2][xC + Cout] bf16.
+// Returns B2_ERR_UNSUPPORTED when the pair does not fit the chained kernel (run the two convs separately then).
+extern "C" int b2_conv2d_chain_bf16(const void* in, int B, int H, int W, int in_cstride, int in_coff, int Cin,
+                                    const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                                    const void* residual, int res_cstride, int res_coff,
+                                    const void* xsrc, int x_cstride, int x_coff, int xC,
+                                    const void* w2, const float* bias2, int Cout2, int act2,
+                                    void* out, int out_cstride, int out_coff, void* stream) {
+    B2_REQUIRE(Cin % 16 == 0 && Cin > 0, "conv: Cin=%d must be a positive multiple of 16", Cin);
+    alignas(64) unsigned char storage[sizeof(B2ConvLaunch)];
+    const B2ConvSrc src{in, in_cstride, in_coff, Cin, 1};
+    const B2ConvChain ch{w2, bias2, Cout2, act2, xsrc, x_cstride, x_coff, xC};
+    int rc = b2_conv_prepare_chain(storage, &src, 1, B, H, W, w, bias, Cout, ksize, stride, act, out, out_cstride, out_coff,
+                                   residual, res_cstride, res_coff, &ch);
+    if (rc != B2_OK) return rc;
+    return b2_conv_launch(storage, (cudaStream_t)stream);
+}
+
+// 1 if b2_conv2d_chain_bf16 would accept this pair (pure planning: callable without a CUDA device), else 0.
+extern "C" int b2_conv_chain_plan_ok(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int has_residual, int xC, int Cout2) {
+    alignas(64) unsigned char storage[sizeof(B2ConvLaunch)];
+    alignas(64) static unsigned char dummy[64];
+    const B2ConvSrc src{dummy, ((Cin + 15) / 16) * 16, 0, Cin, 1};
+    const B2ConvChain ch{dummy, (const float*)dummy, Cout2, 1, xC > 0 ? (const void*)dummy : nullptr, ((xC + 15) / 16) * 16, 0, xC};
+    if (Cin <= 0 || Cin % 16 || Cout <= 0 || Cout2 <= 0 || xC < 0 || xC % 16) return 0;
+    g_plan_only = true;
+    const int rc = b2_conv_prepare_chain(storage, &src, 1, B, H, W, dummy, (const float*)dummy, Cout, ksize, stride, 1, dummy, ((Cout2 + 15) / 16) * 16, 0,
+                                         has_residual ? dummy : nullptr, ((Cout + 15) / 16) * 16, 0, &ch);
+    g_plan_only = false;
+    return rc == B2_OK ? 1 : 0;
 }

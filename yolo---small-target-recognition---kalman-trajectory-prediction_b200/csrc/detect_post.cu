@@ -177,10 +177,10 @@ struct HeadParams {
     float* cand; int32_t* cand_idx; int32_t* cand_count; int cand_cap;
 };
 
-// One thread tests kHcPer * 2 anchors of one (level, image): two 16-byte loads of {logit, class} records per step, all of them
-// issued before any is used.  The kernel moves 8 bytes per anchor; the sigmoid, the box and the 16-byte distance record are
-// touched only for the per-cent of anchors whose logit clears logit_lo (then the reference's exact test `score > conf`).
-constexpr int kHcPer = 4;              // 16-byte loads per thread (2 anchors each)
+// One thread tests kHcPer anchors of one (level, image), a block apart (coalesced 8-byte loads of {logit, class} records), all of
+// them issued before any is used.  The kernel moves 8 bytes per anchor; the sigmoid, the box and the 16-byte distance record
+// are touched only for the per-cent of anchors whose logit clears logit_lo (then the reference's exact test `score > conf`).
+constexpr int kHcPer = 8;
 
 __global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p) {
     const int lane = threadIdx.x & 31;
@@ -188,55 +188,52 @@ __global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p
 #pragma unroll
     for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && (int)blockIdx.x >= p.blk_off[l]) lvl = l;
     const int W = p.w[lvl], HW = p.h[lvl] * W, b = blockIdx.y;
-    const float4* cp = reinterpret_cast<const float4*>(p.cls[lvl] + (size_t)b * HW * 2);       // two anchors per float4
-    const int pair0 = ((int)blockIdx.x - p.blk_off[lvl]) * (256 * kHcPer) + threadIdx.x, npair = HW >> 1;   // HW is even (stride-32 grids)
-    float4 c[kHcPer];
+    const float2* cp = reinterpret_cast<const float2*>(p.cls[lvl]) + (size_t)b * HW;
+    const int la0 = ((int)blockIdx.x - p.blk_off[lvl]) * (256 * kHcPer) + threadIdx.x;
+    float2 c[kHcPer];
 #pragma unroll
     for (int k = 0; k < kHcPer; ++k) {
-        const int q = pair0 + k * 256;
-        c[k] = q < npair ? __ldg(cp + q) : make_float4(-INFINITY, 0.f, -INFINITY, 0.f);
+        const int la = la0 + k * 256;
+        c[k] = la < HW ? __ldg(cp + la) : make_float2(-INFINITY, 0.f);
     }
     const float lo = p.logit_lo;
     bool any = false;
 #pragma unroll
-    for (int k = 0; k < kHcPer; ++k) any |= (c[k].x > lo) | (c[k].z > lo);
+    for (int k = 0; k < kHcPer; ++k) any |= c[k].x > lo;
     if (!__any_sync(0xffffffffu, any)) return;
     const float st = (float)p.stride[lvl];
     const float4* dp = reinterpret_cast<const float4*>(p.dist[lvl]) + (size_t)b * HW;
 #pragma unroll
     for (int k = 0; k < kHcPer; ++k) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float logit = e ? c[k].z : c[k].x;
-            const int bidx = (int)(e ? c[k].w : c[k].y);
-            const int la = 2 * (pair0 + k * 256) + e;
-            bool is_cand = false;
-            float score = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-            if (logit > lo) {
-                score = 1.f / (1.f + __expf(-logit));
-                if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
-                    const float4 d = __ldg(dp + la);
-                    const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f;
-                    const float u1 = ax - d.x, v1 = ay - d.y, u2 = ax + d.z, v2 = ay + d.w;
-                    const float cx = (u1 + u2) / 2.f * st, cy = (v1 + v2) / 2.f * st, bw = (u2 - u1) * st, bh = (v2 - v1) * st;
-                    const float hw = bw / 2.f, hh = bh / 2.f;
-                    x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
-                    is_cand = true;
-                }
+        const float logit = c[k].x;
+        const int bidx = (int)c[k].y;
+        const int la = la0 + k * 256;
+        bool is_cand = false;
+        float score = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+        if (logit > lo) {
+            score = 1.f / (1.f + __expf(-logit));
+            if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
+                const float4 d = __ldg(dp + la);
+                const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f;
+                const float u1 = ax - d.x, v1 = ay - d.y, u2 = ax + d.z, v2 = ay + d.w;
+                const float cx = (u1 + u2) / 2.f * st, cy = (v1 + v2) / 2.f * st, bw = (u2 - u1) * st, bh = (v2 - v1) * st;
+                const float hw = bw / 2.f, hh = bh / 2.f;
+                x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
+                is_cand = true;
             }
-            const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
-            if (!ball) continue;
-            int base = 0;
-            const int leader = __ffs(ball) - 1;
-            if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (is_cand) {
-                const int pos = base + __popc(ball & ((1u << lane) - 1));
-                if (pos < p.cand_cap) {
-                    float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
-                    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = score; o[5] = (float)bidx;
-                    p.cand_idx[(size_t)b * p.cand_cap + pos] = p.a_off[lvl] + la;
-                }
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+        if (!ball) continue;
+        int base = 0;
+        const int leader = __ffs(ball) - 1;
+        if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (is_cand) {
+            const int pos = base + __popc(ball & ((1u << lane) - 1));
+            if (pos < p.cand_cap) {
+                float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
+                o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = score; o[5] = (float)bidx;
+                p.cand_idx[(size_t)b * p.cand_cap + pos] = p.a_off[lvl] + la;
             }
         }
     }
@@ -609,10 +606,7 @@ extern "C" int b2_candidates_from_head(const float* const* level_dist, const flo
     B2_REQUIRE(conf > 0.f && conf < 1.f, "candidates: conf must be in (0, 1)");
     p.logit_lo = logf(conf / (1.f - conf)) - 0.05f;
     p.blk_off[0] = 0;
-    for (int l = 0; l < n_levels; ++l) {
-        B2_REQUIRE((level_h[l] * level_w[l]) % 2 == 0, "candidates: level %d must hold an even number of anchors", l);
-        p.blk_off[l + 1] = p.blk_off[l] + b2_ceil_div(level_h[l] * level_w[l] / 2, 256 * kHcPer);
-    }
+    for (int l = 0; l < n_levels; ++l) p.blk_off[l + 1] = p.blk_off[l] + b2_ceil_div(level_h[l] * level_w[l], 256 * kHcPer);
     p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count; p.cand_cap = cand_cap;
     cudaStream_t st = (cudaStream_t)stream;
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));

@@ -24,6 +24,11 @@ struct B2ConvSrc { const void* ptr; int cstride, coff, C, up; };
 int b2_conv_prepare_ms(void* storage, const B2ConvSrc* srcs, int nsrc, int B, int H, int W,
                        const void* w, const float* bias, int Cout, int ksize, int stride, int act,
                        void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff);
+struct B2ConvChain { const void* w2; const float* bias2; int Cout2, act2; const void* xsrc; int x_cstride, x_coff, xC; };
+int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B, int H, int W,
+                          const void* w, const float* bias, int Cout, int ksize, int stride, int act,
+                          void* out, int out_cstride, int out_coff, const void* residual, int res_cstride, int res_coff,
+                          const B2ConvChain* chain);
 int b2_conv_set_head_epilogue(void* storage, int epi, float* out_f32);
 int b2_conv_launch(const void* storage, cudaStream_t stream);
 
@@ -57,7 +62,7 @@ extern "C" long long b2_launch_count(void) { return g_launches.load(); }
 // ------------------------------------------------------------------------------------------------
 namespace {
 constexpr int kMagic = 0xB2D7;
-constexpr int kOpWords = 20;
+constexpr int kOpWords = 28;
 enum Op { OP_STEM = 1, OP_CONV = 2, OP_POOL = 3, OP_UP = 4 };
 
 struct Buf { int h, w, c; size_t off; };
@@ -139,8 +144,13 @@ extern "C" int b2_engine_create(const int32_t* plan, int plan_words, const void*
             if (i != 0 || !buf_ok(a[0])) { b2_set_error("engine_create: stem must be op 0 with a valid buffer"); return fail(B2_ERR_ARG); }
         } else if (s.op == OP_CONV) {
             // a: 0 in buf, 1 in coff, 2 Cin, 3 out buf, 4 out coff, 5 Cout, 6 k, 7 stride, 8 act, 9 res buf, 10 res coff,
-            //    11 weights, 12 bias, 13 second input buf (-1: none), 14 its coff, 15 its channels, 16 up of input 0, 17 up of input 1
+            //    11 weights, 12 bias, 13 second input buf (-1: none), 14 its coff, 15 its channels, 16 up of input 0, 17 up of input 1,
+            //    18 head epilogue; chained 1x1 conv (conv_tc.cu ConvParams::chain): 19 flag, 20 weights, 21 bias, 22 Cout2, 23 act2,
+            //    24 extra-source buf (-1: none), 25 its coff, 26 its channels.  With a chain, 3 / 4 (and 18) describe the CHAINED
+            //    conv's output and 5 is the main conv's Cout.
             const bool two = a[13] >= 0;
+            const bool chained = a[19] != 0;
+            const int c_final = chained ? a[22] : a[5];
             if (!buf_ok(a[0]) || !buf_ok(a[3]) || (a[9] >= 0 && !buf_ok(a[9])) || (two && !buf_ok(a[13]))) { b2_set_error("engine_create: op %d: bad buffer id", i); return fail(B2_ERR_ARG); }
             const Buf& bi = e->bufs[a[0]]; const Buf& bo = e->bufs[a[3]];
             const int up0 = a[16] == 2 ? 2 : 1, up1 = a[17] == 2 ? 2 : 1;
@@ -152,11 +162,17 @@ extern "C" int b2_engine_create(const int32_t* plan, int plan_words, const void*
                 if (b2.h * up1 != Hin || b2.w * up1 != Win || a[14] + a[15] > b2.c) { b2_set_error("engine_create: op %d: second input geometry mismatch", i); return fail(B2_ERR_ARG); }
             }
             s.conv.resize(b2_conv_launch_size() + 64);
-            rc = b2_conv_prepare_ms(s.conv_ptr(), srcs, two ? 2 : 1, B, Hin, Win,
-                                    wbase + (size_t)(uint32_t)a[11], (const float*)(wbase + (size_t)(uint32_t)a[12]), a[5], a[6], a[7], a[8],
-                                    e->buf_ptr(a[3]), a[18] ? 16 : bo.c, a[18] ? 0 : a[4],   // head epilogues write fp32 records, not a bf16 slice
-                                    a[9] >= 0 ? e->buf_ptr(a[9]) : nullptr,
-                                    a[9] >= 0 ? e->bufs[a[9]].c : 0, a[10]);
+            B2ConvChain ch{};
+            if (chained) {
+                if (a[24] >= 0 && (!buf_ok(a[24]) || a[25] + a[26] > e->bufs[a[24]].c)) { b2_set_error("engine_create: op %d: bad extra source of the chained conv", i); return fail(B2_ERR_ARG); }
+                ch = B2ConvChain{wbase + (size_t)(uint32_t)a[20], (const float*)(wbase + (size_t)(uint32_t)a[21]), a[22], a[23],
+                                 a[24] >= 0 ? e->buf_ptr(a[24]) : nullptr, a[24] >= 0 ? e->bufs[a[24]].c : 0, a[25], a[26]};
+            }
+            rc = b2_conv_prepare_chain(s.conv_ptr(), srcs, two ? 2 : 1, B, Hin, Win,
+                                       wbase + (size_t)(uint32_t)a[11], (const float*)(wbase + (size_t)(uint32_t)a[12]), a[5], a[6], a[7], a[8],
+                                       e->buf_ptr(a[3]), a[18] ? 16 : bo.c, a[18] ? 0 : a[4],   // head epilogues write fp32 records, not a bf16 slice
+                                       a[9] >= 0 ? e->buf_ptr(a[9]) : nullptr,
+                                       a[9] >= 0 ? e->bufs[a[9]].c : 0, a[10], chained ? &ch : nullptr);
             if (rc != B2_OK) return fail(rc);
             const int pad = a[6] / 2, ho = (Hin + 2 * pad - a[6]) / a[7] + 1, wo = (Win + 2 * pad - a[6]) / a[7] + 1;
             if (a[18] != 0) {      // fused Detect-head epilogue: the output buffer holds fp32 {4 distances} or {logit, class} per pixel
@@ -164,7 +180,7 @@ extern "C" int b2_engine_create(const int32_t* plan, int plan_words, const void*
                 if (rc != B2_OK) return fail(rc);
                 if (bo.c != (a[18] == 1 ? 8 : 4)) { b2_set_error("engine_create: op %d: head buffer has the wrong width", i); return fail(B2_ERR_ARG); }
             }
-            if (ho != bo.h || wo != bo.w || (a[18] == 0 && a[4] + a[5] > bo.c) || a[1] + a[2] > bi.c) {
+            if (ho != bo.h || wo != bo.w || (a[18] == 0 && a[4] + c_final > bo.c) || a[1] + a[2] > bi.c) {
                 b2_set_error("engine_create: op %d: conv geometry does not match its buffers", i); return fail(B2_ERR_ARG);
             }
         } else if (s.op == OP_POOL) {

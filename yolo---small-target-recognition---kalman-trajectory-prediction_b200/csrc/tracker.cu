@@ -208,14 +208,17 @@ __device__ __forceinline__ int block_exclusive_scan(int v, unsigned long long* s
 }
 
 constexpr unsigned long long kAggValid = 1ull << 63;
+// The aggregate word IS the message (counts + valid bit in one 64-bit store): nothing else written by the publishing block is
+// read through it, so relaxed gpu-scope accesses suffice -- a release store would drain every state store the thread has in
+// flight (MEMBAR.ALL.GPU on the block's critical path).
 __device__ __forceinline__ void agg_publish(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.global.release.gpu.u64 [%0], %1;" ::"l"(p), "l"(v | kAggValid) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v | kAggValid) : "memory");
 }
 __device__ __forceinline__ unsigned long long agg_wait(const unsigned long long* p) {
     unsigned long long v;
     unsigned spins = 0;
     do {
-        asm volatile("ld.global.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
         if (!(v & kAggValid) && ++spins > (1u << 24)) { printf("b2dt: sweep aggregate wait timed out\n"); __trap(); }
     } while (!(v & kAggValid));
     return v & ~kAggValid;

@@ -13,7 +13,13 @@ bf16 buffers in which every ``torch.cat`` / ``chunk`` of C2f (block.py:315-319),
   * each Detect level owns a ``[B][h*w][64 + ceil8(nc)]`` logits buffer filled by ``cv2[l][2]`` / ``cv3[l][2]``.
 
 Plan layout (int32 words): ``[magic, n_bufs, n_ops, n_levels, nc, lstride]``, ``n_bufs x (h, w, c)``,
-``n_levels x (buf, stride)``, ``n_ops x 20`` (opcode + 19 arguments, see ``OP_*`` below).
+``n_levels x (buf, stride)``, ``n_ops x 28`` (opcode + 27 arguments, see ``OP_*`` below and csrc/engine.cu).
+
+Chained launches (``chain=True``, default): a 3x3 conv whose output is read only by a following 1x1 conv runs WITH that 1x1
+conv in one launch -- the intermediate tile stays in shared memory (csrc/conv_tc.cu, ``ConvParams::chain``).  Three places:
+``Conv(k3, s2) -> C2f.cv1``, ``Bottleneck[n-1].cv2 (+ shortcut) -> C2f.cv2`` (the other channels of the C2f buffer are the 1x1
+conv's extra K source) and the Detect tails ``cv2[l][1] -> cv2[l][2]`` / ``cv3[l][1] -> cv3[l][2]``.  Each is taken only when
+``b2_conv_chain_plan_ok`` says the pair fits the chained kernel; otherwise the two convs stay separate launches.
 
 ``Concat([Upsample(a), b])`` feeding a C2f is *virtual*: its ``cv1`` 1x1 conv takes both tensors as inputs and the
 nearest-2x upsample is folded into the conv's TMA loads (zero-stride tensor-map dimensions), so neither the upsampled
@@ -31,7 +37,7 @@ from . import _lib, cfg, weights
 
 MAGIC = 0xB2D7
 OP_STEM, OP_CONV, OP_POOL, OP_UP = 1, 2, 3, 4
-OP_WORDS = 20
+OP_WORDS = 28
 ACT_NONE, ACT_SILU = 0, 1
 
 
@@ -94,7 +100,16 @@ def _shapes(spec, H, W):
     return hw
 
 
-def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
+def _chain_ok(H, W, cin, cout, k, s, has_res, xc, cout2):
+    """Would the chained kernel take this (3x3 conv at input resolution H x W) -> (1x1 conv) pair?  Pure planning in the library."""
+    try:
+        lib = _lib.load()
+    except Exception:
+        return False
+    return bool(lib.b2_conv_chain_plan_ok(1, int(H), int(W), int(cin), int(cout), int(k), int(s), int(bool(has_res)), int(xc), int(cout2)))
+
+
+def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True, chain=True):
     """Lower ``spec`` (from :func:`cfg.resolve`) with weights ``state_dict`` for an ``H x W`` letterboxed input.
 
     ``fuse_head``: run DFL (softmax expectation) and the class max inside the epilogue of each Detect level's last
@@ -159,8 +174,10 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
         if c % 16:
             raise NotImplementedError(f"{what}: {c} channels -- the tcgen05 conv path needs multiples of 16")
 
-    def emit_conv(prefix, inp, out, k, s, bn, res=None, inp2=None, ups=(1, 1), epi=0):
+    def emit_conv(prefix, inp, out, k, s, bn, res=None, inp2=None, ups=(1, 1), epi=0, chain2=None):
         """inp/out/res/inp2: (buf, coff, C).  inp2: second input of a folded Concat; ups: resolution factors of the inputs.
+        chain2: dict(prefix, bn, x) -- the 1x1 conv ``prefix`` chained onto this conv (x: (buf, coff, C) extra K source or None);
+        ``out`` and ``epi`` then describe the chained conv's output.
         prefix: one module name, or a tuple of modules that read the same input -- their filters are stacked along Cout and run
         as ONE GEMM (the input tile is fetched once, and a wider N uses the tensor pipe better: N = 144 runs at the pipe's
         N/2 cycles per MMA where N = 64 and N = 80 are bound by the operand fetch); ``out`` then covers all their channels."""
@@ -175,7 +192,7 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
         else:
             w, b = weights.folded(sd, prefix, bn)
         cout, cin = w.shape[0], w.shape[1]
-        assert cin == inp[2] + (inp2[2] if inp2 else 0) and (epi or cout == out[2]), (prefix, w.shape, inp, inp2, out)
+        assert cin == inp[2] + (inp2[2] if inp2 else 0) and (epi or chain2 or cout == out[2]), (prefix, w.shape, inp, inp2, out)
         check_c(inp[2], prefix + " input")
         if inp2:
             check_c(inp2[2], prefix + " second input")
@@ -183,18 +200,32 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
         boff = P.blob.add(b.astype(np.float32))
         hb, wb, _ = P.bufs[out[0]]
         P.flops += 2 * hb * wb * cout * cin * k * k
+        tail = [0] * 8
+        if chain2:
+            w2, b2 = weights.folded(sd, chain2["prefix"], chain2["bn"])
+            x = chain2.get("x")
+            cout2, k2 = w2.shape[0], w2.shape[1]
+            assert w2.shape[2:] == (1, 1) and k2 == cout + (x[2] if x else 0) and (epi or cout2 == out[2]), (chain2["prefix"], w2.shape, out)
+            w2off = P.blob.add(weights.f32_to_bf16_bits(w2.reshape(cout2, k2)))
+            b2off = P.blob.add(b2.astype(np.float32))
+            P.flops += 2 * hb * wb * cout2 * k2
+            tail = [1, w2off, b2off, cout2, ACT_SILU if chain2["bn"] else ACT_NONE, x[0] if x else -1, x[1] if x else 0, x[2] if x else 0]
+            P.named[chain2["prefix"]] = out
         P.ops.append([OP_CONV, inp[0], inp[1], inp[2], out[0], out[1], cout, k, s, ACT_SILU if bn else ACT_NONE,
                       res[0] if res else -1, res[1] if res else 0, woff, boff,
-                      inp2[0] if inp2 else -1, inp2[1] if inp2 else 0, inp2[2] if inp2 else 0, ups[0], ups[1], epi])
-        P.named[prefix] = out
+                      inp2[0] if inp2 else -1, inp2[1] if inp2 else 0, inp2[2] if inp2 else 0, ups[0], ups[1], epi] + tail)
+        if not chain2:
+            P.named[prefix] = out
 
+    pending = {}                          # Conv layers chained into the cv1 of the C2f that follows them
     for L in layers:
         i, t = L["i"], L["type"]
         p = f"model.{i}"
         h, w = hw[i]
         if t == "Conv":
-            out = out_loc(L)
+            out = None
             if i == 0:
+                out = out_loc(L)
                 if L["k"] != 3 or L["s"] != 2 or L["c1"] != 3:
                     raise NotImplementedError("stem must be Conv(3 -> C0, k=3, s=2)")
                 wf, bf = weights.fold_conv_bn(sd, p)
@@ -204,6 +235,15 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
                 P.ops.append([OP_STEM, out[0], out[1], L["c2"], woff, boff] + [0] * (OP_WORDS - 6))
                 P.named[p] = out
             else:
+                nxt = consumers.get(i, [])
+                Lc = layers[nxt[0]] if len(nxt) == 1 else None
+                hi_, wi_ = hw[src(i, L["f"])]
+                if (chain and Lc is not None and Lc["type"] == "C2f" and not isinstance(Lc["f"], tuple) and src(Lc["i"], Lc["f"]) == i
+                        and i not in placement and L["k"] == 3 and _chain_ok(hi_, wi_, L["c1"], L["c2"], 3, L["s"], False, 0, 2 * Lc["c"])):
+                    pending[i] = (p, P.loc[src(i, L["f"])], L)          # emitted together with the C2f's cv1
+                    P.loc[i] = None
+                    continue
+                out = out_loc(L)
                 emit_conv(p, P.loc[src(i, L["f"])], out, L["k"], L["s"], True)
             P.loc[i] = out
         elif t == "C2f":
@@ -214,15 +254,26 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
             if s_in in virtual:                                   # Concat([Upsample(a), b]) folded into cv1
                 (la, ua), (lb, ub) = virtual[s_in]
                 emit_conv(p + ".cv1", P.loc[la], (cat, 0, 2 * c), 1, 1, True, inp2=P.loc[lb], ups=(ua, ub))
+            elif s_in in pending:                                 # Conv(k3) -> cv1 in one launch
+                pp, pin, Lp = pending.pop(s_in)
+                emit_conv(pp, pin, (cat, 0, 2 * c), Lp["k"], Lp["s"], True, chain2=dict(prefix=p + ".cv1", bn=True, x=None))
             else:
                 emit_conv(p + ".cv1", P.loc[s_in], (cat, 0, 2 * c), 1, 1, True)
+            out = out_loc(L)
             for j in range(n):
                 a = (cat, (1 + j) * c, c)
                 tmp = P.new_buf(h, w, c)
                 emit_conv(f"{p}.m.{j}.cv1", a, (tmp, 0, c), 3, 1, True)
-                emit_conv(f"{p}.m.{j}.cv2", (tmp, 0, c), (cat, (2 + j) * c, c), 3, 1, True, res=a if L["shortcut"] else None)
-            out = out_loc(L)
-            emit_conv(p + ".cv2", (cat, 0, (2 + n) * c), out, 1, 1, True)
+                res = a if L["shortcut"] else None
+                if chain and j == n - 1 and _chain_ok(h, w, c, c, 3, 1, res is not None, (1 + n) * c, L["c2"]):
+                    # last bottleneck conv + cv2 in one launch: cv2's other inputs (y0, y1, m_1..m_n-1) are the first (1+n)c
+                    # channels of the C2f buffer, its last c input channels never leave the SM
+                    emit_conv(f"{p}.m.{j}.cv2", (tmp, 0, c), out, 3, 1, True, res=res,
+                              chain2=dict(prefix=p + ".cv2", bn=True, x=(cat, 0, (1 + n) * c)))
+                    break
+                emit_conv(f"{p}.m.{j}.cv2", (tmp, 0, c), (cat, (2 + j) * c, c), 3, 1, True, res=res)
+            else:
+                emit_conv(p + ".cv2", (cat, 0, (2 + n) * c), out, 1, 1, True)
             P.loc[i] = out
         elif t == "SPPF":
             if L["k"] != 5:
@@ -249,7 +300,6 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
             for l, f in enumerate(L["f"]):
                 inp = P.loc[f]
                 hh, ww = hw[f]
-                t2, u2 = P.new_buf(hh, ww, cb), P.new_buf(hh, ww, cc)
                 if merge_head and (cb + cc) <= 256 and cb % 8 == 0:
                     # the first conv of the box branch and of the class branch read the same feature map: one conv, Cout = cb + cc
                     tu = P.new_buf(hh, ww, cb + cc)
@@ -260,15 +310,23 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True):
                     emit_conv(f"{p}.cv2.{l}.0", inp, (t1, 0, cb), 3, 1, True)
                     emit_conv(f"{p}.cv3.{l}.0", inp, (u1, 0, cc), 3, 1, True)
                     t1_loc, u1_loc = (t1, 0, cb), (u1, 0, cc)
-                emit_conv(f"{p}.cv2.{l}.1", t1_loc, (t2, 0, cb), 3, 1, True)
-                emit_conv(f"{p}.cv3.{l}.1", u1_loc, (u2, 0, cc), 3, 1, True)
                 if fuse_head and nc <= 256:
                     dist = P.new_buf(hh, ww, 8)                       # 4 fp32 per pixel
                     clsb = P.new_buf(hh, ww, 4)                       # 2 fp32 per pixel
-                    emit_conv(f"{p}.cv2.{l}.2", (t2, 0, cb), (dist, 0, 8), 1, 1, False, epi=1)
-                    emit_conv(f"{p}.cv3.{l}.2", (u2, 0, cc), (clsb, 0, 4), 1, 1, False, epi=2)
+                    for q, a_loc, c_, o_loc, e_, n2 in ((f"{p}.cv2.{l}", t1_loc, cb, (dist, 0, 8), 1, 64),
+                                                    (f"{p}.cv3.{l}", u1_loc, cc, (clsb, 0, 4), 2, nc)):
+                        if chain and _chain_ok(hh, ww, c_, c_, 3, 1, False, 0, n2):
+                            # 3x3 conv + the branch's final 1x1 conv + DFL / class-max epilogue in one launch
+                            emit_conv(q + ".1", a_loc, o_loc, 3, 1, True, epi=e_, chain2=dict(prefix=q + ".2", bn=False, x=None))
+                        else:
+                            t_loc = (P.new_buf(hh, ww, c_), 0, c_)
+                            emit_conv(q + ".1", a_loc, t_loc, 3, 1, True)
+                            emit_conv(q + ".2", t_loc, o_loc, 1, 1, False, epi=e_)
                     P.levels.append((-1, H // hh, dist, clsb))
                 else:
+                    t2, u2 = P.new_buf(hh, ww, cb), P.new_buf(hh, ww, cc)
+                    emit_conv(f"{p}.cv2.{l}.1", t1_loc, (t2, 0, cb), 3, 1, True)
+                    emit_conv(f"{p}.cv3.{l}.1", u1_loc, (u2, 0, cc), 3, 1, True)
                     logits = P.new_buf(hh, ww, P.lstride)
                     emit_conv(f"{p}.cv2.{l}.2", (t2, 0, cb), (logits, 0, 64), 1, 1, False)
                     emit_conv(f"{p}.cv3.{l}.2", (u2, 0, cc), (logits, 64, nc), 1, 1, False)
@@ -297,7 +355,8 @@ class Engine:
         self.lib = _lib.load()
         self.spec, self.B, self.H, self.W = spec, int(batch), int(H), int(W)
         # B2_MERGE_HEAD=0: keep Detect's first box / class convs as two launches (A/B experiments)
-        self.plan = lower(spec, state_dict, H, W, fuse_head=fuse_head, merge_head=os.environ.get("B2_MERGE_HEAD", "1") != "0")
+        self.plan = lower(spec, state_dict, H, W, fuse_head=fuse_head, merge_head=os.environ.get("B2_MERGE_HEAD", "1") != "0",
+                          chain=os.environ.get("B2_CHAIN", "1") != "0")      # B2_CHAIN=0: every conv its own launch (A/B experiments)
         self.fused_head = self.plan.levels[0][0] < 0
         words = self.plan.words()
         blob = self.plan.blob.bytes()
@@ -376,6 +435,11 @@ class Engine:
                 fl = 2 * h * w * cout * ct * k * k * self.B
                 nbytes = (in_elems + h * w * cout * (2 if rb >= 0 else 1)) * 2 * self.B + cout * ct * k * k * 2
                 desc = f"{ct}->{cout} k{k} s{s} @{h}x{w}" + ("  [up2|cat]" if ib2 >= 0 else "")
+                if op[20]:          # chained 1x1 conv: its flops, its extra source, its output instead of the main conv's
+                    cout2, xc = op[23], op[27]
+                    fl += 2 * h * w * cout2 * (cout + xc) * self.B
+                    nbytes = (in_elems + h * w * (xc + cout2 + (cout if rb >= 0 else 0))) * 2 * self.B + (cout * ct * k * k + cout2 * (cout + xc)) * 2
+                    desc += f"  -> 1x1 {cout + xc}->{cout2}"
                 if op[19]:
                     nbytes = (in_elems * 2 + h * w * (16 if op[19] == 1 else 8)) * self.B + cout * ct * 2
                     desc += "  [DFL]" if op[19] == 1 else "  [cls max]"

@@ -49,6 +49,32 @@ def conv2d_bf16(x, w, bias, ksize, stride=1, act=True, out=None, out_coff=0, in_
     return out
 
 
+def conv_chain_plan_ok(H, W, cin, cout, ksize, stride, has_residual, xc, cout2, B=1):
+    """Does ``conv2d_chain_bf16`` take this pair?  (Pure planning in the library; works without a GPU.)"""
+    return bool(_lib.load().b2_conv_chain_plan_ok(B, H, W, cin, cout, ksize, stride, int(bool(has_residual)), xc, cout2))
+
+
+def conv2d_chain_bf16(x, w, bias, stride, w2, bias2, act=True, act2=True, residual=None, extra=None, out=None, out_coff=0, stream=None):
+    """SiLU(conv3x3(x) + b) (+ residual), rounded to bf16, concatenated BEHIND ``extra`` along channels and fed to the 1x1 conv
+    ``w2`` [Cout2][Cx + Cout] (+ SiLU if ``act2``), in one launch (csrc/conv_tc.cu, ConvParams::chain).
+    x: [B][H][W][Cin] bf16, w: [Cout][3][3][Cin], extra: [B][Ho][Wo][Cx] bf16 or None.  Returns [B][Ho][Wo][Cout2] bf16.
+    Raises NotImplementedError when the pair does not fit the chained kernel."""
+    torch = _torch()
+    lib = _lib.load()
+    B, H, W, cin = x.shape
+    cout, cout2 = w.shape[0], w2.shape[0]
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, cout2), dtype=torch.bfloat16, device=x.device)
+    xc = extra.shape[3] if extra is not None else 0
+    assert tuple(w2.shape) == (cout2, xc + cout) and x.is_contiguous() and w.is_contiguous() and w2.is_contiguous()
+    _lib.check(lib.b2_conv2d_chain_bf16(_lib.ptr(x), B, H, W, cin, 0, cin, _lib.ptr(w), _lib.ptr(bias), cout, 3, stride, 1 if act else 0,
+                                        _lib.ptr(residual), residual.shape[3] if residual is not None else 0, 0,
+                                        _lib.ptr(extra), xc, 0, xc, _lib.ptr(w2), _lib.ptr(bias2), cout2, 1 if act2 else 0,
+                                        _lib.ptr(out), out.shape[3], out_coff, _lib.stream_ptr(stream)))
+    return out
+
+
 def conv2d_cat_bf16(x0, x1, w, bias, ksize=1, stride=1, act=True, up0=1, up1=1, out=None, out_coff=0, stream=None):
     """Conv over cat([up(x0), up(x1)], channel) without materialising the upsample or the concat.
     x0, x1: [B][h][w][C] bf16 (full NHWC tensors; up_i = 2 means stored at half the conv resolution)."""
