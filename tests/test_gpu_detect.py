@@ -137,8 +137,8 @@ def test_engine_graph_and_end_to_end_drift(n_p2):
     heads = net.forward(x, record=True)
     errs = {}
     for name, ref in net.trace.items():
-        if name.startswith("layer."):
-            continue
+        if name.startswith("layer.") or name not in eng.plan.named:
+            continue                      # chained launches keep their intermediate tile in shared memory: no buffer to read
         got = eng.activation(name).cpu().numpy()
         assert got.shape == ref.shape, name
         errs[name] = _rel_l2(got, ref)

@@ -87,8 +87,8 @@ def test_chained_conv_matches_oracle(case):
     ex = _rand_bf16(g, (B, Ho, Wo, cx)) if cx else None
     w2 = _rand_bf16(g, (cout2, cx + cout), 1.0 / np.sqrt((cx + cout) * 0.36))
     b2 = g.standard_normal(cout2).astype(np.float32) * 0.1
-    got = ops.conv2d_chain_bf16(_dev(x), _dev(w), torch.from_numpy(b).cuda(), stride, _dev(w2), torch.from_numpy(b2).cuda(), act=True, act2=act2,
-                                residual=None if res is None else _dev(res), extra=None if ex is None else _dev(ex)).float().cpu().numpy()
+    got = ops.conv2d_chain_bf16(_bf16_tensor(x), _bf16_tensor(w), torch.from_numpy(b).cuda(), stride, _bf16_tensor(w2), torch.from_numpy(b2).cuda(), act=True, act2=act2,
+                                residual=None if res is None else _bf16_tensor(res), extra=None if ex is None else _bf16_tensor(ex)).float().cpu().numpy()
     mid = onet.silu(onet.conv2d(x.transpose(0, 3, 1, 2), np.ascontiguousarray(w.transpose(0, 3, 1, 2)), b, stride, 1))
     if has_res:
         mid = mid + res.transpose(0, 3, 1, 2)

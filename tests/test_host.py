@@ -71,7 +71,7 @@ def test_lowering_is_consistent(name, hw):
     assert sum(1 for o in Pf.ops if o[19] == 1) == 4 and sum(1 for o in Pf.ops if o[19] == 2) == 4
     # chained launches (default): same arithmetic, one launch less per chained pair, every chained op well formed
     for fh in (False, True):
-        Pc = engine.lower(spec, sd, *hw, fuse_head=fh)
+        Pc = engine.lower(spec, sd, *hw, fuse_head=fh, chain=15)
         nch = sum(1 for o in Pc.ops if o[0] == engine.OP_CONV and o[20])
         assert Pc.flops == P.flops and len(Pc.ops) == len(P.ops) - nch
         if name == "yolov8s-p2":

@@ -441,7 +441,6 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
             }
         }
         pdl_wait();                 // activations of the previous layer: only after the predecessor grid has completed
-        int kk = 0;                 // CH: ordinal of the tile inside this CTA
         // p.mma_warps == 2: two stage rings of num_stages / 2 slots; ring r holds the tiles issued by MMA warp r (a ring with
         // two consumers would let one of them run a whole revolution ahead, which mbarrier phase parity cannot tell apart)
         const int ring_stages = MW == 2 ? num_stages >> 1 : num_stages;
@@ -498,21 +497,6 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                         if (++stage == stage_hi) { stage = stage_lo; phase ^= 1; }
                     }
                 }
-            }
-            if (CH) {
-                // TMA-fed K blocks of the chained GEMM (the tile's own pixels, no halo), into staged-tile buffer kk & 1 once the
-                // chained MMAs of tile kk - 2 have read it.  Issued after this tile's main loads so that those are not held up.
-                if (p.c2_nx) {
-                    const int buf = kk & 1;
-                    mbar_wait(&a2_empty[buf], ((uint32_t)(kk >> 1) & 1u) ^ 1u);
-                    if (leader) {
-                        mbar_expect_tx(&x_full[buf], p.c2_x_tx);
-                        for (int i = 0; i < p.c2_nx; ++i)
-                            tma_load_4d(smem + p.c2_buf_off + (size_t)buf * p.c2_buf_bytes + p.c2_a_off[i], &p.tmX[i], &x_full[buf], p.c2_src_c[i], w0, h0, n0);
-                    }
-                    __syncwarp();
-                }
-                ++kk;
             }
             if (MW == 2) {                                  // the next tile belongs to the other MMA warp: switch rings
                 const int ts_ = stage; stage = ostage; ostage = ts_;
@@ -671,6 +655,20 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
         const uint32_t magic_nt = p.magic_nt, magic_tw = p.magic_tw, magic_th = p.magic_th;
         int kk = 0;                                         // CH: ordinal of the tile inside this CTA (buffer kk & 1, parity (kk >> 1) & 1)
         const uint32_t smem_lo = smem_u32(smem);
+        // CH with TMA-fed K blocks (the channels the 1x1 conv reads besides this conv's output): one lane of the first E2 warp
+        // loads them -- for tiles 0 and 1 up front, for tile kk + 2 as soon as the chained MMAs of tile kk have completed (which is
+        // what this warp waits for anyway, and what frees staged-tile buffer kk & 1).  The producer warp never waits on the chain.
+        const bool x_issuer = CH && p.c2_nx > 0 && ew == kE1Warps && lane == 0;
+        auto x_load = [&](int t, int buf) {
+            const int m0 = fast_div(t, magic_nt);
+            const int m1 = fast_div(m0, magic_tw), m2 = fast_div(m1, magic_th);
+            const int w0 = (m0 - m1 * tiles_w) * TW, h0 = (m1 - m2 * tiles_h) * TH, n0 = m2 * NB;
+            mbar_expect_tx(&x_full[buf], p.c2_x_tx);
+            for (int i = 0; i < p.c2_nx; ++i)
+                tma_load_4d(smem + p.c2_buf_off + (size_t)buf * p.c2_buf_bytes + p.c2_a_off[i], &p.tmX[i], &x_full[buf], p.c2_src_c[i], w0, h0, n0);
+        };
+        if (x_issuer)
+            for (int j = 0; j < 2; ++j) if ((int)blockIdx.x + j * (int)gridDim.x < total_tiles) x_load((int)blockIdx.x + j * (int)gridDim.x, j);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++kk) {
             const int m0 = fast_div(tile, magic_nt), n_idx = tile - m0 * n_tiles;
             const int m1 = fast_div(m0, magic_tw), m2 = fast_div(m1, magic_th);
@@ -736,8 +734,10 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
             // final epilogue: the conv's own accumulator, or (CH) the chained accumulator kk & 1
             const float* const s_bias_f = CH ? s_bias2 : s_bias;
             const int act_f = CH ? p.c2_act : act;
-            if (CH) mbar_wait(&t2_full[kk & 1], (uint32_t)(kk >> 1) & 1u);
-            else mbar_wait(&tfull_bar[acc], acc_phase);
+            if (CH) {
+                mbar_wait(&t2_full[kk & 1], (uint32_t)(kk >> 1) & 1u);
+                if (x_issuer && tile + 2 * (int)gridDim.x < total_tiles) x_load(tile + 2 * (int)gridDim.x, kk & 1);
+            } else mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (CH ? p.c2_tmem_col + (uint32_t)((kk & 1) * p.c2_n) : (uint32_t)(acc * n_tile));
             if (epi == 0) {

@@ -109,6 +109,13 @@ def _chain_ok(H, W, cin, cout, k, s, has_res, xc, cout2):
     return bool(lib.b2_conv_chain_plan_ok(1, int(H), int(W), int(cin), int(cout), int(k), int(s), int(bool(has_res)), int(xc), int(cout2)))
 
 
+CHAIN_CONV_CV1, CHAIN_C2F_TAIL, CHAIN_DETECT_BOX, CHAIN_DETECT_CLS = 1, 2, 4, 8
+# measured on the bench workload (tools/ab_chain.py, one process, per-launch CUDA events; conv time of one forward 10.33 ms unchained):
+# CONV_CV1 -0.07 ms, C2F_TAIL -0.11 ms, DETECT_BOX -0.10 ms, DETECT_CLS +0.19 ms (its class-max epilogue on 8 warps is slower than
+# the stand-alone tail kernel's 16) -> the class tail stays a launch of its own
+CHAIN_DEFAULT = CHAIN_CONV_CV1 | CHAIN_C2F_TAIL | CHAIN_DETECT_BOX
+
+
 def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True, chain=True):
     """Lower ``spec`` (from :func:`cfg.resolve`) with weights ``state_dict`` for an ``H x W`` letterboxed input.
 
@@ -117,6 +124,7 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True, chain=True):
     exposes ``b2_engine_head`` buffers instead of ``b2_engine_levels`` logits."""
     if H % 32 or W % 32:
         raise ValueError(f"input size {H}x{W} must be a multiple of the maximum stride 32")
+    chain = CHAIN_DEFAULT if chain is True else int(chain or 0)      # bit mask of the CHAIN_* patterns to take
     sd = state_dict
     layers = spec["layers"]
     hw = _shapes(spec, H, W)
@@ -238,7 +246,7 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True, chain=True):
                 nxt = consumers.get(i, [])
                 Lc = layers[nxt[0]] if len(nxt) == 1 else None
                 hi_, wi_ = hw[src(i, L["f"])]
-                if (chain and Lc is not None and Lc["type"] == "C2f" and not isinstance(Lc["f"], tuple) and src(Lc["i"], Lc["f"]) == i
+                if ((chain & CHAIN_CONV_CV1) and Lc is not None and Lc["type"] == "C2f" and not isinstance(Lc["f"], tuple) and src(Lc["i"], Lc["f"]) == i
                         and i not in placement and L["k"] == 3 and _chain_ok(hi_, wi_, L["c1"], L["c2"], 3, L["s"], False, 0, 2 * Lc["c"])):
                     pending[i] = (p, P.loc[src(i, L["f"])], L)          # emitted together with the C2f's cv1
                     P.loc[i] = None
@@ -265,7 +273,7 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True, chain=True):
                 tmp = P.new_buf(h, w, c)
                 emit_conv(f"{p}.m.{j}.cv1", a, (tmp, 0, c), 3, 1, True)
                 res = a if L["shortcut"] else None
-                if chain and j == n - 1 and _chain_ok(h, w, c, c, 3, 1, res is not None, (1 + n) * c, L["c2"]):
+                if (chain & CHAIN_C2F_TAIL) and j == n - 1 and _chain_ok(h, w, c, c, 3, 1, res is not None, (1 + n) * c, L["c2"]):
                     # last bottleneck conv + cv2 in one launch: cv2's other inputs (y0, y1, m_1..m_n-1) are the first (1+n)c
                     # channels of the C2f buffer, its last c input channels never leave the SM
                     emit_conv(f"{p}.m.{j}.cv2", (tmp, 0, c), out, 3, 1, True, res=res,
@@ -315,7 +323,7 @@ def lower(spec, state_dict, H, W, fuse_head=False, merge_head=True, chain=True):
                     clsb = P.new_buf(hh, ww, 4)                       # 2 fp32 per pixel
                     for q, a_loc, c_, o_loc, e_, n2 in ((f"{p}.cv2.{l}", t1_loc, cb, (dist, 0, 8), 1, 64),
                                                     (f"{p}.cv3.{l}", u1_loc, cc, (clsb, 0, 4), 2, nc)):
-                        if chain and _chain_ok(hh, ww, c_, c_, 3, 1, False, 0, n2):
+                        if (chain & (CHAIN_DETECT_BOX if e_ == 1 else CHAIN_DETECT_CLS)) and _chain_ok(hh, ww, c_, c_, 3, 1, False, 0, n2):
                             # 3x3 conv + the branch's final 1x1 conv + DFL / class-max epilogue in one launch
                             emit_conv(q + ".1", a_loc, o_loc, 3, 1, True, epi=e_, chain2=dict(prefix=q + ".2", bn=False, x=None))
                         else:
@@ -356,7 +364,7 @@ class Engine:
         self.spec, self.B, self.H, self.W = spec, int(batch), int(H), int(W)
         # B2_MERGE_HEAD=0: keep Detect's first box / class convs as two launches (A/B experiments)
         self.plan = lower(spec, state_dict, H, W, fuse_head=fuse_head, merge_head=os.environ.get("B2_MERGE_HEAD", "1") != "0",
-                          chain=os.environ.get("B2_CHAIN", "1") != "0")      # B2_CHAIN=0: every conv its own launch (A/B experiments)
+                          chain=int(os.environ.get("B2_CHAIN", str(CHAIN_DEFAULT))))      # B2_CHAIN: bit mask of CHAIN_* (0: every conv its own launch)
         self.fused_head = self.plan.levels[0][0] < 0
         words = self.plan.words()
         blob = self.plan.blob.bytes()
