@@ -189,6 +189,14 @@ int b2_engine_use_graph(b2_engine_t* e, int on);
 typedef struct b2_tracker b2_tracker_t;
 int b2_tracker_create(int n_streams, int capacity, int max_dets, int max_lost_frames, int min_hits,
                       float iou_threshold, b2_tracker_t** out);
+/* mode 1: the same bank driven by the rules of camera_motion_compensation/motion_compensated_multi_tracker.py:75-283 (update
+ * without a frame) over MotionResetKalmanTracker tracks (motion_reset_kalman_tracker.py:16-355): per-track position-jump /
+ * velocity-change / size-change detectors with a 15-frame cooldown, reset = state overwritten by the detection with the
+ * covariance rescaled, the association box blended towards the last stored position for 10 frames after a reset, candidates
+ * IoU > threshold with ties to the LARGER (detection, track), every live track reported.  stats (b2_tracker_export /
+ * b2_tracker_stats): slots 3 / 4 hold individual_resets / tracking_recoveries ([6], [7] of b2_tracker_stats). */
+int b2_tracker_create_ex(int n_streams, int capacity, int max_dets, int max_lost_frames, int min_hits,
+                         float iou_threshold, int mode, b2_tracker_t** out);
 int b2_tracker_destroy(b2_tracker_t* t);
 int b2_tracker_reset(b2_tracker_t* t, void* stream);
 /* The reference's track list is unbounded (enhanced_multi_target_tracker.py:92-101 appends); the bank is not.  A caller that
@@ -210,6 +218,14 @@ int b2_tracker_stats(b2_tracker_t* t, long long* stats_dev_out, void* stream);
  * candidate detection; then new tracks): order by column 0 for the reference's list order. */
 int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_cols, const int32_t* det_counts,
                       float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, int out_cap, void* stream);
+/* The same with the per-row extras of a mode-1 bank: out_extra (may be NULL): [n_streams][out_cap][4]
+ * {reset_count (i32), frames_since_reset (i32), motion_consistency (fp32), 0} (get_track_info, motion_reset_kalman_tracker.py:323-342). */
+int b2_tracker_update_ex(b2_tracker_t* t, const float* dets, int det_cols, const int32_t* det_counts,
+                         float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, float* out_extra,
+                         int out_cap, void* stream);
+/* mode-1 bank, one stream (synchronises): reset_host [cap][8] {id, reset_count, last_reset_frame, (i32 bits) motion_consistency (fp32),
+ * len(position_history), len(motion_scores), len(bbox_history) (i32 bits), 0}, slot order. */
+int b2_tracker_export_reset(b2_tracker_t* t, int stream_idx, float* reset_host, int32_t* n_tracks_host);
 /* Host-side inspection (synchronises): dense state of one stream.  x: [cap][8], P: [cap][64] (dense 8x8
  * rebuilt from the decoupled blocks), meta: [cap][8] int32 {id, age, hits, hit_streak, tsu, lost_frames, is_lost, n_vel},
  * stats: [8] int64 {created, terminated, active, long_term_predictions, recoveries, frame_count, next_track_id,

@@ -162,9 +162,13 @@ def test_engine_graph_and_end_to_end_drift(n_p2):
         assert torch.equal(first[l], eng.level_logits(l))
 
 
+@pytest.mark.parametrize("chain", ["default", "15", "0"])
 @pytest.mark.parametrize("name,nc", [("yolov8n-p2", 80), ("yolov8n-p2", 1), ("yolov8s-p2", 80)])
-def test_fused_head_equals_unfused_decode(name, nc):
-    """DFL + class max inside the conv epilogue (fused head) vs plain logits + decode kernel: same candidates, same bits."""
+def test_fused_head_equals_unfused_decode(name, nc, chain, monkeypatch):
+    """DFL + class max inside the conv epilogue (fused head) vs plain logits + decode kernel: same candidates, same bits --
+    with the default chained launches, with every chain pattern on (B2_CHAIN=15: the class tail too) and with none."""
+    if chain != "default":
+        monkeypatch.setenv("B2_CHAIN", chain)
     from b200dt import ops
     from b200dt.engine import Engine
 

@@ -380,3 +380,40 @@ def test_ultralytics_kf_general_covariance_matches_oracle(kind):
         um, uc = okf.update(kind, rm, rc, meas[n])
         assert np.abs(m2[n] - um).max() / max(np.abs(um).max(), 1.0) < 5e-5      # dense fp32 Cholesky solve of a general S
         assert np.abs(c2[n] - uc).max() / np.abs(uc).max() < 5e-5
+
+
+# ----------------------------------------------------------------------------- N1: camera-motion compensation on the bank
+def test_motion_compensated_multi_tracker_matches_reference():
+    """MotionCompensatedMultiTracker.update(detections) on the CUDA bank (mode 1) against the reference's own output
+    (tests/golden/motion_multi.npz: 160 frames, camera shakes, a zoom): the same number of live tracks every frame, the same
+    reset decisions and lifecycle counters bit for bit, state and boxes to 1e-5, list order = ascending id."""
+    from b200dt.tracker import MotionCompensatedMultiTracker
+
+    g = np.load(os.path.join(G, "motion_multi.npz"))
+    dets, ndets, rows, counts, stats = g["dets"], g["ndets"], g["rows"], g["counts"], g["stats"]
+    trk = MotionCompensatedMultiTracker(150, 1, 0.1, capacity=64, max_dets=32)
+    k = 0
+    worst_x = worst_b = 0.0
+    for f in range(len(ndets)):
+        d = [[float(v) for v in dets[f, 5 * i:5 * i + 5]] for i in range(int(ndets[f]))]
+        res = trk.update(d)
+        assert len(res) == counts[f], f"frame {f}"
+        x, P, meta, _ = trk.bank.export(0)
+        rs = trk.bank.export_reset(0)
+        assert len(x) == len(res)
+        for j, info in enumerate(res):
+            r = rows[k]; k += 1
+            # golden row: bbox(4) x(8) confidence reset_count age hits hit_streak time_since_update is_lost lost_frames motion_consistency frames_since_reset
+            exact_got = [info["reset_count"], info["age"], info["hits"], info["hit_streak"], info["time_since_update"], int(meta[j, 6]), int(meta[j, 5]),
+                         info["frames_since_reset"]]
+            exact_ref = [r[13], r[14], r[15], r[16], r[17], r[18], r[19], r[21]]
+            assert exact_got == [int(v) for v in exact_ref], (f, j, exact_got, exact_ref)
+            worst_b = max(worst_b, float(np.abs(np.asarray(info["bbox"]) - r[0:4]).max() / max(np.abs(r[0:4]).max(), 1.0)))
+            worst_x = max(worst_x, float(np.abs(x[j] - r[4:12]).max() / max(np.abs(r[4:12]).max(), 1.0)))
+            assert abs(info["confidence"] - r[12]) < 1e-5
+            assert abs(info["motion_consistency"] - r[20]) < 1e-4 and abs(rs[j, 3] - r[20]) < 1e-4
+    assert k == len(rows)
+    assert worst_x < STATE_RTOL and worst_b < STATE_RTOL, (worst_x, worst_b)
+    assert [trk.stats["total_frames"], trk.stats["individual_resets"], trk.stats["tracking_recoveries"]] == [int(v) for v in stats[:3]]
+    with pytest.raises(NotImplementedError):
+        trk.update([], frame=np.zeros((8, 8, 3), np.uint8))

@@ -52,12 +52,15 @@ SIGNATURES = {
     "b2_engine_num_launches": (c_int, [_P]),
     "b2_engine_use_graph": (c_int, [_P, c_int]),
     "b2_tracker_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, C.POINTER(_P)]),
+    "b2_tracker_create_ex": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_int, C.POINTER(_P)]),
     "b2_tracker_destroy": (c_int, [_P]),
     "b2_tracker_reset": (c_int, [_P, _P]),
     "b2_tracker_capacity": (c_int, [_P]),
     "b2_tracker_grow": (c_int, [_P, c_int, _P]),
     "b2_tracker_stats": (c_int, [_P, _P, _P]),
     "b2_tracker_update": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, c_int, _P]),
+    "b2_tracker_update_ex": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "b2_tracker_export_reset": (c_int, [_P, c_int, _P, _P]),
     "b2_tracker_export": (c_int, [_P, c_int, _P, _P, _P, _P, _P]),
     "b2_tracker_export_motion": (c_int, [_P, c_int, _P, _P]),
     "b2_tracker_bytes_per_track": (c_int, [C.POINTER(c_int), C.POINTER(c_int)]),

@@ -36,6 +36,14 @@ namespace {
 
 enum FField { X0 = 0, X1, X2, X3, X4, X5, X6, X7, PPX, PPV, PVV, PSX, PSV, PSVV, VAVGX, VAVGY, DIRN, SPEED, STAB, PCONF, NFF };
 enum IField { ID = 0, AGE, HITS, STREAK, TSU, LOSTF, ISLOST, NVEL, VHEAD, TLEN, THEAD, NIF };
+// mode 1 (camera_motion_compensation/motion_reset_kalman_tracker.py:16-355): per-slot reset state
+//   position_history deque(maxlen=8) (:41), last bbox of bbox_history + its length (:43, only [-1] and len >= 2 are read),
+//   motion_scores deque(maxlen=10) (:55), motion_consistency, reset_count, last_reset_frame (:52-53)
+constexpr int kPosRing = 8, kScoreRing = 10;
+enum MRF { MR_PH = 0, MR_BB = MR_PH + 2 * kPosRing, MR_MS = MR_BB + 4, MR_MCONS = MR_MS + kScoreRing, MR_NF };
+enum MRI { MR_PHLEN = 0, MR_PHHEAD, MR_BBLEN, MR_MSLEN, MR_MSHEAD, MR_RESETS, MR_LASTRESET, MR_NI };
+constexpr float kJumpThr = 40.f, kVelThr = 60.f, kSizeThr = 0.3f;      // :46-48
+constexpr int kResetCooldown = 15;                                     // :49
 constexpr int kVelRing = 50;       // deque(maxlen=50)  enhanced_aircraft_kalman_tracker.py:79
 constexpr int kTraj = B2_TRAJ_LEN; // only the last 30 trajectory points are ever read (:377)
 constexpr int kChunk = 256;        // slots per sweep block
@@ -52,6 +60,8 @@ struct Bank {
     int32_t* i;     // [NIF][N]
     float* vel;     // [kVelRing*2][N]
     float* traj;    // [kTraj*2][N]
+    float* mrf;     // mode 1: [MR_NF][N]
+    int32_t* mri;   // mode 1: [MR_NI][N]
     // ---- per-frame scratch ----
     unsigned long long* agg;   // [S][nchunks] chunk aggregates of the sweep: bit 63 valid | pairs << 32 | cand << 16 | emitted
     int32_t* chunk_free;       // [S][nchunks] free slots per chunk after the sweep
@@ -64,8 +74,10 @@ struct Bank {
     uint4* pairs;              // [S][pair_cap] {iou bits, det, candidate index, track id}
     int32_t* next_id;          // [S]
     int32_t* frame_count;      // [S]
-    long long* stats;          // [S][8]: created, terminated, active, long_term, recoveries, dropped (no free slot)
+    long long* stats;          // [S][8]: created, terminated, active, long_term, recoveries, dropped (no free slot),
+                               //         mode 1: individual_resets, tracking_recoveries (motion_compensated_multi_tracker.py:58-66)
     int S, C, N, max_dets, nchunks, pair_cap;
+    int mode;                  // 0: EnhancedMultiTargetTracker; 1: MotionCompensatedMultiTracker (update without a frame)
     int max_lost, min_hits; float iou_thr;
 };
 
@@ -73,6 +85,7 @@ struct Frame {
     const float* dets; int det_cols; const int32_t* det_counts;
     float* out_rows; int32_t* out_counts; float* out_traj; int32_t* out_traj_len;
     int out_cap;   // rows per stream the output buffers hold (<= capacity); rows beyond are counted, not written
+    float* out_extra;          // mode 1 (may be NULL): [S][out_cap][4] {reset_count (i32), frames_since_reset (i32), motion_consistency, 0}
 };
 
 struct b2_tracker_impl {
@@ -83,6 +96,21 @@ struct b2_tracker_impl {
 
 __device__ __forceinline__ float& FF(const Bank& b, int field, int g) { return b.f[(size_t)field * b.N + g]; }
 __device__ __forceinline__ int32_t& II(const Bank& b, int field, int g) { return b.i[(size_t)field * b.N + g]; }
+__device__ __forceinline__ float& RF(const Bank& b, int field, int g) { return b.mrf[(size_t)field * b.N + g]; }
+__device__ __forceinline__ int32_t& RI(const Bank& b, int field, int g) { return b.mri[(size_t)field * b.N + g]; }
+
+// MotionResetKalmanTracker.predict (:300-321): for 10 frames after a reset the box handed to the association is centred between
+// the last stored position and the Kalman prediction; the state is not touched.  age: after the predict's increment.
+__device__ __forceinline__ float4 blended_box(const Bank& b, int g, int age, float cx, float cy, float w, float h) {
+    const int since = age - RI(b, MR_LASTRESET, g), n = RI(b, MR_PHLEN, g);
+    if (since < 10 && n > 0) {
+        int last = RI(b, MR_PHHEAD, g) - 1; if (last < 0) last += kPosRing;
+        const float blend = fminf((float)since / 10.f, 1.f);
+        cx = (1.f - blend) * RF(b, MR_PH + 2 * last, g) + blend * cx;
+        cy = (1.f - blend) * RF(b, MR_PH + 2 * last + 1, g) + blend * cy;
+    }
+    return make_float4(cx - w / 2.f, cy - h / 2.f, cx + w / 2.f, cy + h / 2.f);
+}
 
 __device__ __forceinline__ void push_traj(const Bank& b, int g, float cx, float cy) {
     int head = II(b, THEAD, g), len = II(b, TLEN, g);
@@ -246,6 +274,7 @@ __device__ __forceinline__ unsigned long long sweep_scan(unsigned long long v, u
 // Block b = chunk (b % nchunks) of stream (b / nchunks).  The aggregate look-back below waits for blocks with a LOWER block
 // index only; the hardware dispatches the blocks of a 1-D grid in index order, so a waiting block's predecessors are always
 // resident or finished (a bounded spin traps instead of hanging should that ever not hold).
+template <int MODE>
 __global__ void __launch_bounds__(kChunk, 4) sweep_kernel(const Bank b, const Frame fr) {
     extern __shared__ float4 s_det[];                              // [D] detections of the stream
     __shared__ __align__(16) float s_rows[kChunk * B2_TRACK_COLS];
@@ -298,12 +327,15 @@ __global__ void __launch_bounds__(kChunk, 4) sweep_kernel(const Bank b, const Fr
         age += 1; tsu += 1;
         b.traj[(size_t)(2 * thead) * N + g] = x[0]; b.traj[(size_t)(2 * thead + 1) * N + g] = x[1];
         thead = thead + 1 == kTraj ? 0 : thead + 1; tlen = min(tlen + 1, kTraj);
-        box = make_float4(x[0] - x[2] / 2.f, x[1] - x[3] / 2.f, x[0] + x[2] / 2.f, x[1] + x[3] / 2.f);   // state_to_bbox :121-135
+        box = MODE ? blended_box(b, g, age, x[0], x[1], x[2], x[3])
+                   : make_float4(x[0] - x[2] / 2.f, x[1] - x[3] / 2.f, x[0] + x[2] / 2.f, x[1] + x[3] / 2.f);   // state_to_bbox :121-135
         const float thr = b.iou_thr;
         for (int d = 0; d < D; ++d) {
             const float4 db = s_det[d];
-            if (fminf(db.z, box.z) > fmaxf(db.x, box.x) && fminf(db.w, box.w) > fmaxf(db.y, box.y))
-                npairs += iou_ref(db, box) >= thr ? 1 : 0;
+            if (fminf(db.z, box.z) > fmaxf(db.x, box.x) && fminf(db.w, box.w) > fmaxf(db.y, box.y)) {
+                const float v = iou_ref(db, box);
+                npairs += (MODE ? v > thr : v >= thr) ? 1 : 0;      // mode 1 candidates: strictly above (motion_compensated_multi_tracker.py:262)
+            }
         }
     }
     const bool cand = npairs > 0;
@@ -314,7 +346,7 @@ __global__ void __launch_bounds__(kChunk, 4) sweep_kernel(const Bank b, const Fr
         if (!islost) { islost = 1; lostf = 0; }
         lostf += 1;
         const bool del = tsu > b.max_lost || (age < 5 && tsu > 15) || (age < 10 && tsu > 30);
-        if (del) { II(b, ID, g) = 0; terminated = 1; freed = 1; }
+        if (del) { II(b, ID, g) = 0; terminated = 1; freed = 1; if (MODE && RI(b, MR_RESETS, g) > 0) atomicAdd(b.fcnt + s * 4 + 2, 1); }
         else {
             emit = 1;                                            // a lost track is always reported (multi_target_tracker.py:117-126)
             const int k = lostf;
@@ -326,6 +358,10 @@ __global__ void __launch_bounds__(kChunk, 4) sweep_kernel(const Bank b, const Fr
                 b.traj[(size_t)(2 * thead) * N + g] = x[0]; b.traj[(size_t)(2 * thead + 1) * N + g] = x[1];
                 thead = thead + 1 == kTraj ? 0 : thead + 1; tlen = min(tlen + 1, kTraj);
                 bx = x[0]; by = x[1]; bw = x[2]; bh = x[3]; conf = 1.f;
+                if (MODE) {                                      // the overridden predict() returns the blended box (:300-321)
+                    const float4 bb = blended_box(b, g, age, x[0], x[1], x[2], x[3]);
+                    bx = (bb.x + bb.z) / 2.f; by = (bb.y + bb.w) / 2.f;
+                }
             } else if (m[PCONF - VAVGX] > 0.3f) {                // high confidence: mean-velocity extrapolation (:224-236)
                 bx = x[0] + m[0] * (float)k; by = x[1] + m[1] * (float)k; bw = x[2]; bh = x[3];
                 conf = m[PCONF - VAVGX] * fmaxf(0.1f, 1.f - (float)k / (float)b.max_lost);
@@ -378,6 +414,9 @@ __global__ void __launch_bounds__(kChunk, 4) sweep_kernel(const Bank b, const Fr
         const int n4 = (min(e0 + n_emit, fr.out_cap) - e0) * (B2_TRACK_COLS / 4);
         for (int i = tid; i < n4; i += kChunk) dst4[i] = src4[i];
     }
+    if (MODE && emit && fr.out_extra && e0 + (int)(off & 0xFFFFu) < fr.out_cap)
+        reinterpret_cast<float4*>(fr.out_extra)[(size_t)s * fr.out_cap + e0 + (int)(off & 0xFFFFu)] =
+            make_float4(__int_as_float(RI(b, MR_RESETS, g)), __int_as_float(age - RI(b, MR_LASTRESET, g)), RF(b, MR_MCONS, g), 0.f);
     if (emit && fr.out_traj && e0 + (int)(off & 0xFFFFu) < fr.out_cap) {
         const int pos = e0 + (int)(off & 0xFFFFu);
         float* to = fr.out_traj + ((size_t)s * fr.out_cap + pos) * kTraj * 2;
@@ -398,7 +437,7 @@ __global__ void __launch_bounds__(kChunk, 4) sweep_kernel(const Bank b, const Fr
             const float4 db = s_det[d];
             if (fminf(db.z, box.z) > fmaxf(db.x, box.x) && fminf(db.w, box.w) > fmaxf(db.y, box.y)) {
                 const float v = iou_ref(db, box);
-                if (v >= thr) {
+                if (MODE ? v > thr : v >= thr) {
                     if (pp < (unsigned long long)b.pair_cap)
                         b.pairs[(size_t)s * b.pair_cap + pp] = make_uint4(__float_as_uint(v), (unsigned)d, (unsigned)ci, (unsigned)id);
                     ++pp;
@@ -517,6 +556,91 @@ __device__ __forceinline__ void init_slot(const Bank& b, int g, const float4& d,
     push_traj(b, g, cx, cy);
 }
 
+// ---- mode 1: MotionResetKalmanTracker (camera_motion_compensation/motion_reset_kalman_tracker.py) ----
+__device__ __forceinline__ void mr_push_pos(const Bank& b, int g, float cx, float cy) {       // position_history.append
+    int head = RI(b, MR_PHHEAD, g);
+    RF(b, MR_PH + 2 * head, g) = cx; RF(b, MR_PH + 2 * head + 1, g) = cy;
+    RI(b, MR_PHHEAD, g) = head + 1 == kPosRing ? 0 : head + 1;
+    RI(b, MR_PHLEN, g) = min(RI(b, MR_PHLEN, g) + 1, kPosRing);
+}
+__device__ __forceinline__ void mr_init_slot(const Bank& b, int g, const float4& d) {         // __init__ :37-58
+    RI(b, MR_PHLEN, g) = 0; RI(b, MR_PHHEAD, g) = 0; RI(b, MR_MSLEN, g) = 0; RI(b, MR_MSHEAD, g) = 0;
+    RI(b, MR_RESETS, g) = 0; RI(b, MR_LASTRESET, g) = -999; RF(b, MR_MCONS, g) = 0.f;
+    mr_push_pos(b, g, (d.x + d.z) / 2.f, (d.y + d.w) / 2.f);
+    RF(b, MR_BB, g) = d.x; RF(b, MR_BB + 1, g) = d.y; RF(b, MR_BB + 2, g) = d.z; RF(b, MR_BB + 3, g) = d.w;
+    RI(b, MR_BBLEN, g) = 1;
+}
+// the k-th most recent stored position (k = 1: last)
+__device__ __forceinline__ float2 mr_pos_back(const Bank& b, int g, int k) {
+    int r = RI(b, MR_PHHEAD, g) - k; if (r < 0) r += kPosRing;
+    return make_float2(RF(b, MR_PH + 2 * r, g), RF(b, MR_PH + 2 * r + 1, g));
+}
+// should_reset (:161-244) with its side effects (a motion score is stored by the jump detector, motion_consistency is refreshed
+// when a detector fires); returns the reset confidence (> 1: reset)
+__device__ float mr_should_reset(const Bank& b, int g, const float4& d) {
+    const int since = II(b, AGE, g) - RI(b, MR_LASTRESET, g);
+    if (since < kResetCooldown) return 0.f;
+    const float cx = (d.x + d.z) / 2.f, cy = (d.y + d.w) / 2.f;
+    const int n = RI(b, MR_PHLEN, g);
+    float fsum = 0.f; int nf = 0;
+    if (n >= 2) {                                               // _detect_position_jump :78-94
+        const int m = min(n, 3);
+        float ax = 0.f, ay = 0.f;
+        for (int k = m; k >= 1; --k) { const float2 q = mr_pos_back(b, g, k); ax += q.x; ay += q.y; }
+        ax /= (float)m; ay /= (float)m;
+        const float dist = sqrtf((cx - ax) * (cx - ax) + (cy - ay) * (cy - ay));
+        int head = RI(b, MR_MSHEAD, g);
+        RF(b, MR_MS + head, g) = fminf(dist / kJumpThr, 3.f);
+        RI(b, MR_MSHEAD, g) = head + 1 == kScoreRing ? 0 : head + 1;
+        RI(b, MR_MSLEN, g) = min(RI(b, MR_MSLEN, g) + 1, kScoreRing);
+        if (dist > kJumpThr) { fsum += fminf(dist / kJumpThr, 2.f); ++nf; }
+    }
+    if (n >= 3) {                                               // _detect_velocity_change :96-121
+        const float2 p0 = mr_pos_back(b, g, 3), p1 = mr_pos_back(b, g, 2), p2 = mr_pos_back(b, g, 1);
+        const float v1 = sqrtf((p1.x - p0.x) * (p1.x - p0.x) + (p1.y - p0.y) * (p1.y - p0.y));
+        const float v2 = sqrtf((p2.x - p1.x) * (p2.x - p1.x) + (p2.y - p1.y) * (p2.y - p1.y));
+        const float v3 = sqrtf((cx - p2.x) * (cx - p2.x) + (cy - p2.y) * (cy - p2.y));
+        const float change = fabsf(v3 - (v1 + v2) / 2.f);
+        if (change > kVelThr) { fsum += fminf(change / kVelThr, 2.f); ++nf; }
+    }
+    if (RI(b, MR_BBLEN, g) >= 2) {                              // _detect_size_change :123-142
+        const float pw = fmaxf(RF(b, MR_BB + 2, g) - RF(b, MR_BB, g), 1.f), ph = fmaxf(RF(b, MR_BB + 3, g) - RF(b, MR_BB + 1, g), 1.f);
+        const float m = fmaxf(fabsf((d.z - d.x) / pw - 1.f), fabsf((d.w - d.y) / ph - 1.f));
+        if (m > kSizeThr) { fsum += m / kSizeThr; ++nf; }
+    }
+    if (!nf) return 0.f;
+    float conf = fsum / (float)nf;
+    float mc = 0.f;                                             // _calculate_motion_consistency :144-159
+    const int ns = RI(b, MR_MSLEN, g);
+    if (ns >= 3) {
+        float sm = 0.f;
+        for (int k = 0; k < ns; ++k) sm += RF(b, MR_MS + k, g);       // mean / variance do not depend on the ring order
+        const float mean = sm / (float)ns;
+        float var = 0.f;
+        for (int k = 0; k < ns; ++k) { const float e = RF(b, MR_MS + k, g) - mean; var += e * e; }
+        var /= (float)ns;
+        mc = mean > 0.f ? fmaxf(0.f, 1.f - var / (mean + 0.1f)) : 1.f;
+    }
+    RF(b, MR_MCONS, g) = mc;
+    if (mc < 0.3f) conf *= 1.5f;
+    if (RI(b, MR_RESETS, g) > 0 && since < 50) conf *= 0.8f;
+    return conf;
+}
+// _perform_reset (:246-279): the state is overwritten by the detection, velocities zeroed, P rescaled (velocity block x100,
+// position block x5, cross terms untouched), histories cleared; is_lost / lost_frames are NOT cleared
+__device__ void mr_reset_slot(const Bank& b, int g, const float4& d) {
+    RI(b, MR_RESETS, g) += 1; RI(b, MR_LASTRESET, g) = II(b, AGE, g);
+    const float cx = (d.x + d.z) / 2.f, cy = (d.y + d.w) / 2.f;
+    FF(b, X0, g) = cx; FF(b, X1, g) = cy; FF(b, X2, g) = d.z - d.x; FF(b, X3, g) = d.w - d.y;
+    FF(b, X4, g) = 0.f; FF(b, X5, g) = 0.f; FF(b, X6, g) = 0.f; FF(b, X7, g) = 0.f;
+    FF(b, PPX, g) *= 5.f; FF(b, PVV, g) *= 100.f; FF(b, PSX, g) *= 5.f; FF(b, PSVV, g) *= 100.f;
+    II(b, TLEN, g) = 0; II(b, THEAD, g) = 0; push_traj(b, g, cx, cy);
+    II(b, NVEL, g) = 0; II(b, VHEAD, g) = 0;
+    RI(b, MR_PHLEN, g) = 0; RI(b, MR_PHHEAD, g) = 0; mr_push_pos(b, g, cx, cy);
+    RI(b, MR_MSLEN, g) = 0; RI(b, MR_MSHEAD, g) = 0;
+    II(b, HITS, g) += 1; II(b, STREAK, g) += 1; II(b, TSU, g) = 0;
+}
+
 // get_track_info (:335-383) incl. get_lost_prediction / enhanced_long_term_predict side effects; the row goes to global
 // memory as five 16-byte stores
 __device__ void emit_slot(const Bank& b, int g, float* out_row, float* traj_out, int32_t* traj_len_out, int slot, int* long_term) {
@@ -527,6 +651,10 @@ __device__ void emit_slot(const Bank& b, int g, float* out_row, float* traj_out,
             if (k <= 1) {                                   // enhanced_long_term_predict(1) -> self.predict(), 1.0 (:216-217)
                 predict_slot(b, g);
                 bx = FF(b, X0, g); by = FF(b, X1, g); bw = FF(b, X2, g); bh = FF(b, X3, g); conf = 1.f;
+                if (b.mode) {                               // the overridden predict() returns the blended box
+                    const float4 bb = blended_box(b, g, II(b, AGE, g), bx, by, bw, bh);
+                    bx = (bb.x + bb.z) / 2.f; by = (bb.y + bb.w) / 2.f;
+                }
             } else if (FF(b, PCONF, g) > 0.3f) {            // high confidence: mean-velocity extrapolation (:224-236)
                 bx = FF(b, X0, g) + FF(b, VAVGX, g) * (float)k; by = FF(b, X1, g) + FF(b, VAVGY, g) * (float)k;
                 bw = FF(b, X2, g); bh = FF(b, X3, g);
@@ -567,6 +695,7 @@ __device__ void emit_slot(const Bank& b, int g, float* out_row, float* traj_out,
 // ------------------------------------------------------------------------------------------------------------------
 // (2) resolve: one CTA per stream on the candidate lists
 // ------------------------------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, const Frame fr) {
     __shared__ float4 s_det[kMaxDetsSmem];
     __shared__ int s_dmatch[kMaxDetsSmem];
@@ -625,8 +754,9 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
                     const int d = (int)pr.y, i = (int)pr.z;
                     if (s_dmatch[d] >= 0 || l_match[i] >= 0) continue;
                     const unsigned long long hi = (unsigned long long)pr.x << 32;   // IoU > 0: bits order like the float
-                    atomicMax(&d_best[d], hi | (unsigned)(0xFFFFFFFFu - pr.w));
-                    atomicMax(&t_best[i], hi | (unsigned)(0xFFFFFFFFu - (unsigned)d));
+                    // ties: mode 0 lowest (detection, track id); mode 1 the reference sorts (iou, d, t) tuples descending: highest
+                    atomicMax(&d_best[d], hi | (MODE ? pr.w : (unsigned)(0xFFFFFFFFu - pr.w)));
+                    atomicMax(&t_best[i], hi | (MODE ? (unsigned)d : (unsigned)(0xFFFFFFFFu - (unsigned)d)));
                 }
                 __syncthreads();
                 // an accepted pair is the unique entry whose key is the maximum of both its detection and its track; it is only
@@ -636,7 +766,7 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
                     const int d = (int)pr.y, i = (int)pr.z;
                     if (s_dmatch[d] >= 0 || l_match[i] >= 0) continue;
                     const unsigned long long hi = (unsigned long long)pr.x << 32;
-                    if (d_best[d] == (hi | (unsigned)(0xFFFFFFFFu - pr.w)) && t_best[i] == (hi | (unsigned)(0xFFFFFFFFu - (unsigned)d))) {
+                    if (d_best[d] == (hi | (MODE ? pr.w : (unsigned)(0xFFFFFFFFu - pr.w))) && t_best[i] == (hi | (MODE ? (unsigned)d : (unsigned)(0xFFFFFFFFu - (unsigned)d)))) {
                         s_list[d] = i; s_progress = 1;
                     }
                 }
@@ -656,18 +786,18 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
                 for (int d = warp; d < D; d += nwarps) {              // row pass: best free track per free detection
                     if (s_dmatch[d] >= 0) continue;
                     const float4 db = s_det[d];
-                    float best = -1.f; int bt = -1, bid = 0x7fffffff;
+                    float best = -1.f; int bt = -1, bid = MODE ? -1 : 0x7fffffff;
                     for (int i = lane; i < T; i += 32) {
                         if (match[i] >= 0) continue;
                         const float v = iou_ref(db, cbox[i]);
                         const int id = cid[i];
-                        if (v >= thr && (v > best || (v == best && id < bid))) { best = v; bt = i; bid = id; }
+                        if ((MODE ? v > thr : v >= thr) && (v > best || (v == best && (MODE ? id > bid : id < bid)))) { best = v; bt = i; bid = id; }
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
                         const int ot = __shfl_xor_sync(0xffffffffu, bt, o), oid = __shfl_xor_sync(0xffffffffu, bid, o);
-                        if (ob > best || (ob == best && oid < bid)) { best = ob; bt = ot; bid = oid; }
+                        if (ob > best || (ob == best && (MODE ? oid > bid : oid < bid))) { best = ob; bt = ot; bid = oid; }
                     }
                     if (lane == 0) { s_bt[d] = bt; s_bv[d] = best; }
                 }
@@ -682,7 +812,7 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
                         for (int e = 0; e < D && !dominated; ++e) {
                             if (e == d || s_dmatch[e] >= 0) continue;
                             const float ve = iou_ref(s_det[e], tb);
-                            if (ve >= thr && (ve > v || (ve == v && e < d))) dominated = true;
+                            if ((MODE ? ve > thr : ve >= thr) && (ve > v || (ve == v && (MODE ? e > d : e < d)))) dominated = true;
                         }
                         if (!dominated) acc = i;
                     }
@@ -706,15 +836,30 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
         const int md = match[i];
         if (md >= 0) {
             if (II(b, ISLOST, g)) atomicAdd(&s_cnt[2], 1);                              // successful recovery (:73-79)
-            update_slot(b, g, s_det[md]);
-            s_list[atomicAdd(&s_an, 1)] = t;
+            const float4 dd = s_det[md];
+            if (MODE && mr_should_reset(b, g, dd) > 1.f) {                              // MotionResetKalmanTracker.update :281-298
+                mr_reset_slot(b, g, dd);
+                atomicAdd(&s_cnt[3], 1);                                                // individual_resets
+            } else {
+                update_slot(b, g, dd);
+                s_list[atomicAdd(&s_an, 1)] = t;
+                if (MODE) mr_push_pos(b, g, FF(b, X0, g), FF(b, X1, g));                // the base class's append of the filtered centre
+            }
+            if (MODE) {
+                mr_push_pos(b, g, (dd.x + dd.z) / 2.f, (dd.y + dd.w) / 2.f);
+                RF(b, MR_BB, g) = dd.x; RF(b, MR_BB + 1, g) = dd.y; RF(b, MR_BB + 2, g) = dd.z; RF(b, MR_BB + 3, g) = dd.w;
+                RI(b, MR_BBLEN, g) = min(RI(b, MR_BBLEN, g) + 1, 5);
+            }
         } else {
             if (!II(b, ISLOST, g)) { II(b, ISLOST, g) = 1; II(b, LOSTF, g) = 0; }
             II(b, LOSTF, g) += 1; II(b, STREAK, g) = 0;
         }
         const int tsu = II(b, TSU, g), age = II(b, AGE, g), hs = II(b, STREAK, g);
         const bool del = tsu > b.max_lost || (age < 5 && hs == 0 && tsu > 15) || (age < 10 && hs <= 1 && tsu > 30);
-        if (del) { II(b, ID, g) = 0; atomicAdd(&s_cnt[0], 1); atomicAdd(b.chunk_free + (size_t)s * b.nchunks + t / kChunk, 1); }
+        if (del) {
+            II(b, ID, g) = 0; atomicAdd(&s_cnt[0], 1); atomicAdd(b.chunk_free + (size_t)s * b.nchunks + t / kChunk, 1);
+            if (MODE && RI(b, MR_RESETS, g) > 0) atomicAdd(b.fcnt + s * 4 + 2, 1);     // tracking_recoveries
+        }
     }
     __syncthreads();
     for (int i = warp; i < s_an; i += nwarps) analyze_slot_warp(b, g0 + s_list[i], lane);
@@ -730,8 +875,8 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
         int emit = 0, t = 0, g = 0;
         if (i < T) {
             t = cslot[i]; g = g0 + t;
-            if (II(b, ID, g) != 0)
-                emit = (II(b, STREAK, g) >= b.min_hits || frame <= b.min_hits || II(b, ISLOST, g)) ? 1 : 0;   // multi_target_tracker.py:117-126
+            if (II(b, ID, g) != 0)     // mode 1 reports every live track (motion_compensated_multi_tracker.py:231-238)
+                emit = (MODE || II(b, STREAK, g) >= b.min_hits || frame <= b.min_hits || II(b, ISLOST, g)) ? 1 : 0;   // multi_target_tracker.py:117-126
         }
         int total;
         const int off = block_exclusive_scan(emit, s_warp, &total);
@@ -741,6 +886,9 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
             const bool fits = pos < fr.out_cap;
             emit_slot(b, g, fits ? rows + (size_t)pos * B2_TRACK_COLS : nullptr, fits && fr.out_traj ? fr.out_traj + (o0 + pos) * kTraj * 2 : nullptr,
                       fits && fr.out_traj_len ? fr.out_traj_len + o0 + pos : nullptr, t, &long_term);
+            if (MODE && fits && fr.out_extra)
+                reinterpret_cast<float4*>(fr.out_extra)[o0 + pos] =
+                    make_float4(__int_as_float(RI(b, MR_RESETS, g)), __int_as_float(II(b, AGE, g) - RI(b, MR_LASTRESET, g)), RF(b, MR_MCONS, g), 0.f);
         }
         __syncthreads();
         if (tid == 0) s_emit_base = ebase + total;
@@ -762,7 +910,7 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
     __syncthreads();
     int created = 0;
     if (n_new > 0) {
-        const bool emit_new = (1 >= b.min_hits) || (frame <= b.min_hits);     // hit_streak = 1
+        const bool emit_new = MODE || (1 >= b.min_hits) || (frame <= b.min_hits);     // hit_streak = 1
         int32_t* cfree = b.chunk_free + (size_t)s * b.nchunks;
         for (int base = 0; base < b.C && created < n_new; base += kResolveThreads) {
             // chunks without a free slot (the common case in a full bank) are skipped without touching the slots
@@ -779,12 +927,15 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
             const int take = min(total, n_new - created);
             if (is_free && rank < n_new) {
                 init_slot(b, g, s_det[s_list[rank]], id0 + rank);
+                if (MODE) mr_init_slot(b, g, s_det[s_list[rank]]);
                 atomicSub(b.chunk_free + (size_t)s * b.nchunks + t / kChunk, 1);     // the sweep skips chunks it believes empty
                 if (emit_new) {
                     const int pos = ebase + off;
                     const bool fits = pos < fr.out_cap;
                     emit_slot(b, g, fits ? rows + (size_t)pos * B2_TRACK_COLS : nullptr, fits && fr.out_traj ? fr.out_traj + (o0 + pos) * kTraj * 2 : nullptr,
                               fits && fr.out_traj_len ? fr.out_traj_len + o0 + pos : nullptr, t, &long_term);
+                    if (MODE && fits && fr.out_extra)
+                        reinterpret_cast<float4*>(fr.out_extra)[o0 + pos] = make_float4(__int_as_float(0), __int_as_float(999), 0.f, 0.f);
                 }
             }
             created += take;
@@ -801,8 +952,9 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
         int32_t* fc = b.fcnt + s * 4;
         long long* st = b.stats + (size_t)s * 8;
         const int terminated = fc[0] + s_cnt[0], lt = fc[1] + s_cnt[1];
-        fc[0] = 0; fc[1] = 0;
         st[0] += created; st[1] += terminated; st[2] += created - terminated; st[3] += lt; st[4] += s_cnt[2]; st[5] += n_new - created;
+        st[6] += s_cnt[3]; st[7] += fc[2];
+        fc[0] = 0; fc[1] = 0; fc[2] = 0;
         // the reference numbers every unmatched detection; ids keep advancing even if the bank overflowed
         b.next_id[s] = id0 + n_new;
         b.frame_count[s] = frame;
@@ -851,6 +1003,22 @@ __global__ void export_motion_kernel(const Bank b, int s, float* out, int32_t* n
     if (threadIdx.x == 0) *n_out = cnt;
 }
 
+__global__ void export_reset_kernel(const Bank b, int s, float* out, int32_t* n_out) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < b.C; t += blockDim.x) {
+        const int g = s * b.C + t;
+        if (II(b, ID, g) == 0) continue;
+        float* o = out + (size_t)atomicAdd(&cnt, 1) * 8;
+        o[0] = __int_as_float(II(b, ID, g)); o[1] = __int_as_float(RI(b, MR_RESETS, g)); o[2] = __int_as_float(RI(b, MR_LASTRESET, g));
+        o[3] = RF(b, MR_MCONS, g); o[4] = __int_as_float(RI(b, MR_PHLEN, g)); o[5] = __int_as_float(RI(b, MR_MSLEN, g));
+        o[6] = __int_as_float(RI(b, MR_BBLEN, g)); o[7] = 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *n_out = cnt;
+}
+
 // bank regrid for b2_tracker_grow: rows of a field-major [rows][S*C] array move to [rows][S*C2]
 __global__ void regrid_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int rows, int S, int C, int C2) {
     const size_t n = (size_t)rows * S * C;
@@ -862,9 +1030,9 @@ __global__ void regrid_kernel(const uint32_t* __restrict__ src, uint32_t* __rest
 }
 __global__ void fill_i32(int32_t* p, int n, int v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
-struct Layout { size_t f, i, v, t, agg, cf, fc, tk, cs, cb, ci, cm, pr, ni, fcn, st, total; };
+struct Layout { size_t f, i, v, t, rf, ri, agg, cf, fc, tk, cs, cb, ci, cm, pr, ni, fcn, st, total; };
 
-Layout bank_layout(int S, int C, int max_dets, int nchunks, int pair_cap) {
+Layout bank_layout(int S, int C, int max_dets, int nchunks, int pair_cap, int mode) {
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t N = (size_t)S * C;
     Layout L;
@@ -873,6 +1041,8 @@ Layout bank_layout(int S, int C, int max_dets, int nchunks, int pair_cap) {
     L.i = off; off += up(N * NIF * 4);
     L.v = off; off += up(N * kVelRing * 2 * 4);
     L.t = off; off += up(N * kTraj * 2 * 4);
+    L.rf = off; off += mode ? up(N * MR_NF * 4) : 0;
+    L.ri = off; off += mode ? up(N * MR_NI * 4) : 0;
     L.agg = off; off += up((size_t)S * nchunks * 8);
     L.cf = off; off += up((size_t)S * nchunks * 4);
     L.fc = off; off += up((size_t)S * 4 * 4);
@@ -892,6 +1062,7 @@ Layout bank_layout(int S, int C, int max_dets, int nchunks, int pair_cap) {
 
 void bank_bind(Bank& b, char* a, const Layout& L) {
     b.f = (float*)(a + L.f); b.i = (int32_t*)(a + L.i); b.vel = (float*)(a + L.v); b.traj = (float*)(a + L.t);
+    b.mrf = (float*)(a + L.rf); b.mri = (int32_t*)(a + L.ri);
     b.agg = (unsigned long long*)(a + L.agg); b.chunk_free = (int32_t*)(a + L.cf); b.fcnt = (int32_t*)(a + L.fc);
     b.ticket = (unsigned int*)(a + L.tk); b.ctrk_slot = (int32_t*)(a + L.cs); b.cbox = (float4*)(a + L.cb);
     b.cid = (int32_t*)(a + L.ci); b.cmatch = (int32_t*)(a + L.cm); b.pairs = (uint4*)(a + L.pr);
@@ -904,7 +1075,13 @@ struct b2_tracker { b2_tracker_impl impl; };
 
 extern "C" int b2_tracker_create(int n_streams, int capacity, int max_dets, int max_lost_frames, int min_hits,
                                  float iou_threshold, b2_tracker_t** out) {
+    return b2_tracker_create_ex(n_streams, capacity, max_dets, max_lost_frames, min_hits, iou_threshold, 0, out);
+}
+
+extern "C" int b2_tracker_create_ex(int n_streams, int capacity, int max_dets, int max_lost_frames, int min_hits,
+                                    float iou_threshold, int mode, b2_tracker_t** out) {
     B2_REQUIRE(out, "tracker_create: out is null");
+    B2_REQUIRE(mode == 0 || mode == 1, "tracker_create: mode must be 0 (EnhancedMultiTargetTracker) or 1 (MotionCompensatedMultiTracker)");
     B2_REQUIRE(n_streams >= 1 && capacity >= 1 && capacity <= 65535 && max_dets >= 1 && max_dets <= kMaxDetsSmem,
                "tracker_create: need n_streams>=1, 1<=capacity<=65535, 1<=max_dets<=%d", kMaxDetsSmem);
     B2_REQUIRE((long long)n_streams * capacity < (1ll << 31), "tracker_create: n_streams*capacity must be below 2^31");
@@ -914,8 +1091,8 @@ extern "C" int b2_tracker_create(int n_streams, int capacity, int max_dets, int 
     b.S = n_streams; b.C = capacity; b.N = n_streams * capacity; b.max_dets = max_dets;
     b.nchunks = b2_ceil_div(capacity, kChunk);
     b.pair_cap = 16 * max_dets < 1024 ? 1024 : 16 * max_dets;
-    b.max_lost = max_lost_frames; b.min_hits = min_hits; b.iou_thr = iou_threshold;
-    const Layout L = bank_layout(b.S, b.C, max_dets, b.nchunks, b.pair_cap);
+    b.max_lost = max_lost_frames; b.min_hits = min_hits; b.iou_thr = iou_threshold; b.mode = mode;
+    const Layout L = bank_layout(b.S, b.C, max_dets, b.nchunks, b.pair_cap, mode);
     cudaError_t e = cudaMalloc(&t->impl.arena, L.total);
     if (e != cudaSuccess) { b2_set_error("tracker_create: cudaMalloc(%zu) failed: %s", L.total, cudaGetErrorString(e)); delete t; return B2_ERR_CUDA; }
     t->impl.arena_bytes = L.total;
@@ -951,7 +1128,7 @@ extern "C" int b2_tracker_grow(b2_tracker_t* t, int new_capacity, void* stream) 
     cudaStream_t st = (cudaStream_t)stream;
     Bank nb = b;
     nb.C = new_capacity; nb.N = b.S * new_capacity; nb.nchunks = b2_ceil_div(new_capacity, kChunk);
-    const Layout L = bank_layout(nb.S, nb.C, nb.max_dets, nb.nchunks, nb.pair_cap);
+    const Layout L = bank_layout(nb.S, nb.C, nb.max_dets, nb.nchunks, nb.pair_cap, nb.mode);
     void* arena = nullptr;
     cudaError_t e = cudaMalloc(&arena, L.total);
     if (e != cudaSuccess) { b2_set_error("tracker_grow: cudaMalloc(%zu) failed: %s", L.total, cudaGetErrorString(e)); return B2_ERR_CUDA; }
@@ -962,6 +1139,10 @@ extern "C" int b2_tracker_grow(b2_tracker_t* t, int new_capacity, void* stream) 
     regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.i, (uint32_t*)nb.i, NIF, b.S, b.C, nb.C);
     regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.vel, (uint32_t*)nb.vel, kVelRing * 2, b.S, b.C, nb.C);
     regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.traj, (uint32_t*)nb.traj, kTraj * 2, b.S, b.C, nb.C);
+    if (b.mode) {
+        regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.mrf, (uint32_t*)nb.mrf, MR_NF, b.S, b.C, nb.C);
+        regrid_kernel<<<grid, 256, 0, st>>>((const uint32_t*)b.mri, (uint32_t*)nb.mri, MR_NI, b.S, b.C, nb.C);
+    }
     B2_CUDA(cudaMemcpyAsync(nb.next_id, b.next_id, (size_t)b.S * 4, cudaMemcpyDeviceToDevice, st));
     B2_CUDA(cudaMemcpyAsync(nb.frame_count, b.frame_count, (size_t)b.S * 4, cudaMemcpyDeviceToDevice, st));
     B2_CUDA(cudaMemcpyAsync(nb.stats, b.stats, (size_t)b.S * 64, cudaMemcpyDeviceToDevice, st));
@@ -987,15 +1168,27 @@ extern "C" int b2_tracker_bank_predict(b2_tracker_t* t, void* stream) {
 
 extern "C" int b2_tracker_update(b2_tracker_t* t, const float* dets, int det_cols, const int32_t* det_counts,
                                  float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, int out_cap, void* stream) {
+    return b2_tracker_update_ex(t, dets, det_cols, det_counts, out_rows, out_counts, out_traj, out_traj_len, nullptr, out_cap, stream);
+}
+
+extern "C" int b2_tracker_update_ex(b2_tracker_t* t, const float* dets, int det_cols, const int32_t* det_counts,
+                                    float* out_rows, int32_t* out_counts, float* out_traj, int32_t* out_traj_len, float* out_extra,
+                                    int out_cap, void* stream) {
     B2_REQUIRE(t && dets && det_counts && out_rows && out_counts, "tracker_update: null pointer");
+    B2_REQUIRE(!out_extra || ((uintptr_t)out_extra % 16 == 0 && t->impl.b.mode == 1), "tracker_update: out_extra needs a mode-1 bank and 16-byte alignment");
     B2_REQUIRE(out_cap >= 1, "tracker_update: out_cap must be >= 1");
     B2_REQUIRE(det_cols >= 4, "tracker_update: det_cols must be >= 4");
     B2_REQUIRE((out_traj == nullptr) == (out_traj_len == nullptr), "tracker_update: out_traj and out_traj_len go together");
     const Bank& b = t->impl.b;
     cudaStream_t st = (cudaStream_t)stream;
-    const Frame fr{dets, det_cols, det_counts, out_rows, out_counts, out_traj, out_traj_len, out_cap};
-    sweep_kernel<<<b.S * b.nchunks, kChunk, (size_t)b.max_dets * sizeof(float4), st>>>(b, fr);
-    resolve_kernel<<<b.S, kResolveThreads, 0, st>>>(b, fr);
+    const Frame fr{dets, det_cols, det_counts, out_rows, out_counts, out_traj, out_traj_len, out_cap, out_extra};
+    if (b.mode) {
+        sweep_kernel<1><<<b.S * b.nchunks, kChunk, (size_t)b.max_dets * sizeof(float4), st>>>(b, fr);
+        resolve_kernel<1><<<b.S, kResolveThreads, 0, st>>>(b, fr);
+    } else {
+        sweep_kernel<0><<<b.S * b.nchunks, kChunk, (size_t)b.max_dets * sizeof(float4), st>>>(b, fr);
+        resolve_kernel<0><<<b.S, kResolveThreads, 0, st>>>(b, fr);
+    }
     B2_CUDA(cudaGetLastError());
     b2_count_launch(2);
     return B2_OK;
@@ -1029,6 +1222,7 @@ extern "C" int b2_tracker_export(b2_tracker_t* t, int stream_idx, float* x_host,
         B2_CUDA(cudaMemcpy(&nid, b.next_id + stream_idx, 4, cudaMemcpyDeviceToHost));
         for (int k = 0; k < 5; ++k) stats_host[k] = st[k];
         stats_host[5] = fc; stats_host[6] = nid; stats_host[7] = st[5];
+        if (b.mode) { stats_host[3] = st[6]; stats_host[4] = st[7]; }       // mode 1: individual_resets, tracking_recoveries
     }
     return B2_OK;
 }
@@ -1044,6 +1238,23 @@ extern "C" int b2_tracker_export_motion(b2_tracker_t* t, int stream_idx, float* 
     int n = 0;
     cudaError_t e = cudaMemcpy(&n, dn, 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(motion_host, dm, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dm); cudaFree(dn);
+    B2_CUDA(e);
+    *n_tracks_host = n;
+    return B2_OK;
+}
+
+extern "C" int b2_tracker_export_reset(b2_tracker_t* t, int stream_idx, float* reset_host, int32_t* n_tracks_host) {
+    B2_REQUIRE(t && stream_idx >= 0 && stream_idx < t->impl.b.S && reset_host && n_tracks_host && t->impl.b.mode == 1, "tracker_export_reset: bad argument (mode-1 bank required)");
+    const Bank& b = t->impl.b;
+    B2_CUDA(cudaDeviceSynchronize());
+    float* dm = nullptr; int32_t* dn = nullptr;
+    B2_CUDA(cudaMalloc(&dm, (size_t)b.C * 8 * 4)); B2_CUDA(cudaMalloc(&dn, 4));
+    export_reset_kernel<<<1, 256>>>(b, stream_idx, dm, dn);
+    b2_count_launch(1);
+    int n = 0;
+    cudaError_t e = cudaMemcpy(&n, dn, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(reset_host, dm, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost);
     cudaFree(dm); cudaFree(dn);
     B2_CUDA(e);
     *n_tracks_host = n;

@@ -33,16 +33,18 @@ class TrackerBank:
     ``max_out`` (default: capacity) is the number of rows per stream the output block holds."""
 
     def __init__(self, n_streams, capacity=256, max_dets=300, max_lost_frames=450, min_hits=3, iou_threshold=0.3, device=None,
-                 max_out=None):
+                 max_out=None, mode=0):
+        """mode 1: the rules of camera_motion_compensation's MotionCompensatedMultiTracker / MotionResetKalmanTracker."""
         self.device = device or _lib.require_cuda()
         self.lib = _lib.load()
+        self.mode = int(mode)
         self.S, self.capacity, self.max_dets = int(n_streams), int(capacity), int(max_dets)
         self.max_lost_frames, self.min_hits, self.iou_threshold = int(max_lost_frames), int(min_hits), float(iou_threshold)
         self._follow_capacity = max_out is None
         self.max_out = self.capacity if max_out is None else int(max_out)
         self._h = C.c_void_p()
-        _lib.check(self.lib.b2_tracker_create(self.S, self.capacity, self.max_dets, self.max_lost_frames, self.min_hits,
-                                              self.iou_threshold, C.byref(self._h)))
+        _lib.check(self.lib.b2_tracker_create_ex(self.S, self.capacity, self.max_dets, self.max_lost_frames, self.min_hits,
+                                                 self.iou_threshold, self.mode, C.byref(self._h)))
         self._alloc_outputs()
 
     def _alloc_outputs(self):
@@ -51,6 +53,7 @@ class TrackerBank:
         self.rows = torch.zeros((self.S, self.max_out, TRACK_COLS), dtype=torch.float32, device=self.device)
         self.counts = torch.zeros((self.S,), dtype=torch.int32, device=self.device)
         self.traj = self.traj_len = None
+        self.extra = torch.zeros((self.S, self.max_out, 4), dtype=torch.float32, device=self.device) if self.mode else None
         self.stats_dev = torch.zeros((self.S, 8), dtype=torch.int64, device=self.device)
 
     def close(self):
@@ -80,10 +83,10 @@ class TrackerBank:
         if with_trajectory and self.traj is None:
             self.traj = torch.zeros((self.S, self.max_out, TRAJ_LEN, 2), dtype=torch.float32, device=self.device)
             self.traj_len = torch.zeros((self.S, self.max_out), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.b2_tracker_update(self._h, _lib.ptr(dets), dets.shape[2], _lib.ptr(det_counts), _lib.ptr(self.rows),
-                                              _lib.ptr(self.counts), _lib.ptr(self.traj) if with_trajectory else None,
-                                              _lib.ptr(self.traj_len) if with_trajectory else None, self.max_out,
-                                              _lib.stream_ptr(stream)))
+        _lib.check(self.lib.b2_tracker_update_ex(self._h, _lib.ptr(dets), dets.shape[2], _lib.ptr(det_counts), _lib.ptr(self.rows),
+                                                 _lib.ptr(self.counts), _lib.ptr(self.traj) if with_trajectory else None,
+                                                 _lib.ptr(self.traj_len) if with_trajectory else None, _lib.ptr(self.extra), self.max_out,
+                                                 _lib.stream_ptr(stream)))
         return self.rows, self.counts
 
     def stats_async(self, stream=None):
@@ -116,6 +119,18 @@ class TrackerBank:
         _lib.check(self.lib.b2_tracker_export_motion(self._h, stream_idx, m.ctypes.data_as(C.c_void_p), C.byref(n)))
         m = m[:n.value]
         return m[np.argsort(m[:, 0].copy().view(np.int32), kind="stable"), 6]
+
+    def export_reset(self, stream_idx=0):
+        """mode 1: (n, 7) {id, reset_count, last_reset_frame, motion_consistency, len(position_history), len(motion_scores),
+        len(bbox_history)} of one stream's live tracks, ascending track id (synchronises)."""
+        m = np.zeros((self.capacity, 8), np.float32)
+        n = C.c_int32()
+        _lib.check(self.lib.b2_tracker_export_reset(self._h, stream_idx, m.ctypes.data_as(C.c_void_p), C.byref(n)))
+        m = m[:n.value]
+        iv = m.view(np.int32)
+        order = np.argsort(iv[:, 0], kind="stable")
+        out = np.stack([iv[:, 0], iv[:, 1], iv[:, 2], m[:, 3], iv[:, 4], iv[:, 5], iv[:, 6]], 1).astype(np.float64)
+        return out[order]
 
     @staticmethod
     def bytes_per_track():
@@ -226,6 +241,67 @@ class EnhancedMultiTargetTracker:
         d["frame_count"] = self.frame_count
         d["tracker_details"] = [{"track_id": f"T{int(m[0]):03d}", "age": int(m[1]), "hits": int(m[2]), "lost_frames": int(m[5]),
                                  "is_lost": bool(m[6]), "confidence": float(c)} for m, c in zip(meta, conf)]
+        return d
+
+
+class MotionCompensatedMultiTracker(EnhancedMultiTargetTracker):
+    """Drop-in for camera_motion_compensation/motion_compensated_multi_tracker.py:18 on the CUDA track bank (mode 1):
+    MotionResetKalmanTracker tracks (per-track jump / velocity / size reset detectors, cooldown, covariance rescale, blended
+    association box), the subclass's own association (IoU > threshold, ties to the larger indices) and reporting of every
+    live track.  ``update(detections, frame=None)``: the global camera-motion detector (optical flow on ``frame``,
+    global_motion_detector.py) is not part of this path -- passing a frame raises."""
+
+    def __init__(self, max_lost_frames=150, min_hits=1, iou_threshold=0.1, capacity=512, max_dets=300):
+        import torch
+
+        self.max_lost_frames, self.min_hits, self.iou_threshold = max_lost_frames, min_hits, iou_threshold
+        self.bank = TrackerBank(1, capacity, max_dets, max_lost_frames, min_hits, iou_threshold, mode=1)
+        self.frame_count = 0
+        self.next_track_id = 1
+        self.stats = {"total_frames": 0, "individual_resets": 0, "tracking_recoveries": 0, "global_resets": 0}
+        self._active = 0
+        self._dets = torch.zeros((1, max_dets, 4), dtype=torch.float32, device=self.bank.device)
+        self._host = torch.zeros((max_dets, 4), dtype=torch.float32).pin_memory()
+        self._cnt = torch.zeros((1,), dtype=torch.int32, device=self.bank.device)
+
+    def update(self, detections, frame=None):
+        import torch
+
+        if frame is not None:
+            raise NotImplementedError("global camera-motion detection (GlobalMotionDetector, optical flow) is not implemented; call update(detections)")
+        n = len(detections)
+        if n > self.bank.max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self.bank.max_dets}")
+        if self._active + n > self.bank.capacity:
+            self.bank.grow(min(65535, max(2 * self.bank.capacity, self._active + n)))
+        if n:
+            self._host[:n] = torch.as_tensor(np.asarray([list(d)[:4] for d in detections], dtype=np.float32))
+            self._dets[0, :n].copy_(self._host[:n], non_blocking=True)
+        self._cnt.fill_(n)
+        rows, counts = self.bank.update(self._dets, self._cnt)
+        k = int(counts[0].item())
+        r = rows[0, :k].cpu().numpy()
+        ex = self.bank.extra[0, :k].cpu().numpy()
+        tr, tl = self.bank.traj[0, :k].cpu().numpy(), self.bank.traj_len[0, :k].cpu().numpy()
+        st = (C.c_longlong * 8)()
+        _lib.check(self.bank.lib.b2_tracker_export(self.bank._h, 0, None, None, None, None, st))
+        self._active = int(st[2])
+        self.frame_count, self.next_track_id = int(st[5]), int(st[6])
+        self.stats.update(total_frames=self.frame_count, individual_resets=int(st[3]), tracking_recoveries=int(st[4]))
+        if st[7]:
+            raise RuntimeError(f"track bank overflow: {int(st[7])} detections found no free slot")
+        out = rows_to_dicts(r, tr, tl)
+        order = np.argsort(r.view(np.int32)[:, 0], kind="stable")
+        for d, j in zip(out, order):
+            d["reset_count"] = int(ex[j].view(np.int32)[0])
+            d["frames_since_reset"] = int(ex[j].view(np.int32)[1])
+            d["motion_consistency"] = float(ex[j][2])
+        return out
+
+    def get_statistics(self):
+        d = dict(self.stats)
+        d["frame_count"] = self.frame_count
+        d["active_trackers"] = self._active
         return d
 
 
