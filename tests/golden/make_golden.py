@@ -248,7 +248,12 @@ def gold_predict(names=("yolov8n-p2", "yolov8s-p2")):
                 sc, cl = yb[:, 4:].max(1)
                 keep = sc > 0.15
                 box = uops.xywh2xyxy(yb[keep, :4])
-                box = uops.scale_boxes(im.shape[2:], box.clone(), (h, w))
+                # NMS runs on the letterboxed, UNCLIPPED boxes (clip_boxes comes after it, ops.py:105-138): the candidates are
+                # stored in original-frame coordinates without the clip; these frames need no resize (gain 1)
+                gain = min(im.shape[2] / h, im.shape[3] / w)
+                assert gain == 1.0
+                pad_x, pad_y = round((im.shape[3] - w) / 2 - 0.1), round((im.shape[2] - h) / 2 - 0.1)
+                box = box - torch.tensor([pad_x, pad_y, pad_x, pad_y], dtype=box.dtype)
                 out[f"{tag}_cand_{b}"] = torch.cat([box, sc[keep, None], cl[keep, None].float()], 1).numpy()
         np.savez_compressed(os.path.join(HERE, f"predict_{name[6:].replace('-', '_')}.npz"), **out)
 

@@ -77,9 +77,10 @@ def _greedy_keep(boxes, scores, cls, alive, iou_thres):
     return keep
 
 
-def detection_set_report(dets, ref, cand, conf, iou_thres, seed=0):
+def detection_set_report(dets, ref, cand, conf, iou_thres, seed=0, frame_hw=None):
     """Compare engine detections ``dets`` (k,6) with the fp32 reference's ``ref`` (n,6), given the candidate list ``cand`` (m,6)
-    the reference's NMS saw (every row of ``ref`` is a row of ``cand``).
+    the reference's NMS saw (every row of ``ref`` is a row of ``cand``; ``cand`` boxes are NOT clipped to the frame -- NMS
+    runs before clip_boxes -- while ``dets`` / ``ref`` are: pass ``frame_hw`` so that rows are matched on the clipped boxes).
 
     Exclusion band: the reference's own NMS is re-run BAND_TRIALS times on its candidates with every class logit moved by
     up to +-BAND_LOGIT and every box coordinate by up to +-BAND_BOX px (seeded) -- the size of change bf16 storage of the
@@ -102,12 +103,17 @@ def detection_set_report(dets, ref, cand, conf, iou_thres, seed=0):
         kept_count += _greedy_keep(b2, l2, cand[:, 5], l2 > lconf, iou_thres)
     always, never = kept_count == BAND_TRIALS, kept_count == 0
 
+    cand_m = cand.copy()                                          # what a candidate looks like in the output: clipped to the frame
+    if frame_hw is not None and m:
+        cand_m[:, [0, 2]] = cand_m[:, [0, 2]].clip(0, frame_hw[1])
+        cand_m[:, [1, 3]] = cand_m[:, [1, 3]].clip(0, frame_hw[0])
+
     def cand_index(row):
         """index of the reference candidate this row corresponds to (same class, box within BOX_RTOL; boxes clipped to the same
         frame border can coincide, then the closest score decides), or -1"""
         if not m:
             return -1
-        e = np.abs(cand[:, :4] - row[:4]).max(1) / max(np.abs(row[:4]).max(), 1.0)
+        e = np.abs(cand_m[:, :4] - row[:4]).max(1) / max(np.abs(row[:4]).max(), 1.0)
         e[cand[:, 5] != row[5]] = np.inf
         if not e.min() < BOX_RTOL:
             return -1

@@ -360,7 +360,7 @@ def test_predict_matches_reference_golden(name, gfile, tag, hw):
         assert r.orig_shape == hw and d.shape[1] == 6
         assert np.all(np.diff(d[:, 4]) <= 0)                              # sorted by descending confidence
         assert d[:, [0, 2]].min() >= 0 and d[:, [0, 2]].max() <= hw[1] and d[:, [1, 3]].max() <= hw[0]
-        rep = detection_set_report(d, ref, cand, 0.15, 0.6)
+        rep = detection_set_report(d, ref, cand, 0.15, 0.6, frame_hw=hw)
         _diag(f"predict {name} {tag} frame {b}: reference {rep['n_ref']} detections ({rep['n_ref_strict']} decided, {rep['n_ref_in_band']} in the "
               f"band), engine {rep['n_det']}, violations {len(rep['errors'])}")
         assert not rep["errors"], (b, rep["errors"][:5])
@@ -397,10 +397,10 @@ def test_predict_engine_agrees_with_bf16_oracle(n_p2):
             sc, cl = t[:, 4:].max(1), t[:, 4:].argmax(1)
             k = sc > 0.15
             xy = np.stack([t[k, 0] - t[k, 2] / 2, t[k, 1] - t[k, 3] / 2, t[k, 0] + t[k, 2] / 2, t[k, 1] + t[k, 3] / 2], 1)
-            cand = np.concatenate([pp.scale_boxes(hw, xy, hw), sc[k, None], cl[k, None]], 1)
+            cand = np.concatenate([xy, sc[k, None], cl[k, None]], 1)                 # unclipped: what NMS sees (no padding at 512x640)
             o = ob[b].copy()
             o[:, :4] = pp.scale_boxes(hw, o[:, :4], hw)
-            rep = gc.detection_set_report(res[b].boxes.data.cpu().numpy(), o, cand, 0.15, 0.6)
+            rep = gc.detection_set_report(res[b].boxes.data.cpu().numpy(), o, cand, 0.15, 0.6, frame_hw=hw)
             _diag(f"engine vs bf16 oracle frame {b}: oracle {rep['n_ref']} ({rep['n_ref_strict']} decided), engine {rep['n_det']}, violations {len(rep['errors'])}")
             assert not rep["errors"], (b, rep["errors"][:5])
             assert rep["n_ref_strict"] >= 0.8 * rep["n_ref"]

@@ -306,7 +306,7 @@ def test_bf16_rounding_points_keep_the_reference_detection_set(name, gfile):
     for b, d in enumerate(dets):
         d = d.copy()
         d[:, :4] = pp.scale_boxes(hw, d[:, :4], hw)
-        rep = detection_set_report(d, g[f"512x640_exact_{b}"], g[f"512x640_cand_{b}"], 0.15, 0.6)
+        rep = detection_set_report(d, g[f"512x640_exact_{b}"], g[f"512x640_cand_{b}"], 0.15, 0.6, frame_hw=hw)
         assert not rep["errors"], (b, rep)
         strict += rep["n_ref_strict"]; total += rep["n_ref"]
     assert strict >= 0.6 * total, (strict, total)            # the band must not swallow the comparison
