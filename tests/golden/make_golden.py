@@ -206,7 +206,7 @@ def gold_net():
     print("net", y.shape, [h.shape for h in heads])
 
 
-def gold_predict(names=("yolov8n-p2", "yolov8s-p2")):
+def gold_predict(names=("yolov8n-p2", "yolov8s-p2", "yolov8-small")):
     """YOLO(cfg).predict of the unmodified reference (fp32, CPU) on synthetic IR frames, both NMS branches, plus the
     candidate list the NMS saw (every anchor with best-class score > conf, boxes in original-frame pixels): the tests
     derive their exclusion band (near-ties an fp32-vs-bf16 comparison cannot decide) from it."""
@@ -255,7 +255,7 @@ def gold_predict(names=("yolov8n-p2", "yolov8s-p2")):
                 pad_x, pad_y = round((im.shape[3] - w) / 2 - 0.1), round((im.shape[2] - h) / 2 - 0.1)
                 box = box - torch.tensor([pad_x, pad_y, pad_x, pad_y], dtype=box.dtype)
                 out[f"{tag}_cand_{b}"] = torch.cat([box, sc[keep, None], cl[keep, None].float()], 1).numpy()
-        np.savez_compressed(os.path.join(HERE, f"predict_{name[6:].replace('-', '_')}.npz"), **out)
+        np.savez_compressed(os.path.join(HERE, f"predict_{name[6:].strip('-').replace('-', '_')}.npz"), **out)
 
 
 def motion_reset_script(n=140, seed=11):

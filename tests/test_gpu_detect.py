@@ -39,7 +39,8 @@ def _diag(msg):
             fh.write(msg + "\n")
 
 
-@pytest.mark.parametrize("name,B,H,W", [("yolov8n-p2", 2, 64, 96), ("yolov8s-p2", 1, 96, 64), ("yolov8x-p2", 1, 64, 64), ("yolov8s-p2", 3, 128, 160)])
+@pytest.mark.parametrize("name,B,H,W", [("yolov8n-p2", 2, 64, 96), ("yolov8s-p2", 1, 96, 64), ("yolov8x-p2", 1, 64, 64), ("yolov8s-p2", 3, 128, 160),
+                                        ("yolov8-small", 2, 64, 96)])      # the project's own model: widths 12 / 24 padded to 16 / 32
 def test_engine_every_layer_matches_oracle_on_identical_inputs(name, B, H, W):
     """Primary kernel gate: after one engine forward, EVERY launch of the plan is re-evaluated by
     the oracle on the engine's own input buffer (bf16 values, bf16 weights, fp32 accumulate) and must agree with
@@ -337,7 +338,8 @@ def _golden_frames(hw):
 
 @pytest.mark.parametrize("name,gfile,tag,hw", [("yolov8n-p2", "predict_n_p2.npz", "512x640", (512, 640)),
                                                ("yolov8n-p2", "predict_n_p2.npz", "500x640", (500, 640)),
-                                               ("yolov8s-p2", "predict_s_p2.npz", "512x640", (512, 640))])
+                                               ("yolov8s-p2", "predict_s_p2.npz", "512x640", (512, 640)),
+                                               ("yolov8-small", "predict_small.npz", "512x640", (512, 640))])
 def test_predict_matches_reference_golden(name, gfile, tag, hw):
     """North-star gate: YOLO(cfg).predict on uint8 frames returns the SAME detection set as the reference's predict()
     (fp32, CPU; tests/golden/predict_*.npz) at conf 0.15 / iou 0.6 -- every decided reference detection present with its box

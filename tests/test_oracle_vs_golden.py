@@ -282,7 +282,7 @@ def test_resize_oracle_is_cv2():
     np.testing.assert_array_equal(out, cv2.resize(img, (1280, 960), interpolation=cv2.INTER_LINEAR))
 
 
-@pytest.mark.parametrize("name,gfile", [("yolov8n-p2", "predict_n_p2.npz"), ("yolov8s-p2", "predict_s_p2.npz")])
+@pytest.mark.parametrize("name,gfile", [("yolov8n-p2", "predict_n_p2.npz"), ("yolov8s-p2", "predict_s_p2.npz"), ("yolov8-small", "predict_small.npz")])
 def test_bf16_rounding_points_keep_the_reference_detection_set(name, gfile):
     """The oracle evaluated at the engine's rounding points (bf16 stored activations, fp32 accumulate) returns the SAME
     detection set as the fp32 reference's predict(), boxes within 1e-2 relative, outside the stated exclusion band

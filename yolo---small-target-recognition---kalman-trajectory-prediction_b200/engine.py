@@ -362,8 +362,13 @@ class Engine:
         _lib.require_cuda()
         self.lib = _lib.load()
         self.spec, self.B, self.H, self.W = spec, int(batch), int(H), int(W)
+        self.lowered_spec = spec
+        if weights.needs_padding(spec):
+            # widths that are not multiples of 16 (yolov8-small.yaml at its default scale: 12 / 24): the same function with the
+            # hidden widths rounded up and zero weights in the padding (weights.pad_channels)
+            self.lowered_spec, state_dict = weights.pad_channels(spec, state_dict)
         # B2_MERGE_HEAD=0: keep Detect's first box / class convs as two launches (A/B experiments)
-        self.plan = lower(spec, state_dict, H, W, fuse_head=fuse_head, merge_head=os.environ.get("B2_MERGE_HEAD", "1") != "0",
+        self.plan = lower(self.lowered_spec, state_dict, H, W, fuse_head=fuse_head, merge_head=os.environ.get("B2_MERGE_HEAD", "1") != "0",
                           chain=int(os.environ.get("B2_CHAIN", str(CHAIN_DEFAULT))))      # B2_CHAIN: bit mask of CHAIN_* (0: every conv its own launch)
         self.fused_head = self.plan.levels[0][0] < 0
         words = self.plan.words()
@@ -389,7 +394,7 @@ class Engine:
             _lib.check(self.lib.b2_engine_head(self._h, dp, cp))
             self.head_dist = [dp[i] for i in range(n.value)]
             self.head_cls = [cp[i] for i in range(n.value)]
-        self.flops_per_image = self.plan.flops
+        self.flops_per_image = cfg.conv_flops(spec, H, W)          # algorithmic FLOPs of the model as given (padding channels are not work)
         self.stride = max(self.level_stride)
         self.names = spec["names"]
 

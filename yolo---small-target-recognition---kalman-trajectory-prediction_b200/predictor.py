@@ -257,8 +257,15 @@ class YOLO:
         import torch
 
         a = {**self.overrides, **kwargs}
+        if a.get("predictor") is not None:
+            # engine/model.py:549 swaps the predictor class; this facade IS the predictor -- to put the engine behind an installed
+            # Ultralytics model use b200dt.ultra_plugin.predictor_class()
+            raise TypeError("predictor= is not supported by b200dt.YOLO; pass b200dt.ultra_plugin.predictor_class() to ultralytics' own YOLO.predict")
+        dv = a.get("device")
+        if dv not in (None, "", "cuda") and not (isinstance(dv, int) and dv == _lib.require_cuda().index) and str(dv) != f"cuda:{_lib.require_cuda().index}" and str(dv) != str(_lib.require_cuda().index):
+            raise ValueError(f"device={dv!r}: b200dt runs on the current CUDA device ({_lib.require_cuda()}); there is no CPU path")
         for k in ("half", "device", "save", "show", "rect", "mode", "augment", "visualize", "embed", "predictor"):
-            a.pop(k, None)
+            a.pop(k, None)          # half: the engine always computes in bf16 with fp32 accumulation; the rest do not touch the hot path
         conf, iou, max_det = float(a["conf"]), float(a["iou"]), int(a["max_det"])
         assert 0 <= conf <= 1, f"Invalid Confidence threshold {conf}, valid values are between 0.0 and 1.0"
         assert 0 <= iou <= 1, f"Invalid IoU {iou}, valid values are between 0.0 and 1.0"

@@ -275,3 +275,106 @@ def pack_stem(w):
     k = np.zeros((c0, 32), np.float32)
     k[:, :27] = np.transpose(w, (0, 2, 3, 1)).reshape(c0, 27)
     return f32_to_bf16_bits(k)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# channel padding: the tcgen05 conv path wants every tensor's channel count to be a multiple of 16
+# ---------------------------------------------------------------------------------------------------------------------
+def needs_padding(spec, multiple=16):
+    return any(((c1 % multiple) and p != "model.0") or c2 % multiple for p, c1, c2, _, _, bn in conv_list(spec) if bn) or \
+        any(c1 % multiple for _, c1, _, _, _, bn in conv_list(spec) if not bn)
+
+
+def pad_channels(spec, sd, multiple=16):
+    """Re-parameterise (spec, state_dict) as the SAME function with every hidden width rounded up to ``multiple``.
+
+    The project's own model, ``yolov8-small.yaml`` at its default scale (train_small_targets.py:20), has C2f hidden widths of
+    12 / 24 channels (cfg/models/v8/yolov8-small.yaml:12-16 with width 0.375).  Padding channels get zero conv rows, BN
+    (gamma, beta, mean, var) = (1, 0, 0, 1 - eps) and zero columns in every consumer, so they carry SiLU(0) = 0 through
+    shortcuts, max-pools, upsamples and concatenations; the real channels compute exactly what they did.  A C2f's ``cv1``
+    output is two padded halves (chunk(2) of block.py:316 stays a split in the middle), a Concat is the concatenation of its
+    padded inputs.  Returns (spec_padded, sd_padded); Detect's outputs (64 DFL bins, nc classes) are unchanged."""
+    import copy
+
+    def up(c):
+        return (c + multiple - 1) // multiple * multiple
+
+    sp = copy.deepcopy(spec)
+    L0 = {L["i"]: L for L in spec["layers"]}
+    out = {}
+    omap, ophys = {}, {}                    # layer -> physical index of each logical output channel, physical channel count
+
+    def src(i, f):
+        return i - 1 if f == -1 else f
+
+    def conv_bn(prefix, rows, n_rows, cols, n_cols):
+        """rows / cols: physical index of each logical output / input channel."""
+        w = np.asarray(sd[prefix + ".conv.weight"], np.float32)
+        wp = np.zeros((n_rows, n_cols) + w.shape[2:], np.float32)
+        wp[np.ix_(rows, cols)] = w
+        out[prefix + ".conv.weight"] = wp
+        for key, fill in ((".bn.weight", 1.0), (".bn.bias", 0.0), (".bn.running_mean", 0.0), (".bn.running_var", 1.0 - BN_EPS)):
+            v = np.full(n_rows, fill, np.float32)
+            v[rows] = np.asarray(sd[prefix + key], np.float32)
+            out[prefix + key] = v
+        out[prefix + ".bn.num_batches_tracked"] = np.asarray(sd.get(prefix + ".bn.num_batches_tracked", 0))
+
+    def blocks(n_blocks, c, pc):
+        return np.concatenate([j * pc + np.arange(c) for j in range(n_blocks)])
+
+    for L, Lp in zip(spec["layers"], sp["layers"]):
+        i, t, f = L["i"], L["type"], L["f"]
+        p = f"model.{i}"
+        if t in ("Conv", "C2f", "SPPF"):
+            s_in = src(i, f)
+            cols, n_cols = (np.arange(L["c1"]), L["c1"]) if i == 0 else (omap[s_in], ophys[s_in])
+            c2, pc2 = L["c2"], up(L["c2"])
+            if t == "Conv":
+                conv_bn(p, np.arange(c2), pc2, cols, n_cols)
+            elif t == "C2f":
+                c, n = L["c"], L["n"]
+                pc = up(c)
+                conv_bn(p + ".cv1", blocks(2, c, pc), 2 * pc, cols, n_cols)
+                for j in range(n):
+                    conv_bn(f"{p}.m.{j}.cv1", np.arange(c), pc, np.arange(c), pc)
+                    conv_bn(f"{p}.m.{j}.cv2", np.arange(c), pc, np.arange(c), pc)
+                conv_bn(p + ".cv2", np.arange(c2), pc2, blocks(2 + n, c, pc), (2 + n) * pc)
+                Lp["c"] = pc
+            else:
+                c_ = L["c1"] // 2
+                pc_ = up(c_)
+                conv_bn(p + ".cv1", np.arange(c_), pc_, cols, n_cols)
+                conv_bn(p + ".cv2", np.arange(c2), pc2, blocks(4, c_, pc_), 4 * pc_)
+                if 2 * pc_ != n_cols:
+                    raise NotImplementedError("SPPF: padded hidden width must stay half of the padded input")
+            omap[i], ophys[i] = np.arange(c2), pc2
+            Lp["c1"], Lp["c2"], Lp["c_out"] = n_cols, pc2, pc2
+        elif t == "Upsample":
+            s_in = src(i, f)
+            omap[i], ophys[i] = omap[s_in], ophys[s_in]
+            Lp["c_out"] = ophys[i]
+        elif t == "Concat":
+            idx, off = [], 0
+            for x in f:
+                s_in = src(i, x)
+                idx.append(off + omap[s_in]); off += ophys[s_in]
+            omap[i], ophys[i] = np.concatenate(idx), off
+            Lp["c_out"] = off
+        elif t == "Detect":
+            cb, cc, nc = L["c2_box"], L["c3_cls"], L["nc"]
+            pcb, pcc = up(cb), up(cc)
+            for l, x in enumerate(f):
+                cols, n_cols = omap[x], ophys[x]
+                for br, ch, pch, n_out in (("cv2", cb, pcb, 4 * REG_MAX), ("cv3", cc, pcc, nc)):
+                    conv_bn(f"{p}.{br}.{l}.0", np.arange(ch), pch, cols, n_cols)
+                    conv_bn(f"{p}.{br}.{l}.1", np.arange(ch), pch, np.arange(ch), pch)
+                    w = np.asarray(sd[f"{p}.{br}.{l}.2.weight"], np.float32)
+                    wp = np.zeros((n_out, pch, 1, 1), np.float32)
+                    wp[:, :ch] = w
+                    out[f"{p}.{br}.{l}.2.weight"] = wp
+                    out[f"{p}.{br}.{l}.2.bias"] = np.asarray(sd[f"{p}.{br}.{l}.2.bias"], np.float32)
+            out[f"{p}.dfl.conv.weight"] = np.asarray(sd[f"{p}.dfl.conv.weight"], np.float32)
+            Lp["ch"], Lp["c2_box"], Lp["c3_cls"] = [ophys[x] for x in f], pcb, pcc
+        else:
+            raise NotImplementedError(t)
+    return sp, out
