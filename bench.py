@@ -442,10 +442,14 @@ def run_b200(a):
     # DRAM traffic per launch of the same kernel: dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one
     # forward of this workload, from the committed ncu capture (profiles/; per-launch list beside it), averaged per launch
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic_v38.json")
-    if os.path.exists(tp) and S == 256 and a.model == MODEL:
-        tj = json.load(open(tp))
-        traffic, traffic_src = tj["conv_dram_bytes_per_launch"], "profiles/r01_conv_traffic_v38.json (ncu, %d launches)" % tj["conv_launches"]
+    for tp_name in ("r02_conv_traffic.json", "r01_conv_traffic_v38.json"):
+        tp = os.path.join(ROOT, "profiles", tp_name)
+        if os.path.exists(tp) and S == 256 and a.model == MODEL:
+            tj = json.load(open(tp))
+            if tj["conv_launches"] != len(conv):
+                continue                 # captured on a different launch plan (e.g. before the chained launches): not this build
+            traffic, traffic_src = tj["conv_dram_bytes_per_launch"], "profiles/%s (ncu, %d launches)" % (tp_name, tj["conv_launches"])
+            break
     conv_bytes = sum(p["bytes"] for p in conv)
     roofline = {"bound": "tensor", "kernel": f"conv_tc_kernel (tcgen05 implicit GEMM, {len(conv)} launches/step)", "achieved": achieved,
                 "peak": pk["tc_sustained"], "peak_kind": f"bf16 dense sustained, {pk['src']}", "unit": "TFLOP/s",

@@ -42,8 +42,8 @@ def main():
         return re.sub(r"\(.*\)$", "", n)
 
     with open(out_csv, "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; "
-                "python tools/profile_forward.py --streams 256 (last eager pass: one forward of the bench workload + post-processing)\n")
+        f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+                "<command> (launches from the last stem kernel on: one forward of the bench workload + whatever follows it)\n")
         w = csv.writer(f)
         w.writerow(["id", "kernel", "grid", "block", "time_us", "dram_read_bytes", "dram_write_bytes"])
         for d in ls:
