@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libb2dt.so")
+_LIB_PATH = os.environ.get("B2DT_LIB") or os.path.join(_HERE, "libb2dt.so")     # B2DT_LIB: an experiment build (tools/build_variant.sh)
 _lib = None
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t

@@ -102,14 +102,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// B2_MBAR_NS (experiment builds only): suspend-time hint of try_wait in ns.  Measured (tools/ab_chain.py, same box): a 1 us or
+// 20 us hint makes the chained convs 1-3 % SLOWER than the plain form, although a waiting epilogue warp then runs far fewer
+// spin iterations -- the default wake-up is faster than the hinted one.  The product build uses no hint.
+#ifndef B2_MBAR_NS
+#define B2_MBAR_NS 0u
+#endif
+constexpr uint32_t kMbarSuspendNs = B2_MBAR_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if B2_MBAR_NS
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs) : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 // Bounded spin: a pipeline bug must trap instead of hanging the GPU.

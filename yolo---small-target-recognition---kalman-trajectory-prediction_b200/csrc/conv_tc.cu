@@ -25,6 +25,17 @@
 //     C2f / SPPF / Concat / Detect become offset writes and offset reads.
 #include "common.cuh"
 
+// Experiment switches of the issue loops (tools/build_variant.sh): unrolled stride-2 stage, unrolled chained GEMM.  Both are OFF:
+// measured in one process on one box (tools/ab_chain.py), the unrolled forms issue fewer instructions per MMA but run SLOWER
+// (32->64 s2 chain 523 -> 586 us, DFL chain 488 -> 539 us): each tile then executes ~1000 straight-line instructions once
+// instead of a loop body that stays in the instruction cache, next to four other warp roles doing the same.
+#ifndef B2_S2_UNROLL
+#define B2_S2_UNROLL 0
+#endif
+#ifndef B2_CHAIN_UNROLL
+#define B2_CHAIN_UNROLL 0
+#endif
+
 #include <limits.h>
 
 #include <algorithm>
@@ -205,10 +216,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], const fl
 }
 
 // E1 of a chained conv: bias + activation (+ residual) + bf16 pack of one 16-column chunk, stored as two 16-byte units of
-// row `row` of a K-major operand block with `row_bytes`-byte rows (128 / 64 / 32: SWIZZLE_128B / 64B / 32B).  The swizzle is a
-// function of the absolute shared-memory address: unit index ^= address bits [7, 7 + log2(row_bytes / 16)).
+// its row of a K-major operand block.  p0 / p1 are the units' shared-memory addresses with the swizzle already applied (the
+// swizzle is a function of the absolute address, DESIGN.md fact 3: unit index ^= address bits [7, 7 + log2(row_bytes / 16));
+// a thread's row and chunk never change, so the caller computes them once per kernel, not per tile).
 __device__ __forceinline__ void epilogue_chunk_smem(const uint32_t (&v)[16], const float* __restrict__ sb, int act,
-                                                    const __nv_bfloat16* __restrict__ rptr, uint32_t blk_addr, int row, uint32_t row_bytes, uint32_t unit0) {
+                                                    const __nv_bfloat16* __restrict__ rptr, uint32_t p0, uint32_t p1) {
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
@@ -237,10 +249,6 @@ __device__ __forceinline__ void epilogue_chunk_smem(const uint32_t (&v)[16], con
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-    const uint32_t mask = (row_bytes >> 4) - 1u;                      // 7 / 3 / 1
-    const uint32_t off0 = (uint32_t)row * row_bytes + unit0 * 16u, off1 = off0 + 16u;
-    const uint32_t a0 = blk_addr + off0, a1 = blk_addr + off1;
-    const uint32_t p0 = a0 ^ (((a0 >> 7) & mask) << 4), p1 = a1 ^ (((a1 >> 7) & mask) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(p0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(p1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
 }
@@ -339,6 +347,36 @@ __device__ __forceinline__ void ss_issue_taps(uint32_t leader, uint32_t d_addr, 
             accum = 1;
         }
     }
+}
+
+// One stage of a 3x3 stride-2 conv (halo 3), unrolled: the stage holds the (TW + PW) x (TH + PH) box of input parity (PH, PW); it
+// serves filter rows kh in {0, 2} (box rows 0 / 1) when PH else {1}, columns likewise.  row16 = one box row in descriptor units,
+// tb_lo = weight block (tap 0, this K chunk), tap_step = blocks between taps.
+template <int MPS, int PH, int PW>
+__device__ __forceinline__ void ss_issue_s2(uint32_t leader, uint32_t d_addr, uint32_t idesc, uint64_t hi_a, uint64_t hi_w, uint32_t a_lo,
+                                            uint32_t row16, uint32_t tb_lo, uint32_t tap_step, uint32_t& accum) {
+#pragma unroll
+    for (int a = 0; a <= PH; ++a) {
+#pragma unroll
+        for (int c = 0; c <= PW; ++c) {
+            const int kh = PH ? 2 * a : 1, kw = PW ? 2 * c : 1;
+            const uint32_t ta = a_lo + (uint32_t)(a * (8 + PW) + c) * row16;
+            const uint32_t tb = tb_lo + (uint32_t)(kh * 3 + kw) * tap_step;
+#pragma unroll
+            for (int j = 0; j < MPS; ++j) {
+                tc_mma_bf16_if(leader, d_addr, hi_a | (uint64_t)(ta + 2u * j), hi_w | (uint64_t)(tb + 2u * j), idesc, accum);
+                accum = 1;
+            }
+        }
+    }
+}
+template <int MPS>
+__device__ __forceinline__ void ss_issue_s2_g(int g, uint32_t leader, uint32_t d_addr, uint32_t idesc, uint64_t hi8, uint64_t hi9, uint64_t hi_w,
+                                              uint32_t a_lo, uint32_t row16, uint32_t tb_lo, uint32_t tap_step, uint32_t& accum) {
+    if (g == 0) ss_issue_s2<MPS, 0, 0>(leader, d_addr, idesc, hi8, hi_w, a_lo, row16, tb_lo, tap_step, accum);
+    else if (g == 1) ss_issue_s2<MPS, 0, 1>(leader, d_addr, idesc, hi9, hi_w, a_lo, row16, tb_lo, tap_step, accum);
+    else if (g == 2) ss_issue_s2<MPS, 1, 0>(leader, d_addr, idesc, hi8, hi_w, a_lo, row16, tb_lo, tap_step, accum);
+    else ss_issue_s2<MPS, 1, 1>(leader, d_addr, idesc, hi9, hi_w, a_lo, row16, tb_lo, tap_step, accum);
 }
 
 // MW: MMA-issuing warps.  1: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, up to two CTAs per SM.  2 (plans with ONE CTA per SM):
@@ -545,6 +583,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
         // E1 has had a whole tile of tensor-pipe time to stage it, and the pipe never idles waiting for the epilogue
         const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c2_n >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t smem_lo0 = smem_u32(smem);
+        const int c2_nblk = p.c2_nblk;
         auto chain_issue = [&](int k) {
             const int buf = k & 1;
             const uint32_t par = (uint32_t)(k >> 1) & 1u;
@@ -554,15 +593,31 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
             tc_fence_after();
             const uint32_t d2 = tmem_base_u + p.c2_tmem_col + (uint32_t)(buf * p.c2_n);
             uint32_t accum2 = 0;
-            for (int i = 0; i < p.c2_nblk; ++i) {
-                const uint32_t a_lo = (((smem_lo0 + p.c2_buf_off + (uint32_t)buf * p.c2_buf_bytes + p.c2_a_off[i]) >> 4) & 0x3FFFu) | (1u << 16);
-                const uint32_t w_lo = (((smem_lo0 + p.c2_wreg_off + p.c2_w_off[i]) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t buf_lo = smem_lo0 + p.c2_buf_off + (uint32_t)buf * p.c2_buf_bytes, w_lo0 = smem_lo0 + p.c2_wreg_off;
+#if B2_CHAIN_UNROLL
+#pragma unroll
+            for (int i = 0; i < kMaxChainBlk; ++i) {        // static indices: the per-block constants are read straight from the parameter bank
+                if (i < c2_nblk) {
+                    const uint32_t a_lo = (((buf_lo + p.c2_a_off[i]) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t w_lo = (((w_lo0 + p.c2_w_off[i]) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint64_t hi = (uint64_t)p.c2_desc_hi[i] << 32;
+                    const int mps = p.c2_bk[i] >> 4;
+                    if (mps == 4) ss_issue_taps<4, 1>(leader, d2, idesc2, hi, a_lo, w_lo, 0u, accum2);
+                    else if (mps == 2) ss_issue_taps<2, 1>(leader, d2, idesc2, hi, a_lo, w_lo, 0u, accum2);
+                    else ss_issue_taps<1, 1>(leader, d2, idesc2, hi, a_lo, w_lo, 0u, accum2);
+                }
+            }
+#else
+            for (int i = 0; i < c2_nblk; ++i) {
+                const uint32_t a_lo = (((buf_lo + p.c2_a_off[i]) >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t w_lo = (((w_lo0 + p.c2_w_off[i]) >> 4) & 0x3FFFu) | (1u << 16);
                 const uint64_t hi = (uint64_t)p.c2_desc_hi[i] << 32;
                 for (int j = 0; j < (p.c2_bk[i] >> 4); ++j) {
                     tc_mma_bf16_if(leader, d2, hi | (uint64_t)(a_lo + 2u * j), hi | (uint64_t)(w_lo + 2u * j), idesc2, accum2);
                     accum2 = 1;
                 }
             }
+#endif
             tc_commit_if(leader, &t2_full[buf]);
             tc_commit_if(leader, &a2_empty[buf]);
         };
@@ -585,6 +640,13 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                         if (halo == 3) {
                             // stride 2: this stage holds the (TW + pw) x (TH + ph) box of input parity (ph, pw) = (g >> 1, g & 1); it
                             // serves taps kh in {0, 2} (box rows 0 / 1) or {1}, kw likewise (kh16 = one row); resident weights
+#if B2_S2_UNROLL
+                            const uint64_t hi9 = (uint64_t)sg_hi9[s] << 32;
+                            const uint32_t tb_lo = b_lo0 + b_base16 + (uint32_t)kc * b_blk16, tap_step = (uint32_t)kchunks * b_blk16;
+                            if (mma_per_step == 4) ss_issue_s2_g<4>(g, leader, d_addr, idesc, desc_hi_w, hi9, desc_hi_w, a_lo, kh16, tb_lo, tap_step, accum);
+                            else if (mma_per_step == 2) ss_issue_s2_g<2>(g, leader, d_addr, idesc, desc_hi_w, hi9, desc_hi_w, a_lo, kh16, tb_lo, tap_step, accum);
+                            else ss_issue_s2_g<1>(g, leader, d_addr, idesc, desc_hi_w, hi9, desc_hi_w, a_lo, kh16, tb_lo, tap_step, accum);
+#else
                             const int ph = g >> 1, pw = g & 1;
                             const uint64_t hi_a = pw ? (uint64_t)sg_hi9[s] << 32 : desc_hi_w;
                             const uint32_t row_pitch = (uint32_t)(8 + pw) * kh16;
@@ -600,6 +662,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
                                     }
                                 }
                             }
+#endif
                         } else if (halo == 2) {
                             // one box, nine taps, resident weights: block (tap, kc)
                             const uint32_t tb_lo = b_lo0 + b_base16 + (uint32_t)kc * b_blk16, tb_step = (uint32_t)kchunks * b_blk16;
@@ -669,6 +732,29 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
         };
         if (x_issuer)
             for (int j = 0; j < 2; ++j) if ((int)blockIdx.x + j * (int)gridDim.x < total_tiles) x_load((int)blockIdx.x + j * (int)gridDim.x, j);
+        // E1: this thread's first two chunks are half and half + kSubR (all of them when n_tile <= 32 kSubR); the swizzled shared-memory
+        // address of a chunk's first 16-byte unit inside staged-tile buffer 0 is fixed for the whole kernel.  The second unit is
+        // that address ^ 16 (a chunk starts at an even unit and the swizzle only XORs bits 4..6 with row bits); buffer 1 is
+        // c2_buf_bytes, a multiple of 1024, further on (the swizzle bits do not change).
+        uint32_t e1_pa = 0, e1_pb = 0;
+        int e1_nq = 0;
+        const uint32_t c2_buf_bytes = p.c2_buf_bytes;
+        if (CH && is_e1) {
+            const int nch1 = n_tile >> 4;                   // padding channels (>= Cout) carry zero weights and bias: they stage SiLU(0) = 0
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int jj = half + q * kSubR;
+                if (jj < nch1) {
+                    int bi = p.c2_nx;                       // chunk jj -> E1 block holding main channel 16 jj (blocks c2_nx.. are E1's, in channel order)
+                    while (bi + 1 < p.c2_nblk && jj * 16 >= p.c2_src_c[bi + 1]) ++bi;
+                    const uint32_t rb = (uint32_t)p.c2_bk[bi] * 2u, mask = (rb >> 4) - 1u;     // row bytes 128 / 64 / 32, swizzle mask 7 / 3 / 1
+                    const uint32_t a0 = smem_lo + p.c2_buf_off + p.c2_a_off[bi] + (uint32_t)row * rb + ((uint32_t)(jj * 16 - p.c2_src_c[bi]) >> 3) * 16u;
+                    const uint32_t pq = a0 ^ (((a0 >> 7) & mask) << 4);
+                    if (q) e1_pb = pq; else e1_pa = pq;
+                    e1_nq = q + 1;
+                }
+            }
+        }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++kk) {
             const int m0 = fast_div(tile, magic_nt), n_idx = tile - m0 * n_tiles;
             const int m1 = fast_div(m0, magic_tw), m2 = fast_div(m1, magic_th);
@@ -683,33 +769,37 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
             if (CH && is_e1) {
                 // ===== E1: main accumulator -> bias / SiLU (+ shortcut) -> bf16 -> staged operand tile kk & 1 in shared memory =====
                 const int buf = kk & 1;
-                const int nch1 = n_tile >> 4;               // padding channels (>= Cout) carry zero weights and bias: they stage SiLU(0) = 0
-                if (rptr && valid)
-                    for (int j = half; j < nch1; j += kSubR) asm volatile("prefetch.global.L2 [%0];" ::"l"(rptr + j * 16));
+                if (rptr && valid && e1_nq > 0) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rptr + half * 16));
+                    if (e1_nq > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(rptr + (half + kSubR) * 16));
+                }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 mbar_wait(&a2_empty[buf], ((uint32_t)(kk >> 1) & 1u) ^ 1u);     // the chained MMAs of tile kk - 2 have read this buffer
                 tc_fence_after();
-                const uint32_t t_addr1 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_tile);
-                const uint32_t buf_addr = smem_lo + p.c2_buf_off + (uint32_t)buf * p.c2_buf_bytes;
-                for (int j = half; j < nch1; j += 2 * kSubR) {
-                    const int j2 = j + kSubR;
-                    const bool two = j2 < nch1;
+                const uint32_t t_addr1 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_tile) + (uint32_t)(half * 16);
+                const uint32_t boff = buf ? c2_buf_bytes : 0u;
+                const bool res_ok = rptr && valid;
+                if (e1_nq > 0) {                            // (n_tile = 16: the second warp of a quadrant has no chunk, it only keeps the barriers' counts)
+                    const bool two = e1_nq > 1;
                     uint32_t v0[16], v1[16];
-                    tmem_ld16(t_addr1 + j * 16, v0);
-                    if (two) tmem_ld16(t_addr1 + j2 * 16, v1);
+                    tmem_ld16(t_addr1, v0);
+                    if (two) tmem_ld16(t_addr1 + kSubR * 16, v1);
                     tmem_ld_wait();
-                    // chunk j -> E1 block holding main channel 16 j (blocks c2_nx.. are E1's, in channel order)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int jj = e ? j2 : j;
-                        if (e && !two) break;
-                        int bi = p.c2_nx;
-                        while (bi + 1 < p.c2_nblk && jj * 16 >= p.c2_src_c[bi + 1]) ++bi;
-                        const uint32_t rb = (uint32_t)p.c2_bk[bi] * 2u;
-                        const bool have_res = rptr && valid && jj * 16 < Cout;
-                        epilogue_chunk_smem(e ? v1 : v0, s_bias + jj * 16, act, have_res ? rptr + jj * 16 : nullptr,
-                                            buf_addr + p.c2_a_off[bi], row, rb, (uint32_t)(jj * 16 - p.c2_src_c[bi]) >> 3);
-                    }
+                    const int c0 = half * 16, c1 = c0 + kSubR * 16;
+                    epilogue_chunk_smem(v0, s_bias + c0, act, (res_ok && c0 < Cout) ? rptr + c0 : nullptr, e1_pa + boff, (e1_pa + boff) ^ 16u);
+                    if (two) epilogue_chunk_smem(v1, s_bias + c1, act, (res_ok && c1 < Cout) ? rptr + c1 : nullptr, e1_pb + boff, (e1_pb + boff) ^ 16u);
+                }
+                // wider main convs (n_tile > 32 kSubR, e.g. the 80-channel class branch): further chunks, address worked out per tile
+                for (int jj = half + 2 * kSubR; jj < (n_tile >> 4); jj += kSubR) {
+                    uint32_t v0[16];
+                    tmem_ld16(t_addr1 + (uint32_t)(jj - half) * 16u, v0);
+                    tmem_ld_wait();
+                    int bi = p.c2_nx;
+                    while (bi + 1 < p.c2_nblk && jj * 16 >= p.c2_src_c[bi + 1]) ++bi;
+                    const uint32_t rb = (uint32_t)p.c2_bk[bi] * 2u, mask = (rb >> 4) - 1u;
+                    const uint32_t a0 = smem_lo + p.c2_buf_off + boff + p.c2_a_off[bi] + (uint32_t)row * rb + ((uint32_t)(jj * 16 - p.c2_src_c[bi]) >> 3) * 16u;
+                    const uint32_t pq = a0 ^ (((a0 >> 7) & mask) << 4);
+                    epilogue_chunk_smem(v0, s_bias + jj * 16, act, (res_ok && jj * 16 < Cout) ? rptr + jj * 16 : nullptr, pq, pq ^ 16u);
                 }
                 fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&a2_full[buf]);
@@ -1587,6 +1677,7 @@ int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B,
     if (chain) {
         p.c2_wreg_off = (uint32_t)((size_t)stages * a_stage + b_all);
         p.c2_buf_off = (uint32_t)(p.c2_wreg_off + (chain_bytes - 2 * (size_t)p.c2_buf_bytes));
+        if ((p.c2_buf_off | p.c2_buf_bytes) & 1023u) { b2_set_error("conv(chain): staged-tile buffers must be 1 KiB aligned"); return B2_ERR_UNSUPPORTED; }
         for (int i = 0; i < p.c2_nblk; ++i) p.b_res_bytes += p.c2_w_bytes[i];
         L->smem += chain_bytes;
     }

@@ -8,6 +8,8 @@
 //                  scale_boxes / clip_boxes (utils/ops.py:105-138, :157-183).
 #include "common.cuh"
 
+#include <algorithm>
+
 void b2_count_launch(int n);
 
 namespace {
@@ -33,7 +35,10 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 // 8 lanes cooperate on one anchor: lane s loads 16-byte chunk s of the 64 DFL logits (side = s/2,
 // bins (s&1)*8..+7), then chunks s, s+8, ... of the class logits.  A warp covers 4 consecutive anchors
 // = 4 x (64+nc) x 2 contiguous bytes of the NHWC logits.
-__global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
+// DENSE: also write the reference-shaped (B, 4 + nc, A) tensor (every anchor decoded); the candidate-only instance keeps fewer
+// registers live (6 blocks of 256 threads per SM instead of 4: the kernel is bound by bytes in flight, 32 per thread)
+template <bool DENSE>
+__global__ void __launch_bounds__(256, DENSE ? 4 : 6) decode_kernel(const DecodeParams p) {
     const int lane = threadIdx.x & 31, sub = lane & 7;
     const int b = blockIdx.y;
     int lvl = 0;
@@ -51,7 +56,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     const uint4 ninf4 = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // bf16 -inf pairs
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = ninf4, q2 = ninf4;
     if (active) {
-        if (p.dense) q0 = ldg_nc_v4(row + sub * 8);
+        if (DENSE) q0 = ldg_nc_v4(row + sub * 8);
         if (sub < nchunks) q1 = ldg_nc_v4(row + 64 + sub * 8);
         if (sub + 8 < nchunks) q2 = ldg_nc_v4(row + 64 + (sub + 8) * 8);
     }
@@ -59,7 +64,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     // ---- classes: max logit / argmax over nc ----
     float best = -INFINITY; int bidx = 0x7fffffff;
     const size_t dense_base = (size_t)b * (4 + p.nc) * p.A + a;
-    if (!p.dense) {
+    if (!DENSE) {
         // Pass 1: only the MAX logit of the anchor, with packed bf16x2 max instructions (exact: max of bf16 values).  The class
         // index is looked up afterwards, and only in warps that hold a candidate.
         __nv_bfloat162 m2 = __floats2bfloat162_rn(-INFINITY, -INFINITY);
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
         for (int i = 0; i < 8; ++i) {
             const int ci = ck * 8 + i;
             if (ci < p.nc) {
-                if (p.dense && active) p.dense[dense_base + (size_t)(4 + ci) * p.A] = 1.f / (1.f + __expf(-c[i]));
+                if (DENSE && active) p.dense[dense_base + (size_t)(4 + ci) * p.A] = 1.f / (1.f + __expf(-c[i]));
                 if (c[i] > best) { best = c[i]; bidx = ci; }
             }
         }
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     const bool anchor_cand = active && bidx != 0x7fffffff && score > p.conf && (!p.cmask || p.cmask[bidx]);
     // Boxes are only needed for candidates (a per cent of the anchors at conf 0.15) unless the dense tensor is asked for:
     // warps without a candidate stop here -- 128 of the 288 bytes per anchor are never read, 64 exponentials never taken.
-    if (!p.dense) {
+    if (!DENSE) {
         if (!__any_sync(0xffffffffu, anchor_cand)) return;
         if (active) q0 = ldg_nc_v4(row + sub * 8);
     }
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
     const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f, st = (float)p.stride[lvl];
     const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + db;
     const float cx = (x1 + x2) / 2.f * st, cy = (y1 + y2) / 2.f * st, bw = (x2 - x1) * st, bh = (y2 - y1) * st;
-    if (p.dense && active && sub < 4) p.dense[dense_base + (size_t)sub * p.A] = sub == 0 ? cx : sub == 1 ? cy : sub == 2 ? bw : bh;
+    if (DENSE && active && sub < 4) p.dense[dense_base + (size_t)sub * p.A] = sub == 0 ? cx : sub == 1 ? cy : sub == 2 ? bw : bh;
 
     const bool is_cand = anchor_cand && sub == 0;
     const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
@@ -177,63 +182,68 @@ struct HeadParams {
     float* cand; int32_t* cand_idx; int32_t* cand_count; int cand_cap;
 };
 
-// One thread tests kHcPer anchors of one (level, image), a block apart (coalesced 8-byte loads of {logit, class} records), all of
-// them issued before any is used.  The kernel moves 8 bytes per anchor; the sigmoid, the box and the 16-byte distance record
-// are touched only for the per-cent of anchors whose logit clears logit_lo (then the reference's exact test `score > conf`).
+// One thread tests kHcPer anchors of one (level, image) per chunk, a block apart (coalesced 8-byte loads of {logit, class}
+// records), all of them issued before any is used.  The kernel moves 8 bytes per anchor; the sigmoid, the box and the 16-byte
+// distance record are touched only for the per-cent of anchors whose logit clears logit_lo (then the reference's exact test
+// `score > conf`).  A block walks chunks blockIdx.x, blockIdx.x + gridDim.x, ... of its image (chunk -> level through blk_off:
+// a chunk never straddles a level); the grid is sized to ONE wave of resident blocks -- with one chunk per block the kernel
+// spent more time dispatching 3840 short-lived blocks than moving its 58 MB.
 constexpr int kHcPer = 8;
 
 __global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p) {
-    const int lane = threadIdx.x & 31;
-    int lvl = 0;
-#pragma unroll
-    for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && (int)blockIdx.x >= p.blk_off[l]) lvl = l;
-    const int W = p.w[lvl], HW = p.h[lvl] * W, b = blockIdx.y;
-    const float2* cp = reinterpret_cast<const float2*>(p.cls[lvl]) + (size_t)b * HW;
-    const int la0 = ((int)blockIdx.x - p.blk_off[lvl]) * (256 * kHcPer) + threadIdx.x;
-    float2 c[kHcPer];
-#pragma unroll
-    for (int k = 0; k < kHcPer; ++k) {
-        const int la = la0 + k * 256;
-        c[k] = la < HW ? __ldg(cp + la) : make_float2(-INFINITY, 0.f);
-    }
+    const int lane = threadIdx.x & 31, b = blockIdx.y;
     const float lo = p.logit_lo;
-    bool any = false;
+    for (int chunk = blockIdx.x; chunk < p.blk_off[p.n_levels]; chunk += gridDim.x) {
+        int lvl = 0;
 #pragma unroll
-    for (int k = 0; k < kHcPer; ++k) any |= c[k].x > lo;
-    if (!__any_sync(0xffffffffu, any)) return;
-    const float st = (float)p.stride[lvl];
-    const float4* dp = reinterpret_cast<const float4*>(p.dist[lvl]) + (size_t)b * HW;
+        for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && chunk >= p.blk_off[l]) lvl = l;
+        const int W = p.w[lvl], HW = p.h[lvl] * W;
+        const float2* cp = reinterpret_cast<const float2*>(p.cls[lvl]) + (size_t)b * HW;
+        const int la0 = (chunk - p.blk_off[lvl]) * (256 * kHcPer) + threadIdx.x;
+        float2 c[kHcPer];
 #pragma unroll
-    for (int k = 0; k < kHcPer; ++k) {
-        const float logit = c[k].x;
-        const int bidx = (int)c[k].y;
-        const int la = la0 + k * 256;
-        bool is_cand = false;
-        float score = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-        if (logit > lo) {
-            score = 1.f / (1.f + __expf(-logit));
-            if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
-                const float4 d = __ldg(dp + la);
-                const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f;
-                const float u1 = ax - d.x, v1 = ay - d.y, u2 = ax + d.z, v2 = ay + d.w;
-                const float cx = (u1 + u2) / 2.f * st, cy = (v1 + v2) / 2.f * st, bw = (u2 - u1) * st, bh = (v2 - v1) * st;
-                const float hw = bw / 2.f, hh = bh / 2.f;
-                x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
-                is_cand = true;
-            }
+        for (int k = 0; k < kHcPer; ++k) {
+            const int la = la0 + k * 256;
+            c[k] = la < HW ? __ldg(cp + la) : make_float2(-INFINITY, 0.f);
         }
-        const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
-        if (!ball) continue;
-        int base = 0;
-        const int leader = __ffs(ball) - 1;
-        if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (is_cand) {
-            const int pos = base + __popc(ball & ((1u << lane) - 1));
-            if (pos < p.cand_cap) {
-                float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
-                o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = score; o[5] = (float)bidx;
-                p.cand_idx[(size_t)b * p.cand_cap + pos] = p.a_off[lvl] + la;
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < kHcPer; ++k) any |= c[k].x > lo;
+        if (!__any_sync(0xffffffffu, any)) continue;
+        const float st = (float)p.stride[lvl];
+        const float4* dp = reinterpret_cast<const float4*>(p.dist[lvl]) + (size_t)b * HW;
+#pragma unroll
+        for (int k = 0; k < kHcPer; ++k) {
+            const float logit = c[k].x;
+            const int bidx = (int)c[k].y;
+            const int la = la0 + k * 256;
+            bool is_cand = false;
+            float score = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+            if (logit > lo) {
+                score = 1.f / (1.f + __expf(-logit));
+                if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
+                    const float4 d = __ldg(dp + la);
+                    const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f;
+                    const float u1 = ax - d.x, v1 = ay - d.y, u2 = ax + d.z, v2 = ay + d.w;
+                    const float cx = (u1 + u2) / 2.f * st, cy = (v1 + v2) / 2.f * st, bw = (u2 - u1) * st, bh = (v2 - v1) * st;
+                    const float hw = bw / 2.f, hh = bh / 2.f;
+                    x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
+                    is_cand = true;
+                }
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+            if (!ball) continue;
+            int base = 0;
+            const int leader = __ffs(ball) - 1;
+            if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (is_cand) {
+                const int pos = base + __popc(ball & ((1u << lane) - 1));
+                if (pos < p.cand_cap) {
+                    float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
+                    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = score; o[5] = (float)bidx;
+                    p.cand_idx[(size_t)b * p.cand_cap + pos] = p.a_off[lvl] + la;
+                }
             }
         }
     }
@@ -583,7 +593,8 @@ extern "C" int b2_decode(const void* const* level_logits, const int* level_h, co
     p.blk_off[0] = 0;
     for (int l = 0; l < n_levels; ++l) p.blk_off[l + 1] = p.blk_off[l] + b2_ceil_div(level_h[l] * level_w[l] * 8, 256);
     dim3 grid(p.blk_off[n_levels], B);
-    decode_kernel<<<grid, 256, 0, st>>>(p);
+    if (dense_out) decode_kernel<true><<<grid, 256, 0, st>>>(p);
+    else decode_kernel<false><<<grid, 256, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
@@ -610,7 +621,9 @@ extern "C" int b2_candidates_from_head(const float* const* level_dist, const flo
     p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count; p.cand_cap = cand_cap;
     cudaStream_t st = (cudaStream_t)stream;
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
-    head_candidates_kernel<<<dim3(p.blk_off[n_levels], B), 256, 0, st>>>(p);
+    // one wave: 6 resident blocks of 256 threads per SM (40 registers), split evenly over the images
+    const int gx = std::max(1, std::min(p.blk_off[n_levels], (b2_num_sms() * 6) / B));
+    head_candidates_kernel<<<dim3(gx, B), 256, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;

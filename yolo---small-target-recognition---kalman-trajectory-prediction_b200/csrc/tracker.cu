@@ -39,6 +39,9 @@ enum IField { ID = 0, AGE, HITS, STREAK, TSU, LOSTF, ISLOST, NVEL, VHEAD, TLEN, 
 // mode 1 (camera_motion_compensation/motion_reset_kalman_tracker.py:16-355): per-slot reset state
 //   position_history deque(maxlen=8) (:41), last bbox of bbox_history + its length (:43, only [-1] and len >= 2 are read),
 //   motion_scores deque(maxlen=10) (:55), motion_consistency, reset_count, last_reset_frame (:52-53)
+#ifndef B2_SWEEP_BLOCKS
+#define B2_SWEEP_BLOCKS 4      // resident sweep blocks per SM the register budget is set for (experiment builds: 5, 6)
+#endif
 constexpr int kPosRing = 8, kScoreRing = 10;
 enum MRF { MR_PH = 0, MR_BB = MR_PH + 2 * kPosRing, MR_MS = MR_BB + 4, MR_MCONS = MR_MS + kScoreRing, MR_NF };
 enum MRI { MR_PHLEN = 0, MR_PHHEAD, MR_BBLEN, MR_MSLEN, MR_MSHEAD, MR_RESETS, MR_LASTRESET, MR_NI };
@@ -275,7 +278,7 @@ __device__ __forceinline__ unsigned long long sweep_scan(unsigned long long v, u
 // index only; the hardware dispatches the blocks of a 1-D grid in index order, so a waiting block's predecessors are always
 // resident or finished (a bounded spin traps instead of hanging should that ever not hold).
 template <int MODE>
-__global__ void __launch_bounds__(kChunk, 4) sweep_kernel(const Bank b, const Frame fr) {
+__global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Bank b, const Frame fr) {
     extern __shared__ float4 s_det[];                              // [D] detections of the stream
     __shared__ __align__(16) float s_rows[kChunk * B2_TRACK_COLS];
     __shared__ unsigned long long s_warp[kChunk / 32];

@@ -85,6 +85,7 @@ class DetectTrackPipeline:
         self._d2h_stream = torch.cuda.Stream()
         self.overlap_post = bool(overlap_post)
         self._post_stream = torch.cuda.Stream()
+        self.forward_events = None                     # a list: step_device appends (start, end) events of each forward
         self._cand_done = torch.cuda.Event()
         self._post_done = torch.cuda.Event()
         self._post_done.record()
@@ -114,7 +115,13 @@ class DetectTrackPipeline:
             cur.wait_event(self._rows_downloaded)
             return self.bank.update(dets, counts, with_trajectory=with_trajectory, stream=stream)
         d, ps = self.detect, self._post_stream
+        if self.forward_events is not None:           # bench.py: CUDA events around the forward graph, on the stream it runs on
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(cur)
         d.engine.forward_u8(frames_u8, self.top, self.left, stream=stream)
+        if self.forward_events is not None:
+            ev[1].record(cur)
+            self.forward_events.append(ev)
         cur.wait_event(self._post_done)               # NMS of the previous step has read the candidate lists
         d.candidates(self.conf, None, stream)
         self._cand_done.record(cur)
