@@ -310,6 +310,19 @@ def hbm_kernels(pipe, pk):
                                   "frac_of_hbm_peak": nb / ms / 1e6 / pk["hbm"]}
     del flush_buf
     bank.close()
+    # DRAM traffic of the same launches (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full` capture of
+    # tools/hbm_probe.py --once, the same sizes and data recipes; committed under profiles/): traffic above the algorithmic bytes
+    # means re-reads, below it means the L2 still held written lines when the capture ended
+    tp = os.path.join(ROOT, "profiles", "r02_hbm_traffic.json")
+    if os.path.exists(tp):
+        tk = json.load(open(tp))["kernels"]
+        for name, keys in (("decode", ["decode"]), ("head_candidates", ["head_candidates"]), ("nms", ["nms"]),
+                           ("kalman_sweep_coast", ["sweep_coast", "resolve_coast"]), ("kalman_frame_c3", ["sweep_frame", "resolve_frame"]),
+                           ("kalman_predict_only", ["bank_predict"])):
+            if name in out and all(k in tk for k in keys):
+                out[name]["traffic"] = sum((tk[k]["dram_read_mb"] + tk[k]["dram_write_mb"]) * 1e6 for k in keys)
+                out[name]["ncu_duration_us"] = {k: tk[k]["duration_us"] for k in keys}
+                out[name]["traffic_source"] = "profiles/r02_hbm_traffic.json"
     return out
 
 

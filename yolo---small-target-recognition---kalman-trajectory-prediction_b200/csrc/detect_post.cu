@@ -182,68 +182,63 @@ struct HeadParams {
     float* cand; int32_t* cand_idx; int32_t* cand_count; int cand_cap;
 };
 
-// One thread tests kHcPer anchors of one (level, image) per chunk, a block apart (coalesced 8-byte loads of {logit, class}
-// records), all of them issued before any is used.  The kernel moves 8 bytes per anchor; the sigmoid, the box and the 16-byte
-// distance record are touched only for the per-cent of anchors whose logit clears logit_lo (then the reference's exact test
-// `score > conf`).  A block walks chunks blockIdx.x, blockIdx.x + gridDim.x, ... of its image (chunk -> level through blk_off:
-// a chunk never straddles a level); the grid is sized to ONE wave of resident blocks -- with one chunk per block the kernel
-// spent more time dispatching 3840 short-lived blocks than moving its 58 MB.
+// One thread tests kHcPer anchors of one (level, image), a block apart (coalesced 8-byte loads of {logit, class} records), all of
+// them issued before any is used.  The kernel moves 8 bytes per anchor; the sigmoid, the box and the 16-byte distance record
+// are touched only for the per-cent of anchors whose logit clears logit_lo (then the reference's exact test `score > conf`).
 constexpr int kHcPer = 8;
 
 __global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p) {
-    const int lane = threadIdx.x & 31, b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    int lvl = 0;
+#pragma unroll
+    for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && (int)blockIdx.x >= p.blk_off[l]) lvl = l;
+    const int W = p.w[lvl], HW = p.h[lvl] * W, b = blockIdx.y;
+    const float2* cp = reinterpret_cast<const float2*>(p.cls[lvl]) + (size_t)b * HW;
+    const int la0 = ((int)blockIdx.x - p.blk_off[lvl]) * (256 * kHcPer) + threadIdx.x;
+    float2 c[kHcPer];
+#pragma unroll
+    for (int k = 0; k < kHcPer; ++k) {
+        const int la = la0 + k * 256;
+        c[k] = la < HW ? __ldg(cp + la) : make_float2(-INFINITY, 0.f);
+    }
     const float lo = p.logit_lo;
-    for (int chunk = blockIdx.x; chunk < p.blk_off[p.n_levels]; chunk += gridDim.x) {
-        int lvl = 0;
+    bool any = false;
 #pragma unroll
-        for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && chunk >= p.blk_off[l]) lvl = l;
-        const int W = p.w[lvl], HW = p.h[lvl] * W;
-        const float2* cp = reinterpret_cast<const float2*>(p.cls[lvl]) + (size_t)b * HW;
-        const int la0 = (chunk - p.blk_off[lvl]) * (256 * kHcPer) + threadIdx.x;
-        float2 c[kHcPer];
+    for (int k = 0; k < kHcPer; ++k) any |= c[k].x > lo;
+    if (!__any_sync(0xffffffffu, any)) return;
+    const float st = (float)p.stride[lvl];
+    const float4* dp = reinterpret_cast<const float4*>(p.dist[lvl]) + (size_t)b * HW;
 #pragma unroll
-        for (int k = 0; k < kHcPer; ++k) {
-            const int la = la0 + k * 256;
-            c[k] = la < HW ? __ldg(cp + la) : make_float2(-INFINITY, 0.f);
-        }
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < kHcPer; ++k) any |= c[k].x > lo;
-        if (!__any_sync(0xffffffffu, any)) continue;
-        const float st = (float)p.stride[lvl];
-        const float4* dp = reinterpret_cast<const float4*>(p.dist[lvl]) + (size_t)b * HW;
-#pragma unroll
-        for (int k = 0; k < kHcPer; ++k) {
-            const float logit = c[k].x;
-            const int bidx = (int)c[k].y;
-            const int la = la0 + k * 256;
-            bool is_cand = false;
-            float score = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-            if (logit > lo) {
-                score = 1.f / (1.f + __expf(-logit));
-                if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
-                    const float4 d = __ldg(dp + la);
-                    const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f;
-                    const float u1 = ax - d.x, v1 = ay - d.y, u2 = ax + d.z, v2 = ay + d.w;
-                    const float cx = (u1 + u2) / 2.f * st, cy = (v1 + v2) / 2.f * st, bw = (u2 - u1) * st, bh = (v2 - v1) * st;
-                    const float hw = bw / 2.f, hh = bh / 2.f;
-                    x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
-                    is_cand = true;
-                }
+    for (int k = 0; k < kHcPer; ++k) {
+        const float logit = c[k].x;
+        const int bidx = (int)c[k].y;
+        const int la = la0 + k * 256;
+        bool is_cand = false;
+        float score = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+        if (logit > lo) {
+            score = 1.f / (1.f + __expf(-logit));
+            if (score > p.conf && (!p.cmask || p.cmask[bidx])) {
+                const float4 d = __ldg(dp + la);
+                const float ax = (float)(la % W) + 0.5f, ay = (float)(la / W) + 0.5f;
+                const float u1 = ax - d.x, v1 = ay - d.y, u2 = ax + d.z, v2 = ay + d.w;
+                const float cx = (u1 + u2) / 2.f * st, cy = (v1 + v2) / 2.f * st, bw = (u2 - u1) * st, bh = (v2 - v1) * st;
+                const float hw = bw / 2.f, hh = bh / 2.f;
+                x1 = cx - hw; y1 = cy - hh; x2 = cx + hw; y2 = cy + hh;
+                is_cand = true;
             }
-            const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
-            if (!ball) continue;
-            int base = 0;
-            const int leader = __ffs(ball) - 1;
-            if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (is_cand) {
-                const int pos = base + __popc(ball & ((1u << lane) - 1));
-                if (pos < p.cand_cap) {
-                    float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
-                    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = score; o[5] = (float)bidx;
-                    p.cand_idx[(size_t)b * p.cand_cap + pos] = p.a_off[lvl] + la;
-                }
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+        if (!ball) continue;
+        int base = 0;
+        const int leader = __ffs(ball) - 1;
+        if (lane == leader) base = atomicAdd(p.cand_count + b, __popc(ball));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (is_cand) {
+            const int pos = base + __popc(ball & ((1u << lane) - 1));
+            if (pos < p.cand_cap) {
+                float* o = p.cand + ((size_t)b * p.cand_cap + pos) * 6;
+                o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2; o[4] = score; o[5] = (float)bidx;
+                p.cand_idx[(size_t)b * p.cand_cap + pos] = p.a_off[lvl] + la;
             }
         }
     }
@@ -621,9 +616,9 @@ extern "C" int b2_candidates_from_head(const float* const* level_dist, const flo
     p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count; p.cand_cap = cand_cap;
     cudaStream_t st = (cudaStream_t)stream;
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
-    // one wave: 6 resident blocks of 256 threads per SM (40 registers), split evenly over the images
-    const int gx = std::max(1, std::min(p.blk_off[n_levels], (b2_num_sms() * 6) / B));
-    head_candidates_kernel<<<dim3(gx, B), 256, 0, st>>>(p);
+    // (one block per chunk: a one-wave grid walking several chunks per block, and 16-byte loads of record pairs, both measured
+    //  SLOWER at the bench size -- 32-33 us against 26.5 us, tools/hbm_probe.py)
+    head_candidates_kernel<<<dim3(p.blk_off[n_levels], B), 256, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;
