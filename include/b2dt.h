@@ -256,6 +256,22 @@ int b2_kf_update(int kind, float* mean, float* cov, const float* meas, const uin
 int b2_kf_gating(int kind, const float* mean, const float* cov, int N, const float* meas, int M,
                  int only_position, int metric, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Association of the upstream tracker plug-in (ByteTrack / BoT-SORT), batched over S independent problems (one per video
+ * stream and association stage).  Problem s has na[s] <= n_max rows (tracks) and nb[s] <= m_max columns (detections);
+ * na / nb NULL: every problem is n_max x m_max.  boxes: [S][n_max][4] / [S][m_max][4] xyxy fp32 (16-byte aligned),
+ * cost: [S][n_max][m_max] fp32 (entries outside a problem's na x nb corner are not touched).
+ * ---------------------------------------------------------------------------------------------- */
+/* matching.iou_distance (ultralytics/trackers/utils/matching.py:66-113: 1 - bbox_ioa(a, b, iou=True), utils/metrics.py:19-52)
+ * and, when scores_b [S][m_max] is given, matching.fuse_score (:135-157): 1 - (1 - cost) * score -- float32, reference op order */
+int b2_iou_cost(const float* boxes_a, const float* boxes_b, const float* scores_b, const int32_t* na, const int32_t* nb,
+                int S, int n_max, int m_max, float* cost, void* stream);
+/* matching.linear_assignment(cost, thresh) on its default branch (matching.py:20-63: lap.lapjv(cost, extend_cost=True,
+ * cost_limit=thresh)): x_out [S][n_max] = matched column of each row or -1, y_out [S][m_max] = matched row of each column or -1.
+ * Exact optimum (float64 shortest augmenting paths), one CTA per problem. */
+int b2_linear_assignment(const float* cost, const int32_t* na, const int32_t* nb, int S, int n_max, int m_max, float thresh,
+                         int32_t* x_out, int32_t* y_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

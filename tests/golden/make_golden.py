@@ -12,6 +12,7 @@ Files written:
   kf_ultra.npz                                KalmanFilterXYAH / XYWH initiate/predict/update/gating
   nms_cases.npz                               non_max_suppression, both branches (TorchNMS.nms / torchvision)
   net_n_p2_small.npz                          yolov8n-p2 head maps + decoded tensor on a 64x96 input
+  bytetrack.npz                               BYTETracker.update over a scripted 90-frame scene (two parameterisations) + linear_assignment cases
   predict_n_p2.npz / predict_s_p2.npz         YOLO(cfg).predict on 512x640 (and 500x640) frames + the NMS candidate lists
 """
 import contextlib
@@ -350,6 +351,56 @@ def gold_motion_multi():
     np.savez_compressed(os.path.join(HERE, "motion_multi.npz"), rows=np.array(rows), counts=np.array(counts), stats=np.array(stats),
                         dets=flat, ndets=np.array([len(d) for d in script]))
     print("motion_multi", np.array(rows).shape, "stats", stats, "max tracks", max(counts))
+
+
+def gold_bytetrack():
+    """The reference's BYTETracker (ultralytics/trackers/byte_tracker.py) over the scripted scene, default bytetrack.yaml values and a
+    second parameterisation (no score fusion, short buffer).  `lap` (gatagat/lap) is not installed here: matching.py's import
+    is satisfied by a module whose lapjv is oracle.byte_tracker.lapjv (the restated extended-matrix problem solved by scipy)."""
+    import types
+
+    from golden_common import bytetrack_script
+    from oracle import byte_tracker as obt
+
+    lap = types.ModuleType("lap")
+    lap.__version__ = "0.5.12"
+    lap.lapjv = obt.lapjv
+    sys.modules["lap"] = lap
+    from ultralytics.engine.results import Boxes
+    from ultralytics.trackers.byte_tracker import BYTETracker
+    from ultralytics.utils import IterableSimpleNamespace
+
+    out = {}
+    frames = bytetrack_script()
+    for tag, args in (("default", dict(track_high_thresh=0.25, track_low_thresh=0.1, new_track_thresh=0.25, track_buffer=30, match_thresh=0.8, fuse_score=True)),
+                      ("nofuse", dict(track_high_thresh=0.4, track_low_thresh=0.15, new_track_thresh=0.5, track_buffer=8, match_thresh=0.7, fuse_score=False))):
+        trk = BYTETracker(IterableSimpleNamespace(tracker_type="bytetrack", **args), frame_rate=30)
+        rows, counts, states = [], [], []
+        for f, d in enumerate(frames):
+            r = trk.update(Boxes(d, (512, 640)).numpy())
+            r = np.asarray(r, dtype=np.float32).reshape(-1, 8)
+            rows.append(r); counts.append(len(r))
+            # filter state of every live track, by id (means / covariances are float64 in the reference)
+            st = sorted(((t.track_id, t.state, t.mean, t.covariance) for t in trk.tracked_stracks + trk.lost_stracks), key=lambda q: q[0])
+            states.append((np.array([q[0] for q in st]), np.array([q[1] for q in st]), np.array([q[2] for q in st], dtype=np.float64).reshape(-1, 8),
+                           np.array([q[3] for q in st], dtype=np.float64).reshape(-1, 8, 8)))
+        out[f"{tag}_rows"] = np.concatenate(rows) if rows else np.zeros((0, 8), np.float32)
+        out[f"{tag}_counts"] = np.array(counts)
+        out[f"{tag}_ids"] = np.concatenate([s[0] for s in states]); out[f"{tag}_nstate"] = np.array([len(s[0]) for s in states])
+        out[f"{tag}_state"] = np.concatenate([s[1] for s in states]); out[f"{tag}_mean"] = np.concatenate([s[2] for s in states])
+        out[f"{tag}_cov_diag"] = np.concatenate([np.diagonal(s[3], axis1=1, axis2=2) for s in states])
+    # linear_assignment known answers on random rectangular costs (the default lap branch through the same module)
+    from ultralytics.trackers.utils import matching
+
+    g = np.random.default_rng(3)
+    for k, (n, m, th) in enumerate([(5, 7, 0.8), (12, 9, 0.5), (1, 6, 0.7), (20, 20, 0.9), (30, 4, 0.6)]):
+        c = g.uniform(0, 1, (n, m)).astype(np.float32)
+        mt, ua, ub = matching.linear_assignment(c, th)
+        x = np.full(n, -1); 
+        for i, j in mt:
+            x[i] = j
+        out[f"lap{k}_cost"] = c; out[f"lap{k}_x"] = x; out[f"lap{k}_thresh"] = np.float32(th)
+    np.savez_compressed(os.path.join(HERE, "bytetrack.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -141,3 +141,41 @@ def detection_set_report(dets, ref, cand, conf, iou_thres, seed=0, frame_hw=None
     n_strict = int(sum(always[k] for k in ref_idx))
     return {"n_ref": len(ref), "n_det": len(dets), "n_ref_strict": n_strict, "n_ref_in_band": len(ref) - n_strict,
             "n_cand": m, "n_cand_in_band": int((~always & ~never).sum()), "errors": errors}
+
+
+def bytetrack_script(n_frames=90, n_targets=14, seed=5, hw=(512, 640)):
+    """Scripted detections for the ByteTrack goldens: targets on straight lines with jitter, per-frame scores that wander across
+    the high / low thresholds (0.25 / 0.1), misses (a target undetected for a few frames -> lost -> re-found), crossings
+    (overlapping boxes) and clutter.  Returns a list of (n, 6) float32 arrays [x1, y1, x2, y2, conf, cls] per frame."""
+    g = np.random.default_rng(seed)
+    H, W = hw
+    pos = np.stack([g.uniform(40, W - 40, n_targets), g.uniform(40, H - 40, n_targets)], 1)
+    vel = g.normal(0, 2.0, (n_targets, 2))
+    size = g.uniform(8, 40, (n_targets, 2))
+    base = g.uniform(0.2, 0.9, n_targets)
+    cls = g.integers(0, 3, n_targets)
+    off_until = np.zeros(n_targets, int)
+    frames = []
+    for f in range(n_frames):
+        pos += vel
+        for k in range(n_targets):
+            for a, lim in ((0, W), (1, H)):
+                if pos[k, a] < 20 or pos[k, a] > lim - 20:
+                    vel[k, a] = -vel[k, a]
+        rows = []
+        for k in range(n_targets):
+            if f >= off_until[k] and g.random() < 0.04:
+                off_until[k] = f + int(g.integers(2, 12))
+            if f < off_until[k]:
+                continue
+            c = pos[k] + g.normal(0, 0.6, 2)
+            s = size[k] * (1 + g.normal(0, 0.03, 2))
+            conf = float(np.clip(base[k] + g.normal(0, 0.12), 0.02, 0.99))
+            rows.append([c[0] - s[0] / 2, c[1] - s[1] / 2, c[0] + s[0] / 2, c[1] + s[1] / 2, conf, cls[k]])
+        for _ in range(int(g.integers(0, 4))):
+            c = np.array([g.uniform(10, W - 10), g.uniform(10, H - 10)])
+            s = g.uniform(6, 30, 2)
+            rows.append([c[0] - s[0] / 2, c[1] - s[1] / 2, c[0] + s[0] / 2, c[1] + s[1] / 2, float(g.uniform(0.05, 0.6)), int(g.integers(0, 3))])
+        arr = np.asarray(rows, dtype=np.float32).reshape(-1, 6)
+        frames.append(arr[g.permutation(len(arr))])
+    return frames

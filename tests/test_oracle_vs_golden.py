@@ -310,3 +310,62 @@ def test_bf16_rounding_points_keep_the_reference_detection_set(name, gfile):
         assert not rep["errors"], (b, rep)
         strict += rep["n_ref_strict"]; total += rep["n_ref"]
     assert strict >= 0.6 * total, (strict, total)            # the band must not swallow the comparison
+
+
+BYTE_PARAMS = {"default": {}, "nofuse": dict(track_high_thresh=0.4, track_low_thresh=0.15, new_track_thresh=0.5, track_buffer=8,
+                                             match_thresh=0.7, fuse_score=False)}
+
+
+def _xywh(d):
+    return np.stack([(d[:, 0] + d[:, 2]) / 2, (d[:, 1] + d[:, 3]) / 2, d[:, 2] - d[:, 0], d[:, 3] - d[:, 1]], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("tag", ["default", "nofuse"])
+def test_bytetrack_oracle_matches_reference(tag):
+    """oracle.byte_tracker.BYTETracker against the reference's BYTETracker.update (ultralytics/trackers/byte_tracker.py) over the
+    scripted 90-frame scene (misses, low-score boxes, clutter, crossings): the same rows every frame -- track id, score, class
+    and detection index bit-exact, boxes to float32 rounding -- and the same filter state for every tracked / lost track."""
+    from golden_common import bytetrack_script
+    from oracle import byte_tracker as obt
+
+    g = _load("bytetrack.npz")
+    t = obt.BYTETracker(**BYTE_PARAMS[tag])
+    off = so = 0
+    assert g[f"{tag}_rows"][:, 4].max() > 30 and (g[f"{tag}_state"] == obt.LOST).sum() > 50         # the script exercises lost / re-found tracks
+    for f, d in enumerate(bytetrack_script()):
+        r = t.update(_xywh(d), d[:, 4], d[:, 5]).reshape(-1, 8)
+        n = int(g[f"{tag}_counts"][f])
+        ref = g[f"{tag}_rows"][off:off + n]
+        off += n
+        assert len(r) == n, (f, len(r), n)
+        assert np.array_equal(r[:, 4:], ref[:, 4:]), f
+        np.testing.assert_allclose(r[:, :4], ref[:, :4], rtol=0, atol=1e-4)
+        st = sorted(((q.track_id, q.state, q.mean, np.diag(q.covariance)) for q in t.tracked_stracks + t.lost_stracks), key=lambda q: q[0])
+        ns = int(g[f"{tag}_nstate"][f])
+        assert [q[0] for q in st] == list(g[f"{tag}_ids"][so:so + ns]) and [q[1] for q in st] == list(g[f"{tag}_state"][so:so + ns]), f
+        if ns:
+            np.testing.assert_allclose(np.array([q[2] for q in st]), g[f"{tag}_mean"][so:so + ns], rtol=1e-8, atol=1e-5)
+            np.testing.assert_allclose(np.array([q[3] for q in st]), g[f"{tag}_cov_diag"][so:so + ns], rtol=1e-7, atol=1e-9)
+        so += ns
+
+
+def test_linear_assignment_oracle_cases():
+    """matching.linear_assignment(cost, thresh) through the reference module (its default lap branch, `lap` = the restated
+    extended-matrix problem) on rectangular random costs; every match respects the limit and the restated optimum is not beaten by
+    a brute-force search on the small case."""
+    import itertools
+
+    from oracle import byte_tracker as obt
+
+    g = _load("bytetrack.npz")
+    for k in range(5):
+        c, x, th = g[f"lap{k}_cost"], g[f"lap{k}_x"], float(g[f"lap{k}_thresh"])
+        _, x2, _ = obt.lapjv(c, extend_cost=True, cost_limit=th)
+        assert np.array_equal(x, x2)
+        assert all(c[i, j] <= th for i, j in enumerate(x) if j >= 0)
+    c, x, th = g["lap0_cost"], g["lap0_x"], float(g["lap0_thresh"])         # 5 x 7: brute force over partial matchings
+    n, m = c.shape
+    best = min(sum((c[i, j] - th) for i, j in enumerate(p) if j >= 0)
+               for p in itertools.product(range(-1, m), repeat=n) if len({j for j in p if j >= 0}) == sum(j >= 0 for j in p))
+    got = sum((c[i, j] - th) for i, j in enumerate(x) if j >= 0)
+    assert abs(got - best) < 1e-9

@@ -1,0 +1,385 @@
+"""Upstream tracker plug-in (ByteTrack) over the B200 kernels: mirror of ``ultralytics/trackers/byte_tracker.py`` (STrack
+:14-237, BYTETracker :240-485), ``trackers/utils/matching.py`` (linear_assignment :20-63, iou_distance :66-113, fuse_score
+:135-157) and the ``trackers/track.py`` callback contract (:72-102: ``tracker.update(boxes) -> (k, 8)`` rows
+``[x1, y1, x2, y2, track_id, score, cls, idx]``, ``Results.update(boxes=rows[:, :-1])``).
+
+Same names, arguments and control flow as the reference; the numeric work of a frame runs on the GPU through the C ABI:
+``b2_kf_predict`` (STrack.multi_predict), ``b2_iou_cost`` (iou_distance + fuse_score), ``b2_linear_assignment`` (the
+``lap.lapjv(extend_cost=True, cost_limit=thresh)`` branch -- an exact float64 shortest-augmenting-path solver, no ``lap``
+dependency), ``b2_kf_update`` / ``b2_kf_initiate`` batched over the matches of a stage (the reference updates matched tracks one
+by one; the stages only ever look at tracks that were NOT matched before, so batching per stage is the same computation).
+Track state is float32 on the device (float64 numpy in the reference).  No CPU fallback: every call needs the CUDA library.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import _lib
+from .kalman_filter import KalmanFilterXYAH
+
+
+class TrackState:
+    """basetrack.py:9-26."""
+    New, Tracked, Lost, Removed = 0, 1, 2, 3
+
+
+# ---------------------------------------------------------------------------------------------------
+# matching (trackers/utils/matching.py)
+# ---------------------------------------------------------------------------------------------------
+def _boxes_of(tracks):
+    if len(tracks) and isinstance(tracks[0], np.ndarray):
+        return np.ascontiguousarray(tracks, dtype=np.float32).reshape(-1, 4)
+    return np.ascontiguousarray([t.xyxy for t in tracks], dtype=np.float32).reshape(-1, 4)
+
+
+def iou_distance(atracks, btracks, _scores=None):
+    """matching.py:66-113: 1 - IoU cost matrix (N, M), float32.  Lists of STrack or of xyxy arrays."""
+    import torch
+
+    n, m = len(atracks), len(btracks)
+    if n == 0 or m == 0:
+        return np.zeros((n, m), dtype=np.float32)
+    _lib.require_cuda()
+    lib = _lib.load()
+    a = torch.as_tensor(_boxes_of(atracks), device="cuda")
+    b = torch.as_tensor(_boxes_of(btracks), device="cuda")
+    sc = None if _scores is None else torch.as_tensor(np.ascontiguousarray(_scores, np.float32), device="cuda")
+    cost = torch.empty((n, m), dtype=torch.float32, device="cuda")
+    _lib.check(lib.b2_iou_cost(_lib.ptr(a), _lib.ptr(b), _lib.ptr(sc), None, None, 1, n, m, _lib.ptr(cost), _lib.stream_ptr()))
+    return cost.cpu().numpy()
+
+
+def fuse_score(cost_matrix, detections):
+    """matching.py:135-157 (host form, for callers that hold a cost matrix already; BYTETracker fuses inside b2_iou_cost)."""
+    if cost_matrix.size == 0:
+        return cost_matrix
+    det_scores = np.array([d.score for d in detections], dtype=np.float32)[None].repeat(cost_matrix.shape[0], axis=0)
+    return 1 - (1 - cost_matrix) * det_scores
+
+
+def linear_assignment(cost_matrix, thresh, use_lap=True):
+    """matching.py:20-63 -> (matches [[row, col], ...], unmatched rows, unmatched cols).  Both of the reference's branches
+    return the optimum of the same thresholded problem; one exact GPU solver serves both."""
+    import torch
+
+    cost_matrix = np.asarray(cost_matrix)
+    if cost_matrix.size == 0:
+        return np.empty((0, 2), dtype=int), tuple(range(cost_matrix.shape[0])), tuple(range(cost_matrix.shape[1]))
+    x, y = linear_assignment_device(torch.as_tensor(np.ascontiguousarray(cost_matrix, np.float32), device="cuda")[None], thresh)
+    x, y = x[0].cpu().numpy(), y[0].cpu().numpy()
+    matches = [[ix, int(mx)] for ix, mx in enumerate(x) if mx >= 0]
+    return matches, np.where(x < 0)[0], np.where(y < 0)[0]
+
+
+def linear_assignment_device(cost, thresh, na=None, nb=None):
+    """Batched form: cost CUDA float32 [S][n_max][m_max] (problem s uses its na[s] x nb[s] corner) -> (x [S][n_max], y [S][m_max])
+    int32 CUDA tensors, -1 = unmatched."""
+    import torch
+
+    _lib.require_cuda()
+    lib = _lib.load()
+    S, n, m = cost.shape
+    x = torch.empty((S, n), dtype=torch.int32, device="cuda")
+    y = torch.empty((S, m), dtype=torch.int32, device="cuda")
+    _lib.check(lib.b2_linear_assignment(_lib.ptr(cost.contiguous()), _lib.ptr(na), _lib.ptr(nb), S, n, m, float(thresh), _lib.ptr(x), _lib.ptr(y),
+                                        _lib.stream_ptr()))
+    return x, y
+
+
+# ---------------------------------------------------------------------------------------------------
+# STrack / BYTETracker
+# ---------------------------------------------------------------------------------------------------
+class STrack:
+    """byte_tracker.py:14-237 for axis-aligned boxes.  mean (8,) / covariance (8, 8) are numpy copies of the device state."""
+
+    shared_kalman = None
+    _count = 0
+
+    def __init__(self, xywh, score, cls):
+        assert len(xywh) in {5, 6}, f"expected 5 or 6 values but got {len(xywh)}"
+        x, y, w, h = (np.float32(v) for v in xywh[:4])
+        self._tlwh = np.asarray([x - w / 2, y - h / 2, w, h], dtype=np.float32)
+        self.kalman_filter = None
+        self.mean, self.covariance = None, None
+        self.is_activated = False
+        self.score, self.cls, self.idx = score, cls, xywh[-1]
+        self.tracklet_len = 0
+        self.angle = xywh[4] if len(xywh) == 6 else None
+        self.track_id = 0
+        self.state = TrackState.New
+        self.start_frame = self.frame_id = 0
+
+    @staticmethod
+    def next_id():
+        STrack._count += 1
+        return STrack._count
+
+    @staticmethod
+    def reset_id():
+        STrack._count = 0
+
+    @property
+    def end_frame(self):
+        return self.frame_id
+
+    def mark_lost(self):
+        self.state = TrackState.Lost
+
+    def mark_removed(self):
+        self.state = TrackState.Removed
+
+    @staticmethod
+    def multi_predict(stracks):
+        """:94-107 -- one b2_kf_predict launch for the pool."""
+        if len(stracks) <= 0:
+            return
+        mm = np.asarray([st.mean.copy() for st in stracks])
+        mc = np.asarray([st.covariance for st in stracks])
+        for i, st in enumerate(stracks):
+            if st.state != TrackState.Tracked:
+                mm[i][7] = 0
+        mm, mc = STrack.shared_kalman.multi_predict(mm, mc)
+        for i, st in enumerate(stracks):
+            st.mean, st.covariance = mm[i], mc[i]
+
+    # the three state changes of the reference take the Kalman result computed for the whole stage (see BYTETracker._apply)
+    def activate(self, kalman_filter, frame_id, mean, covariance):
+        self.kalman_filter = kalman_filter
+        self.track_id = self.next_id()
+        self.mean, self.covariance = mean, covariance
+        self.tracklet_len = 0
+        self.state = TrackState.Tracked
+        if frame_id == 1:
+            self.is_activated = True
+        self.frame_id = self.start_frame = frame_id
+
+    def re_activate(self, new_track, frame_id, mean, covariance, new_id=False):
+        self.mean, self.covariance = mean, covariance
+        self.tracklet_len = 0
+        self.state = TrackState.Tracked
+        self.is_activated = True
+        self.frame_id = frame_id
+        if new_id:
+            self.track_id = self.next_id()
+        self.score, self.cls, self.angle, self.idx = new_track.score, new_track.cls, new_track.angle, new_track.idx
+
+    def update(self, new_track, frame_id, mean, covariance):
+        self.frame_id = frame_id
+        self.tracklet_len += 1
+        self.mean, self.covariance = mean, covariance
+        self.state = TrackState.Tracked
+        self.is_activated = True
+        self.score, self.cls, self.angle, self.idx = new_track.score, new_track.cls, new_track.angle, new_track.idx
+
+    @property
+    def tlwh(self):
+        if self.mean is None:
+            return self._tlwh.copy()
+        ret = self.mean[:4].copy()
+        ret[2] *= ret[3]
+        ret[:2] -= ret[2:] / 2
+        return ret
+
+    @property
+    def xyxy(self):
+        ret = self.tlwh.copy()
+        ret[2:] += ret[:2]
+        return ret
+
+    @staticmethod
+    def tlwh_to_xyah(tlwh):
+        ret = np.asarray(tlwh).copy()
+        ret[:2] += ret[2:] / 2
+        ret[2] /= ret[3]
+        return ret
+
+    def convert_coords(self, tlwh):
+        return self.tlwh_to_xyah(tlwh)
+
+    @property
+    def xywh(self):
+        ret = np.asarray(self.tlwh).copy()
+        ret[:2] += ret[2:] / 2
+        return ret
+
+    @property
+    def result(self):
+        return self.xyxy.tolist() + [self.track_id, self.score, self.cls, self.idx]
+
+    def __repr__(self):
+        return f"OT_{self.track_id}_({self.start_frame}-{self.end_frame})"
+
+
+DEFAULT_ARGS = dict(tracker_type="bytetrack", track_high_thresh=0.25, track_low_thresh=0.1, new_track_thresh=0.25, track_buffer=30,
+                    match_thresh=0.8, fuse_score=True)          # ultralytics/cfg/trackers/bytetrack.yaml
+
+
+class BYTETracker:
+    """byte_tracker.py:240-485.  ``args``: a namespace / dict with the bytetrack.yaml keys (None: the yaml's defaults)."""
+
+    def __init__(self, args=None, frame_rate=30):
+        if args is None:
+            args = DEFAULT_ARGS
+        if isinstance(args, dict):
+            args = SimpleNamespace(**{**DEFAULT_ARGS, **args})
+        self.tracked_stracks, self.lost_stracks, self.removed_stracks = [], [], []
+        self.frame_id = 0
+        self.args = args
+        self.max_time_lost = int(frame_rate / 30.0 * args.track_buffer)
+        self.kalman_filter = self.get_kalmanfilter()
+        STrack.shared_kalman = self.kalman_filter
+        self.reset_id()
+
+    def get_kalmanfilter(self):
+        return KalmanFilterXYAH()
+
+    def init_track(self, results, img=None):
+        if len(results) == 0:
+            return []
+        bboxes = np.asarray(results.xywh, dtype=np.float32)
+        bboxes = np.concatenate([bboxes, np.arange(len(bboxes), dtype=np.float32).reshape(-1, 1)], axis=-1)
+        return [STrack(xywh, s, c) for (xywh, s, c) in zip(bboxes, np.asarray(results.conf), np.asarray(results.cls))]
+
+    def get_dists(self, tracks, detections):
+        """iou_distance (+ fuse_score) in one launch."""
+        return iou_distance(tracks, detections, [d.score for d in detections] if self.args.fuse_score else None)
+
+    def multi_predict(self, tracks):
+        STrack.multi_predict(tracks)
+
+    @staticmethod
+    def reset_id():
+        STrack.reset_id()
+
+    def reset(self):
+        self.tracked_stracks, self.lost_stracks, self.removed_stracks = [], [], []
+        self.frame_id = 0
+        self.kalman_filter = self.get_kalmanfilter()
+        STrack.shared_kalman = self.kalman_filter
+        self.reset_id()
+
+    def _apply(self, pairs, activated, refind):
+        """KalmanFilterXYAH.update for every (track, detection) pair of one association stage in ONE launch, then the reference's
+        per-pair state change (update for tracked tracks, re_activate for lost ones: :346-353, :361-368, :380-382)."""
+        if not pairs:
+            return
+        mm = np.asarray([t.mean for t, _ in pairs])
+        mc = np.asarray([t.covariance for t, _ in pairs])
+        zz = np.asarray([t.convert_coords(d.tlwh) for t, d in pairs], dtype=np.float32)
+        mm, mc = self.kalman_filter.update(mm, mc, zz)
+        for k, (t, d) in enumerate(pairs):
+            if t.state == TrackState.Tracked:
+                t.update(d, self.frame_id, mm[k], mc[k])
+                activated.append(t)
+            else:
+                t.re_activate(d, self.frame_id, mm[k], mc[k], new_id=False)
+                refind.append(t)
+
+    def update(self, results, img=None, feats=None):
+        """:299-410.  results: a ``Boxes``-like object on the host (``.conf``, ``.cls``, ``.xywh``, boolean-mask indexing)."""
+        self.frame_id += 1
+        activated_stracks, refind_stracks, lost_stracks, removed_stracks = [], [], [], []
+        scores = np.asarray(results.conf)
+        remain_inds = scores >= self.args.track_high_thresh
+        inds_second = (scores > self.args.track_low_thresh) & (scores < self.args.track_high_thresh)
+        results_second = results[inds_second]
+        results = results[remain_inds]
+        detections = self.init_track(results)
+        unconfirmed = [t for t in self.tracked_stracks if not t.is_activated]
+        tracked_stracks = [t for t in self.tracked_stracks if t.is_activated]
+        # first association, high-score boxes
+        strack_pool = self.joint_stracks(tracked_stracks, self.lost_stracks)
+        self.multi_predict(strack_pool)
+        dists = self.get_dists(strack_pool, detections)
+        matches, u_track, u_detection = linear_assignment(dists, thresh=self.args.match_thresh)
+        self._apply([(strack_pool[it], detections[idt]) for it, idt in matches], activated_stracks, refind_stracks)
+        # second association, low-score boxes against the still-unmatched tracked tracks
+        detections_second = self.init_track(results_second)
+        r_tracked_stracks = [strack_pool[i] for i in u_track if strack_pool[i].state == TrackState.Tracked]
+        dists = iou_distance(r_tracked_stracks, detections_second)
+        matches, u_track, _ = linear_assignment(dists, thresh=0.5)
+        self._apply([(r_tracked_stracks[it], detections_second[idt]) for it, idt in matches], activated_stracks, refind_stracks)
+        for it in u_track:
+            track = r_tracked_stracks[it]
+            if track.state != TrackState.Lost:
+                track.mark_lost()
+                lost_stracks.append(track)
+        # unconfirmed tracks (one frame old) against the remaining high-score boxes
+        detections = [detections[i] for i in u_detection]
+        dists = self.get_dists(unconfirmed, detections)
+        matches, u_unconfirmed, u_detection = linear_assignment(dists, thresh=0.7)
+        self._apply([(unconfirmed[it], detections[idt]) for it, idt in matches], activated_stracks, refind_stracks)
+        for it in u_unconfirmed:
+            unconfirmed[it].mark_removed()
+            removed_stracks.append(unconfirmed[it])
+        # new tracks: one b2_kf_initiate launch
+        new = [detections[i] for i in u_detection if detections[i].score >= self.args.new_track_thresh]
+        if new:
+            zz = np.asarray([t.convert_coords(t._tlwh) for t in new], dtype=np.float32)
+            mm, mc = self.kalman_filter.initiate(zz)
+            for k, t in enumerate(new):
+                t.activate(self.kalman_filter, self.frame_id, mm[k], mc[k])
+                activated_stracks.append(t)
+        for track in self.lost_stracks:
+            if self.frame_id - track.end_frame > self.max_time_lost:
+                track.mark_removed()
+                removed_stracks.append(track)
+        self.tracked_stracks = [t for t in self.tracked_stracks if t.state == TrackState.Tracked]
+        self.tracked_stracks = self.joint_stracks(self.tracked_stracks, activated_stracks)
+        self.tracked_stracks = self.joint_stracks(self.tracked_stracks, refind_stracks)
+        self.lost_stracks = self.sub_stracks(self.lost_stracks, self.tracked_stracks)
+        self.lost_stracks.extend(lost_stracks)
+        self.lost_stracks = self.sub_stracks(self.lost_stracks, self.removed_stracks)
+        self.tracked_stracks, self.lost_stracks = self.remove_duplicate_stracks(self.tracked_stracks, self.lost_stracks)
+        self.removed_stracks.extend(removed_stracks)
+        if len(self.removed_stracks) > 1000:
+            self.removed_stracks = self.removed_stracks[-999:]
+        return np.asarray([x.result for x in self.tracked_stracks if x.is_activated], dtype=np.float32)
+
+    @staticmethod
+    def joint_stracks(tlista, tlistb):
+        exists, res = {}, []
+        for t in tlista:
+            exists[t.track_id] = 1
+            res.append(t)
+        for t in tlistb:
+            if not exists.get(t.track_id, 0):
+                exists[t.track_id] = 1
+                res.append(t)
+        return res
+
+    @staticmethod
+    def sub_stracks(tlista, tlistb):
+        ids = {t.track_id for t in tlistb}
+        return [t for t in tlista if t.track_id not in ids]
+
+    @staticmethod
+    def remove_duplicate_stracks(stracksa, stracksb):
+        pdist = iou_distance(stracksa, stracksb)
+        dupa, dupb = [], []
+        for p, q in zip(*np.where(pdist < 0.15)):
+            timep = stracksa[p].frame_id - stracksa[p].start_frame
+            timeq = stracksb[q].frame_id - stracksb[q].start_frame
+            if timep > timeq:
+                dupb.append(q)
+            else:
+                dupa.append(p)
+        return [t for i, t in enumerate(stracksa) if i not in dupa], [t for i, t in enumerate(stracksb) if i not in dupb]
+
+
+# ---------------------------------------------------------------------------------------------------
+# trackers/track.py:72-102: attach ids to a list of Results
+# ---------------------------------------------------------------------------------------------------
+def update_results(trackers, results, is_stream=True):
+    """on_predict_postprocess_end: results[i].boxes -> tracker.update -> results[i] = results[i][idx] with boxes replaced by the
+    (k, 7) track rows [x1, y1, x2, y2, id, conf, cls].  Results without tracks are left untouched, as in the reference."""
+    for i, result in enumerate(results):
+        tracker = trackers[i if is_stream else 0]
+        det = result.boxes.cpu().numpy()
+        tracks = tracker.update(det, getattr(result, "orig_img", None))
+        if len(tracks) == 0:
+            continue
+        result.update(boxes=tracks[:, :-1])
+    return results

@@ -323,6 +323,27 @@ class YOLO:
                 print(f"{r.orig_shape[0]}x{r.orig_shape[1]} {r.verbose()}{r.speed['inference']:.1f}ms")
         return iter(results) if stream else results
 
+    def track(self, source=None, stream=False, persist=False, **kwargs):
+        """engine/model.py:559-591 + trackers/track.py: predict with conf 0.1 by default (ByteTrack wants the low-confidence boxes),
+        then the tracker's update attaches ids (``Results.boxes.id``).  ``tracker``: 'bytetrack.yaml' or a dict of its keys.
+        A list of frames is one video, walked in order by ONE tracker (the reference's non-stream datasets); ``persist=True`` keeps
+        the tracker between calls."""
+        from . import byte_tracker
+
+        tracker = kwargs.pop("tracker", "bytetrack.yaml")
+        if isinstance(tracker, str):
+            if "botsort" in tracker:
+                raise NotImplementedError("BoT-SORT (GMC + ReID) is not on the hot path; its Kalman filter is b200dt.kalman_filter.KalmanFilterXYWH")
+            if "bytetrack" not in tracker:
+                raise AssertionError(f"Only 'bytetrack' and 'botsort' are supported for now, but got '{tracker}'")
+            tracker = None
+        kwargs["conf"] = kwargs.get("conf") or 0.1
+        if not (persist and getattr(self, "trackers", None)):
+            self.trackers = [byte_tracker.BYTETracker(tracker, frame_rate=30)]
+        results = list(self.predict(source, False, **kwargs))
+        byte_tracker.update_results(self.trackers, results, is_stream=False)
+        return iter(results) if stream else results
+
     def fuse(self):
         return self          # BN is always folded at lowering time (engine.lower)
 
