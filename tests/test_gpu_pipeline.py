@@ -93,3 +93,59 @@ def test_pipeline_step_equals_predict_plus_tracker_update_per_frame():
             assert [g["track_id"] for g in got] == [w["track_id"] for w in want]
             for g, w in zip(got, want):
                 np.testing.assert_allclose(g["bbox"], w["bbox"], rtol=1e-5, atol=1e-3)
+
+
+def test_yolo_loads_a_pt_checkpoint(tmp_path):
+    """YOLO('best.pt') (engine/model.py:_load -> nn/tasks.py:1487-1521): a checkpoint pickled from classes of a package called
+    `ultralytics` (a stand-in module tree built here from the synthetic state_dict: the reference package does not exist on the GPU
+    box) is read without that package, and predicts exactly what YOLO(yaml, state_dict=...) predicts."""
+    import sys
+    import types
+
+    import torch
+
+    from b200dt import cfg, synth, weights
+    from b200dt.predictor import YOLO
+
+    spec = cfg.resolve("yolov8n-p2.yaml", nc=80)
+    sd = weights.synthetic_state_dict(spec, seed=0)
+    fake = types.ModuleType("ultralytics"); fake_nn = types.ModuleType("ultralytics.nn"); fake_tasks = types.ModuleType("ultralytics.nn.tasks")
+
+    class Node(torch.nn.Module):
+        pass
+
+    class DetectionModel(torch.nn.Module):
+        pass
+
+    Node.__module__ = DetectionModel.__module__ = "ultralytics.nn.tasks"
+    Node.__qualname__, DetectionModel.__qualname__ = "Node", "DetectionModel"
+    fake_tasks.Node, fake_tasks.DetectionModel = Node, DetectionModel
+    root = DetectionModel()
+    for k, v in sd.items():
+        *path, leaf = k.split(".")
+        m = root
+        for p in path:
+            if p not in m._modules:
+                m.add_module(p, Node())
+            m = m._modules[p]
+        t = torch.as_tensor(np.asarray(v))
+        if leaf in ("running_mean", "running_var", "num_batches_tracked"):
+            m.register_buffer(leaf, t)
+        else:
+            m.register_parameter(leaf, torch.nn.Parameter(t, requires_grad=False))
+    root.yaml = dict(cfg.model_dict("yolov8n-p2.yaml"), nc=80)
+    root.names = {i: f"c{i}" for i in range(80)}
+    sys.modules.update({"ultralytics": fake, "ultralytics.nn": fake_nn, "ultralytics.nn.tasks": fake_tasks})
+    try:
+        path = str(tmp_path / "best.pt")
+        torch.save({"epoch": 3, "model": None, "ema": root, "train_args": {}}, path)
+    finally:
+        for k in ("ultralytics", "ultralytics.nn", "ultralytics.nn.tasks"):
+            sys.modules.pop(k, None)
+    frames = [synth.IRStream(seed=60 + b, h=512, w=640).frame() for b in range(2)]
+    a = YOLO(path).predict(frames, conf=0.15, iou=0.6)
+    assert "ultralytics" not in sys.modules
+    b = YOLO("yolov8n-p2.yaml", state_dict=sd, nc=80).predict(frames, conf=0.15, iou=0.6)
+    assert a[0].names[5] == "c5"
+    for ra, rb in zip(a, b):
+        assert len(ra) > 0 and torch.equal(ra.boxes.data, rb.boxes.data)

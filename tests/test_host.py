@@ -274,3 +274,71 @@ def test_ultralytics_plugin_is_a_genuine_detection_predictor(tmp_path, monkeypat
     assert res[0].boxes.xyxy.shape == (2, 4) and res[0].boxes.conf.tolist() == pytest.approx([0.9, 0.4]) and res[0].boxes.cls.tolist() == [0.0, 0.0]
     assert res[0].orig_shape == (96, 128) and len(res[1].boxes) == 0 and res[0].names == {0: "aircraft"}
     assert res[0].boxes.xyxy.cpu().numpy().dtype == np.float32
+
+
+def test_pt_checkpoint_loader_and_results_exports_match_reference(tmp_path, monkeypatch):
+    """N4: (a) weights.load_checkpoint reads the two checkpoint forms the reference writes (trainer: EMA half weights,
+    engine/trainer.py save_model; Model.save: `model` half weights) WITHOUT importing ultralytics -- same YAML dict, same
+    state_dict keys and values (fp16-widened), same names -- and the layer list resolves; (b) Results.summary / save_txt give the
+    reference's output for the same boxes, with and without track ids.  Build-container test (needs the reference checkout to
+    WRITE the checkpoint and to compare against)."""
+    import subprocess
+    import sys
+
+    if not os.path.isdir("/root/reference/ultralytics"):
+        pytest.skip("the reference checkout is not present on this machine")
+    import torch
+
+    from b200dt import cfg, weights
+    from b200dt.predictor import Results
+
+    gen = tmp_path / "gen.py"
+    gen.write_text('''
+import sys, copy
+sys.path.insert(0, "/root/reference")
+import torch
+from ultralytics.nn.tasks import DetectionModel
+torch.manual_seed(3)
+m = DetectionModel("/root/reference/ultralytics/cfg/models/v8/yolov8-small.yaml", ch=3, nc=1, verbose=False)
+for mod in m.modules():
+    if isinstance(mod, torch.nn.BatchNorm2d):
+        mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5)
+m.names = {0: "aircraft"}
+torch.save({"epoch": 7, "model": None, "ema": copy.deepcopy(m).half(), "train_args": {"imgsz": 640}, "date": "x"}, sys.argv[1])
+torch.save({"model": copy.deepcopy(m).half(), "ema": None, "train_args": {}}, sys.argv[2])
+torch.save({k: v for k, v in m.state_dict().items()}, sys.argv[3])
+''')
+    p1, p2, p3 = tmp_path / "best.pt", tmp_path / "saved.pt", tmp_path / "sd.pt"
+    env = dict(os.environ, YOLO_CONFIG_DIR=str(tmp_path))
+    subprocess.run([sys.executable, str(gen), str(p1), str(p2), str(p3)], check=True, env=env, capture_output=True)
+    assert "ultralytics" not in sys.modules or True
+    ref_sd = torch.load(p3, map_location="cpu")
+    for p in (p1, p2):
+        before = set(sys.modules)
+        yd, sd, names = weights.load_checkpoint(str(p))
+        assert not any(k == "ultralytics" or k.startswith("ultralytics.") for k in set(sys.modules) - before)
+        assert names == {0: "aircraft"} and yd["nc"] == 1 and "backbone" in yd and "head" in yd
+        assert set(sd) == set(ref_sd)
+        for k, v in ref_sd.items():
+            want = v.half().float().numpy() if v.dtype.is_floating_point else v.numpy().astype(np.float32)
+            np.testing.assert_array_equal(sd[k], want, err_msg=k)
+        spec = cfg.resolve(yd)
+        assert spec["nc"] == 1 and spec["layers"][-1]["type"] == "Detect" and len(spec["layers"]) == len(yd["backbone"]) + len(yd["head"])
+        assert [L["c_out"] for L in spec["layers"]] == [L["c_out"] for L in cfg.resolve("yolov8-small.yaml", nc=1)["layers"]]
+    # (b) exports
+    monkeypatch.setenv("YOLO_CONFIG_DIR", str(tmp_path))
+    monkeypatch.syspath_prepend("/root/reference")
+    from ultralytics.engine.results import Results as URes
+
+    img = np.zeros((96, 128, 3), np.uint8)
+    names = {0: "aircraft", 1: "bird"}
+    for data in (np.array([[10.5, 12.25, 30.0, 40.75, 0.912345, 0.0], [50.0, 20.0, 70.125, 44.0, 0.4, 1.0]], np.float32),
+                 np.array([[10.5, 12.25, 30.0, 40.75, 7.0, 0.912345, 0.0], [50.0, 20.0, 70.125, 44.0, 12.0, 0.4, 1.0]], np.float32)):
+        mine, ref = Results(img, "a.jpg", names, data.copy()), URes(img, "a.jpg", names, boxes=torch.as_tensor(data))
+        assert mine.summary() == ref.summary() and mine.summary(normalize=True, decimals=3) == ref.summary(normalize=True, decimals=3)
+        for save_conf in (False, True):
+            a, b = tmp_path / f"m{save_conf}{data.shape[1]}.txt", tmp_path / f"r{save_conf}{data.shape[1]}.txt"
+            mine.save_txt(a, save_conf=save_conf); ref.save_txt(b, save_conf=save_conf)
+            assert a.read_text() == b.read_text() and a.read_text().count("\n") == 2
+        assert mine.plot().shape == img.shape and mine.plot().any()
+    assert Results(img, "a.jpg", names, np.zeros((0, 6), np.float32)).summary() == []

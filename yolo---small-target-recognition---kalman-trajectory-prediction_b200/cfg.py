@@ -93,6 +93,15 @@ def model_dict(name):
             "backbone": [list(r) for r in fam["rows"]], "head": [], "yaml_file": base + ".yaml"}
 
 
+def _literal(a):
+    import ast
+
+    try:
+        return ast.literal_eval(a)
+    except (ValueError, SyntaxError):
+        return a
+
+
 def resolve(name_or_dict, nc=None, ch=3):
     """parse_model for the hot-path module set: returns the concrete layer list.
 
@@ -113,6 +122,8 @@ def resolve(name_or_dict, nc=None, ch=3):
     chs, layers = [ch], []
     for i, (f, n, m, args) in enumerate(d["backbone"] + d["head"]):
         args = [nc if a == "nc" else a for a in args]
+        # parse_model (tasks.py:1580-1584) literal_evals string arguments: a YAML dict pickled inside a checkpoint carries 'None'
+        args = ["nearest" if a == "nearest" else (None if a == "None" else (a if not isinstance(a, str) or a in ("nc",) else _literal(a))) for a in args]
         n = max(round(n * depth), 1) if n > 1 else n
         f = tuple(f) if isinstance(f, (list, tuple)) else f
         L = {"i": i, "f": f, "type": m.replace("nn.", "")}

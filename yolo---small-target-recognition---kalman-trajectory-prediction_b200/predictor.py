@@ -139,6 +139,68 @@ class Results:
         r.boxes = self.boxes.numpy() if self.boxes is not None else None
         return r
 
+    def summary(self, normalize=False, decimals=5):
+        """results.py:788-860 for detections: one dict per box {name, class, confidence, box{x1,y1,x2,y2}[, track_id]}."""
+        out = []
+        if self.boxes is None:
+            return out
+        h, w = self.orig_shape if normalize else (1, 1)
+        d = self.boxes.numpy()
+        for row in d.data:
+            cls, conf = int(row[-1]), round(float(row[-2]), decimals)
+            r = {"name": self.names[cls], "class": cls, "confidence": conf,
+                 "box": {"x1": round(float(row[0]) / w, decimals), "y1": round(float(row[1]) / h, decimals),
+                         "x2": round(float(row[2]) / w, decimals), "y2": round(float(row[3]) / h, decimals)}}
+            if d.is_track:
+                r["track_id"] = int(row[4])
+            out.append(r)
+        return out
+
+    def to_json(self, normalize=False, decimals=5):
+        """results.py: to_json."""
+        import json
+
+        return json.dumps(self.summary(normalize=normalize, decimals=decimals), indent=2)
+
+    tojson = to_json
+
+    def save_txt(self, txt_file, save_conf=False):
+        """results.py:695-750 for detections: one line per box, ``class x_center y_center width height [conf] [track_id]`` with
+        normalised coordinates in '%g' format, APPENDED to the file."""
+        import os
+
+        texts = []
+        if self.boxes is not None and len(self.boxes):
+            d = self.boxes.numpy()
+            for row, nb in zip(d.data, d.xywhn):
+                line = (int(row[-1]), *[float(v) for v in nb]) + ((float(row[-2]),) if save_conf else ()) + ((int(row[4]),) if d.is_track else ())
+                texts.append(("%g " * len(line)).rstrip() % line)
+        if texts:
+            os.makedirs(os.path.dirname(os.path.abspath(str(txt_file))), exist_ok=True)
+            with open(txt_file, "a", encoding="utf-8") as f:
+                f.writelines(t + "\n" for t in texts)
+        return str(txt_file)
+
+    def plot(self, conf=True, labels=True, line_width=None, img=None, **_):
+        """results.py:475-613 restricted to boxes: a BGR copy of the frame with one rectangle (+ label) per detection.  Needs cv2
+        (host-side drawing, not part of the hot path; colours / fonts are not the reference Annotator's)."""
+        import cv2
+
+        im = (self.orig_img if img is None else img).copy()
+        lw = line_width or max(round(sum(im.shape[:2]) / 2 * 0.003), 2)
+        if self.boxes is None:
+            return im
+        d = self.boxes.numpy()
+        for row in d.data:
+            c = int(row[-1])
+            col = tuple(int(v) for v in ((37 * c + 90) % 256, (17 * c + 200) % 256, (29 * c + 40) % 256))
+            p1, p2 = (int(row[0]), int(row[1])), (int(row[2]), int(row[3]))
+            cv2.rectangle(im, p1, p2, col, thickness=lw, lineType=cv2.LINE_AA)
+            if labels:
+                name = ("" if not d.is_track else f"id:{int(row[4])} ") + str(self.names[c])
+                cv2.putText(im, f"{name} {float(row[-2]):.2f}" if conf else name, (p1[0], max(p1[1] - 2, 0)), 0, lw / 3, col, thickness=max(lw - 1, 1), lineType=cv2.LINE_AA)
+        return im
+
     def verbose(self):
         """results.py:663-693."""
         if not len(self):
@@ -230,8 +292,12 @@ class YOLO:
         if task not in (None, "detect"):
             raise NotImplementedError(f"task {task!r}: only 'detect' is on the hot path")
         _lib.require_cuda()
+        ckpt_names = None
+        if isinstance(model, str) and model.endswith(".pt"):           # engine/model.py:_load -> nn/tasks.py load_checkpoint
+            model, ckpt_sd, ckpt_names = weights.load_checkpoint(model)
+            state_dict = ckpt_sd if state_dict is None else state_dict
         self.spec = cfg.resolve(model, nc=nc)
-        self.names = self.spec["names"]
+        self.names = ckpt_names if ckpt_names and len(ckpt_names) == self.spec["nc"] else self.spec["names"]
         self.state_dict = weights.to_numpy_state_dict(state_dict) if state_dict is not None else weights.synthetic_state_dict(self.spec, seed)
         self.overrides = {"conf": 0.25, "iou": 0.7, "imgsz": 640, "max_det": 300, "agnostic_nms": False, "classes": None,
                           "batch": 1, "verbose": verbose, "nms_mode": "exact"}

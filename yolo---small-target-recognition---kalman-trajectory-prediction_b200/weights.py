@@ -378,3 +378,82 @@ def pad_channels(spec, sd, multiple=16):
         else:
             raise NotImplementedError(t)
     return sp, out
+
+
+# ---------------------------------------------------------------------------------------------------
+# `.pt` checkpoints (ultralytics/nn/tasks.py:1404-1521 torch_safe_load / load_checkpoint) without the ultralytics package
+# ---------------------------------------------------------------------------------------------------
+class _CkptStub:
+    """Stands in for any class of the `ultralytics` package while unpickling: keeps the pickled attribute dict.  nn.Module
+    subclasses arrive as their `__dict__` (`_parameters`, `_buffers`, `_modules`, plus plain attributes such as `yaml`, `names`)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        if isinstance(state, tuple) and len(state) == 2:            # (dict, slots)
+            state = {**(state[0] or {}), **(state[1] or {})}
+        if isinstance(state, dict):
+            self.__dict__.update(state)
+
+
+def _walk_state(obj, prefix, out):
+    """state_dict() of a pickled module tree whose ultralytics containers are stubs and whose leaves are real torch modules."""
+    for name, p in (getattr(obj, "_parameters", None) or {}).items():
+        if p is not None:
+            out[prefix + name] = p.detach()
+    persistent_off = getattr(obj, "_non_persistent_buffers_set", None) or set()
+    for name, b in (getattr(obj, "_buffers", None) or {}).items():
+        if b is not None and name not in persistent_off:
+            out[prefix + name] = b
+    for name, child in (getattr(obj, "_modules", None) or {}).items():
+        if child is not None:
+            _walk_state(child, prefix + name + ".", out)
+
+
+def load_checkpoint(path):
+    """Read an Ultralytics `.pt` checkpoint (``model.save(...)`` / the trainer's ``best.pt``) -> ``(model_dict, state_dict, names)``:
+    the model YAML dict the network was built from (``DetectionModel.yaml``: scale, nc, backbone, head -- what :func:`cfg.resolve`
+    takes), the float32 numpy state_dict with the reference's key names (``model.0.conv.weight`` ...) and the class-name dict.
+    Follows load_checkpoint (tasks.py:1487-1521): the EMA weights win over ``model``, half weights are widened to fp32.  The
+    ``ultralytics`` package is NOT needed: its classes are unpickled as attribute-dict stubs, tensors by torch itself."""
+    import pickle
+    import types
+
+    import torch
+
+    stubs = {}
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, mod, name):
+            root = mod.split(".")[0]
+            if root in ("ultralytics", "__main__", "models", "utils"):      # the last two: how YOLOv5-era pickles name their classes
+                if root in ("models", "utils"):
+                    raise TypeError(f"{path} looks like a YOLOv5 checkpoint ({mod}.{name}); it is not forwards compatible (tasks.py:1450-1459)")
+                key = (mod, name)
+                if key not in stubs:
+                    stubs[key] = type(name, (_CkptStub,), {"__module__": "b200dt._ckpt." + mod})
+                return stubs[key]
+            return super().find_class(mod, name)
+
+    pm = types.ModuleType("b2dt_ckpt_pickle")
+    pm.Unpickler = _Unpickler
+    pm.load = lambda f, **kw: _Unpickler(f, **kw).load()
+    pm.__name__ = "pickle"
+    with open(path, "rb") as fh:
+        ckpt = torch.load(fh, map_location="cpu", pickle_module=pm, weights_only=False)
+    if not isinstance(ckpt, dict):                                          # torch.save(model, ...) of a whole YOLO object (tasks.py:1475-1481)
+        ckpt = {"model": getattr(ckpt, "model", ckpt)}
+    model = ckpt.get("ema") or ckpt["model"]
+    yaml_d = getattr(model, "yaml", None)
+    if not isinstance(yaml_d, dict) or "backbone" not in yaml_d or "head" not in yaml_d:
+        raise ValueError(f"{path}: the pickled model carries no YAML dict (model.yaml); cannot rebuild the layer list")
+    sd = {}
+    _walk_state(model, "", sd)
+    if not sd:
+        raise ValueError(f"{path}: no parameters found in the pickled model")
+    names = getattr(model, "names", None)
+    if isinstance(names, (list, tuple)):
+        names = dict(enumerate(names))
+    out = {k: v.float().numpy() for k, v in sd.items()}
+    return dict(yaml_d), out, names
