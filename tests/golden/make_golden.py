@@ -400,6 +400,20 @@ def gold_bytetrack():
         for i, j in mt:
             x[i] = j
         out[f"lap{k}_cost"] = c; out[f"lap{k}_x"] = x; out[f"lap{k}_thresh"] = np.float32(th)
+    # BoT-SORT (bot_sort.py) without ReID, botsort.yaml defaults: XYWH filter + sparse-optical-flow GMC driven by the frames
+    from golden_common import botsort_scene
+    from ultralytics.trackers.bot_sort import BOTSORT
+
+    frames_b, dets_b = botsort_scene()
+    bargs = dict(tracker_type="botsort", track_high_thresh=0.25, track_low_thresh=0.1, new_track_thresh=0.25, track_buffer=30, match_thresh=0.8,
+                 fuse_score=True, gmc_method="sparseOptFlow", proximity_thresh=0.5, appearance_thresh=0.8, with_reid=False, model="auto")
+    for tag, use_img in (("botsort", True), ("botsort_nogmc", False)):
+        trk = BOTSORT(IterableSimpleNamespace(**bargs), frame_rate=30)
+        rows, counts, warps = [], [], []
+        for f, d in enumerate(dets_b):
+            r = np.asarray(trk.update(Boxes(d, frames_b[f].shape[:2]).numpy(), frames_b[f] if use_img else None), dtype=np.float32).reshape(-1, 8)
+            rows.append(r); counts.append(len(r))
+        out[f"{tag}_rows"] = np.concatenate(rows); out[f"{tag}_counts"] = np.array(counts)
     np.savez_compressed(os.path.join(HERE, "bytetrack.npz"), **out)
 
 

@@ -179,3 +179,33 @@ def bytetrack_script(n_frames=90, n_targets=14, seed=5, hw=(512, 640)):
         arr = np.asarray(rows, dtype=np.float32).reshape(-1, 6)
         frames.append(arr[g.permutation(len(arr))])
     return frames
+
+
+def botsort_scene(n_frames=50, seed=9, hw=(256, 320)):
+    """Frames + detections for the BoT-SORT goldens: a fixed textured world (sum of random Gaussian spots: plenty of corners for
+    goodFeaturesToTrack) seen through a window that shakes a few pixels per frame (global camera motion for the GMC), and the
+    scripted detections of bytetrack_script shifted by the same offsets.  Returns (frames [n] of (h, w, 3) uint8, dets [n] of (k, 6))."""
+    g = np.random.default_rng(seed)
+    h, w = hw
+    pad = 40
+    world = np.zeros((h + 2 * pad, w + 2 * pad), np.float32)
+    yy, xx = np.mgrid[0:world.shape[0], 0:world.shape[1]]
+    for _ in range(500):
+        cx, cy, s, a = g.uniform(0, world.shape[1]), g.uniform(0, world.shape[0]), g.uniform(1.5, 4.0), g.uniform(20, 90)
+        x0, x1, y0, y1 = int(max(cx - 4 * s, 0)), int(min(cx + 4 * s + 1, world.shape[1])), int(max(cy - 4 * s, 0)), int(min(cy + 4 * s + 1, world.shape[0]))
+        world[y0:y1, x0:x1] += a * np.exp(-((xx[y0:y1, x0:x1] - cx) ** 2 + (yy[y0:y1, x0:x1] - cy) ** 2) / (2 * s * s))
+    world = np.clip(world + 20, 0, 255).astype(np.uint8)
+    dets = bytetrack_script(n_frames, 10, seed + 1, hw)
+    off = np.zeros(2, int)
+    frames, out = [], []
+    for f in range(n_frames):
+        off = np.clip(off + g.integers(-3, 4, 2), -pad + 2, pad - 2)
+        if f in (20, 21, 35):
+            off = np.clip(off + g.integers(-12, 13, 2), -pad + 2, pad - 2)          # a camera jolt
+        win = world[pad + off[1]:pad + off[1] + h, pad + off[0]:pad + off[0] + w]
+        frames.append(np.ascontiguousarray(np.stack([win, win, win], -1)))
+        d = dets[f].copy()
+        d[:, [0, 2]] -= off[0]
+        d[:, [1, 3]] -= off[1]
+        out.append(d)
+    return frames, out

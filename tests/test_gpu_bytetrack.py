@@ -157,5 +157,33 @@ def test_yolo_track_attaches_ids():
     nxt = model.track(frames[4:], conf=0.15, iou=0.6, persist=True)
     ids2 = set(np.asarray(nxt[0].boxes.id).astype(int).tolist())
     assert len(ids2 & ids[-1]) >= max(1, len(ids2) // 2)
-    with pytest.raises(NotImplementedError):
-        model.track(frames[:1], tracker="botsort.yaml")
+    bot = model.track(frames[:3], conf=0.15, iou=0.6, tracker="botsort.yaml")               # BoT-SORT: XYWH filter + GMC on the frames
+    assert all(r.boxes.is_track for r in bot if len(r))
+    with pytest.raises(AssertionError):
+        model.track(frames[:1], tracker="deepsort.yaml")
+
+
+@pytest.mark.parametrize("tag,use_img", [("botsort", True), ("botsort_nogmc", False)])
+def test_botsort_matches_reference(tag, use_img):
+    """b200dt.byte_tracker.BOTSORT (no ReID) against the reference's BOTSORT.update on a shaking-camera scene: with the frames
+    (sparse-optical-flow GMC, OpenCV on the host as in the reference) and without (img=None): same ids / scores / classes /
+    indices every frame, boxes within 2e-3 px."""
+    from b200dt import byte_tracker as bt
+    from b200dt.predictor import Boxes
+
+    from golden_common import botsort_scene
+
+    g = np.load(os.path.join(G, "bytetrack.npz"))
+    frames, dets = botsort_scene()
+    trk = bt.BOTSORT()
+    off, worst = 0, 0.0
+    for f, d in enumerate(dets):
+        r = np.asarray(trk.update(Boxes(d, frames[f].shape[:2]), frames[f] if use_img else None), dtype=np.float32).reshape(-1, 8)
+        n = int(g[f"{tag}_counts"][f])
+        ref = g[f"{tag}_rows"][off:off + n]
+        off += n
+        assert len(r) == n, (f, len(r), n)
+        assert np.array_equal(r[:, 4:], ref[:, 4:]), f
+        if n:
+            worst = max(worst, float(np.abs(r[:, :4] - ref[:, :4]).max()))
+    assert worst < 2e-3, worst

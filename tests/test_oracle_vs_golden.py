@@ -369,3 +369,24 @@ def test_linear_assignment_oracle_cases():
                for p in itertools.product(range(-1, m), repeat=n) if len({j for j in p if j >= 0}) == sum(j >= 0 for j in p))
     got = sum((c[i, j] - th) for i, j in enumerate(x) if j >= 0)
     assert abs(got - best) < 1e-9
+
+
+@pytest.mark.parametrize("tag,use_img", [("botsort", True), ("botsort_nogmc", False)])
+def test_botsort_oracle_matches_reference(tag, use_img):
+    """oracle.byte_tracker.BOTSORT (bot_sort.py without ReID: XYWH filter, sparse-optical-flow GMC through the same OpenCV calls)
+    against the reference's BOTSORT.update over the shaking-camera scene, with and without the frames."""
+    from golden_common import botsort_scene
+    from oracle import byte_tracker as obt
+
+    g = _load("bytetrack.npz")
+    frames, dets = botsort_scene()
+    t = obt.BOTSORT()
+    off = 0
+    assert not np.array_equal(g["botsort_counts"], g["botsort_nogmc_counts"])          # the compensation changes the outcome
+    for f, d in enumerate(dets):
+        r = t.update(_xywh(d), d[:, 4], d[:, 5], frames[f] if use_img else None).reshape(-1, 8)
+        n = int(g[f"{tag}_counts"][f])
+        ref = g[f"{tag}_rows"][off:off + n]
+        off += n
+        assert len(r) == n and np.array_equal(r[:, 4:], ref[:, 4:]), f
+        np.testing.assert_allclose(r[:, :4], ref[:, :4], rtol=0, atol=1e-4)

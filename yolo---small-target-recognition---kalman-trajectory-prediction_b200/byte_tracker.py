@@ -1,4 +1,4 @@
-"""Upstream tracker plug-in (ByteTrack) over the B200 kernels: mirror of ``ultralytics/trackers/byte_tracker.py`` (STrack
+"""Upstream tracker plug-in (ByteTrack, BoT-SORT without ReID) over the B200 kernels: mirror of ``ultralytics/trackers/byte_tracker.py`` (STrack
 :14-237, BYTETracker :240-485), ``trackers/utils/matching.py`` (linear_assignment :20-63, iou_distance :66-113, fuse_score
 :135-157) and the ``trackers/track.py`` callback contract (:72-102: ``tracker.update(boxes) -> (k, 8)`` rows
 ``[x1, y1, x2, y2, track_id, score, cls, idx]``, ``Results.update(boxes=rows[:, :-1])``).
@@ -143,6 +143,17 @@ class STrack:
         mm, mc = STrack.shared_kalman.multi_predict(mm, mc)
         for i, st in enumerate(stracks):
             st.mean, st.covariance = mm[i], mc[i]
+
+    @staticmethod
+    def multi_gmc(stracks, H=np.eye(2, 3)):
+        """:109-125 -- the camera-motion warp applied to every state and covariance (8 x 8 products on the host, as the reference)."""
+        if stracks:
+            R8x8 = np.kron(np.eye(4, dtype=float), H[:2, :2])
+            t = H[:2, 2]
+            for st in stracks:
+                mean = R8x8.dot(st.mean)
+                mean[:2] += t
+                st.mean, st.covariance = mean, R8x8.dot(st.covariance).dot(R8x8.transpose())
 
     # the three state changes of the reference take the Kalman result computed for the whole stage (see BYTETracker._apply)
     def activate(self, kalman_filter, frame_id, mean, covariance):
@@ -292,6 +303,13 @@ class BYTETracker:
         # first association, high-score boxes
         strack_pool = self.joint_stracks(tracked_stracks, self.lost_stracks)
         self.multi_predict(strack_pool)
+        if hasattr(self, "gmc") and img is not None:              # BoT-SORT: global motion compensation (:329-337)
+            try:
+                warp = self.gmc.apply(img, None)
+            except Exception:
+                warp = np.eye(2, 3)
+            STrack.multi_gmc(strack_pool, warp)
+            STrack.multi_gmc(unconfirmed, warp)
         dists = self.get_dists(strack_pool, detections)
         matches, u_track, u_detection = linear_assignment(dists, thresh=self.args.match_thresh)
         self._apply([(strack_pool[it], detections[idt]) for it, idt in matches], activated_stracks, refind_stracks)
@@ -367,6 +385,133 @@ class BYTETracker:
             else:
                 dupa.append(p)
         return [t for i, t in enumerate(stracksa) if i not in dupa], [t for i, t in enumerate(stracksb) if i not in dupb]
+
+
+# ---------------------------------------------------------------------------------------------------
+# BoT-SORT without ReID (trackers/bot_sort.py: BOTrack :20-151, BOTSORT :154-232; utils/gmc.py)
+# ---------------------------------------------------------------------------------------------------
+class GMC:
+    """utils/gmc.py:14-350 for the methods 'sparseOptFlow' (botsort.yaml's default) and none.  Host-side OpenCV exactly as in the
+    reference (goodFeaturesToTrack, calcOpticalFlowPyrLK, estimateAffinePartial2D): one 2 x 3 matrix per frame, not a GPU path."""
+
+    def __init__(self, method="sparseOptFlow", downscale=2):
+        self.method = None if method in ("none", "None", None) else method
+        if self.method not in (None, "sparseOptFlow"):
+            raise NotImplementedError(f"GMC method {method!r}: only 'sparseOptFlow' and 'none' are provided")
+        self.downscale = max(1, downscale)
+        self.feature_params = dict(maxCorners=1000, qualityLevel=0.01, minDistance=1, blockSize=3, useHarrisDetector=False, k=0.04)
+        self.reset_params()
+
+    def reset_params(self):
+        self.prevFrame = self.prevKeyPoints = None
+        self.initializedFirstFrame = False
+
+    def apply(self, raw_frame, detections=None):
+        import copy
+
+        import cv2
+
+        if self.method is None:
+            return np.eye(2, 3)
+        height, width, c = raw_frame.shape
+        frame = cv2.cvtColor(raw_frame, cv2.COLOR_BGR2GRAY) if c == 3 else raw_frame
+        H = np.eye(2, 3)
+        if self.downscale > 1.0:
+            frame = cv2.resize(frame, (width // self.downscale, height // self.downscale))
+        keypoints = cv2.goodFeaturesToTrack(frame, mask=None, **self.feature_params)
+        if not self.initializedFirstFrame or self.prevKeyPoints is None:
+            self.prevFrame, self.prevKeyPoints, self.initializedFirstFrame = frame.copy(), copy.copy(keypoints), True
+            return H
+        matched, status, _ = cv2.calcOpticalFlowPyrLK(self.prevFrame, frame, self.prevKeyPoints, None)
+        prev = np.array([self.prevKeyPoints[i] for i in range(len(status)) if status[i]])
+        curr = np.array([matched[i] for i in range(len(status)) if status[i]])
+        if prev.shape[0] > 4 and prev.shape[0] == curr.shape[0]:
+            H, _ = cv2.estimateAffinePartial2D(prev, curr, cv2.RANSAC)
+            if self.downscale > 1.0:
+                H[0, 2] *= self.downscale
+                H[1, 2] *= self.downscale
+        self.prevFrame, self.prevKeyPoints = frame.copy(), copy.copy(keypoints)
+        return H
+
+
+class BOTrack(STrack):
+    """bot_sort.py:20-151 without appearance features: XYWH filter, both size velocities zeroed while a track is not Tracked."""
+
+    shared_kalman = None
+
+    @staticmethod
+    def multi_predict(stracks):
+        if len(stracks) <= 0:
+            return
+        mm = np.asarray([st.mean.copy() for st in stracks])
+        mc = np.asarray([st.covariance for st in stracks])
+        for i, st in enumerate(stracks):
+            if st.state != TrackState.Tracked:
+                mm[i][6] = 0
+                mm[i][7] = 0
+        mm, mc = BOTrack.shared_kalman.multi_predict(mm, mc)
+        for i, st in enumerate(stracks):
+            st.mean, st.covariance = mm[i], mc[i]
+
+    @property
+    def tlwh(self):
+        if self.mean is None:
+            return self._tlwh.copy()
+        ret = self.mean[:4].copy()
+        ret[:2] -= ret[2:] / 2
+        return ret
+
+    def convert_coords(self, tlwh):
+        return self.tlwh_to_xywh(tlwh)
+
+    @staticmethod
+    def tlwh_to_xywh(tlwh):
+        ret = np.asarray(tlwh).copy()
+        ret[:2] += ret[2:] / 2
+        return ret
+
+
+BOTSORT_DEFAULT_ARGS = dict(DEFAULT_ARGS, tracker_type="botsort", gmc_method="sparseOptFlow", proximity_thresh=0.5, appearance_thresh=0.8,
+                            with_reid=False, model="auto")          # ultralytics/cfg/trackers/botsort.yaml
+
+
+class BOTSORT(BYTETracker):
+    """bot_sort.py:154-232 with ``with_reid=False`` (the yaml's default): ByteTrack's association on the XYWH filter plus global
+    motion compensation from the frame handed to ``update(results, img)``."""
+
+    def __init__(self, args=None, frame_rate=30):
+        from .kalman_filter import KalmanFilterXYWH
+
+        self._kf_cls = KalmanFilterXYWH
+        if args is None:
+            args = BOTSORT_DEFAULT_ARGS
+        if isinstance(args, dict):
+            args = SimpleNamespace(**{**BOTSORT_DEFAULT_ARGS, **args})
+        if getattr(args, "with_reid", False):
+            raise NotImplementedError("BoT-SORT ReID (appearance embeddings) is outside the hot path")
+        super().__init__(args, frame_rate)
+        self.gmc = GMC(method=args.gmc_method)
+        self.proximity_thresh, self.appearance_thresh = args.proximity_thresh, args.appearance_thresh
+        self.encoder = None
+
+    def get_kalmanfilter(self):
+        kf = self._kf_cls()
+        BOTrack.shared_kalman = kf
+        return kf
+
+    def init_track(self, results, img=None):
+        if len(results) == 0:
+            return []
+        bboxes = np.asarray(results.xywh, dtype=np.float32)
+        bboxes = np.concatenate([bboxes, np.arange(len(bboxes), dtype=np.float32).reshape(-1, 1)], axis=-1)
+        return [BOTrack(xywh, s, c) for (xywh, s, c) in zip(bboxes, np.asarray(results.conf), np.asarray(results.cls))]
+
+    def multi_predict(self, tracks):
+        BOTrack.multi_predict(tracks)
+
+    def reset(self):
+        super().reset()
+        self.gmc.reset_params()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -1368,10 +1368,11 @@ int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B,
     B2_REQUIRE(!residual || (res_cstride % 8 == 0 && res_coff % 8 == 0), "conv: residual stride/offset must be multiples of 8");
     B2_REQUIRE(Cout > 0 && B > 0 && H > 0 && W > 0, "conv: bad shape");
     B2_REQUIRE(((uintptr_t)out % 16 == 0) && ((uintptr_t)w % 16 == 0), "conv: pointers must be 16-byte aligned");
-    if (!plan_only) {   // opt in to the large dynamic shared memory carve-out once (not a stream operation: safe before graph capture)
-        static std::once_flag once;
-        static cudaError_t attr_err = cudaSuccess;
-        std::call_once(once, [] {
+    if (!plan_only) {   // opt in to the large dynamic shared memory carve-out (not a stream operation: safe before graph capture).
+        // The attribute belongs to the current device's context, so it is set on every plan (plan time, a few microseconds), not once
+        // per process: a process that drives a second GPU would otherwise launch there without the opt-in.
+        cudaError_t attr_err = cudaSuccess;
+        {
             const int bytes = 227 * 1024 - 4096;
             cudaError_t e = cudaSuccess;
             auto set = [&](const void* fn) { cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); if (r != cudaSuccess) e = r; };
@@ -1382,7 +1383,7 @@ int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B,
             set((const void*)conv_tc_kernel<0, 2, 2, 16, 1>); set((const void*)conv_tc_kernel<0, 3, 2, 16, 1>);
             set((const void*)conv_tc_kernel<1, 2, 2, 16, 1>); set((const void*)conv_tc_kernel<2, 2, 2, 16, 1>);
             attr_err = e;
-        });
+        }
         B2_CUDA(attr_err);
     }
     EncodeTiledFn encode = plan_only ? nullptr : get_encode();
@@ -1552,10 +1553,7 @@ int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B,
         p.tw_log2 = 0; while ((1 << p.tw_log2) < p.TW) ++p.tw_log2;
         p.th_log2 = 0; while ((1 << p.th_log2) < p.TH) ++p.th_log2;
         B2_REQUIRE((1 << p.tw_log2) == p.TW && (1 << p.th_log2) == p.TH, "conv(ts): tile extents must be powers of two");
-        static std::once_flag once_ts;
-        static cudaError_t attr_err_ts = cudaSuccess;
-        std::call_once(once_ts, [] { attr_err_ts = cudaFuncSetAttribute(conv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192); });
-        B2_CUDA(attr_err_ts);
+        if (!plan_only) B2_CUDA(cudaFuncSetAttribute(conv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));   // per device: see above
     } else {
     // ---- resident-weight 3x3 stride-1 layers: single halo box per K chunk (halo 2, see the TS branch) when the weights and
     //      >= 3 box stages fit; decided on the resident footprint, which does not depend on the stage layout ----

@@ -667,10 +667,8 @@ extern "C" int b2_nms(const float* cand, const int32_t* cand_idx, const int32_t*
     p.P_max = (int)P;
     { static const bool dbg = [] { const char* v = getenv("B2_NMS_DEBUG"); return v && atoi(v) != 0; }(); p.debug = dbg ? 1 : 0; }
     const size_t dyn = (size_t)kSmemSort * 12 + (size_t)kFastN * 16 + (size_t)kFastN * ((kFastN + 31) / 32) * 4 + (size_t)kMaxKeep * 16;
-    {
-        static cudaError_t attr_err = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        B2_CUDA(attr_err);
-    }
+    // the attribute belongs to the current device's context: set on every call (a microsecond of host time), not once per process
+    B2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     nms_kernel<<<B, kNmsThreads, dyn, (cudaStream_t)stream>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);

@@ -397,15 +397,18 @@ class YOLO:
         from . import byte_tracker
 
         tracker = kwargs.pop("tracker", "bytetrack.yaml")
+        cls = byte_tracker.BYTETracker
         if isinstance(tracker, str):
             if "botsort" in tracker:
-                raise NotImplementedError("BoT-SORT (GMC + ReID) is not on the hot path; its Kalman filter is b200dt.kalman_filter.KalmanFilterXYWH")
-            if "bytetrack" not in tracker:
+                cls = byte_tracker.BOTSORT
+            elif "bytetrack" not in tracker:
                 raise AssertionError(f"Only 'bytetrack' and 'botsort' are supported for now, but got '{tracker}'")
             tracker = None
+        elif isinstance(tracker, dict) and tracker.get("tracker_type") == "botsort":
+            cls = byte_tracker.BOTSORT
         kwargs["conf"] = kwargs.get("conf") or 0.1
         if not (persist and getattr(self, "trackers", None)):
-            self.trackers = [byte_tracker.BYTETracker(tracker, frame_rate=30)]
+            self.trackers = [cls(tracker, frame_rate=30)]
         results = list(self.predict(source, False, **kwargs))
         byte_tracker.update_results(self.trackers, results, is_stream=False)
         return iter(results) if stream else results
