@@ -2,6 +2,8 @@
 // nearest-2x upsample / concat slice copy, stand-alone preprocess.  All NHWC bf16, 16-byte vector accesses.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 void b2_count_launch(int n);
 
 namespace {
@@ -22,6 +24,9 @@ namespace {
 // as the bytes lie in memory -- K index = kh * 10 + kw * 3 + c (c in B, G, R order, index 9 of every kh a zero weight) --
 // so a row is three runs of 10 consecutive frame bytes: 3 aligned word loads, 3 funnel shifts and 5 PRMT per run.
 // ------------------------------------------------------------------------------------------------
+#ifndef B2_STEM_CTAS
+#define B2_STEM_CTAS 8          // co-resident stem CTAs per SM the register budget is set for (experiment builds: 10, 12)
+#endif
 constexpr int kStemThreads = 128;
 constexpr int kStemMaxC0 = 128;
 constexpr int kStemPitch = 144;          // bytes between staged patch rows (16-byte multiple, not a multiple of 128: rows 2 apart hit other banks)
@@ -31,7 +36,7 @@ __device__ __forceinline__ uint32_t swz64_chunk_off(int row, int chunk) {   // b
 }
 
 template <typename Loader>
-__global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B, int H, int W, int Ho, int Wo,
+__global__ void __launch_bounds__(kStemThreads, B2_STEM_CTAS) stem_tc_kernel(Loader ld, int B, int H, int W, int Ho, int Wo,
                                                                const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                                                                float in_scale, int C0, int n_tile, uint32_t tmem_cols,
                                                                __nv_bfloat16* __restrict__ out, int out_cstride, int out_coff,
@@ -93,19 +98,26 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
     const uint32_t a_lo = ((smem_u32(s_a) >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((smem_u32(s_b) >> 4) & 0x3FFFu) | (1u << 16);
     const int tw = tid & 15, th = tid >> 4;                 // 16 x 8 output pixels per tile
     uint32_t phase = 0;
+    // tile -> (column cx, row cy, image cb) once, then advanced by the grid stride in mixed radix: no division per tile (the
+    // divisions, 64-bit patch addresses and coordinate products were most of the 560 instructions a warp spent per tile -- ncu:
+    // 59 % of the issue slots, 136 of them the arithmetic of the layer)
+    const int tpi = tiles_w * tiles_h;
+    int cb = (int)blockIdx.x / tpi, cy = ((int)blockIdx.x - cb * tpi) / tiles_w, cx = (int)blockIdx.x - cb * tpi - cy * tiles_w;
+    const int sb = (int)gridDim.x / tpi, sy = ((int)gridDim.x - sb * tpi) / tiles_w, sx = (int)gridDim.x - sb * tpi - sy * tiles_w;
+    auto advance = [&](int& x, int& y, int& b_) {
+        x += sx; if (x >= tiles_w) { x -= tiles_w; y += 1; }
+        y += sy; if (y >= tiles_h) { y -= tiles_h; b_ += 1; }
+        b_ += sb;
+    };
+    int nx = cx, ny = cy, nb = cb;
+    advance(nx, ny, nb);
     // patch of the first tile (see LoadU8::fetch)
-    uint4 pv0 = make_uint4(0, 0, 0, 0), pv1 = make_uint4(0, 0, 0, 0);
-    long long pg = 0;
+    typename Loader::Patch pp;
+    const int roff = ld.row_offset(tid);
     bool pok = false;
-    if (Loader::kStaged && (int)blockIdx.x < total_tiles) {
-        const int t0 = blockIdx.x;
-        pok = ld.fetch(t0 / (tiles_w * tiles_h), 2 * (((t0 / tiles_w) % tiles_h) * 8) - 1, 2 * ((t0 % tiles_w) * 16) - 1, tid, pv0, pv1, pg);
-    }
+    if (Loader::kStaged && (int)blockIdx.x < total_tiles) pok = ld.fetch(cb, 16 * cy - 1, 32 * cx - 1, tid, roff, pp);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int wo = (t % tiles_w) * 16 + tw; t /= tiles_w;
-        const int ho = (t % tiles_h) * 8 + th;
-        const int b = t / tiles_h;
+        const int wo = cx * 16 + tw, ho = cy * 8 + th, b = cb;
         // ---- im2col row of this thread's pixel ----
         bool staged = false;
         uint32_t pk[16];
@@ -114,12 +126,10 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
             // with aligned 16-byte loads (<= 8 per row; one or two per thread) and each thread then takes its three runs of
             // 10 bytes from there -- 136 vector loads and no per-byte bounds checks instead of 3456 byte loads per tile.
             staged = pok;                                                                        // uniform across the CTA
-            if (staged) ld.commit(s_in, tid, pv0, pv1, pg);
+            if (staged) ld.commit(s_in, tid, pp);
             {   // loads of the next tile's patch: consumed at the top of the next iteration
-                const int t2 = tile + gridDim.x;
                 pok = false;
-                if (t2 < total_tiles)
-                    pok = ld.fetch(t2 / (tiles_w * tiles_h), 2 * (((t2 / tiles_w) % tiles_h) * 8) - 1, 2 * ((t2 % tiles_w) * 16) - 1, tid, pv0, pv1, pg);
+                if (tile + (int)gridDim.x < total_tiles) pok = ld.fetch(nb, 16 * ny - 1, 32 * nx - 1, tid, roff, pp);
             }
             if (staged) {
                 __syncthreads();
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
         phase ^= 1;
         tc_fence_after();
         const bool valid = wo < Wo && ho < Ho;
-        __nv_bfloat16* op = out + (((size_t)b * Ho + ho) * Wo + wo) * out_cstride + out_coff;
+        __nv_bfloat16* op = out + (size_t)((b * Ho + ho) * Wo + wo) * out_cstride + out_coff;        // B * Ho * Wo < 2^31 (checked on the host)
         const uint32_t t_addr = tmem + ((uint32_t)(warp * 32) << 16);
         for (int j = 0; j < n_tile; j += 16) {
             uint32_t a[16];
@@ -207,6 +217,8 @@ __global__ void __launch_bounds__(kStemThreads) stem_tc_kernel(Loader ld, int B,
         }
         tc_fence_before();
         __syncthreads();                                     // accumulator and A tile are free for the next tile
+        cx = nx; cy = ny; cb = nb;
+        advance(nx, ny, nb);
     }
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
@@ -220,33 +232,38 @@ struct LoadU8 {   // [B][src_h][src_w][3] uint8 BGR placed at (pad_top, pad_left
     // fetch(): the loads of one patch into registers (chunk tid, and chunk 128 + tid for tid < 8); commit(): registers -> s_in.
     // The kernel fetches the patch of its NEXT tile before it works on the current one, so the global-memory latency of the
     // patch is hidden behind a whole tile of build / MMA / epilogue instead of being paid at the top of every tile.
-    __device__ __forceinline__ bool fetch(int b, int y0, int x0, int tid, uint4& v0, uint4& v1, long long& g_first) const {
+    // Per-thread state of one patch between fetch and commit: the two vectors, the low address bits of the thread's rows (row r
+    // starts lo bytes into its first 16-byte vector) and whether the thread's vectors belong to the patch at all.
+    struct Patch { uint4 v0, v1; int lo0, lo1; bool p0, p1; };
+    __device__ __forceinline__ int row_offset(int tid) const { return (tid >> 3) * sw * 3; }       // byte offset of the thread's patch row
+    __device__ __forceinline__ bool fetch(int b, int y0, int x0, int tid, int roff, Patch& P) const {
         const int fy0 = y0 - pt, fx0 = x0 - pl;
         if (fy0 < 0 || fx0 < 0 || fy0 + 16 >= sh || fx0 + 32 >= sw) return false;
-        g_first = (((long long)b * sh + fy0) * sw + fx0) * 3;
+        const long long g_first = (((long long)b * sh + fy0) * sw + fx0) * 3;                       // block-uniform
         if (g_first + 16ll * sw * 3 + 99 + 16 > total_bytes) return false;
+        const int c16 = (tid & 7) * 16;
         {
-            const int r = tid >> 3, c = tid & 7;
-            const long long g0 = g_first + (long long)r * sw * 3, ga = (g0 & ~15ll) + c * 16;
-            if (ga < g0 + 99) v0 = __ldg(reinterpret_cast<const uint4*>(p + ga));
+            const long long g0 = g_first + roff;
+            P.lo0 = (int)(g0 & 15);
+            P.p0 = c16 < P.lo0 + 99;
+            if (P.p0) P.v0 = __ldg(reinterpret_cast<const uint4*>(p + (g0 - P.lo0) + c16));
         }
+        P.p1 = false;
         if (tid < 8) {
-            const long long g0 = g_first + 16ll * sw * 3, ga = (g0 & ~15ll) + tid * 16;
-            if (ga < g0 + 99) v1 = __ldg(reinterpret_cast<const uint4*>(p + ga));
+            const long long g0 = g_first + 16ll * sw * 3;
+            P.lo1 = (int)(g0 & 15);
+            P.p1 = c16 < P.lo1 + 99;
+            if (P.p1) P.v1 = __ldg(reinterpret_cast<const uint4*>(p + (g0 - P.lo1) + c16));
         }
         return true;
     }
-    __device__ __forceinline__ void commit(uint8_t* s_in, int tid, const uint4& v0, const uint4& v1, long long g_first) const {
-        {
-            const int r = tid >> 3, c = tid & 7;
-            const long long g0 = g_first + (long long)r * sw * 3, ga = (g0 & ~15ll) + c * 16;
-            if (ga < g0 + 99) *reinterpret_cast<uint4*>(s_in + r * kStemPitch + c * 16) = v0;
-            if (c == 0) s_in[17 * kStemPitch + r] = (uint8_t)(g0 & 15);
-        }
+    __device__ __forceinline__ void commit(uint8_t* s_in, int tid, const Patch& P) const {
+        const int r = tid >> 3, c16 = (tid & 7) * 16;
+        if (P.p0) *reinterpret_cast<uint4*>(s_in + r * kStemPitch + c16) = P.v0;
+        if (c16 == 0) s_in[17 * kStemPitch + r] = (uint8_t)P.lo0;
         if (tid < 8) {
-            const long long g0 = g_first + 16ll * sw * 3, ga = (g0 & ~15ll) + tid * 16;
-            if (ga < g0 + 99) *reinterpret_cast<uint4*>(s_in + 16 * kStemPitch + tid * 16) = v1;
-            if (tid == 0) s_in[17 * kStemPitch + 16] = (uint8_t)(g0 & 15);
+            if (P.p1) *reinterpret_cast<uint4*>(s_in + 16 * kStemPitch + c16) = P.v1;
+            if (tid == 0) s_in[17 * kStemPitch + 16] = (uint8_t)P.lo1;
         }
     }
     __device__ __forceinline__ void load(int b, int y, int x, int H, int W, float (&rgb)[3]) const {
@@ -261,8 +278,10 @@ template <typename T>
 struct LoadPlanar {   // [B][3][H][W] RGB in [0,1]; the tensor core consumes bf16(255 x) (exact for uint8-derived inputs)
     static constexpr bool kStaged = false, kMagic = false;
     const T* p;
-    __device__ __forceinline__ bool fetch(int, int, int, int, uint4&, uint4&, long long&) const { return false; }
-    __device__ __forceinline__ void commit(uint8_t*, int, const uint4&, const uint4&, long long) const {}
+    struct Patch {};
+    __device__ __forceinline__ int row_offset(int) const { return 0; }
+    __device__ __forceinline__ bool fetch(int, int, int, int, int, Patch&) const { return false; }
+    __device__ __forceinline__ void commit(uint8_t*, int, const Patch&) const {}
     __device__ __forceinline__ void load(int b, int y, int x, int H, int W, float (&rgb)[3]) const {
         if (y < 0 || x < 0 || y >= H || x >= W) { rgb[0] = rgb[1] = rgb[2] = 0.f; return; }
         const size_t plane = (size_t)H * W;
@@ -281,7 +300,10 @@ int launch_stem(Loader ld, int B, int H, int W, const void* w, const float* bias
     while (cols < (uint32_t)n_tile) cols <<= 1;
     const int tiles_w = b2_ceil_div(Wo, 16), tiles_h = b2_ceil_div(Ho, 8);
     const long long total = (long long)tiles_w * tiles_h * B;
-    const int per_sm = (int)(512 / cols) < 8 ? (int)(512 / cols) : 8;       // TMEM columns bound the co-resident CTAs
+    // (a two-role variant -- 128 builder + 128 drainer threads, two tiles in flight per CTA, four CTAs per SM -- was slower: 0.71 vs
+    //  0.58 ms; the kernel is bound by instruction issue and the shared-memory pipe, not by the serial phases of a tile)
+    if ((long long)B * Ho * Wo >= (1ll << 31)) { b2_set_error("stem: B * Ho * Wo exceeds 2^31"); return B2_ERR_UNSUPPORTED; }
+    const int per_sm = (int)(512 / cols) < B2_STEM_CTAS ? (int)(512 / cols) : B2_STEM_CTAS;       // TMEM columns bound the co-resident CTAs
     const long long slots = (long long)b2_num_sms() * per_sm;
     const int grid = (int)(total < slots ? total : slots);
     stem_tc_kernel<Loader><<<grid, kStemThreads, 0, st>>>(ld, B, H, W, Ho, Wo, (const __nv_bfloat16*)w, bias, 1.f / 255.f, C0, n_tile, cols,
