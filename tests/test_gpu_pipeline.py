@@ -149,3 +149,30 @@ def test_yolo_loads_a_pt_checkpoint(tmp_path):
     assert a[0].names[5] == "c5"
     for ra, rb in zip(a, b):
         assert len(ra) > 0 and torch.equal(ra.boxes.data, rb.boxes.data)
+
+
+def test_predict_and_track_from_files(tmp_path):
+    """YOLO.predict / YOLO.track on file sources (data/loaders.py ingest in front of the engine): a directory of PNGs gives exactly
+    the detections of the decoded arrays; a video file streams Results frame by frame with track ids and the file path."""
+    import os
+    import sys
+
+    cv2 = pytest.importorskip("cv2")
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_host import _write_media
+
+    from b200dt.predictor import YOLO
+
+    imgs, clip = _write_media(tmp_path, n_img=3, n_vid=6, hw=(256, 320))
+    model = YOLO("yolov8n-p2.yaml")
+    a = model.predict(str(tmp_path / "im*.png"), conf=0.15, iou=0.6, batch=2)
+    b = model.predict(imgs, conf=0.15, iou=0.6)
+    assert len(a) == 3 and [os.path.basename(r.path) for r in a] == ["im0.png", "im1.png", "im2.png"]
+    for ra, rb in zip(a, b):
+        assert torch.equal(ra.boxes.data, rb.boxes.data)
+    n = 0
+    for r in model.track(clip, stream=True, conf=0.15, iou=0.6, batch=4):
+        assert r.path.endswith("clip.avi") and r.orig_shape == (256, 320)
+        assert len(r) == 0 or r.boxes.is_track
+        n += 1
+    assert n == 6

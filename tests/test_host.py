@@ -342,3 +342,57 @@ torch.save({k: v for k, v in m.state_dict().items()}, sys.argv[3])
             assert a.read_text() == b.read_text() and a.read_text().count("\n") == 2
         assert mine.plot().shape == img.shape and mine.plot().any()
     assert Results(img, "a.jpg", names, np.zeros((0, 6), np.float32)).summary() == []
+
+
+def _write_media(tmp_path, n_img=3, n_vid=7, hw=(96, 128)):
+    import cv2
+
+    from b200dt import synth
+
+    vid = synth.IRStream(seed=11, h=hw[0], w=hw[1], n_targets=3)
+    imgs = []
+    for i in range(n_img):
+        f = vid.frame()
+        cv2.imwrite(str(tmp_path / f"im{i}.png"), f)
+        imgs.append(f)
+    path = str(tmp_path / "clip.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25, (hw[1], hw[0]))
+    assert wr.isOpened()
+    for _ in range(n_vid):
+        wr.write(vid.frame())
+    wr.release()
+    return imgs, path
+
+
+def test_file_loader_matches_reference(tmp_path, monkeypatch):
+    """N3: loaders.LoadImagesAndVideos (data/loaders.py:346-490) on a directory with PNG images and an MJPG clip: images first then
+    the video, batches of `batch` frames, `vid_stride`, glob / .txt sources; decoded frames equal the PNG contents exactly, and the
+    batch sequence equals the reference loader's when the reference checkout is present."""
+    cv2 = pytest.importorskip("cv2")
+    from b200dt.loaders import LoadImagesAndVideos
+
+    imgs, clip = _write_media(tmp_path)
+    ds = LoadImagesAndVideos(str(tmp_path), batch=2)
+    got = [(p, [i.copy() for i in im]) for p, im, _ in ds]
+    flat = [(os.path.basename(p), im) for ps, ims in got for p, im in zip(ps, ims)]
+    assert [n for n, _ in flat] == ["im0.png", "im1.png", "im2.png"] + ["clip.avi"] * 7
+    assert [len(ims) for _, ims in got] == [2, 1, 2, 2, 2, 1]               # the image list ends a batch (loaders.py:478-479)
+    for k in range(3):
+        assert np.array_equal(flat[k][1], imgs[k])
+    assert all(im.shape == (96, 128, 3) and im.dtype == np.uint8 for _, im in flat)
+    assert sum(len(im) for _, im, _ in LoadImagesAndVideos(clip, batch=4, vid_stride=2)) == 3
+    assert sum(len(im) for _, im, _ in LoadImagesAndVideos(str(tmp_path / "im*.png"), batch=8)) == 3
+    (tmp_path / "list.txt").write_text("im2.png\nim0.png\n")
+    assert [os.path.basename(p) for ps, _, _ in LoadImagesAndVideos(str(tmp_path / "list.txt")) for p in ps] == ["im0.png", "im2.png"]
+    with pytest.raises(FileNotFoundError):
+        LoadImagesAndVideos(str(tmp_path / "nope.mp4"))
+    if os.path.isdir("/root/reference/ultralytics"):
+        monkeypatch.setenv("YOLO_CONFIG_DIR", str(tmp_path / "cfg"))
+        monkeypatch.syspath_prepend("/root/reference")
+        from ultralytics.data.loaders import LoadImagesAndVideos as Ref
+
+        for kw in (dict(batch=2), dict(batch=3, vid_stride=2)):
+            a = [(p, [i.copy() for i in im]) for p, im, _ in LoadImagesAndVideos(str(tmp_path), **kw)]
+            b = [(p, [i.copy() for i in im]) for p, im, _ in Ref(str(tmp_path), **kw)]
+            assert [p for p, _ in a] == [p for p, _ in b]
+            assert all(np.array_equal(x, y) for (_, xs), (_, ys) in zip(a, b) for x, y in zip(xs, ys))

@@ -12,6 +12,7 @@ with the three stages executed by the CUDA library: stem-fused preprocess + forw
 from __future__ import annotations
 
 import math
+import os
 import time
 
 import numpy as np
@@ -319,8 +320,25 @@ class YOLO:
         return self.predict(source, stream, **kwargs)
 
     def predict(self, source=None, stream=False, **kwargs):
-        """engine/model.py:498-557.  source: HWC BGR uint8 ndarray, list of them, or a BCHW float tensor in [0,1]."""
+        """engine/model.py:498-557.  source: HWC BGR uint8 ndarray, list of them, a BCHW float tensor in [0,1], or a path / glob /
+        directory / .txt list of image and video files (data/loaders.py LoadImagesAndVideos; ``batch`` frames per forward,
+        ``vid_stride``; with ``stream=True`` a generator, as the reference asks for long videos)."""
         import torch
+
+        if isinstance(source, (str, os.PathLike)) or (isinstance(source, (list, tuple)) and source and isinstance(source[0], (str, os.PathLike))):
+            from .loaders import LoadImagesAndVideos
+
+            ds = LoadImagesAndVideos(source if not isinstance(source, os.PathLike) else str(source), batch=int(kwargs.pop("batch", self.overrides["batch"])),
+                                     vid_stride=int(kwargs.pop("vid_stride", 1)))
+            self.dataset = ds
+
+            def gen():
+                for paths, imgs, _ in ds:
+                    for r, pth in zip(self.predict(imgs, False, **kwargs), paths):
+                        r.path = pth
+                        yield r
+
+            return gen() if stream else list(gen())
 
         a = {**self.overrides, **kwargs}
         if a.get("predictor") is not None:
@@ -409,6 +427,18 @@ class YOLO:
         kwargs["conf"] = kwargs.get("conf") or 0.1
         if not (persist and getattr(self, "trackers", None)):
             self.trackers = [cls(tracker, frame_rate=30)]
+        if isinstance(source, (str, os.PathLike)) or (isinstance(source, (list, tuple)) and source and isinstance(source[0], (str, os.PathLike))):
+            # file sources: frames arrive batch by batch; the tracker is reset when the file changes (track.py:87-89, persist=False)
+            def gen():
+                last = None
+                for r in self.predict(source, True, **kwargs):
+                    if not persist and last is not None and r.path != last:
+                        self.trackers[0].reset()
+                    last = r.path
+                    byte_tracker.update_results(self.trackers, [r], is_stream=False)
+                    yield r
+
+            return gen() if stream else list(gen())
         results = list(self.predict(source, False, **kwargs))
         byte_tracker.update_results(self.trackers, results, is_stream=False)
         return iter(results) if stream else results
