@@ -185,20 +185,26 @@ struct HeadParams {
 // One thread tests kHcPer anchors of one (level, image), a block apart (coalesced 8-byte loads of {logit, class} records), all of
 // them issued before any is used.  The kernel moves 8 bytes per anchor; the sigmoid, the box and the 16-byte distance record
 // are touched only for the per-cent of anchors whose logit clears logit_lo (then the reference's exact test `score > conf`).
-constexpr int kHcPer = 8;
+#ifndef B2_HC_PER
+#define B2_HC_PER 4
+#endif
+#ifndef B2_HC_THREADS
+#define B2_HC_THREADS 128
+#endif
+constexpr int kHcPer = B2_HC_PER, kHcThreads = B2_HC_THREADS;      // experiment builds: tools/build_variant.sh
 
-__global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p) {
+__global__ void __launch_bounds__(kHcThreads) head_candidates_kernel(const HeadParams p) {
     const int lane = threadIdx.x & 31;
     int lvl = 0;
 #pragma unroll
     for (int l = 1; l < kMaxLevels; ++l) if (l < p.n_levels && (int)blockIdx.x >= p.blk_off[l]) lvl = l;
     const int W = p.w[lvl], HW = p.h[lvl] * W, b = blockIdx.y;
     const float2* cp = reinterpret_cast<const float2*>(p.cls[lvl]) + (size_t)b * HW;
-    const int la0 = ((int)blockIdx.x - p.blk_off[lvl]) * (256 * kHcPer) + threadIdx.x;
+    const int la0 = ((int)blockIdx.x - p.blk_off[lvl]) * (kHcThreads * kHcPer) + threadIdx.x;
     float2 c[kHcPer];
 #pragma unroll
     for (int k = 0; k < kHcPer; ++k) {
-        const int la = la0 + k * 256;
+        const int la = la0 + k * kHcThreads;
         c[k] = la < HW ? __ldg(cp + la) : make_float2(-INFINITY, 0.f);
     }
     const float lo = p.logit_lo;
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(256) head_candidates_kernel(const HeadParams p
     for (int k = 0; k < kHcPer; ++k) {
         const float logit = c[k].x;
         const int bidx = (int)c[k].y;
-        const int la = la0 + k * 256;
+        const int la = la0 + k * kHcThreads;
         bool is_cand = false;
         float score = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
         if (logit > lo) {
@@ -612,13 +618,14 @@ extern "C" int b2_candidates_from_head(const float* const* level_dist, const flo
     B2_REQUIRE(conf > 0.f && conf < 1.f, "candidates: conf must be in (0, 1)");
     p.logit_lo = logf(conf / (1.f - conf)) - 0.05f;
     p.blk_off[0] = 0;
-    for (int l = 0; l < n_levels; ++l) p.blk_off[l + 1] = p.blk_off[l] + b2_ceil_div(level_h[l] * level_w[l], 256 * kHcPer);
+    for (int l = 0; l < n_levels; ++l) p.blk_off[l + 1] = p.blk_off[l] + b2_ceil_div(level_h[l] * level_w[l], kHcThreads * kHcPer);
     p.cand = cand; p.cand_idx = cand_idx; p.cand_count = cand_count; p.cand_cap = cand_cap;
     cudaStream_t st = (cudaStream_t)stream;
     B2_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * B, st));
-    // (one block per chunk: a one-wave grid walking several chunks per block, and 16-byte loads of record pairs, both measured
-    //  SLOWER at the bench size -- 32-33 us against 26.5 us, tools/hbm_probe.py)
-    head_candidates_kernel<<<dim3(p.blk_off[n_levels], B), 256, 0, st>>>(p);
+    // (one block per chunk.  Measured at the bench size, 256 images x 27 200 anchors, L2 flushed: 128 threads x 4 records 22.6 us;
+    //  256 x 8 26.6; 256 x 4 and 128 x 8 24.6; 64 x 2 36.9; a one-wave grid walking several chunks per block 32; 16-byte loads of
+    //  record pairs 33: the kernel is a short burst of loads, finer blocks fill and drain the SMs more evenly)
+    head_candidates_kernel<<<dim3(p.blk_off[n_levels], B), kHcThreads, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
     b2_count_launch(1);
     return B2_OK;

@@ -49,7 +49,10 @@ constexpr float kJumpThr = 40.f, kVelThr = 60.f, kSizeThr = 0.3f;      // :46-48
 constexpr int kResetCooldown = 15;                                     // :49
 constexpr int kVelRing = 50;       // deque(maxlen=50)  enhanced_aircraft_kalman_tracker.py:79
 constexpr int kTraj = B2_TRAJ_LEN; // only the last 30 trajectory points are ever read (:377)
-constexpr int kChunk = 256;        // slots per sweep block
+#ifndef B2_SWEEP_CHUNK
+#define B2_SWEEP_CHUNK 256
+#endif
+constexpr int kChunk = B2_SWEEP_CHUNK;        // slots per sweep block (experiment builds: 128 with B2_SWEEP_BLOCKS=8)
 constexpr int kMaxDetsSmem = 1024;
 constexpr int kResolveThreads = 512;
 constexpr int kCtSmem = 1024;      // candidate tracks whose match keys live in shared memory (more -> dense fallback)
