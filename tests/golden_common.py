@@ -139,7 +139,9 @@ def detection_set_report(dets, ref, cand, conf, iou_thres, seed=0, frame_hw=None
         if k not in got:
             errors.append(("decided reference detection missing", cand[k].tolist()))
     n_strict = int(sum(always[k] for k in ref_idx))
-    return {"n_ref": len(ref), "n_det": len(dets), "n_ref_strict": n_strict, "n_ref_in_band": len(ref) - n_strict,
+    n_matched = int(sum(k in got for k in ref_idx))              # reference rows the engine also reports (band or not), box within BOX_RTOL
+    return {"n_ref": len(ref), "n_det": len(dets), "n_ref_strict": n_strict, "n_ref_in_band": len(ref) - n_strict, "n_ref_matched": n_matched,
+            "n_det_not_in_ref": int(len(dets) - sum(1 for k in got if k in set(ref_idx))),
             "n_cand": m, "n_cand_in_band": int((~always & ~never).sum()), "errors": errors}
 
 

@@ -355,7 +355,7 @@ def test_predict_matches_reference_golden(name, gfile, tag, hw):
     model = YOLO(name + ".yaml")
     res = model.predict(frames, conf=0.15, iou=0.6, verbose=False)
     assert len(res) == 3
-    strict = total = band = 0
+    strict = total = band = matched = 0
     for b, r in enumerate(res):
         ref, cand = g[f"{tag}_exact_{b}"], g[f"{tag}_cand_{b}"]
         d = r.boxes.data.cpu().numpy()
@@ -364,13 +364,16 @@ def test_predict_matches_reference_golden(name, gfile, tag, hw):
         assert d[:, [0, 2]].min() >= 0 and d[:, [0, 2]].max() <= hw[1] and d[:, [1, 3]].max() <= hw[0]
         rep = detection_set_report(d, ref, cand, 0.15, 0.6, frame_hw=hw)
         _diag(f"predict {name} {tag} frame {b}: reference {rep['n_ref']} detections ({rep['n_ref_strict']} decided, {rep['n_ref_in_band']} in the "
-              f"band), engine {rep['n_det']}, violations {len(rep['errors'])}")
+              f"band), engine {rep['n_det']} ({rep['n_ref_matched']} of the reference rows, {rep['n_det_not_in_ref']} others), violations {len(rep['errors'])}")
         assert not rep["errors"], (b, rep["errors"][:5])
         # outside the band: the same set -- every decided reference row is there, and every engine row is either a decided
         # reference row or a band candidate
-        strict += rep["n_ref_strict"]; total += rep["n_ref"]; band += rep["n_ref_in_band"]
+        strict += rep["n_ref_strict"]; total += rep["n_ref"]; band += rep["n_ref_in_band"]; matched += rep["n_ref_matched"]
     if tag == "512x640":
         assert strict >= 0.6 * total, (strict, total)        # the band must not swallow the comparison
+    # band or not: how many of the reference's rows the engine reports with the box within 1e-2 (measured: 512x640 207 of 212,
+    # 500x640 -- 200 to 225 detections per frame, most of them clutter at the confidence threshold -- 530 of 633)
+    assert matched >= (0.93 if tag == "512x640" else 0.78) * total, (matched, total)
     # the reference API surface
     r = res[0]
     assert r.boxes.xyxy.shape[1] == 4 and r.boxes.conf.ndim == 1 and r.boxes.cls.ndim == 1 and r.boxes.id is None
