@@ -194,6 +194,18 @@ class MotionCompensatedMultiTracker:
         self._next += 1
         return t
 
+    def _should_global_reset(self):                       # :119-146
+        info = self.frame_motion_info
+        if not info or not info["should_reset"]:
+            return False
+        if len(self.detection_stability_history) >= 5:
+            recent = list(self.detection_stability_history)[-5:]
+            if np.std(recent) / (np.mean(recent) + 1) > 0.5:
+                return True
+        if len(self.global_motion_history) >= 3 and np.mean(list(self.global_motion_history)[-3:]) > 30.0:
+            return True
+        return info["magnitude"] > 60.0
+
     def associate(self, dets, preds):                     # :240-283
         if len(dets) == 0:
             return [], [], list(range(len(preds)))
@@ -212,9 +224,29 @@ class MotionCompensatedMultiTracker:
                 matched.append([d, t]); used_d.add(d); used_t.add(t)
         return matched, [d for d in range(len(dets)) if d not in used_d], [t for t in range(len(preds)) if t not in used_t]
 
-    def update(self, detections):                         # :76-117 (frame is None) + :168-238
+    def update(self, detections, frame=None):             # :75-117 + :168-238; frame drives the global detector (:92-114)
+        from collections import deque
+
         self.frame_count += 1
         self.stats["total_frames"] += 1
+        if not hasattr(self, "motion_detector"):
+            self.motion_detector = GlobalMotionDetector()
+            self.global_motion_history, self.detection_stability_history = deque(maxlen=20), deque(maxlen=10)
+            self.stats.setdefault("global_motion_events", 0); self.stats.setdefault("global_resets", 0)
+            self.frame_motion_info = None
+        global_motion = False
+        if frame is not None:
+            is_motion, mag, vec, should_reset = self.motion_detector.detect_motion(frame)
+            self.frame_motion_info = {"is_motion": is_motion, "magnitude": mag, "should_reset": should_reset}
+            self.global_motion_history.append(mag)
+            if should_reset:
+                global_motion = True
+                self.stats["global_motion_events"] += 1
+        self.detection_stability_history.append(len(detections))
+        if global_motion and self._should_global_reset():  # :116-117, :148-166: every track dropped, one new track per detection
+            self.stats["global_resets"] += 1
+            self.trackers = [self._new(d[:4]) for d in detections]
+            return [t.info() for t in self.trackers]
         preds = [t.predict() for t in self.trackers]
         if len(detections) > 0 and len(self.trackers) > 0:
             matched, um_d, um_t = self.associate(detections, preds)
@@ -236,3 +268,66 @@ class MotionCompensatedMultiTracker:
                 keep.append(t)
         self.trackers = keep
         return [t.info() for t in self.trackers]
+
+
+class GlobalMotionDetector:
+    """camera_motion_compensation/global_motion_detector.py, method 'optical_flow' (the tracker's default, :30-31 of the multi
+    tracker): corners of the PREVIOUS frame tracked into the current one, the global vector is the mean flow of the 75 % of
+    points closest to the median flow; motion above 30 px, reset above 50 px or above 45 px when the last three vectors point the
+    same way (:113-184, consistency :262-280).  The image operations are OpenCV's (third party): cvtColor, goodFeaturesToTrack,
+    calcOpticalFlowPyrLK, called with the reference's parameters."""
+
+    def __init__(self):
+        from collections import deque
+
+        self.prev_gray = None
+        self.motion_vectors = deque(maxlen=5)
+        self.motion_threshold, self.reset_threshold, self.consistency_threshold = 30.0, 50.0, 0.7
+        self.stats = {"total_detections": 0, "motion_events": 0, "reset_triggers": 0}
+
+    def detect_motion(self, frame):
+        import cv2
+
+        gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+        if self.prev_gray is None:
+            self.prev_gray = gray
+            return False, 0.0, np.array([0.0, 0.0]), False
+        res = self._flow(gray)
+        self.prev_gray = gray.copy()
+        self.stats["total_detections"] += 1
+        self.stats["motion_events"] += int(res[0]); self.stats["reset_triggers"] += int(res[3])
+        return res
+
+    def _flow(self, gray):
+        import cv2
+
+        none = (False, 0.0, np.array([0.0, 0.0]), False)
+        corners = cv2.goodFeaturesToTrack(self.prev_gray, maxCorners=200, qualityLevel=0.01, minDistance=15, blockSize=7)
+        if corners is None or len(corners) < 20:
+            return none
+        nxt, status, _ = cv2.calcOpticalFlowPyrLK(self.prev_gray, gray, corners, None, winSize=(21, 21), maxLevel=3,
+                                                  criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01))
+        if status is None:
+            return none
+        good = status.flatten() == 1
+        if np.sum(good) < 10:
+            return none
+        mv = nxt[good].reshape(-1, 2) - corners[good].reshape(-1, 2)
+        if len(mv) > 8:
+            dist = np.linalg.norm(mv - np.median(mv, axis=0), axis=1)
+            inl = dist < np.percentile(dist, 75)
+            if np.sum(inl) > 5:
+                g = np.mean(mv[inl], axis=0)
+                mag = np.linalg.norm(g)
+                self.motion_vectors.append(g)
+                is_motion, should_reset = mag > self.motion_threshold, mag > self.reset_threshold
+                if len(self.motion_vectors) >= 3:
+                    ang = [np.arctan2(v[1], v[0]) for v in list(self.motion_vectors)[-3:]]
+                    diffs = []
+                    for i in range(1, len(ang)):
+                        d = abs(ang[i] - ang[i - 1])
+                        diffs.append(2 * np.pi - d if d > np.pi else d)
+                    if max(0.0, 1.0 - np.mean(diffs) / np.pi) > self.consistency_threshold and is_motion:
+                        should_reset = should_reset or mag > self.motion_threshold * 1.5
+                return is_motion, mag, g, should_reset
+        return none

@@ -353,6 +353,35 @@ def gold_motion_multi():
     print("motion_multi", np.array(rows).shape, "stats", stats, "max tracks", max(counts))
 
 
+def gold_motion_frames():
+    """camera_motion_compensation/motion_compensated_multi_tracker.py, update(detections, frame): the GlobalMotionDetector (optical
+    flow, OpenCV) on a shaking / jolting camera scene, global resets included."""
+    sys.path.insert(0, REF)
+    from camera_motion_compensation.motion_compensated_multi_tracker import MotionCompensatedMultiTracker
+
+    from golden_common import motion_frames_scene
+
+    frames, script = motion_frames_scene()
+    rows, counts, mags, resets = [], [], [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        trk = MotionCompensatedMultiTracker(150, 1, 0.1)
+        for f, dets in enumerate(script):
+            res = trk.update([list(r) for r in dets], frames[f])
+            assert len(res) == len(trk.trackers)
+            counts.append(len(res))
+            mags.append(trk.frame_motion_info["magnitude"] if trk.frame_motion_info else 0.0)
+            resets.append(trk.stats["global_resets"])
+            for info, t in zip(res, trk.trackers):
+                rows.append(np.concatenate([np.asarray(info["bbox"], np.float64), t.x, [info["confidence"], t.reset_count, t.age, t.hits,
+                                            t.hit_streak, t.time_since_update, float(t.is_lost), t.lost_frames, t.motion_consistency,
+                                            info["frames_since_reset"]]]))
+    stats = [trk.stats["total_frames"], trk.stats["individual_resets"], trk.stats["tracking_recoveries"], trk.stats["global_resets"],
+             trk.stats["global_motion_events"]]
+    np.savez_compressed(os.path.join(HERE, "motion_frames.npz"), rows=np.array(rows), counts=np.array(counts), stats=np.array(stats),
+                        magnitude=np.array(mags), global_resets=np.array(resets))
+    print("motion_frames", np.array(rows).shape, "stats", stats, "max magnitude", max(mags))
+
+
 def gold_bytetrack():
     """The reference's BYTETracker (ultralytics/trackers/byte_tracker.py) over the scripted scene, default bytetrack.yaml values and a
     second parameterisation (no score fusion, short buffer).  `lap` (gatagat/lap) is not installed here: matching.py's import

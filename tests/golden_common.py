@@ -211,3 +211,37 @@ def botsort_scene(n_frames=50, seed=9, hw=(256, 320)):
         d[:, [1, 3]] -= off[1]
         out.append(d)
     return frames, out
+
+
+def motion_frames_scene(n_frames=60, seed=13, hw=(256, 320)):
+    """Frames + detections for the frame-driven path of the camera-motion tracker (N1): the textured world of botsort_scene seen
+    through a window that drifts a pixel or two per frame and JOLTS by 35-75 px at a few frames (global motion above the detector's
+    30 / 50 px thresholds, twice in the same direction on consecutive frames), detections shifted by the same offsets.
+    Returns (frames [n] (h, w, 3) uint8, dets [n] list of [x1, y1, x2, y2, conf] python floats)."""
+    g = np.random.default_rng(seed)
+    h, w = hw
+    pad = 220
+    world = np.zeros((h + 2 * pad, w + 2 * pad), np.float32)
+    yy, xx = np.mgrid[0:world.shape[0], 0:world.shape[1]]
+    for _ in range(420):                                             # broad spots: pyramidal LK must follow 60-px displacements
+        cx, cy, s, a = g.uniform(0, world.shape[1]), g.uniform(0, world.shape[0]), g.uniform(10.0, 26.0), g.uniform(12, 45)
+        x0, x1, y0, y1 = int(max(cx - 4 * s, 0)), int(min(cx + 4 * s + 1, world.shape[1])), int(max(cy - 4 * s, 0)), int(min(cy + 4 * s + 1, world.shape[0]))
+        world[y0:y1, x0:x1] += a * np.exp(-((xx[y0:y1, x0:x1] - cx) ** 2 + (yy[y0:y1, x0:x1] - cy) ** 2) / (2 * s * s))
+    world = np.clip(world + 20, 0, 255).astype(np.uint8)
+    dets = bytetrack_script(n_frames, 8, seed + 1, hw)
+    jolts = {12: (38, 0), 24: (58, 10), 25: (61, 8), 26: (40, 5), 40: (-70, -30), 41: (-66, -25), 52: (0, 75)}
+    off = np.zeros(2, int)
+    frames, out = [], []
+    for f in range(n_frames):
+        off = off + g.integers(-2, 3, 2)
+        if f in jolts:
+            off = off + np.array(jolts[f])
+        off = np.clip(off, -pad + 2, pad - 2)
+        win = world[pad + off[1]:pad + off[1] + h, pad + off[0]:pad + off[0] + w]
+        frames.append(np.ascontiguousarray(np.stack([win, win, win], -1)))
+        d = dets[f].astype(np.float64).copy()
+        d = d[d[:, 4] > 0.2]
+        d[:, [0, 2]] -= off[0]
+        d[:, [1, 3]] -= off[1]
+        out.append([[float(v) for v in r[:5]] for r in d])
+    return frames, out

@@ -415,5 +415,38 @@ def test_motion_compensated_multi_tracker_matches_reference():
     assert k == len(rows)
     assert worst_x < STATE_RTOL and worst_b < STATE_RTOL, (worst_x, worst_b)
     assert [trk.stats["total_frames"], trk.stats["individual_resets"], trk.stats["tracking_recoveries"]] == [int(v) for v in stats[:3]]
-    with pytest.raises(NotImplementedError):
-        trk.update([], frame=np.zeros((8, 8, 3), np.uint8))
+
+
+def test_motion_compensated_multi_tracker_with_frames_matches_reference():
+    """update(detections, frame): GlobalMotionDetector (host OpenCV optical flow, as the reference) in front of the CUDA bank on a
+    drifting / jolting camera scene (tests/golden/motion_frames.npz from the reference): the same motion magnitude every frame,
+    global resets at the same frames (all tracks dropped, the detections found new ones), the same track count, lifecycle
+    counters bit for bit and state to 1e-5 in between."""
+    from b200dt.tracker import MotionCompensatedMultiTracker
+
+    from golden_common import motion_frames_scene
+
+    g = np.load(os.path.join(G, "motion_frames.npz"))
+    rows, counts, stats = g["rows"], g["counts"], g["stats"]
+    assert stats[3] >= 2 and stats[4] > stats[3]                 # global resets happen, and some reset requests are declined
+    frames, script = motion_frames_scene()
+    trk = MotionCompensatedMultiTracker(150, 1, 0.1, capacity=64, max_dets=32)
+    k = 0
+    worst_x = worst_b = 0.0
+    for f, dets in enumerate(script):
+        res = trk.update([list(r) for r in dets], frames[f])
+        assert len(res) == counts[f], f"frame {f}"
+        assert abs((trk.frame_motion_info["magnitude"] if trk.frame_motion_info else 0.0) - g["magnitude"][f]) < 1e-4, f
+        assert trk.stats["global_resets"] == g["global_resets"][f], f
+        x, P, meta, _ = trk.bank.export(0)
+        for j, info in enumerate(res):
+            r = rows[k]; k += 1
+            exact_got = [info["reset_count"], info["age"], info["hits"], info["hit_streak"], info["time_since_update"], int(meta[j, 6]), int(meta[j, 5]),
+                         info["frames_since_reset"]]
+            assert exact_got == [int(v) for v in (r[13], r[14], r[15], r[16], r[17], r[18], r[19], r[21])], (f, j)
+            worst_b = max(worst_b, float(np.abs(np.asarray(info["bbox"]) - r[0:4]).max() / max(np.abs(r[0:4]).max(), 1.0)))
+            worst_x = max(worst_x, float(np.abs(x[j] - r[4:12]).max() / max(np.abs(r[4:12]).max(), 1.0)))
+    assert k == len(rows)
+    assert worst_x < STATE_RTOL and worst_b < STATE_RTOL, (worst_x, worst_b)
+    st = trk.stats
+    assert [st["total_frames"], st["individual_resets"], st["tracking_recoveries"], st["global_resets"], st["global_motion_events"]] == [int(v) for v in stats]

@@ -390,3 +390,31 @@ def test_botsort_oracle_matches_reference(tag, use_img):
         off += n
         assert len(r) == n and np.array_equal(r[:, 4:], ref[:, 4:]), f
         np.testing.assert_allclose(r[:, :4], ref[:, :4], rtol=0, atol=1e-4)
+
+
+def test_motion_tracker_with_frames_matches_reference():
+    """oracle.motion_reset.MotionCompensatedMultiTracker.update(detections, frame) -- the restated GlobalMotionDetector (optical
+    flow through the same OpenCV calls) and global-reset rules -- against the reference on the drifting / jolting camera scene:
+    motion magnitude, global resets, track counts and per-track state every frame."""
+    pytest.importorskip("cv2")
+    from golden_common import motion_frames_scene
+    from oracle.motion_reset import MotionCompensatedMultiTracker
+
+    g = _load("motion_frames.npz")
+    rows, counts, stats = g["rows"], g["counts"], g["stats"]
+    assert stats[3] >= 2 and stats[4] > stats[3]
+    frames, script = motion_frames_scene()
+    trk = MotionCompensatedMultiTracker(150, 1, 0.1)
+    k = 0
+    for f, dets in enumerate(script):
+        res = trk.update([list(r) for r in dets], frames[f])
+        assert len(res) == counts[f], f"frame {f}"
+        assert abs((trk.frame_motion_info["magnitude"] if trk.frame_motion_info else 0.0) - g["magnitude"][f]) < 1e-9
+        assert trk.stats["global_resets"] == g["global_resets"][f]
+        for info, t in zip(res, trk.trackers):
+            got = np.concatenate([np.asarray(info["bbox"], np.float64), t.x, [info["confidence"], t.reset_count, t.age, t.hits, t.hit_streak,
+                                  t.time_since_update, float(t.is_lost), t.lost_frames, t.motion_consistency, info["frames_since_reset"]]])
+            np.testing.assert_allclose(got, rows[k], rtol=1e-11, atol=1e-8, err_msg=f"frame {f}")
+            k += 1
+    assert k == len(rows)
+    assert [trk.stats[n] for n in ("total_frames", "individual_resets", "tracking_recoveries", "global_resets", "global_motion_events")] == [int(v) for v in stats]

@@ -248,8 +248,10 @@ class MotionCompensatedMultiTracker(EnhancedMultiTargetTracker):
     """Drop-in for camera_motion_compensation/motion_compensated_multi_tracker.py:18 on the CUDA track bank (mode 1):
     MotionResetKalmanTracker tracks (per-track jump / velocity / size reset detectors, cooldown, covariance rescale, blended
     association box), the subclass's own association (IoU > threshold, ties to the larger indices) and reporting of every
-    live track.  ``update(detections, frame=None)``: the global camera-motion detector (optical flow on ``frame``,
-    global_motion_detector.py) is not part of this path -- passing a frame raises."""
+    live track.  ``update(detections, frame)``: the frame feeds :class:`GlobalMotionDetector` (global_motion_detector.py: sparse
+    optical flow, OpenCV on the host exactly as the reference -- one decision per frame); when it asks for a reset and
+    ``_should_global_reset`` agrees (motion_compensated_multi_tracker.py:119-146) every track of the stream is dropped and the
+    frame's detections found new ones (:148-166): ``b2_tracker_reset`` + a normal update on the empty bank."""
 
     def __init__(self, max_lost_frames=150, min_hits=1, iou_threshold=0.1, capacity=512, max_dets=300):
         import torch
@@ -258,8 +260,15 @@ class MotionCompensatedMultiTracker(EnhancedMultiTargetTracker):
         self.bank = TrackerBank(1, capacity, max_dets, max_lost_frames, min_hits, iou_threshold, mode=1)
         self.frame_count = 0
         self.next_track_id = 1
-        self.stats = {"total_frames": 0, "individual_resets": 0, "tracking_recoveries": 0, "global_resets": 0}
+        self.stats = {"total_frames": 0, "global_motion_events": 0, "individual_resets": 0, "tracking_recoveries": 0, "global_resets": 0}
         self._active = 0
+        from collections import deque
+
+        self.motion_detector = GlobalMotionDetector()
+        self.global_motion_compensation = True
+        self.global_motion_history, self.detection_stability_history = deque(maxlen=20), deque(maxlen=10)
+        self.frame_motion_info = None
+        self._base = [0, 0]            # individual resets / recoveries counted by banks that a global reset has cleared since
         self._dets = torch.zeros((1, max_dets, 4), dtype=torch.float32, device=self.bank.device)
         self._host = torch.zeros((max_dets, 4), dtype=torch.float32).pin_memory()
         self._cnt = torch.zeros((1,), dtype=torch.int32, device=self.bank.device)
@@ -267,8 +276,21 @@ class MotionCompensatedMultiTracker(EnhancedMultiTargetTracker):
     def update(self, detections, frame=None):
         import torch
 
-        if frame is not None:
-            raise NotImplementedError("global camera-motion detection (GlobalMotionDetector, optical flow) is not implemented; call update(detections)")
+        self.frame_count += 1
+        global_motion = False
+        if frame is not None and self.global_motion_compensation:
+            is_motion, mag, vec, should_reset = self.motion_detector.detect_motion(frame)
+            self.frame_motion_info = {"is_motion": bool(is_motion), "magnitude": float(mag), "vector": np.asarray(vec).tolist(), "should_reset": bool(should_reset)}
+            self.global_motion_history.append(float(mag))
+            if should_reset:
+                global_motion = True
+                self.stats["global_motion_events"] += 1
+        self.detection_stability_history.append(len(detections))
+        if global_motion and self._should_global_reset():
+            self.stats["global_resets"] += 1
+            self._base = [self.stats["individual_resets"], self.stats["tracking_recoveries"]]
+            self.bank.reset()
+            self._active = 0
         n = len(detections)
         if n > self.bank.max_dets:
             raise ValueError(f"{n} detections exceed max_dets={self.bank.max_dets}")
@@ -286,8 +308,8 @@ class MotionCompensatedMultiTracker(EnhancedMultiTargetTracker):
         st = (C.c_longlong * 8)()
         _lib.check(self.bank.lib.b2_tracker_export(self.bank._h, 0, None, None, None, None, st))
         self._active = int(st[2])
-        self.frame_count, self.next_track_id = int(st[5]), int(st[6])
-        self.stats.update(total_frames=self.frame_count, individual_resets=int(st[3]), tracking_recoveries=int(st[4]))
+        self.next_track_id = int(st[6])
+        self.stats.update(total_frames=self.frame_count, individual_resets=self._base[0] + int(st[3]), tracking_recoveries=self._base[1] + int(st[4]))
         if st[7]:
             raise RuntimeError(f"track bank overflow: {int(st[7])} detections found no free slot")
         out = rows_to_dicts(r, tr, tl)
@@ -298,11 +320,98 @@ class MotionCompensatedMultiTracker(EnhancedMultiTargetTracker):
             d["motion_consistency"] = float(ex[j][2])
         return out
 
+    def _should_global_reset(self):
+        """motion_compensated_multi_tracker.py:119-146."""
+        info = self.frame_motion_info
+        if not info or not info["should_reset"]:
+            return False
+        if len(self.detection_stability_history) >= 5:
+            recent = list(self.detection_stability_history)[-5:]
+            if np.std(recent) / (np.mean(recent) + 1) > 0.5:
+                return True
+        if len(self.global_motion_history) >= 3 and np.mean(list(self.global_motion_history)[-3:]) > 30.0:
+            return True
+        return info["magnitude"] > 60.0
+
     def get_statistics(self):
         d = dict(self.stats)
         d["frame_count"] = self.frame_count
         d["active_trackers"] = self._active
+        d["motion_detector"] = dict(self.motion_detector.stats)
         return d
+
+
+class GlobalMotionDetector:
+    """camera_motion_compensation/global_motion_detector.py for its default method 'optical_flow' (:113-184): corners of the previous
+    frame (goodFeaturesToTrack) followed into the current one (calcOpticalFlowPyrLK); the global vector is the mean flow of the
+    points within the 75th percentile of the distance to the median flow; ``is_motion`` above 30 px, ``should_reset`` above 50 px, or
+    above 45 px when the last three vectors point the same way (consistency > 0.7, :262-280).  Host-side OpenCV as in the reference:
+    one small decision per frame in front of the GPU tracker, not a GPU path."""
+
+    def __init__(self, method="optical_flow"):
+        from collections import deque
+
+        if method != "optical_flow":
+            raise NotImplementedError(f"motion detection method {method!r}: only 'optical_flow' (the reference's default) is provided")
+        self.method = method
+        self.prev_gray = None
+        self.motion_history, self.motion_vectors = deque(maxlen=10), deque(maxlen=5)
+        self.global_motion_threshold, self.reset_motion_threshold, self.consistency_threshold = 30.0, 50.0, 0.7
+        self.stats = {"total_detections": 0, "motion_events": 0, "reset_triggers": 0, "avg_motion_magnitude": 0.0}
+
+    def detect_motion(self, frame):
+        """-> (is_motion, magnitude, vector, should_reset)."""
+        import cv2
+
+        gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+        if self.prev_gray is None:
+            self.prev_gray = gray
+            return False, 0.0, np.array([0.0, 0.0]), False
+        res = self._detect_by_optical_flow(gray)
+        self.prev_gray = gray
+        st = self.stats
+        st["total_detections"] += 1
+        st["motion_events"] += int(bool(res[0]))
+        st["reset_triggers"] += int(bool(res[3]))
+        st["avg_motion_magnitude"] = (st["avg_motion_magnitude"] * (st["total_detections"] - 1) + float(res[1])) / st["total_detections"]
+        return res
+
+    def _detect_by_optical_flow(self, gray):
+        import cv2
+
+        nothing = (False, 0.0, np.array([0.0, 0.0]), False)
+        corners = cv2.goodFeaturesToTrack(self.prev_gray, maxCorners=200, qualityLevel=0.01, minDistance=15, blockSize=7)
+        if corners is None or len(corners) < 20:
+            return nothing
+        nxt, status, _ = cv2.calcOpticalFlowPyrLK(self.prev_gray, gray, corners, None, winSize=(21, 21), maxLevel=3,
+                                                  criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01))
+        if status is None:
+            return nothing
+        ok = status.flatten() == 1
+        if ok.sum() < 10:
+            return nothing
+        flow = nxt[ok].reshape(-1, 2) - corners[ok].reshape(-1, 2)
+        if len(flow) <= 8:
+            return nothing
+        dist = np.linalg.norm(flow - np.median(flow, axis=0), axis=1)
+        near = dist < np.percentile(dist, 75)
+        if near.sum() <= 5:
+            return nothing
+        vec = np.mean(flow[near], axis=0)
+        mag = np.linalg.norm(vec)
+        self.motion_history.append(mag)
+        self.motion_vectors.append(vec)
+        is_motion, should_reset = mag > self.global_motion_threshold, mag > self.reset_motion_threshold
+        if len(self.motion_vectors) >= 3 and is_motion and self._consistency(list(self.motion_vectors)[-3:]) > self.consistency_threshold:
+            should_reset = should_reset or mag > self.global_motion_threshold * 1.5
+        return is_motion, mag, vec, should_reset
+
+    @staticmethod
+    def _consistency(vectors):
+        ang = [np.arctan2(v[1], v[0]) for v in vectors]
+        d = [abs(a - b) for a, b in zip(ang[1:], ang[:-1])]
+        d = [2 * np.pi - x if x > np.pi else x for x in d]
+        return max(0.0, 1.0 - np.mean(d) / np.pi)
 
 
 def direction_wrap(c):
