@@ -102,11 +102,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// B2_MBAR_NS (experiment builds only): suspend-time hint of try_wait in ns.  Measured (tools/ab_chain.py, same box): a 1 us or
-// 20 us hint makes the chained convs 1-3 % SLOWER than the plain form, although a waiting epilogue warp then runs far fewer
-// spin iterations -- the default wake-up is faster than the hinted one.  The product build uses no hint.
+// B2_MBAR_NS: suspend-time hint of try_wait in ns (0: the plain form).  A waiting warp runs ~17 iterations of the spin loop per
+// tile; the hint lets the hardware hold the thread a little longer per attempt.  Measured (one box, tools/ab_chain.py alone and
+// tools/sustained.py under the power cap): 1 us and 20 us hints wake the waiter late -- chained convs 1-3 % slower alone, 0.5 %
+// faster sustained; 200 ns is neutral-to-better on both (+0.3 % / +0.3 %) and is the default.
 #ifndef B2_MBAR_NS
-#define B2_MBAR_NS 0u
+#define B2_MBAR_NS 200u
 #endif
 constexpr uint32_t kMbarSuspendNs = B2_MBAR_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
