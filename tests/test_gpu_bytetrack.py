@@ -187,3 +187,41 @@ def test_botsort_matches_reference(tag, use_img):
         if n:
             worst = max(worst, float(np.abs(r[:, :4] - ref[:, :4]).max()))
     assert worst < 2e-3, worst
+
+
+def test_bytetracker_edge_frames_match_oracle():
+    """Frames the scripted scene does not have: no detections at all (every track goes lost, then is removed after track_buffer
+    frames), a single detection, only low-score detections, and recovery afterwards -- against the restated tracker fed the same
+    boxes (ids / states bit-exact, boxes within the fp32 tolerance)."""
+    from b200dt import byte_tracker as bt
+    from b200dt.predictor import Boxes
+
+    g = np.random.default_rng(4)
+    base = _boxes(g, 6, 400)
+    seq = []
+    for f in range(70):
+        if 10 <= f < 14 or 30 <= f < 65:
+            d = np.zeros((0, 6), np.float32)                                  # nothing detected
+        else:
+            b = base + np.float32(f) * np.array([1.5, 0.5, 1.5, 0.5], np.float32)
+            conf = np.full(6, 0.8, np.float32)
+            if f == 20:
+                b, conf = b[:1], conf[:1]                                     # a single box
+            if f in (22, 23):
+                conf = np.full(len(b), 0.15, np.float32)                      # low-score boxes only: second association alone
+            d = np.concatenate([b, conf[:, None], np.zeros((len(b), 1), np.float32)], 1)
+        seq.append(d)
+    trk, ora = bt.BYTETracker(None), obt.BYTETracker()
+    xywh = lambda d: np.stack([(d[:, 0] + d[:, 2]) / 2, (d[:, 1] + d[:, 3]) / 2, d[:, 2] - d[:, 0], d[:, 3] - d[:, 1]], 1).astype(np.float32)
+    for f, d in enumerate(seq):
+        r = np.asarray(trk.update(Boxes(d, (512, 640))), dtype=np.float32).reshape(-1, 8)
+        o = ora.update(xywh(d), d[:, 4], d[:, 5]).reshape(-1, 8)
+        assert r.shape == o.shape, (f, r.shape, o.shape)
+        assert np.array_equal(r[:, 4:], o[:, 4:]), f
+        if len(r):
+            assert np.abs(r[:, :4] - o[:, :4]).max() < 2e-3, f
+        sa = sorted((t.track_id, t.state) for t in trk.tracked_stracks + trk.lost_stracks)
+        sb = sorted((t.track_id, t.state) for t in ora.tracked_stracks + ora.lost_stracks)
+        assert sa == sb, f
+    # the six original tracks timed out in the long gap (track_buffer = 30 frames); the boxes of the last frames founded new ones
+    assert len(trk.removed_stracks) >= 6 and all(t.track_id > 6 for t in trk.tracked_stracks + trk.lost_stracks)
