@@ -271,120 +271,120 @@ class BYTETracker:
         STrack.shared_kalman = self.kalman_filter
         self.reset_id()
 
-    def _apply(self, pairs, activated, refind):
-        """KalmanFilterXYAH.update for every (track, detection) pair of one association stage in ONE launch, then the reference's
-        per-pair state change (update for tracked tracks, re_activate for lost ones: :346-353, :361-368, :380-382)."""
+    def _apply(self, pairs, touched):
+        """KalmanFilter.update for every (track, detection) pair of one association stage in ONE launch, then the reference's
+        per-pair state change: ``update`` for tracked tracks, ``re_activate`` for lost ones (:346-353, :361-368, :380-382).
+        ``touched`` collects the tracks, re-found ones flagged."""
         if not pairs:
             return
-        mm = np.asarray([t.mean for t, _ in pairs])
-        mc = np.asarray([t.covariance for t, _ in pairs])
-        zz = np.asarray([t.convert_coords(d.tlwh) for t, d in pairs], dtype=np.float32)
-        mm, mc = self.kalman_filter.update(mm, mc, zz)
-        for k, (t, d) in enumerate(pairs):
-            if t.state == TrackState.Tracked:
-                t.update(d, self.frame_id, mm[k], mc[k])
-                activated.append(t)
+        means, covs = self.kalman_filter.update(np.asarray([t.mean for t, _ in pairs]), np.asarray([t.covariance for t, _ in pairs]),
+                                                np.asarray([t.convert_coords(d.tlwh) for t, d in pairs], dtype=np.float32))
+        for (trk, det), m, c in zip(pairs, means, covs):
+            was_tracked = trk.state == TrackState.Tracked
+            if was_tracked:
+                trk.update(det, self.frame_id, m, c)
             else:
-                t.re_activate(d, self.frame_id, mm[k], mc[k], new_id=False)
-                refind.append(t)
+                trk.re_activate(det, self.frame_id, m, c, new_id=False)
+            touched.append((trk, not was_tracked))
+
+    def _stage(self, tracks, dets, thresh, fuse):
+        """One association stage: cost launch + assignment launch -> (pairs, unmatched track indices, unmatched detection indices)."""
+        cost = iou_distance(tracks, dets, [d.score for d in dets] if fuse else None)
+        matches, free_t, free_d = linear_assignment(cost, thresh=thresh)
+        return [(tracks[a], dets[b]) for a, b in matches], list(free_t), list(free_d)
 
     def update(self, results, img=None, feats=None):
-        """:299-410.  results: a ``Boxes``-like object on the host (``.conf``, ``.cls``, ``.xywh``, boolean-mask indexing)."""
+        """:299-410.  results: a ``Boxes``-like object on the host (``.conf``, ``.cls``, ``.xywh``, boolean-mask indexing).
+        Stages as in the reference: high-score boxes against tracked + lost tracks (threshold ``match_thresh``, scores fused when
+        ``fuse_score``), low-score boxes against the still-unmatched TRACKED tracks (plain IoU, 0.5), the remaining high-score
+        boxes against the one-frame-old unconfirmed tracks (0.7), then births, time-outs and de-duplication."""
         self.frame_id += 1
-        activated_stracks, refind_stracks, lost_stracks, removed_stracks = [], [], [], []
-        scores = np.asarray(results.conf)
-        remain_inds = scores >= self.args.track_high_thresh
-        inds_second = (scores > self.args.track_low_thresh) & (scores < self.args.track_high_thresh)
-        results_second = results[inds_second]
-        results = results[remain_inds]
-        detections = self.init_track(results)
-        unconfirmed = [t for t in self.tracked_stracks if not t.is_activated]
-        tracked_stracks = [t for t in self.tracked_stracks if t.is_activated]
-        # first association, high-score boxes
-        strack_pool = self.joint_stracks(tracked_stracks, self.lost_stracks)
-        self.multi_predict(strack_pool)
+        cfg_ = self.args
+        conf = np.asarray(results.conf)
+        high = conf >= cfg_.track_high_thresh
+        low = (conf > cfg_.track_low_thresh) & (conf < cfg_.track_high_thresh)
+        dets_high, dets_low = self.init_track(results[high]), None
+        confirmed = [t for t in self.tracked_stracks if t.is_activated]
+        tentative = [t for t in self.tracked_stracks if not t.is_activated]
+        pool = self.joint_stracks(confirmed, self.lost_stracks)
+        self.multi_predict(pool)
         if hasattr(self, "gmc") and img is not None:              # BoT-SORT: global motion compensation (:329-337)
             try:
                 warp = self.gmc.apply(img, None)
             except Exception:
                 warp = np.eye(2, 3)
-            STrack.multi_gmc(strack_pool, warp)
-            STrack.multi_gmc(unconfirmed, warp)
-        dists = self.get_dists(strack_pool, detections)
-        matches, u_track, u_detection = linear_assignment(dists, thresh=self.args.match_thresh)
-        self._apply([(strack_pool[it], detections[idt]) for it, idt in matches], activated_stracks, refind_stracks)
-        # second association, low-score boxes against the still-unmatched tracked tracks
-        detections_second = self.init_track(results_second)
-        r_tracked_stracks = [strack_pool[i] for i in u_track if strack_pool[i].state == TrackState.Tracked]
-        dists = iou_distance(r_tracked_stracks, detections_second)
-        matches, u_track, _ = linear_assignment(dists, thresh=0.5)
-        self._apply([(r_tracked_stracks[it], detections_second[idt]) for it, idt in matches], activated_stracks, refind_stracks)
-        for it in u_track:
-            track = r_tracked_stracks[it]
-            if track.state != TrackState.Lost:
-                track.mark_lost()
-                lost_stracks.append(track)
-        # unconfirmed tracks (one frame old) against the remaining high-score boxes
-        detections = [detections[i] for i in u_detection]
-        dists = self.get_dists(unconfirmed, detections)
-        matches, u_unconfirmed, u_detection = linear_assignment(dists, thresh=0.7)
-        self._apply([(unconfirmed[it], detections[idt]) for it, idt in matches], activated_stracks, refind_stracks)
-        for it in u_unconfirmed:
-            unconfirmed[it].mark_removed()
-            removed_stracks.append(unconfirmed[it])
-        # new tracks: one b2_kf_initiate launch
-        new = [detections[i] for i in u_detection if detections[i].score >= self.args.new_track_thresh]
-        if new:
-            zz = np.asarray([t.convert_coords(t._tlwh) for t in new], dtype=np.float32)
-            mm, mc = self.kalman_filter.initiate(zz)
-            for k, t in enumerate(new):
-                t.activate(self.kalman_filter, self.frame_id, mm[k], mc[k])
-                activated_stracks.append(t)
-        for track in self.lost_stracks:
-            if self.frame_id - track.end_frame > self.max_time_lost:
-                track.mark_removed()
-                removed_stracks.append(track)
-        self.tracked_stracks = [t for t in self.tracked_stracks if t.state == TrackState.Tracked]
-        self.tracked_stracks = self.joint_stracks(self.tracked_stracks, activated_stracks)
-        self.tracked_stracks = self.joint_stracks(self.tracked_stracks, refind_stracks)
-        self.lost_stracks = self.sub_stracks(self.lost_stracks, self.tracked_stracks)
-        self.lost_stracks.extend(lost_stracks)
-        self.lost_stracks = self.sub_stracks(self.lost_stracks, self.removed_stracks)
-        self.tracked_stracks, self.lost_stracks = self.remove_duplicate_stracks(self.tracked_stracks, self.lost_stracks)
-        self.removed_stracks.extend(removed_stracks)
+            STrack.multi_gmc(pool, warp)
+            STrack.multi_gmc(tentative, warp)
+        touched, newly_lost, dropped = [], [], []
+        # stage 1
+        pairs, free_t, free_d = self._stage(pool, dets_high, cfg_.match_thresh, cfg_.fuse_score)
+        self._apply(pairs, touched)
+        # stage 2: only tracks that were being tracked compete for the low-score boxes; the rest of stage 1's leftovers stay lost
+        dets_low = self.init_track(results[low])
+        still_tracked = [pool[k] for k in free_t if pool[k].state == TrackState.Tracked]
+        pairs, free_t2, _ = self._stage(still_tracked, dets_low, 0.5, False)
+        self._apply(pairs, touched)
+        for k in free_t2:
+            trk = still_tracked[k]
+            if trk.state != TrackState.Lost:
+                trk.mark_lost()
+                newly_lost.append(trk)
+        # stage 3
+        leftovers = [dets_high[k] for k in free_d]
+        pairs, free_u, free_d = self._stage(tentative, leftovers, 0.7, cfg_.fuse_score)
+        self._apply(pairs, touched)
+        for k in free_u:
+            tentative[k].mark_removed()
+            dropped.append(tentative[k])
+        # births: one b2_kf_initiate launch
+        born = [leftovers[k] for k in free_d if leftovers[k].score >= cfg_.new_track_thresh]
+        if born:
+            means, covs = self.kalman_filter.initiate(np.asarray([t.convert_coords(t._tlwh) for t in born], dtype=np.float32))
+            for trk, m, c in zip(born, means, covs):
+                trk.activate(self.kalman_filter, self.frame_id, m, c)
+                touched.append((trk, False))
+        for trk in self.lost_stracks:                              # time-outs
+            if self.frame_id - trk.end_frame > self.max_time_lost:
+                trk.mark_removed()
+                dropped.append(trk)
+        # list bookkeeping (:397-408): survivors, then this frame's updated / born tracks, then the re-found ones
+        alive = [t for t in self.tracked_stracks if t.state == TrackState.Tracked]
+        alive = self.joint_stracks(alive, [t for t, refound in touched if not refound])
+        alive = self.joint_stracks(alive, [t for t, refound in touched if refound])
+        lost = self.sub_stracks(self.lost_stracks, alive) + newly_lost
+        lost = self.sub_stracks(lost, self.removed_stracks)
+        self.tracked_stracks, self.lost_stracks = self.remove_duplicate_stracks(alive, lost)
+        self.removed_stracks = (self.removed_stracks + dropped)
         if len(self.removed_stracks) > 1000:
             self.removed_stracks = self.removed_stracks[-999:]
-        return np.asarray([x.result for x in self.tracked_stracks if x.is_activated], dtype=np.float32)
+        return np.asarray([t.result for t in self.tracked_stracks if t.is_activated], dtype=np.float32)
 
     @staticmethod
     def joint_stracks(tlista, tlistb):
-        exists, res = {}, []
-        for t in tlista:
-            exists[t.track_id] = 1
-            res.append(t)
-        for t in tlistb:
-            if not exists.get(t.track_id, 0):
-                exists[t.track_id] = 1
-                res.append(t)
-        return res
+        """:450-463: union keeping the first occurrence of every track id."""
+        seen, merged = set(), []
+        for trk in list(tlista) + list(tlistb):
+            if trk.track_id not in seen:
+                seen.add(trk.track_id)
+                merged.append(trk)
+        return merged
 
     @staticmethod
     def sub_stracks(tlista, tlistb):
-        ids = {t.track_id for t in tlistb}
-        return [t for t in tlista if t.track_id not in ids]
+        """:465-469."""
+        gone = {trk.track_id for trk in tlistb}
+        return [trk for trk in tlista if trk.track_id not in gone]
 
     @staticmethod
     def remove_duplicate_stracks(stracksa, stracksb):
-        pdist = iou_distance(stracksa, stracksb)
-        dupa, dupb = [], []
-        for p, q in zip(*np.where(pdist < 0.15)):
-            timep = stracksa[p].frame_id - stracksa[p].start_frame
-            timeq = stracksb[q].frame_id - stracksb[q].start_frame
-            if timep > timeq:
-                dupb.append(q)
-            else:
-                dupa.append(p)
-        return [t for i, t in enumerate(stracksa) if i not in dupa], [t for i, t in enumerate(stracksb) if i not in dupb]
+        """:471-485: of a tracked / lost pair that overlaps with IoU > 0.85 the one with the shorter history goes."""
+        close = np.argwhere(iou_distance(stracksa, stracksb) < 0.15)
+        drop_a, drop_b = set(), set()
+        for ia, ib in close:
+            span_a = stracksa[ia].frame_id - stracksa[ia].start_frame
+            span_b = stracksb[ib].frame_id - stracksb[ib].start_frame
+            (drop_b if span_a > span_b else drop_a).add(int(ib if span_a > span_b else ia))
+        return ([t for k, t in enumerate(stracksa) if k not in drop_a], [t for k, t in enumerate(stracksb) if k not in drop_b])
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -1,8 +1,11 @@
-"""Frame ingest for file sources: mirror of ``ultralytics/data/loaders.py`` ``LoadImagesAndVideos`` (:346-490) for image files,
-video files, directories, globs and ``.txt`` / ``.csv`` lists (``IMG_FORMATS`` / ``VID_FORMATS``: data/utils.py:39-40).
+"""Frame ingest for file sources, behaviour of ``ultralytics/data/loaders.py`` ``LoadImagesAndVideos`` (:346-490): image files,
+video files, directories, globs and ``.txt`` / ``.csv`` lists (suffix sets: data/utils.py:39-40), images before videos, batches of
+``batch`` frames where the end of the image list closes a batch, ``vid_stride`` frames grabbed per frame returned.
 
-Host-side plumbing in front of the hot path (OpenCV decode, as in the reference): it hands batches of HWC BGR uint8 frames to
+Host-side plumbing in front of the hot path (OpenCV decode, as in the reference): it hands HWC BGR uint8 frames to
 ``YOLO.predict`` / ``YOLO.track``; letterbox, colour conversion and normalisation happen inside the stem kernel on the GPU.
+Written as a frame generator plus a batcher (the reference is one ``__next__`` state machine); the batch sequence is checked
+against the reference loader in tests/test_host.py.
 """
 from __future__ import annotations
 
@@ -13,105 +16,120 @@ from pathlib import Path
 
 import numpy as np
 
-IMG_FORMATS = {"bmp", "dng", "jpeg", "jpg", "mpo", "png", "tif", "tiff", "webp", "pfm"}        # heic needs pi-heif: not provided
-VID_FORMATS = {"asf", "avi", "gif", "m4v", "mkv", "mov", "mp4", "mpeg", "mpg", "ts", "wmv", "webm"}
-FORMATS_HELP_MSG = f"Supported formats are:\nimages: {IMG_FORMATS}\nvideos: {VID_FORMATS}"
+IMG_FORMATS = frozenset("bmp dng jpeg jpg mpo png tif tiff webp pfm".split())            # heic needs pi-heif: not provided
+VID_FORMATS = frozenset("asf avi gif m4v mkv mov mp4 mpeg mpg ts wmv webm".split())
+FORMATS_HELP_MSG = f"Supported formats are:\nimages: {sorted(IMG_FORMATS)}\nvideos: {sorted(VID_FORMATS)}"
+
+
+def _suffix(name):
+    return name.rpartition(".")[2].lower()
+
+
+def expand_sources(path):
+    """Source spec -> absolute file names in the reference's order (sorted top-level entries, globs and directories expanded)."""
+    base = None
+    if isinstance(path, (str, Path)) and Path(path).suffix in (".txt", ".csv"):
+        listing = Path(path)
+        base = listing.parent
+        text = listing.read_text()
+        path = [item.strip() for item in (text.splitlines() if listing.suffix == ".txt" else text.split(","))]
+    names = []
+    for entry in (sorted(path) if isinstance(path, (list, tuple)) else [path]):
+        full = str(Path(entry).absolute())
+        if "*" in full:
+            names += sorted(glob.glob(full, recursive=True))
+        elif os.path.isdir(full):
+            names += sorted(glob.glob(os.path.join(full, "*.*")))
+        elif os.path.isfile(full):
+            names.append(full)
+        elif base is not None and (base / entry).is_file():
+            names.append(str((base / entry).absolute()))
+        else:
+            raise FileNotFoundError(f"{entry} does not exist")
+    return names
 
 
 class LoadImagesAndVideos:
-    """Iterates ``(paths, imgs, info)`` batches of up to ``batch`` frames; ``vid_stride`` skips video frames (grab without retrieve).
-    ``mode`` is 'image' or 'video' (what the reference's predictor uses to decide between one tracker per video)."""
+    """Iterate ``(paths, imgs, info)`` batches.  ``mode`` is 'image' or 'video' (what the reference's predictor looks at to decide
+    between one tracker per video and one per batch slot); ``frame`` / ``frames`` describe the video being read."""
 
     def __init__(self, path, batch=1, vid_stride=1, channels=3):
-        parent = None
-        if isinstance(path, (str, Path)) and Path(path).suffix in {".txt", ".csv"}:
-            parent, content = Path(path).parent, Path(path).read_text()
-            path = [p.strip() for p in (content.splitlines() if Path(path).suffix == ".txt" else content.split(","))]
-        files = []
-        for p in sorted(path) if isinstance(path, (list, tuple)) else [path]:
-            a = str(Path(p).absolute())
-            if "*" in a:
-                files.extend(sorted(glob.glob(a, recursive=True)))
-            elif os.path.isdir(a):
-                files.extend(sorted(glob.glob(os.path.join(a, "*.*"))))
-            elif os.path.isfile(a):
-                files.append(a)
-            elif parent and (parent / p).is_file():
-                files.append(str((parent / p).absolute()))
-            else:
-                raise FileNotFoundError(f"{p} does not exist")
-        images = [f for f in files if f.rpartition(".")[-1].lower() in IMG_FORMATS]
-        videos = [f for f in files if f.rpartition(".")[-1].lower() in VID_FORMATS]
-        self.files, self.ni, self.nf = images + videos, len(images), len(images) + len(videos)
-        self.video_flag = [False] * len(images) + [True] * len(videos)
-        self.mode = "video" if not images else "image"
-        self.vid_stride, self.bs, self.channels = vid_stride, batch, channels
-        self.cap = None
-        if self.nf == 0:
+        names = expand_sources(path)
+        stills = [n for n in names if _suffix(n) in IMG_FORMATS]
+        clips = [n for n in names if _suffix(n) in VID_FORMATS]
+        if not stills and not clips:
             raise FileNotFoundError(f"No images or videos found in {path}. {FORMATS_HELP_MSG}")
-        if videos:
-            self._new_video(videos[0])
+        self.files = stills + clips
+        self.ni, self.nf = len(stills), len(stills) + len(clips)
+        self.video_flag = [k >= self.ni for k in range(self.nf)]
+        self.mode = "image" if stills else "video"
+        self.bs, self.vid_stride, self.channels = int(batch), int(vid_stride), int(channels)
+        self.cap, self.frame, self.frames, self.fps = None, 0, 0, 0
+        self.count = 0
+        for clip in clips:                      # the reference opens its first video at construction: a broken file fails here
+            self._open(clip).release()
+            break
 
     def __len__(self):
         return math.ceil(self.nf / self.bs)
 
-    def __iter__(self):
-        self.count = 0
-        return self
-
-    def _new_video(self, path):
+    def _open(self, name):
         import cv2
 
+        cap = cv2.VideoCapture(name)
+        if not cap.isOpened():
+            raise FileNotFoundError(f"Failed to open video {name}")
+        self.fps = int(cap.get(cv2.CAP_PROP_FPS))
+        self.frames = int(cap.get(cv2.CAP_PROP_FRAME_COUNT) / self.vid_stride)
         self.frame = 0
-        self.cap = cv2.VideoCapture(path)
-        self.fps = int(self.cap.get(cv2.CAP_PROP_FPS))
-        if not self.cap.isOpened():
-            raise FileNotFoundError(f"Failed to open video {path}")
-        self.frames = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT) / self.vid_stride)
+        return cap
 
-    def __next__(self):
+    def _gray(self, im):
         import cv2
 
-        paths, imgs, info = [], [], []
-        while len(imgs) < self.bs:
-            if self.count >= self.nf:
-                if imgs:
-                    return paths, imgs, info
-                raise StopIteration
-            path = self.files[self.count]
-            if self.video_flag[self.count]:
-                self.mode = "video"
-                if not self.cap or not self.cap.isOpened():
-                    self._new_video(path)
-                success = False
-                for _ in range(self.vid_stride):
-                    success = self.cap.grab()
-                    if not success:
-                        break
-                if success:
-                    success, im0 = self.cap.retrieve()
-                    if success:
-                        if self.channels == 1:
-                            im0 = cv2.cvtColor(im0, cv2.COLOR_BGR2GRAY)[..., None]
-                        self.frame += 1
-                        paths.append(path); imgs.append(im0)
-                        info.append(f"video {self.count + 1}/{self.nf} (frame {self.frame}/{self.frames}) {path}: ")
-                        if self.frame == self.frames:
-                            self.count += 1
-                            self.cap.release()
-                else:
-                    self.count += 1
-                    if self.cap:
-                        self.cap.release()
-                    if self.count < self.nf:
-                        self._new_video(self.files[self.count])
-            else:
+        return cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)[..., None] if self.channels == 1 and im.ndim == 3 and im.shape[2] == 3 else im
+
+    def _items(self):
+        """One (file index, is_last_still, path, image, info) per decoded frame, in file order."""
+        import cv2
+
+        for k, name in enumerate(self.files):
+            self.count = k
+            if not self.video_flag[k]:
                 self.mode = "image"
-                im0 = cv2.imdecode(np.fromfile(path, np.uint8), cv2.IMREAD_GRAYSCALE if self.channels == 1 else cv2.IMREAD_COLOR)   # utils/patches.py imread
-                if im0 is not None:
-                    paths.append(path); imgs.append(im0 if im0.ndim == 3 else im0[..., None])
-                    info.append(f"image {self.count + 1}/{self.nf} {path}: ")
-                self.count += 1
-                if self.count >= self.ni:
-                    break
-        return paths, imgs, info
+                im = cv2.imdecode(np.fromfile(name, np.uint8), cv2.IMREAD_GRAYSCALE if self.channels == 1 else cv2.IMREAD_COLOR)
+                if im is None:
+                    continue                                  # unreadable image: skipped (the reference logs a warning)
+                yield k, k == self.ni - 1, name, (im if im.ndim == 3 else im[..., None]), f"image {k + 1}/{self.nf} {name}: "
+                continue
+            self.mode = "video"
+            self.cap = self._open(name)
+            try:
+                while True:
+                    alive = True
+                    for _ in range(self.vid_stride):          # grab vid_stride frames, decode only the last
+                        alive = self.cap.grab()
+                        if not alive:
+                            break
+                    if not alive:
+                        break
+                    ok, im = self.cap.retrieve()
+                    if not ok:
+                        continue
+                    self.frame += 1
+                    yield k, False, name, self._gray(im), f"video {k + 1}/{self.nf} (frame {self.frame}/{self.frames}) {name}: "
+                    if self.frame == self.frames:
+                        break
+            finally:
+                self.cap.release()
+        self.count = self.nf
+
+    def __iter__(self):
+        paths, imgs, info = [], [], []
+        for _, closes_batch, name, im, text in self._items():
+            paths.append(name); imgs.append(im); info.append(text)
+            if len(imgs) == self.bs or closes_batch:          # the end of the image list ends a batch (loaders.py:478-479)
+                yield paths, imgs, info
+                paths, imgs, info = [], [], []
+        if imgs:
+            yield paths, imgs, info
