@@ -176,3 +176,28 @@ def test_predict_and_track_from_files(tmp_path):
         assert len(r) == 0 or r.boxes.is_track
         n += 1
     assert n == 6
+
+
+def test_track_over_a_streams_file(tmp_path):
+    """YOLO.track(source='cams.streams'): LoadStreams hands one frame per source to one forward (batch = number of sources) and
+    every source has its own tracker (trackers/track.py:62-68); Results come back source by source with ids attached."""
+    cv2 = pytest.importorskip("cv2")
+    from b200dt import synth
+    from b200dt.predictor import YOLO
+
+    clips = []
+    for k in range(2):
+        vid = synth.IRStream(seed=70 + k, h=256, w=320)
+        path = str(tmp_path / f"cam{k}.avi")
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25, (320, 256))
+        for _ in range(5):
+            wr.write(vid.frame())
+        wr.release()
+        clips.append(path)
+    (tmp_path / "cams.streams").write_text("\n".join(clips))
+    model = YOLO("yolov8n-p2.yaml")
+    out = list(model.track(str(tmp_path / "cams.streams"), stream=True, conf=0.15, iou=0.6, stream_buffer=True))
+    assert len(out) == 10 and len(model.trackers) == 2 and model.dataset.mode == "stream"
+    assert [r.path for r in out[:4]] == [model.dataset.sources[0], model.dataset.sources[1]] * 2
+    assert model.trackers[0] is not model.trackers[1] and model.trackers[0].frame_id == 5 and model.trackers[1].frame_id == 5
+    assert all(r.boxes.is_track for r in out if len(r))

@@ -396,3 +396,50 @@ def test_file_loader_matches_reference(tmp_path, monkeypatch):
             b = [(p, [i.copy() for i in im]) for p, im, _ in Ref(str(tmp_path), **kw)]
             assert [p for p, _ in a] == [p for p, _ in b]
             assert all(np.array_equal(x, y) for (_, xs), (_, ys) in zip(a, b) for x, y in zip(xs, ys))
+
+
+def test_stream_loader_delivers_one_frame_per_source(tmp_path, monkeypatch):
+    """N3: loaders.LoadStreams (data/loaders.py:54-230) on a .streams file of three MJPG clips (7, 5 and 9 frames) with
+    buffer=True: every batch holds the next frame of every source, in order, until the shortest source runs dry (5 batches);
+    frames equal what a plain sequential cv2 read gives, and the reference loader's batches when the checkout is present."""
+    cv2 = pytest.importorskip("cv2")
+    from b200dt import synth
+    from b200dt.loaders import LoadStreams
+
+    clips, decoded = [], []
+    for k, n in enumerate((7, 5, 9)):
+        vid = synth.IRStream(seed=20 + k, h=96, w=128, n_targets=3)
+        path = str(tmp_path / f"cam{k}.avi")
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25, (128, 96))
+        for _ in range(n):
+            wr.write(vid.frame())
+        wr.release()
+        cap, fr = cv2.VideoCapture(path), []
+        while True:
+            ok, im = cap.read()
+            if not ok:
+                break
+            fr.append(im)
+        cap.release()
+        assert len(fr) == n
+        clips.append(path); decoded.append(fr)
+    listing = tmp_path / "cams.streams"
+    listing.write_text("\n".join(clips) + "\n")
+    ds = LoadStreams(str(listing), buffer=True)
+    assert ds.mode == "stream" and ds.bs == 3 and len(ds) == 3
+    got = [[im.copy() for im in imgs] for _, imgs, _ in ds]
+    assert len(got) == 5
+    for t, batch in enumerate(got):
+        assert len(batch) == 3 and all(np.array_equal(batch[k], decoded[k][t]) for k in range(3)), t
+    one = LoadStreams(clips[1], buffer=True)                             # a single source, vid_stride
+    assert one.bs == 1 and sum(1 for _ in one) == 5
+    assert sum(1 for _ in LoadStreams(clips[2], vid_stride=2, buffer=True)) == 5          # frame 0 + frames 2, 4, 6, 8
+    with pytest.raises(ConnectionError):
+        LoadStreams(str(tmp_path / "missing.avi"))
+    if os.path.isdir("/root/reference/ultralytics"):
+        monkeypatch.setenv("YOLO_CONFIG_DIR", str(tmp_path / "cfg"))
+        monkeypatch.syspath_prepend("/root/reference")
+        from ultralytics.data.loaders import LoadStreams as Ref
+
+        ref = [[im.copy() for im in imgs] for _, imgs, _ in Ref(str(listing), buffer=True)]
+        assert len(ref) == len(got) and all(np.array_equal(a, b) for x, y in zip(got, ref) for a, b in zip(x, y))

@@ -133,3 +133,109 @@ class LoadImagesAndVideos:
                 paths, imgs, info = [], [], []
         if imgs:
             yield paths, imgs, info
+
+
+class LoadStreams:
+    """Several live sources read concurrently, behaviour of ``ultralytics/data/loaders.py`` ``LoadStreams`` (:54-230): ``sources`` is
+    a ``*.streams`` text file (one source per whitespace-separated token) or a single source (a video file / device index / URL that
+    OpenCV can open).  One reader thread per source; every iteration hands out ONE frame per source -- the batch a multi-stream
+    detect+track step consumes (``mode == 'stream'``: one tracker per source).  ``buffer=False`` keeps only the newest frame of a
+    source (live cameras: drop what the consumer was too slow for), ``buffer=True`` queues up to 30 frames per source and delivers
+    every frame in order.  Iteration ends when a source has run dry and its reader has finished."""
+
+    mode = "stream"
+    QUEUE = 30
+
+    def __init__(self, sources="file.streams", vid_stride=1, buffer=False, channels=3):
+        import threading
+
+        import cv2
+
+        self.buffer, self.vid_stride, self.channels = bool(buffer), int(vid_stride), int(channels)
+        specs = Path(sources).read_text().split() if os.path.isfile(str(sources)) and str(sources).endswith(".streams") else [str(sources)]
+        self.bs = len(specs)
+        self.sources = ["".join(ch if ch.isalnum() or ch in "-." else "_" for ch in s) for s in specs]     # names safe for file paths
+        self.running = True
+        self.caps, self.queues, self.shape, self.fps, self.frames, self.threads = [], [], [], [], [], []
+        self._lock = threading.Lock()
+        for k, spec in enumerate(specs):
+            cap = cv2.VideoCapture(int(spec) if spec.isnumeric() else spec)
+            if not cap.isOpened():
+                raise ConnectionError(f"{k + 1}/{self.bs}: Failed to open {spec}")
+            rate = cap.get(cv2.CAP_PROP_FPS)
+            total = max(int(cap.get(cv2.CAP_PROP_FRAME_COUNT)), 0) or float("inf")                         # live sources report 0
+            ok, first = cap.read()
+            if not ok or first is None:
+                raise ConnectionError(f"{k + 1}/{self.bs}: Failed to read images from {spec}")
+            first = self._convert(first)
+            self.caps.append(cap); self.queues.append([first]); self.shape.append(first.shape)
+            self.fps.append(max((rate if math.isfinite(rate) else 0) % 100, 0) or 30); self.frames.append(total)
+            th = threading.Thread(target=self._reader, args=(k, cap, spec), daemon=True)
+            self.threads.append(th)
+        for th in self.threads:
+            th.start()
+
+    def _convert(self, im):
+        import cv2
+
+        return cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)[..., None] if self.channels == 1 else im
+
+    def _reader(self, k, cap, spec):
+        import time
+
+        seen = 0
+        while self.running and cap.isOpened() and seen < self.frames[k] - 1:
+            if len(self.queues[k]) >= self.QUEUE:
+                time.sleep(0.01)                      # the consumer is behind: wait instead of growing the queue
+                continue
+            seen += 1
+            cap.grab()
+            if seen % self.vid_stride:
+                continue
+            ok, im = cap.retrieve()
+            if ok:
+                im = self._convert(im)
+            else:                                     # signal lost: a black frame now, try to re-open the source
+                im = np.zeros(self.shape[k], dtype=np.uint8)
+                cap.open(int(spec) if spec.isnumeric() else spec)
+            with self._lock:
+                if self.buffer:
+                    self.queues[k].append(im)
+                else:
+                    self.queues[k] = [im]
+
+    def close(self):
+        self.running = False
+        for th in self.threads:
+            if th.is_alive():
+                th.join(timeout=5)
+        for cap in self.caps:
+            try:
+                cap.release()
+            except Exception:
+                pass
+
+    def __len__(self):
+        return self.bs
+
+    def __iter__(self):
+        import time
+
+        while True:
+            batch = []
+            for k in range(self.bs):
+                while not self.queues[k]:
+                    if not self.threads[k].is_alive():
+                        if not self.queues[k]:        # (re-checked: the reader may have queued its last frame just before it ended)
+                            self.close()
+                            return
+                        break
+                    time.sleep(1 / min(self.fps))
+                with self._lock:
+                    q = self.queues[k]
+                    if self.buffer:
+                        batch.append(q.pop(0))
+                    else:
+                        batch.append(q[-1] if q else np.zeros(self.shape[k], dtype=np.uint8))
+                        self.queues[k] = []
+            yield self.sources, batch, [""] * self.bs

@@ -326,10 +326,15 @@ class YOLO:
         import torch
 
         if isinstance(source, (str, os.PathLike)) or (isinstance(source, (list, tuple)) and source and isinstance(source[0], (str, os.PathLike))):
-            from .loaders import LoadImagesAndVideos
+            from .loaders import LoadImagesAndVideos, LoadStreams
 
-            ds = LoadImagesAndVideos(source if not isinstance(source, os.PathLike) else str(source), batch=int(kwargs.pop("batch", self.overrides["batch"])),
-                                     vid_stride=int(kwargs.pop("vid_stride", 1)))
+            batch, stride = int(kwargs.pop("batch", self.overrides["batch"])), int(kwargs.pop("vid_stride", 1))
+            src = str(source) if isinstance(source, os.PathLike) else source
+            if isinstance(src, str) and (src.endswith(".streams") or src.lower().startswith(("rtsp://", "rtmp://", "http://", "https://", "tcp://")) or src.isnumeric()):
+                ds = LoadStreams(src, vid_stride=stride, buffer=bool(kwargs.pop("stream_buffer", False)))       # data/build.py check_source
+            else:
+                kwargs.pop("stream_buffer", None)
+                ds = LoadImagesAndVideos(src, batch=batch, vid_stride=stride)
             self.dataset = ds
 
             def gen():
@@ -430,8 +435,16 @@ class YOLO:
         if isinstance(source, (str, os.PathLike)) or (isinstance(source, (list, tuple)) and source and isinstance(source[0], (str, os.PathLike))):
             # file sources: frames arrive batch by batch; the tracker is reset when the file changes (track.py:87-89, persist=False)
             def gen():
-                last = None
+                last, slot = None, 0
                 for r in self.predict(source, True, **kwargs):
+                    ds = self.dataset
+                    if getattr(ds, "mode", "") == "stream":               # one tracker per source (track.py:62-68), results arrive source by source
+                        if len(self.trackers) != ds.bs:
+                            self.trackers = [cls(tracker, frame_rate=30) for _ in range(ds.bs)]
+                        byte_tracker.update_results([self.trackers[slot]], [r], is_stream=False)
+                        slot = (slot + 1) % ds.bs
+                        yield r
+                        continue
                     if not persist and last is not None and r.path != last:
                         self.trackers[0].reset()
                     last = r.path
