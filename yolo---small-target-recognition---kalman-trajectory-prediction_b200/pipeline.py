@@ -170,6 +170,26 @@ class DetectTrackPipeline:
         torch.cuda.current_stream().wait_event(self._post_done)
 
 
+    def run(self, loader):
+        """The driver loop of kalman/aircraft_detection_tracking.py:88-109 for all sources at once: ``loader`` yields
+        ``(sources, frames, info)`` with one HWC BGR uint8 frame per stream (``loaders.LoadStreams``, or any iterable of such
+        batches).  Yields ``(sources, rows, counts)`` per frame time: numpy copies of the step's track rows [S][max_tracks_out][20]
+        and per-stream counts, after the reference-equivalence checks of :meth:`results`."""
+        import numpy as np
+        import torch
+
+        stage = torch.empty((self.S, self.h0, self.w0, 3), dtype=torch.uint8).pin_memory()
+        for sources, frames, _ in loader:
+            if len(frames) != self.S:
+                raise ValueError(f"the loader delivered {len(frames)} frames, the pipeline was built for {self.S} streams")
+            for k, f in enumerate(frames):
+                if f.shape != (self.h0, self.w0, 3):
+                    raise ValueError(f"stream {k}: frame shape {f.shape}, the pipeline was built for {(self.h0, self.w0, 3)}")
+                stage[k] = torch.from_numpy(np.ascontiguousarray(f))
+            self.step_host(stage)
+            rows, counts = self.results()                 # synchronises: `stage` may be refilled afterwards
+            yield sources, rows.numpy().copy(), counts.numpy().copy()
+
     def results(self):
         """Synchronise the last ``step_host`` and return its host block (rows [S][max_tracks_out][20], counts [S]) after
         checking that it is the reference's result: no detection was dropped for lack of a track slot (the reference's list
