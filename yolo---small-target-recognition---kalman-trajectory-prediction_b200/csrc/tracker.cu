@@ -302,18 +302,13 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
     const bool in = tid < chunk_slots;
     const int g = s * b.C + (in ? t : c * kChunk);
     const size_t N = b.N;
-    // ---- state of the slot into registers: every load is independent of every other (no look at the id first), ~29 coalesced
-    //      4-byte loads in flight per thread; dead slots of a live chunk are read and ignored ----
+    // ---- phase 1 loads: what decides the output positions -- id, state vector, age, time since update (11 coalesced 4-byte loads
+    //      per thread, independent of each other; dead slots of a live chunk are read and ignored) ----
     float x[8], p[6], m[6];
     int id = II(b, ID, g);
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = b.f[(size_t)(X0 + k) * N + g];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) p[k] = b.f[(size_t)(PPX + k) * N + g];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) m[k] = b.f[(size_t)(VAVGX + k) * N + g];
-    int age = II(b, AGE, g), hits = II(b, HITS, g), tsu = II(b, TSU, g);
-    int lostf = II(b, LOSTF, g), islost = II(b, ISLOST, g), tlen = II(b, TLEN, g), thead = II(b, THEAD, g);
+    int age = II(b, AGE, g), tsu = II(b, TSU, g);
     if (!in) id = 0;
     const bool live = id != 0;
     const int D = min(fr.det_counts[s], b.max_dets);
@@ -323,16 +318,12 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
     }
     __syncthreads();
 
-    // ---- predict (:184-203) ----
+    // ---- predict of the state vector (:184-203) and the candidate test ----
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
     int npairs = 0;
     if (live) {
         x[0] += x[4]; x[1] += x[5]; x[2] += x[6]; x[3] += x[7];
-        p[0] = p[0] + 2.f * p[1] + p[2] + Q_POS; p[1] = p[1] + p[2]; p[2] = p[2] + Q_VEL;
-        p[3] = p[3] + 2.f * p[4] + p[5] + Q_SIZE; p[4] = p[4] + p[5]; p[5] = p[5] + Q_SVEL;
         age += 1; tsu += 1;
-        b.traj[(size_t)(2 * thead) * N + g] = x[0]; b.traj[(size_t)(2 * thead + 1) * N + g] = x[1];
-        thead = thead + 1 == kTraj ? 0 : thead + 1; tlen = min(tlen + 1, kTraj);
         box = MODE ? blended_box(b, g, age, x[0], x[1], x[2], x[3])
                    : make_float4(x[0] - x[2] / 2.f, x[1] - x[3] / 2.f, x[0] + x[2] / 2.f, x[1] + x[3] / 2.f);   // state_to_bbox :121-135
         const float thr = b.iou_thr;
@@ -345,17 +336,39 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
         }
     }
     const bool cand = npairs > 0;
-    int emit = 0, terminated = 0, long_term = 0, freed = in && !live ? 1 : 0;
+    // should_delete (:385-405) of a track no detection can match: it is reported (emitted) unless it is deleted
+    const bool del = live && !cand && (tsu > b.max_lost || (age < 5 && tsu > 15) || (age < 10 && tsu > 30));
+    const int emit = (live && !cand && !del) ? 1 : 0;
+    // ---- phase 2 loads, issued now: covariance, motion statistics, lifecycle counters (18 loads).  Their latency runs under the
+    //      block scan, the publication of the chunk's counts and the other blocks' look-back, none of which needs them ----
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p[k] = b.f[(size_t)(PPX + k) * N + g];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m[k] = b.f[(size_t)(VAVGX + k) * N + g];
+    int hits = II(b, HITS, g);
+    int lostf = II(b, LOSTF, g), islost = II(b, ISLOST, g), tlen = II(b, TLEN, g), thead = II(b, THEAD, g);
+    // ---- positions: block scan + publication of this chunk's counts (the stream's later chunks look back over them) ----
+    unsigned long long total;
+    const unsigned long long mine = (unsigned long long)emit | ((unsigned long long)(cand ? 1 : 0) << 16) | ((unsigned long long)npairs << 32);
+    const unsigned long long off = sweep_scan(mine, s_warp, &total);
+    if (tid == 0) agg_publish(agg + c, total);
+
+    // ---- the rest of the predict: covariance, trajectory ring ----
+    if (live) {
+        p[0] = p[0] + 2.f * p[1] + p[2] + Q_POS; p[1] = p[1] + p[2]; p[2] = p[2] + Q_VEL;
+        p[3] = p[3] + 2.f * p[4] + p[5] + Q_SIZE; p[4] = p[4] + p[5]; p[5] = p[5] + Q_SVEL;
+        b.traj[(size_t)(2 * thead) * N + g] = x[0]; b.traj[(size_t)(2 * thead + 1) * N + g] = x[1];
+        thead = thead + 1 == kTraj ? 0 : thead + 1; tlen = min(tlen + 1, kTraj);
+    }
+    int terminated = 0, long_term = 0, freed = in && !live ? 1 : 0;
     float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f, conf = 0.f;
     if (live && !cand) {
-        // ---- no detection can match this track: mark_as_lost (:299-317), should_delete (:385-405), get_track_info (:335-383) ----
+        // ---- no detection can match this track: mark_as_lost (:299-317), delete, get_track_info (:335-383) ----
         if (!islost) { islost = 1; lostf = 0; }
         lostf += 1;
-        const bool del = tsu > b.max_lost || (age < 5 && tsu > 15) || (age < 10 && tsu > 30);
         if (del) { II(b, ID, g) = 0; terminated = 1; freed = 1; if (MODE && RI(b, MR_RESETS, g) > 0) atomicAdd(b.fcnt + s * 4 + 2, 1); }
         else {
-            emit = 1;                                            // a lost track is always reported (multi_target_tracker.py:117-126)
-            const int k = lostf;
+            const int k = lostf;                                 // a lost track is always reported (multi_target_tracker.py:117-126)
             if (k <= 1) {                                        // enhanced_long_term_predict(1) -> self.predict(), 1.0 (:216-217)
                 x[0] += x[4]; x[1] += x[5]; x[2] += x[6]; x[3] += x[7];
                 p[0] = p[0] + 2.f * p[1] + p[2] + Q_POS; p[1] = p[1] + p[2]; p[2] = p[2] + Q_VEL;
@@ -388,11 +401,7 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
         II(b, AGE, g) = age; II(b, TSU, g) = tsu; II(b, TLEN, g) = tlen; II(b, THEAD, g) = thead;
         if (!cand) { II(b, STREAK, g) = 0; II(b, LOSTF, g) = lostf; II(b, ISLOST, g) = 1; }
     }
-    // ---- positions: block scan + the aggregates of the stream's preceding chunks ----
-    unsigned long long total;
-    const unsigned long long mine = (unsigned long long)emit | ((unsigned long long)(cand ? 1 : 0) << 16) | ((unsigned long long)npairs << 32);
-    const unsigned long long off = sweep_scan(mine, s_warp, &total);
-    if (tid == 0) agg_publish(agg + c, total);
+    // ---- the aggregates of the stream's preceding chunks (published long ago by now) ----
     {
         unsigned long long before = 0ull;
         for (int i = tid; i < c; i += kChunk) before += agg_wait(agg + i);
