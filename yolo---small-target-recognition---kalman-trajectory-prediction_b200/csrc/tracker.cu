@@ -285,7 +285,6 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
     extern __shared__ float4 s_det[];                              // [D] detections of the stream
     __shared__ __align__(16) float s_rows[kChunk * B2_TRACK_COLS];
     __shared__ unsigned long long s_warp[kChunk / 32];
-    __shared__ unsigned long long s_prefix;
     __shared__ int s_cnt[3];
     const int tid = threadIdx.x;
     const int s = (int)(blockIdx.x / (unsigned)b.nchunks), c = (int)(blockIdx.x % (unsigned)b.nchunks);
@@ -296,7 +295,6 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
         if (tid == 0) agg_publish(agg + c, 0ull);
         return;
     }
-    if (tid == 0) s_prefix = 0ull;
     if (tid < 3) s_cnt[tid] = 0;
     const int t = c * kChunk + tid;
     const bool in = tid < chunk_slots;
@@ -401,12 +399,13 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
         II(b, AGE, g) = age; II(b, TSU, g) = tsu; II(b, TLEN, g) = tlen; II(b, THEAD, g) = thead;
         if (!cand) { II(b, STREAK, g) = 0; II(b, LOSTF, g) = lostf; II(b, ISLOST, g) = 1; }
     }
-    // ---- the aggregates of the stream's preceding chunks (published long ago by now) ----
-    {
-        unsigned long long before = 0ull;
-        for (int i = tid; i < c; i += kChunk) before += agg_wait(agg + i);
-        if (before) atomicAdd(&s_prefix, before);
-    }
+    // ---- the aggregates of the stream's preceding chunks (published long ago by now), summed by every warp for itself: from
+    //      here on a warp depends on no other warp of the block -- it stages its rows, copies them out and writes its list entries
+    //      as soon as ITS loads are back instead of waiting at a block barrier for the slowest warp (ncu: 30 % of the samples) ----
+    unsigned long long prefix = 0ull;
+    for (int i = tid & 31; i < c; i += 32) prefix += agg_wait(agg + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) prefix += __shfl_xor_sync(0xffffffffu, prefix, o);
     if (terminated) atomicAdd(&s_cnt[0], 1);
     if (long_term) atomicAdd(&s_cnt[1], 1);
     if (freed) atomicAdd(&s_cnt[2], 1);
@@ -418,16 +417,16 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
         sr[3] = make_float4(__int_as_float(1), x[4], x[5], m[PCONF - VAVGX]);
         sr[4] = make_float4(__int_as_float(m[STAB - VAVGX] > 0.5f ? 1 : 0), m[SPEED - VAVGX], m[DIRN - VAVGX], __int_as_float(t));
     }
-    __syncthreads();
-    const unsigned long long prefix = s_prefix;
-    const int n_emit = (int)(total & 0xFFFFu);
+    __syncwarp();
     const int e0 = (int)(prefix & 0xFFFFu), c0 = (int)((prefix >> 16) & 0xFFFFu);
-    // emitted rows of the chunk are contiguous in the output: coalesced 16-byte stores
+    // the rows a warp emits are contiguous in the block's order, hence in the output: coalesced 16-byte stores, warp by warp
     {
-        const float4* src4 = reinterpret_cast<const float4*>(s_rows);
-        float4* dst4 = reinterpret_cast<float4*>(fr.out_rows + ((size_t)s * fr.out_cap + e0) * B2_TRACK_COLS);
-        const int n4 = (min(e0 + n_emit, fr.out_cap) - e0) * (B2_TRACK_COLS / 4);
-        for (int i = tid; i < n4; i += kChunk) dst4[i] = src4[i];
+        const int w0 = (int)__shfl_sync(0xffffffffu, (unsigned)(off & 0xFFFFu), 0);        // rows emitted by the block before this warp
+        const int nw = __popc(__ballot_sync(0xffffffffu, emit != 0));
+        const float4* src4 = reinterpret_cast<const float4*>(s_rows + w0 * B2_TRACK_COLS);
+        float4* dst4 = reinterpret_cast<float4*>(fr.out_rows + ((size_t)s * fr.out_cap + e0 + w0) * B2_TRACK_COLS);
+        const int n4 = max(min(e0 + w0 + nw, fr.out_cap) - (e0 + w0), 0) * (B2_TRACK_COLS / 4);
+        for (int i = tid & 31; i < n4; i += 32) dst4[i] = src4[i];
     }
     if (MODE && emit && fr.out_extra && e0 + (int)(off & 0xFFFFu) < fr.out_cap)
         reinterpret_cast<float4*>(fr.out_extra)[(size_t)s * fr.out_cap + e0 + (int)(off & 0xFFFFu)] =
@@ -460,6 +459,7 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
             }
         }
     }
+    __syncthreads();                                   // every thread's count is in
     if (tid == 0) {
         b.chunk_free[(size_t)s * b.nchunks + c] = s_cnt[2];
         if (s_cnt[0]) atomicAdd(b.fcnt + s * 4 + 0, s_cnt[0]);
