@@ -742,6 +742,17 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
     const int E1 = (int)(s_tot & 0xFFFFu), T = (int)((s_tot >> 16) & 0xFFFFu);
     const unsigned long long M64 = s_tot >> 32;
     const int frame = b.frame_count[s] + 1;
+    // everything the last step (stats, counters) needs from global memory is requested now: on a frame with nothing to resolve the
+    // kernel is a chain of dependent round trips, and these would be the last links of it
+    const int id0 = b.next_id[s];
+    int fc0 = 0, fc1 = 0;                                  // (fcnt[2] is also incremented by this kernel: read at the end)
+    long long st_in[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (tid == 0) {
+        const int32_t* fcp = b.fcnt + s * 4;
+        fc0 = fcp[0]; fc1 = fcp[1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) st_in[k] = b.stats[(size_t)s * 8 + k];
+    }
     const float thr = b.iou_thr;
     const int32_t* cslot = b.ctrk_slot + (size_t)g0;
     const float4* cbox = b.cbox + (size_t)g0;
@@ -912,7 +923,6 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
 
     // ---- new tracks for unmatched detections, ascending detection index -> ascending ids; the k-th new track takes the k-th
     //      free slot of the stream ----
-    const int id0 = b.next_id[s];
     int n_new = 0;
     for (int base = 0; base < D; base += kResolveThreads) {
         const int d = base + tid;
@@ -966,9 +976,9 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, 
     if (tid == 0) {
         int32_t* fc = b.fcnt + s * 4;
         long long* st = b.stats + (size_t)s * 8;
-        const int terminated = fc[0] + s_cnt[0], lt = fc[1] + s_cnt[1];
-        st[0] += created; st[1] += terminated; st[2] += created - terminated; st[3] += lt; st[4] += s_cnt[2]; st[5] += n_new - created;
-        st[6] += s_cnt[3]; st[7] += fc[2];
+        const int terminated = fc0 + s_cnt[0], lt = fc1 + s_cnt[1];
+        st[0] = st_in[0] + created; st[1] = st_in[1] + terminated; st[2] = st_in[2] + created - terminated; st[3] = st_in[3] + lt;
+        st[4] = st_in[4] + s_cnt[2]; st[5] = st_in[5] + n_new - created; st[6] = st_in[6] + s_cnt[3]; st[7] = st_in[7] + fc[2];
         fc[0] = 0; fc[1] = 0; fc[2] = 0;
         // the reference numbers every unmatched detection; ids keep advancing even if the bank overflowed
         b.next_id[s] = id0 + n_new;
