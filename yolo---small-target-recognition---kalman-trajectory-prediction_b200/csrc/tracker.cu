@@ -529,33 +529,50 @@ __device__ void analyze_slot_warp(const Bank& b, int g, int lane) {
 
 // Kalman update with measurement z = bbox_to_state(det)  (:249-297); the motion analysis follows separately (one warp per track)
 __device__ __forceinline__ void update_slot(const Bank& b, int g, const float4& d) {
-    II(b, TSU, g) = 0; II(b, HITS, g) += 1; II(b, STREAK, g) += 1;
-    if (II(b, ISLOST, g)) { II(b, ISLOST, g) = 0; II(b, LOSTF, g) = 0; }
+    // Every field the update touches is loaded first, then everything is computed, then everything is stored.  Written as
+    // read-modify-writes on the bank (`FF(b, X0, g) += ...`) the compiler must assume that a store to the bank may alias the next
+    // load from it: ~25 global round trips one after the other, by ONE thread per matched track, with the other ~480 threads of
+    // the stream's CTA waiting at the next barrier (ncu: 43 % of the kernel's samples there).
+    const size_t N = b.N;
+    float x[8], pp[6];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = b.f[(size_t)(X0 + k) * N + g];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pp[k] = b.f[(size_t)(PPX + k) * N + g];
+    const int hits = II(b, HITS, g), streak = II(b, STREAK, g), islost = II(b, ISLOST, g);
+    const int head = II(b, VHEAD, g), nvel = II(b, NVEL, g), thead = II(b, THEAD, g), tlen = II(b, TLEN, g);
     const float z0 = (d.x + d.z) / 2.f, z1 = (d.y + d.w) / 2.f, z2 = d.z - d.x, z3 = d.w - d.y;
     {   // position block (x, y share the covariance triple)
-        const float pxx = FF(b, PPX, g), pxv = FF(b, PPV, g), pvv = FF(b, PVV, g);
+        const float pxx = pp[0], pxv = pp[1], pvv = pp[2];
         // (I - K H) P with 1 - K_x evaluated as R / S: no cancellation when P_xx >> R (long coasting tracks)
         const float S = pxx + R_MEAS, kx = pxx / S, kv = pxv / S, omk = R_MEAS / S;
-        const float y0 = z0 - FF(b, X0, g), y1 = z1 - FF(b, X1, g);
-        FF(b, X0, g) += kx * y0; FF(b, X4, g) += kv * y0;
-        FF(b, X1, g) += kx * y1; FF(b, X5, g) += kv * y1;
-        FF(b, PPX, g) = omk * pxx; FF(b, PPV, g) = omk * pxv; FF(b, PVV, g) = pvv - kv * pxv;
+        const float y0 = z0 - x[0], y1 = z1 - x[1];
+        x[0] += kx * y0; x[4] += kv * y0;
+        x[1] += kx * y1; x[5] += kv * y1;
+        pp[0] = omk * pxx; pp[1] = omk * pxv; pp[2] = pvv - kv * pxv;
     }
     {   // size block (w, h)
-        const float pxx = FF(b, PSX, g), pxv = FF(b, PSV, g), pvv = FF(b, PSVV, g);
+        const float pxx = pp[3], pxv = pp[4], pvv = pp[5];
         const float S = pxx + R_MEAS, kx = pxx / S, kv = pxv / S, omk = R_MEAS / S;
-        const float y2 = z2 - FF(b, X2, g), y3 = z3 - FF(b, X3, g);
-        FF(b, X2, g) += kx * y2; FF(b, X6, g) += kv * y2;
-        FF(b, X3, g) += kx * y3; FF(b, X7, g) += kv * y3;
-        FF(b, PSX, g) = omk * pxx; FF(b, PSV, g) = omk * pxv; FF(b, PSVV, g) = pvv - kv * pxv;
+        const float y2 = z2 - x[2], y3 = z3 - x[3];
+        x[2] += kx * y2; x[6] += kv * y2;
+        x[3] += kx * y3; x[7] += kv * y3;
+        pp[3] = omk * pxx; pp[4] = omk * pxv; pp[5] = pvv - kv * pxv;
     }
-    // velocity ring push, trajectory push
-    int head = II(b, VHEAD, g);
-    b.vel[(size_t)(2 * head) * b.N + g] = FF(b, X4, g);
-    b.vel[(size_t)(2 * head + 1) * b.N + g] = FF(b, X5, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b.f[(size_t)(X0 + k) * N + g] = x[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b.f[(size_t)(PPX + k) * N + g] = pp[k];
+    II(b, TSU, g) = 0; II(b, HITS, g) = hits + 1; II(b, STREAK, g) = streak + 1;
+    if (islost) { II(b, ISLOST, g) = 0; II(b, LOSTF, g) = 0; }
+    // velocity ring push, trajectory push (push_traj)
+    b.vel[(size_t)(2 * head) * N + g] = x[4];
+    b.vel[(size_t)(2 * head + 1) * N + g] = x[5];
     II(b, VHEAD, g) = head + 1 == kVelRing ? 0 : head + 1;
-    II(b, NVEL, g) = min(II(b, NVEL, g) + 1, kVelRing);
-    push_traj(b, g, FF(b, X0, g), FF(b, X1, g));
+    II(b, NVEL, g) = min(nvel + 1, kVelRing);
+    b.traj[(size_t)(2 * thead) * N + g] = x[0]; b.traj[(size_t)(2 * thead + 1) * N + g] = x[1];
+    II(b, THEAD, g) = thead + 1 == kTraj ? 0 : thead + 1;
+    II(b, TLEN, g) = min(tlen + 1, kTraj);
 }
 
 // AircraftKalmanTracker.__init__ (:23-101)
@@ -711,7 +728,7 @@ __device__ void emit_slot(const Bank& b, int g, float* out_row, float* traj_out,
 // (2) resolve: one CTA per stream on the candidate lists
 // ------------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const Bank b, const Frame fr) {
+__global__ void __launch_bounds__(kResolveThreads, 2) resolve_kernel(const Bank b, const Frame fr) {
     __shared__ float4 s_det[kMaxDetsSmem];
     __shared__ int s_dmatch[kMaxDetsSmem];
     __shared__ unsigned long long d_best[kMaxDetsSmem];      // sparse rounds: best key per detection; dense rounds: {best track, IoU}
