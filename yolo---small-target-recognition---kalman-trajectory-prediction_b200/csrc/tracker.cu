@@ -706,12 +706,16 @@ __device__ void emit_slot(const Bank& b, int g, float* out_row, float* traj_out,
     const int tsu = II(b, TSU, g);
     if (predicted && tsu > 30) *long_term += 1;
     if (!out_row) return;                                    // beyond the caller's row capacity: state side effects only
+    // every field first, then the five stores: a store to the row may alias the bank as far as the compiler knows, so loads
+    // written between the stores would each wait for the previous round trip
+    const int rid = II(b, ID, g), rage = II(b, AGE, g), rhits = II(b, HITS, g), rstreak = II(b, STREAK, g);
+    const float vx = FF(b, X4, g), vy = FF(b, X5, g), pc = FF(b, PCONF, g), stab = FF(b, STAB, g), spd = FF(b, SPEED, g), dirn = FF(b, DIRN, g);
     float4* o = reinterpret_cast<float4*>(out_row);
-    o[0] = make_float4(__int_as_float(II(b, ID, g)), bx - bw / 2.f, by - bh / 2.f, bx + bw / 2.f);
-    o[1] = make_float4(by + bh / 2.f, conf, __int_as_float(predicted), __int_as_float(II(b, AGE, g)));
-    o[2] = make_float4(__int_as_float(II(b, HITS, g)), __int_as_float(II(b, STREAK, g)), __int_as_float(tsu), __int_as_float(tsu));
-    o[3] = make_float4(__int_as_float(predicted), FF(b, X4, g), FF(b, X5, g), FF(b, PCONF, g));
-    o[4] = make_float4(__int_as_float(FF(b, STAB, g) > 0.5f ? 1 : 0), FF(b, SPEED, g), FF(b, DIRN, g), __int_as_float(slot));
+    o[0] = make_float4(__int_as_float(rid), bx - bw / 2.f, by - bh / 2.f, bx + bw / 2.f);
+    o[1] = make_float4(by + bh / 2.f, conf, __int_as_float(predicted), __int_as_float(rage));
+    o[2] = make_float4(__int_as_float(rhits), __int_as_float(rstreak), __int_as_float(tsu), __int_as_float(tsu));
+    o[3] = make_float4(__int_as_float(predicted), vx, vy, pc);
+    o[4] = make_float4(__int_as_float(stab > 0.5f ? 1 : 0), spd, dirn, __int_as_float(slot));
     if (traj_out) {
         const int len = II(b, TLEN, g), head = II(b, THEAD, g);
         int start = head - len; if (start < 0) start += kTraj;
