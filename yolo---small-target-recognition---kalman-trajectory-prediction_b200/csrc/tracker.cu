@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
     __shared__ __align__(16) float s_rows[kChunk * B2_TRACK_COLS];
     __shared__ unsigned long long s_warp[kChunk / 32];
     __shared__ int s_cnt[3];
+    __shared__ int s_done;                                         // warps that have finished (the last one writes the chunk's counters)
     const int tid = threadIdx.x;
     const int s = (int)(blockIdx.x / (unsigned)b.nchunks), c = (int)(blockIdx.x % (unsigned)b.nchunks);
     unsigned long long* agg = b.agg + (size_t)s * b.nchunks;
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
         return;
     }
     if (tid < 3) s_cnt[tid] = 0;
+    if (tid == 3) s_done = 0;
     const int t = c * kChunk + tid;
     const bool in = tid < chunk_slots;
     const int g = s * b.C + (in ? t : c * kChunk);
@@ -459,11 +461,16 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
             }
         }
     }
-    __syncthreads();                                   // every thread's count is in
-    if (tid == 0) {
-        b.chunk_free[(size_t)s * b.nchunks + c] = s_cnt[2];
-        if (s_cnt[0]) atomicAdd(b.fcnt + s * 4 + 0, s_cnt[0]);
-        if (s_cnt[1]) atomicAdd(b.fcnt + s * 4 + 1, s_cnt[1]);
+    // the chunk's counters go out with the LAST warp to get here (no block barrier: the other warps have left already)
+    __syncwarp();
+    if ((tid & 31) == 0) {
+        __threadfence_block();
+        if (atomicAdd(&s_done, 1) == kChunk / 32 - 1) {
+            b.chunk_free[(size_t)s * b.nchunks + c] = atomicAdd(&s_cnt[2], 0);
+            const int n0 = atomicAdd(&s_cnt[0], 0), n1 = atomicAdd(&s_cnt[1], 0);
+            if (n0) atomicAdd(b.fcnt + s * 4 + 0, n0);
+            if (n1) atomicAdd(b.fcnt + s * 4 + 1, n1);
+        }
     }
 }
 
