@@ -37,31 +37,44 @@ struct P {
     uint32_t bytes, bytes1;
     uint32_t stage_bytes;
     int depth;
+    int issuers;       // warps that issue (each its own ring of `depth` stages and every issuers-th box of the CTA)
+    int lanes;         // 1: the issuers are lanes 0.. of warp 0 instead of lane 0 of warps 0..
+    int rr;            // > 0: ONE issuing loop run by the whole warp 0, box i issued by lane i % rr
+    int twomaps;       // 1: alternate between two copies of the same tensor map
     const char* base;
 };
 
 __global__ void __launch_bounds__(128) probe(const __grid_constant__ P p, unsigned long long* cyc) {
     extern __shared__ uint8_t raw[];
-    __shared__ __align__(8) uint64_t bar[16];
+    __shared__ __align__(8) uint64_t bar_all[32];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.depth; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
+        for (int i = 0; i < p.depth * p.issuers; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_all[i])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
+    if (p.rr ? threadIdx.x >= 32 : p.lanes ? (int)threadIdx.x >= p.issuers : ((threadIdx.x & 31) != 0 || (int)(threadIdx.x >> 5) >= p.issuers)) return;
+    const int iw = p.rr ? 0 : p.lanes ? threadIdx.x : threadIdx.x >> 5;
+    uint64_t* bar = bar_all + iw * p.depth;
+    smem += (size_t)iw * p.depth * p.stage_bytes;
     const long long t0 = clock64();
     int issued = 0, done = 0;
+    long long c_issue = 0, c_wait = 0;
     int n_mine = 0;
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) ++n_mine;
-    int t_next = blockIdx.x;
+    const int tstep = gridDim.x * p.issuers;
+    for (int t = blockIdx.x + iw * gridDim.x; t < p.tiles; t += tstep) ++n_mine;
+    int t_next = blockIdx.x + iw * gridDim.x;
+    int dshift = 0; while ((1 << dshift) < p.depth) ++dshift;
+    int tx = t_next % p.tw, ty = (t_next / p.tw) % p.th, tn = t_next / (p.tw * p.th);      // 4-D: advanced without divisions
+    const int sx = tstep % p.tw, sy = (tstep / p.tw) % p.th, sn = tstep / (p.tw * p.th);
     while (done < n_mine) {
         while (issued < n_mine && issued - done < p.depth) {
-            const int s = issued % p.depth;
+            const int s = issued & (p.depth - 1);
             uint64_t* b = &bar[s];
             uint8_t* dst = smem + (size_t)s * p.stage_bytes;
+            const int t = t_next; t_next += tstep;
+            if (p.rr && (int)threadIdx.x != (issued & (p.rr - 1))) { ++issued; tx += sx; ty += sy; tn += sn; if (tx >= p.tw) { tx -= p.tw; ++ty; } if (ty >= p.th) { ty -= p.th; ++tn; } continue; }
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(p.bytes + p.bytes1) : "memory");
-            const int t = t_next; t_next += gridDim.x;
             if (p.mode == 2) {
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                              ::"r"(smem_u32(dst)), "l"(&p.m0), "r"(smem_u32(b)), "r"(0), "r"(t * p.TW) : "memory");
@@ -74,20 +87,27 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ P p, unsign
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                              ::"r"(smem_u32(dst)), "l"(&p.m0), "r"(smem_u32(b)), "r"(0), "r"(t * p.TW), "r"(0) : "memory");
             } else if (p.mode == 4) {
-                const int tx = t % p.tw, ty = (t / p.tw) % p.th, n = t / (p.tw * p.th);
+                const int n = tn;
+                const long long ci0 = clock64();
                 asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                             ::"r"(smem_u32(dst)), "l"(&p.m0), "r"(smem_u32(b)), "r"(0), "r"(tx * p.TW - p.hh), "r"(ty * p.TH - p.hh), "r"(n) : "memory");
+                             ::"r"(smem_u32(dst)), "l"((p.twomaps && (issued & 1)) ? &p.m1 : &p.m0), "r"(smem_u32(b)), "r"(0), "r"(tx * p.TW - p.hh), "r"(ty * p.TH - p.hh), "r"(n) : "memory");
+                c_issue += clock64() - ci0;
+                tx += sx; ty += sy; tn += sn;
+                if (tx >= p.tw) { tx -= p.tw; ++ty; }
+                if (ty >= p.th) { ty -= p.th; ++tn; }
             } else {
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(smem_u32(dst)), "l"(p.base + (size_t)t * p.bytes), "r"(p.bytes), "r"(smem_u32(b)) : "memory");
             }
             ++issued;
         }
-        const int s = done % p.depth;
-        while (!try_wait(&bar[s], (uint32_t)(done / p.depth) & 1u)) {}
+        const int s = done & (p.depth - 1);
+        const long long cw0 = clock64();
+        while (!try_wait(&bar[s], (uint32_t)(done >> dshift) & 1u)) {}
+        c_wait += clock64() - cw0;
         ++done;
     }
-    if (blockIdx.x == 0) *cyc = (unsigned long long)(clock64() - t0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cyc[0] = (unsigned long long)(clock64() - t0); cyc[1] = c_issue; cyc[2] = c_wait; }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -106,17 +126,21 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&buf, npix * 80 * 2));
     CK(cudaMemset(buf, 1, npix * 80 * 2));
     unsigned long long* cyc;
-    CK(cudaMalloc(&cyc, 8));
+    CK(cudaMalloc(&cyc, 24));
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     for (const char* v = "abcdefghi"; *v; ++v) {
         for (int ctas = 1; ctas <= 2; ++ctas) {
-            for (int depth = 2; depth <= 8; depth *= 2) {
+            for (int depth = 2; depth <= 8; depth *= 2)
+            for (int iss = 1; iss <= 10; ++iss) {      // 8, 9, 10: round robin over 2 / 4 / 8 lanes of one issuing loop       // 6, 7: 2 / 4 issuing LANES of warp 0       // 1, 2, 4 issuing warps; 5 = one issuer alternating between two copies of the map
+                if (iss == 3) continue;
+                if (iss > 1 && !(*v == 'b' || *v == 'c' || *v == 'e' || (*v == 'a' && iss != 5))) continue;
                 P p;
-                memset(&p, 0, sizeof(p));
-                p.depth = depth; p.bytes1 = 0; p.base = buf;
+                memset(&p, 0, sizeof(p)); p.tw = p.th = 1;
+                p.depth = depth; p.bytes1 = 0; p.base = buf; p.issuers = iss == 5 ? 1 : iss == 6 ? 2 : iss == 7 ? 4 : iss; p.twomaps = iss == 5; p.lanes = iss == 6 || iss == 7; if (iss >= 8) { p.issuers = 1; p.rr = 2 << (iss - 8); }
+                if (p.issuers * depth > 32) continue;
                 int C = 64; CUresult r = CUDA_SUCCESS;
                 if (*v == 'a' || *v == 'd' || *v == 'f') {
                     C = *v == 'd' ? 32 : 64;
@@ -133,6 +157,7 @@ int main(int argc, char** argv) {
                     cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)(16 + 2 * hh), (cuuint32_t)(8 + 2 * hh), 1};
                     r = enc(&p.m0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, buf, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    p.m1 = p.m0;
                     p.mode = 4; p.TW = 16; p.TH = 8; p.hh = hh; p.tw = W / 16; p.th = H / 8; p.tiles = p.tw * p.th * B;
                     p.bytes = (16 + 2 * hh) * (8 + 2 * hh) * C * 2;
                 } else if (*v == 'g') {
@@ -157,7 +182,7 @@ int main(int argc, char** argv) {
                 }
                 if (r != CUDA_SUCCESS) { printf("%c: encode failed %d\n", *v, (int)r); continue; }
                 p.stage_bytes = (p.bytes + p.bytes1 + 1023) & ~1023u;
-                const size_t smem = (size_t)p.stage_bytes * depth + 1024;
+                const size_t smem = (size_t)p.stage_bytes * depth * p.issuers + 1024;
                 if (smem * ctas > 220 * 1024) continue;
                 cudaEvent_t e0, e1;
                 CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -168,11 +193,11 @@ int main(int argc, char** argv) {
                 CK(cudaEventRecord(e1));
                 CK(cudaDeviceSynchronize());
                 float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-                unsigned long long hc; CK(cudaMemcpy(&hc, cyc, 8, cudaMemcpyDeviceToHost));
+                unsigned long long hcs[3]; CK(cudaMemcpy(hcs, cyc, 24, cudaMemcpyDeviceToHost)); const unsigned long long hc = hcs[0];
                 const double total = (double)p.tiles * (p.bytes + p.bytes1);
                 const double rows_per_box = *v == 'g' ? 640 : *v == 'h' ? 256 : (double)(p.bytes) / (C * 2);
-                printf("%c ctas/SM=%d depth=%d  %.3f ms  %.2f TB/s  %.1f B/clk/SM  %.2f clk/row (cta0 %llu clk)\n", *v, ctas, depth, ms, total / ms / 1e9,
-                       total / sms / (double)hc, (double)hc / ((double)p.tiles / sms * rows_per_box), hc);
+                printf("%c ctas/SM=%d issuers=%d%s depth=%d  %.3f ms  %.2f TB/s  %.1f B/clk/SM  %.2f clk/row (cta0 %llu clk, in TMA issue %llu, in wait %llu)\n", *v, ctas, p.issuers, p.twomaps ? "(2 maps)" : p.lanes ? "(lanes)" : p.rr == 2 ? "(rr2)" : p.rr == 4 ? "(rr4)" : p.rr ? "(rr8)" : "", depth, ms, total / ms / 1e9,
+                       total / sms / (double)hc, (double)hc / ((double)p.tiles / sms * rows_per_box), hc, hcs[1], hcs[2]);
             }
         }
     }

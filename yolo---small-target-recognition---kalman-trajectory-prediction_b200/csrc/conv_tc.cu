@@ -113,6 +113,8 @@ struct alignas(64) ConvParams {
     int epi_warps;            // conv_tc_kernel: 8 or 16 epilogue warps (16 only with two MMA warps, one CTA per SM)
     int acc_stages;           // conv_tc_kernel: accumulator stages in tensor memory (2..4): tile t uses stage t % acc_stages
     uint32_t magic_nt, magic_tw, magic_th;   // ceil(2^32 / d) for d = n_tiles, tiles_w, tiles_h (0: d == 1) -- tile index -> coordinates
+    int tma_lanes;            // halo 3: 4 = the producer issues four stage fills per instruction (lanes 0..3), 1 = one by one
+    int halo3_k;              // halo 3: K chunks of all segments together (stage fills per parity view)
     int dbg_skip_mma;         // B2_CONV_DEBUG=1: issue no MMAs (timing of the TMA / epilogue paths alone; results are garbage)
     // ---- chained 1x1 conv (conv_tc_kernel<.., CH = 1>): the activated bf16 tile of this conv never leaves the SM.  Half of the
     //      epilogue warps ("E1") write it into shared memory in the UMMA operand layout, the MMA warps run a second GEMM on it
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
         // p.mma_warps == 2: two stage rings of num_stages / 2 slots; ring r holds the tiles issued by MMA warp r (a ring with
         // two consumers would let one of them run a whole revolution ahead, which mbarrier phase parity cannot tell apart)
         const int ring_stages = MW == 2 ? num_stages >> 1 : num_stages;
+        const int tma_lanes = p.tma_lanes;
         int stage = 0; uint32_t phase = 0;                  // MW == 1: the one ring; MW == 2: the ring of the current tile
         int ostage = ring_stages; uint32_t ophase = 0;      // MW == 2: saved position in the other ring
         int stage_lo = 0, stage_hi = ring_stages;
@@ -491,6 +494,32 @@ __global__ void __launch_bounds__(32 * (1 + MW + EW), MW == 1 ? 2 : 1) conv_tc_k
             const int w0 = (m0 - m1 * tiles_w) * TW;
             const int h0 = (m1 - m2 * tiles_h) * TH;
             const int n0 = m2 * NB;
+            if (halo == 3 && tma_lanes > 1) {
+                // stride 2, four stage fills per instruction: the tile's fills in consumption order (parity view g, then K chunk)
+                // are dealt to lanes 0..3, which wait for their own stage and issue their own box side by side -- the producer warp
+                // ran ~110 instructions per box and was 87 % busy on the 32 -> 64 stride-2 layer (profiles/r02_conv_chain_summary.md);
+                // tools/tma_probe.cu: boxes issued by several lanes of one instruction proceed in parallel
+                const int K = p.halo3_k, n_fill = 4 * K;
+                int r = lane, g = 0;
+                while (r >= K) { r -= K; ++g; }
+                for (int b0 = 0; b0 < n_fill; b0 += 4) {
+                    if (lane < 4) {
+                        int st = stage + lane; uint32_t ph = phase;
+                        if (st >= stage_hi) { st -= ring_stages; ph ^= 1; }
+                        int s = 0, kc = r;
+                        while (s + 1 < nseg && kc >= p.seg[s].kchunks) { kc -= p.seg[s].kchunks; ++s; }
+                        const Seg& sg = p.seg[s];
+                        mbar_wait(&empty_bar[st], ph ^ 1);
+                        mbar_expect_tx(&full_bar[st], sg.a_tx4[g]);
+                        tma_load_4d(smem_a + (size_t)st * a_bytes, &sg.tmA[g], &full_bar[st], sg.src_c + kc * sg.bk, w0 - (g & 1), h0 - (g >> 1), n0);
+                        r += 4;
+                        while (r >= K) { r -= K; ++g; }
+                    }
+                    __syncwarp();
+                    stage += 4;
+                    if (stage >= stage_hi) { stage -= ring_stages; phase ^= 1; }
+                }
+            } else
             for (int g = 0; g < groups; ++g) {
                 int map = 0, cw, chh;
                 if (halo == 3) {                  // stride 2: g = input parity (row parity * 2 + column parity); odd views start one earlier
@@ -1632,7 +1661,10 @@ int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B,
     else if (s1r >= 3 || (p.halo == 2 && s1r >= 2)) { ctas = 1; stages = s1r; p.b_resident = 1; }
     else if (s2s >= 4) { ctas = 2; stages = s2s; }
     else { ctas = 1; stages = s1s; }
-    if (stages > want + 2 && stages > 4) stages = want + 2 > 4 ? want + 2 : 4;
+    int tmal = 4;                                       // B2_CONV_TMAL=1: stride-2 boxes issued one by one (experiments)
+    if (const char* tv = getenv("B2_CONV_TMAL")) tmal = atoi(tv);
+    const bool lanes3 = p.halo == 3 && tmal > 1;        // four fills per instruction want rings of >= 4 stages: keep every stage that fits
+    if (!lanes3 && stages > want + 2 && stages > 4) stages = want + 2 > 4 ? want + 2 : 4;
     if (stages > kMaxStages) stages = kMaxStages;
     B2_REQUIRE(stages >= 2, "conv: tile does not fit in shared memory (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
     // two MMA-issuing warps when each can have a ring of >= 2 stages (B2_CONV_MMAW=1 forces one)
@@ -1644,6 +1676,9 @@ int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B,
     p.mma_warps = (mmaw >= 2 && (stages >= 4 || (p.halo == 2 && stages == 2)) && p.halo >= 2 && ctas == 1) ? 2 : 1;
     if (p.mma_warps == 2) stages &= ~1;
     p.num_stages = stages;
+    p.halo3_k = 0;
+    for (int si = 0; si < p.nseg; ++si) p.halo3_k += p.seg[si].kchunks;
+    p.tma_lanes = (lanes3 && p.b_resident && (p.mma_warps == 2 ? stages / 2 : stages) >= 4) ? 4 : 1;
     p.epi_warps = 8;
     if (p.mma_warps == 2) {
         // measured (tools/conv_bench.py --ab B2_CONV_EPIW=8,16): 16 warps pay when a quadrant has more than four 16-column
