@@ -13,6 +13,7 @@ Files written:
   nms_cases.npz                               non_max_suppression, both branches (TorchNMS.nms / torchvision)
   net_n_p2_small.npz                          yolov8n-p2 head maps + decoded tensor on a 64x96 input
   bytetrack.npz                               BYTETracker.update over a scripted 90-frame scene (two parameterisations) + linear_assignment cases
+  overlay.npz                                 TrajectoryVisualizer.draw_tracks over a scripted 14-frame scene (annotated frames)
   predict_n_p2.npz / predict_s_p2.npz         YOLO(cfg).predict on 512x640 (and 500x640) frames + the NMS candidate lists
 """
 import contextlib
@@ -444,6 +445,24 @@ def gold_bytetrack():
             rows.append(r); counts.append(len(r))
         out[f"{tag}_rows"] = np.concatenate(rows); out[f"{tag}_counts"] = np.array(counts)
     np.savez_compressed(os.path.join(HERE, "bytetrack.npz"), **out)
+
+
+def gold_overlay():
+    """kalman/trajectory_visualizer.py TrajectoryVisualizer.draw_tracks over the scripted scene: the pixels of every frame."""
+    from golden_common import overlay_scene
+    spec = importlib.util.spec_from_file_location("ref_trajectory_visualizer", os.path.join(REF, "kalman", "trajectory_visualizer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    vis = mod.TrajectoryVisualizer()
+    out = []
+    for image, tracks, dets, info in overlay_scene():
+        keep = image.copy()
+        out.append(vis.draw_tracks(image, tracks, dets, info))
+        assert np.array_equal(image, keep)
+    import hashlib
+    digests = np.array([hashlib.sha256(np.ascontiguousarray(o).tobytes()).hexdigest() for o in out])
+    full = [0, 5, 8]                # whole frames for three of them (a failing digest can then be looked at), digests for all
+    np.savez_compressed(os.path.join(HERE, "overlay.npz"), digests=digests, full_index=np.array(full), full=np.stack([out[i] for i in full]))
 
 
 if __name__ == "__main__":

@@ -245,3 +245,27 @@ def motion_frames_scene(n_frames=60, seed=13, hw=(256, 320)):
         d[:, [1, 3]] -= off[1]
         out.append([[float(v) for v in r[:5]] for r in d])
     return frames, out
+
+
+def overlay_scene(n_frames=14, h=240, w=320):
+    """Scripted input of the track-overlay test (tests/golden/overlay.npz): per frame (image, tracks, detections, frame_info) with a
+    tracked target, a coasting one that blinks, one at the right / bottom edges (captions flip), long trails and fast targets."""
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 255 // w), (yy * 255 // h), ((xx + yy) * 255 // (w + h))], axis=-1).astype(np.uint8)
+    frames = []
+    for f in range(n_frames):
+        trail_a = [(40 + 3 * k, 60 + 2 * k) for k in range(f + 1)]
+        trail_b = [(200 - 2 * k, 120 + k) for k in range(30)][: 2 * f + 3]
+        tracks = [
+            {"track_id": 1, "bbox": [30.4 + 3 * f, 50.9 + 2 * f, 52.2 + 3 * f, 68.1 + 2 * f], "status": "detected", "time_since_update": 0,
+             "confidence": 0.91 - 0.01 * f, "trajectory": trail_a, "velocity": (3.0, 2.0)},
+            {"track_id": 7, "bbox": [190.0 - 2 * f, 110.0 + f, 214.5 - 2 * f, 131.5 + f], "status": "predicted", "time_since_update": f + 1,
+             "confidence": 0.6 * 0.95 ** f, "trajectory": trail_b, "velocity": (-2.0, 1.0)},
+            {"track_id": "12", "bbox": np.array([w - 40.0, h - 18.0, w - 8.0, h - 2.0], dtype=np.float32), "status": "detected",
+             "confidence": 1.0, "trajectory": [(w - 24, h - 10)], "velocity": (0.3, -0.4)},
+            {"track_id": 20, "bbox": (5, 200, 25, 236), "status": "predicted", "time_since_update": 3},
+        ]
+        dets = [[31.0 + 3 * f, 51.0 + 2 * f, 52.0 + 3 * f, 68.0 + 2 * f, 0.88], [100.0, 20.0, 112.0, 29.0, 0.42, 0.0], [1, 2, 3, 4]] if f % 3 else []
+        info = None if f == 2 else ({"frame_number": f, "state_changes": f // 4} if f % 2 else {"frame_number": f})
+        frames.append((base.copy(), tracks, dets, info))
+    return frames

@@ -443,3 +443,33 @@ def test_stream_loader_delivers_one_frame_per_source(tmp_path, monkeypatch):
 
         ref = [[im.copy() for im in imgs] for _, imgs, _ in Ref(str(listing), buffer=True)]
         assert len(ref) == len(got) and all(np.array_equal(a, b) for x, y in zip(got, ref) for a, b in zip(x, y))
+
+
+def test_trajectory_visualizer_matches_reference_pixels():
+    """visualizer.TrajectoryVisualizer.draw_tracks against frames drawn by the reference class (kalman/trajectory_visualizer.py)
+    on the scripted scene of golden_common.overlay_scene: every pixel of every frame (byte work: exact)."""
+    import hashlib
+    from golden_common import overlay_scene
+    from b200dt.visualizer import Prim, TrajectoryVisualizer
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "overlay.npz"))
+    vis = TrajectoryVisualizer()
+    assert (vis.trajectory_length, vis.velocity_scale, vis.font_scale, vis.font_thickness, vis.frame_counter) == (20, 5.0, 0.4, 1, 0)
+    full = {int(i): f for i, f in zip(gold["full_index"], gold["full"])}
+    for k, (image, tracks, dets, info) in enumerate(overlay_scene()):
+        keep = image.copy()
+        got = vis.draw_tracks(image, tracks, dets, info)
+        assert np.array_equal(image, keep), "the input frame must not be drawn on"
+        if k in full:
+            assert np.array_equal(got, full[k]), f"frame {k}: {int((got != full[k]).any(-1).sum())} pixels differ"
+        assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == str(gold["digests"][k]), f"frame {k}"
+    assert vis.frame_counter == len(gold["digests"])
+    # the display list is plain data: an empty frame still carries the legend, and a list can be replayed on another image
+    prims = vis.compile_frame((240, 320, 3), [], None, None)
+    assert all(isinstance(p, Prim) for p in prims) and [p.kind for p in prims][:3] == ["box", "box", "text"]
+    a = TrajectoryVisualizer.rasterize(np.zeros((240, 320, 3), np.uint8), prims)
+    b = TrajectoryVisualizer().draw_tracks(np.zeros((240, 320, 3), np.uint8), [])
+    assert np.array_equal(a, b)
+    # detections given as an array (the reference only takes lists: `if detections:`), custom palette
+    arr = np.array([[10, 10, 30, 30, 0.5]], dtype=np.float32)
+    c = TrajectoryVisualizer(colors={**vis.colors, "detected": (1, 2, 3)}).draw_tracks(np.zeros((240, 320, 3), np.uint8), [], arr, {"frame_number": 1})
+    assert (c == np.array([1, 2, 3], np.uint8)).all(-1).any()
