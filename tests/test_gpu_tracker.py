@@ -288,6 +288,40 @@ def test_pair_list_overflow_with_exact_ties_matches_oracle():
     bank.close()
 
 
+def test_detection_grid_edge_cases_match_oracle():
+    """The sweep's detection grid (<= 128 detections: tracks test only the detections of the grid cells they touch) at its edges:
+    128 detections (both bit words), 129 (the loop over all detections), one detection, 65 fanned out over one track, a far outlier next to a detection that covers every track, degenerate rows, none."""
+    import torch
+
+    from b200dt.tracker import TrackerBank
+
+    C_, D = 512, 160
+    params = (150, 1, 0.02)
+    g = np.random.default_rng(5)
+    grid = _grid_boxes(12, 31.0, 17.0)                        # 144 boxes, 14 px gaps
+    jig = lambda n: np.concatenate([g.uniform(-4.0, 4.0, (n, 2)).astype(np.float32)] * 2, 1)
+    f1 = grid[:129].copy(); f1[:, :4] += jig(129)
+    f3 = np.repeat(grid[70:71], 65, 0)                        # 65 detections fanned out over one track: a few cells hold them all
+    f3[:, :4] += np.outer(np.arange(65, dtype=np.float32), np.array([0.37, 0.11, 0.37, 0.11], np.float32))
+    f4 = np.array([[1.0e6, 1.0e6, 1.0e6 + 9, 1.0e6 + 9, 0.7], [-50.0, -50.0, 420.0, 420.0, 0.6]], np.float32)
+    f5 = grid[100:140].copy(); f5[:, :4] += jig(40)
+    f5[3, [0, 2]] = f5[3, [2, 0]]                             # x1 > x2: overlaps nothing, founds a track of negative width
+    f5[7, :4] = f5[7, [0, 1, 0, 1]]                           # empty box
+    frames = [grid[:128], f1, grid[60:61] + np.float32(2.0), f3, f4, f5,
+              np.zeros((0, 5), np.float32), grid[:128]]
+    o = otr.MultiTracker(*params)
+    bank = TrackerBank(1, C_, D, *params)
+    for f, d in enumerate(frames):
+        dets = torch.full((1, D, 5), 7.0e5, dtype=torch.float32)          # rows past the count hold junk, not zeros
+        dets[0, :len(d)] = torch.from_numpy(np.ascontiguousarray(d))
+        bank.update(dets.cuda(), torch.tensor([len(d)], dtype=torch.int32).cuda(), with_trajectory=False)
+        ref = o.update([r for r in d])
+        _assert_same_tracks(_bank_rows_as_dicts(bank, 0), ref, f)
+    _assert_fixture_is_decidable(o, "detection grid fixture")
+    assert int(bank.export(0)[3][7]) == 0
+    bank.close()
+
+
 def test_bank_grows_like_the_unbounded_reference_list():
     """The reference appends tracks without bound; a 16-slot bank that doubles on demand gives, frame by frame, the bits of a
     bank that was large from the start."""
