@@ -209,7 +209,8 @@ int b2_tracker_grow(b2_tracker_t* t, int new_capacity, void* stream);
  * a pipeline downloads it with its rows instead of synchronising on b2_tracker_export. */
 int b2_tracker_stats(b2_tracker_t* t, long long* stats_dev_out, void* stream);
 /* One frame for every stream.  dets: [n_streams][max_dets][det_cols] fp32 rows starting with
- * x1,y1,x2,y2 (det_cols >= 4, e.g. 6 for NMS output rows); det_counts: [n_streams] int32.
+ * x1,y1,x2,y2 (det_cols >= 4, e.g. 6 for NMS output rows); det_counts: [n_streams] int32.  All max_dets rows of a stream must be
+ * allocated: rows past the count are requested before the count is known and ignored (their contents do not matter).
  * out_rows: [n_streams][out_cap][B2_TRACK_COLS]; out_counts: [n_streams] int32 = tracks reported (rows beyond out_cap are
  * counted but not written: out_counts[s] > out_cap tells the caller its buffer was too small);
  * out_traj (may be NULL): [n_streams][out_cap][B2_TRAJ_LEN][2] fp32 last centres, oldest first,
