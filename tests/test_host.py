@@ -341,6 +341,25 @@ torch.save({k: v for k, v in m.state_dict().items()}, sys.argv[3])
             mine.save_txt(a, save_conf=save_conf); ref.save_txt(b, save_conf=save_conf)
             assert a.read_text() == b.read_text() and a.read_text().count("\n") == 2
         assert mine.plot().shape == img.shape and mine.plot().any()
+    # plot(): the reference Annotator's pixels (OpenCV path) -- boxes at the top / right edges, every palette colour class,
+    # tracked and untracked rows, the switches
+    g = np.random.default_rng(3)
+    frame = g.integers(0, 255, (240, 320, 3), dtype=np.uint8)
+    many = {c: f"class{c}" for c in range(24)}
+    xy = np.array([[4.2, 3.9, 60.0, 40.0], [250.5, 100.0, 318.0, 160.7], [100.0, 120.0, 101.0, 121.0], [-5.0, 200.0, 40.0, 260.0]], np.float32)
+    for tracked in (False, True):
+        rows = []
+        for c in range(24):
+            b = xy[c % 4] + np.float32(3 * (c // 4))
+            rows.append(np.concatenate([b, [100.0 + c] if tracked else [], [0.05 + 0.04 * c, float(c)]]))
+        data = np.array(rows, np.float32)
+        mine, ref = Results(frame, "a.jpg", many, data.copy()), URes(frame, "a.jpg", many, boxes=torch.as_tensor(data))
+        for kw in ({}, {"conf": False}, {"labels": False}, {"line_width": 1}, {"line_width": 5}, {"color_mode": "instance"}, {"boxes": False}):
+            a, b = mine.plot(**kw), ref.plot(**kw)
+            assert a.dtype == np.uint8 and np.array_equal(a, b), (tracked, kw, int((a != b).any(-1).sum()))
+        assert np.array_equal(mine.orig_img, frame)
+        big = np.zeros((720, 1280, 3), np.uint8)                      # image-scaled line width 3, font scale 1
+        assert np.array_equal(mine.plot(img=big), ref.plot(img=big))
     assert Results(img, "a.jpg", names, np.zeros((0, 6), np.float32)).summary() == []
 
 

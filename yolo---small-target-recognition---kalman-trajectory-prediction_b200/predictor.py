@@ -24,6 +24,17 @@ from .engine import Engine
 # ---------------------------------------------------------------------------------------------------
 # Results containers (engine/results.py)
 # ---------------------------------------------------------------------------------------------------
+
+# Annotator colours (utils/plotting.py:95-120 hex palette, as BGR tuples) and the plate colours that get dark / white ink (:255-278)
+_PALETTE_BGR = tuple((int(h[4:6], 16), int(h[2:4], 16), int(h[0:2], 16)) for h in (
+    "042AFF 0BDBEB F3F3F3 00DFB7 111F68 FF6FDD FF444F CCED00 00F344 BD00FF 00B4FF DD00BA 00FFFF 26C000 01FFB3 7D24FF 7B0068 FF1B6C "
+    "FC6D2F A2FF0B").split())
+_DARK_INK_ON = frozenset({(235, 219, 11), (243, 243, 243), (183, 223, 0), (221, 111, 255), (0, 237, 204), (68, 243, 0), (255, 255, 0),
+                          (179, 255, 1), (11, 255, 162)})
+_WHITE_INK_ON = frozenset({(255, 42, 4), (79, 68, 255), (255, 0, 189), (255, 180, 0), (186, 0, 221), (0, 192, 38), (255, 36, 125),
+                           (104, 0, 123), (108, 27, 255), (47, 109, 252), (104, 31, 17)})
+
+
 class Boxes:
     """Detection boxes: ``data`` is (n, 6) [x1, y1, x2, y2, conf, cls] or (n, 7) with a track id in column 4."""
 
@@ -182,24 +193,42 @@ class Results:
                 f.writelines(t + "\n" for t in texts)
         return str(txt_file)
 
-    def plot(self, conf=True, labels=True, line_width=None, img=None, **_):
-        """results.py:475-613 restricted to boxes: a BGR copy of the frame with one rectangle (+ label) per detection.  Needs cv2
-        (host-side drawing, not part of the hot path; colours / fonts are not the reference Annotator's)."""
+    def plot(self, conf=True, labels=True, line_width=None, img=None, boxes=True, color_mode="class", txt_color=(255, 255, 255), **_):
+        """results.py:475-613 restricted to boxes, drawn the way the reference's Annotator draws them with OpenCV
+        (utils/plotting.py:170-364, the path taken for ASCII class names): same pixels as `Results.plot()` of the reference for
+        the same boxes -- palette colour by class (or by track id / row with color_mode="instance"), anti-aliased rectangle of
+        the image-scaled line width, label plate above the box (inside it at the top edge, pulled left at the right edge), ink
+        chosen against the plate colour, rows painted last-to-first.  Host-side drawing, not part of the hot path.  Non-ASCII
+        names make the reference switch to PIL and a TrueType font; here they are drawn with the same OpenCV calls."""
         import cv2
 
-        im = (self.orig_img if img is None else img).copy()
-        lw = line_width or max(round(sum(im.shape[:2]) / 2 * 0.003), 2)
-        if self.boxes is None:
+        assert color_mode in {"instance", "class"}, f"Expected color_mode='instance' or 'class', not {color_mode}."
+        im = np.ascontiguousarray((self.orig_img if img is None else img).copy())
+        if self.boxes is None or not boxes:
             return im
+        lw = line_width or max(round(sum(im.shape) / 2 * 0.003), 2)
+        thick, scale = max(lw - 1, 1), lw / 3
         d = self.boxes.numpy()
-        for row in d.data:
+        rows = d.data
+        for i in range(len(rows)):
+            row = rows[len(rows) - 1 - i]                              # reversed(pred_boxes), i counts from the end (:568)
             c = int(row[-1])
-            col = tuple(int(v) for v in ((37 * c + 90) % 256, (17 * c + 200) % 256, (29 * c + 40) % 256))
-            p1, p2 = (int(row[0]), int(row[1])), (int(row[2]), int(row[3]))
-            cv2.rectangle(im, p1, p2, col, thickness=lw, lineType=cv2.LINE_AA)
+            tid = int(row[4]) if d.is_track else None
+            key = c if color_mode == "class" else (tid if tid is not None else i)
+            plate = _PALETTE_BGR[int(key) % len(_PALETTE_BGR)]
+            ink = (104, 31, 17) if plate in _DARK_INK_ON else ((255, 255, 255) if plate in _WHITE_INK_ON else tuple(txt_color))
+            p1 = (int(row[0]), int(row[1]))
+            cv2.rectangle(im, p1, (int(row[2]), int(row[3])), plate, thickness=lw, lineType=cv2.LINE_AA)
             if labels:
-                name = ("" if not d.is_track else f"id:{int(row[4])} ") + str(self.names[c])
-                cv2.putText(im, f"{name} {float(row[-2]):.2f}" if conf else name, (p1[0], max(p1[1] - 2, 0)), 0, lw / 3, col, thickness=max(lw - 1, 1), lineType=cv2.LINE_AA)
+                name = ("" if tid is None else f"id:{tid} ") + str(self.names[c])
+                text = f"{name} {float(row[-2]):.2f}" if conf else name
+                w, h = cv2.getTextSize(text, 0, fontScale=scale, thickness=thick)[0]
+                h += 3
+                above = p1[1] >= h                                      # room for the plate above the box?
+                if p1[0] > im.shape[1] - w:
+                    p1 = (im.shape[1] - w, p1[1])
+                cv2.rectangle(im, p1, (p1[0] + w, p1[1] - h if above else p1[1] + h), plate, -1, cv2.LINE_AA)
+                cv2.putText(im, text, (p1[0], p1[1] - 2 if above else p1[1] + h - 1), 0, scale, ink, thickness=thick, lineType=cv2.LINE_AA)
         return im
 
     def verbose(self):
