@@ -24,4 +24,13 @@ if len(a)==len(b):
     for i,((d,x),(_,y)) in enumerate(zip(a,b)):
         flag="  <<<" if y<0.95*x else ("  >>>" if y>1.05*x else "")
         print(f"{i:3d} {x*1e3:7.1f} {y*1e3:7.1f}  {d}{flag}")
+else:      # the plans differ in length (a switch that changes the chained launches): list both, matched by description where unique
+    from collections import Counter
+    ca,cb=Counter(d for d,_ in a),Counter(d for d,_ in b)
+    tb={d:y for d,y in b if cb[d]==1}
+    for i,(d,x) in enumerate(a):
+        y=tb.get(d) if ca[d]==1 else None
+        print(f"{i:3d} {x*1e3:7.1f} "+(f"{y*1e3:7.1f}" if y is not None else "      -")+f"  {d}")
+    for i,(d,y) in enumerate(b):
+        if not (ca[d]==1 and cb[d]==1): print(f"  b{i:3d}         {y*1e3:7.1f}  {d}")
 print("total",sum(x for _,x in a),sum(y for _,y in b), len(a), len(b))
