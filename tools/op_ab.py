@@ -4,8 +4,8 @@ import sys,os,json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np, b200dt
 from b200dt import cfg, engine, synth, weights
-S,H,W=256,512,640
-spec=cfg.resolve("yolov8s-p2"); sd=weights.synthetic_state_dict(spec,seed=0)
+S,H,W=[int(v) for v in os.environ.get("OP_AB_SHAPE","256,512,640").split(",")]      # OP_AB_MODEL / OP_AB_SHAPE: another plan (e.g. yolov8x-p2, 32,1280,1280)
+spec=cfg.resolve(os.environ.get("OP_AB_MODEL","yolov8s-p2")); sd=weights.synthetic_state_dict(spec,seed=0)
 fr=[synth.IRStream(seed=1000+s,h=H,w=W).frame() for s in range(8)]
 frames=torch.from_numpy(np.stack([fr[s%8] for s in range(S)])).cuda()
 var,vals=sys.argv[1].split("=")
