@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(kChunk, B2_SWEEP_BLOCKS) sweep_kernel(const Ba
     __shared__ __align__(16) unsigned long long s_cell[kGrid * kGrid * 2];   // detection grid: bit d of cell (cy, cx) = detection d touches it
     __shared__ float s_grid[4];                                    // grid origin (x, y) and cells per unit length (x, y)
     const int tid = threadIdx.x;
+    pdl_launch_dependents();            // resolve_kernel's blocks may be placed as soon as every block of this grid has started and SMs free up
     const int s = (int)(blockIdx.x / (unsigned)b.nchunks), c = (int)(blockIdx.x % (unsigned)b.nchunks);
     unsigned long long* agg = b.agg + (size_t)s * b.nchunks;
     const int chunk_slots = min(kChunk, b.C - c * kChunk);
@@ -843,17 +844,20 @@ __global__ void __launch_bounds__(kResolveThreads, 2) resolve_kernel(const Bank 
     const int D = min(fr.det_counts[s], b.max_dets);
     if (tid == 0) { s_tot = 0ull; s_an = 0; }
     if (tid < 4) s_cnt[tid] = 0;
+    // the detections are inputs of the whole update (written before the sweep was launched): they are copied while the sweep's last
+    // blocks still run.  Everything the sweep writes -- aggregates, lists, the bank, its counters -- is read after pdl_wait()
+    for (int d = tid; d < D; d += kResolveThreads) {
+        const float* r = fr.dets + ((size_t)s * b.max_dets + d) * fr.det_cols;
+        s_det[d] = make_float4(r[0], r[1], r[2], r[3]);
+        s_dmatch[d] = -1;
+    }
     __syncthreads();
+    pdl_wait();
     {   // totals of the sweep; the aggregates are consumed (zero = not yet published, for the next frame)
         unsigned long long* agg = b.agg + (size_t)s * b.nchunks;
         unsigned long long sum = 0ull;
         for (int i = tid; i < b.nchunks; i += kResolveThreads) { sum += agg[i] & ~kAggValid; agg[i] = 0ull; }
         if (sum) atomicAdd(&s_tot, sum);
-    }
-    for (int d = tid; d < D; d += kResolveThreads) {
-        const float* r = fr.dets + ((size_t)s * b.max_dets + d) * fr.det_cols;
-        s_det[d] = make_float4(r[0], r[1], r[2], r[3]);
-        s_dmatch[d] = -1;
     }
     __syncthreads();
     const int E1 = (int)(s_tot & 0xFFFFu), T = (int)((s_tot >> 16) & 0xFFFFu);
@@ -1324,12 +1328,22 @@ extern "C" int b2_tracker_update_ex(b2_tracker_t* t, const float* dets, int det_
     const Bank& b = t->impl.b;
     cudaStream_t st = (cudaStream_t)stream;
     const Frame fr{dets, det_cols, det_counts, out_rows, out_counts, out_traj, out_traj_len, out_cap, out_extra};
+    // resolve is launched as a programmatic dependent of the sweep: its blocks are placed while the sweep's last blocks run and wait
+    // (griddepcontrol.wait) for the sweep's completion before they read anything it wrote -- the launch latency and the copy of the
+    // detections come off the frame's critical path (B2_TRK_PDL=0: plain stream order)
+    static const bool pdl = [] { const char* v = getenv("B2_TRK_PDL"); return !(v && atoi(v) == 0); }();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)b.S); cfg.blockDim = dim3((unsigned)kResolveThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     if (b.mode) {
         sweep_kernel<1><<<b.S * b.nchunks, kChunk, (size_t)b.max_dets * sizeof(float4), st>>>(b, fr);
-        resolve_kernel<1><<<b.S, kResolveThreads, 0, st>>>(b, fr);
+        B2_CUDA(cudaLaunchKernelEx(&cfg, resolve_kernel<1>, b, fr));
     } else {
         sweep_kernel<0><<<b.S * b.nchunks, kChunk, (size_t)b.max_dets * sizeof(float4), st>>>(b, fr);
-        resolve_kernel<0><<<b.S, kResolveThreads, 0, st>>>(b, fr);
+        B2_CUDA(cudaLaunchKernelEx(&cfg, resolve_kernel<0>, b, fr));
     }
     B2_CUDA(cudaGetLastError());
     b2_count_launch(2);
