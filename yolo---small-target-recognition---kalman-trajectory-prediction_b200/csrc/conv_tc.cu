@@ -1733,10 +1733,14 @@ int b2_conv_prepare_chain(void* storage, const B2ConvSrc* srcs, int nsrc, int B,
 
     if (plan_only) return B2_OK;
     // ---- tensor maps ---------------------------------------------------------------------------------
-    CUtensorMapL2promotion a_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    // L2 promotion of the activation boxes: 64 bytes.  Measured (ncu, 256 streams): with 128 B (or none) a conv that reads a 32-channel
+    // slice of a 64-channel buffer (Bottleneck.cv1 inside the P2 C2f blocks) pulls the unused half of every 128-byte line from DRAM
+    // (672 MB for a 336 MB input) and the single-box 64-channel layers re-fetch a third of their halo rows (64->64 + DFL at P2: 1175 MB
+    // against 839 MB); the launches themselves take the same time, the power-capped step is 0.6 % shorter (tools/sustained.py)
+    CUtensorMapL2promotion a_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
     if (const char* pv = getenv("B2_CONV_L2PROMO")) {      // experiments only: 0 none, 1 64 B, 2 128 B, 3 256 B
         const int v = atoi(pv);
-        a_promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : a_promo;
+        a_promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : a_promo;
     }
     const int nmaps = stride == 1 ? 1 : 4;
     for (int si = 0; si < p.nseg; ++si) {
